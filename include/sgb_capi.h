@@ -1,0 +1,191 @@
+/*
+ * sgb_capi.h -- C ABI of the B200-native pose-graph optimisation backend for sparse-gslam.
+ *
+ * This is the drop-in boundary of SURVEY.md section 8b: what a g2o plugin
+ * (OptimizationAlgorithm / BlockSolver / LinearSolver) that replaces the three
+ * nested objects built in the reference's
+ *     src/sparse_gslam/src/graphs.cpp:9-15  setup_lm_opt   (LM,  BlockSolver<-1,2>, LinearSolverEigen)
+ *     src/sparse_gslam/src/graphs.cpp:17-23 setup_pose_opt (GN,  BlockSolver<3,3>,  LinearSolverEigen)
+ * binds to. Plain pointers and sizes only; no C++/torch types; no exceptions cross it.
+ * The g2o-facing C++ shim that calls these entry points is
+ * sparse-gslam_b200/adapter/sgb_g2o_adapter.h; INTEGRATION.md shows the two lines of
+ * graphs.cpp that change.
+ *
+ * Every function returns an sgb_status (0 = OK) unless stated otherwise;
+ * sgb_last_error() gives the message of the last failure on that handle.
+ * A handle is NOT re-entrant, but distinct handles may be used concurrently from
+ * different threads (reference: the landmark graph and the pose graph are optimised from
+ * two threads in realtime mode, log_runner.cpp:217-224); each handle owns its CUDA
+ * stream and never touches the default stream.
+ * There is no CPU fallback: every compute entry point fails with SGB_ERR_NO_DEVICE
+ * when no CUDA device is usable.
+ */
+#ifndef SGB_CAPI_H
+#define SGB_CAPI_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum sgb_status {
+  SGB_OK = 0,
+  SGB_ERR_INVALID = 1,      /* bad argument / malformed graph */
+  SGB_ERR_NO_DEVICE = 2,    /* no usable CUDA device (there is no CPU path) */
+  SGB_ERR_CUDA = 3,         /* CUDA runtime error, see sgb_last_error */
+  SGB_ERR_NOT_INITIALIZED = 4, /* g2o: "0 vertices to optimize, maybe forgot to call initializeOptimization()" */
+  SGB_ERR_UNSUPPORTED = 5,
+  SGB_ERR_SOLVE_FAILED = 6, /* g2o SolverResult::Fail (non-SPD system / PCG breakdown) */
+  SGB_ERR_COMM = 7          /* multi-GPU exchange failure */
+} sgb_status;
+
+/* g2o::OptimizationAlgorithm::SolverResult */
+enum { SGB_RESULT_TERMINATE = 2, SGB_RESULT_OK = 1, SGB_RESULT_FAIL = -1 };
+/* which g2o algorithm object is being replaced (graphs.cpp:12 vs graphs.cpp:20) */
+enum { SGB_ALGO_LM = 0, SGB_ALGO_GN = 1 };
+/* Jacobian of EdgeSE2RhoTheta: the reference inherits g2o's central differences
+ * (include/g2o_bindings/edge_se2_rhotheta.h:8-17 has no linearizeOplus); analytic = SURVEY Appendix B */
+enum { SGB_JAC_G2O_NUMERIC = 0, SGB_JAC_ANALYTIC = 1 };
+
+typedef struct sgb_options {
+  int32_t device;           /* CUDA device ordinal; -1 = current */
+  int32_t jacobian_mode;    /* SGB_JAC_* (default SGB_JAC_G2O_NUMERIC = reference behaviour) */
+  double pcg_tolerance;     /* stop when sqrt(r.z) <= tol * sqrt(r0.z0); <=0 -> 1e-10 */
+  int32_t pcg_max_iters;    /* <=0 -> 4 * (3 * free poses) */
+  int32_t verbose;          /* g2o setVerbose; the reference keeps it off (graphs.cpp:13,21) */
+  double lm_tau;            /* lambda0 = tau * max|diag H|; <=0 -> 1e-5 (g2o default) */
+  double lm_user_lambda;    /* >0 overrides lambda0 (g2o userLambdaInit) */
+  int32_t lm_max_trials;    /* <=0 -> 10 (g2o maxTrialsAfterFailure) */
+  int32_t reserved;
+} sgb_options;
+
+/* Host SoA graph. Edges reference vertices by ARRAY INDEX; ids only define g2o's vertex
+ * order (active vertices sorted by id; the reference numbers poses 0,1,2.. drone.cpp:64,121 and
+ * landmarks from 10 000 000, include/drone.h:22). All pose ids must be smaller than all
+ * landmark ids. The caller owns every pointer and may free them when the call returns
+ * (reference ownership convention: graphs.h:22-24, README.md:22-23). */
+typedef struct sgb_graph_soa {
+  int32_t n_poses;
+  const int32_t* pose_id;    /* NULL: id = index */
+  const double* pose_est;    /* [3*n_poses] x, y, theta (VertexSE2::estimate) */
+  const uint8_t* pose_fixed; /* NULL: none */
+  int32_t n_landmarks;
+  const int32_t* lm_id;      /* NULL: id = 10000000 + index */
+  const double* lm_est;      /* [2*n_landmarks] rho, theta (VertexRhoTheta::estimate) */
+  const uint8_t* lm_fixed;   /* NULL: none */
+  int32_t n_pp;              /* g2o::EdgeSE2 */
+  const int32_t* pp_i;       /* vertex 0 (from) */
+  const int32_t* pp_j;       /* vertex 1 (to) */
+  const double* pp_z;        /* [3*n_pp] measurement dx, dy, dtheta */
+  const double* pp_info;     /* [6*n_pp] information, upper triangle 11,12,13,22,23,33 */
+  const double* pp_phi;      /* RobustKernelDCS delta per edge; <=0 or NULL = no robust kernel */
+  const int64_t* pp_seq;     /* insertion rank (g2o internalId); NULL = array order */
+  int32_t n_pl;              /* g2o::EdgeSE2RhoTheta */
+  const int32_t* pl_pose;    /* vertex 0 */
+  const int32_t* pl_lm;      /* vertex 1 */
+  const double* pl_z;        /* [2*n_pl] rho, theta */
+  const double* pl_info;     /* [3*n_pl] 11,12,22 */
+  const int64_t* pl_seq;     /* NULL = after all pose-pose edges, array order */
+} sgb_graph_soa;
+
+typedef struct sgb_iter_stat {
+  int32_t iteration;
+  int32_t trials;           /* g2o levenbergIterations (1 for GN) */
+  int32_t result;           /* SGB_RESULT_* */
+  int32_t pcg_iters;        /* PCG iterations summed over the trials of this iteration */
+  double chi2;              /* currentChi after the iteration (robustified) */
+  double lambda;            /* LM lambda after the iteration */
+  double rho;               /* last gain ratio */
+  double chi2_before;       /* activeRobustChi2 at iteration start */
+  double pcg_residual;      /* last relative preconditioned residual sqrt(r.z / r0.z0) */
+} sgb_iter_stat;
+
+/* sizes of the Hessian block structure after BlockSolver::buildStructure (no Schur;
+ * the reference never marginalises) */
+typedef struct sgb_structure_info {
+  int32_t n_free;           /* vertices with a Hessian index */
+  int32_t n_free_poses;
+  int32_t n_free_landmarks;
+  int32_t n_blocks;         /* stored upper-triangular blocks */
+  int32_t scalar_dim;       /* 3*free poses + 2*free landmarks */
+  int32_t n_active_pp;
+  int32_t n_active_pl;
+  int32_t reserved;
+  int64_t block_values;     /* doubles in the concatenated block value array */
+} sgb_structure_info;
+
+/* per-phase device time of the last sgb_optimize / sgb_step (CUDA events on the handle's stream), ms */
+typedef struct sgb_timings {
+  double linearize_ms;      /* linearise + assemble (per-edge Jacobians, H, b, chi2) */
+  double setup_ms;          /* damping, 2x2 landmark inverses, Schur diagonal + reduced rhs */
+  double pcg_ms;            /* reduced-system PCG */
+  double update_ms;         /* back-substitution, oplus, chi2 of the trial, LM control */
+  double total_ms;
+  int64_t pcg_iters;        /* total PCG iterations */
+  int64_t trials;           /* total LM trials (GN: iterations) */
+  int64_t linearizations;
+  int64_t kernel_launches;  /* kernels launched by this library */
+} sgb_timings;
+
+typedef struct sgb_handle sgb_handle;
+
+const char* sgb_version(void);
+/* number of usable CUDA devices (0 = none); never fails */
+int32_t sgb_device_count(void);
+void sgb_default_options(sgb_options* opt);
+
+sgb_status sgb_create(const sgb_options* opt /* NULL = defaults */, sgb_handle** out);
+void sgb_destroy(sgb_handle* h);
+const char* sgb_last_error(const sgb_handle* h);
+
+/* addVertex/addEdge of the whole graph + SparseOptimizer::initializeOptimization():
+ * builds g2o's index mapping (active vertices sorted by id, fixed -> -1) and block
+ * structure on the host, the symbolic scatter map, and uploads everything. */
+sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g);
+sgb_status sgb_get_structure_info(const sgb_handle* h, sgb_structure_info* out);
+/* Hessian order: hessian index -> (kind 0 pose / 1 landmark, array index, scalar offset);
+ * block list in column-major, row-ascending order (the order g2o's SparseBlockMatrix iterates);
+ * hessian index per vertex (-1 = fixed or inactive). Any pointer may be NULL. */
+sgb_status sgb_get_structure(const sgb_handle* h, int32_t* kind, int32_t* index, int32_t* offset,
+                             int32_t* blk_row, int32_t* blk_col, int32_t* blk_nrows, int32_t* blk_ncols,
+                             int32_t* pose_hidx, int32_t* lm_hidx);
+
+/* Test hook = SparseOptimizer::computeActiveErrors + BlockSolver::buildSystem at the current
+ * estimates: b [scalar_dim], block values in sgb_get_structure order (each block column-major,
+ * like Eigen), chi2[0] = activeChi2, chi2[1] = activeRobustChi2. Any pointer may be NULL. */
+sgb_status sgb_linearize(sgb_handle* h, double* b, double* Hblocks, double* chi2);
+/* Test hook: one damped solve (H + lambda I) x = b at the current estimates (re-linearises).
+ * x [scalar_dim] in Hessian order; pcg_iters / rel_residual may be NULL. */
+sgb_status sgb_solve_once(sgb_handle* h, double lambda, double* x, int32_t* pcg_iters, double* rel_residual);
+
+/* SparseOptimizer::optimize(iters, online): returns through *iters_done what g2o returns
+ * (iterations run; 0 on Fail; -1 if not initialised). stats may be NULL or hold max_iters entries.
+ * Estimates stay resident on the device and are also copied back (sgb_get_estimates). */
+sgb_status sgb_optimize(sgb_handle* h, int32_t algo, int32_t max_iters, int32_t online,
+                        int32_t* iters_done, sgb_iter_stat* stats);
+/* One OptimizationAlgorithm::solve(iteration, online) -- the per-iteration plugin path. */
+sgb_status sgb_step(sgb_handle* h, int32_t algo, int32_t iteration, int32_t online, int32_t* result,
+                    sgb_iter_stat* stat);
+
+/* estimates of ALL vertices, in the array order of sgb_set_graph */
+sgb_status sgb_get_estimates(sgb_handle* h, double* pose_est, double* lm_est);
+sgb_status sgb_set_estimates(sgb_handle* h, const double* pose_est, const double* lm_est);
+/* SparseOptimizer::push / pop / discardTop on the device-resident estimates (drone.cpp:149,180,184) */
+sgb_status sgb_push(sgb_handle* h);
+sgb_status sgb_pop(sgb_handle* h);
+sgb_status sgb_discard_top(sgb_handle* h);
+/* computeActiveErrors(); chi2[0] = activeChi2() (what the caller's gate uses, drone.cpp:164-165),
+ * chi2[1] = activeRobustChi2() */
+sgb_status sgb_chi2(sgb_handle* h, double* chi2);
+sgb_status sgb_get_timings(const sgb_handle* h, sgb_timings* out);
+
+/* device-resident variant for benchmarking: the same as sgb_optimize but the estimates are first
+ * reset on the device from the copy uploaded by sgb_set_graph, and nothing is copied back */
+sgb_status sgb_optimize_resident(sgb_handle* h, int32_t algo, int32_t max_iters, int32_t* iters_done,
+                                 sgb_iter_stat* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SGB_CAPI_H */

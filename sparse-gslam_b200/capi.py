@@ -1,0 +1,99 @@
+"""ctypes mirror of include/sgb_capi.h (the C ABI a g2o plugin binds to). No torch types, plain pointers."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsgb.so")
+
+OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOT_INITIALIZED, ERR_UNSUPPORTED, ERR_SOLVE_FAILED, ERR_COMM = range(8)
+RESULT_TERMINATE, RESULT_OK, RESULT_FAIL = 2, 1, -1
+ALGO_LM, ALGO_GN = 0, 1
+JAC_G2O_NUMERIC, JAC_ANALYTIC = 0, 1
+
+EXPORTS = [
+    "sgb_version", "sgb_device_count", "sgb_default_options", "sgb_create", "sgb_destroy", "sgb_last_error",
+    "sgb_set_graph", "sgb_get_structure_info", "sgb_get_structure", "sgb_linearize", "sgb_solve_once", "sgb_optimize",
+    "sgb_step", "sgb_get_estimates", "sgb_set_estimates", "sgb_push", "sgb_pop", "sgb_discard_top", "sgb_chi2",
+    "sgb_get_timings", "sgb_optimize_resident",
+]
+
+
+class Options(C.Structure):
+    _fields_ = [("device", C.c_int32), ("jacobian_mode", C.c_int32), ("pcg_tolerance", C.c_double),
+                ("pcg_max_iters", C.c_int32), ("verbose", C.c_int32), ("lm_tau", C.c_double),
+                ("lm_user_lambda", C.c_double), ("lm_max_trials", C.c_int32), ("reserved", C.c_int32)]
+
+
+class GraphSoA(C.Structure):
+    _fields_ = [
+        ("n_poses", C.c_int32), ("pose_id", C.c_void_p), ("pose_est", C.c_void_p), ("pose_fixed", C.c_void_p),
+        ("n_landmarks", C.c_int32), ("lm_id", C.c_void_p), ("lm_est", C.c_void_p), ("lm_fixed", C.c_void_p),
+        ("n_pp", C.c_int32), ("pp_i", C.c_void_p), ("pp_j", C.c_void_p), ("pp_z", C.c_void_p), ("pp_info", C.c_void_p),
+        ("pp_phi", C.c_void_p), ("pp_seq", C.c_void_p),
+        ("n_pl", C.c_int32), ("pl_pose", C.c_void_p), ("pl_lm", C.c_void_p), ("pl_z", C.c_void_p),
+        ("pl_info", C.c_void_p), ("pl_seq", C.c_void_p),
+    ]
+
+
+class IterStat(C.Structure):
+    _fields_ = [("iteration", C.c_int32), ("trials", C.c_int32), ("result", C.c_int32), ("pcg_iters", C.c_int32),
+                ("chi2", C.c_double), ("lambda_", C.c_double), ("rho", C.c_double), ("chi2_before", C.c_double),
+                ("pcg_residual", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+class StructureInfo(C.Structure):
+    _fields_ = [("n_free", C.c_int32), ("n_free_poses", C.c_int32), ("n_free_landmarks", C.c_int32),
+                ("n_blocks", C.c_int32), ("scalar_dim", C.c_int32), ("n_active_pp", C.c_int32),
+                ("n_active_pl", C.c_int32), ("reserved", C.c_int32), ("block_values", C.c_int64)]
+
+
+class Timings(C.Structure):
+    _fields_ = [("linearize_ms", C.c_double), ("setup_ms", C.c_double), ("pcg_ms", C.c_double),
+                ("update_ms", C.c_double), ("total_ms", C.c_double), ("pcg_iters", C.c_int64), ("trials", C.c_int64),
+                ("linearizations", C.c_int64), ("kernel_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libsgb.so. Raises loudly when it has not been built: there is no Python/CPU fallback."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: build it with `python -m sparse_gslam_b200.build` "
+                           "(the backend is CUDA-only; there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.sgb_version.restype = C.c_char_p
+    L.sgb_device_count.restype = C.c_int32
+    L.sgb_default_options.argtypes = [C.POINTER(Options)]
+    L.sgb_create.argtypes = [C.POINTER(Options), C.POINTER(vp)]
+    L.sgb_destroy.argtypes = [vp]
+    L.sgb_last_error.argtypes = [vp]
+    L.sgb_last_error.restype = C.c_char_p
+    L.sgb_set_graph.argtypes = [vp, C.POINTER(GraphSoA)]
+    L.sgb_get_structure_info.argtypes = [vp, C.POINTER(StructureInfo)]
+    L.sgb_get_structure.argtypes = [vp] + [vp] * 9
+    L.sgb_linearize.argtypes = [vp, vp, vp, vp]
+    L.sgb_solve_once.argtypes = [vp, C.c_double, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.sgb_optimize.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp]
+    L.sgb_optimize_resident.argtypes = [vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp]
+    L.sgb_step.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp]
+    L.sgb_get_estimates.argtypes = [vp, vp, vp]
+    L.sgb_set_estimates.argtypes = [vp, vp, vp]
+    for f in ("sgb_push", "sgb_pop", "sgb_discard_top"):
+        getattr(L, f).argtypes = [vp]
+    L.sgb_chi2.argtypes = [vp, vp]
+    L.sgb_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    _lib = L
+    return L

@@ -1,0 +1,715 @@
+// sgb_backend.cu -- handle, device memory, host orchestration of the LM / GN iteration and the C ABI
+// (include/sgb_capi.h). There is no CPU path in this file: every compute entry point needs a CUDA device.
+//
+// Control flow restated from the un-vendored g2o:
+//   SparseOptimizer::optimize -> OptimizationAlgorithm{Levenberg,GaussNewton}::solve, called by the reference at
+//   src/sparse_gslam/src/drone.cpp:150,155, submap_loop_closer.cpp:287, log_runner.cpp:204.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/sgb_capi.h"
+#include "sgb_kernels.cuh"
+#include "sgb_structure.h"
+
+using namespace sgb;
+
+namespace {
+
+struct PhaseEvents {
+  cudaEvent_t e[5];
+};
+
+}  // namespace
+
+struct sgb_handle {
+  sgb_options opt;
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  bool has_graph = false;
+  Structure S;
+  DevGraph G;
+  std::vector<void*> allocs;
+  DevScalars* d_sc = nullptr;
+  DevScalars* h_sc = nullptr;  // pinned
+  double* d_part_p = nullptr;
+  double* d_part_l = nullptr;
+  double* d_part_e = nullptr;
+  unsigned long long* d_bar = nullptr;
+  double* d_pose0 = nullptr;
+  double* d_lm0 = nullptr;
+  std::vector<std::pair<double*, double*>> stack;  // SparseOptimizer::push/pop backups (device)
+  int pcg_blocks = 1;
+  sgb_timings tm;
+  PhaseEvents ev;
+  bool lm_state_valid = false;
+};
+
+#define SGB_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(_e);                           \
+      return SGB_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+namespace {
+
+int grid_for(int n) {
+  int b = (n + kThreads - 1) / kThreads;
+  return std::max(1, std::min(b, 148 * 8));
+}
+
+template <class T>
+sgb_status dalloc(sgb_handle* h, T** out, size_t n) {
+  *out = nullptr;
+  void* p = nullptr;
+  size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+  SGB_CUDA(cudaMalloc(&p, bytes));
+  h->allocs.push_back(p);
+  *out = (T*)p;
+  return SGB_OK;
+}
+template <class T>
+sgb_status upload(sgb_handle* h, const T** out, const std::vector<T>& v) {
+  T* d = nullptr;
+  sgb_status s = dalloc(h, &d, v.size());
+  if (s != SGB_OK) return s;
+  if (!v.empty()) SGB_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  *out = d;
+  return SGB_OK;
+}
+sgb_status upload_sell(sgb_handle* h, Sell* out, const HostSell& s, int NC) {
+  out->rows = s.rows;
+  out->nslices = s.nslices;
+  sgb_status st = upload(h, &out->sbase, s.sbase);
+  if (st != SGB_OK) return st;
+  st = upload(h, &out->col, s.col);
+  if (st != SGB_OK) return st;
+  st = dalloc(h, &out->vals, (size_t)s.entries() * NC);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaMemsetAsync(out->vals, 0, std::max<size_t>((size_t)s.entries() * NC, 1) * sizeof(double), h->stream));
+  return SGB_OK;
+}
+
+void free_graph(sgb_handle* h) {
+  for (void* p : h->allocs) cudaFree(p);
+  h->allocs.clear();
+  h->stack.clear();
+  h->has_graph = false;
+  h->lm_state_valid = false;
+}
+
+sgb_status need_graph(sgb_handle* h) {
+  if (!h) return SGB_ERR_INVALID;
+  if (!h->has_graph) {
+    h->err = "0 vertices to optimize, maybe forgot to call initializeOptimization()";
+    return SGB_ERR_NOT_INITIALIZED;
+  }
+  return SGB_OK;
+}
+
+// ---- launches (all on the handle's stream) --------------------------------------------------------------
+sgb_status launch_linearize(sgb_handle* h) {
+  DevGraph& G = h->G;
+  int gp = grid_for(G.Pf), gl = grid_for(G.Lf);
+  if (G.Pf > 0) k_lin_pose<<<gp, kThreads, 0, h->stream>>>(G, h->d_part_p);
+  if (G.Lf > 0) k_lin_lm<<<gl, kThreads, 0, h->stream>>>(G, h->d_part_l);
+  h->tm.kernel_launches += (G.Pf > 0) + (G.Lf > 0);
+  h->tm.linearizations++;
+  SGB_CUDA(cudaGetLastError());
+  return SGB_OK;
+}
+sgb_status launch_finalize_lin(sgb_handle* h, int init_lambda) {
+  DevGraph& G = h->G;
+  double tau = h->opt.lm_tau > 0 ? h->opt.lm_tau : 1e-5;
+  k_finalize_lin<<<1, kThreads, 0, h->stream>>>(h->d_sc, h->d_part_p, G.Pf > 0 ? grid_for(G.Pf) : 0, h->d_part_l,
+                                                G.Lf > 0 ? grid_for(G.Lf) : 0, init_lambda, tau, h->opt.lm_user_lambda);
+  h->tm.kernel_launches++;
+  SGB_CUDA(cudaGetLastError());
+  return SGB_OK;
+}
+sgb_status launch_setup(sgb_handle* h, double lambda_override, int use_override) {
+  DevGraph& G = h->G;
+  if (G.Lf > 0) k_setup_lm<<<grid_for(G.Lf), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
+  if (G.Pf > 0) k_setup_pose<<<grid_for(G.Pf), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
+  h->tm.kernel_launches += (G.Pf > 0) + (G.Lf > 0);
+  SGB_CUDA(cudaGetLastError());
+  return SGB_OK;
+}
+sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
+  DevGraph G = h->G;
+  DevScalars* sc = h->d_sc;
+  double* part = h->d_part_e;
+  unsigned long long* bar = h->d_bar;
+  PcgParams prm;
+  prm.tol = h->opt.pcg_tolerance > 0 ? h->opt.pcg_tolerance : 1e-10;
+  prm.maxit = h->opt.pcg_max_iters > 0 ? h->opt.pcg_max_iters : std::max(100, 4 * 3 * G.Pf);
+  prm.lambda_override = lambda_override;
+  prm.use_override = use_override;
+  SGB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), h->stream));
+  void* args[] = {&G, &sc, &part, &bar, &prm};
+  SGB_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(h->pcg_blocks), dim3(kThreads), args, 0, h->stream));
+  h->tm.kernel_launches++;
+  return SGB_OK;
+}
+sgb_status launch_backsub_update(sgb_handle* h, const double* pose_src, double* pose_dst, const double* lm_src,
+                                 double* lm_dst, double lambda_override, int use_override) {
+  DevGraph& G = h->G;
+  if (G.Lf > 0) {
+    k_backsub<<<grid_for(G.Lf), kThreads, 0, h->stream>>>(G);
+    h->tm.kernel_launches++;
+  }
+  k_update<<<grid_for(G.Pf + G.Lf), kThreads, 0, h->stream>>>(G, h->d_sc, pose_src, pose_dst, lm_src, lm_dst, h->d_part_p,
+                                                             lambda_override, use_override);
+  h->tm.kernel_launches++;
+  SGB_CUDA(cudaGetLastError());
+  return SGB_OK;
+}
+sgb_status launch_chi2(sgb_handle* h, const double* pose, const double* lm) {
+  DevGraph& G = h->G;
+  k_chi2_edges<<<grid_for(G.n_pp + G.n_pl), kThreads, 0, h->stream>>>(G, pose, lm, h->d_part_e);
+  h->tm.kernel_launches++;
+  SGB_CUDA(cudaGetLastError());
+  return SGB_OK;
+}
+sgb_status read_scalars(sgb_handle* h) {
+  SGB_CUDA(cudaMemcpyAsync(h->h_sc, h->d_sc, sizeof(DevScalars), cudaMemcpyDeviceToHost, h->stream));
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  return SGB_OK;
+}
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, a, b);
+  return ms;
+}
+
+// one OptimizationAlgorithm::solve(iteration)
+sgb_status do_step(sgb_handle* h, int algo, int iteration, int* result, sgb_iter_stat* stat) {
+  DevGraph& G = h->G;
+  sgb_status st;
+  cudaStream_t s = h->stream;
+  SGB_CUDA(cudaEventRecord(h->ev.e[0], s));
+  if ((st = launch_linearize(h)) != SGB_OK) return st;
+  if ((st = launch_finalize_lin(h, (algo == SGB_ALGO_LM && (iteration == 0 || !h->lm_state_valid)) ? 1 : 0)) != SGB_OK) return st;
+  SGB_CUDA(cudaEventRecord(h->ev.e[1], s));
+  int pcg_total = 0, trials = 0;
+  bool first = true;
+  float t_lin = 0, t_setup = 0, t_pcg = 0, t_upd = 0;
+  if (algo == SGB_ALGO_GN) {
+    if ((st = launch_setup(h, 0.0, 1)) != SGB_OK) return st;
+    SGB_CUDA(cudaEventRecord(h->ev.e[2], s));
+    if ((st = launch_pcg(h, 0.0, 1)) != SGB_OK) return st;
+    SGB_CUDA(cudaEventRecord(h->ev.e[3], s));
+    if ((st = launch_backsub_update(h, G.pose, G.pose, G.lm, G.lm, 0.0, 1)) != SGB_OK) return st;
+    SGB_CUDA(cudaEventRecord(h->ev.e[4], s));
+    if ((st = read_scalars(h)) != SGB_OK) return st;
+    bool ok = (h->h_sc->pcg_flag != 2) && (h->h_sc->setup_fail == 0);
+    SGB_CUDA(cudaMemsetAsync(&h->d_sc->setup_fail, 0, sizeof(int32_t), s));
+    *result = ok ? SGB_RESULT_OK : SGB_RESULT_FAIL;
+    pcg_total = h->h_sc->pcg_iters;
+    trials = 1;
+    t_lin = ev_ms(h->ev.e[0], h->ev.e[1]);
+    t_setup = ev_ms(h->ev.e[1], h->ev.e[2]);
+    t_pcg = ev_ms(h->ev.e[2], h->ev.e[3]);
+    t_upd = ev_ms(h->ev.e[3], h->ev.e[4]);
+  } else {
+    h->lm_state_valid = true;
+    int max_trials = h->opt.lm_max_trials > 0 ? h->opt.lm_max_trials : 10;
+    while (true) {
+      if (!first) SGB_CUDA(cudaEventRecord(h->ev.e[1], s));
+      if ((st = launch_setup(h, 0.0, 0)) != SGB_OK) return st;
+      SGB_CUDA(cudaEventRecord(h->ev.e[2], s));
+      if ((st = launch_pcg(h, 0.0, 0)) != SGB_OK) return st;
+      SGB_CUDA(cudaEventRecord(h->ev.e[3], s));
+      if ((st = launch_backsub_update(h, G.pose, G.pose_trial, G.lm, G.lm_trial, 0.0, 0)) != SGB_OK) return st;
+      if ((st = launch_chi2(h, G.pose_trial, G.lm_trial)) != SGB_OK) return st;
+      k_lm_control<<<1, kThreads, 0, s>>>(h->d_sc, h->d_part_e, grid_for(G.n_pp + G.n_pl), h->d_part_p,
+                                          grid_for(G.Pf + G.Lf), max_trials);
+      h->tm.kernel_launches++;
+      SGB_CUDA(cudaGetLastError());
+      SGB_CUDA(cudaEventRecord(h->ev.e[4], s));
+      if ((st = read_scalars(h)) != SGB_OK) return st;
+      if (first) t_lin = ev_ms(h->ev.e[0], h->ev.e[1]);
+      t_setup += ev_ms(h->ev.e[1], h->ev.e[2]);
+      t_pcg += ev_ms(h->ev.e[2], h->ev.e[3]);
+      t_upd += ev_ms(h->ev.e[3], h->ev.e[4]);
+      pcg_total += h->h_sc->pcg_iters;
+      first = false;
+      if (h->h_sc->accepted) {  // discardTop: the trial estimates become current
+        std::swap(G.pose, G.pose_trial);
+        std::swap(G.lm, G.lm_trial);
+      }
+      if (!h->h_sc->again) break;
+    }
+    trials = h->h_sc->trials;
+    *result = h->h_sc->result;
+  }
+  h->tm.linearize_ms += t_lin;
+  h->tm.setup_ms += t_setup;
+  h->tm.pcg_ms += t_pcg;
+  h->tm.update_ms += t_upd;
+  h->tm.pcg_iters += pcg_total;
+  h->tm.trials += trials;
+  if (stat) {
+    stat->iteration = iteration;
+    stat->trials = trials;
+    stat->result = *result;
+    stat->pcg_iters = pcg_total;
+    stat->chi2 = algo == SGB_ALGO_LM ? h->h_sc->current_chi : h->h_sc->chi2_robust;
+    stat->lambda = algo == SGB_ALGO_LM ? h->h_sc->lambda : 0.0;
+    stat->rho = algo == SGB_ALGO_LM ? h->h_sc->rho : 0.0;
+    stat->chi2_before = h->h_sc->chi_lin;
+    stat->pcg_residual = h->h_sc->pcg_rel;
+  }
+  return SGB_OK;
+}
+
+sgb_status do_optimize(sgb_handle* h, int algo, int max_iters, int* iters_done, sgb_iter_stat* stats) {
+  if (algo != SGB_ALGO_LM && algo != SGB_ALGO_GN) {
+    h->err = "unknown algorithm";
+    return SGB_ERR_INVALID;
+  }
+  std::memset(&h->tm, 0, sizeof h->tm);
+  cudaEvent_t t0, t1;
+  SGB_CUDA(cudaEventCreate(&t0));
+  SGB_CUDA(cudaEventCreate(&t1));
+  SGB_CUDA(cudaEventRecord(t0, h->stream));
+  int done = 0, result = SGB_RESULT_OK;
+  bool ok = true;
+  sgb_status st = SGB_OK;
+  for (int i = 0; i < max_iters && ok; ++i) {
+    sgb_iter_stat tmp;
+    st = do_step(h, algo, i, &result, &tmp);
+    if (st != SGB_OK) break;
+    if (stats) stats[i] = tmp;
+    ok = (result == SGB_RESULT_OK);
+    ++done;
+  }
+  cudaEventRecord(t1, h->stream);
+  cudaEventSynchronize(t1);
+  h->tm.total_ms = ev_ms(t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  if (st != SGB_OK) return st;
+  if (iters_done) *iters_done = (result == SGB_RESULT_FAIL) ? 0 : done;
+  return SGB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* sgb_version(void) { return "sparse-gslam_b200 0.1 (sm_100a)"; }
+
+int32_t sgb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+void sgb_default_options(sgb_options* o) {
+  if (!o) return;
+  std::memset(o, 0, sizeof *o);
+  o->device = -1;
+  o->jacobian_mode = SGB_JAC_G2O_NUMERIC;
+  o->pcg_tolerance = 1e-10;
+  o->pcg_max_iters = 0;
+  o->verbose = 0;
+  o->lm_tau = 1e-5;
+  o->lm_user_lambda = 0.0;
+  o->lm_max_trials = 10;
+}
+
+sgb_status sgb_create(const sgb_options* opt, sgb_handle** out) {
+  if (!out) return SGB_ERR_INVALID;
+  *out = nullptr;
+  if (sgb_device_count() <= 0) return SGB_ERR_NO_DEVICE;  // no CPU fallback by design
+  sgb_handle* h = new sgb_handle();
+  if (opt) h->opt = *opt; else sgb_default_options(&h->opt);
+  std::memset(&h->tm, 0, sizeof h->tm);
+  std::memset(&h->G, 0, sizeof h->G);
+  auto fail = [&](const char* what, cudaError_t e) {
+    std::fprintf(stderr, "sgb_create: %s: %s\n", what, cudaGetErrorString(e));
+    delete h;
+    return SGB_ERR_CUDA;
+  };
+  cudaError_t e;
+  if (h->opt.device >= 0) {
+    if ((e = cudaSetDevice(h->opt.device)) != cudaSuccess) return fail("cudaSetDevice", e);
+  }
+  if ((e = cudaGetDevice(&h->device)) != cudaSuccess) return fail("cudaGetDevice", e);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, h->device)) != cudaSuccess) return fail("cudaGetDeviceProperties", e);
+  h->sm_count = prop.multiProcessorCount;
+  if (!prop.cooperativeLaunch) {
+    delete h;
+    return SGB_ERR_UNSUPPORTED;
+  }
+  if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  for (auto& ev : h->ev.e)
+    if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
+  if ((e = cudaMalloc((void**)&h->d_sc, sizeof(DevScalars))) != cudaSuccess) return fail("cudaMalloc", e);
+  cudaMemset(h->d_sc, 0, sizeof(DevScalars));
+  if ((e = cudaMallocHost((void**)&h->h_sc, sizeof(DevScalars))) != cudaSuccess) return fail("cudaMallocHost", e);
+  std::memset(h->h_sc, 0, sizeof(DevScalars));
+  size_t pb = 3 * (size_t)kMaxBlocks * sizeof(double);
+  if ((e = cudaMalloc((void**)&h->d_part_p, pb)) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc((void**)&h->d_part_l, pb)) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc((void**)&h->d_part_e, pb)) != cudaSuccess) return fail("cudaMalloc", e);
+  if ((e = cudaMalloc((void**)&h->d_bar, sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
+  *out = h;
+  return SGB_OK;
+}
+
+void sgb_destroy(sgb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  free_graph(h);
+  cudaFree(h->d_sc);
+  cudaFreeHost(h->h_sc);
+  cudaFree(h->d_part_p);
+  cudaFree(h->d_part_l);
+  cudaFree(h->d_part_e);
+  cudaFree(h->d_bar);
+  for (auto& ev : h->ev.e) cudaEventDestroy(ev);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+const char* sgb_last_error(const sgb_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g) {
+  if (!h || !g) return SGB_ERR_INVALID;
+  SGB_CUDA(cudaSetDevice(h->device));
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  free_graph(h);
+  sgb_status st = build_structure(*g, h->S, h->err);
+  if (st != SGB_OK) return st;
+  const Structure& S = h->S;
+  DevGraph& G = h->G;
+  std::memset(&G, 0, sizeof G);
+  G.P_all = S.P_all; G.L_all = S.L_all; G.Pf = S.Pf; G.Lf = S.Lf; G.n_pp = S.n_pp; G.n_pl = S.n_pl;
+  G.has_robust = S.has_robust ? 1 : 0;
+  G.jac_numeric = h->opt.jacobian_mode == SGB_JAC_G2O_NUMERIC ? 1 : 0;
+#define UP(field, vec) if ((st = upload(h, &G.field, vec)) != SGB_OK) return st
+  // estimates (+ trial buffers and the pristine copy used by sgb_optimize_resident)
+  size_t np = 3 * (size_t)S.P_all, nl = 2 * (size_t)S.L_all;
+  if ((st = dalloc(h, &G.pose, np)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.lm, nl)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.pose_trial, np)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.lm_trial, nl)) != SGB_OK) return st;
+  if ((st = dalloc(h, &h->d_pose0, np)) != SGB_OK) return st;
+  if ((st = dalloc(h, &h->d_lm0, nl)) != SGB_OK) return st;
+  if (np) {
+    SGB_CUDA(cudaMemcpyAsync(G.pose, g->pose_est, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(G.pose_trial, G.pose, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(h->d_pose0, G.pose, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (nl) {
+    SGB_CUDA(cudaMemcpyAsync(G.lm, g->lm_est, nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(G.lm_trial, G.lm, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(h->d_lm0, G.lm, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  UP(pose_of_h, S.pose_of_h); UP(lm_of_h, S.lm_of_h);
+  UP(pp_i, S.pp_i); UP(pp_j, S.pp_j); UP(pp_hi, S.pp_hi); UP(pp_hj, S.pp_hj);
+  UP(pp_e_ij, S.pp_e_ij); UP(pp_e_ji, S.pp_e_ji); UP(pp_dup, S.pp_dup);
+  UP(pl_p, S.pl_p); UP(pl_l, S.pl_l); UP(pl_hp, S.pl_hp); UP(pl_hl, S.pl_hl);
+  UP(pl_e_pl, S.pl_e_pl); UP(pl_e_lp, S.pl_e_lp); UP(pl_dup, S.pl_dup);
+  UP(pinc_ptr, S.pinc_ptr); UP(pinc, S.pinc); UP(linc_ptr, S.linc_ptr); UP(linc, S.linc);
+  UP(hpp_diag, S.hpp_diag); UP(lp_row2h, S.lp_row2h); UP(lp_h2row, S.lp_h2row);
+  {  // edge data, component-major, active edges in insertion order; EdgeSE2::setMeasurement caches the inverse
+    std::vector<double> zinv(3 * (size_t)S.n_pp), info(6 * (size_t)S.n_pp), phi(S.n_pp, 0.0);
+    for (int k = 0; k < S.n_pp; ++k) {
+      int s = S.pp_src[k];
+      double x = g->pp_z[3 * (size_t)s], y = g->pp_z[3 * (size_t)s + 1], th = g->pp_z[3 * (size_t)s + 2];
+      double thi = normalize_theta(-th);
+      double c = std::cos(thi), sn = std::sin(thi);
+      zinv[k] = c * (-x) - sn * (-y);
+      zinv[(size_t)S.n_pp + k] = sn * (-x) + c * (-y);
+      zinv[2 * (size_t)S.n_pp + k] = thi;
+      for (int c6 = 0; c6 < 6; ++c6) info[(size_t)c6 * S.n_pp + k] = g->pp_info[6 * (size_t)s + c6];
+      if (g->pp_phi) phi[k] = g->pp_phi[s];
+    }
+    UP(pp_zinv, zinv); UP(pp_info, info); UP(pp_phi, phi);
+    std::vector<double> z(2 * (size_t)S.n_pl), linfo(3 * (size_t)S.n_pl);
+    for (int k = 0; k < S.n_pl; ++k) {
+      int s = S.pl_src[k];
+      z[k] = g->pl_z[2 * (size_t)s];
+      z[(size_t)S.n_pl + k] = g->pl_z[2 * (size_t)s + 1];
+      for (int c3 = 0; c3 < 3; ++c3) linfo[(size_t)c3 * S.n_pl + k] = g->pl_info[3 * (size_t)s + c3];
+    }
+    UP(pl_z, z); UP(pl_info, linfo);
+  }
+#undef UP
+  if ((st = upload_sell(h, &G.Hpp, S.Hpp, 9)) != SGB_OK) return st;
+  if ((st = upload_sell(h, &G.Hpl, S.Hpl, 6)) != SGB_OK) return st;
+  if ((st = upload_sell(h, &G.Hlp, S.Hlp, 6)) != SGB_OK) return st;
+  size_t n3 = 3 * (size_t)S.Pf, n2 = 2 * (size_t)S.Lf;
+  if ((st = dalloc(h, &G.Hll, 3 * (size_t)S.Lf)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.Hll_inv, 3 * (size_t)S.Lf)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.b, n3 + n2)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.x, n3 + n2)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.Minv, 9 * (size_t)S.Pf)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.bt, n3)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.r, n3)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.z, n3)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.p, n3)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.q, n3)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.t, n2)) != SGB_OK) return st;
+  SGB_CUDA(cudaMemsetAsync(G.x, 0, std::max<size_t>(n3 + n2, 1) * sizeof(double), h->stream));
+  SGB_CUDA(cudaMemsetAsync(h->d_sc, 0, sizeof(DevScalars), h->stream));
+  // persistent PCG grid: every CTA must be co-resident
+  int per_sm = 0;
+  SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, kThreads, 0));
+  int limit = std::max(1, per_sm * h->sm_count);
+  int want = std::max(1, (std::max(S.Pf, S.Lf) + kThreads - 1) / kThreads);
+  h->pcg_blocks = std::min(std::min(limit, want), kMaxBlocks);
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  h->has_graph = true;
+  h->lm_state_valid = false;
+  return SGB_OK;
+}
+
+sgb_status sgb_get_structure_info(const sgb_handle* h, sgb_structure_info* o) {
+  if (!h || !o) return SGB_ERR_INVALID;
+  if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
+  const Structure& S = h->S;
+  o->n_free = S.Pf + S.Lf;
+  o->n_free_poses = S.Pf;
+  o->n_free_landmarks = S.Lf;
+  o->n_blocks = (int32_t)S.blk_row.size();
+  o->scalar_dim = S.dim;
+  o->n_active_pp = S.n_pp;
+  o->n_active_pl = S.n_pl;
+  o->reserved = 0;
+  o->block_values = S.block_values;
+  return SGB_OK;
+}
+
+sgb_status sgb_get_structure(const sgb_handle* h, int32_t* kind, int32_t* index, int32_t* offset, int32_t* br,
+                             int32_t* bc, int32_t* bnr, int32_t* bnc, int32_t* ph, int32_t* lh) {
+  if (!h) return SGB_ERR_INVALID;
+  if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
+  const Structure& S = h->S;
+  auto cp = [](int32_t* dst, const std::vector<int32_t>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(int32_t)); };
+  cp(kind, S.ord_kind); cp(index, S.ord_index); cp(offset, S.ord_offset);
+  cp(br, S.blk_row); cp(bc, S.blk_col); cp(bnr, S.blk_nr); cp(bnc, S.blk_nc);
+  if (ph) for (int i = 0; i < S.P_all; ++i) ph[i] = S.pose_h[i];
+  if (lh) for (int i = 0; i < S.L_all; ++i) lh[i] = S.lm_h[i] >= 0 ? S.Pf + S.lm_h[i] : -1;
+  return SGB_OK;
+}
+
+sgb_status sgb_linearize(sgb_handle* h, double* b, double* Hblocks, double* chi2) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  if ((st = launch_linearize(h)) != SGB_OK) return st;
+  if ((st = launch_finalize_lin(h, 0)) != SGB_OK) return st;
+  if ((st = read_scalars(h)) != SGB_OK) return st;
+  const Structure& S = h->S;
+  DevGraph& G = h->G;
+  if (chi2) { chi2[0] = h->h_sc->chi2; chi2[1] = h->h_sc->chi2_robust; }
+  if (b) SGB_CUDA(cudaMemcpy(b, G.b, (size_t)S.dim * sizeof(double), cudaMemcpyDeviceToHost));
+  if (Hblocks) {
+    std::vector<double> hpp((size_t)S.Hpp.entries() * 9), hpl((size_t)S.Hpl.entries() * 6), hll(3 * (size_t)S.Lf);
+    if (!hpp.empty()) SGB_CUDA(cudaMemcpy(hpp.data(), G.Hpp.vals, hpp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (!hpl.empty()) SGB_CUDA(cudaMemcpy(hpl.data(), G.Hpl.vals, hpl.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    if (!hll.empty()) SGB_CUDA(cudaMemcpy(hll.data(), G.Hll, hll.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    size_t o = 0;
+    for (size_t k = 0; k < S.blk_row.size(); ++k) {
+      int kind = S.blk_kind[k], e = S.blk_entry[k];
+      if (kind == 0) {  // 3x3 row-major on the device -> column-major out
+        for (int c = 0; c < 3; ++c)
+          for (int r = 0; r < 3; ++r) Hblocks[o + c * 3 + r] = hpp[sell_vaddr(e, 9, 3 * r + c)];
+        o += 9;
+      } else if (kind == 1) {  // 3x2
+        for (int c = 0; c < 2; ++c)
+          for (int r = 0; r < 3; ++r) Hblocks[o + c * 3 + r] = hpl[sell_vaddr(e, 6, 2 * r + c)];
+        o += 6;
+      } else {
+        double h11 = hll[e], h12 = hll[(size_t)S.Lf + e], h22 = hll[2 * (size_t)S.Lf + e];
+        Hblocks[o] = h11; Hblocks[o + 1] = h12; Hblocks[o + 2] = h12; Hblocks[o + 3] = h22;
+        o += 4;
+      }
+    }
+  }
+  return SGB_OK;
+}
+
+sgb_status sgb_solve_once(sgb_handle* h, double lambda, double* x, int32_t* pcg_iters, double* rel) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  if ((st = launch_linearize(h)) != SGB_OK) return st;
+  if ((st = launch_finalize_lin(h, 0)) != SGB_OK) return st;
+  if ((st = launch_setup(h, lambda, 1)) != SGB_OK) return st;
+  if ((st = launch_pcg(h, lambda, 1)) != SGB_OK) return st;
+  if (h->G.Lf > 0) {
+    k_backsub<<<grid_for(h->G.Lf), kThreads, 0, h->stream>>>(h->G);
+    h->tm.kernel_launches++;
+  }
+  if ((st = read_scalars(h)) != SGB_OK) return st;
+  bool ok = (h->h_sc->pcg_flag != 2) && (h->h_sc->setup_fail == 0);
+  SGB_CUDA(cudaMemset(&h->d_sc->setup_fail, 0, sizeof(int32_t)));
+  if (pcg_iters) *pcg_iters = h->h_sc->pcg_iters;
+  if (rel) *rel = h->h_sc->pcg_rel;
+  if (x) SGB_CUDA(cudaMemcpy(x, h->G.x, (size_t)h->S.dim * sizeof(double), cudaMemcpyDeviceToHost));
+  if (!ok) {
+    h->err = "linear solve failed (system not positive definite)";
+    return SGB_ERR_SOLVE_FAILED;
+  }
+  return SGB_OK;
+}
+
+sgb_status sgb_optimize(sgb_handle* h, int32_t algo, int32_t max_iters, int32_t online, int32_t* iters_done,
+                        sgb_iter_stat* stats) {
+  (void)online;  // the structure is rebuilt by sgb_set_graph; online only skips buildStructure in g2o
+  if (iters_done) *iters_done = -1;
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  h->lm_state_valid = false;  // lambda is re-initialised at iteration 0 of every optimize() call
+  return do_optimize(h, algo, max_iters, iters_done, stats);
+}
+
+sgb_status sgb_optimize_resident(sgb_handle* h, int32_t algo, int32_t max_iters, int32_t* iters_done,
+                                 sgb_iter_stat* stats) {
+  if (iters_done) *iters_done = -1;
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  size_t np = 3 * (size_t)h->S.P_all, nl = 2 * (size_t)h->S.L_all;
+  if (np) SGB_CUDA(cudaMemcpyAsync(h->G.pose, h->d_pose0, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (nl) SGB_CUDA(cudaMemcpyAsync(h->G.lm, h->d_lm0, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->lm_state_valid = false;
+  return do_optimize(h, algo, max_iters, iters_done, stats);
+}
+
+sgb_status sgb_step(sgb_handle* h, int32_t algo, int32_t iteration, int32_t online, int32_t* result, sgb_iter_stat* stat) {
+  (void)online;
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  if (iteration == 0) h->lm_state_valid = false;
+  int r = SGB_RESULT_OK;
+  st = do_step(h, algo, iteration, &r, stat);
+  if (result) *result = r;
+  return st;
+}
+
+sgb_status sgb_get_estimates(sgb_handle* h, double* pose_est, double* lm_est) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  if (pose_est && h->S.P_all)
+    SGB_CUDA(cudaMemcpyAsync(pose_est, h->G.pose, 3 * (size_t)h->S.P_all * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  if (lm_est && h->S.L_all)
+    SGB_CUDA(cudaMemcpyAsync(lm_est, h->G.lm, 2 * (size_t)h->S.L_all * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  return SGB_OK;
+}
+
+sgb_status sgb_set_estimates(sgb_handle* h, const double* pose_est, const double* lm_est) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  size_t np = 3 * (size_t)h->S.P_all * sizeof(double), nl = 2 * (size_t)h->S.L_all * sizeof(double);
+  if (pose_est && np) {
+    SGB_CUDA(cudaMemcpyAsync(h->G.pose, pose_est, np, cudaMemcpyHostToDevice, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(h->G.pose_trial, h->G.pose, np, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (lm_est && nl) {
+    SGB_CUDA(cudaMemcpyAsync(h->G.lm, lm_est, nl, cudaMemcpyHostToDevice, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(h->G.lm_trial, h->G.lm, nl, cudaMemcpyDeviceToDevice, h->stream));
+  }
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  return SGB_OK;
+}
+
+sgb_status sgb_push(sgb_handle* h) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  double *p = nullptr, *l = nullptr;
+  size_t np = 3 * (size_t)h->S.P_all, nl = 2 * (size_t)h->S.L_all;
+  if ((st = dalloc(h, &p, np)) != SGB_OK) return st;
+  if ((st = dalloc(h, &l, nl)) != SGB_OK) return st;
+  if (np) SGB_CUDA(cudaMemcpyAsync(p, h->G.pose, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (nl) SGB_CUDA(cudaMemcpyAsync(l, h->G.lm, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  h->stack.push_back({p, l});
+  return SGB_OK;
+}
+
+static void release_top(sgb_handle* h) {
+  auto top = h->stack.back();
+  h->stack.pop_back();
+  for (void* q : {(void*)top.first, (void*)top.second}) {
+    auto it = std::find(h->allocs.begin(), h->allocs.end(), q);
+    if (it != h->allocs.end()) h->allocs.erase(it);
+    cudaFree(q);
+  }
+}
+
+sgb_status sgb_pop(sgb_handle* h) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  if (h->stack.empty()) { h->err = "pop on an empty stack"; return SGB_ERR_INVALID; }
+  SGB_CUDA(cudaSetDevice(h->device));
+  size_t np = 3 * (size_t)h->S.P_all, nl = 2 * (size_t)h->S.L_all;
+  auto top = h->stack.back();
+  if (np) {
+    SGB_CUDA(cudaMemcpyAsync(h->G.pose, top.first, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(h->G.pose_trial, top.first, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  if (nl) {
+    SGB_CUDA(cudaMemcpyAsync(h->G.lm, top.second, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(h->G.lm_trial, top.second, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  release_top(h);
+  return SGB_OK;
+}
+
+sgb_status sgb_discard_top(sgb_handle* h) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  if (h->stack.empty()) { h->err = "discardTop on an empty stack"; return SGB_ERR_INVALID; }
+  SGB_CUDA(cudaSetDevice(h->device));
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  release_top(h);
+  return SGB_OK;
+}
+
+sgb_status sgb_chi2(sgb_handle* h, double* chi2) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  SGB_CUDA(cudaSetDevice(h->device));
+  if ((st = launch_chi2(h, h->G.pose, h->G.lm)) != SGB_OK) return st;
+  k_finalize_chi<<<1, kThreads, 0, h->stream>>>(h->d_sc, h->d_part_e, grid_for(h->G.n_pp + h->G.n_pl));
+  h->tm.kernel_launches++;
+  SGB_CUDA(cudaGetLastError());
+  if ((st = read_scalars(h)) != SGB_OK) return st;
+  if (chi2) { chi2[0] = h->h_sc->chi2; chi2[1] = h->h_sc->chi2_robust; }
+  return SGB_OK;
+}
+
+sgb_status sgb_get_timings(const sgb_handle* h, sgb_timings* out) {
+  if (!h || !out) return SGB_ERR_INVALID;
+  *out = h->tm;
+  return SGB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,432 @@
+// sgb_rows.h -- the per-row / per-edge bodies of every kernel on the hot path, written once and called from the
+// CUDA kernels (sgb_kernels.cu). The host-side test harness under tests/hostsim executes the same bodies
+// serially to check indexing before GPU time is spent; the product never runs them on the CPU.
+//
+// Reference behaviour restated here: a9 EdgeSE2, a4-a6 EdgeSE2RhoTheta, a10
+// constructQuadraticForm, a11 DCS, a15 buildSystem, a18 setLambda, a20 update. Summation order inside a
+// Hessian block follows the reference: contributions are added in edge insertion order.
+#pragma once
+#include "sgb_math.h"
+#include "sgb_types.h"
+
+#if defined(__CUDA_ARCH__)
+#define SGB_LDG(p) __ldg(p)    // read-only for the lifetime of the kernel
+#define SGB_LDCG(p) __ldcg(p)  // written by other CTAs inside a persistent kernel: bypass L1
+#else
+#define SGB_LDG(p) (*(p))
+#define SGB_LDCG(p) (*(p))
+#endif
+
+namespace sgb {
+
+struct LinAcc {
+  double chi = 0.0;    // sum of e^T Omega e over the edges this row owns
+  double chi_r = 0.0;  // robustified
+  double maxd = 0.0;   // max |diag H|
+};
+
+SGB_HD size_t sell_vaddr(int e, int NC, int c) { return (size_t)(e & ~31) * NC + (size_t)c * 32 + (e & 31); }
+SGB_HD int sell_width(const Sell& m, int slice) { return (m.sbase[slice + 1] - m.sbase[slice]) >> 5; }
+
+// ---------------------------------------------------------------------------------------------------------
+// one pose-pose edge evaluated at (xi, xj): error, Jacobians, weighted information, -Omega e
+struct PPTerm {
+  double e[3], A[9], B[9], om[6], omr[3], chi, chi_r;
+};
+SGB_HD void pp_term(const DevGraph& g, int k, const double* pose, PPTerm& t) {
+  int i = SGB_LDG(&g.pp_i[k]), j = SGB_LDG(&g.pp_j[k]);
+  double xi[3] = {pose[3 * i], pose[3 * i + 1], pose[3 * i + 2]};
+  double xj[3] = {pose[3 * j], pose[3 * j + 1], pose[3 * j + 2]};
+  double zinv[3];
+  for (int c = 0; c < 3; ++c) zinv[c] = SGB_LDG(&g.pp_zinv[(size_t)c * g.n_pp + k]);
+  for (int c = 0; c < 6; ++c) t.om[c] = SGB_LDG(&g.pp_info[(size_t)c * g.n_pp + k]);
+  double si, ci, sz, cz;
+  sgb_sincos(xi[2], &si, &ci);
+  sgb_sincos(zinv[2], &sz, &cz);
+  pp_error(xi, xj, zinv, ci, si, cz, sz, t.e);
+  pp_jacobians(xi, xj, ci, si, cz, sz, t.A, t.B);
+  t.chi = sym3_quad(t.om, t.e);
+  t.chi_r = t.chi;
+  double w = 1.0;
+  if (g.has_robust) {
+    double phi = SGB_LDG(&g.pp_phi[k]);
+    if (phi > 0.0) dcs_robustify(phi, t.chi, &t.chi_r, &w);
+  }
+  if (w != 1.0)
+    for (int c = 0; c < 6; ++c) t.om[c] *= w;  // robustInformation = rho[1] * Omega
+  sym3_mul(t.om, t.e, t.omr);
+  for (int c = 0; c < 3; ++c) t.omr[c] = -t.omr[c];
+}
+// error only (chi2 evaluation after a trial step)
+SGB_HD void pp_chi(const DevGraph& g, int k, const double* pose, double* chi, double* chi_r) {
+  int i = SGB_LDG(&g.pp_i[k]), j = SGB_LDG(&g.pp_j[k]);
+  double xi[3] = {pose[3 * i], pose[3 * i + 1], pose[3 * i + 2]};
+  double xj[3] = {pose[3 * j], pose[3 * j + 1], pose[3 * j + 2]};
+  double zinv[3], om[6], e[3];
+  for (int c = 0; c < 3; ++c) zinv[c] = SGB_LDG(&g.pp_zinv[(size_t)c * g.n_pp + k]);
+  for (int c = 0; c < 6; ++c) om[c] = SGB_LDG(&g.pp_info[(size_t)c * g.n_pp + k]);
+  double si, ci, sz, cz;
+  sgb_sincos(xi[2], &si, &ci);
+  sgb_sincos(zinv[2], &sz, &cz);
+  pp_error(xi, xj, zinv, ci, si, cz, sz, e);
+  double c2 = sym3_quad(om, e), cr = c2, w;
+  if (g.has_robust) {
+    double phi = SGB_LDG(&g.pp_phi[k]);
+    if (phi > 0.0) dcs_robustify(phi, c2, &cr, &w);
+  }
+  *chi = c2;
+  *chi_r = cr;
+}
+
+// M (3x3 row-major) = X^T * sym(om) * Y for 3x3 row-major X, Y
+SGB_HD void xt_om_y(const double X[9], const double om[6], const double Y[9], double M[9]) {
+  double XtO[9];
+  const double O[9] = {om[0], om[1], om[2], om[1], om[3], om[4], om[2], om[4], om[5]};
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) XtO[3 * r + c] = X[r] * O[c] + X[3 + r] * O[3 + c] + X[6 + r] * O[6 + c];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) M[3 * r + c] = XtO[3 * r] * Y[c] + XtO[3 * r + 1] * Y[3 + c] + XtO[3 * r + 2] * Y[6 + c];
+}
+
+struct PLTerm {
+  double e[2], A[6], B[4], om[3], omr[2], chi;
+};
+SGB_HD void pl_term(const DevGraph& g, int k, const double* pose, const double* lm, bool want_A, bool want_B,
+                    PLTerm& t) {
+  int p = SGB_LDG(&g.pl_p[k]), l = SGB_LDG(&g.pl_l[k]);
+  double x[3] = {pose[3 * p], pose[3 * p + 1], pose[3 * p + 2]};
+  double ln[2] = {lm[2 * l], lm[2 * l + 1]};
+  double z[2] = {SGB_LDG(&g.pl_z[k]), SGB_LDG(&g.pl_z[(size_t)g.n_pl + k])};
+  for (int c = 0; c < 3; ++c) t.om[c] = SGB_LDG(&g.pl_info[(size_t)c * g.n_pl + k]);
+  if (g.jac_numeric) {
+    pl_error_literal(x, ln, z, t.e);
+    pl_jac_numeric(x, ln, z, want_A, want_B, t.A, t.B);
+  } else {
+    double sgn, ca, sa;
+    pl_error_closed(x, ln, z, t.e, &sgn, &ca, &sa);
+    pl_jac_analytic(x, sgn, ca, sa, t.A, t.B);
+  }
+  t.chi = sym2_quad(t.om, t.e);
+  sym2_mul(t.om, t.e, t.omr);
+  t.omr[0] = -t.omr[0];
+  t.omr[1] = -t.omr[1];
+}
+SGB_HD double pl_chi(const DevGraph& g, int k, const double* pose, const double* lm) {
+  int p = SGB_LDG(&g.pl_p[k]), l = SGB_LDG(&g.pl_l[k]);
+  double x[3] = {pose[3 * p], pose[3 * p + 1], pose[3 * p + 2]};
+  double ln[2] = {lm[2 * l], lm[2 * l + 1]};
+  double z[2] = {SGB_LDG(&g.pl_z[k]), SGB_LDG(&g.pl_z[(size_t)g.n_pl + k])};
+  double om[3], e[2];
+  for (int c = 0; c < 3; ++c) om[c] = SGB_LDG(&g.pl_info[(size_t)c * g.n_pl + k]);
+  if (g.jac_numeric) {
+    pl_error_literal(x, ln, z, e);
+  } else {
+    double sgn, ca, sa;
+    pl_error_closed(x, ln, z, e, &sgn, &ca, &sa);
+  }
+  return sym2_quad(om, e);
+}
+// 3x2 block A^T Omega B of a pose-line edge (row-major 3x2)
+SGB_HD void pl_offdiag(const PLTerm& t, double blk[6]) {
+  double AtO[6];  // 3x2 = A^T (2x3)^T * Omega(2x2)
+  for (int r = 0; r < 3; ++r) {
+    AtO[2 * r] = t.A[r] * t.om[0] + t.A[3 + r] * t.om[1];
+    AtO[2 * r + 1] = t.A[r] * t.om[1] + t.A[3 + r] * t.om[2];
+  }
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 2; ++c) blk[2 * r + c] = AtO[2 * r] * t.B[c] + AtO[2 * r + 1] * t.B[2 + c];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// linearise + assemble, pose row: diagonal block, gradient, and every off-diagonal block this pose leads
+SGB_HD void lin_pose_row(const DevGraph& g, int hp, LinAcc& acc) {
+  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double bv[3] = {0, 0, 0};
+  int beg = g.pinc_ptr[hp], end = g.pinc_ptr[hp + 1];
+  for (int it = beg; it < end; ++it) {
+    int packed = SGB_LDG(&g.pinc[it]);
+    int k = packed >> 2, role = (packed >> 1) & 1, type = packed & 1;
+    if (type == 0) {
+      PPTerm t;
+      pp_term(g, k, g.pose, t);
+      int hi = SGB_LDG(&g.pp_hi[k]);
+      if (role == 0) {
+        double M[9];
+        xt_om_y(t.A, t.om, t.A, M);
+        for (int c = 0; c < 9; ++c) H[c] += M[c];
+        for (int r = 0; r < 3; ++r) bv[r] += t.A[r] * t.omr[0] + t.A[3 + r] * t.omr[1] + t.A[6 + r] * t.omr[2];
+        acc.chi += t.chi;
+        acc.chi_r += t.chi_r;
+        int e_ij = SGB_LDG(&g.pp_e_ij[k]);
+        if (e_ij >= 0) {  // both vertices free and this edge leads its vertex pair
+          double blk[9];
+          xt_om_y(t.A, t.om, t.B, blk);  // block (row hi, col hj)
+          for (int d = SGB_LDG(&g.pp_dup[k]); d >= 0; d = SGB_LDG(&g.pp_dup[d])) {
+            PPTerm u;
+            pp_term(g, d, g.pose, u);
+            double m2[9];
+            xt_om_y(u.A, u.om, u.B, m2);
+            if (SGB_LDG(&g.pp_hi[d]) == hi) {
+              for (int c = 0; c < 9; ++c) blk[c] += m2[c];
+            } else {  // duplicate with the opposite orientation contributes its transpose
+              for (int r = 0; r < 3; ++r)
+                for (int c = 0; c < 3; ++c) blk[3 * r + c] += m2[3 * c + r];
+            }
+          }
+          int e_ji = SGB_LDG(&g.pp_e_ji[k]);
+          for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) {
+              g.Hpp.vals[sell_vaddr(e_ij, 9, 3 * r + c)] = blk[3 * r + c];
+              g.Hpp.vals[sell_vaddr(e_ji, 9, 3 * c + r)] = blk[3 * r + c];
+            }
+        }
+      } else {
+        double M[9];
+        xt_om_y(t.B, t.om, t.B, M);
+        for (int c = 0; c < 9; ++c) H[c] += M[c];
+        for (int r = 0; r < 3; ++r) bv[r] += t.B[r] * t.omr[0] + t.B[3 + r] * t.omr[1] + t.B[6 + r] * t.omr[2];
+        if (hi < 0) {  // vertex 0 is fixed: the edge's chi2 is owned here
+          acc.chi += t.chi;
+          acc.chi_r += t.chi_r;
+        }
+      }
+    } else {
+      PLTerm t;
+      int hl = SGB_LDG(&g.pl_hl[k]);
+      pl_term(g, k, g.pose, g.lm, true, hl >= 0, t);
+      double AtO[6];
+      for (int r = 0; r < 3; ++r) {
+        AtO[2 * r] = t.A[r] * t.om[0] + t.A[3 + r] * t.om[1];
+        AtO[2 * r + 1] = t.A[r] * t.om[1] + t.A[3 + r] * t.om[2];
+      }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) H[3 * r + c] += AtO[2 * r] * t.A[c] + AtO[2 * r + 1] * t.A[3 + c];
+      for (int r = 0; r < 3; ++r) bv[r] += t.A[r] * t.omr[0] + t.A[3 + r] * t.omr[1];
+      acc.chi += t.chi;
+      acc.chi_r += t.chi;
+      int e_pl = SGB_LDG(&g.pl_e_pl[k]);
+      if (e_pl >= 0) {
+        double blk[6];
+        pl_offdiag(t, blk);
+        for (int d = SGB_LDG(&g.pl_dup[k]); d >= 0; d = SGB_LDG(&g.pl_dup[d])) {
+          PLTerm u;
+          pl_term(g, d, g.pose, g.lm, true, true, u);
+          double m2[6];
+          pl_offdiag(u, m2);
+          for (int c = 0; c < 6; ++c) blk[c] += m2[c];
+        }
+        int e_lp = SGB_LDG(&g.pl_e_lp[k]);
+        for (int c = 0; c < 6; ++c) {
+          g.Hpl.vals[sell_vaddr(e_pl, 6, c)] = blk[c];
+          g.Hlp.vals[sell_vaddr(e_lp, 6, c)] = blk[c];
+        }
+      }
+    }
+  }
+  int ed = g.hpp_diag[hp];
+  for (int c = 0; c < 9; ++c) g.Hpp.vals[sell_vaddr(ed, 9, c)] = H[c];
+  for (int r = 0; r < 3; ++r) g.b[3 * (size_t)hp + r] = bv[r];
+  acc.maxd = fmax(acc.maxd, fmax(fabs(H[0]), fmax(fabs(H[4]), fabs(H[8]))));
+}
+
+// linearise + assemble, landmark row: 2x2 diagonal block and gradient
+SGB_HD void lin_lm_row(const DevGraph& g, int hl, LinAcc& acc) {
+  double h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0;
+  int beg = g.linc_ptr[hl], end = g.linc_ptr[hl + 1];
+  for (int it = beg; it < end; ++it) {
+    int k = SGB_LDG(&g.linc[it]);
+    PLTerm t;
+    pl_term(g, k, g.pose, g.lm, false, true, t);
+    // B^T Omega B
+    double BtO[4];
+    for (int r = 0; r < 2; ++r) {
+      BtO[2 * r] = t.B[r] * t.om[0] + t.B[2 + r] * t.om[1];
+      BtO[2 * r + 1] = t.B[r] * t.om[1] + t.B[2 + r] * t.om[2];
+    }
+    h11 += BtO[0] * t.B[0] + BtO[1] * t.B[2];
+    h12 += BtO[0] * t.B[1] + BtO[1] * t.B[3];
+    h22 += BtO[2] * t.B[1] + BtO[3] * t.B[3];
+    b0 += t.B[0] * t.omr[0] + t.B[2] * t.omr[1];
+    b1 += t.B[1] * t.omr[0] + t.B[3] * t.omr[1];
+    if (SGB_LDG(&g.pl_hp[k]) < 0) {  // pose fixed: chi2 owned by the landmark row
+      acc.chi += t.chi;
+      acc.chi_r += t.chi;
+    }
+  }
+  g.Hll[hl] = h11;
+  g.Hll[(size_t)g.Lf + hl] = h12;
+  g.Hll[2 * (size_t)g.Lf + hl] = h22;
+  g.b[3 * (size_t)g.Pf + 2 * (size_t)hl] = b0;
+  g.b[3 * (size_t)g.Pf + 2 * (size_t)hl + 1] = b1;
+  acc.maxd = fmax(acc.maxd, fmax(fabs(h11), fabs(h22)));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// trial set-up (BlockSolver::setLambda is applied on the fly; H itself is never modified => restoreDiagonal is free)
+SGB_HD bool setup_lm_row(const DevGraph& g, int hl, double lambda) {
+  double inv[3];
+  bool ok = inv2_spd(g.Hll[hl] + lambda, g.Hll[(size_t)g.Lf + hl], g.Hll[2 * (size_t)g.Lf + hl] + lambda, inv);
+  g.Hll_inv[hl] = inv[0];
+  g.Hll_inv[(size_t)g.Lf + hl] = inv[1];
+  g.Hll_inv[2 * (size_t)g.Lf + hl] = inv[2];
+  return ok;
+}
+// Schur diagonal block S_ii = Hpp_ii + lambda I - sum_l Hpl_il (Hll_l + lambda I)^-1 Hpl_il^T, its inverse (the
+// block-Jacobi preconditioner) and the reduced right-hand side bt_i = b_i - sum_l Hpl_il (Hll_l+lambda I)^-1 b_l
+SGB_HD bool setup_pose_row(const DevGraph& g, int hp, double lambda) {
+  double M[9];
+  int ed = g.hpp_diag[hp];
+  for (int c = 0; c < 9; ++c) M[c] = g.Hpp.vals[sell_vaddr(ed, 9, c)];
+  M[0] += lambda;
+  M[4] += lambda;
+  M[8] += lambda;
+  double bt[3] = {g.b[3 * (size_t)hp], g.b[3 * (size_t)hp + 1], g.b[3 * (size_t)hp + 2]};
+  if (g.Lf > 0) {
+    int slice = hp >> 5, lane = hp & 31;
+    int w = sell_width(g.Hpl, slice);
+    int base = g.Hpl.sbase[slice];
+    for (int k = 0; k < w; ++k) {
+      int e = base + k * 32 + lane;
+      int l = SGB_LDG(&g.Hpl.col[e]);
+      if (l < 0) continue;
+      double B[6];
+      for (int c = 0; c < 6; ++c) B[c] = g.Hpl.vals[sell_vaddr(e, 6, c)];
+      double w11 = g.Hll_inv[l], w12 = g.Hll_inv[(size_t)g.Lf + l], w22 = g.Hll_inv[2 * (size_t)g.Lf + l];
+      double BW[6];
+      for (int r = 0; r < 3; ++r) {
+        BW[2 * r] = B[2 * r] * w11 + B[2 * r + 1] * w12;
+        BW[2 * r + 1] = B[2 * r] * w12 + B[2 * r + 1] * w22;
+      }
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) M[3 * r + c] -= BW[2 * r] * B[2 * c] + BW[2 * r + 1] * B[2 * c + 1];
+      double bl0 = g.b[3 * (size_t)g.Pf + 2 * (size_t)l], bl1 = g.b[3 * (size_t)g.Pf + 2 * (size_t)l + 1];
+      for (int r = 0; r < 3; ++r) bt[r] -= BW[2 * r] * bl0 + BW[2 * r + 1] * bl1;
+    }
+  }
+  double Mi[9];
+  bool ok = inv3_spd(M, Mi);
+  for (int c = 0; c < 9; ++c) g.Minv[(size_t)c * g.Pf + hp] = Mi[c];
+  for (int r = 0; r < 3; ++r) g.bt[3 * (size_t)hp + r] = bt[r];
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// implicit Schur-complement operator  q = (Hpp + lambda I) v - Hpl (Hll + lambda I)^-1 Hpl^T v
+// phase A (landmark-major): t_l = (Hll_l + lambda I)^-1 * sum_i Hpl_il^T v_i       row = Hlp row
+SGB_HD void schur_phaseA_row(const DevGraph& g, int row, const double* v) {
+  int slice = row >> 5, lane = row & 31;
+  int w = sell_width(g.Hlp, slice);
+  int base = g.Hlp.sbase[slice];
+  double u0 = 0, u1 = 0;
+  for (int k = 0; k < w; ++k) {
+    int e = base + k * 32 + lane;
+    int i = SGB_LDG(&g.Hlp.col[e]);
+    if (i < 0) continue;
+    double v0 = SGB_LDCG(&v[3 * (size_t)i]), v1 = SGB_LDCG(&v[3 * (size_t)i + 1]), v2 = SGB_LDCG(&v[3 * (size_t)i + 2]);
+    const double* a = g.Hlp.vals + sell_vaddr(e, 6, 0);
+    u0 += SGB_LDG(a) * v0 + SGB_LDG(a + 64) * v1 + SGB_LDG(a + 128) * v2;
+    u1 += SGB_LDG(a + 32) * v0 + SGB_LDG(a + 96) * v1 + SGB_LDG(a + 160) * v2;
+  }
+  int hl = g.lp_row2h[row];
+  double w11 = g.Hll_inv[hl], w12 = g.Hll_inv[(size_t)g.Lf + hl], w22 = g.Hll_inv[2 * (size_t)g.Lf + hl];
+  g.t[2 * (size_t)hl] = w11 * u0 + w12 * u1;
+  g.t[2 * (size_t)hl + 1] = w12 * u0 + w22 * u1;
+}
+// phase B (pose-major): q_i = lambda v_i + sum_j Hpp_ij v_j - sum_l Hpl_il t_l ; returns v_i . q_i
+SGB_HD double schur_phaseB_row(const DevGraph& g, int hp, const double* v, double lambda, double* q) {
+  int slice = hp >> 5, lane = hp & 31;
+  double vi0 = SGB_LDCG(&v[3 * (size_t)hp]), vi1 = SGB_LDCG(&v[3 * (size_t)hp + 1]), vi2 = SGB_LDCG(&v[3 * (size_t)hp + 2]);
+  double q0 = lambda * vi0, q1 = lambda * vi1, q2 = lambda * vi2;
+  {
+    int w = sell_width(g.Hpp, slice);
+    int base = g.Hpp.sbase[slice];
+    for (int k = 0; k < w; ++k) {
+      int e = base + k * 32 + lane;
+      int j = SGB_LDG(&g.Hpp.col[e]);
+      if (j < 0) continue;
+      double v0 = SGB_LDCG(&v[3 * (size_t)j]), v1 = SGB_LDCG(&v[3 * (size_t)j + 1]), v2 = SGB_LDCG(&v[3 * (size_t)j + 2]);
+      const double* a = g.Hpp.vals + sell_vaddr(e, 9, 0);
+      q0 += SGB_LDG(a) * v0 + SGB_LDG(a + 32) * v1 + SGB_LDG(a + 64) * v2;
+      q1 += SGB_LDG(a + 96) * v0 + SGB_LDG(a + 128) * v1 + SGB_LDG(a + 160) * v2;
+      q2 += SGB_LDG(a + 192) * v0 + SGB_LDG(a + 224) * v1 + SGB_LDG(a + 256) * v2;
+    }
+  }
+  if (g.Lf > 0) {
+    int w = sell_width(g.Hpl, slice);
+    int base = g.Hpl.sbase[slice];
+    for (int k = 0; k < w; ++k) {
+      int e = base + k * 32 + lane;
+      int l = SGB_LDG(&g.Hpl.col[e]);
+      if (l < 0) continue;
+      double t0 = SGB_LDCG(&g.t[2 * (size_t)l]), t1 = SGB_LDCG(&g.t[2 * (size_t)l + 1]);
+      const double* a = g.Hpl.vals + sell_vaddr(e, 6, 0);
+      q0 -= SGB_LDG(a) * t0 + SGB_LDG(a + 32) * t1;
+      q1 -= SGB_LDG(a + 64) * t0 + SGB_LDG(a + 96) * t1;
+      q2 -= SGB_LDG(a + 128) * t0 + SGB_LDG(a + 160) * t1;
+    }
+  }
+  q[3 * (size_t)hp] = q0;
+  q[3 * (size_t)hp + 1] = q1;
+  q[3 * (size_t)hp + 2] = q2;
+  return vi0 * q0 + vi1 * q1 + vi2 * q2;
+}
+// z_i = Minv_i r_i ; returns r_i . z_i
+SGB_HD double precond_row(const DevGraph& g, int hp, const double r[3], double z[3]) {
+  const double* m = g.Minv + hp;
+  size_t s = (size_t)g.Pf;
+  z[0] = SGB_LDG(m) * r[0] + SGB_LDG(m + s) * r[1] + SGB_LDG(m + 2 * s) * r[2];
+  z[1] = SGB_LDG(m + 3 * s) * r[0] + SGB_LDG(m + 4 * s) * r[1] + SGB_LDG(m + 5 * s) * r[2];
+  z[2] = SGB_LDG(m + 6 * s) * r[0] + SGB_LDG(m + 7 * s) * r[1] + SGB_LDG(m + 8 * s) * r[2];
+  return r[0] * z[0] + r[1] * z[1] + r[2] * z[2];
+}
+
+// back-substitution  x_l = (Hll_l + lambda I)^-1 (b_l - sum_i Hpl_il^T x_i)
+SGB_HD void backsub_lm_row(const DevGraph& g, int row) {
+  int slice = row >> 5, lane = row & 31;
+  int w = sell_width(g.Hlp, slice);
+  int base = g.Hlp.sbase[slice];
+  int hl = g.lp_row2h[row];
+  double u0 = g.b[3 * (size_t)g.Pf + 2 * (size_t)hl], u1 = g.b[3 * (size_t)g.Pf + 2 * (size_t)hl + 1];
+  for (int k = 0; k < w; ++k) {
+    int e = base + k * 32 + lane;
+    int i = SGB_LDG(&g.Hlp.col[e]);
+    if (i < 0) continue;
+    double v0 = g.x[3 * (size_t)i], v1 = g.x[3 * (size_t)i + 1], v2 = g.x[3 * (size_t)i + 2];
+    const double* a = g.Hlp.vals + sell_vaddr(e, 6, 0);
+    u0 -= a[0] * v0 + a[64] * v1 + a[128] * v2;
+    u1 -= a[32] * v0 + a[96] * v1 + a[160] * v2;
+  }
+  double w11 = g.Hll_inv[hl], w12 = g.Hll_inv[(size_t)g.Lf + hl], w22 = g.Hll_inv[2 * (size_t)g.Lf + hl];
+  g.x[3 * (size_t)g.Pf + 2 * (size_t)hl] = w11 * u0 + w12 * u1;
+  g.x[3 * (size_t)g.Pf + 2 * (size_t)hl + 1] = w12 * u0 + w22 * u1;
+}
+
+// SparseOptimizer::update for one free vertex into the trial buffers; returns its share of
+// computeScale = sum_j x_j (lambda x_j + b_j)
+SGB_HD double update_pose_row(const DevGraph& g, int hp, double lambda, const double* src, double* dst) {
+  int p = g.pose_of_h[hp];
+  const double* x = g.x + 3 * (size_t)hp;
+  const double* b = g.b + 3 * (size_t)hp;
+  double in[3] = {src[3 * (size_t)p], src[3 * (size_t)p + 1], src[3 * (size_t)p + 2]};
+  double u[3] = {x[0], x[1], x[2]};
+  double out[3];
+  pose_oplus(in, u, out);
+  dst[3 * (size_t)p] = out[0];
+  dst[3 * (size_t)p + 1] = out[1];
+  dst[3 * (size_t)p + 2] = out[2];
+  return u[0] * (lambda * u[0] + b[0]) + u[1] * (lambda * u[1] + b[1]) + u[2] * (lambda * u[2] + b[2]);
+}
+SGB_HD double update_lm_row(const DevGraph& g, int hl, double lambda, const double* src, double* dst) {
+  int l = g.lm_of_h[hl];
+  const double* x = g.x + 3 * (size_t)g.Pf + 2 * (size_t)hl;
+  const double* b = g.b + 3 * (size_t)g.Pf + 2 * (size_t)hl;
+  double in[2] = {src[2 * (size_t)l], src[2 * (size_t)l + 1]};
+  double u[2] = {x[0], x[1]};
+  double out[2];
+  lm_oplus(in, u, out);
+  dst[2 * (size_t)l] = out[0];
+  dst[2 * (size_t)l + 1] = out[1];
+  return u[0] * (lambda * u[0] + b[0]) + u[1] * (lambda * u[1] + b[1]);
+}
+
+}  // namespace sgb

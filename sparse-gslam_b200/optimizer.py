@@ -1,0 +1,184 @@
+"""Host-side mirror of the g2o calls sparse-gslam makes on its optimisers, on top of the C ABI.
+
+Method names follow `g2o::SparseOptimizer` as used by the reference (drone.cpp:146-190,
+submap_loop_closer.cpp:286-288, log_runner.cpp:203-204): initializeOptimization, optimize, push, pop, discardTop,
+computeActiveErrors + activeChi2. The graph is handed over as SoA arrays (graphgen.Graph or anything with the same
+attributes); the real C++ drop-in is sparse-gslam_b200/adapter/sgb_g2o_adapter.h.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+
+
+class SgbError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"sgb status {status}: {msg}")
+        self.status = status
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def pack_graph(g):
+    keep = []
+
+    def arr(a, dt):
+        a = np.ascontiguousarray(a, dtype=dt)
+        keep.append(a)
+        return _p(a)
+
+    s = capi.GraphSoA()
+    s.n_poses = int(g.pose_est.shape[0])
+    s.pose_id = arr(g.pose_id, np.int32)
+    s.pose_est = arr(g.pose_est, np.float64)
+    s.pose_fixed = arr(g.pose_fixed, np.uint8)
+    s.n_landmarks = int(g.lm_est.shape[0])
+    s.lm_id = arr(g.lm_id, np.int32)
+    s.lm_est = arr(g.lm_est, np.float64)
+    s.lm_fixed = arr(g.lm_fixed, np.uint8)
+    s.n_pp = int(g.pp_i.shape[0])
+    s.pp_i = arr(g.pp_i, np.int32)
+    s.pp_j = arr(g.pp_j, np.int32)
+    s.pp_z = arr(g.pp_z, np.float64)
+    s.pp_info = arr(g.pp_info, np.float64)
+    s.pp_phi = arr(g.pp_phi, np.float64)
+    s.pp_seq = arr(g.pp_seq, np.int64)
+    s.n_pl = int(g.pl_pose.shape[0])
+    s.pl_pose = arr(g.pl_pose, np.int32)
+    s.pl_lm = arr(g.pl_lm, np.int32)
+    s.pl_z = arr(g.pl_z, np.float64)
+    s.pl_info = arr(g.pl_info, np.float64)
+    s.pl_seq = arr(g.pl_seq, np.int64)
+    return s, keep
+
+
+class SparseOptimizerB200:
+    """One optimiser handle = one of the reference's two graphs (LandmarkGraph.opt / PoseGraph.opt, graphs.h:19-40)."""
+
+    def __init__(self, algo=capi.ALGO_LM, jacobian_mode=capi.JAC_G2O_NUMERIC, pcg_tolerance=1e-10, pcg_max_iters=0,
+                 device=-1, lm_user_lambda=0.0):
+        self.L = capi.load()
+        if self.L.sgb_device_count() <= 0:
+            raise SgbError(capi.ERR_NO_DEVICE, "no CUDA device: the backend has no CPU path")
+        opt = capi.Options()
+        self.L.sgb_default_options(C.byref(opt))
+        opt.device = device
+        opt.jacobian_mode = jacobian_mode
+        opt.pcg_tolerance = pcg_tolerance
+        opt.pcg_max_iters = pcg_max_iters
+        opt.lm_user_lambda = lm_user_lambda
+        self.algo = algo
+        self.h = C.c_void_p()
+        st = self.L.sgb_create(C.byref(opt), C.byref(self.h))
+        if st != capi.OK:
+            raise SgbError(st, "sgb_create failed")
+        self.g = None
+        self.P = self.Lm = 0
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.sgb_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != capi.OK:
+            raise SgbError(st, self.L.sgb_last_error(self.h).decode())
+
+    # g2o: addVertex/addEdge for the whole graph + initializeOptimization()
+    def initialize_optimization(self, g) -> bool:
+        s, keep = pack_graph(g)
+        st = self.L.sgb_set_graph(self.h, C.byref(s))
+        if st == capi.ERR_NOT_INITIALIZED:
+            return False
+        self._check(st)
+        self.g = g
+        self.P, self.Lm = s.n_poses, s.n_landmarks
+        return True
+
+    def structure(self):
+        info = capi.StructureInfo()
+        self._check(self.L.sgb_get_structure_info(self.h, C.byref(info)))
+        nf, nb = info.n_free, info.n_blocks
+        kind, index, off = (np.zeros(nf, np.int32) for _ in range(3))
+        row, col, nr, nc = (np.zeros(nb, np.int32) for _ in range(4))
+        ph, lh = np.zeros(self.P, np.int32), np.zeros(self.Lm, np.int32)
+        self._check(self.L.sgb_get_structure(self.h, _p(kind), _p(index), _p(off), _p(row), _p(col), _p(nr), _p(nc),
+                                             _p(ph), _p(lh)))
+        return dict(n_free=nf, n_blocks=nb, dim=info.scalar_dim, kind=kind, index=index, offset=off, row=row, col=col,
+                    nrows=nr, ncols=nc, pose_hidx=ph, lm_hidx=lh, block_values=info.block_values,
+                    n_free_poses=info.n_free_poses, n_free_landmarks=info.n_free_landmarks,
+                    n_active_pp=info.n_active_pp, n_active_pl=info.n_active_pl)
+
+    def linearize(self):
+        st = self.structure()
+        b = np.zeros(st["dim"])
+        H = np.zeros(st["block_values"])
+        chi = np.zeros(2)
+        self._check(self.L.sgb_linearize(self.h, _p(b), _p(H), _p(chi)))
+        return dict(b=b, H=H, chi2=chi)
+
+    def solve_once(self, lam):
+        st = self.structure()
+        x = np.zeros(st["dim"])
+        it = C.c_int32()
+        rel = C.c_double()
+        rc = self.L.sgb_solve_once(self.h, float(lam), _p(x), C.byref(it), C.byref(rel))
+        if rc not in (capi.OK, capi.ERR_SOLVE_FAILED):
+            self._check(rc)
+        return rc == capi.OK, x, it.value, rel.value
+
+    def optimize(self, iters, online=False, resident=False):
+        """Returns (g2o return value, per-iteration stats)."""
+        stats = (capi.IterStat * max(1, iters))()
+        done = C.c_int32(-1)
+        if resident:
+            st = self.L.sgb_optimize_resident(self.h, self.algo, iters, C.byref(done), C.cast(stats, C.c_void_p))
+        else:
+            st = self.L.sgb_optimize(self.h, self.algo, iters, int(online), C.byref(done), C.cast(stats, C.c_void_p))
+        if st == capi.ERR_NOT_INITIALIZED:
+            return -1, []
+        self._check(st)
+        n = done.value
+        return n, [stats[i].as_dict() for i in range(max(n, 0))]
+
+    def estimates(self):
+        p = np.zeros((self.P, 3))
+        l = np.zeros((self.Lm, 2))
+        self._check(self.L.sgb_get_estimates(self.h, _p(p), _p(l)))
+        return p, l
+
+    def set_estimates(self, poses, lms):
+        p = np.ascontiguousarray(poses, np.float64)
+        l = np.ascontiguousarray(lms, np.float64)
+        self._check(self.L.sgb_set_estimates(self.h, _p(p), _p(l)))
+
+    def push(self):
+        self._check(self.L.sgb_push(self.h))
+
+    def pop(self):
+        self._check(self.L.sgb_pop(self.h))
+
+    def discard_top(self):
+        self._check(self.L.sgb_discard_top(self.h))
+
+    def active_chi2(self):
+        """computeActiveErrors(); returns (activeChi2, activeRobustChi2)."""
+        c = np.zeros(2)
+        self._check(self.L.sgb_chi2(self.h, _p(c)))
+        return float(c[0]), float(c[1])
+
+    def timings(self):
+        t = capi.Timings()
+        self._check(self.L.sgb_get_timings(self.h, C.byref(t)))
+        return t.as_dict()

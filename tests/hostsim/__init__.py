@@ -1,0 +1,109 @@
+"""ctypes binding of the host-side test harness (tests/hostsim/hostsim.cpp). TEST INFRASTRUCTURE ONLY."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from sparse_gslam_b200 import capi
+from sparse_gslam_b200.optimizer import _p, pack_graph
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SO = os.path.join(HERE, "libhostsim.so")
+_lib = None
+
+
+def build():
+    srcs = [os.path.join(HERE, "hostsim.cpp"), os.path.join(ROOT, "sparse-gslam_b200", "csrc", "sgb_structure.cpp")]
+    deps = srcs + [os.path.join(ROOT, "sparse-gslam_b200", "csrc", f) for f in
+                   ("sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h")]
+    if os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
+        return SO
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", SO] + srcs)
+    return SO
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = C.CDLL(build())
+        vp = C.c_void_p
+        L.hs_create.restype = vp
+        L.hs_create.argtypes = [C.POINTER(capi.GraphSoA), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int)]
+        L.hs_destroy.argtypes = [vp]
+        L.hs_error.argtypes = [vp]
+        L.hs_error.restype = C.c_char_p
+        L.hs_info.argtypes = [vp, C.POINTER(capi.StructureInfo)]
+        L.hs_structure.argtypes = [vp] + [vp] * 9
+        L.hs_sell_stats.argtypes = [vp, vp]
+        L.hs_linearize.argtypes = [vp, vp, vp, vp]
+        L.hs_solve_once.argtypes = [vp, C.c_double, vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.hs_optimize.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.hs_get_estimates.argtypes = [vp, vp, vp]
+        L.hs_chi2.argtypes = [vp, vp]
+        _lib = L
+    return _lib
+
+
+class HostSim:
+    def __init__(self, g, jac_numeric=True, tol=1e-10, maxit=0):
+        self.L = lib()
+        s, keep = pack_graph(g)
+        st = C.c_int()
+        self.h = C.c_void_p(self.L.hs_create(C.byref(s), int(jac_numeric), tol, maxit, C.byref(st)))
+        self.status = st.value
+        self.error = self.L.hs_error(self.h).decode()
+        self.P, self.Lm = s.n_poses, s.n_landmarks
+
+    def __del__(self):
+        try:
+            self.L.hs_destroy(self.h)
+        except Exception:
+            pass
+
+    def structure(self):
+        info = capi.StructureInfo()
+        self.L.hs_info(self.h, C.byref(info))
+        nf, nb = info.n_free, info.n_blocks
+        kind, index, off = (np.zeros(nf, np.int32) for _ in range(3))
+        row, col, nr, nc = (np.zeros(nb, np.int32) for _ in range(4))
+        ph, lh = np.zeros(self.P, np.int32), np.zeros(self.Lm, np.int32)
+        self.L.hs_structure(self.h, _p(kind), _p(index), _p(off), _p(row), _p(col), _p(nr), _p(nc), _p(ph), _p(lh))
+        return dict(n_free=nf, n_blocks=nb, dim=info.scalar_dim, kind=kind, index=index, offset=off, row=row, col=col,
+                    nrows=nr, ncols=nc, pose_hidx=ph, lm_hidx=lh, block_values=info.block_values)
+
+    def sell_stats(self):
+        o = np.zeros(6, np.int64)
+        self.L.hs_sell_stats(self.h, _p(o))
+        return dict(hpp=(int(o[0]), int(o[1])), hpl=(int(o[2]), int(o[3])), hlp=(int(o[4]), int(o[5])))
+
+    def linearize(self):
+        st = self.structure()
+        b, H, chi = np.zeros(st["dim"]), np.zeros(st["block_values"]), np.zeros(2)
+        self.L.hs_linearize(self.h, _p(b), _p(H), _p(chi))
+        return dict(b=b, H=H, chi2=chi)
+
+    def solve_once(self, lam):
+        st = self.structure()
+        x = np.zeros(st["dim"])
+        it, rel = C.c_int(), C.c_double()
+        flag = self.L.hs_solve_once(self.h, float(lam), _p(x), C.byref(it), C.byref(rel))
+        return flag, x, it.value, rel.value
+
+    def optimize(self, iters, algo):
+        stats = (capi.IterStat * max(1, iters))()
+        n = self.L.hs_optimize(self.h, algo, iters, C.cast(stats, C.c_void_p))
+        return n, [stats[i].as_dict() for i in range(max(n, 0))]
+
+    def estimates(self):
+        p, l = np.zeros((self.P, 3)), np.zeros((self.Lm, 2))
+        self.L.hs_get_estimates(self.h, _p(p), _p(l))
+        return p, l
+
+    def chi2(self):
+        c = np.zeros(2)
+        self.L.hs_chi2(self.h, _p(c))
+        return float(c[0]), float(c[1])

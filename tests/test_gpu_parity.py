@@ -1,0 +1,187 @@
+"""GPU tier (-m gpu): the CUDA path through the C ABI (libsgb.so) against the CPU oracle on the same seeded inputs.
+
+Tolerances: structure bit-exact; H, b, chi2 <= 1e-12 relative (analytic) / 1e-9 (g2o-numeric, see test_oracle.py on the
+1e-7 Jacobian noise of central differences); final poses / landmarks / chi2 <= 1e-6 relative (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+
+from oracle.cpu_oracle import ALGO_GN, ALGO_LM, JAC_ANALYTIC, JAC_G2O_NUMERIC, Oracle
+from sparse_gslam_b200 import SparseOptimizerB200, capi
+from sparse_gslam_b200 import graphgen as gg
+
+pytestmark = pytest.mark.gpu
+
+STRUCT_KEYS = ("kind", "index", "offset", "row", "col", "nrows", "ncols", "pose_hidx", "lm_hidx")
+JAC = {capi.JAC_G2O_NUMERIC: JAC_G2O_NUMERIC, capi.JAC_ANALYTIC: JAC_ANALYTIC}
+
+
+def rel_err(a, b):
+    scale = max(1.0, float(np.abs(b).max()))
+    return float(np.abs(a - b).max()) / scale
+
+
+def pose_err(a, b):
+    d = a - b
+    d[:, 2] = gg.wrap(d[:, 2])
+    return float(np.abs(d).max()) / max(1.0, float(np.abs(b[:, :2]).max()))
+
+
+def converged_prefix(stats):
+    """Iterations before the LM plateau (where accept/reject depends on rounding noise)."""
+    n = 0
+    for s in stats:
+        if s["trials"] != 1:
+            break
+        n += 1
+    return n
+
+
+@pytest.mark.parametrize("name", ["small", "c4", "c1"])
+@pytest.mark.parametrize("jac", [capi.JAC_G2O_NUMERIC, capi.JAC_ANALYTIC])
+def test_structure_linearize_chi2(name, jac):
+    g = gg.make(name)
+    o = Oracle(g)
+    assert o.initialize_optimization()
+    opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=jac)
+    assert opt.initialize_optimization(g)
+    so, sg = o.structure(), opt.structure()
+    for k in ("n_free", "n_blocks", "dim"):
+        assert so[k] == sg[k]
+    for k in STRUCT_KEYS:
+        assert np.array_equal(so[k], sg[k]), k
+    lo, lg = o.linearize(JAC[jac]), opt.linearize()
+    tol = 1e-9 if jac == capi.JAC_G2O_NUMERIC else 1e-12
+    assert rel_err(lg["H"], lo["H"]) < tol
+    assert rel_err(lg["b"], lo["b"]) < tol
+    np.testing.assert_allclose(lg["chi2"], lo["chi2"], rtol=1e-12)
+    np.testing.assert_allclose(opt.active_chi2(), o.chi2(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_damped_solve_matches_exact_cholesky(name):
+    g = gg.make(name)
+    o = Oracle(g)
+    o.initialize_optimization()
+    opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC, pcg_tolerance=1e-12)
+    opt.initialize_optimization(g)
+    lam0 = 1e-5 * np.abs(o.dense_hessian(o.linearize(JAC_ANALYTIC))).diagonal().max() if name == "small" else 200.0
+    for lam in (lam0, 10 * lam0):
+        ok, xo = o.solve_once(lam, JAC_ANALYTIC)
+        okg, xg, iters, rel = opt.solve_once(lam)
+        assert ok and okg and iters > 0 and rel <= 1e-12
+        assert rel_err(xg, xo) < 1e-8
+
+
+@pytest.mark.parametrize("name,jac", [("small", capi.JAC_ANALYTIC), ("small", capi.JAC_G2O_NUMERIC),
+                                      ("c4", capi.JAC_G2O_NUMERIC), ("c1", capi.JAC_G2O_NUMERIC),
+                                      ("c1", capi.JAC_ANALYTIC), ("c3", capi.JAC_ANALYTIC)])
+def test_lm15_final_state_parity(name, jac):
+    """optimize(15) as drone.cpp:150 does: final poses, landmarks and chi2 within 1e-6 relative of the oracle."""
+    g = gg.make(name)
+    o = Oracle(g)
+    o.initialize_optimization()
+    n_o, s_o = o.optimize(15, ALGO_LM, JAC[jac])
+    opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=jac)
+    opt.initialize_optimization(g)
+    opt.push()
+    n_g, s_g = opt.optimize(15)
+    assert n_g >= 1
+    # identical LM decisions while the iteration is still making progress
+    k = min(converged_prefix(s_o), converged_prefix(s_g))
+    assert k >= 3
+    for a, b in zip(s_o[:k], s_g[:k]):
+        assert a["trials"] == b["trials"]
+        np.testing.assert_allclose(b["chi2"], a["chi2"], rtol=1e-6)
+        np.testing.assert_allclose(b["lambda_"], a["lambda_"], rtol=1e-4)
+    po, lo = o.estimates()
+    pg, lg = opt.estimates()
+    assert pose_err(pg, po) < 1e-6
+    assert rel_err(lg, lo) < 1e-6
+    np.testing.assert_allclose(opt.active_chi2()[0], o.chi2()[0], rtol=1e-6)
+    # caller protocol: pop() restores the pre-optimisation estimates (drone.cpp:180)
+    opt.pop()
+    pg, lg = opt.estimates()
+    np.testing.assert_array_equal(pg, g.pose_est)
+    np.testing.assert_array_equal(lg, g.lm_est)
+
+
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_gn20_dcs_pose_graph_parity(name):
+    """optimize(20) with DCS closures as submap_loop_closer.cpp:287 does."""
+    g = gg.make(name)
+    gp = g.pose_only(phi=g.meta.get("dcs_phi", 1.0))
+    o = Oracle(gp)
+    o.initialize_optimization()
+    n_o, s_o = o.optimize(20, ALGO_GN)
+    opt = SparseOptimizerB200(capi.ALGO_GN, pcg_tolerance=1e-12)
+    opt.initialize_optimization(gp)
+    n_g, s_g = opt.optimize(20)
+    assert n_o == n_g == 20
+    po, _ = o.estimates()
+    pg, _ = opt.estimates()
+    assert pose_err(pg, po) < 1e-6
+    np.testing.assert_allclose(opt.active_chi2(), o.chi2(), rtol=1e-6)
+
+
+def test_zero_noise_fixed_point_and_recovery():
+    g = gg.make_small(seed=1, noise_free=True)
+    g.pose_est = g.pose_gt.copy()
+    g.lm_est = g.lm_gt.copy()
+    opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
+    opt.initialize_optimization(g)
+    assert opt.active_chi2()[0] < 1e-18
+    opt.optimize(3)
+    p, l = opt.estimates()
+    assert np.abs(p - g.pose_gt).max() < 1e-9 and np.abs(l - g.lm_gt).max() < 1e-9
+    rng = np.random.default_rng(0)
+    p0 = g.pose_gt + rng.normal(0, 0.03, g.pose_gt.shape)
+    p0[0] = g.pose_gt[0]
+    opt.set_estimates(p0, g.lm_gt + rng.normal(0, 0.02, g.lm_gt.shape))
+    opt.optimize(15)
+    p, l = opt.estimates()
+    assert np.abs(p[:, :2] - g.pose_gt[:, :2]).max() < 1e-6
+
+
+def test_singular_system_fails_like_g2o():
+    """GN on a rank-deficient system: solve fails -> optimize returns 0 (g2o SolverResult::Fail)."""
+    from test_oracle import tiny_graph
+    g = tiny_graph()
+    g.pose_fixed = np.array([1, 1], np.uint8)
+    g.pl_pose = g.pl_pose[:1]; g.pl_lm = g.pl_lm[:1]; g.pl_z = g.pl_z[:1]; g.pl_seq = g.pl_seq[:1]
+    g.pl_info = np.array([[900.0, 0.0, 0.0]])
+    opt = SparseOptimizerB200(capi.ALGO_GN, jacobian_mode=capi.JAC_ANALYTIC)
+    assert opt.initialize_optimization(g)
+    n, _ = opt.optimize(3)
+    assert n == 0
+    opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
+    opt.initialize_optimization(g)
+    n, _ = opt.optimize(3)
+    assert n >= 1
+
+
+def test_not_initialised_returns_minus_one():
+    opt = SparseOptimizerB200()
+    n, _ = opt.optimize(5)
+    assert n == -1
+
+
+def test_c5_slice_properties():
+    """Size-independent checks on a C5-shaped graph too large for a per-entry comparison to be the point:
+    accepted LM steps never increase chi2, the result agrees with the oracle, and two handles can run concurrently."""
+    g = gg.make_c5(rows=60, cols=60)
+    o = Oracle(g)
+    o.initialize_optimization()
+    o.optimize(8, ALGO_LM, JAC_ANALYTIC)
+    a = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
+    b = SparseOptimizerB200(capi.ALGO_GN)
+    a.initialize_optimization(g)
+    b.initialize_optimization(g.pose_only(phi=1.0))
+    c0 = a.active_chi2()[1]
+    n, st = a.optimize(8)
+    b.optimize(2)
+    chis = [c0] + [s["chi2"] for s in st]
+    assert all(y <= x * (1 + 1e-12) for x, y in zip(chis, chis[1:]))
+    po, lo = o.estimates()
+    pg, lg = a.estimates()
+    assert pose_err(pg, po) < 1e-6 and rel_err(lg, lo) < 1e-6

@@ -268,7 +268,9 @@ def test_unobserved_direction_fails_solve():
     """KAT 10: GN on a graph whose Hessian is singular -> solve fails -> optimize returns 0 (Fail)."""
     g = tiny_graph()
     g.pose_fixed = np.array([1, 1], np.uint8)  # only the line is free ...
-    g.pl_info = np.array([[900.0, 0.0, 0.0], [1000.0, 0.0, 0.0]])  # ... and its angle is never measured
+    # ... it is seen once, from the pose at the origin, and its angle is not measured: H = diag(900, 0)
+    g.pl_pose = g.pl_pose[:1]; g.pl_lm = g.pl_lm[:1]; g.pl_z = g.pl_z[:1]; g.pl_seq = g.pl_seq[:1]
+    g.pl_info = np.array([[900.0, 0.0, 0.0]])
     o = Oracle(g)
     assert o.initialize_optimization()
     assert o.structure()["dim"] == 2

@@ -1,0 +1,172 @@
+"""CPU tier: the product's host-side symbolic phase (sgb_structure.cpp) and the kernel row bodies (sgb_rows.h, run
+serially by tests/hostsim) against the oracle. No GPU, no compute call into libsgb.so."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import hostsim
+from oracle.cpu_oracle import ALGO_GN, ALGO_LM, JAC_ANALYTIC, JAC_G2O_NUMERIC, Oracle
+from sparse_gslam_b200 import capi
+from sparse_gslam_b200 import graphgen as gg
+
+STRUCT_KEYS = ("kind", "index", "offset", "row", "col", "nrows", "ncols", "pose_hidx", "lm_hidx")
+
+
+def assert_same_structure(so, sh):
+    for k in ("n_free", "n_blocks", "dim"):
+        assert so[k] == sh[k], k
+    for k in STRUCT_KEYS:
+        assert np.array_equal(so[k], sh[k]), k
+
+
+@pytest.mark.parametrize("maker", [lambda: gg.make_small(seed=0), lambda: gg.make_small(seed=7, P=120, L=20, E_l=300, n_closures=10),
+                                   lambda: gg.make_c4_window(1003), lambda: gg.make_c5(rows=20, cols=20),
+                                   lambda: gg.make_c1().pose_only(phi=10.0)])
+def test_structure_bit_exact(maker):
+    """The ordered block list (row, col, nrows, ncols), scalar offsets and Hessian indices equal the oracle's."""
+    g = maker()
+    o = Oracle(g)
+    assert o.initialize_optimization()
+    hs = hostsim.HostSim(g)
+    assert hs.status == capi.OK, hs.error
+    assert_same_structure(o.structure(), hs.structure())
+
+
+def test_structure_with_fixed_landmark_and_inactive_vertices():
+    g = gg.make_small(seed=2)
+    g.lm_fixed = g.lm_fixed.copy()
+    g.lm_fixed[3] = 1
+    g.pose_fixed = g.pose_fixed.copy()
+    g.pose_fixed[5] = 1
+    # a pose and a landmark that no edge touches
+    g.pose_est = np.vstack([g.pose_est, [[50.0, 50.0, 0.0]]])
+    g.pose_gt = np.vstack([g.pose_gt, [[50.0, 50.0, 0.0]]])
+    g.pose_id = np.append(g.pose_id, g.pose_id.max() + 1).astype(np.int32)
+    g.pose_fixed = np.append(g.pose_fixed, 0).astype(np.uint8)
+    g.lm_est = np.vstack([g.lm_est, [[3.0, 0.1]]])
+    g.lm_gt = np.vstack([g.lm_gt, [[3.0, 0.1]]])
+    g.lm_id = np.append(g.lm_id, g.lm_id.max() + 1).astype(np.int32)
+    g.lm_fixed = np.append(g.lm_fixed, 0).astype(np.uint8)
+    o = Oracle(g)
+    assert o.initialize_optimization()
+    hs = hostsim.HostSim(g)
+    assert hs.status == capi.OK
+    so, sh = o.structure(), hs.structure()
+    assert_same_structure(so, sh)
+    assert sh["pose_hidx"][-1] == -1 and sh["lm_hidx"][-1] == -1 and sh["lm_hidx"][3] == -1 and sh["pose_hidx"][5] == -1
+    for numeric in (True, False):
+        hs = hostsim.HostSim(g, jac_numeric=numeric)
+        lo = o.linearize(JAC_G2O_NUMERIC if numeric else JAC_ANALYTIC)
+        lh = hs.linearize()
+        np.testing.assert_allclose(lh["H"], lo["H"], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(lh["b"], lo["b"], rtol=1e-12, atol=1e-8)
+        np.testing.assert_allclose(lh["chi2"], lo["chi2"], rtol=1e-12)
+
+
+def test_duplicate_and_reversed_edges_share_a_block():
+    g = gg.make_small(seed=1)
+    k = 10  # duplicate one odometry edge, once in the same and once in the opposite direction
+    z = g.pp_z[k]
+    c, s = np.cos(z[2]), np.sin(z[2])
+    zinv = np.array([-(c * z[0] + s * z[1]), (s * z[0] - c * z[1]), -z[2]])
+    g.pp_i = np.concatenate([g.pp_i, [g.pp_i[k], g.pp_j[k]]]).astype(np.int32)
+    g.pp_j = np.concatenate([g.pp_j, [g.pp_j[k], g.pp_i[k]]]).astype(np.int32)
+    g.pp_z = np.vstack([g.pp_z, z + [0.01, -0.01, 0.002], zinv])
+    g.pp_info = np.vstack([g.pp_info, g.pp_info[k] * 0.5, g.pp_info[k] * 0.25])
+    g.pp_phi = np.concatenate([g.pp_phi, [0.0, 0.0]])
+    top = max(g.pp_seq.max(), g.pl_seq.max())
+    g.pp_seq = np.concatenate([g.pp_seq, [top + 1, top + 2]])
+    # duplicate a pose-line edge too
+    g.pl_pose = np.append(g.pl_pose, g.pl_pose[4]).astype(np.int32)
+    g.pl_lm = np.append(g.pl_lm, g.pl_lm[4]).astype(np.int32)
+    g.pl_z = np.vstack([g.pl_z, g.pl_z[4] + [0.01, 0.003]])
+    g.pl_info = np.vstack([g.pl_info, g.pl_info[4] * 0.7])
+    g.pl_seq = np.append(g.pl_seq, top + 3)
+    o = Oracle(g)
+    o.initialize_optimization()
+    hs = hostsim.HostSim(g, jac_numeric=False)
+    assert_same_structure(o.structure(), hs.structure())
+    lo, lh = o.linearize(JAC_ANALYTIC), hs.linearize()
+    np.testing.assert_allclose(lh["H"], lo["H"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(lh["b"], lo["b"], rtol=1e-12, atol=1e-8)
+
+
+def test_rows_linearize_and_solve_match_oracle(small_graph):
+    g = small_graph
+    o = Oracle(g)
+    o.initialize_optimization()
+    for numeric, jac in ((True, JAC_G2O_NUMERIC), (False, JAC_ANALYTIC)):
+        hs = hostsim.HostSim(g, jac_numeric=numeric, tol=1e-12)
+        lo, lh = o.linearize(jac), hs.linearize()
+        np.testing.assert_allclose(lh["H"], lo["H"], rtol=1e-12, atol=1e-9)
+        np.testing.assert_allclose(lh["b"], lo["b"], rtol=1e-12, atol=1e-8)
+        for lam in (0.0, 0.5, 300.0):
+            ok, xo = o.solve_once(lam, jac)
+            flag, xh, iters, rel = hs.solve_once(lam)
+            assert ok and flag == 0 and iters > 0
+            np.testing.assert_allclose(xh, xo, rtol=1e-8, atol=1e-10)
+
+
+def test_rows_lm_and_gn_match_oracle():
+    g = gg.make_small(seed=5, n_closures=8)
+    o = Oracle(g)
+    o.initialize_optimization()
+    hs = hostsim.HostSim(g, jac_numeric=False, tol=1e-12)
+    n1, s1 = o.optimize(6, ALGO_LM, JAC_ANALYTIC)
+    n2, s2 = hs.optimize(6, capi.ALGO_LM)
+    assert n1 == n2
+    for a, b in zip(s1, s2):
+        assert a["trials"] == b["trials"]
+        np.testing.assert_allclose(b["chi2"], a["chi2"], rtol=1e-9)
+        np.testing.assert_allclose(b["lambda_"], a["lambda_"], rtol=1e-6)
+    po, lo = o.estimates()
+    ph, lh = hs.estimates()
+    np.testing.assert_allclose(ph, po, atol=1e-8)
+    np.testing.assert_allclose(lh, lo, atol=1e-8)
+    gp = g.pose_only(phi=1.0)
+    o = Oracle(gp)
+    o.initialize_optimization()
+    hs = hostsim.HostSim(gp, tol=1e-12)
+    assert o.optimize(20, ALGO_GN)[0] == hs.optimize(20, capi.ALGO_GN)[0] == 20
+    np.testing.assert_allclose(hs.estimates()[0], o.estimates()[0], atol=1e-9)
+
+
+def test_unsupported_and_invalid_graphs():
+    g = gg.make_small(seed=0)
+    bad = g.copy()
+    bad.pp_j = bad.pp_j.copy()
+    bad.pp_j[0] = 10_000
+    assert hostsim.HostSim(bad).status == capi.ERR_INVALID
+    bad = g.copy()
+    bad.lm_id = (bad.lm_id - gg.LANDMARK_ID0).astype(np.int32)  # landmark ids below pose ids
+    assert hostsim.HostSim(bad).status == capi.ERR_UNSUPPORTED
+    empty = g.copy()
+    for k in ("pp_i", "pp_j", "pp_z", "pp_info", "pp_phi", "pp_seq", "pl_pose", "pl_lm", "pl_z", "pl_info", "pl_seq"):
+        setattr(empty, k, getattr(empty, k)[:0])
+    assert hostsim.HostSim(empty).status == capi.ERR_NOT_INITIALIZED
+
+
+def test_library_exports_every_declared_symbol():
+    """libsgb.so loads without a GPU and exports everything include/sgb_capi.h declares (no compute calls here)."""
+    import re
+    from sparse_gslam_b200 import build
+    build.build()
+    L = capi.load()
+    hdr = open(os.path.join(os.path.dirname(capi.HERE), "include", "sgb_capi.h")).read()
+    declared = sorted(set(re.findall(r"^(?:sgb_status|const char\*|int32_t|void)\s+(sgb_[a-z0-9_]+)\s*\(", hdr, re.M)))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in sgb_capi.h but not exported"
+    assert sorted(capi.EXPORTS) == declared
+    assert b"sm_100a" in L.sgb_version()
+    opt = capi.Options()
+    L.sgb_default_options(C.byref(opt))
+    assert opt.pcg_tolerance == 1e-10 and opt.lm_max_trials == 10 and opt.jacobian_mode == capi.JAC_G2O_NUMERIC
+    if L.sgb_device_count() == 0:  # no GPU here: creation must fail loudly, not fall back
+        h = C.c_void_p()
+        assert L.sgb_create(None, C.byref(h)) == capi.ERR_NO_DEVICE
+        from sparse_gslam_b200 import SgbError, SparseOptimizerB200
+        with pytest.raises(SgbError):
+            SparseOptimizerB200()
