@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- LM iterations/s of the pose-graph optimisation hot path (BASELINE.json metric).
+
+One "step" = one `optimize(15)` of the workload graph, the call the reference makes per key-frame
+(reference src/sparse_gslam/src/drone.cpp:150). Default workload = C5, the 1M-pose grid world of BASELINE.json
+(the configuration the metric "LM iterations/sec at 1/2/4/8 B200" is quoted on; it fits one GPU), LM with the
+analytic pose-line Jacobian. `--workload c1|c2|c3|c4` select the other BASELINE configs.
+
+  value  : LM iterations/s with the graph resident in HBM (sgb_optimize_resident), CUDA-event timed, max over ranks
+  e2e    : the same metric through the C ABI with HOST buffers: sgb_set_graph (host symbolic phase + H2D of the
+           whole graph) + sgb_optimize + sgb_get_estimates (D2H) inside the timed region
+  roofline: dominant kernel k_pcg; achieved = algorithmic bytes / CUDA-event time of the launches
+  cpu_baseline / --impl reference: the CPU oracle (g2o-equivalent restatement, 1 thread) on a bounded sample
+
+Launch: `python bench.py --gpus N --steps K --warmup W` (N>1 under torchrun, one rank per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+LM_ITERS = 15  # reference: drone.cpp:150 optimize(15, ...)
+GN_ITERS = 20  # reference: submap_loop_closer.cpp:287 optimize(20)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_workload(name, rank=0, world=1):
+    from sparse_gslam_b200 import capi
+    from sparse_gslam_b200 import graphgen as gg
+    name = name.lower()
+    if name == "c5":
+        g = gg.make_c5()
+        return g, capi.ALGO_LM, LM_ITERS, "C5 synthetic 1M-pose grid world (P=1e6, L=2e5, E_o~1.5e6, E_l=4e6), LM-15"
+    if name == "c5s":  # small C5 used by CI-style quick runs
+        g = gg.make_c5(rows=200, cols=200)
+        return g, capi.ALGO_LM, LM_ITERS, "C5-shaped 200x200 grid world (P=4e4), LM-15"
+    if name in ("c1", "c2", "c3", "c4"):
+        g = gg.make(name)
+        return g, capi.ALGO_LM, LM_ITERS, f"{name.upper()} {g.name} (P={g.P}, L={g.L}, E_o={g.n_pp}, E_l={g.n_pl}), LM-15"
+    if name in ("c1gn", "c2gn", "c3gn"):
+        g0 = gg.make(name[:2])
+        g = g0.pose_only(phi=g0.meta.get("dcs_phi", 1.0))
+        return g, capi.ALGO_GN, GN_ITERS, f"{name[:2].upper()} pose graph + DCS closures (P={g.P}, E_o={g.n_pp}), GN-20"
+    raise SystemExit(f"unknown workload {name}")
+
+
+def graph_h2d_bytes(g):
+    tot = 0
+    for k in ("pose_id", "pose_est", "pose_fixed", "lm_id", "lm_est", "lm_fixed", "pp_i", "pp_j", "pp_z", "pp_info",
+              "pp_phi", "pp_seq", "pl_pose", "pl_lm", "pl_z", "pl_info", "pl_seq"):
+        tot += getattr(g, k).nbytes
+    return int(tot)
+
+
+def pcg_bytes_per_iteration(st):
+    """Algorithmic bytes of one PCG iteration on the implicit Schur complement:
+    Hpp blocks 76 B (72 values + 4 index), Hpl blocks 52 B read twice (pose-major and landmark-major pass),
+    (Hll+lambda I)^-1 24 B and t 2x16 B per landmark, vectors 384 B per pose."""
+    P, L = st["n_free_poses"], st["n_free_landmarks"]
+    nnzb_pp = P + 2 * st["n_pairs_pp"]
+    n_pl = st["n_pairs_pl"]
+    return 76 * nnzb_pp + 2 * 52 * n_pl + 56 * L + 384 * P
+
+
+def cpu_reference_run(workload, steps, warmup, quiet=False):
+    """The reference arm / cpu_baseline: CPU oracle (g2o-equivalent restatement, serial like the reference build)
+    on a bounded sample of the workload; LM iterations/s scaled linearly by pose count to the full workload."""
+    from oracle.cpu_oracle import ALGO_GN, ALGO_LM, JAC_G2O_NUMERIC, Oracle
+    from sparse_gslam_b200 import capi
+    from sparse_gslam_b200 import graphgen as gg
+    if workload == "c5":
+        g = gg.make_c5(rows=100, cols=100)
+        full_P = 1_000_000
+        sample = ("C5 generator at 100x100 cells (P=1e4, L=2e3, E_l=4e4), LM-15 with g2o-numeric Jacobians and exact "
+                  "sparse LDLt; iterations/s scaled by P_sample/P_full = 1/100 (linear extrapolation, optimistic for a "
+                  "direct solver)")
+        algo, iters = ALGO_LM, LM_ITERS
+    else:
+        g, a, iters, _ = make_workload(workload)
+        full_P = g.P
+        algo = ALGO_LM if a == capi.ALGO_LM else ALGO_GN
+        sample = f"full {workload} graph, optimize({iters}) with g2o-numeric Jacobians and exact sparse LDLt"
+    times, its = [], 0
+    for s in range(warmup + steps):
+        o = Oracle(g)
+        o.initialize_optimization()
+        t0 = time.perf_counter()
+        n, _ = o.optimize(iters, algo, JAC_G2O_NUMERIC)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+            its += max(n, 0)
+        if sum(times) > 60:
+            break
+    total = sum(times)
+    scale = g.P / full_P
+    value = its / total * scale if total > 0 else 0.0
+    return dict(value=value, unit="LM iterations/s", cores=1, kind="port", sample=sample, sample_ms_per_step=1e3 * total / max(1, len(times)),
+                sample_steps=len(times), host_cores=os.cpu_count())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("SGB_WORKLOAD", "c5"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--pcg-tol", type=float, default=1e-10)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    warmup = max(int(os.environ.get("SGB_MIN_WARMUP", "3")), args.warmup)  # SGB_MIN_WARMUP=1 only for ncu captures
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = cpu_reference_run(args.workload, max(1, args.steps), 1)
+        line = {"impl": "reference", "metric": "LM iterations/s", "value": r["value"], "unit": "LM iterations/s",
+                "n_gpus": args.gpus, "steps": r["sample_steps"], "warmup": 1, "ms_per_step": r["sample_ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": args.workload}, "cpu_baseline": r,
+                "e2e": {"value": r["value"], "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sparse_gslam_b200 import SparseOptimizerB200, capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the backend has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    g, algo, iters, desc = make_workload(args.workload, rank, world)
+    opt = SparseOptimizerB200(algo, jacobian_mode=capi.JAC_ANALYTIC, pcg_tolerance=args.pcg_tol, device=local_rank)
+    t0 = time.perf_counter()
+    assert opt.initialize_optimization(g)
+    t_setgraph = time.perf_counter() - t0
+    st = opt.structure()
+    # distinct off-diagonal pairs from the block list
+    kinds = st["kind"]
+    nP = st["n_free_poses"]
+    offd = st["row"] != st["col"]
+    st["n_pairs_pp"] = int(np.sum(offd & (st["col"] < nP)))
+    st["n_pairs_pl"] = int(np.sum(offd & (st["col"] >= nP)))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- resident (device-timed) ----------------
+    for _ in range(warmup):
+        opt.optimize(iters, resident=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    tot_iters = 0
+    agg = dict(linearize_ms=0.0, setup_ms=0.0, pcg_ms=0.0, update_ms=0.0, total_ms=0.0, pcg_iters=0, trials=0,
+               linearizations=0, kernel_launches=0)
+    wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        n, stats = opt.optimize(iters, resident=True)
+        tot_iters += max(n, 0)
+        t = opt.timings()
+        for k in agg:
+            agg[k] += t[k]
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    dev_ms = agg["total_ms"]
+    if world > 1:
+        tt = torch.tensor([dev_ms, float(tot_iters)], dtype=torch.float64, device="cuda")
+        mx = tt.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = tt.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms_max = float(mx[0])
+        total_iters_all = float(sm[1])
+    else:
+        dev_ms_max, total_iters_all = dev_ms, float(tot_iters)
+    value = total_iters_all / (dev_ms_max * 1e-3) if dev_ms_max > 0 else 0.0
+
+    # ---------------- end to end through the C ABI with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        h2d = graph_h2d_bytes(g)
+        d2h = int(g.pose_est.nbytes + g.lm_est.nbytes)
+        e_iters, e_steps = 0, max(1, min(args.steps, 3))
+        barrier()
+        te0 = time.perf_counter()
+        for _ in range(e_steps):
+            assert opt.initialize_optimization(g)   # host symbolic phase + H2D of the whole graph
+            n, _ = opt.optimize(iters)
+            opt.estimates()                          # D2H of the result
+            e_iters += max(n, 0)
+        barrier()
+        te = time.perf_counter() - te0
+        if world > 1:
+            tt = torch.tensor([te], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            te = float(tt[0])
+            ti = torch.tensor([float(e_iters)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(ti, op=dist.ReduceOp.SUM)
+            e_iters = float(ti[0])
+        e2e = {"value": e_iters / te, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "ms_per_step": 1e3 * te / e_steps, "steps": e_steps}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peaks()
+    b_iter = pcg_bytes_per_iteration(st)
+    pcg_bytes = b_iter * agg["pcg_iters"]
+    pcg_s = agg["pcg_ms"] * 1e-3
+    achieved = pcg_bytes / pcg_s / 1e9 if pcg_s > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "pcg_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_pcg", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_pcg_iteration": b_iter, "pcg_iterations": agg["pcg_iters"],
+                "pcg_launches": agg["trials"], "share_of_step": agg["pcg_ms"] / dev_ms if dev_ms > 0 else None}
+    line = {
+        "metric": "LM iterations/s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": dev_ms_max / max(1, args.steps), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "algorithm": "LM" if algo == capi.ALGO_LM else "GN+DCS",
+                   "iterations_per_step": iters, "jacobian": "analytic", "pcg_tolerance": args.pcg_tol,
+                   "l2": "inputs larger than L2 (Hessian + edge arrays >> 126 MB)" if g.P >= 200000 else
+                         "graph fits L2 (latency-bound config; see DESIGN.md)",
+                   "parallelism": "1 GPU" if world == 1 else f"{world} GPUs"},
+        "optimize_ms": dev_ms_max / max(1, args.steps),
+        "lm_iterations": tot_iters, "wall_s": wall,
+        "phases_ms": {k: agg[k] for k in ("linearize_ms", "setup_ms", "pcg_ms", "update_ms", "total_ms")},
+        "lm_trials": agg["trials"], "set_graph_s": t_setgraph,
+        "gpu_launches": int(agg["kernel_launches"]),
+        "clocks": clocks, "roofline": roofline,
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference_run(args.workload, 1, 0)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
