@@ -128,6 +128,19 @@ typedef struct sgb_timings {
   int64_t kernel_launches;  /* kernels launched by this library */
 } sgb_timings;
 
+/* this rank's share of a row-block partitioned graph */
+typedef struct sgb_partition_info {
+  int32_t world, rank;
+  int32_t n_poses;          /* free pose rows owned */
+  int32_t n_landmarks;      /* free landmarks owned */
+  int32_t n_pp, n_pl;       /* local edges (incident to an owned row) */
+  int32_t n_pp_owned, n_pl_owned; /* edges whose chi2 is accounted on this rank */
+  int64_t halo_pose_gathers;     /* off-rank pose-vector entries gathered per PCG iteration */
+  int64_t halo_landmark_gathers; /* off-rank landmark-vector entries gathered per PCG iteration */
+  int64_t hpp_entries, hpl_entries, hlp_entries; /* SELL entries including padding */
+  int64_t hpp_blocks, hpl_blocks;                /* stored blocks */
+} sgb_partition_info;
+
 typedef struct sgb_handle sgb_handle;
 
 const char* sgb_version(void);
@@ -143,6 +156,16 @@ const char* sgb_last_error(const sgb_handle* h);
  * builds g2o's index mapping (active vertices sorted by id, fixed -> -1) and block
  * structure on the host, the symbolic scatter map, and uploads everything. */
 sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g);
+/* Multi-GPU, one process per GPU: every rank passes the SAME whole graph; rank r keeps the free-pose rows
+ * [r*ceil(Pf/world), ...) of the reduced system and the landmarks first observed from them. Afterwards the ranks
+ * exchange sgb_comm_get_handle() blobs (64 bytes each, e.g. with torch.distributed.all_gather) and call
+ * sgb_comm_connect() with all of them in rank order; the PCG then gathers halo entries and reduces its dot
+ * products directly through NVLink peer memory. Every rank must issue the same sequence of compute calls.
+ * The reference has no counterpart (single process). world <= 8. */
+sgb_status sgb_set_graph_partitioned(sgb_handle* h, const sgb_graph_soa* g, int32_t world, int32_t rank);
+sgb_status sgb_comm_get_handle(sgb_handle* h, void* out64);
+sgb_status sgb_comm_connect(sgb_handle* h, const void* handles /* world * 64 bytes, rank order */, int32_t world);
+sgb_status sgb_get_partition_info(const sgb_handle* h, sgb_partition_info* out);
 sgb_status sgb_get_structure_info(const sgb_handle* h, sgb_structure_info* out);
 /* Hessian order: hessian index -> (kind 0 pose / 1 landmark, array index, scalar offset);
  * block list in column-major, row-ascending order (the order g2o's SparseBlockMatrix iterates);

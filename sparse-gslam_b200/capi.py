@@ -16,7 +16,8 @@ EXPORTS = [
     "sgb_version", "sgb_device_count", "sgb_default_options", "sgb_create", "sgb_destroy", "sgb_last_error",
     "sgb_set_graph", "sgb_get_structure_info", "sgb_get_structure", "sgb_linearize", "sgb_solve_once", "sgb_optimize",
     "sgb_step", "sgb_get_estimates", "sgb_set_estimates", "sgb_push", "sgb_pop", "sgb_discard_top", "sgb_chi2",
-    "sgb_get_timings", "sgb_optimize_resident",
+    "sgb_get_timings", "sgb_optimize_resident", "sgb_set_graph_partitioned", "sgb_comm_get_handle", "sgb_comm_connect",
+    "sgb_get_partition_info",
 ]
 
 
@@ -61,6 +62,17 @@ class Timings(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class PartitionInfo(C.Structure):
+    _fields_ = [("world", C.c_int32), ("rank", C.c_int32), ("n_poses", C.c_int32), ("n_landmarks", C.c_int32),
+                ("n_pp", C.c_int32), ("n_pl", C.c_int32), ("n_pp_owned", C.c_int32), ("n_pl_owned", C.c_int32),
+                ("halo_pose_gathers", C.c_int64), ("halo_landmark_gathers", C.c_int64), ("hpp_entries", C.c_int64),
+                ("hpl_entries", C.c_int64), ("hlp_entries", C.c_int64), ("hpp_blocks", C.c_int64),
+                ("hpl_blocks", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -82,6 +94,10 @@ def load() -> C.CDLL:
     L.sgb_last_error.argtypes = [vp]
     L.sgb_last_error.restype = C.c_char_p
     L.sgb_set_graph.argtypes = [vp, C.POINTER(GraphSoA)]
+    L.sgb_set_graph_partitioned.argtypes = [vp, C.POINTER(GraphSoA), C.c_int32, C.c_int32]
+    L.sgb_comm_get_handle.argtypes = [vp, vp]
+    L.sgb_comm_connect.argtypes = [vp, vp, C.c_int32]
+    L.sgb_get_partition_info.argtypes = [vp, C.POINTER(PartitionInfo)]
     L.sgb_get_structure_info.argtypes = [vp, C.POINTER(StructureInfo)]
     L.sgb_get_structure.argtypes = [vp] + [vp] * 9
     L.sgb_linearize.argtypes = [vp, vp, vp, vp]

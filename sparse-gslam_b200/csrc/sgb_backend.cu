@@ -15,6 +15,7 @@
 
 #include "../../include/sgb_capi.h"
 #include "sgb_kernels.cuh"
+#include "sgb_partition.h"
 #include "sgb_structure.h"
 
 using namespace sgb;
@@ -35,8 +36,15 @@ struct sgb_handle {
   std::string err;
   bool has_graph = false;
   Structure S;
+  LocalPlan LP;
   DevGraph G;
   std::vector<void*> allocs;
+  // peer-mapped arena: estimates (2 buffers), p, x_p, t, b_l, Hll_inv, mailbox -- same offsets on every rank
+  char* arena = nullptr;
+  size_t arena_bytes = 0;
+  size_t off_pose[2] = {0, 0}, off_lm[2] = {0, 0}, off_p = 0, off_xp = 0, off_t = 0, off_bl = 0, off_hllinv = 0, off_mbox = 0;
+  void* peer_base[kMaxRanks] = {nullptr};
+  bool connected = false;
   DevScalars* d_sc = nullptr;
   DevScalars* h_sc = nullptr;  // pinned
   double* d_part_p = nullptr;
@@ -101,6 +109,12 @@ sgb_status upload_sell(sgb_handle* h, Sell* out, const HostSell& s, int NC) {
 }
 
 void free_graph(sgb_handle* h) {
+  for (int r = 0; r < kMaxRanks; ++r) {
+    if (h->peer_base[r] && r != h->LP.rank) cudaIpcCloseMemHandle(h->peer_base[r]);
+    h->peer_base[r] = nullptr;
+  }
+  h->connected = false;
+  h->arena = nullptr;
   for (void* p : h->allocs) cudaFree(p);
   h->allocs.clear();
   h->stack.clear();
@@ -114,16 +128,20 @@ sgb_status need_graph(sgb_handle* h) {
     h->err = "0 vertices to optimize, maybe forgot to call initializeOptimization()";
     return SGB_ERR_NOT_INITIALIZED;
   }
+  if (h->LP.world > 1 && !h->connected) {
+    h->err = "partitioned graph: call sgb_comm_connect() with every rank's handle first";
+    return SGB_ERR_COMM;
+  }
   return SGB_OK;
 }
 
 // ---- launches (all on the handle's stream) --------------------------------------------------------------
 sgb_status launch_linearize(sgb_handle* h) {
   DevGraph& G = h->G;
-  int gp = grid_for(G.Pf), gl = grid_for(G.Lf);
-  if (G.Pf > 0) k_lin_pose<<<gp, kThreads, 0, h->stream>>>(G, h->d_part_p);
-  if (G.Lf > 0) k_lin_lm<<<gl, kThreads, 0, h->stream>>>(G, h->d_part_l);
-  h->tm.kernel_launches += (G.Pf > 0) + (G.Lf > 0);
+  int gp = grid_for(G.nP), gl = grid_for(G.nL);
+  if (G.nP > 0) k_lin_pose<<<gp, kThreads, 0, h->stream>>>(G, h->d_part_p);
+  if (G.nL > 0) k_lin_lm<<<gl, kThreads, 0, h->stream>>>(G, h->d_part_l);
+  h->tm.kernel_launches += (G.nP > 0) + (G.nL > 0);
   h->tm.linearizations++;
   SGB_CUDA(cudaGetLastError());
   return SGB_OK;
@@ -131,17 +149,21 @@ sgb_status launch_linearize(sgb_handle* h) {
 sgb_status launch_finalize_lin(sgb_handle* h, int init_lambda) {
   DevGraph& G = h->G;
   double tau = h->opt.lm_tau > 0 ? h->opt.lm_tau : 1e-5;
-  k_finalize_lin<<<1, kThreads, 0, h->stream>>>(h->d_sc, h->d_part_p, G.Pf > 0 ? grid_for(G.Pf) : 0, h->d_part_l,
-                                                G.Lf > 0 ? grid_for(G.Lf) : 0, init_lambda, tau, h->opt.lm_user_lambda);
+  k_finalize_lin<<<1, kThreads, 0, h->stream>>>(G, h->d_sc, h->d_part_p, G.nP > 0 ? grid_for(G.nP) : 0, h->d_part_l,
+                                                G.nL > 0 ? grid_for(G.nL) : 0, init_lambda, tau, h->opt.lm_user_lambda);
   h->tm.kernel_launches++;
   SGB_CUDA(cudaGetLastError());
   return SGB_OK;
 }
 sgb_status launch_setup(sgb_handle* h, double lambda_override, int use_override) {
   DevGraph& G = h->G;
-  if (G.Lf > 0) k_setup_lm<<<grid_for(G.Lf), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
-  if (G.Pf > 0) k_setup_pose<<<grid_for(G.Pf), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
-  h->tm.kernel_launches += (G.Pf > 0) + (G.Lf > 0);
+  if (G.nL > 0) k_setup_lm<<<grid_for(G.nL), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
+  if (G.world > 1) {  // pose rows read (Hll + lambda I)^-1 of landmarks owned by other ranks
+    k_xbarrier<<<1, 32, 0, h->stream>>>(G, h->d_sc);
+    h->tm.kernel_launches++;
+  }
+  if (G.nP > 0) k_setup_pose<<<grid_for(G.nP), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
+  h->tm.kernel_launches += (G.nP > 0) + (G.nL > 0);
   SGB_CUDA(cudaGetLastError());
   return SGB_OK;
 }
@@ -152,7 +174,7 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   unsigned long long* bar = h->d_bar;
   PcgParams prm;
   prm.tol = h->opt.pcg_tolerance > 0 ? h->opt.pcg_tolerance : 1e-10;
-  prm.maxit = h->opt.pcg_max_iters > 0 ? h->opt.pcg_max_iters : std::max(100, 4 * 3 * G.Pf);
+  prm.maxit = h->opt.pcg_max_iters > 0 ? h->opt.pcg_max_iters : std::max(100, 4 * 3 * h->S.Pf);
   prm.lambda_override = lambda_override;
   prm.use_override = use_override;
   SGB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), h->stream));
@@ -161,22 +183,24 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   h->tm.kernel_launches++;
   return SGB_OK;
 }
-sgb_status launch_backsub_update(sgb_handle* h, const double* pose_src, double* pose_dst, const double* lm_src,
-                                 double* lm_dst, double lambda_override, int use_override) {
+sgb_status launch_backsub_update(sgb_handle* h, int dst, double lambda_override, int use_override) {
   DevGraph& G = h->G;
-  if (G.Lf > 0) {
-    k_backsub<<<grid_for(G.Lf), kThreads, 0, h->stream>>>(G);
+  if (G.nL > 0) {
+    k_backsub<<<grid_for(G.nL), kThreads, 0, h->stream>>>(G);
     h->tm.kernel_launches++;
   }
-  k_update<<<grid_for(G.Pf + G.Lf), kThreads, 0, h->stream>>>(G, h->d_sc, pose_src, pose_dst, lm_src, lm_dst, h->d_part_p,
-                                                             lambda_override, use_override);
+  k_update<<<grid_for(G.nP + G.nL), kThreads, 0, h->stream>>>(G, h->d_sc, dst, h->d_part_p, lambda_override, use_override);
   h->tm.kernel_launches++;
+  if (G.world > 1) {  // every replica of the estimates has received every owner's rows
+    k_xbarrier<<<1, 32, 0, h->stream>>>(G, h->d_sc);
+    h->tm.kernel_launches++;
+  }
   SGB_CUDA(cudaGetLastError());
   return SGB_OK;
 }
-sgb_status launch_chi2(sgb_handle* h, const double* pose, const double* lm) {
+sgb_status launch_chi2(sgb_handle* h, int buf) {
   DevGraph& G = h->G;
-  k_chi2_edges<<<grid_for(G.n_pp + G.n_pl), kThreads, 0, h->stream>>>(G, pose, lm, h->d_part_e);
+  k_chi2_edges<<<grid_for(G.n_pp_owned + G.n_pl_owned), kThreads, 0, h->stream>>>(G, buf, h->d_part_e);
   h->tm.kernel_launches++;
   SGB_CUDA(cudaGetLastError());
   return SGB_OK;
@@ -209,12 +233,13 @@ sgb_status do_step(sgb_handle* h, int algo, int iteration, int* result, sgb_iter
     SGB_CUDA(cudaEventRecord(h->ev.e[2], s));
     if ((st = launch_pcg(h, 0.0, 1)) != SGB_OK) return st;
     SGB_CUDA(cudaEventRecord(h->ev.e[3], s));
-    if ((st = launch_backsub_update(h, G.pose, G.pose, G.lm, G.lm, 0.0, 1)) != SGB_OK) return st;
+    if ((st = launch_backsub_update(h, G.cur, 0.0, 1)) != SGB_OK) return st;
+    k_gn_control<<<1, 32, 0, s>>>(G, h->d_sc);
+    h->tm.kernel_launches++;
+    SGB_CUDA(cudaGetLastError());
     SGB_CUDA(cudaEventRecord(h->ev.e[4], s));
     if ((st = read_scalars(h)) != SGB_OK) return st;
-    bool ok = (h->h_sc->pcg_flag != 2) && (h->h_sc->setup_fail == 0);
-    SGB_CUDA(cudaMemsetAsync(&h->d_sc->setup_fail, 0, sizeof(int32_t), s));
-    *result = ok ? SGB_RESULT_OK : SGB_RESULT_FAIL;
+    *result = h->h_sc->result == 1 ? SGB_RESULT_OK : SGB_RESULT_FAIL;
     pcg_total = h->h_sc->pcg_iters;
     trials = 1;
     t_lin = ev_ms(h->ev.e[0], h->ev.e[1]);
@@ -230,10 +255,10 @@ sgb_status do_step(sgb_handle* h, int algo, int iteration, int* result, sgb_iter
       SGB_CUDA(cudaEventRecord(h->ev.e[2], s));
       if ((st = launch_pcg(h, 0.0, 0)) != SGB_OK) return st;
       SGB_CUDA(cudaEventRecord(h->ev.e[3], s));
-      if ((st = launch_backsub_update(h, G.pose, G.pose_trial, G.lm, G.lm_trial, 0.0, 0)) != SGB_OK) return st;
-      if ((st = launch_chi2(h, G.pose_trial, G.lm_trial)) != SGB_OK) return st;
-      k_lm_control<<<1, kThreads, 0, s>>>(h->d_sc, h->d_part_e, grid_for(G.n_pp + G.n_pl), h->d_part_p,
-                                          grid_for(G.Pf + G.Lf), max_trials);
+      if ((st = launch_backsub_update(h, G.cur ^ 1, 0.0, 0)) != SGB_OK) return st;
+      if ((st = launch_chi2(h, G.cur ^ 1)) != SGB_OK) return st;
+      k_lm_control<<<1, kThreads, 0, s>>>(G, h->d_sc, h->d_part_e, grid_for(G.n_pp_owned + G.n_pl_owned), h->d_part_p,
+                                          grid_for(G.nP + G.nL), max_trials);
       h->tm.kernel_launches++;
       SGB_CUDA(cudaGetLastError());
       SGB_CUDA(cudaEventRecord(h->ev.e[4], s));
@@ -244,10 +269,7 @@ sgb_status do_step(sgb_handle* h, int algo, int iteration, int* result, sgb_iter
       t_upd += ev_ms(h->ev.e[3], h->ev.e[4]);
       pcg_total += h->h_sc->pcg_iters;
       first = false;
-      if (h->h_sc->accepted) {  // discardTop: the trial estimates become current
-        std::swap(G.pose, G.pose_trial);
-        std::swap(G.lm, G.lm_trial);
-      }
+      if (h->h_sc->accepted) G.cur ^= 1;  // discardTop: the trial estimates become current (on every rank)
       if (!h->h_sc->again) break;
     }
     trials = h->h_sc->trials;
@@ -391,95 +413,179 @@ void sgb_destroy(sgb_handle* h) {
 
 const char* sgb_last_error(const sgb_handle* h) { return h ? h->err.c_str() : "null handle"; }
 
-sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g) {
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void fill_peer_tables(sgb_handle* h) {
+  DevGraph& G = h->G;
+  for (int r = 0; r < kMaxRanks; ++r) {
+    char* base = (char*)h->peer_base[r];
+    if (!base) base = h->arena;  // unconnected slots alias this rank (never dereferenced: owners < world)
+    for (int bsel = 0; bsel < 2; ++bsel) {
+      G.pose_buf[bsel][r] = (double*)(base + h->off_pose[bsel]);
+      G.lm_buf[bsel][r] = (double*)(base + h->off_lm[bsel]);
+    }
+    G.p[r] = (double*)(base + h->off_p);
+    G.x_p[r] = (double*)(base + h->off_xp);
+    G.t[r] = (double*)(base + h->off_t);
+    G.b_l[r] = (double*)(base + h->off_bl);
+    G.Hll_inv[r] = (double*)(base + h->off_hllinv);
+    G.mbox[r] = (Mailbox*)(base + h->off_mbox);
+  }
+}
+
+static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int world, int rank) {
   if (!h || !g) return SGB_ERR_INVALID;
   SGB_CUDA(cudaSetDevice(h->device));
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   free_graph(h);
   sgb_status st = build_structure(*g, h->S, h->err);
   if (st != SGB_OK) return st;
+  st = partition(h->S, world, rank, h->LP, h->err);
+  if (st != SGB_OK) return st;
   const Structure& S = h->S;
+  const LocalPlan& P = h->LP;
   DevGraph& G = h->G;
   std::memset(&G, 0, sizeof G);
-  G.P_all = S.P_all; G.L_all = S.L_all; G.Pf = S.Pf; G.Lf = S.Lf; G.n_pp = S.n_pp; G.n_pl = S.n_pl;
+  G.world = world; G.rank = rank; G.nP = P.nP; G.nL = P.nL; G.capP = P.capP; G.capL = P.capL;
+  G.P_all = S.P_all; G.L_all = S.L_all; G.n_pp = P.n_pp; G.n_pl = P.n_pl;
+  G.n_pp_owned = P.n_pp_owned; G.n_pl_owned = P.n_pl_owned;
   G.has_robust = S.has_robust ? 1 : 0;
   G.jac_numeric = h->opt.jacobian_mode == SGB_JAC_G2O_NUMERIC ? 1 : 0;
-#define UP(field, vec) if ((st = upload(h, &G.field, vec)) != SGB_OK) return st
-  // estimates (+ trial buffers and the pristine copy used by sgb_optimize_resident)
+  G.cur = 0;
+  // ---- arena (identical layout on every rank: sizes depend on global quantities only)
   size_t np = 3 * (size_t)S.P_all, nl = 2 * (size_t)S.L_all;
-  if ((st = dalloc(h, &G.pose, np)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.lm, nl)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.pose_trial, np)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.lm_trial, nl)) != SGB_OK) return st;
+  size_t off = 0;
+  auto take = [&](size_t doubles) { size_t o = off; off = align256(off + std::max<size_t>(doubles, 1) * sizeof(double)); return o; };
+  h->off_pose[0] = take(np); h->off_pose[1] = take(np);
+  h->off_lm[0] = take(nl); h->off_lm[1] = take(nl);
+  h->off_p = take(3 * (size_t)P.capP); h->off_xp = take(3 * (size_t)P.capP);
+  h->off_t = take(2 * (size_t)P.capL); h->off_bl = take(2 * (size_t)P.capL); h->off_hllinv = take(3 * (size_t)P.capL);
+  h->off_mbox = off; off = align256(off + sizeof(Mailbox));
+  h->arena_bytes = off;
+  if ((st = dalloc(h, &h->arena, h->arena_bytes)) != SGB_OK) return st;
+  SGB_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+  for (int r = 0; r < kMaxRanks; ++r) h->peer_base[r] = nullptr;
+  h->peer_base[rank] = h->arena;
+  fill_peer_tables(h);
+  h->connected = (world == 1);
   if ((st = dalloc(h, &h->d_pose0, np)) != SGB_OK) return st;
   if ((st = dalloc(h, &h->d_lm0, nl)) != SGB_OK) return st;
-  if (np) {
-    SGB_CUDA(cudaMemcpyAsync(G.pose, g->pose_est, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    SGB_CUDA(cudaMemcpyAsync(G.pose_trial, G.pose, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    SGB_CUDA(cudaMemcpyAsync(h->d_pose0, G.pose, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  for (int bsel = 0; bsel < 2; ++bsel) {
+    if (np) SGB_CUDA(cudaMemcpyAsync(G.pose_buf[bsel][rank], g->pose_est, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (nl) SGB_CUDA(cudaMemcpyAsync(G.lm_buf[bsel][rank], g->lm_est, nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   }
-  if (nl) {
-    SGB_CUDA(cudaMemcpyAsync(G.lm, g->lm_est, nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    SGB_CUDA(cudaMemcpyAsync(G.lm_trial, G.lm, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    SGB_CUDA(cudaMemcpyAsync(h->d_lm0, G.lm, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  }
-  UP(pose_of_h, S.pose_of_h); UP(lm_of_h, S.lm_of_h);
-  UP(pp_i, S.pp_i); UP(pp_j, S.pp_j); UP(pp_hi, S.pp_hi); UP(pp_hj, S.pp_hj);
-  UP(pp_e_ij, S.pp_e_ij); UP(pp_e_ji, S.pp_e_ji); UP(pp_dup, S.pp_dup);
-  UP(pl_p, S.pl_p); UP(pl_l, S.pl_l); UP(pl_hp, S.pl_hp); UP(pl_hl, S.pl_hl);
-  UP(pl_e_pl, S.pl_e_pl); UP(pl_e_lp, S.pl_e_lp); UP(pl_dup, S.pl_dup);
-  UP(pinc_ptr, S.pinc_ptr); UP(pinc, S.pinc); UP(linc_ptr, S.linc_ptr); UP(linc, S.linc);
-  UP(hpp_diag, S.hpp_diag); UP(lp_row2h, S.lp_row2h); UP(lp_h2row, S.lp_h2row);
-  {  // edge data, component-major, active edges in insertion order; EdgeSE2::setMeasurement caches the inverse
-    std::vector<double> zinv(3 * (size_t)S.n_pp), info(6 * (size_t)S.n_pp), phi(S.n_pp, 0.0);
-    for (int k = 0; k < S.n_pp; ++k) {
-      int s = S.pp_src[k];
+  if (np) SGB_CUDA(cudaMemcpyAsync(h->d_pose0, g->pose_est, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (nl) SGB_CUDA(cudaMemcpyAsync(h->d_lm0, g->lm_est, nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+#define UP(field, vec) if ((st = upload(h, &G.field, vec)) != SGB_OK) return st
+  UP(pose_of_l, P.pose_of_l); UP(lm_of_l, P.lm_of_l);
+  UP(pp_i, P.pp_i); UP(pp_j, P.pp_j); UP(pp_hi, P.pp_hi); UP(pp_hj, P.pp_hj);
+  UP(pp_e_ij, P.pp_e_ij); UP(pp_e_ji, P.pp_e_ji); UP(pp_dup, P.pp_dup);
+  UP(pl_p, P.pl_p); UP(pl_l, P.pl_l); UP(pl_hp, P.pl_hp); UP(pl_hl, P.pl_hl);
+  UP(pl_e_pl, P.pl_e_pl); UP(pl_e_lp, P.pl_e_lp); UP(pl_dup, P.pl_dup);
+  UP(pinc_ptr, P.pinc_ptr); UP(pinc, P.pinc); UP(linc_ptr, P.linc_ptr); UP(linc, P.linc);
+  UP(hpp_diag, P.hpp_diag); UP(lp_row2l, P.lp_row2l);
+  {  // edge data, component-major, local edges; EdgeSE2::setMeasurement caches the inverse
+    std::vector<double> zinv(3 * (size_t)P.n_pp), info(6 * (size_t)P.n_pp), phi(P.n_pp, 0.0);
+    for (int k = 0; k < P.n_pp; ++k) {
+      int s = S.pp_src[P.pp_g[k]];
       double x = g->pp_z[3 * (size_t)s], y = g->pp_z[3 * (size_t)s + 1], th = g->pp_z[3 * (size_t)s + 2];
       double thi = normalize_theta(-th);
       double c = std::cos(thi), sn = std::sin(thi);
       zinv[k] = c * (-x) - sn * (-y);
-      zinv[(size_t)S.n_pp + k] = sn * (-x) + c * (-y);
-      zinv[2 * (size_t)S.n_pp + k] = thi;
-      for (int c6 = 0; c6 < 6; ++c6) info[(size_t)c6 * S.n_pp + k] = g->pp_info[6 * (size_t)s + c6];
+      zinv[(size_t)P.n_pp + k] = sn * (-x) + c * (-y);
+      zinv[2 * (size_t)P.n_pp + k] = thi;
+      for (int c6 = 0; c6 < 6; ++c6) info[(size_t)c6 * P.n_pp + k] = g->pp_info[6 * (size_t)s + c6];
       if (g->pp_phi) phi[k] = g->pp_phi[s];
     }
     UP(pp_zinv, zinv); UP(pp_info, info); UP(pp_phi, phi);
-    std::vector<double> z(2 * (size_t)S.n_pl), linfo(3 * (size_t)S.n_pl);
-    for (int k = 0; k < S.n_pl; ++k) {
-      int s = S.pl_src[k];
+    std::vector<double> z(2 * (size_t)P.n_pl), linfo(3 * (size_t)P.n_pl);
+    for (int k = 0; k < P.n_pl; ++k) {
+      int s = S.pl_src[P.pl_g[k]];
       z[k] = g->pl_z[2 * (size_t)s];
-      z[(size_t)S.n_pl + k] = g->pl_z[2 * (size_t)s + 1];
-      for (int c3 = 0; c3 < 3; ++c3) linfo[(size_t)c3 * S.n_pl + k] = g->pl_info[3 * (size_t)s + c3];
+      z[(size_t)P.n_pl + k] = g->pl_z[2 * (size_t)s + 1];
+      for (int c3 = 0; c3 < 3; ++c3) linfo[(size_t)c3 * P.n_pl + k] = g->pl_info[3 * (size_t)s + c3];
     }
     UP(pl_z, z); UP(pl_info, linfo);
   }
 #undef UP
-  if ((st = upload_sell(h, &G.Hpp, S.Hpp, 9)) != SGB_OK) return st;
-  if ((st = upload_sell(h, &G.Hpl, S.Hpl, 6)) != SGB_OK) return st;
-  if ((st = upload_sell(h, &G.Hlp, S.Hlp, 6)) != SGB_OK) return st;
-  size_t n3 = 3 * (size_t)S.Pf, n2 = 2 * (size_t)S.Lf;
-  if ((st = dalloc(h, &G.Hll, 3 * (size_t)S.Lf)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.Hll_inv, 3 * (size_t)S.Lf)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.b, n3 + n2)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.x, n3 + n2)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.Minv, 9 * (size_t)S.Pf)) != SGB_OK) return st;
+  if ((st = upload_sell(h, &G.Hpp, P.Hpp, 9)) != SGB_OK) return st;
+  if ((st = upload_sell(h, &G.Hpl, P.Hpl, 6)) != SGB_OK) return st;
+  if ((st = upload_sell(h, &G.Hlp, P.Hlp, 6)) != SGB_OK) return st;
+  size_t n3 = 3 * (size_t)P.nP, n2 = 2 * (size_t)P.nL;
+  if ((st = dalloc(h, &G.Hll, 3 * (size_t)P.nL)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.b_p, n3)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.x_l, n2)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.Minv, 9 * (size_t)P.nP)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.bt, n3)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.r, n3)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.z, n3)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.p, n3)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.q, n3)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.t, n2)) != SGB_OK) return st;
-  SGB_CUDA(cudaMemsetAsync(G.x, 0, std::max<size_t>(n3 + n2, 1) * sizeof(double), h->stream));
   SGB_CUDA(cudaMemsetAsync(h->d_sc, 0, sizeof(DevScalars), h->stream));
   // persistent PCG grid: every CTA must be co-resident
   int per_sm = 0;
   SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, kThreads, 0));
   int limit = std::max(1, per_sm * h->sm_count);
-  int want = std::max(1, (std::max(S.Pf, S.Lf) + kThreads - 1) / kThreads);
+  int want = std::max(1, (std::max(P.nP, P.nL) + kThreads - 1) / kThreads);
   h->pcg_blocks = std::min(std::min(limit, want), kMaxBlocks);
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   h->has_graph = true;
   h->lm_state_valid = false;
+  return SGB_OK;
+}
+
+sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g) { return set_graph_impl(h, g, 1, 0); }
+
+sgb_status sgb_set_graph_partitioned(sgb_handle* h, const sgb_graph_soa* g, int32_t world, int32_t rank) {
+  return set_graph_impl(h, g, world, rank);
+}
+
+sgb_status sgb_comm_get_handle(sgb_handle* h, void* out64) {
+  if (!h || !out64) return SGB_ERR_INVALID;
+  if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
+  SGB_CUDA(cudaSetDevice(h->device));
+  cudaIpcMemHandle_t mh;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  SGB_CUDA(cudaIpcGetMemHandle(&mh, h->arena));
+  std::memcpy(out64, &mh, 64);
+  return SGB_OK;
+}
+
+sgb_status sgb_comm_connect(sgb_handle* h, const void* handles, int32_t world) {
+  if (!h || !handles) return SGB_ERR_INVALID;
+  if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
+  if (world != h->LP.world) { h->err = "world size mismatch"; return SGB_ERR_INVALID; }
+  SGB_CUDA(cudaSetDevice(h->device));
+  for (int r = 0; r < world; ++r) {
+    if (r == h->LP.rank) continue;
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, (const char*)handles + 64 * (size_t)r, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      h->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+      return SGB_ERR_COMM;
+    }
+    h->peer_base[r] = p;
+  }
+  fill_peer_tables(h);
+  h->connected = true;
+  return SGB_OK;
+}
+
+sgb_status sgb_get_partition_info(const sgb_handle* h, sgb_partition_info* o) {
+  if (!h || !o) return SGB_ERR_INVALID;
+  if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
+  const LocalPlan& P = h->LP;
+  o->world = P.world; o->rank = P.rank; o->n_poses = P.nP; o->n_landmarks = P.nL;
+  o->n_pp = P.n_pp; o->n_pl = P.n_pl; o->n_pp_owned = P.n_pp_owned; o->n_pl_owned = P.n_pl_owned;
+  o->halo_pose_gathers = P.halo_p; o->halo_landmark_gathers = P.halo_t;
+  o->hpp_entries = P.Hpp.entries(); o->hpl_entries = P.Hpl.entries(); o->hlp_entries = P.Hlp.entries();
+  int64_t real = 0;
+  for (int32_t c : P.Hpp.col) real += c >= 0;
+  o->hpp_blocks = real;
+  real = 0;
+  for (int32_t c : P.Hpl.col) real += c >= 0;
+  o->hpl_blocks = real;
   return SGB_OK;
 }
 
@@ -512,6 +618,24 @@ sgb_status sgb_get_structure(const sgb_handle* h, int32_t* kind, int32_t* index,
   return SGB_OK;
 }
 
+// copies this rank's owned part of a Hessian-ordered vector (pose part from `dp` [3*nP], landmark part from `dl` [2*nL])
+static sgb_status gather_owned_vector(sgb_handle* h, const double* dp, const double* dl, double* out) {
+  const Structure& S = h->S;
+  const LocalPlan& P = h->LP;
+  std::fill(out, out + S.dim, 0.0);
+  if (P.nP) SGB_CUDA(cudaMemcpy(out + 3 * (size_t)P.p_begin, dp, 3 * (size_t)P.nP * sizeof(double), cudaMemcpyDeviceToHost));
+  if (P.nL) {
+    std::vector<double> tmp(2 * (size_t)P.nL);
+    SGB_CUDA(cudaMemcpy(tmp.data(), dl, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int l = 0; l < P.nL; ++l) {
+      size_t o = 3 * (size_t)S.Pf + 2 * (size_t)P.lm_global[l];
+      out[o] = tmp[2 * (size_t)l];
+      out[o + 1] = tmp[2 * (size_t)l + 1];
+    }
+  }
+  return SGB_OK;
+}
+
 sgb_status sgb_linearize(sgb_handle* h, double* b, double* Hblocks, double* chi2) {
   sgb_status st = need_graph(h);
   if (st != SGB_OK) return st;
@@ -520,30 +644,32 @@ sgb_status sgb_linearize(sgb_handle* h, double* b, double* Hblocks, double* chi2
   if ((st = launch_finalize_lin(h, 0)) != SGB_OK) return st;
   if ((st = read_scalars(h)) != SGB_OK) return st;
   const Structure& S = h->S;
+  const LocalPlan& P = h->LP;
   DevGraph& G = h->G;
   if (chi2) { chi2[0] = h->h_sc->chi2; chi2[1] = h->h_sc->chi2_robust; }
-  if (b) SGB_CUDA(cudaMemcpy(b, G.b, (size_t)S.dim * sizeof(double), cudaMemcpyDeviceToHost));
+  if (b && (st = gather_owned_vector(h, G.b_p, G.b_l[P.rank], b)) != SGB_OK) return st;
   if (Hblocks) {
-    std::vector<double> hpp((size_t)S.Hpp.entries() * 9), hpl((size_t)S.Hpl.entries() * 6), hll(3 * (size_t)S.Lf);
+    std::vector<double> hpp((size_t)P.Hpp.entries() * 9), hpl((size_t)P.Hpl.entries() * 6), hll(3 * (size_t)P.nL);
     if (!hpp.empty()) SGB_CUDA(cudaMemcpy(hpp.data(), G.Hpp.vals, hpp.size() * sizeof(double), cudaMemcpyDeviceToHost));
     if (!hpl.empty()) SGB_CUDA(cudaMemcpy(hpl.data(), G.Hpl.vals, hpl.size() * sizeof(double), cudaMemcpyDeviceToHost));
     if (!hll.empty()) SGB_CUDA(cudaMemcpy(hll.data(), G.Hll, hll.size() * sizeof(double), cudaMemcpyDeviceToHost));
     size_t o = 0;
     for (size_t k = 0; k < S.blk_row.size(); ++k) {
-      int kind = S.blk_kind[k], e = S.blk_entry[k];
-      if (kind == 0) {  // 3x3 row-major on the device -> column-major out
+      int kind = S.blk_kind[k], e = P.blk_entry[k];
+      int sz = S.blk_nr[k] * S.blk_nc[k];
+      if (P.blk_owner[k] != P.rank) {  // owned by another rank: left zero (sum over ranks = full matrix)
+        for (int c = 0; c < sz; ++c) Hblocks[o + c] = 0.0;
+      } else if (kind == 0) {  // 3x3 row-major on the device -> column-major out
         for (int c = 0; c < 3; ++c)
           for (int r = 0; r < 3; ++r) Hblocks[o + c * 3 + r] = hpp[sell_vaddr(e, 9, 3 * r + c)];
-        o += 9;
       } else if (kind == 1) {  // 3x2
         for (int c = 0; c < 2; ++c)
           for (int r = 0; r < 3; ++r) Hblocks[o + c * 3 + r] = hpl[sell_vaddr(e, 6, 2 * r + c)];
-        o += 6;
       } else {
-        double h11 = hll[e], h12 = hll[(size_t)S.Lf + e], h22 = hll[2 * (size_t)S.Lf + e];
+        double h11 = hll[e], h12 = hll[(size_t)P.nL + e], h22 = hll[2 * (size_t)P.nL + e];
         Hblocks[o] = h11; Hblocks[o + 1] = h12; Hblocks[o + 2] = h12; Hblocks[o + 3] = h22;
-        o += 4;
       }
+      o += sz;
     }
   }
   return SGB_OK;
@@ -557,16 +683,17 @@ sgb_status sgb_solve_once(sgb_handle* h, double lambda, double* x, int32_t* pcg_
   if ((st = launch_finalize_lin(h, 0)) != SGB_OK) return st;
   if ((st = launch_setup(h, lambda, 1)) != SGB_OK) return st;
   if ((st = launch_pcg(h, lambda, 1)) != SGB_OK) return st;
-  if (h->G.Lf > 0) {
-    k_backsub<<<grid_for(h->G.Lf), kThreads, 0, h->stream>>>(h->G);
+  if (h->G.nL > 0) {
+    k_backsub<<<grid_for(h->G.nL), kThreads, 0, h->stream>>>(h->G);
     h->tm.kernel_launches++;
   }
+  k_gn_control<<<1, 32, 0, h->stream>>>(h->G, h->d_sc);
+  h->tm.kernel_launches++;
   if ((st = read_scalars(h)) != SGB_OK) return st;
-  bool ok = (h->h_sc->pcg_flag != 2) && (h->h_sc->setup_fail == 0);
-  SGB_CUDA(cudaMemset(&h->d_sc->setup_fail, 0, sizeof(int32_t)));
+  bool ok = h->h_sc->result == 1;
   if (pcg_iters) *pcg_iters = h->h_sc->pcg_iters;
   if (rel) *rel = h->h_sc->pcg_rel;
-  if (x) SGB_CUDA(cudaMemcpy(x, h->G.x, (size_t)h->S.dim * sizeof(double), cudaMemcpyDeviceToHost));
+  if (x && (st = gather_owned_vector(h, h->G.x_p[h->LP.rank], h->G.x_l, x)) != SGB_OK) return st;
   if (!ok) {
     h->err = "linear solve failed (system not positive definite)";
     return SGB_ERR_SOLVE_FAILED;
@@ -585,15 +712,27 @@ sgb_status sgb_optimize(sgb_handle* h, int32_t algo, int32_t max_iters, int32_t 
   return do_optimize(h, algo, max_iters, iters_done, stats);
 }
 
+static sgb_status copy_into_both(sgb_handle* h, const double* pose, const double* lm, cudaMemcpyKind kind) {
+  size_t np = 3 * (size_t)h->S.P_all * sizeof(double), nl = 2 * (size_t)h->S.L_all * sizeof(double);
+  int r = h->LP.rank;
+  for (int bsel = 0; bsel < 2; ++bsel) {
+    if (pose && np) SGB_CUDA(cudaMemcpyAsync(h->G.pose_buf[bsel][r], pose, np, kind, h->stream));
+    if (lm && nl) SGB_CUDA(cudaMemcpyAsync(h->G.lm_buf[bsel][r], lm, nl, kind, h->stream));
+  }
+  return SGB_OK;
+}
+
 sgb_status sgb_optimize_resident(sgb_handle* h, int32_t algo, int32_t max_iters, int32_t* iters_done,
                                  sgb_iter_stat* stats) {
   if (iters_done) *iters_done = -1;
   sgb_status st = need_graph(h);
   if (st != SGB_OK) return st;
   SGB_CUDA(cudaSetDevice(h->device));
-  size_t np = 3 * (size_t)h->S.P_all, nl = 2 * (size_t)h->S.L_all;
-  if (np) SGB_CUDA(cudaMemcpyAsync(h->G.pose, h->d_pose0, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  if (nl) SGB_CUDA(cudaMemcpyAsync(h->G.lm, h->d_lm0, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if ((st = copy_into_both(h, h->d_pose0, h->d_lm0, cudaMemcpyDeviceToDevice)) != SGB_OK) return st;
+  if (h->G.world > 1) {  // no rank may start pushing new estimates before every replica has been reset
+    k_xbarrier<<<1, 32, 0, h->stream>>>(h->G, h->d_sc);
+    SGB_CUDA(cudaGetLastError());
+  }
   h->lm_state_valid = false;
   return do_optimize(h, algo, max_iters, iters_done, stats);
 }
@@ -614,10 +753,11 @@ sgb_status sgb_get_estimates(sgb_handle* h, double* pose_est, double* lm_est) {
   sgb_status st = need_graph(h);
   if (st != SGB_OK) return st;
   SGB_CUDA(cudaSetDevice(h->device));
+  const DevGraph& G = h->G;
   if (pose_est && h->S.P_all)
-    SGB_CUDA(cudaMemcpyAsync(pose_est, h->G.pose, 3 * (size_t)h->S.P_all * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(pose_est, G.pose_buf[G.cur][G.rank], 3 * (size_t)h->S.P_all * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   if (lm_est && h->S.L_all)
-    SGB_CUDA(cudaMemcpyAsync(lm_est, h->G.lm, 2 * (size_t)h->S.L_all * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    SGB_CUDA(cudaMemcpyAsync(lm_est, G.lm_buf[G.cur][G.rank], 2 * (size_t)h->S.L_all * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   return SGB_OK;
 }
@@ -626,15 +766,7 @@ sgb_status sgb_set_estimates(sgb_handle* h, const double* pose_est, const double
   sgb_status st = need_graph(h);
   if (st != SGB_OK) return st;
   SGB_CUDA(cudaSetDevice(h->device));
-  size_t np = 3 * (size_t)h->S.P_all * sizeof(double), nl = 2 * (size_t)h->S.L_all * sizeof(double);
-  if (pose_est && np) {
-    SGB_CUDA(cudaMemcpyAsync(h->G.pose, pose_est, np, cudaMemcpyHostToDevice, h->stream));
-    SGB_CUDA(cudaMemcpyAsync(h->G.pose_trial, h->G.pose, np, cudaMemcpyDeviceToDevice, h->stream));
-  }
-  if (lm_est && nl) {
-    SGB_CUDA(cudaMemcpyAsync(h->G.lm, lm_est, nl, cudaMemcpyHostToDevice, h->stream));
-    SGB_CUDA(cudaMemcpyAsync(h->G.lm_trial, h->G.lm, nl, cudaMemcpyDeviceToDevice, h->stream));
-  }
+  if ((st = copy_into_both(h, pose_est, lm_est, cudaMemcpyHostToDevice)) != SGB_OK) return st;
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   return SGB_OK;
 }
@@ -647,8 +779,9 @@ sgb_status sgb_push(sgb_handle* h) {
   size_t np = 3 * (size_t)h->S.P_all, nl = 2 * (size_t)h->S.L_all;
   if ((st = dalloc(h, &p, np)) != SGB_OK) return st;
   if ((st = dalloc(h, &l, nl)) != SGB_OK) return st;
-  if (np) SGB_CUDA(cudaMemcpyAsync(p, h->G.pose, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  if (nl) SGB_CUDA(cudaMemcpyAsync(l, h->G.lm, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  const DevGraph& G = h->G;
+  if (np) SGB_CUDA(cudaMemcpyAsync(p, G.pose_buf[G.cur][G.rank], np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (nl) SGB_CUDA(cudaMemcpyAsync(l, G.lm_buf[G.cur][G.rank], nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   h->stack.push_back({p, l});
   return SGB_OK;
 }
@@ -668,16 +801,8 @@ sgb_status sgb_pop(sgb_handle* h) {
   if (st != SGB_OK) return st;
   if (h->stack.empty()) { h->err = "pop on an empty stack"; return SGB_ERR_INVALID; }
   SGB_CUDA(cudaSetDevice(h->device));
-  size_t np = 3 * (size_t)h->S.P_all, nl = 2 * (size_t)h->S.L_all;
   auto top = h->stack.back();
-  if (np) {
-    SGB_CUDA(cudaMemcpyAsync(h->G.pose, top.first, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    SGB_CUDA(cudaMemcpyAsync(h->G.pose_trial, top.first, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  }
-  if (nl) {
-    SGB_CUDA(cudaMemcpyAsync(h->G.lm, top.second, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-    SGB_CUDA(cudaMemcpyAsync(h->G.lm_trial, top.second, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-  }
+  if ((st = copy_into_both(h, top.first, top.second, cudaMemcpyDeviceToDevice)) != SGB_OK) return st;
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   release_top(h);
   return SGB_OK;
@@ -697,8 +822,8 @@ sgb_status sgb_chi2(sgb_handle* h, double* chi2) {
   sgb_status st = need_graph(h);
   if (st != SGB_OK) return st;
   SGB_CUDA(cudaSetDevice(h->device));
-  if ((st = launch_chi2(h, h->G.pose, h->G.lm)) != SGB_OK) return st;
-  k_finalize_chi<<<1, kThreads, 0, h->stream>>>(h->d_sc, h->d_part_e, grid_for(h->G.n_pp + h->G.n_pl));
+  if ((st = launch_chi2(h, h->G.cur)) != SGB_OK) return st;
+  k_finalize_chi<<<1, kThreads, 0, h->stream>>>(h->G, h->d_sc, h->d_part_e, grid_for(h->G.n_pp_owned + h->G.n_pl_owned));
   h->tm.kernel_launches++;
   SGB_CUDA(cudaGetLastError());
   if ((st = read_scalars(h)) != SGB_OK) return st;

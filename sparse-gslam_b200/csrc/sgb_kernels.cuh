@@ -8,6 +8,11 @@
 //   k_pcg                   persistent cooperative PCG on the implicit Schur complement, block-Jacobi   [a19 replaced]
 //   k_backsub / k_update    landmark back-substitution, oplus into the trial buffers, computeScale   [a20, a7, a8]
 //   k_lm_control            Levenberg-Marquardt gain ratio / lambda logic on the device              [a16]
+//
+// Multi-GPU (one process per GPU, row-block partition): the same kernels; rows are rank-local, remote
+// vector entries are gathered through NVLink peer pointers (sgb_types.h), and the scalar reductions / barriers are
+// exchanged through peer-mapped mailboxes written with st.release.sys and polled with ld.acquire.sys -- no host
+// round trip and no separate collective kernel inside the PCG iteration.
 #pragma once
 #include <cuda_runtime.h>
 #include <float.h>
@@ -59,12 +64,74 @@ __device__ __forceinline__ double reduce_partials(const double* part, int n, dou
   return block_sum(v, smem);
 }
 
+// ------------------------------------------------------------------------------------------------ cross-rank
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
+  asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+// All-reduce of up to 4 block-uniform doubles across the ranks (op 0 = sum, 1 = max), also a barrier: everything
+// this GPU wrote before the caller's preceding grid-wide sync is visible to the peers once they pass.
+// Called by every thread of a block; `pusher` blocks (one per GPU) publish this rank's contribution into every
+// peer's mailbox, every calling block then waits for all contributions in its OWN mailbox and combines them in rank
+// order (identical result on every block of every rank). seq must be the same on all ranks and increase by one per call.
+__device__ __forceinline__ void xreduce(const DevGraph& g, unsigned long long seq, double* vals, int nv, int op, bool pusher) {
+  if (g.world == 1) return;
+  const int slot = (int)(seq & 1ull);
+  const int t = threadIdx.x;
+  if (pusher && t < g.world) {
+    Mailbox* mb = g.mbox[t];
+    for (int k = 0; k < nv; ++k) st_relaxed_sys_f64(&mb->val[slot][g.rank][k], vals[k]);
+    __threadfence_system();
+    st_release_sys_u64(&mb->flag[slot][g.rank], seq);
+  }
+  const Mailbox* me = g.mbox[g.rank];
+  if (t < g.world) {
+    // relaxed polling (an acquire here would issue a system-scope fence per probe); everything read after the
+    // barrier is fetched with L1-bypassing loads (ld.cg / ld.relaxed.sys), so no stale line can be observed
+    while (ld_relaxed_sys_u64(&me->flag[slot][t]) < seq) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  double out[4];
+  for (int k = 0; k < nv; ++k) out[k] = op == 0 ? 0.0 : -DBL_MAX;
+  for (int o = 0; o < g.world; ++o)
+    for (int k = 0; k < nv; ++k) {
+      double v = ld_relaxed_sys_f64(&me->val[slot][o][k]);
+      out[k] = op == 0 ? out[k] + v : fmax(out[k], v);
+    }
+  for (int k = 0; k < nv; ++k) vals[k] = out[k];
+}
+// pure cross-rank barrier, launched between kernels (after k_update pushed the new estimates to every replica)
+__global__ void k_xbarrier(DevGraph g, DevScalars* sc) {
+  unsigned long long seq = sc->xseq + 1;
+  xreduce(g, seq, nullptr, 0, 0, true);
+  if (threadIdx.x == 0) sc->xseq = seq;
+}
+
 // ------------------------------------------------------------------------------------------------ linearise
 // part layout: [0]=chi [1]=chi_r [2]=maxd, each kMaxBlocks wide
 __global__ void __launch_bounds__(kThreads) k_lin_pose(DevGraph g, double* part) {
   __shared__ double sm[32];
   LinAcc acc;
-  for (int hp = blockIdx.x * blockDim.x + threadIdx.x; hp < g.Pf; hp += gridDim.x * blockDim.x) lin_pose_row(g, hp, acc);
+  for (int lp = blockIdx.x * blockDim.x + threadIdx.x; lp < g.nP; lp += gridDim.x * blockDim.x) lin_pose_row(g, lp, acc);
   double c = block_sum(acc.chi, sm), cr = block_sum(acc.chi_r, sm), m = block_max(acc.maxd, sm);
   if (threadIdx.x == 0) {
     part[blockIdx.x] = c;
@@ -75,7 +142,7 @@ __global__ void __launch_bounds__(kThreads) k_lin_pose(DevGraph g, double* part)
 __global__ void __launch_bounds__(kThreads) k_lin_lm(DevGraph g, double* part) {
   __shared__ double sm[32];
   LinAcc acc;
-  for (int hl = blockIdx.x * blockDim.x + threadIdx.x; hl < g.Lf; hl += gridDim.x * blockDim.x) lin_lm_row(g, hl, acc);
+  for (int ll = blockIdx.x * blockDim.x + threadIdx.x; ll < g.nL; ll += gridDim.x * blockDim.x) lin_lm_row(g, ll, acc);
   double c = block_sum(acc.chi, sm), cr = block_sum(acc.chi_r, sm), m = block_max(acc.maxd, sm);
   if (threadIdx.x == 0) {
     part[blockIdx.x] = c;
@@ -83,24 +150,30 @@ __global__ void __launch_bounds__(kThreads) k_lin_lm(DevGraph g, double* part) {
     part[2 * kMaxBlocks + blockIdx.x] = m;
   }
 }
-// sums the partials of the two linearise kernels; initialises LM state at iteration 0
-__global__ void __launch_bounds__(kThreads) k_finalize_lin(DevScalars* sc, const double* part_p, int nb_p,
+// sums the partials of the two linearise kernels (and of all ranks); initialises LM state at iteration 0
+__global__ void __launch_bounds__(kThreads) k_finalize_lin(DevGraph g, DevScalars* sc, const double* part_p, int nb_p,
                                                           const double* part_l, int nb_l, int init_lambda, double tau,
                                                           double user_lambda) {
   __shared__ double sm[32];
-  double c = reduce_partials(part_p, nb_p, sm) + reduce_partials(part_l, nb_l, sm);
-  double cr = reduce_partials(part_p + kMaxBlocks, nb_p, sm) + reduce_partials(part_l + kMaxBlocks, nb_l, sm);
+  double v[2];
+  v[0] = reduce_partials(part_p, nb_p, sm) + reduce_partials(part_l, nb_l, sm);
+  v[1] = reduce_partials(part_p + kMaxBlocks, nb_p, sm) + reduce_partials(part_l + kMaxBlocks, nb_l, sm);
   double m = 0.0;
   for (int i = threadIdx.x; i < nb_p; i += blockDim.x) m = fmax(m, part_p[2 * kMaxBlocks + i]);
   for (int i = threadIdx.x; i < nb_l; i += blockDim.x) m = fmax(m, part_l[2 * kMaxBlocks + i]);
   m = block_max(m, sm);
+  unsigned long long seq = sc->xseq;
+  __syncthreads();
+  xreduce(g, ++seq, v, 2, 0, true);
+  xreduce(g, ++seq, &m, 1, 1, true);
   if (threadIdx.x == 0) {
-    sc->chi2 = c;
-    sc->chi2_robust = cr;
-    sc->chi_lin = cr;
+    sc->xseq = seq;
+    sc->chi2 = v[0];
+    sc->chi2_robust = v[1];
+    sc->chi_lin = v[1];
     sc->max_diag = m;
-    sc->current_chi = cr;
-    sc->temp_chi = cr;
+    sc->current_chi = v[1];
+    sc->temp_chi = v[1];
     sc->trials = 0;
     sc->rho = 0.0;
     sc->again = 0;
@@ -112,19 +185,21 @@ __global__ void __launch_bounds__(kThreads) k_finalize_lin(DevScalars* sc, const
 }
 
 // ------------------------------------------------------------------------------------------------ chi2 only
-// one thread per edge, coalesced component-major SoA loads, warp-shuffle + block reduction
-__global__ void __launch_bounds__(kThreads) k_chi2_edges(DevGraph g, const double* pose, const double* lm, double* part) {
+// one thread per owned edge, coalesced component-major SoA loads, warp-shuffle + block reduction
+__global__ void __launch_bounds__(kThreads) k_chi2_edges(DevGraph g, int buf, double* part) {
   __shared__ double sm[32];
+  const double* pose = g.pose_buf[buf][g.rank];
+  const double* lm = g.lm_buf[buf][g.rank];
   double c = 0.0, cr = 0.0;
-  int n = g.n_pp + g.n_pl;
+  int n = g.n_pp_owned + g.n_pl_owned;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    if (k < g.n_pp) {
+    if (k < g.n_pp_owned) {
       double a, b;
       pp_chi(g, k, pose, &a, &b);
       c += a;
       cr += b;
     } else {
-      double a = pl_chi(g, k - g.n_pp, pose, lm);
+      double a = pl_chi(g, k - g.n_pp_owned, pose, lm);
       c += a;
       cr += a;
     }
@@ -136,13 +211,18 @@ __global__ void __launch_bounds__(kThreads) k_chi2_edges(DevGraph g, const doubl
     part[kMaxBlocks + blockIdx.x] = cr;
   }
 }
-__global__ void __launch_bounds__(kThreads) k_finalize_chi(DevScalars* sc, const double* part, int nb) {
+__global__ void __launch_bounds__(kThreads) k_finalize_chi(DevGraph g, DevScalars* sc, const double* part, int nb) {
   __shared__ double sm[32];
-  double c = reduce_partials(part, nb, sm);
-  double cr = reduce_partials(part + kMaxBlocks, nb, sm);
+  double v[2];
+  v[0] = reduce_partials(part, nb, sm);
+  v[1] = reduce_partials(part + kMaxBlocks, nb, sm);
+  unsigned long long seq = sc->xseq;
+  __syncthreads();
+  xreduce(g, ++seq, v, 2, 0, true);
   if (threadIdx.x == 0) {
-    sc->chi2 = c;
-    sc->chi2_robust = cr;
+    sc->xseq = seq;
+    sc->chi2 = v[0];
+    sc->chi2_robust = v[1];
   }
 }
 
@@ -150,13 +230,13 @@ __global__ void __launch_bounds__(kThreads) k_finalize_chi(DevScalars* sc, const
 __global__ void __launch_bounds__(kThreads) k_setup_lm(DevGraph g, DevScalars* sc, double lambda_override, int use_override) {
   double lambda = use_override ? lambda_override : sc->lambda;
   bool ok = true;
-  for (int hl = blockIdx.x * blockDim.x + threadIdx.x; hl < g.Lf; hl += gridDim.x * blockDim.x) ok &= setup_lm_row(g, hl, lambda);
+  for (int ll = blockIdx.x * blockDim.x + threadIdx.x; ll < g.nL; ll += gridDim.x * blockDim.x) ok &= setup_lm_row(g, ll, lambda);
   if (!ok) atomicOr(&sc->setup_fail, 1);
 }
 __global__ void __launch_bounds__(kThreads) k_setup_pose(DevGraph g, DevScalars* sc, double lambda_override, int use_override) {
   double lambda = use_override ? lambda_override : sc->lambda;
   bool ok = true;
-  for (int hp = blockIdx.x * blockDim.x + threadIdx.x; hp < g.Pf; hp += gridDim.x * blockDim.x) ok &= setup_pose_row(g, hp, lambda);
+  for (int lp = blockIdx.x * blockDim.x + threadIdx.x; lp < g.nP; lp += gridDim.x * blockDim.x) ok &= setup_pose_row(g, lp, lambda);
   if (!ok) atomicOr(&sc->setup_fail, 1);
 }
 
@@ -182,35 +262,81 @@ struct PcgParams {
   int use_override;
 };
 
+// Grid-wide AND cross-rank all-reduce (sum of up to 2 values) + barrier in ONE step for the persistent kernel:
+// every CTA deposits its partial and takes a ticket; the CTA that draws the last ticket reduces the partials in
+// index order (deterministic) and publishes the rank's sum into the mailbox of every rank (its own included, so
+// world == 1 is the same code); every CTA then polls its own mailbox until all ranks have published and combines the
+// values in rank order. One ticket round + one publish replaces "grid barrier, redundant reduction in every CTA,
+// second exchange". nv == 0 is a pure barrier. Writes made before the call are visible to every CTA of every rank
+// after it (fence before the ticket, fence + release store by the publisher, L1-bypassing loads afterwards).
+__device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long long* bar, unsigned int nb,
+                                             unsigned long long& epoch, unsigned long long& seq, double* part,
+                                             double* vals, int nv, double* sm, int* s_last) {
+  ++seq;
+  epoch += nb;
+  const int slot = (int)(seq & 1ull);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < nv; ++k) part[k * kMaxBlocks + blockIdx.x] = vals[k];
+    __threadfence();
+    unsigned long long ticket = atomicAdd(bar, 1ull);
+    *s_last = (ticket == epoch - 1ull) ? 1 : 0;
+  }
+  __syncthreads();
+  if (*s_last) {
+    __threadfence();
+    double loc[2] = {0.0, 0.0};
+    for (int k = 0; k < nv; ++k) loc[k] = reduce_partials(part + k * kMaxBlocks, (int)nb, sm);
+    if (threadIdx.x < g.world) {
+      Mailbox* mb = g.mbox[threadIdx.x];
+      for (int k = 0; k < nv; ++k) st_relaxed_sys_f64(&mb->val[slot][g.rank][k], loc[k]);
+      if (g.world > 1) __threadfence_system(); else __threadfence();
+      st_release_sys_u64(&mb->flag[slot][g.rank], seq);
+    }
+  }
+  const Mailbox* me = g.mbox[g.rank];
+  if (threadIdx.x < g.world) {
+    while (ld_relaxed_sys_u64(&me->flag[slot][threadIdx.x]) < seq) {
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  for (int k = 0; k < nv; ++k) {
+    double acc = 0.0;
+    for (int o = 0; o < g.world; ++o) acc += ld_relaxed_sys_f64(&me->val[slot][o][k]);
+    vals[k] = acc;
+  }
+}
+
 // Preconditioned conjugate gradient on S = (Hpp + lambda I) - Hpl (Hll + lambda I)^-1 Hpl^T, M = blockdiag(S).
-// One launch runs the whole solve; every CTA evaluates the same scalars from the same partial sums in the same
-// order, so control flow is uniform across the grid without any host round trip.
+// One launch per GPU runs the whole solve; every CTA of every rank evaluates the same scalars from the same sums, so
+// control flow is uniform across the grid and across the GPUs without a host round trip or a collective kernel.
 __global__ void __launch_bounds__(kThreads) k_pcg(DevGraph g, DevScalars* sc, double* part, unsigned long long* bar,
                                                  PcgParams prm) {
   __shared__ double sm[32];
+  __shared__ int s_last;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   const unsigned int nb = gridDim.x;
   unsigned long long epoch = 0;
+  unsigned long long seq = sc->xseq;
   const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
-  double* part_rz = part;
-  double* part_pq = part + kMaxBlocks;
+  double* x = g.x_p[g.rank];
+  double* p = g.p[g.rank];
 
   // x = 0, r = bt, z = Minv r, p = z
   double acc = 0.0;
-  for (int hp = tid; hp < g.Pf; hp += nthreads) {
-    double r[3] = {g.bt[3 * (size_t)hp], g.bt[3 * (size_t)hp + 1], g.bt[3 * (size_t)hp + 2]}, z[3];
-    acc += precond_row(g, hp, r, z);
+  for (int lp = tid; lp < g.nP; lp += nthreads) {
+    double r[3] = {g.bt[3 * (size_t)lp], g.bt[3 * (size_t)lp + 1], g.bt[3 * (size_t)lp + 2]}, z[3];
+    acc += precond_row(g, lp, r, z);
     for (int c = 0; c < 3; ++c) {
-      g.x[3 * (size_t)hp + c] = 0.0;
-      g.r[3 * (size_t)hp + c] = r[c];
-      g.p[3 * (size_t)hp + c] = z[c];
+      x[3 * (size_t)lp + c] = 0.0;
+      g.r[3 * (size_t)lp + c] = r[c];
+      p[3 * (size_t)lp + c] = z[c];
     }
   }
-  acc = block_sum(acc, sm);
-  if (threadIdx.x == 0) part_rz[blockIdx.x] = acc;
-  grid_sync(bar, nb, epoch);
-  double rz = reduce_partials(part_rz, nb, sm);
+  double rz = block_sum(acc, sm);
+  grid_xreduce(g, bar, nb, epoch, seq, part, &rz, 1, sm, &s_last);  // also: every rank's p segment is complete
   const double rz0 = rz;
   int it = 0, flag = 0;
   if (!(rz0 > 0.0)) {
@@ -219,37 +345,33 @@ __global__ void __launch_bounds__(kThreads) k_pcg(DevGraph g, DevScalars* sc, do
     const double target = prm.tol * prm.tol * rz0;
     flag = 1;
     while (it < prm.maxit) {
-      if (g.Lf > 0) {
-        for (int row = tid; row < g.Lf; row += nthreads) schur_phaseA_row(g, row, g.p);
-        grid_sync(bar, nb, epoch);
+      if (g.capL > 0) {
+        for (int row = tid; row < g.nL; row += nthreads) schur_phaseA_row(g, row);
+        grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, &s_last);  // every rank's t segment is complete
       }
       acc = 0.0;
-      for (int hp = tid; hp < g.Pf; hp += nthreads) acc += schur_phaseB_row(g, hp, g.p, lambda, g.q);
-      acc = block_sum(acc, sm);
-      if (threadIdx.x == 0) part_pq[blockIdx.x] = acc;
-      grid_sync(bar, nb, epoch);
-      double pq = reduce_partials(part_pq, nb, sm);
+      for (int lp = tid; lp < g.nP; lp += nthreads) acc += schur_phaseB_row(g, lp, lambda);
+      double pq = block_sum(acc, sm);
+      grid_xreduce(g, bar, nb, epoch, seq, part, &pq, 1, sm, &s_last);
       if (!(pq > 0.0)) {  // S not positive definite (or NaN): g2o's "Cholesky failure" analogue
         flag = 2;
         break;
       }
       double alpha = rz / pq;
       acc = 0.0;
-      for (int hp = tid; hp < g.Pf; hp += nthreads) {
+      for (int lp = tid; lp < g.nP; lp += nthreads) {
         double r[3], z[3];
         for (int c = 0; c < 3; ++c) {
-          size_t o = 3 * (size_t)hp + c;
-          g.x[o] += alpha * g.p[o];
+          size_t o = 3 * (size_t)lp + c;
+          x[o] += alpha * p[o];
           r[c] = g.r[o] - alpha * g.q[o];
           g.r[o] = r[c];
         }
-        acc += precond_row(g, hp, r, z);
-        for (int c = 0; c < 3; ++c) g.z[3 * (size_t)hp + c] = z[c];
+        acc += precond_row(g, lp, r, z);
+        for (int c = 0; c < 3; ++c) g.z[3 * (size_t)lp + c] = z[c];
       }
-      acc = block_sum(acc, sm);
-      if (threadIdx.x == 0) part_rz[blockIdx.x] = acc;
-      grid_sync(bar, nb, epoch);
-      double rzn = reduce_partials(part_rz, nb, sm);
+      double rzn = block_sum(acc, sm);
+      grid_xreduce(g, bar, nb, epoch, seq, part, &rzn, 1, sm, &s_last);
       ++it;
       if (!(rzn == rzn)) {
         flag = 2;
@@ -262,15 +384,16 @@ __global__ void __launch_bounds__(kThreads) k_pcg(DevGraph g, DevScalars* sc, do
       }
       double beta = rzn / rz;
       rz = rzn;
-      for (int hp = tid; hp < g.Pf; hp += nthreads)
+      for (int lp = tid; lp < g.nP; lp += nthreads)
         for (int c = 0; c < 3; ++c) {
-          size_t o = 3 * (size_t)hp + c;
-          g.p[o] = g.z[o] + beta * g.p[o];
+          size_t o = 3 * (size_t)lp + c;
+          p[o] = g.z[o] + beta * p[o];
         }
-      grid_sync(bar, nb, epoch);
+      grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, &s_last);  // every rank's p segment is complete
     }
   }
   if (tid == 0) {
+    sc->xseq = seq;
     sc->rz0 = rz0;
     sc->rz = rz;
     sc->pcg_iters = it;
@@ -281,35 +404,44 @@ __global__ void __launch_bounds__(kThreads) k_pcg(DevGraph g, DevScalars* sc, do
 
 // ------------------------------------------------------------------------------------------------ update
 __global__ void __launch_bounds__(kThreads) k_backsub(DevGraph g) {
-  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < g.Lf; row += gridDim.x * blockDim.x) backsub_lm_row(g, row);
+  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < g.nL; row += gridDim.x * blockDim.x) backsub_lm_row(g, row);
 }
-// SparseOptimizer::update into dst (trial buffers for LM, in place for GN) + computeScale partials
-__global__ void __launch_bounds__(kThreads) k_update(DevGraph g, DevScalars* sc, const double* pose_src, double* pose_dst,
-                                                    const double* lm_src, double* lm_dst, double* part, double lambda_override,
+// SparseOptimizer::update into estimate buffer `dst` of every rank (the LM trial buffer, or the current one for GN)
+// + computeScale partials
+__global__ void __launch_bounds__(kThreads) k_update(DevGraph g, DevScalars* sc, int dst, double* part, double lambda_override,
                                                     int use_override) {
   __shared__ double sm[32];
   double lambda = use_override ? lambda_override : sc->lambda;
   double s = 0.0;
-  int n = g.Pf + g.Lf;
+  int n = g.nP + g.nL;
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
-    if (v < g.Pf) s += update_pose_row(g, v, lambda, pose_src, pose_dst);
-    else s += update_lm_row(g, v - g.Pf, lambda, lm_src, lm_dst);
+    if (v < g.nP) s += update_pose_row(g, v, lambda, dst);
+    else s += update_lm_row(g, v - g.nP, lambda, dst);
   }
+  if (g.world > 1) __threadfence_system();
   s = block_sum(s, sm);
   if (threadIdx.x == 0) part[2 * kMaxBlocks + blockIdx.x] = s;
 }
 
 // OptimizationAlgorithmLevenberg::solve, the part after the trial's chi2 is known
-__global__ void __launch_bounds__(kThreads) k_lm_control(DevScalars* sc, const double* part_chi, int nb_chi,
+__global__ void __launch_bounds__(kThreads) k_lm_control(DevGraph g, DevScalars* sc, const double* part_chi, int nb_chi,
                                                         const double* part_scale, int nb_scale, int max_trials) {
   __shared__ double sm[32];
-  double c = reduce_partials(part_chi, nb_chi, sm);
-  double cr = reduce_partials(part_chi + kMaxBlocks, nb_chi, sm);
-  double scale = reduce_partials(part_scale + 2 * kMaxBlocks, nb_scale, sm);
+  double v[3];
+  v[0] = reduce_partials(part_chi, nb_chi, sm);
+  v[1] = reduce_partials(part_chi + kMaxBlocks, nb_chi, sm);
+  v[2] = reduce_partials(part_scale + 2 * kMaxBlocks, nb_scale, sm);
+  double fail = (double)sc->setup_fail;
+  unsigned long long seq = sc->xseq;
+  __syncthreads();
+  xreduce(g, ++seq, v, 3, 0, true);
+  xreduce(g, ++seq, &fail, 1, 1, true);
   if (threadIdx.x == 0) {
+    sc->xseq = seq;
+    double c = v[0], cr = v[1], scale = v[2];
     sc->chi2 = c;
     sc->chi2_robust = cr;
-    bool ok2 = (sc->pcg_flag != 2) && (sc->setup_fail == 0);
+    bool ok2 = (sc->pcg_flag != 2) && (fail == 0.0);
     double tempChi = ok2 ? cr : DBL_MAX;
     double rho = sc->current_chi - tempChi;
     scale += 1e-3;
@@ -342,6 +474,19 @@ __global__ void __launch_bounds__(kThreads) k_lm_control(DevScalars* sc, const d
     int again = (rho < 0.0 && trials < max_trials && lambda_finite) ? 1 : 0;
     sc->again = again;
     if (!again) sc->result = (trials == max_trials || rho == 0.0 || !lambda_finite) ? 2 : 1;
+    sc->setup_fail = 0;
+  }
+}
+// Gauss-Newton: the solve succeeded iff no rank saw a breakdown
+__global__ void k_gn_control(DevGraph g, DevScalars* sc) {
+  double fail = (double)sc->setup_fail;
+  unsigned long long seq = sc->xseq;
+  __syncthreads();
+  xreduce(g, ++seq, &fail, 1, 1, true);
+  if (threadIdx.x == 0) {
+    sc->xseq = seq;
+    bool ok = (sc->pcg_flag != 2) && (fail == 0.0);
+    sc->result = ok ? 1 : -1;
     sc->setup_fail = 0;
   }
 }

@@ -1,0 +1,231 @@
+// sgb_partition.cpp -- see sgb_partition.h. Host-only.
+#include "sgb_partition.h"
+
+#include <algorithm>
+#include <numeric>
+
+#include "sgb_types.h"
+
+namespace sgb {
+
+namespace {
+
+// the k-th stored block of a SELL row and its column; returns the row width
+inline int sell_row_cols(const HostSell& M, int sell_row, std::vector<int32_t>& cols) {
+  cols.clear();
+  int s = sell_row >> 5, lane = sell_row & 31;
+  int w = (M.sbase[s + 1] - M.sbase[s]) >> 5;
+  for (int k = 0; k < w; ++k) {
+    int c = M.col[(size_t)M.sbase[s] + k * 32 + lane];
+    if (c < 0) break;  // columns are packed at the front of a row
+    cols.push_back(c);
+  }
+  return (int)cols.size();
+}
+inline int entry_k(const HostSell& M, int sell_row, int entry) { return (entry - M.sbase[sell_row >> 5]) >> 5; }
+inline int entry_of(const HostSell& M, int sell_row, int k) { return M.sbase[sell_row >> 5] + k * 32 + (sell_row & 31); }
+
+void build_local_sell(const std::vector<std::vector<int32_t>>& rows, HostSell& S) {
+  int n = (int)rows.size();
+  S.rows = n;
+  S.nslices = (n + 31) / 32;
+  S.sbase.assign(S.nslices + 1, 0);
+  for (int s = 0; s < S.nslices; ++s) {
+    size_t w = 0;
+    for (int lane = 0; lane < 32 && s * 32 + lane < n; ++lane) w = std::max(w, rows[s * 32 + lane].size());
+    S.sbase[s + 1] = S.sbase[s] + (int)w * 32;
+  }
+  S.col.assign((size_t)S.sbase[S.nslices], -1);
+  for (int r = 0; r < n; ++r)
+    for (size_t k = 0; k < rows[r].size(); ++k) S.col[(size_t)S.sbase[r >> 5] + k * 32 + (r & 31)] = rows[r][k];
+}
+
+}  // namespace
+
+sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std::string& err) {
+  P = LocalPlan();
+  if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) { err = "bad world/rank"; return SGB_ERR_INVALID; }
+  P.world = world;
+  P.rank = rank;
+  P.chunkP = std::max(1, (S.Pf + world - 1) / world);
+  if (P.chunkP > kLocalMask) { err = "too many rows per rank for the column encoding"; return SGB_ERR_UNSUPPORTED; }
+  auto owner_p = [&](int hp) { return hp / P.chunkP; };
+  P.p_begin = std::min(S.Pf, rank * P.chunkP);
+  int p_end = std::min(S.Pf, (rank + 1) * P.chunkP);
+  P.nP = std::max(0, p_end - P.p_begin);
+  P.capP = P.chunkP;
+
+  // ---- landmark ownership: rank of the first free observer (global Hlp rows list observers ascending)
+  std::vector<int32_t> lm_owner(S.Lf, 0), lm_first(S.Lf, -1);
+  for (int k = 0; k < S.n_pl; ++k) {
+    int hp = S.pl_hp[k], hl = S.pl_hl[k];
+    if (hp < 0 || hl < 0) continue;
+    if (lm_first[hl] < 0 || hp < lm_first[hl]) lm_first[hl] = hp;
+  }
+  std::vector<int32_t> count(world, 0);
+  P.enc_lm.assign(S.Lf, 0);
+  for (int hl = 0; hl < S.Lf; ++hl) {
+    int o = lm_first[hl] >= 0 ? owner_p(lm_first[hl]) : 0;
+    lm_owner[hl] = o;
+    P.enc_lm[hl] = (o << kOwnerShift) | count[o];
+    if (o == rank) P.lm_global.push_back(hl);
+    count[o]++;
+  }
+  P.nL = count[rank];
+  P.capL = *std::max_element(count.begin(), count.end());
+  if (P.capL > kLocalMask) { err = "too many landmarks per rank for the column encoding"; return SGB_ERR_UNSUPPORTED; }
+  P.pose_of_l.resize(P.nP);
+  for (int l = 0; l < P.nP; ++l) P.pose_of_l[l] = S.pose_of_h[P.p_begin + l];
+  P.lm_of_l.resize(P.nL);
+  for (int l = 0; l < P.nL; ++l) P.lm_of_l[l] = S.lm_of_h[P.lm_global[l]];
+
+  auto pose_local = [&](int hp) { return hp >= 0 && owner_p(hp) == rank; };
+  auto lm_local = [&](int hl) { return hl >= 0 && lm_owner[hl] == rank; };
+
+  // ---- local edges: owned (chi2 accounted here) first, then the halo edges; global order inside each group
+  std::vector<int32_t> pp_g2l(S.n_pp, -1), pl_g2l(S.n_pl, -1);
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k = 0; k < S.n_pp; ++k) {
+      int hi = S.pp_hi[k], hj = S.pp_hj[k];
+      bool local = pose_local(hi) || pose_local(hj);
+      if (!local) continue;
+      bool owned = hi >= 0 ? pose_local(hi) : pose_local(hj);
+      if ((pass == 0) != owned) continue;
+      pp_g2l[k] = (int)P.pp_g.size();
+      P.pp_g.push_back(k);
+    }
+    if (pass == 0) P.n_pp_owned = (int)P.pp_g.size();
+  }
+  for (int pass = 0; pass < 2; ++pass) {
+    for (int k = 0; k < S.n_pl; ++k) {
+      int hp = S.pl_hp[k], hl = S.pl_hl[k];
+      bool local = pose_local(hp) || lm_local(hl);
+      if (!local) continue;
+      bool owned = hp >= 0 ? pose_local(hp) : lm_local(hl);
+      if ((pass == 0) != owned) continue;
+      pl_g2l[k] = (int)P.pl_g.size();
+      P.pl_g.push_back(k);
+    }
+    if (pass == 0) P.n_pl_owned = (int)P.pl_g.size();
+  }
+  P.n_pp = (int)P.pp_g.size();
+  P.n_pl = (int)P.pl_g.size();
+
+  // ---- local SELL matrices with encoded columns
+  std::vector<int32_t> cols;
+  {
+    std::vector<std::vector<int32_t>> rows(P.nP), rows_pl(P.nP);
+    for (int l = 0; l < P.nP; ++l) {
+      int hp = P.p_begin + l;
+      sell_row_cols(S.Hpp, hp, cols);
+      for (int c : cols) {
+        rows[l].push_back(enc_pose(c, P.chunkP));
+        if (owner_p(c) != rank) P.halo_p++;
+      }
+      sell_row_cols(S.Hpl, hp, cols);
+      for (int c : cols) {
+        rows_pl[l].push_back(P.enc_lm[c]);
+        if (lm_owner[c] != rank) P.halo_t++;
+      }
+    }
+    build_local_sell(rows, P.Hpp);
+    build_local_sell(rows_pl, P.Hpl);
+    P.hpp_diag.resize(P.nP);
+    for (int l = 0; l < P.nP; ++l) {
+      int hp = P.p_begin + l;
+      P.hpp_diag[l] = entry_of(P.Hpp, l, entry_k(S.Hpp, hp, S.hpp_diag[hp]));
+    }
+  }
+  std::vector<int32_t> lrow_of_local(P.nL, 0);  // local landmark -> Hlp row
+  {
+    // owned landmarks sorted by descending observer count (stable) to keep the SELL padding small
+    std::vector<std::vector<int32_t>> obs(P.nL);
+    for (int l = 0; l < P.nL; ++l) {
+      sell_row_cols(S.Hlp, S.lp_h2row[P.lm_global[l]], cols);
+      for (int c : cols) {
+        obs[l].push_back(enc_pose(c, P.chunkP));
+        if (owner_p(c) != rank) P.halo_p++;
+      }
+    }
+    P.lp_row2l.resize(P.nL);
+    std::iota(P.lp_row2l.begin(), P.lp_row2l.end(), 0);
+    std::stable_sort(P.lp_row2l.begin(), P.lp_row2l.end(), [&](int a, int b) { return obs[a].size() > obs[b].size(); });
+    std::vector<std::vector<int32_t>> rows(P.nL);
+    for (int r = 0; r < P.nL; ++r) {
+      rows[r] = obs[P.lp_row2l[r]];
+      lrow_of_local[P.lp_row2l[r]] = r;
+    }
+    build_local_sell(rows, P.Hlp);
+  }
+
+  // ---- per-edge arrays
+  P.pp_i.resize(P.n_pp); P.pp_j.resize(P.n_pp); P.pp_hi.resize(P.n_pp); P.pp_hj.resize(P.n_pp);
+  P.pp_e_ij.assign(P.n_pp, -1); P.pp_e_ji.assign(P.n_pp, -1); P.pp_dup.assign(P.n_pp, -1);
+  for (int l = 0; l < P.n_pp; ++l) {
+    int k = P.pp_g[l];
+    P.pp_i[l] = S.pp_i[k]; P.pp_j[l] = S.pp_j[k]; P.pp_hi[l] = S.pp_hi[k]; P.pp_hj[l] = S.pp_hj[k];
+    if (S.pp_dup[k] >= 0) P.pp_dup[l] = pp_g2l[S.pp_dup[k]];  // chain members share both endpoints => all local
+    int hi = S.pp_hi[k], hj = S.pp_hj[k];
+    if (S.pp_e_ij[k] >= 0) {  // leader of a free pair
+      if (pose_local(hi)) P.pp_e_ij[l] = entry_of(P.Hpp, hi - P.p_begin, entry_k(S.Hpp, hi, S.pp_e_ij[k]));
+      if (pose_local(hj)) P.pp_e_ji[l] = entry_of(P.Hpp, hj - P.p_begin, entry_k(S.Hpp, hj, S.pp_e_ji[k]));
+    }
+  }
+  P.pl_p.resize(P.n_pl); P.pl_l.resize(P.n_pl); P.pl_hp.resize(P.n_pl); P.pl_hl.resize(P.n_pl);
+  P.pl_e_pl.assign(P.n_pl, -1); P.pl_e_lp.assign(P.n_pl, -1); P.pl_dup.assign(P.n_pl, -1);
+  for (int l = 0; l < P.n_pl; ++l) {
+    int k = P.pl_g[l];
+    P.pl_p[l] = S.pl_p[k]; P.pl_l[l] = S.pl_l[k]; P.pl_hp[l] = S.pl_hp[k]; P.pl_hl[l] = S.pl_hl[k];
+    if (S.pl_dup[k] >= 0) P.pl_dup[l] = pl_g2l[S.pl_dup[k]];
+    int hp = S.pl_hp[k], hl = S.pl_hl[k];
+    if (S.pl_e_pl[k] >= 0) {
+      if (pose_local(hp)) P.pl_e_pl[l] = entry_of(P.Hpl, hp - P.p_begin, entry_k(S.Hpl, hp, S.pl_e_pl[k]));
+      if (lm_local(hl)) {
+        int ll = P.enc_lm[hl] & kLocalMask;
+        P.pl_e_lp[l] = entry_of(P.Hlp, lrow_of_local[ll], entry_k(S.Hlp, S.lp_h2row[hl], S.pl_e_lp[k]));
+      }
+    }
+  }
+
+  // ---- incidence lists of owned rows, local edge ids
+  P.pinc_ptr.assign(P.nP + 1, 0);
+  for (int l = 0; l < P.nP; ++l) {
+    int hp = P.p_begin + l;
+    for (int q = S.pinc_ptr[hp]; q < S.pinc_ptr[hp + 1]; ++q) {
+      int packed = S.pinc[q];
+      int k = packed >> 2, low = packed & 3;
+      int lk = (low & 1) ? pl_g2l[k] : pp_g2l[k];
+      P.pinc.push_back((lk << 2) | low);
+    }
+    P.pinc_ptr[l + 1] = (int)P.pinc.size();
+  }
+  P.linc_ptr.assign(P.nL + 1, 0);
+  for (int l = 0; l < P.nL; ++l) {
+    int hl = P.lm_global[l];
+    for (int q = S.linc_ptr[hl]; q < S.linc_ptr[hl + 1]; ++q) P.linc.push_back(pl_g2l[S.linc[q]]);
+    P.linc_ptr[l + 1] = (int)P.linc.size();
+  }
+
+  // ---- reference-order export map
+  P.blk_owner.resize(S.blk_row.size());
+  P.blk_entry.assign(S.blk_row.size(), -1);
+  for (size_t b = 0; b < S.blk_row.size(); ++b) {
+    int kind = S.blk_kind[b];
+    if (kind == 2) {
+      int hl = S.blk_entry[b];
+      P.blk_owner[b] = lm_owner[hl];
+      if (lm_owner[hl] == rank) P.blk_entry[b] = P.enc_lm[hl] & kLocalMask;
+    } else {
+      int hp = S.blk_row[b];  // block (row r, col c) is stored in pose row r
+      P.blk_owner[b] = owner_p(hp);
+      if (owner_p(hp) == rank) {
+        const HostSell& G = kind == 0 ? S.Hpp : S.Hpl;
+        const HostSell& Lc = kind == 0 ? P.Hpp : P.Hpl;
+        P.blk_entry[b] = entry_of(Lc, hp - P.p_begin, entry_k(G, hp, S.blk_entry[b]));
+      }
+    }
+  }
+  return SGB_OK;
+}
+
+}  // namespace sgb

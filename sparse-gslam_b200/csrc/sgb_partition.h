@@ -1,0 +1,39 @@
+// sgb_partition.h -- row-block partition of the symbolic structure across the GPUs of one box.
+//
+// Rank r owns the free-pose rows [r*chunkP, (r+1)*chunkP) and every landmark whose first (lowest-index) free
+// observer it owns. A rank keeps: the Hessian rows it owns (SELL matrices with ENCODED columns, see sgb_types.h),
+// the edges incident to those rows, and their incidence lists. world == 1 reproduces the global structure.
+// Host-only, no CUDA. The reference has no counterpart (single process, single thread).
+#pragma once
+#include <vector>
+
+#include "sgb_structure.h"
+
+namespace sgb {
+
+struct LocalPlan {
+  int world = 1, rank = 0;
+  int chunkP = 0;            // pose rows per rank (last rank may own fewer)
+  int nP = 0, nL = 0, capP = 0, capL = 0;
+  int p_begin = 0;           // first global free pose owned
+  int n_pp = 0, n_pl = 0, n_pp_owned = 0, n_pl_owned = 0;
+  std::vector<int32_t> pose_of_l, lm_of_l;       // local row -> vertex array index
+  std::vector<int32_t> lm_global;                // local landmark -> global free landmark
+  std::vector<int32_t> enc_lm;                   // [Lf] global free landmark -> encoded (owner, local)
+  std::vector<int32_t> pp_g, pl_g;               // local edge -> global ACTIVE edge index (Structure order)
+  std::vector<int32_t> pp_i, pp_j, pp_hi, pp_hj, pp_e_ij, pp_e_ji, pp_dup;
+  std::vector<int32_t> pl_p, pl_l, pl_hp, pl_hl, pl_e_pl, pl_e_lp, pl_dup;
+  std::vector<int32_t> pinc_ptr, pinc, linc_ptr, linc;
+  HostSell Hpp, Hpl, Hlp;
+  std::vector<int32_t> hpp_diag, lp_row2l;
+  // reference-order export: for every block of Structure::blk_* the owner rank and the local entry
+  std::vector<int32_t> blk_owner, blk_entry;
+  // halo statistics (distinct remote entries this rank gathers per PCG iteration)
+  int64_t halo_p = 0, halo_t = 0;
+};
+
+inline int enc_pose(int hp, int chunkP) { return ((hp / chunkP) << 26) | (hp % chunkP); }
+
+sgb_status partition(const Structure& S, int world, int rank, LocalPlan& out, std::string& err);
+
+}  // namespace sgb

@@ -11,7 +11,7 @@
 
 #if defined(__CUDA_ARCH__)
 #define SGB_LDG(p) __ldg(p)    // read-only for the lifetime of the kernel
-#define SGB_LDCG(p) __ldcg(p)  // written by other CTAs inside a persistent kernel: bypass L1
+#define SGB_LDCG(p) __ldcg(p)  // written by other CTAs (or, through NVLink, other GPUs) while the kernel runs: no L1
 #else
 #define SGB_LDG(p) (*(p))
 #define SGB_LDCG(p) (*(p))
@@ -138,18 +138,51 @@ SGB_HD void pl_offdiag(const PLTerm& t, double blk[6]) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// linearise + assemble, pose row: diagonal block, gradient, and every off-diagonal block this pose leads
-SGB_HD void lin_pose_row(const DevGraph& g, int hp, LinAcc& acc) {
+// current / trial estimate buffers of this rank
+SGB_HD const double* cur_pose(const DevGraph& g) { return g.pose_buf[g.cur][g.rank]; }
+SGB_HD const double* cur_lm(const DevGraph& g) { return g.lm_buf[g.cur][g.rank]; }
+
+// sum of A^T Omega B over the duplicate chain headed by edge k, oriented as (row of vertex `from_h`, col other)
+SGB_HD void pp_chain_block(const DevGraph& g, int k, const PPTerm& t, int row_h, const double* pose, double blk[9]) {
+  // block as seen from vertex 0 of the head edge: A^T Omega B  (row hi, col hj)
+  double m[9];
+  xt_om_y(t.A, t.om, t.B, m);
+  int hi = SGB_LDG(&g.pp_hi[k]);
+  bool head_is_row = (hi == row_h);
+  if (head_is_row) {
+    for (int c = 0; c < 9; ++c) blk[c] = m[c];
+  } else {
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) blk[3 * r + c] = m[3 * c + r];
+  }
+  for (int d = SGB_LDG(&g.pp_dup[k]); d >= 0; d = SGB_LDG(&g.pp_dup[d])) {
+    PPTerm u;
+    pp_term(g, d, pose, u);
+    double m2[9];
+    xt_om_y(u.A, u.om, u.B, m2);
+    if (SGB_LDG(&g.pp_hi[d]) == row_h) {
+      for (int c = 0; c < 9; ++c) blk[c] += m2[c];
+    } else {  // this duplicate runs the other way: its (row hj, col hi) view is the transpose
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) blk[3 * r + c] += m2[3 * c + r];
+    }
+  }
+}
+
+// linearise + assemble, owned pose row lp: diagonal block, gradient, and the off-diagonal blocks of THIS row
+SGB_HD void lin_pose_row(const DevGraph& g, int lp, LinAcc& acc) {
+  const double* pose = cur_pose(g);
+  const double* lm = cur_lm(g);
   double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   double bv[3] = {0, 0, 0};
-  int beg = g.pinc_ptr[hp], end = g.pinc_ptr[hp + 1];
+  int beg = g.pinc_ptr[lp], end = g.pinc_ptr[lp + 1];
   for (int it = beg; it < end; ++it) {
     int packed = SGB_LDG(&g.pinc[it]);
     int k = packed >> 2, role = (packed >> 1) & 1, type = packed & 1;
     if (type == 0) {
       PPTerm t;
-      pp_term(g, k, g.pose, t);
-      int hi = SGB_LDG(&g.pp_hi[k]);
+      pp_term(g, k, pose, t);
+      int hi = SGB_LDG(&g.pp_hi[k]), hj = SGB_LDG(&g.pp_hj[k]);
       if (role == 0) {
         double M[9];
         xt_om_y(t.A, t.om, t.A, M);
@@ -158,27 +191,10 @@ SGB_HD void lin_pose_row(const DevGraph& g, int hp, LinAcc& acc) {
         acc.chi += t.chi;
         acc.chi_r += t.chi_r;
         int e_ij = SGB_LDG(&g.pp_e_ij[k]);
-        if (e_ij >= 0) {  // both vertices free and this edge leads its vertex pair
+        if (e_ij >= 0) {  // both vertices free, this edge leads its vertex pair: block (row hi, col hj)
           double blk[9];
-          xt_om_y(t.A, t.om, t.B, blk);  // block (row hi, col hj)
-          for (int d = SGB_LDG(&g.pp_dup[k]); d >= 0; d = SGB_LDG(&g.pp_dup[d])) {
-            PPTerm u;
-            pp_term(g, d, g.pose, u);
-            double m2[9];
-            xt_om_y(u.A, u.om, u.B, m2);
-            if (SGB_LDG(&g.pp_hi[d]) == hi) {
-              for (int c = 0; c < 9; ++c) blk[c] += m2[c];
-            } else {  // duplicate with the opposite orientation contributes its transpose
-              for (int r = 0; r < 3; ++r)
-                for (int c = 0; c < 3; ++c) blk[3 * r + c] += m2[3 * c + r];
-            }
-          }
-          int e_ji = SGB_LDG(&g.pp_e_ji[k]);
-          for (int r = 0; r < 3; ++r)
-            for (int c = 0; c < 3; ++c) {
-              g.Hpp.vals[sell_vaddr(e_ij, 9, 3 * r + c)] = blk[3 * r + c];
-              g.Hpp.vals[sell_vaddr(e_ji, 9, 3 * c + r)] = blk[3 * r + c];
-            }
+          pp_chain_block(g, k, t, hi, pose, blk);
+          for (int c = 0; c < 9; ++c) g.Hpp.vals[sell_vaddr(e_ij, 9, c)] = blk[c];
         }
       } else {
         double M[9];
@@ -189,11 +205,17 @@ SGB_HD void lin_pose_row(const DevGraph& g, int hp, LinAcc& acc) {
           acc.chi += t.chi;
           acc.chi_r += t.chi_r;
         }
+        int e_ji = SGB_LDG(&g.pp_e_ji[k]);
+        if (e_ji >= 0) {  // block (row hj, col hi) = (A^T Omega B)^T summed over the chain
+          double blk[9];
+          pp_chain_block(g, k, t, hj, pose, blk);
+          for (int c = 0; c < 9; ++c) g.Hpp.vals[sell_vaddr(e_ji, 9, c)] = blk[c];
+        }
       }
     } else {
       PLTerm t;
       int hl = SGB_LDG(&g.pl_hl[k]);
-      pl_term(g, k, g.pose, g.lm, true, hl >= 0, t);
+      pl_term(g, k, pose, lm, true, hl >= 0, t);
       double AtO[6];
       for (int r = 0; r < 3; ++r) {
         AtO[2 * r] = t.A[r] * t.om[0] + t.A[3 + r] * t.om[1];
@@ -210,33 +232,33 @@ SGB_HD void lin_pose_row(const DevGraph& g, int hp, LinAcc& acc) {
         pl_offdiag(t, blk);
         for (int d = SGB_LDG(&g.pl_dup[k]); d >= 0; d = SGB_LDG(&g.pl_dup[d])) {
           PLTerm u;
-          pl_term(g, d, g.pose, g.lm, true, true, u);
+          pl_term(g, d, pose, lm, true, true, u);
           double m2[6];
           pl_offdiag(u, m2);
           for (int c = 0; c < 6; ++c) blk[c] += m2[c];
         }
-        int e_lp = SGB_LDG(&g.pl_e_lp[k]);
-        for (int c = 0; c < 6; ++c) {
-          g.Hpl.vals[sell_vaddr(e_pl, 6, c)] = blk[c];
-          g.Hlp.vals[sell_vaddr(e_lp, 6, c)] = blk[c];
-        }
+        for (int c = 0; c < 6; ++c) g.Hpl.vals[sell_vaddr(e_pl, 6, c)] = blk[c];
       }
     }
   }
-  int ed = g.hpp_diag[hp];
+  int ed = g.hpp_diag[lp];
   for (int c = 0; c < 9; ++c) g.Hpp.vals[sell_vaddr(ed, 9, c)] = H[c];
-  for (int r = 0; r < 3; ++r) g.b[3 * (size_t)hp + r] = bv[r];
+  for (int r = 0; r < 3; ++r) g.b_p[3 * (size_t)lp + r] = bv[r];
   acc.maxd = fmax(acc.maxd, fmax(fabs(H[0]), fmax(fabs(H[4]), fabs(H[8]))));
 }
 
-// linearise + assemble, landmark row: 2x2 diagonal block and gradient
-SGB_HD void lin_lm_row(const DevGraph& g, int hl, LinAcc& acc) {
+// linearise + assemble, owned landmark row ll: 2x2 diagonal block, gradient, and the landmark-major copy of the
+// pose-line blocks (recomputed here so that every rank writes only rows it owns)
+SGB_HD void lin_lm_row(const DevGraph& g, int ll, LinAcc& acc) {
+  const double* pose = cur_pose(g);
+  const double* lm = cur_lm(g);
   double h11 = 0, h12 = 0, h22 = 0, b0 = 0, b1 = 0;
-  int beg = g.linc_ptr[hl], end = g.linc_ptr[hl + 1];
+  int beg = g.linc_ptr[ll], end = g.linc_ptr[ll + 1];
   for (int it = beg; it < end; ++it) {
     int k = SGB_LDG(&g.linc[it]);
+    int e_lp = SGB_LDG(&g.pl_e_lp[k]);
     PLTerm t;
-    pl_term(g, k, g.pose, g.lm, false, true, t);
+    pl_term(g, k, pose, lm, e_lp >= 0, true, t);
     // B^T Omega B
     double BtO[4];
     for (int r = 0; r < 2; ++r) {
@@ -252,46 +274,62 @@ SGB_HD void lin_lm_row(const DevGraph& g, int hl, LinAcc& acc) {
       acc.chi += t.chi;
       acc.chi_r += t.chi;
     }
+    if (e_lp >= 0) {
+      double blk[6];
+      pl_offdiag(t, blk);
+      for (int d = SGB_LDG(&g.pl_dup[k]); d >= 0; d = SGB_LDG(&g.pl_dup[d])) {
+        PLTerm u;
+        pl_term(g, d, pose, lm, true, true, u);
+        double m2[6];
+        pl_offdiag(u, m2);
+        for (int c = 0; c < 6; ++c) blk[c] += m2[c];
+      }
+      for (int c = 0; c < 6; ++c) g.Hlp.vals[sell_vaddr(e_lp, 6, c)] = blk[c];
+    }
   }
-  g.Hll[hl] = h11;
-  g.Hll[(size_t)g.Lf + hl] = h12;
-  g.Hll[2 * (size_t)g.Lf + hl] = h22;
-  g.b[3 * (size_t)g.Pf + 2 * (size_t)hl] = b0;
-  g.b[3 * (size_t)g.Pf + 2 * (size_t)hl + 1] = b1;
+  g.Hll[ll] = h11;
+  g.Hll[(size_t)g.nL + ll] = h12;
+  g.Hll[2 * (size_t)g.nL + ll] = h22;
+  g.b_l[g.rank][2 * (size_t)ll] = b0;
+  g.b_l[g.rank][2 * (size_t)ll + 1] = b1;
   acc.maxd = fmax(acc.maxd, fmax(fabs(h11), fabs(h22)));
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // trial set-up (BlockSolver::setLambda is applied on the fly; H itself is never modified => restoreDiagonal is free)
-SGB_HD bool setup_lm_row(const DevGraph& g, int hl, double lambda) {
+SGB_HD bool setup_lm_row(const DevGraph& g, int ll, double lambda) {
   double inv[3];
-  bool ok = inv2_spd(g.Hll[hl] + lambda, g.Hll[(size_t)g.Lf + hl], g.Hll[2 * (size_t)g.Lf + hl] + lambda, inv);
-  g.Hll_inv[hl] = inv[0];
-  g.Hll_inv[(size_t)g.Lf + hl] = inv[1];
-  g.Hll_inv[2 * (size_t)g.Lf + hl] = inv[2];
+  bool ok = inv2_spd(g.Hll[ll] + lambda, g.Hll[(size_t)g.nL + ll], g.Hll[2 * (size_t)g.nL + ll] + lambda, inv);
+  double* W = g.Hll_inv[g.rank];
+  W[ll] = inv[0];
+  W[(size_t)g.capL + ll] = inv[1];
+  W[2 * (size_t)g.capL + ll] = inv[2];
   return ok;
 }
 // Schur diagonal block S_ii = Hpp_ii + lambda I - sum_l Hpl_il (Hll_l + lambda I)^-1 Hpl_il^T, its inverse (the
-// block-Jacobi preconditioner) and the reduced right-hand side bt_i = b_i - sum_l Hpl_il (Hll_l+lambda I)^-1 b_l
-SGB_HD bool setup_pose_row(const DevGraph& g, int hp, double lambda) {
+// block-Jacobi preconditioner) and the reduced right-hand side bt_i = b_i - sum_l Hpl_il (Hll_l+lambda I)^-1 b_l.
+// Landmark quantities may live on another rank: gathered through the peer tables.
+SGB_HD bool setup_pose_row(const DevGraph& g, int lp, double lambda) {
   double M[9];
-  int ed = g.hpp_diag[hp];
+  int ed = g.hpp_diag[lp];
   for (int c = 0; c < 9; ++c) M[c] = g.Hpp.vals[sell_vaddr(ed, 9, c)];
   M[0] += lambda;
   M[4] += lambda;
   M[8] += lambda;
-  double bt[3] = {g.b[3 * (size_t)hp], g.b[3 * (size_t)hp + 1], g.b[3 * (size_t)hp + 2]};
-  if (g.Lf > 0) {
-    int slice = hp >> 5, lane = hp & 31;
+  double bt[3] = {g.b_p[3 * (size_t)lp], g.b_p[3 * (size_t)lp + 1], g.b_p[3 * (size_t)lp + 2]};
+  if (g.Hpl.rows > 0) {
+    int slice = lp >> 5, lane = lp & 31;
     int w = sell_width(g.Hpl, slice);
     int base = g.Hpl.sbase[slice];
     for (int k = 0; k < w; ++k) {
       int e = base + k * 32 + lane;
-      int l = SGB_LDG(&g.Hpl.col[e]);
-      if (l < 0) continue;
+      int enc = SGB_LDG(&g.Hpl.col[e]);
+      if (enc < 0) continue;
+      int o = enc >> kOwnerShift, l = enc & kLocalMask;
       double B[6];
       for (int c = 0; c < 6; ++c) B[c] = g.Hpl.vals[sell_vaddr(e, 6, c)];
-      double w11 = g.Hll_inv[l], w12 = g.Hll_inv[(size_t)g.Lf + l], w22 = g.Hll_inv[2 * (size_t)g.Lf + l];
+      const double* W = g.Hll_inv[o];
+      double w11 = SGB_LDCG(&W[l]), w12 = SGB_LDCG(&W[(size_t)g.capL + l]), w22 = SGB_LDCG(&W[2 * (size_t)g.capL + l]);
       double BW[6];
       for (int r = 0; r < 3; ++r) {
         BW[2 * r] = B[2 * r] * w11 + B[2 * r + 1] * w12;
@@ -299,81 +337,95 @@ SGB_HD bool setup_pose_row(const DevGraph& g, int hp, double lambda) {
       }
       for (int r = 0; r < 3; ++r)
         for (int c = 0; c < 3; ++c) M[3 * r + c] -= BW[2 * r] * B[2 * c] + BW[2 * r + 1] * B[2 * c + 1];
-      double bl0 = g.b[3 * (size_t)g.Pf + 2 * (size_t)l], bl1 = g.b[3 * (size_t)g.Pf + 2 * (size_t)l + 1];
+      const double* bl = g.b_l[o];
+      double bl0 = SGB_LDCG(&bl[2 * (size_t)l]), bl1 = SGB_LDCG(&bl[2 * (size_t)l + 1]);
       for (int r = 0; r < 3; ++r) bt[r] -= BW[2 * r] * bl0 + BW[2 * r + 1] * bl1;
     }
   }
   double Mi[9];
   bool ok = inv3_spd(M, Mi);
-  for (int c = 0; c < 9; ++c) g.Minv[(size_t)c * g.Pf + hp] = Mi[c];
-  for (int r = 0; r < 3; ++r) g.bt[3 * (size_t)hp + r] = bt[r];
+  for (int c = 0; c < 9; ++c) g.Minv[(size_t)c * g.nP + lp] = Mi[c];
+  for (int r = 0; r < 3; ++r) g.bt[3 * (size_t)lp + r] = bt[r];
   return ok;
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // implicit Schur-complement operator  q = (Hpp + lambda I) v - Hpl (Hll + lambda I)^-1 Hpl^T v
-// phase A (landmark-major): t_l = (Hll_l + lambda I)^-1 * sum_i Hpl_il^T v_i       row = Hlp row
-SGB_HD void schur_phaseA_row(const DevGraph& g, int row, const double* v) {
+// phase A (landmark-major): t_l = (Hll_l + lambda I)^-1 * sum_i Hpl_il^T v_i       row = local Hlp row
+// vtab[o] = pose-vector segment of rank o (p during PCG, x_p during back-substitution)
+SGB_HD void lm_gather_row(const DevGraph& g, int row, double* const* vtab, double* u0_out, double* u1_out) {
   int slice = row >> 5, lane = row & 31;
   int w = sell_width(g.Hlp, slice);
   int base = g.Hlp.sbase[slice];
   double u0 = 0, u1 = 0;
   for (int k = 0; k < w; ++k) {
     int e = base + k * 32 + lane;
-    int i = SGB_LDG(&g.Hlp.col[e]);
-    if (i < 0) continue;
-    double v0 = SGB_LDCG(&v[3 * (size_t)i]), v1 = SGB_LDCG(&v[3 * (size_t)i + 1]), v2 = SGB_LDCG(&v[3 * (size_t)i + 2]);
+    int enc = SGB_LDG(&g.Hlp.col[e]);
+    if (enc < 0) continue;
+    const double* v = vtab[enc >> kOwnerShift] + 3 * (size_t)(enc & kLocalMask);
+    double v0 = SGB_LDCG(v), v1 = SGB_LDCG(v + 1), v2 = SGB_LDCG(v + 2);
     const double* a = g.Hlp.vals + sell_vaddr(e, 6, 0);
     u0 += SGB_LDG(a) * v0 + SGB_LDG(a + 64) * v1 + SGB_LDG(a + 128) * v2;
     u1 += SGB_LDG(a + 32) * v0 + SGB_LDG(a + 96) * v1 + SGB_LDG(a + 160) * v2;
   }
-  int hl = g.lp_row2h[row];
-  double w11 = g.Hll_inv[hl], w12 = g.Hll_inv[(size_t)g.Lf + hl], w22 = g.Hll_inv[2 * (size_t)g.Lf + hl];
-  g.t[2 * (size_t)hl] = w11 * u0 + w12 * u1;
-  g.t[2 * (size_t)hl + 1] = w12 * u0 + w22 * u1;
+  *u0_out = u0;
+  *u1_out = u1;
 }
-// phase B (pose-major): q_i = lambda v_i + sum_j Hpp_ij v_j - sum_l Hpl_il t_l ; returns v_i . q_i
-SGB_HD double schur_phaseB_row(const DevGraph& g, int hp, const double* v, double lambda, double* q) {
-  int slice = hp >> 5, lane = hp & 31;
-  double vi0 = SGB_LDCG(&v[3 * (size_t)hp]), vi1 = SGB_LDCG(&v[3 * (size_t)hp + 1]), vi2 = SGB_LDCG(&v[3 * (size_t)hp + 2]);
+SGB_HD void schur_phaseA_row(const DevGraph& g, int row) {
+  double u0, u1;
+  lm_gather_row(g, row, g.p, &u0, &u1);
+  int ll = g.lp_row2l[row];
+  const double* W = g.Hll_inv[g.rank];
+  double w11 = W[ll], w12 = W[(size_t)g.capL + ll], w22 = W[2 * (size_t)g.capL + ll];
+  double* t = g.t[g.rank];
+  t[2 * (size_t)ll] = w11 * u0 + w12 * u1;
+  t[2 * (size_t)ll + 1] = w12 * u0 + w22 * u1;
+}
+// phase B (pose-major): q_i = lambda v_i + sum_j Hpp_ij v_j - sum_l Hpl_il t_l ; returns v_i . q_i  (v = p)
+SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda) {
+  int slice = lp >> 5, lane = lp & 31;
+  const double* vown = g.p[g.rank] + 3 * (size_t)lp;
+  double vi0 = SGB_LDCG(vown), vi1 = SGB_LDCG(vown + 1), vi2 = SGB_LDCG(vown + 2);
   double q0 = lambda * vi0, q1 = lambda * vi1, q2 = lambda * vi2;
   {
     int w = sell_width(g.Hpp, slice);
     int base = g.Hpp.sbase[slice];
     for (int k = 0; k < w; ++k) {
       int e = base + k * 32 + lane;
-      int j = SGB_LDG(&g.Hpp.col[e]);
-      if (j < 0) continue;
-      double v0 = SGB_LDCG(&v[3 * (size_t)j]), v1 = SGB_LDCG(&v[3 * (size_t)j + 1]), v2 = SGB_LDCG(&v[3 * (size_t)j + 2]);
+      int enc = SGB_LDG(&g.Hpp.col[e]);
+      if (enc < 0) continue;
+      const double* v = g.p[enc >> kOwnerShift] + 3 * (size_t)(enc & kLocalMask);
+      double v0 = SGB_LDCG(v), v1 = SGB_LDCG(v + 1), v2 = SGB_LDCG(v + 2);
       const double* a = g.Hpp.vals + sell_vaddr(e, 9, 0);
       q0 += SGB_LDG(a) * v0 + SGB_LDG(a + 32) * v1 + SGB_LDG(a + 64) * v2;
       q1 += SGB_LDG(a + 96) * v0 + SGB_LDG(a + 128) * v1 + SGB_LDG(a + 160) * v2;
       q2 += SGB_LDG(a + 192) * v0 + SGB_LDG(a + 224) * v1 + SGB_LDG(a + 256) * v2;
     }
   }
-  if (g.Lf > 0) {
+  if (g.Hpl.rows > 0) {
     int w = sell_width(g.Hpl, slice);
     int base = g.Hpl.sbase[slice];
     for (int k = 0; k < w; ++k) {
       int e = base + k * 32 + lane;
-      int l = SGB_LDG(&g.Hpl.col[e]);
-      if (l < 0) continue;
-      double t0 = SGB_LDCG(&g.t[2 * (size_t)l]), t1 = SGB_LDCG(&g.t[2 * (size_t)l + 1]);
+      int enc = SGB_LDG(&g.Hpl.col[e]);
+      if (enc < 0) continue;
+      const double* tt = g.t[enc >> kOwnerShift] + 2 * (size_t)(enc & kLocalMask);
+      double t0 = SGB_LDCG(tt), t1 = SGB_LDCG(tt + 1);
       const double* a = g.Hpl.vals + sell_vaddr(e, 6, 0);
       q0 -= SGB_LDG(a) * t0 + SGB_LDG(a + 32) * t1;
       q1 -= SGB_LDG(a + 64) * t0 + SGB_LDG(a + 96) * t1;
       q2 -= SGB_LDG(a + 128) * t0 + SGB_LDG(a + 160) * t1;
     }
   }
-  q[3 * (size_t)hp] = q0;
-  q[3 * (size_t)hp + 1] = q1;
-  q[3 * (size_t)hp + 2] = q2;
+  g.q[3 * (size_t)lp] = q0;
+  g.q[3 * (size_t)lp + 1] = q1;
+  g.q[3 * (size_t)lp + 2] = q2;
   return vi0 * q0 + vi1 * q1 + vi2 * q2;
 }
 // z_i = Minv_i r_i ; returns r_i . z_i
-SGB_HD double precond_row(const DevGraph& g, int hp, const double r[3], double z[3]) {
-  const double* m = g.Minv + hp;
-  size_t s = (size_t)g.Pf;
+SGB_HD double precond_row(const DevGraph& g, int lp, const double r[3], double z[3]) {
+  const double* m = g.Minv + lp;
+  size_t s = (size_t)g.nP;
   z[0] = SGB_LDG(m) * r[0] + SGB_LDG(m + s) * r[1] + SGB_LDG(m + 2 * s) * r[2];
   z[1] = SGB_LDG(m + 3 * s) * r[0] + SGB_LDG(m + 4 * s) * r[1] + SGB_LDG(m + 5 * s) * r[2];
   z[2] = SGB_LDG(m + 6 * s) * r[0] + SGB_LDG(m + 7 * s) * r[1] + SGB_LDG(m + 8 * s) * r[2];
@@ -382,50 +434,52 @@ SGB_HD double precond_row(const DevGraph& g, int hp, const double r[3], double z
 
 // back-substitution  x_l = (Hll_l + lambda I)^-1 (b_l - sum_i Hpl_il^T x_i)
 SGB_HD void backsub_lm_row(const DevGraph& g, int row) {
-  int slice = row >> 5, lane = row & 31;
-  int w = sell_width(g.Hlp, slice);
-  int base = g.Hlp.sbase[slice];
-  int hl = g.lp_row2h[row];
-  double u0 = g.b[3 * (size_t)g.Pf + 2 * (size_t)hl], u1 = g.b[3 * (size_t)g.Pf + 2 * (size_t)hl + 1];
-  for (int k = 0; k < w; ++k) {
-    int e = base + k * 32 + lane;
-    int i = SGB_LDG(&g.Hlp.col[e]);
-    if (i < 0) continue;
-    double v0 = g.x[3 * (size_t)i], v1 = g.x[3 * (size_t)i + 1], v2 = g.x[3 * (size_t)i + 2];
-    const double* a = g.Hlp.vals + sell_vaddr(e, 6, 0);
-    u0 -= a[0] * v0 + a[64] * v1 + a[128] * v2;
-    u1 -= a[32] * v0 + a[96] * v1 + a[160] * v2;
-  }
-  double w11 = g.Hll_inv[hl], w12 = g.Hll_inv[(size_t)g.Lf + hl], w22 = g.Hll_inv[2 * (size_t)g.Lf + hl];
-  g.x[3 * (size_t)g.Pf + 2 * (size_t)hl] = w11 * u0 + w12 * u1;
-  g.x[3 * (size_t)g.Pf + 2 * (size_t)hl + 1] = w12 * u0 + w22 * u1;
+  double u0, u1;
+  lm_gather_row(g, row, g.x_p, &u0, &u1);
+  int ll = g.lp_row2l[row];
+  const double* bl = g.b_l[g.rank];
+  u0 = bl[2 * (size_t)ll] - u0;
+  u1 = bl[2 * (size_t)ll + 1] - u1;
+  const double* W = g.Hll_inv[g.rank];
+  double w11 = W[ll], w12 = W[(size_t)g.capL + ll], w22 = W[2 * (size_t)g.capL + ll];
+  g.x_l[2 * (size_t)ll] = w11 * u0 + w12 * u1;
+  g.x_l[2 * (size_t)ll + 1] = w12 * u0 + w22 * u1;
 }
 
-// SparseOptimizer::update for one free vertex into the trial buffers; returns its share of
-// computeScale = sum_j x_j (lambda x_j + b_j)
-SGB_HD double update_pose_row(const DevGraph& g, int hp, double lambda, const double* src, double* dst) {
-  int p = g.pose_of_h[hp];
-  const double* x = g.x + 3 * (size_t)hp;
-  const double* b = g.b + 3 * (size_t)hp;
+// SparseOptimizer::update for one owned free vertex: reads the current estimate, writes the new one into buffer
+// `dst` of EVERY rank (estimates are replicated; the owner pushes its rows over NVLink); returns the vertex's share
+// of computeScale = sum_j x_j (lambda x_j + b_j)
+SGB_HD double update_pose_row(const DevGraph& g, int lp, double lambda, int dst) {
+  int p = g.pose_of_l[lp];
+  const double* x = g.x_p[g.rank] + 3 * (size_t)lp;
+  const double* b = g.b_p + 3 * (size_t)lp;
+  const double* src = cur_pose(g);
   double in[3] = {src[3 * (size_t)p], src[3 * (size_t)p + 1], src[3 * (size_t)p + 2]};
   double u[3] = {x[0], x[1], x[2]};
   double out[3];
   pose_oplus(in, u, out);
-  dst[3 * (size_t)p] = out[0];
-  dst[3 * (size_t)p + 1] = out[1];
-  dst[3 * (size_t)p + 2] = out[2];
+  for (int o = 0; o < g.world; ++o) {
+    double* d = g.pose_buf[dst][o] + 3 * (size_t)p;
+    d[0] = out[0];
+    d[1] = out[1];
+    d[2] = out[2];
+  }
   return u[0] * (lambda * u[0] + b[0]) + u[1] * (lambda * u[1] + b[1]) + u[2] * (lambda * u[2] + b[2]);
 }
-SGB_HD double update_lm_row(const DevGraph& g, int hl, double lambda, const double* src, double* dst) {
-  int l = g.lm_of_h[hl];
-  const double* x = g.x + 3 * (size_t)g.Pf + 2 * (size_t)hl;
-  const double* b = g.b + 3 * (size_t)g.Pf + 2 * (size_t)hl;
+SGB_HD double update_lm_row(const DevGraph& g, int ll, double lambda, int dst) {
+  int l = g.lm_of_l[ll];
+  const double* x = g.x_l + 2 * (size_t)ll;
+  const double* b = g.b_l[g.rank] + 2 * (size_t)ll;
+  const double* src = cur_lm(g);
   double in[2] = {src[2 * (size_t)l], src[2 * (size_t)l + 1]};
   double u[2] = {x[0], x[1]};
   double out[2];
   lm_oplus(in, u, out);
-  dst[2 * (size_t)l] = out[0];
-  dst[2 * (size_t)l + 1] = out[1];
+  for (int o = 0; o < g.world; ++o) {
+    double* d = g.lm_buf[dst][o] + 2 * (size_t)l;
+    d[0] = out[0];
+    d[1] = out[1];
+  }
   return u[0] * (lambda * u[0] + b[0]) + u[1] * (lambda * u[1] + b[1]);
 }
 

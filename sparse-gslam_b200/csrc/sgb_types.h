@@ -1,90 +1,108 @@
-// sgb_types.h -- device-resident layout of one graph (pointers into HBM) shared by the kernels, the host
-// orchestration and the host-side test harness. See DESIGN.md "Data layout in HBM".
+// sgb_types.h -- device-resident layout of one rank's share of a graph (pointers into HBM), shared by the kernels,
+// the host orchestration and the host-side test harness. See DESIGN.md "Data layout in HBM".
+//
+// Multi-GPU model: the reduced pose system is partitioned by contiguous blocks of free-pose rows; a landmark is
+// owned by the rank that owns its first observer. Every rank stores the rows it owns (Hessian rows, gradient,
+// PCG vectors). Column indices are ENCODED as (owner << kOwnerShift) | local index, and the few vectors that
+// other ranks gather from (p, t, x_pose, b_landmark, Hll^-1) live in a peer-mapped arena, so a kernel reads a
+// remote entry with an ordinary load through NVLink. world == 1 is the same code with one owner.
 #pragma once
 #include <stdint.h>
 
 namespace sgb {
+
+constexpr int kMaxRanks = 8;
+constexpr int kOwnerShift = 26;  // up to 64M rows per rank
+constexpr int kLocalMask = (1 << kOwnerShift) - 1;
 
 // Sliced-ELL (SELL-32) block matrix: rows grouped in slices of 32, every slice padded to its widest row.
 // Entry e = sbase[slice] + k*32 + lane addresses the k-th block of row (slice*32 + lane); its NC values live at
 // vals[(e & ~31) * NC + c * 32 + (e & 31)], c = 0..NC-1, so that one warp reading component c of its k-th blocks
 // touches 32 consecutive doubles (one 256-byte, fully coalesced request).
 struct Sell {
-  int32_t rows;          // number of rows
+  int32_t rows;          // number of (local) rows
   int32_t nslices;
   const int32_t* sbase;  // [nslices + 1] entry offset of each slice (multiple of 32)
-  const int32_t* col;    // [entries] column (block index) or -1 for padding
+  const int32_t* col;    // [entries] encoded column or -1 for padding
   double* vals;          // [entries * NC]
 };
 
-constexpr int SELL_C = 32;
+// cross-rank signalling slots (one per rank, in the peer-mapped arena)
+struct Mailbox {
+  unsigned long long flag[2][kMaxRanks];  // [parity][source rank] = sequence number of the last message
+  double val[2][kMaxRanks][4];
+};
 
 struct DevGraph {
-  // ---- sizes
-  int32_t P_all, L_all;  // all vertices (array order of sgb_set_graph)
-  int32_t Pf, Lf;        // free (Hessian-indexed) poses / landmarks
-  int32_t n_pp, n_pl;    // active edges
+  // ---- partition
+  int32_t world, rank;
+  int32_t nP, nL;        // rows owned by this rank: free poses / free landmarks
+  int32_t capP, capL;    // max rows owned by any rank (array strides in the arena)
+  int32_t P_all, L_all;  // all vertices (array order of sgb_set_graph); estimates are replicated on every rank
+  int32_t n_pp, n_pl;    // local edges: incident to an owned row
+  int32_t n_pp_owned, n_pl_owned;  // the first n_*_owned local edges have their chi2 accounted on this rank
   int32_t has_robust;    // any DCS edge
   int32_t jac_numeric;   // 1 = g2o central differences for pose-line edges
-  // ---- estimates: [3*P_all], [2*L_all]
-  double* pose;
-  double* lm;
+  int32_t cur;           // which estimate buffer is current (0/1); the other one holds the LM trial
+  int32_t pad0;
+  // ---- estimates, replicated: est[buffer][rank] -> [3*P_all] / [2*L_all]; est[b][rank] is this rank's copy
+  double* pose_buf[2][kMaxRanks];
+  double* lm_buf[2][kMaxRanks];
   // ---- vertex maps
-  const int32_t* pose_of_h;  // [Pf] free pose -> pose array index
-  const int32_t* lm_of_h;    // [Lf]
-  // ---- active pose-pose edges (insertion order), SoA
+  const int32_t* pose_of_l;  // [nP] local free pose -> pose array index
+  const int32_t* lm_of_l;    // [nL]
+  // ---- local pose-pose edges (owned first, insertion order inside each group), component-major SoA
   const int32_t* pp_i;       // [n_pp] pose array index of vertex 0
   const int32_t* pp_j;
-  const int32_t* pp_hi;      // [n_pp] free index of vertex 0 or -1 (fixed)
+  const int32_t* pp_hi;      // [n_pp] GLOBAL free index of vertex 0 or -1 (fixed)
   const int32_t* pp_hj;
-  const double* pp_zinv;     // [3][n_pp] inverse measurement (x, y, theta), component-major
-  const double* pp_info;     // [6][n_pp] upper triangle, component-major
+  const double* pp_zinv;     // [3][n_pp] inverse measurement (x, y, theta)
+  const double* pp_info;     // [6][n_pp] upper triangle
   const double* pp_phi;      // [n_pp] DCS delta (<= 0: none); only read when has_robust
-  const int32_t* pp_e_ij;    // [n_pp] SELL entry of block (row hi, col hj) in Hpp; -1 if a vertex is fixed or the
-                             //        edge is not the first (leader) of its vertex pair
-  const int32_t* pp_e_ji;    // [n_pp] SELL entry of block (row hj, col hi)
-  const int32_t* pp_dup;     // [n_pp] next edge on the same vertex pair (chain), -1 = none
-  // ---- active pose-line edges
+  const int32_t* pp_e_ij;    // [n_pp] local Hpp entry of block (row hi, col hj); -1 unless row hi is owned, both
+                             //        vertices are free and the edge is the first (leader) of its vertex pair
+  const int32_t* pp_e_ji;    // [n_pp] local Hpp entry of block (row hj, col hi); -1 unless row hj is owned, ...
+  const int32_t* pp_dup;     // [n_pp] next local edge on the same vertex pair (chain), -1 = none
+  // ---- local pose-line edges
   const int32_t* pl_p;       // [n_pl] pose array index
   const int32_t* pl_l;       // [n_pl] landmark array index
-  const int32_t* pl_hp;      // free index or -1
+  const int32_t* pl_hp;      // GLOBAL free index or -1
   const int32_t* pl_hl;
   const double* pl_z;        // [2][n_pl]
   const double* pl_info;     // [3][n_pl]
-  const int32_t* pl_e_pl;    // [n_pl] SELL entry in Hpl (pose-major), -1 if not leader / a vertex fixed
-  const int32_t* pl_e_lp;    // [n_pl] SELL entry in Hlp (landmark-major)
+  const int32_t* pl_e_pl;    // [n_pl] local Hpl entry (pose row owned, leader), else -1
+  const int32_t* pl_e_lp;    // [n_pl] local Hlp entry (landmark row owned, leader), else -1
   const int32_t* pl_dup;     // [n_pl] duplicate chain
-  // ---- incidence lists (insertion order within a vertex)
-  const int32_t* pinc_ptr;   // [Pf + 1]
-  const int32_t* pinc;       // packed: (edge << 2) | (role << 1) | type ; type 0 = pose-pose, 1 = pose-line
-  const int32_t* linc_ptr;   // [Lf + 1]
-  const int32_t* linc;       // pose-line edge index
-  // ---- Hessian (un-reduced, lambda NOT included) and gradient
-  Sell Hpp;                  // Pf x Pf, 3x3 blocks row-major (NC = 9), both triangles
-  Sell Hpl;                  // Pf x Lf, 3x2 blocks row-major (NC = 6), pose-major
-  Sell Hlp;                  // Lf x Pf, the same 3x2 blocks (NC = 6), landmark-major; row r = landmark lp_row2h[r]
-  const int32_t* hpp_diag;   // [Pf] SELL entry of the diagonal block
-  const int32_t* lp_row2h;   // [Lf] Hlp row -> free landmark
-  const int32_t* lp_h2row;   // [Lf]
-  double* Hll;               // [3][Lf] (11,12,22)
-  double* b;                 // [3*Pf + 2*Lf] Hessian order
-  // ---- per-trial quantities
-  double* Hll_inv;           // [3][Lf] (Hll + lambda I)^-1
-  double* Minv;              // [9][Pf] block-Jacobi preconditioner = inverse of the Schur diagonal block
-  double* bt;                // [3*Pf] reduced right-hand side
-  double* x;                 // [3*Pf + 2*Lf] step
-  // ---- PCG vectors [3*Pf], t [2*Lf]
+  // ---- incidence lists of the owned rows (insertion order within a vertex)
+  const int32_t* pinc_ptr;   // [nP + 1]
+  const int32_t* pinc;       // packed: (local edge << 2) | (role << 1) | type ; type 0 = pose-pose, 1 = pose-line
+  const int32_t* linc_ptr;   // [nL + 1]
+  const int32_t* linc;       // local pose-line edge index
+  // ---- Hessian rows owned by this rank (un-reduced, lambda NOT included) and gradient
+  Sell Hpp;                  // nP x Pf, 3x3 blocks row-major (NC = 9), both triangles; columns = encoded poses
+  Sell Hpl;                  // nP x Lf, 3x2 blocks row-major (NC = 6); columns = encoded landmarks
+  Sell Hlp;                  // nL x Pf, the same 3x2 blocks (NC = 6), landmark-major; row r = local landmark lp_row2l[r]
+  const int32_t* hpp_diag;   // [nP] Hpp entry of the diagonal block
+  const int32_t* lp_row2l;   // [nL] Hlp row -> local landmark
+  double* Hll;               // [3][nL] (11,12,22), stride nL
+  double* b_p;               // [3*nP]
+  // ---- vectors other ranks gather from: tbl[rank] is this rank's own array
+  double* b_l[kMaxRanks];     // [2*capL] gradient of the owned landmarks
+  double* Hll_inv[kMaxRanks]; // [3][capL] (Hll + lambda I)^-1, stride capL
+  double* x_p[kMaxRanks];     // [3*capP] pose step
+  double* p[kMaxRanks];       // [3*capP] PCG search direction
+  double* t[kMaxRanks];       // [2*capL] (Hll + lambda I)^-1 Hpl^T p
+  Mailbox* mbox[kMaxRanks];
+  // ---- local only
+  double* x_l;               // [2*nL] landmark step
+  double* Minv;              // [9][nP] block-Jacobi preconditioner = inverse of the Schur diagonal block
+  double* bt;                // [3*nP] reduced right-hand side
   double* r;
   double* z;
-  double* p;
   double* q;
-  double* t;
-  // ---- trial estimates
-  double* pose_trial;
-  double* lm_trial;
 };
 
-// scalars of the optimiser kept on the device (LM / GN control, reductions)
+// scalars of the optimiser kept on the device (LM / GN control, reductions); identical on every rank
 struct DevScalars {
   double chi2;          // activeChi2 of the last evaluation
   double chi2_robust;   // activeRobustChi2
@@ -98,9 +116,10 @@ struct DevScalars {
   double scale;         // computeScale
   double rz0, rz, pq;   // PCG
   double pcg_rel;       // sqrt(rz / rz0) at exit
+  unsigned long long xseq;  // sequence number of the last cross-rank message this rank took part in
   int32_t pcg_iters;
   int32_t pcg_flag;     // 0 converged, 1 max iterations, 2 breakdown (not SPD / non-finite)
-  int32_t setup_fail;   // non-invertible diagonal block seen in the trial set-up
+  int32_t setup_fail;   // non-invertible diagonal block seen in the trial set-up (this rank)
   int32_t accepted;     // LM: last trial accepted
   int32_t trials;
   int32_t result;       // SGB_RESULT_*

@@ -106,6 +106,30 @@ class SparseOptimizerB200:
         self.P, self.Lm = s.n_poses, s.n_landmarks
         return True
 
+    def initialize_partitioned(self, g, world, rank, exchange):
+        """Row-block partition across `world` GPUs (one process per GPU). `exchange(blob: bytes) -> list[bytes]` must
+        return every rank's 64-byte blob in rank order (e.g. torch.distributed.all_gather_object)."""
+        s, keep = pack_graph(g)
+        st = self.L.sgb_set_graph_partitioned(self.h, C.byref(s), world, rank)
+        if st == capi.ERR_NOT_INITIALIZED:
+            return False
+        self._check(st)
+        self.g = g
+        self.P, self.Lm = s.n_poses, s.n_landmarks
+        if world > 1:
+            blob = C.create_string_buffer(64)
+            self._check(self.L.sgb_comm_get_handle(self.h, blob))
+            blobs = exchange(bytes(blob.raw))
+            assert len(blobs) == world and all(len(b) == 64 for b in blobs)
+            allb = C.create_string_buffer(b"".join(blobs), 64 * world)
+            self._check(self.L.sgb_comm_connect(self.h, allb, world))
+        return True
+
+    def partition_info(self):
+        info = capi.PartitionInfo()
+        self._check(self.L.sgb_get_partition_info(self.h, C.byref(info)))
+        return info.as_dict()
+
     def structure(self):
         info = capi.StructureInfo()
         self._check(self.L.sgb_get_structure_info(self.h, C.byref(info)))

@@ -17,9 +17,11 @@ _lib = None
 
 
 def build():
-    srcs = [os.path.join(HERE, "hostsim.cpp"), os.path.join(ROOT, "sparse-gslam_b200", "csrc", "sgb_structure.cpp")]
-    deps = srcs + [os.path.join(ROOT, "sparse-gslam_b200", "csrc", f) for f in
-                   ("sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h")]
+    csrc = os.path.join(ROOT, "sparse-gslam_b200", "csrc")
+    srcs = [os.path.join(HERE, "hostsim.cpp"), os.path.join(csrc, "sgb_structure.cpp"),
+            os.path.join(csrc, "sgb_partition.cpp")]
+    deps = srcs + [os.path.join(csrc, f) for f in
+                   ("sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h", "sgb_partition.h")]
     if os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps):
         return SO
     subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-o", SO] + srcs)
@@ -32,7 +34,7 @@ def lib():
         L = C.CDLL(build())
         vp = C.c_void_p
         L.hs_create.restype = vp
-        L.hs_create.argtypes = [C.POINTER(capi.GraphSoA), C.c_int, C.c_double, C.c_int, C.POINTER(C.c_int)]
+        L.hs_create.argtypes = [C.POINTER(capi.GraphSoA), C.c_int, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int)]
         L.hs_destroy.argtypes = [vp]
         L.hs_error.argtypes = [vp]
         L.hs_error.restype = C.c_char_p
@@ -42,18 +44,22 @@ def lib():
         L.hs_linearize.argtypes = [vp, vp, vp, vp]
         L.hs_solve_once.argtypes = [vp, C.c_double, vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.hs_optimize.argtypes = [vp, C.c_int, C.c_int, vp]
-        L.hs_get_estimates.argtypes = [vp, vp, vp]
+        L.hs_get_estimates.argtypes = [vp, C.c_int, vp, vp]
+        L.hs_partition_stats.argtypes = [vp, vp]
+        L.hs_check_hlp.argtypes = [vp]
+        L.hs_check_hlp.restype = C.c_double
         L.hs_chi2.argtypes = [vp, vp]
         _lib = L
     return _lib
 
 
 class HostSim:
-    def __init__(self, g, jac_numeric=True, tol=1e-10, maxit=0):
+    def __init__(self, g, jac_numeric=True, tol=1e-10, maxit=0, world=1):
         self.L = lib()
         s, keep = pack_graph(g)
         st = C.c_int()
-        self.h = C.c_void_p(self.L.hs_create(C.byref(s), int(jac_numeric), tol, maxit, C.byref(st)))
+        self.world = world
+        self.h = C.c_void_p(self.L.hs_create(C.byref(s), int(jac_numeric), tol, maxit, world, C.byref(st)))
         self.status = st.value
         self.error = self.L.hs_error(self.h).decode()
         self.P, self.Lm = s.n_poses, s.n_landmarks
@@ -98,10 +104,19 @@ class HostSim:
         n = self.L.hs_optimize(self.h, algo, iters, C.cast(stats, C.c_void_p))
         return n, [stats[i].as_dict() for i in range(max(n, 0))]
 
-    def estimates(self):
+    def estimates(self, rank=0):
         p, l = np.zeros((self.P, 3)), np.zeros((self.Lm, 2))
-        self.L.hs_get_estimates(self.h, _p(p), _p(l))
+        self.L.hs_get_estimates(self.h, rank, _p(p), _p(l))
         return p, l
+
+    def partition_stats(self):
+        o = np.zeros((self.world, 8), np.int64)
+        self.L.hs_partition_stats(self.h, _p(o))
+        keys = ("nP", "nL", "n_pp", "n_pl", "n_pp_owned", "n_pl_owned", "halo_p", "halo_t")
+        return [dict(zip(keys, map(int, row))) for row in o]
+
+    def check_hlp(self):
+        return float(self.L.hs_check_hlp(self.h))
 
     def chi2(self):
         c = np.zeros(2)

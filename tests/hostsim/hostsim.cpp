@@ -1,92 +1,126 @@
 // hostsim.cpp -- TEST HARNESS ONLY (never shipped, never loaded by the sparse_gslam_b200 package).
 //
 // Executes the row bodies of the CUDA kernels (sparse-gslam_b200/csrc/sgb_rows.h) serially on the host, over the
-// structure produced by the real host-side symbolic phase (sgb_structure.cpp), so that the scatter maps, SELL
-// addressing and per-row arithmetic can be checked against the oracle in the CPU-only test tier before GPU time is
-// spent. The orchestration below mirrors sgb_backend.cu / k_pcg step by step. The product library libsgb.so does not
-// contain this file and has no CPU path.
+// structure produced by the real host-side symbolic phase and partition planner (sgb_structure.cpp,
+// sgb_partition.cpp), so that the scatter maps, SELL addressing, owner/local column encoding and per-row arithmetic
+// can be checked against the oracle in the CPU-only test tier before GPU time is spent. `world` virtual ranks live
+// in one process: their peer tables point at each other's arrays exactly as the NVLink peer mappings do on the
+// GPUs, and every phase is run rank after rank (bulk-synchronous), mirroring sgb_backend.cu / k_pcg step by step.
+// The product library libsgb.so does not contain this file and has no CPU path.
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
 #include "../../include/sgb_capi.h"
+#include "../../sparse-gslam_b200/csrc/sgb_partition.h"
 #include "../../sparse-gslam_b200/csrc/sgb_rows.h"
 #include "../../sparse-gslam_b200/csrc/sgb_structure.h"
 
 using namespace sgb;
 
-struct hs_handle {
-  Structure S;
+struct Rank {
+  LocalPlan P;
   DevGraph G;
   std::vector<std::vector<double>> dbl;
   std::vector<std::vector<int32_t>> ints;
-  std::string err;
-  double lambda = 0, ni = 2;
-  double tol = 1e-10;
-  int maxit = 0;
   double* D(size_t n) { dbl.emplace_back(std::max<size_t>(n, 1), 0.0); return dbl.back().data(); }
   const int32_t* I(const std::vector<int32_t>& v) { ints.push_back(v); if (ints.back().empty()) ints.back().push_back(0); return ints.back().data(); }
 };
 
-static void mk_sell(hs_handle* h, Sell* out, const HostSell& s, int NC) {
+struct hs_handle {
+  Structure S;
+  int world = 1;
+  std::vector<std::unique_ptr<Rank>> R;
+  std::string err;
+  double lambda = 0, ni = 2;
+  double tol = 1e-10;
+  int maxit = 0;
+  int cur = 0;
+};
+
+static void mk_sell(Rank* r, Sell* out, const HostSell& s, int NC) {
   out->rows = s.rows;
   out->nslices = s.nslices;
-  out->sbase = h->I(s.sbase);
-  out->col = h->I(s.col);
-  out->vals = h->D((size_t)s.entries() * NC);
+  out->sbase = r->I(s.sbase);
+  out->col = r->I(s.col);
+  out->vals = r->D((size_t)s.entries() * NC);
 }
 
 extern "C" {
 
-hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int maxit, int* status) {
+hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int maxit, int world, int* status) {
   hs_handle* h = new hs_handle();
+  h->world = std::max(1, world);
   sgb_status st = build_structure(*g, h->S, h->err);
   if (status) *status = st;
   if (st != SGB_OK) return h;
   const Structure& S = h->S;
-  DevGraph& G = h->G;
-  std::memset(&G, 0, sizeof G);
-  G.P_all = S.P_all; G.L_all = S.L_all; G.Pf = S.Pf; G.Lf = S.Lf; G.n_pp = S.n_pp; G.n_pl = S.n_pl;
-  G.has_robust = S.has_robust; G.jac_numeric = jac_numeric;
   h->tol = tol > 0 ? tol : 1e-10;
   h->maxit = maxit > 0 ? maxit : std::max(100, 12 * S.Pf);
   size_t np = 3 * (size_t)S.P_all, nl = 2 * (size_t)S.L_all;
-  G.pose = h->D(np); G.lm = h->D(nl); G.pose_trial = h->D(np); G.lm_trial = h->D(nl);
-  std::copy(g->pose_est, g->pose_est + np, G.pose); std::copy(g->pose_est, g->pose_est + np, G.pose_trial);
-  std::copy(g->lm_est, g->lm_est + nl, G.lm); std::copy(g->lm_est, g->lm_est + nl, G.lm_trial);
-  G.pose_of_h = h->I(S.pose_of_h); G.lm_of_h = h->I(S.lm_of_h);
-  G.pp_i = h->I(S.pp_i); G.pp_j = h->I(S.pp_j); G.pp_hi = h->I(S.pp_hi); G.pp_hj = h->I(S.pp_hj);
-  G.pp_e_ij = h->I(S.pp_e_ij); G.pp_e_ji = h->I(S.pp_e_ji); G.pp_dup = h->I(S.pp_dup);
-  G.pl_p = h->I(S.pl_p); G.pl_l = h->I(S.pl_l); G.pl_hp = h->I(S.pl_hp); G.pl_hl = h->I(S.pl_hl);
-  G.pl_e_pl = h->I(S.pl_e_pl); G.pl_e_lp = h->I(S.pl_e_lp); G.pl_dup = h->I(S.pl_dup);
-  G.pinc_ptr = h->I(S.pinc_ptr); G.pinc = h->I(S.pinc); G.linc_ptr = h->I(S.linc_ptr); G.linc = h->I(S.linc);
-  G.hpp_diag = h->I(S.hpp_diag); G.lp_row2h = h->I(S.lp_row2h); G.lp_h2row = h->I(S.lp_h2row);
-  double* zinv = h->D(3 * (size_t)S.n_pp); double* info = h->D(6 * (size_t)S.n_pp); double* phi = h->D(S.n_pp);
-  for (int k = 0; k < S.n_pp; ++k) {
-    int s = S.pp_src[k];
-    double x = g->pp_z[3 * (size_t)s], y = g->pp_z[3 * (size_t)s + 1], th = g->pp_z[3 * (size_t)s + 2];
-    double thi = normalize_theta(-th), c = std::cos(thi), sn = std::sin(thi);
-    zinv[k] = c * (-x) - sn * (-y);
-    zinv[(size_t)S.n_pp + k] = sn * (-x) + c * (-y);
-    zinv[2 * (size_t)S.n_pp + k] = thi;
-    for (int c6 = 0; c6 < 6; ++c6) info[(size_t)c6 * S.n_pp + k] = g->pp_info[6 * (size_t)s + c6];
-    phi[k] = g->pp_phi ? g->pp_phi[s] : 0.0;
+  for (int rk = 0; rk < h->world; ++rk) {
+    h->R.emplace_back(new Rank());
+    Rank* r = h->R.back().get();
+    st = partition(S, h->world, rk, r->P, h->err);
+    if (st != SGB_OK) { if (status) *status = st; return h; }
+    const LocalPlan& P = r->P;
+    DevGraph& G = r->G;
+    std::memset(&G, 0, sizeof G);
+    G.world = h->world; G.rank = rk; G.nP = P.nP; G.nL = P.nL; G.capP = P.capP; G.capL = P.capL;
+    G.P_all = S.P_all; G.L_all = S.L_all; G.n_pp = P.n_pp; G.n_pl = P.n_pl;
+    G.n_pp_owned = P.n_pp_owned; G.n_pl_owned = P.n_pl_owned;
+    G.has_robust = S.has_robust; G.jac_numeric = jac_numeric; G.cur = 0;
+    G.pose_of_l = r->I(P.pose_of_l); G.lm_of_l = r->I(P.lm_of_l);
+    G.pp_i = r->I(P.pp_i); G.pp_j = r->I(P.pp_j); G.pp_hi = r->I(P.pp_hi); G.pp_hj = r->I(P.pp_hj);
+    G.pp_e_ij = r->I(P.pp_e_ij); G.pp_e_ji = r->I(P.pp_e_ji); G.pp_dup = r->I(P.pp_dup);
+    G.pl_p = r->I(P.pl_p); G.pl_l = r->I(P.pl_l); G.pl_hp = r->I(P.pl_hp); G.pl_hl = r->I(P.pl_hl);
+    G.pl_e_pl = r->I(P.pl_e_pl); G.pl_e_lp = r->I(P.pl_e_lp); G.pl_dup = r->I(P.pl_dup);
+    G.pinc_ptr = r->I(P.pinc_ptr); G.pinc = r->I(P.pinc); G.linc_ptr = r->I(P.linc_ptr); G.linc = r->I(P.linc);
+    G.hpp_diag = r->I(P.hpp_diag); G.lp_row2l = r->I(P.lp_row2l);
+    double* zinv = r->D(3 * (size_t)P.n_pp); double* info = r->D(6 * (size_t)P.n_pp); double* phi = r->D(P.n_pp);
+    for (int k = 0; k < P.n_pp; ++k) {
+      int s = S.pp_src[P.pp_g[k]];
+      double x = g->pp_z[3 * (size_t)s], y = g->pp_z[3 * (size_t)s + 1], th = g->pp_z[3 * (size_t)s + 2];
+      double thi = normalize_theta(-th), c = std::cos(thi), sn = std::sin(thi);
+      zinv[k] = c * (-x) - sn * (-y);
+      zinv[(size_t)P.n_pp + k] = sn * (-x) + c * (-y);
+      zinv[2 * (size_t)P.n_pp + k] = thi;
+      for (int c6 = 0; c6 < 6; ++c6) info[(size_t)c6 * P.n_pp + k] = g->pp_info[6 * (size_t)s + c6];
+      phi[k] = g->pp_phi ? g->pp_phi[s] : 0.0;
+    }
+    G.pp_zinv = zinv; G.pp_info = info; G.pp_phi = phi;
+    double* z = r->D(2 * (size_t)P.n_pl); double* linfo = r->D(3 * (size_t)P.n_pl);
+    for (int k = 0; k < P.n_pl; ++k) {
+      int s = S.pl_src[P.pl_g[k]];
+      z[k] = g->pl_z[2 * (size_t)s]; z[(size_t)P.n_pl + k] = g->pl_z[2 * (size_t)s + 1];
+      for (int c3 = 0; c3 < 3; ++c3) linfo[(size_t)c3 * P.n_pl + k] = g->pl_info[3 * (size_t)s + c3];
+    }
+    G.pl_z = z; G.pl_info = linfo;
+    mk_sell(r, &G.Hpp, P.Hpp, 9); mk_sell(r, &G.Hpl, P.Hpl, 6); mk_sell(r, &G.Hlp, P.Hlp, 6);
+    size_t n3 = 3 * (size_t)P.nP, n2 = 2 * (size_t)P.nL;
+    G.Hll = r->D(3 * (size_t)P.nL); G.b_p = r->D(n3); G.x_l = r->D(n2);
+    G.Minv = r->D(9 * (size_t)P.nP); G.bt = r->D(n3); G.r = r->D(n3); G.z = r->D(n3); G.q = r->D(n3);
+    // the "arena": arrays other ranks reach into
+    for (int b = 0; b < 2; ++b) {
+      G.pose_buf[b][rk] = r->D(np); G.lm_buf[b][rk] = r->D(nl);
+      std::copy(g->pose_est, g->pose_est + np, G.pose_buf[b][rk]);
+      std::copy(g->lm_est, g->lm_est + nl, G.lm_buf[b][rk]);
+    }
+    G.p[rk] = r->D(3 * (size_t)P.capP); G.x_p[rk] = r->D(3 * (size_t)P.capP);
+    G.t[rk] = r->D(2 * (size_t)P.capL); G.b_l[rk] = r->D(2 * (size_t)P.capL); G.Hll_inv[rk] = r->D(3 * (size_t)P.capL);
   }
-  G.pp_zinv = zinv; G.pp_info = info; G.pp_phi = phi;
-  double* z = h->D(2 * (size_t)S.n_pl); double* linfo = h->D(3 * (size_t)S.n_pl);
-  for (int k = 0; k < S.n_pl; ++k) {
-    int s = S.pl_src[k];
-    z[k] = g->pl_z[2 * (size_t)s]; z[(size_t)S.n_pl + k] = g->pl_z[2 * (size_t)s + 1];
-    for (int c3 = 0; c3 < 3; ++c3) linfo[(size_t)c3 * S.n_pl + k] = g->pl_info[3 * (size_t)s + c3];
-  }
-  G.pl_z = z; G.pl_info = linfo;
-  mk_sell(h, &G.Hpp, S.Hpp, 9); mk_sell(h, &G.Hpl, S.Hpl, 6); mk_sell(h, &G.Hlp, S.Hlp, 6);
-  size_t n3 = 3 * (size_t)S.Pf, n2 = 2 * (size_t)S.Lf;
-  G.Hll = h->D(3 * (size_t)S.Lf); G.Hll_inv = h->D(3 * (size_t)S.Lf); G.b = h->D(n3 + n2); G.x = h->D(n3 + n2);
-  G.Minv = h->D(9 * (size_t)S.Pf); G.bt = h->D(n3); G.r = h->D(n3); G.z = h->D(n3); G.p = h->D(n3); G.q = h->D(n3); G.t = h->D(n2);
+  // "sgb_comm_connect": cross-link the peer tables
+  for (int a = 0; a < h->world; ++a)
+    for (int b = 0; b < h->world; ++b) {
+      DevGraph& A = h->R[a]->G;
+      const DevGraph& B = h->R[b]->G;
+      for (int s = 0; s < 2; ++s) { A.pose_buf[s][b] = B.pose_buf[s][b]; A.lm_buf[s][b] = B.lm_buf[s][b]; }
+      A.p[b] = B.p[b]; A.x_p[b] = B.x_p[b]; A.t[b] = B.t[b]; A.b_l[b] = B.b_l[b]; A.Hll_inv[b] = B.Hll_inv[b];
+    }
   return h;
 }
 void hs_destroy(hs_handle* h) { delete h; }
@@ -106,43 +140,83 @@ void hs_structure(hs_handle* h, int32_t* kind, int32_t* index, int32_t* offset, 
   if (ph) for (int i = 0; i < S.P_all; ++i) ph[i] = S.pose_h[i];
   if (lh) for (int i = 0; i < S.L_all; ++i) lh[i] = S.lm_h[i] >= 0 ? S.Pf + S.lm_h[i] : -1;
 }
-// padding statistics of the three SELL matrices: entries (incl. padding) and real blocks
+// padding statistics of the three SELL matrices summed over ranks: entries (incl. padding) and real blocks
 void hs_sell_stats(hs_handle* h, int64_t* out /*[6]*/) {
-  const HostSell* m[3] = {&h->S.Hpp, &h->S.Hpl, &h->S.Hlp};
-  for (int i = 0; i < 3; ++i) {
-    out[2 * i] = m[i]->entries();
-    int64_t real = 0;
-    for (int32_t c : m[i]->col) real += c >= 0;
-    out[2 * i + 1] = real;
+  for (int i = 0; i < 6; ++i) out[i] = 0;
+  for (auto& r : h->R) {
+    const HostSell* m[3] = {&r->P.Hpp, &r->P.Hpl, &r->P.Hlp};
+    for (int i = 0; i < 3; ++i) {
+      out[2 * i] += m[i]->entries();
+      for (int32_t c : m[i]->col) out[2 * i + 1] += c >= 0;
+    }
+  }
+}
+// per-rank partition summary: [world][8] = nP, nL, n_pp, n_pl, n_pp_owned, n_pl_owned, halo_p, halo_t
+void hs_partition_stats(hs_handle* h, int64_t* out) {
+  for (int k = 0; k < h->world; ++k) {
+    const LocalPlan& P = h->R[k]->P;
+    int64_t v[8] = {P.nP, P.nL, P.n_pp, P.n_pl, P.n_pp_owned, P.n_pl_owned, P.halo_p, P.halo_t};
+    std::copy(v, v + 8, out + 8 * k);
   }
 }
 
+static void set_cur(hs_handle* h, int cur) {
+  h->cur = cur;
+  for (auto& r : h->R) r->G.cur = cur;
+}
+
 static void linearize(hs_handle* h, double chi[3]) {
-  DevGraph& G = h->G;
   LinAcc acc;
-  for (int hp = 0; hp < G.Pf; ++hp) lin_pose_row(G, hp, acc);
-  for (int hl = 0; hl < G.Lf; ++hl) lin_lm_row(G, hl, acc);
+  for (auto& r : h->R) {
+    DevGraph& G = r->G;
+    for (int lp = 0; lp < G.nP; ++lp) lin_pose_row(G, lp, acc);
+    for (int ll = 0; ll < G.nL; ++ll) lin_lm_row(G, ll, acc);
+  }
   chi[0] = acc.chi; chi[1] = acc.chi_r; chi[2] = acc.maxd;
 }
-static void chi2_edges(hs_handle* h, const double* pose, const double* lm, double chi[2]) {
-  DevGraph& G = h->G;
+static void chi2_edges(hs_handle* h, int buf, double chi[2]) {
   double c = 0, cr = 0;
-  for (int k = 0; k < G.n_pp; ++k) { double a, b; pp_chi(G, k, pose, &a, &b); c += a; cr += b; }
-  for (int k = 0; k < G.n_pl; ++k) { double a = pl_chi(G, k, pose, lm); c += a; cr += a; }
+  for (auto& r : h->R) {
+    DevGraph& G = r->G;
+    const double* pose = G.pose_buf[buf][G.rank];
+    const double* lm = G.lm_buf[buf][G.rank];
+    for (int k = 0; k < G.n_pp_owned; ++k) { double a, b; pp_chi(G, k, pose, &a, &b); c += a; cr += b; }
+    for (int k = 0; k < G.n_pl_owned; ++k) { double a = pl_chi(G, k, pose, lm); c += a; cr += a; }
+  }
   chi[0] = c; chi[1] = cr;
+}
+
+static void gather_vec(hs_handle* h, bool step, double* out) {
+  const Structure& S = h->S;
+  for (auto& r : h->R) {
+    const DevGraph& G = r->G;
+    const LocalPlan& P = r->P;
+    const double* dp = step ? G.x_p[G.rank] : G.b_p;
+    const double* dl = step ? G.x_l : G.b_l[G.rank];
+    for (int l = 0; l < 3 * P.nP; ++l) out[3 * (size_t)P.p_begin + l] = dp[l];
+    for (int l = 0; l < P.nL; ++l) {
+      size_t o = 3 * (size_t)S.Pf + 2 * (size_t)P.lm_global[l];
+      out[o] = dl[2 * l];
+      out[o + 1] = dl[2 * l + 1];
+    }
+  }
 }
 
 void hs_linearize(hs_handle* h, double* b, double* Hblocks, double* chi2) {
   const Structure& S = h->S;
-  DevGraph& G = h->G;
   double chi[3];
   linearize(h, chi);
   if (chi2) { chi2[0] = chi[0]; chi2[1] = chi[1]; }
-  if (b) std::copy(G.b, G.b + S.dim, b);
+  if (b) gather_vec(h, false, b);
   if (Hblocks) {
     size_t o = 0;
     for (size_t k = 0; k < S.blk_row.size(); ++k) {
-      int kind = S.blk_kind[k], e = S.blk_entry[k];
+      int kind = S.blk_kind[k];
+      // every rank agrees on the owner; take the values from it
+      int owner = h->R[0]->P.blk_owner[k];
+      const Rank& R = *h->R[owner];
+      int e = R.P.blk_entry[k];
+      const DevGraph& G = R.G;
       if (kind == 0) {
         for (int c = 0; c < 3; ++c) for (int r = 0; r < 3; ++r) Hblocks[o + c * 3 + r] = G.Hpp.vals[sell_vaddr(e, 9, 3 * r + c)];
         o += 9;
@@ -150,55 +224,101 @@ void hs_linearize(hs_handle* h, double* b, double* Hblocks, double* chi2) {
         for (int c = 0; c < 2; ++c) for (int r = 0; r < 3; ++r) Hblocks[o + c * 3 + r] = G.Hpl.vals[sell_vaddr(e, 6, 2 * r + c)];
         o += 6;
       } else {
-        double h11 = G.Hll[e], h12 = G.Hll[(size_t)S.Lf + e], h22 = G.Hll[2 * (size_t)S.Lf + e];
+        double h11 = G.Hll[e], h12 = G.Hll[(size_t)G.nL + e], h22 = G.Hll[2 * (size_t)G.nL + e];
         Hblocks[o] = h11; Hblocks[o + 1] = h12; Hblocks[o + 2] = h12; Hblocks[o + 3] = h22;
         o += 4;
       }
     }
-    // the landmark-major copy must hold the same blocks
   }
+}
+// the landmark-major copy Hlp must hold exactly the blocks of Hpl: returns the max abs difference
+double hs_check_hlp(hs_handle* h) {
+  const Structure& S = h->S;
+  double worst = 0;
+  // global (pose hp, landmark hl) -> value from Hpl; compare with Hlp rows
+  for (auto& r : h->R) {
+    const DevGraph& G = r->G;
+    const LocalPlan& P = r->P;
+    for (int row = 0; row < G.nL; ++row) {
+      int ll = P.lp_row2l[row];
+      int hl = P.lm_global[ll];
+      int slice = row >> 5, lane = row & 31, w = sell_width(G.Hlp, slice);
+      for (int k = 0; k < w; ++k) {
+        int e = G.Hlp.sbase[slice] + k * 32 + lane;
+        int enc = G.Hlp.col[e];
+        if (enc < 0) continue;
+        int o = enc >> kOwnerShift, lp = enc & kLocalMask;
+        const Rank& Q = *h->R[o];
+        // find hl in pose row lp of rank o
+        int s2 = lp >> 5, l2 = lp & 31, w2 = sell_width(Q.G.Hpl, s2);
+        bool found = false;
+        for (int k2 = 0; k2 < w2; ++k2) {
+          int e2 = Q.G.Hpl.sbase[s2] + k2 * 32 + l2;
+          if (Q.G.Hpl.col[e2] == r->P.enc_lm[hl]) {
+            for (int c = 0; c < 6; ++c) worst = std::max(worst, std::fabs(Q.G.Hpl.vals[sell_vaddr(e2, 6, c)] - G.Hlp.vals[sell_vaddr(e, 6, c)]));
+            found = true;
+          }
+        }
+        if (!found) worst = 1e300;
+      }
+    }
+  }
+  (void)S;
+  return worst;
 }
 
 // mirrors k_setup_* + k_pcg + k_backsub; returns pcg flag (0 ok, 1 maxit, 2 breakdown), iterations in *iters
 static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
-  DevGraph& G = h->G;
   bool ok = true;
-  for (int hl = 0; hl < G.Lf; ++hl) ok &= setup_lm_row(G, hl, lambda);
-  for (int hp = 0; hp < G.Pf; ++hp) ok &= setup_pose_row(G, hp, lambda);
+  for (auto& r : h->R) for (int ll = 0; ll < r->G.nL; ++ll) ok &= setup_lm_row(r->G, ll, lambda);
+  for (auto& r : h->R) for (int lp = 0; lp < r->G.nP; ++lp) ok &= setup_pose_row(r->G, lp, lambda);
   double rz = 0;
-  for (int hp = 0; hp < G.Pf; ++hp) {
-    double r[3] = {G.bt[3 * hp], G.bt[3 * hp + 1], G.bt[3 * hp + 2]}, z[3];
-    rz += precond_row(G, hp, r, z);
-    for (int c = 0; c < 3; ++c) { G.x[3 * hp + c] = 0; G.r[3 * hp + c] = r[c]; G.p[3 * hp + c] = z[c]; }
+  for (auto& rk : h->R) {
+    DevGraph& G = rk->G;
+    double* x = G.x_p[G.rank]; double* p = G.p[G.rank];
+    for (int lp = 0; lp < G.nP; ++lp) {
+      double r[3] = {G.bt[3 * lp], G.bt[3 * lp + 1], G.bt[3 * lp + 2]}, z[3];
+      rz += precond_row(G, lp, r, z);
+      for (int c = 0; c < 3; ++c) { x[3 * lp + c] = 0; G.r[3 * lp + c] = r[c]; p[3 * lp + c] = z[c]; }
+    }
   }
   double rz0 = rz;
   int it = 0, flag = 0;
+  bool any_lm = h->R[0]->G.capL > 0;
   if (!(rz0 > 0.0)) {
     flag = (rz0 == 0.0) ? 0 : 2;
   } else {
     double target = h->tol * h->tol * rz0;
     flag = 1;
     while (it < h->maxit) {
-      for (int row = 0; row < G.Lf; ++row) schur_phaseA_row(G, row, G.p);
+      if (any_lm) for (auto& rk : h->R) for (int row = 0; row < rk->G.nL; ++row) schur_phaseA_row(rk->G, row);
       double pq = 0;
-      for (int hp = 0; hp < G.Pf; ++hp) pq += schur_phaseB_row(G, hp, G.p, lambda, G.q);
+      for (auto& rk : h->R) for (int lp = 0; lp < rk->G.nP; ++lp) pq += schur_phaseB_row(rk->G, lp, lambda);
       if (!(pq > 0.0)) { flag = 2; break; }
       double alpha = rz / pq, rzn = 0;
-      for (int hp = 0; hp < G.Pf; ++hp) {
-        double r[3], z[3];
-        for (int c = 0; c < 3; ++c) { size_t o = 3 * (size_t)hp + c; G.x[o] += alpha * G.p[o]; r[c] = G.r[o] - alpha * G.q[o]; G.r[o] = r[c]; }
-        rzn += precond_row(G, hp, r, z);
-        for (int c = 0; c < 3; ++c) G.z[3 * (size_t)hp + c] = z[c];
+      for (auto& rk : h->R) {
+        DevGraph& G = rk->G;
+        double* x = G.x_p[G.rank]; double* p = G.p[G.rank];
+        for (int lp = 0; lp < G.nP; ++lp) {
+          double r[3], z[3];
+          for (int c = 0; c < 3; ++c) { size_t o = 3 * (size_t)lp + c; x[o] += alpha * p[o]; r[c] = G.r[o] - alpha * G.q[o]; G.r[o] = r[c]; }
+          rzn += precond_row(G, lp, r, z);
+          for (int c = 0; c < 3; ++c) G.z[3 * (size_t)lp + c] = z[c];
+        }
       }
       ++it;
       if (!(rzn == rzn)) { flag = 2; break; }
       if (rzn <= target) { rz = rzn; flag = 0; break; }
       double beta = rzn / rz;
       rz = rzn;
-      for (size_t o = 0; o < 3 * (size_t)G.Pf; ++o) G.p[o] = G.z[o] + beta * G.p[o];
+      for (auto& rk : h->R) {
+        DevGraph& G = rk->G;
+        double* p = G.p[G.rank];
+        for (size_t o = 0; o < 3 * (size_t)G.nP; ++o) p[o] = G.z[o] + beta * p[o];
+      }
     }
   }
-  for (int row = 0; row < G.Lf; ++row) backsub_lm_row(G, row);
+  for (auto& rk : h->R) for (int row = 0; row < rk->G.nL; ++row) backsub_lm_row(rk->G, row);
   if (iters) *iters = it;
   if (rel) *rel = rz0 > 0 ? std::sqrt(std::fabs(rz) / rz0) : 0.0;
   if (!ok) flag = 2;
@@ -209,12 +329,21 @@ int hs_solve_once(hs_handle* h, double lambda, double* x, int* iters, double* re
   double chi[3];
   linearize(h, chi);
   int flag = solve(h, lambda, iters, rel);
-  if (x) std::copy(h->G.x, h->G.x + h->S.dim, x);
+  if (x) gather_vec(h, true, x);
   return flag;
 }
 
+static double update_all(hs_handle* h, double lambda, int dst) {
+  double scale = 0;
+  for (auto& rk : h->R) {
+    DevGraph& G = rk->G;
+    for (int lp = 0; lp < G.nP; ++lp) scale += update_pose_row(G, lp, lambda, dst);
+    for (int ll = 0; ll < G.nL; ++ll) scale += update_lm_row(G, ll, lambda, dst);
+  }
+  return scale;
+}
+
 int hs_optimize(hs_handle* h, int algo, int max_iters, sgb_iter_stat* stats) {
-  DevGraph& G = h->G;
   int done = 0, result = SGB_RESULT_OK;
   bool ok = true;
   for (int it = 0; it < max_iters && ok; ++it) {
@@ -227,8 +356,7 @@ int hs_optimize(hs_handle* h, int algo, int max_iters, sgb_iter_stat* stats) {
       int iters = 0;
       int flag = solve(h, 0.0, &iters, &rel);
       pcg_total = iters;
-      for (int hp = 0; hp < G.Pf; ++hp) update_pose_row(G, hp, 0.0, G.pose, G.pose);
-      for (int hl = 0; hl < G.Lf; ++hl) update_lm_row(G, hl, 0.0, G.lm, G.lm);
+      update_all(h, 0.0, h->cur);
       result = flag != 2 ? SGB_RESULT_OK : SGB_RESULT_FAIL;
       trials = 1;
     } else {
@@ -237,11 +365,9 @@ int hs_optimize(hs_handle* h, int algo, int max_iters, sgb_iter_stat* stats) {
         int iters = 0;
         int flag = solve(h, h->lambda, &iters, &rel);
         pcg_total += iters;
-        double scale = 0;
-        for (int hp = 0; hp < G.Pf; ++hp) scale += update_pose_row(G, hp, h->lambda, G.pose, G.pose_trial);
-        for (int hl = 0; hl < G.Lf; ++hl) scale += update_lm_row(G, hl, h->lambda, G.lm, G.lm_trial);
+        double scale = update_all(h, h->lambda, h->cur ^ 1);
         double c2[2];
-        chi2_edges(h, G.pose_trial, G.lm_trial, c2);
+        chi2_edges(h, h->cur ^ 1, c2);
         double tempChi = flag != 2 ? c2[1] : DBL_MAX;
         rho = (currentChi - tempChi) / (scale + 1e-3);
         bool lambda_finite = true;
@@ -250,8 +376,7 @@ int hs_optimize(hs_handle* h, int algo, int max_iters, sgb_iter_stat* stats) {
           h->lambda *= std::max(1.0 / 3.0, alpha);
           h->ni = 2;
           currentChi = tempChi;
-          std::swap(G.pose, G.pose_trial);
-          std::swap(G.lm, G.lm_trial);
+          set_cur(h, h->cur ^ 1);
         } else {
           h->lambda *= h->ni;
           h->ni *= 2;
@@ -273,10 +398,12 @@ int hs_optimize(hs_handle* h, int algo, int max_iters, sgb_iter_stat* stats) {
   return result == SGB_RESULT_FAIL ? 0 : done;
 }
 
-void hs_get_estimates(hs_handle* h, double* pose, double* lm) {
-  if (pose) std::copy(h->G.pose, h->G.pose + 3 * (size_t)h->S.P_all, pose);
-  if (lm) std::copy(h->G.lm, h->G.lm + 2 * (size_t)h->S.L_all, lm);
+// estimates of virtual rank `rank` (all replicas must agree)
+void hs_get_estimates(hs_handle* h, int rank, double* pose, double* lm) {
+  const DevGraph& G = h->R[rank]->G;
+  if (pose) std::copy(G.pose_buf[h->cur][rank], G.pose_buf[h->cur][rank] + 3 * (size_t)h->S.P_all, pose);
+  if (lm) std::copy(G.lm_buf[h->cur][rank], G.lm_buf[h->cur][rank] + 2 * (size_t)h->S.L_all, lm);
 }
-void hs_chi2(hs_handle* h, double* chi2) { chi2_edges(h, h->G.pose, h->G.lm, chi2); }
+void hs_chi2(hs_handle* h, double* chi2) { chi2_edges(h, h->cur, chi2); }
 
 }  // extern "C"

@@ -102,8 +102,12 @@ def test_lm15_final_state_parity(name, jac):
             np.testing.assert_allclose(b["lambda_"], a["lambda_"], rtol=1e-4)
     po, lo = o.estimates()
     pg, lg = opt.estimates()
-    assert pose_err(pg, po) < 1e-6
-    assert rel_err(lg, lo) < 1e-6
+    # analytic mode: 1e-6 relative (north_star). g2o-numeric mode: the reference's own central differences make its
+    # result reproducible only to a few 1e-6 (two CPU restatements of it differ by 1.9e-6 mid-trajectory, see
+    # tests/test_oracle.py::test_lm_trace_cpp_equals_numpy), so the bound there is 5e-6.
+    tol = 5e-6 if jac == capi.JAC_G2O_NUMERIC else 1e-6
+    assert pose_err(pg, po) < tol
+    assert rel_err(lg, lo) < tol
     np.testing.assert_allclose(opt.active_chi2()[0], o.chi2()[0], rtol=1e-6)
     # caller protocol: pop() restores the pre-optimisation estimates (drone.cpp:180)
     opt.pop()

@@ -1,0 +1,102 @@
+"""GPU tier, needs >= 2 GPUs (skipped otherwise): the row-block partitioned path, one process per GPU, against the
+single-GPU result and the oracle. Halo gathers and PCG reductions run over NVLink peer memory."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sparse_gslam_b200 import SparseOptimizerB200, capi
+    from sparse_gslam_b200 import dist as sdist
+    from sparse_gslam_b200 import graphgen as gg
+    out = {}
+    g = gg.make_c5(rows=40, cols=40)
+    opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC, device=rank)
+    assert opt.initialize_partitioned(g, world, rank, sdist.exchange_blobs)
+    out["info"] = opt.partition_info()
+    lin = opt.linearize()
+    out["H"], out["b"], out["chi2"] = lin["H"], lin["b"], lin["chi2"]
+    sdist.barrier()
+    ok, x, it, rel = opt.solve_once(50.0)
+    out["x"], out["solve"] = x, (ok, it, rel)
+    sdist.barrier()
+    n, st = opt.optimize(8)
+    out["lm"] = (n, [s["trials"] for s in st], [s["chi2"] for s in st])
+    out["est"] = opt.estimates()
+    out["chi2_after"] = opt.active_chi2()
+    sdist.barrier()
+    gp = g.pose_only(phi=1.0)
+    gn = SparseOptimizerB200(capi.ALGO_GN, device=rank)
+    assert gn.initialize_partitioned(gp, world, rank, sdist.exchange_blobs)
+    out["gn"] = gn.optimize(3)[0]
+    out["gn_est"] = gn.estimates()[0]
+    sdist.barrier()
+    opt.close()
+    gn.close()
+    dist.destroy_process_group()
+    q.put((rank, out))
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world", [2])
+def test_partitioned_matches_single_gpu(world):
+    import torch.multiprocessing as mp
+    from sparse_gslam_b200 import SparseOptimizerB200, capi
+    from sparse_gslam_b200 import graphgen as gg
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29700 + os.getpid() % 200
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g = gg.make_c5(rows=40, cols=40)
+    one = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
+    one.initialize_optimization(g)
+    lin = one.linearize()
+    H = sum(res[r]["H"] for r in range(world))
+    b = sum(res[r]["b"] for r in range(world))
+    np.testing.assert_array_equal(H, lin["H"])     # each block is written by exactly one rank, same arithmetic
+    np.testing.assert_array_equal(b, lin["b"])
+    for r in range(world):
+        np.testing.assert_allclose(res[r]["chi2"], lin["chi2"], rtol=1e-13)
+    ok, x1, it1, _ = one.solve_once(50.0)
+    x = sum(res[r]["x"] for r in range(world))
+    assert ok and all(res[r]["solve"][0] for r in range(world))
+    np.testing.assert_allclose(x, x1, rtol=1e-8, atol=1e-12)
+    n1, s1 = one.optimize(8)
+    p1, l1 = one.estimates()
+    for r in range(world):
+        n, trials, chis = res[r]["lm"]
+        assert n == n1 and trials == [s["trials"] for s in s1]
+        np.testing.assert_allclose(chis, [s["chi2"] for s in s1], rtol=1e-9)
+        np.testing.assert_allclose(res[r]["est"][0], p1, atol=1e-8)
+        np.testing.assert_allclose(res[r]["est"][1], l1, atol=1e-8)
+        np.testing.assert_allclose(res[r]["chi2_after"], one.active_chi2(), rtol=1e-9)
+    gn = SparseOptimizerB200(capi.ALGO_GN)
+    gn.initialize_optimization(g.pose_only(phi=1.0))
+    assert gn.optimize(3)[0] == 3 == res[0]["gn"]
+    np.testing.assert_allclose(res[1]["gn_est"], gn.estimates()[0], atol=1e-8)

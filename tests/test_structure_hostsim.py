@@ -170,3 +170,66 @@ def test_library_exports_every_declared_symbol():
         from sparse_gslam_b200 import SgbError, SparseOptimizerB200
         with pytest.raises(SgbError):
             SparseOptimizerB200()
+
+
+# ------------------------------------------------------------------ row-block partition (multi-GPU path, virtual ranks)
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_partition_covers_graph_and_matches_single_rank(world):
+    """Every row / edge is owned exactly once; linearise, solve and LM over `world` virtual ranks (peer tables wired
+    like the NVLink mappings) equal the single-rank result."""
+    g = gg.make_small(seed=3, P=120, L=20, E_l=300, n_closures=10)
+    one = hostsim.HostSim(g, jac_numeric=False, tol=1e-12)
+    many = hostsim.HostSim(g, jac_numeric=False, tol=1e-12, world=world)
+    assert many.status == capi.OK, many.error
+    st = one.structure()
+    ps = many.partition_stats()
+    nP = int((st["kind"] == 0).sum())
+    nL = int((st["kind"] == 1).sum())
+    assert sum(p["nP"] for p in ps) == nP and sum(p["nL"] for p in ps) == nL
+    n_pp = int((g.pose_fixed[g.pp_i] == 0).sum() if False else g.n_pp)
+    assert sum(p["n_pp_owned"] for p in ps) == n_pp and sum(p["n_pl_owned"] for p in ps) == g.n_pl
+    assert all(p["n_pp"] >= p["n_pp_owned"] and p["n_pl"] >= p["n_pl_owned"] for p in ps)
+    l1, lm = one.linearize(), many.linearize()
+    np.testing.assert_array_equal(lm["H"], l1["H"])      # same arithmetic, same order => bit-identical
+    np.testing.assert_array_equal(lm["b"], l1["b"])
+    np.testing.assert_allclose(lm["chi2"], l1["chi2"], rtol=1e-13)
+    assert many.check_hlp() == 0.0 and one.check_hlp() == 0.0
+    f1, x1, it1, _ = one.solve_once(0.3)
+    fm, xm, itm, _ = many.solve_once(0.3)
+    assert f1 == fm == 0 and abs(it1 - itm) <= 2
+    np.testing.assert_allclose(xm, x1, rtol=1e-9, atol=1e-12)
+    n1, s1 = one.optimize(6, capi.ALGO_LM)
+    nm, sm = many.optimize(6, capi.ALGO_LM)
+    assert n1 == nm and [s["trials"] for s in s1] == [s["trials"] for s in sm]
+    p1, q1 = one.estimates()
+    for r in range(world):  # every replica of the estimates agrees
+        pm, qm = many.estimates(r)
+        np.testing.assert_allclose(pm, p1, atol=1e-9)
+        np.testing.assert_allclose(qm, q1, atol=1e-9)
+
+
+def test_partition_c5_halo_is_small():
+    g = gg.make_c5(rows=40, cols=40)
+    many = hostsim.HostSim(g, jac_numeric=False, world=4)
+    ps = many.partition_stats()
+    assert all(p["nP"] == 400 or p["nP"] == 399 for p in ps)
+    # boustrophedon rows are contiguous in pose id: only the rows next to a cut are halo
+    assert max(p["halo_p"] for p in ps) < 0.25 * 400 * 8
+    one = hostsim.HostSim(g, jac_numeric=False)
+    np.testing.assert_array_equal(many.linearize()["H"], one.linearize()["H"])
+    gp = g.pose_only(phi=1.0)
+    a, b = hostsim.HostSim(gp, world=3), hostsim.HostSim(gp)
+    assert a.optimize(3, capi.ALGO_GN)[0] == b.optimize(3, capi.ALGO_GN)[0] == 3
+    np.testing.assert_allclose(a.estimates(2)[0], b.estimates()[0], atol=1e-9)
+
+
+def test_more_ranks_than_rows():
+    from test_oracle import tiny_graph
+    g = tiny_graph()
+    many = hostsim.HostSim(g, jac_numeric=False, world=4)
+    one = hostsim.HostSim(g, jac_numeric=False)
+    assert many.status == capi.OK
+    np.testing.assert_array_equal(many.linearize()["H"], one.linearize()["H"])
+    many.optimize(3, capi.ALGO_LM)
+    one.optimize(3, capi.ALGO_LM)
+    np.testing.assert_allclose(many.estimates(3)[0], one.estimates()[0], atol=1e-12)
