@@ -1,0 +1,174 @@
+// sgb_g2o_adapter.h -- header-only g2o plugin that puts the B200 backend behind the interface the reference
+// configures in src/sparse_gslam/src/graphs.cpp:9-23:
+//
+//     opt.setAlgorithm(new g2o::OptimizationAlgorithmLevenberg(make_unique<BlockSolver<..>>(make_unique<LinearSolverEigen<..>>())));
+//  becomes
+//     opt.setAlgorithm(new g2o::OptimizationAlgorithmB200(SGB_ALGO_LM));        // setup_lm_opt
+//     opt.setAlgorithm(new g2o::OptimizationAlgorithmB200(SGB_ALGO_GN));        // setup_pose_opt
+//
+// It implements g2o::OptimizationAlgorithm (init / solve / updateStructure / computeMarginals), i.e. it replaces the
+// algorithm + BlockSolver + LinearSolver triple at once, so that LM damping and the accept/reject logic stay on the
+// GPU (SURVEY.md 8b "recommended level"). init() flattens the optimizer's active graph into the SoA of
+// include/sgb_capi.h and uploads it; solve(i) runs one iteration on the device and writes the estimates back to the
+// g2o vertices (the caller reads them right after optimize(), drone.cpp:164-165,186, and uses host push/pop).
+//
+// Compiles against real g2o headers (define SGB_USE_REAL_G2O and include them first) or against
+// g2o_compat/g2o_compat.h (this repository's tests). Links libsgb.so only.
+#pragma once
+#include <cstdio>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/sgb_capi.h"
+#ifndef SGB_USE_REAL_G2O
+#include "g2o_compat/g2o_compat.h"
+#endif
+
+namespace g2o {
+
+class OptimizationAlgorithmB200 : public OptimizationAlgorithm
+#ifndef SGB_USE_REAL_G2O
+    , public SparseOptimizer::ErrorEvaluator
+#endif
+{
+ public:
+  explicit OptimizationAlgorithmB200(int algo, const sgb_options* options = nullptr) : _algo(algo) {
+    sgb_options o;
+    sgb_default_options(&o);
+    if (options) o = *options;
+    sgb_status st = sgb_create(&o, &_h);
+    if (st != SGB_OK) {
+      std::fprintf(stderr, "OptimizationAlgorithmB200: sgb_create failed with status %d (no CUDA device? there is no CPU fallback)\n", (int)st);
+      _h = nullptr;
+    }
+  }
+  ~OptimizationAlgorithmB200() override { if (_h) sgb_destroy(_h); }
+  OptimizationAlgorithmB200(const OptimizationAlgorithmB200&) = delete;
+  OptimizationAlgorithmB200& operator=(const OptimizationAlgorithmB200&) = delete;
+
+  // OptimizationAlgorithmWithHessian::init: here the whole symbolic phase (index mapping is the optimizer's)
+  bool init(bool online = false) override {
+    (void)online;
+    if (!_h || !_optimizer) return false;
+#ifndef SGB_USE_REAL_G2O
+    _optimizer->setErrorEvaluator(this);
+#endif
+    return upload();
+  }
+
+  SolverResult solve(int iteration, bool online = false) override {
+    if (!_h) return Fail;
+    if (iteration > 0 || !_fresh) {
+      // estimates may have been changed on the host between solve() calls (host-side push/pop): re-send them
+      if (!sendEstimates()) return Fail;
+    }
+    _fresh = false;
+    int32_t result = SGB_RESULT_FAIL;
+    sgb_iter_stat stat;
+    sgb_status st = sgb_step(_h, _algo, iteration, online ? 1 : 0, &result, &stat);
+    if (st != SGB_OK) {
+      std::fprintf(stderr, "OptimizationAlgorithmB200::solve: %s\n", sgb_last_error(_h));
+      return Fail;
+    }
+    _last = stat;
+    if (!fetchEstimates()) return Fail;
+    return result == SGB_RESULT_OK ? OK : (result == SGB_RESULT_TERMINATE ? Terminate : Fail);
+  }
+
+  bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) override {
+    // online path: the structure is re-derived (in insertion order) at the next init(); nothing to patch here
+    return _h != nullptr;
+  }
+
+  const sgb_iter_stat& lastIteration() const { return _last; }
+  sgb_handle* handle() const { return _h; }
+
+  // computeActiveErrors()/activeChi2() of the caller's gate (drone.cpp:164-165), evaluated on the device
+  bool chi2(number_t* plain, number_t* robust)
+#ifndef SGB_USE_REAL_G2O
+      override
+#endif
+  {
+    if (!_h || !sendEstimates()) return false;
+    double c[2] = {0, 0};
+    if (sgb_chi2(_h, c) != SGB_OK) return false;
+    *plain = c[0];
+    *robust = c[1];
+    return true;
+  }
+
+ private:
+  bool upload() {
+    const auto& verts = _optimizer->activeVertices();
+    const auto& edges = _optimizer->activeEdges();
+    _poses.clear(); _lms.clear();
+    std::unordered_map<const HyperGraph::Vertex*, int> pidx, lidx;
+    std::vector<int32_t> pose_id, lm_id;
+    std::vector<uint8_t> pose_fixed, lm_fixed;
+    for (auto* v : verts) {
+      if (v->dimension() == 3) { pidx[v] = (int)_poses.size(); _poses.push_back(v); pose_id.push_back(v->id()); pose_fixed.push_back(v->fixed()); }
+      else if (v->dimension() == 2) { lidx[v] = (int)_lms.size(); _lms.push_back(v); lm_id.push_back(v->id()); lm_fixed.push_back(v->fixed()); }
+      else { std::fprintf(stderr, "OptimizationAlgorithmB200: unsupported vertex dimension %d\n", v->dimension()); return false; }
+    }
+    _pose_est.assign(3 * _poses.size(), 0.0);
+    _lm_est.assign(2 * _lms.size(), 0.0);
+    gatherEstimates();
+    std::vector<int32_t> pp_i, pp_j, pl_p, pl_l;
+    std::vector<double> pp_z, pp_info, pp_phi, pl_z, pl_info;
+    std::vector<int64_t> pp_seq, pl_seq;
+    for (auto* e : edges) {
+      if (e->dimension() == 3) {
+        auto* ee = static_cast<EdgeSE2*>(e);
+        pp_i.push_back(pidx.at(e->vertex(0))); pp_j.push_back(pidx.at(e->vertex(1)));
+        const SE2& z = ee->measurement();
+        pp_z.insert(pp_z.end(), {z[0], z[1], z[2]});
+        const auto& I = ee->information();
+        pp_info.insert(pp_info.end(), {I(0, 0), I(0, 1), I(0, 2), I(1, 1), I(1, 2), I(2, 2)});
+        pp_phi.push_back(e->robustKernel() ? e->robustKernel()->delta() : 0.0);  // the reference only uses RobustKernelDCS
+        pp_seq.push_back(e->internalId());
+      } else if (e->dimension() == 2) {
+        auto* ee = static_cast<EdgeSE2RhoTheta*>(e);
+        pl_p.push_back(pidx.at(e->vertex(0))); pl_l.push_back(lidx.at(e->vertex(1)));
+        const auto& z = ee->measurement();
+        pl_z.insert(pl_z.end(), {z[0], z[1]});
+        const auto& I = ee->information();
+        pl_info.insert(pl_info.end(), {I(0, 0), I(0, 1), I(1, 1)});
+        pl_seq.push_back(e->internalId());
+      } else { std::fprintf(stderr, "OptimizationAlgorithmB200: unsupported edge dimension %d\n", e->dimension()); return false; }
+    }
+    sgb_graph_soa g{};
+    g.n_poses = (int32_t)_poses.size(); g.pose_id = pose_id.data(); g.pose_est = _pose_est.data(); g.pose_fixed = pose_fixed.data();
+    g.n_landmarks = (int32_t)_lms.size(); g.lm_id = lm_id.data(); g.lm_est = _lm_est.data(); g.lm_fixed = lm_fixed.data();
+    g.n_pp = (int32_t)pp_i.size(); g.pp_i = pp_i.data(); g.pp_j = pp_j.data(); g.pp_z = pp_z.data(); g.pp_info = pp_info.data();
+    g.pp_phi = pp_phi.data(); g.pp_seq = pp_seq.data();
+    g.n_pl = (int32_t)pl_p.size(); g.pl_pose = pl_p.data(); g.pl_lm = pl_l.data(); g.pl_z = pl_z.data(); g.pl_info = pl_info.data();
+    g.pl_seq = pl_seq.data();
+    sgb_status st = sgb_set_graph(_h, &g);
+    if (st != SGB_OK) { std::fprintf(stderr, "OptimizationAlgorithmB200::init: %s\n", sgb_last_error(_h)); return false; }
+    _fresh = true;
+    return true;
+  }
+  void gatherEstimates() {
+    for (size_t i = 0; i < _poses.size(); ++i) _poses[i]->getEstimateData(&_pose_est[3 * i]);
+    for (size_t i = 0; i < _lms.size(); ++i) _lms[i]->getEstimateData(&_lm_est[2 * i]);
+  }
+  bool sendEstimates() {
+    gatherEstimates();
+    return sgb_set_estimates(_h, _pose_est.data(), _lm_est.data()) == SGB_OK;
+  }
+  bool fetchEstimates() {
+    if (sgb_get_estimates(_h, _pose_est.data(), _lm_est.data()) != SGB_OK) return false;
+    for (size_t i = 0; i < _poses.size(); ++i) if (!_poses[i]->fixed()) _poses[i]->setEstimateData(&_pose_est[3 * i]);
+    for (size_t i = 0; i < _lms.size(); ++i) if (!_lms[i]->fixed()) _lms[i]->setEstimateData(&_lm_est[2 * i]);
+    return true;
+  }
+
+  int _algo;
+  sgb_handle* _h = nullptr;
+  bool _fresh = false;
+  std::vector<OptimizableGraph::Vertex*> _poses, _lms;
+  std::vector<double> _pose_est, _lm_est;
+  sgb_iter_stat _last{};
+};
+
+}  // namespace g2o
