@@ -245,6 +245,7 @@ def main():
     tot_iters = 0
     agg = dict(linearize_ms=0.0, setup_ms=0.0, pcg_ms=0.0, update_ms=0.0, total_ms=0.0, pcg_iters=0, trials=0,
                linearizations=0, kernel_launches=0)
+    pcg_phase = [0.0] * 4
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         n, stats = opt.optimize(iters, resident=True)
@@ -252,6 +253,7 @@ def main():
         t = opt.timings()
         for k in agg:
             agg[k] += t[k]
+        pcg_phase = [a + b for a, b in zip(pcg_phase, t["pcg_phase_ms"])]
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
@@ -310,7 +312,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_pcg", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_pcg_iteration": b_iter, "pcg_iterations": agg["pcg_iters"],
-                "pcg_launches": agg["trials"], "share_of_step": agg["pcg_ms"] / dev_ms if dev_ms > 0 else None}
+                "pcg_launches": agg["trials"], "share_of_step": agg["pcg_ms"] / dev_ms if dev_ms > 0 else None,
+                "pcg_phase_us_per_iteration": [1e3 * v / max(1, agg["pcg_iters"]) for v in pcg_phase]}
     line = {
         "metric": "LM iterations/s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": dev_ms_max / max(1, args.steps), "higher_is_better": True,

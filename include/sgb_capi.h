@@ -126,6 +126,10 @@ typedef struct sgb_timings {
   int64_t trials;           /* total LM trials (GN: iterations) */
   int64_t linearizations;
   int64_t kernel_launches;  /* kernels launched by this library */
+  /* wall time inside the persistent PCG kernel, split by phase of an iteration (barrier waits included):
+   * [0] landmark-major pass t = W Hlp^T p, [1] pose-major pass q = S p and p.q, [2] x/r/z update and r.z,
+   * [3] search-direction update */
+  double pcg_phase_ms[4];
 } sgb_timings;
 
 /* this rank's share of a row-block partitioned graph */

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsgb.so")
+LIB_PATH = os.environ.get("SGB_LIB") or os.path.join(HERE, "libsgb.so")  # SGB_LIB: a variant build (tuning runs)
 
 OK, ERR_INVALID, ERR_NO_DEVICE, ERR_CUDA, ERR_NOT_INITIALIZED, ERR_UNSUPPORTED, ERR_SOLVE_FAILED, ERR_COMM = range(8)
 RESULT_TERMINATE, RESULT_OK, RESULT_FAIL = 2, 1, -1
@@ -56,10 +56,12 @@ class StructureInfo(C.Structure):
 class Timings(C.Structure):
     _fields_ = [("linearize_ms", C.c_double), ("setup_ms", C.c_double), ("pcg_ms", C.c_double),
                 ("update_ms", C.c_double), ("total_ms", C.c_double), ("pcg_iters", C.c_int64), ("trials", C.c_int64),
-                ("linearizations", C.c_int64), ("kernel_launches", C.c_int64)]
+                ("linearizations", C.c_int64), ("kernel_launches", C.c_int64), ("pcg_phase_ms", C.c_double * 4)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["pcg_phase_ms"] = list(self.pcg_phase_ms)
+        return d
 
 
 class PartitionInfo(C.Structure):

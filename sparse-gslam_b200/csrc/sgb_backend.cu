@@ -7,10 +7,13 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sgb_capi.h"
@@ -38,7 +41,12 @@ struct sgb_handle {
   Structure S;
   LocalPlan LP;
   DevGraph G;
-  std::vector<void*> allocs;
+  std::vector<void*> allocs;  // individually cudaMalloc'ed: the IPC-exported arena (world > 1) and push/pop backups
+  // Slab pool for everything else: sgb_set_graph is called once per key-frame by the reference's caller
+  // (drone.cpp:146-156), so the device memory of the previous graph is recycled instead of freed and re-allocated
+  // (cudaFree/cudaMalloc of ~60 arrays cost up to 0.5 s on a 1M-pose graph).
+  struct Slab { char* base; size_t cap, off; };
+  std::vector<Slab> slabs;
   // peer-mapped arena: estimates (2 buffers), p, x_p, t, b_l, Hll_inv, mailbox -- same offsets on every rank
   char* arena = nullptr;
   size_t arena_bytes = 0;
@@ -76,13 +84,34 @@ int grid_for(int n) {
   return std::max(1, std::min(b, 148 * 8));
 }
 
+// individually allocated (and individually freed) device memory
 template <class T>
-sgb_status dalloc(sgb_handle* h, T** out, size_t n) {
+sgb_status dalloc_raw(sgb_handle* h, T** out, size_t n) {
   *out = nullptr;
   void* p = nullptr;
   size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
   SGB_CUDA(cudaMalloc(&p, bytes));
   h->allocs.push_back(p);
+  *out = (T*)p;
+  return SGB_OK;
+}
+// pooled device memory, recycled by the next sgb_set_graph (256-byte aligned)
+template <class T>
+sgb_status dalloc(sgb_handle* h, T** out, size_t n) {
+  *out = nullptr;
+  size_t bytes = (std::max<size_t>(n, 1) * sizeof(T) + 255) & ~(size_t)255;
+  for (auto& sl : h->slabs)
+    if (sl.cap - sl.off >= bytes) {
+      *out = (T*)(sl.base + sl.off);
+      sl.off += bytes;
+      return SGB_OK;
+    }
+  size_t total = 0;
+  for (auto& sl : h->slabs) total += sl.cap;
+  size_t cap = std::max(bytes, std::max<size_t>(total / 2, (size_t)8 << 20));
+  void* p = nullptr;
+  SGB_CUDA(cudaMalloc(&p, cap));
+  h->slabs.push_back({(char*)p, cap, bytes});
   *out = (T*)p;
   return SGB_OK;
 }
@@ -117,6 +146,7 @@ void free_graph(sgb_handle* h) {
   h->arena = nullptr;
   for (void* p : h->allocs) cudaFree(p);
   h->allocs.clear();
+  for (auto& sl : h->slabs) sl.off = 0;
   h->stack.clear();
   h->has_graph = false;
   h->lm_state_valid = false;
@@ -281,6 +311,7 @@ sgb_status do_step(sgb_handle* h, int algo, int iteration, int* result, sgb_iter
   h->tm.update_ms += t_upd;
   h->tm.pcg_iters += pcg_total;
   h->tm.trials += trials;
+  for (int i = 0; i < 4; ++i) h->tm.pcg_phase_ms[i] = 1e-6 * (double)h->h_sc->pcg_phase_ns[i];
   if (stat) {
     stat->iteration = iteration;
     stat->trials = trials;
@@ -301,6 +332,7 @@ sgb_status do_optimize(sgb_handle* h, int algo, int max_iters, int* iters_done, 
     return SGB_ERR_INVALID;
   }
   std::memset(&h->tm, 0, sizeof h->tm);
+  SGB_CUDA(cudaMemsetAsync(&h->d_sc->pcg_phase_ns, 0, sizeof h->d_sc->pcg_phase_ns, h->stream));
   cudaEvent_t t0, t1;
   SGB_CUDA(cudaEventCreate(&t0));
   SGB_CUDA(cudaEventCreate(&t1));
@@ -386,7 +418,7 @@ sgb_status sgb_create(const sgb_options* opt, sgb_handle** out) {
   cudaMemset(h->d_sc, 0, sizeof(DevScalars));
   if ((e = cudaMallocHost((void**)&h->h_sc, sizeof(DevScalars))) != cudaSuccess) return fail("cudaMallocHost", e);
   std::memset(h->h_sc, 0, sizeof(DevScalars));
-  size_t pb = 3 * (size_t)kMaxBlocks * sizeof(double);
+  size_t pb = 4 * (size_t)kMaxBlocks * sizeof(double);  // k_pcg double-buffers two partial sums
   if ((e = cudaMalloc((void**)&h->d_part_p, pb)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc((void**)&h->d_part_l, pb)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc((void**)&h->d_part_e, pb)) != cudaSuccess) return fail("cudaMalloc", e);
@@ -400,6 +432,8 @@ void sgb_destroy(sgb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   free_graph(h);
+  for (auto& sl : h->slabs) cudaFree(sl.base);
+  h->slabs.clear();
   cudaFree(h->d_sc);
   cudaFreeHost(h->h_sc);
   cudaFree(h->d_part_p);
@@ -435,13 +469,24 @@ static void fill_peer_tables(sgb_handle* h) {
 
 static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int world, int rank) {
   if (!h || !g) return SGB_ERR_INVALID;
+  static const bool prof = std::getenv("SGB_PROFILE") != nullptr;  // per-phase host timing of this call on stderr
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[sgb_set_graph] %-18s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+    tp0 = t;
+  };
   SGB_CUDA(cudaSetDevice(h->device));
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   free_graph(h);
+  lap("free");
   sgb_status st = build_structure(*g, h->S, h->err);
   if (st != SGB_OK) return st;
+  lap("build_structure");
   st = partition(h->S, world, rank, h->LP, h->err);
   if (st != SGB_OK) return st;
+  lap("partition");
   const Structure& S = h->S;
   const LocalPlan& P = h->LP;
   DevGraph& G = h->G;
@@ -462,7 +507,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   h->off_t = take(2 * (size_t)P.capL); h->off_bl = take(2 * (size_t)P.capL); h->off_hllinv = take(3 * (size_t)P.capL);
   h->off_mbox = off; off = align256(off + sizeof(Mailbox));
   h->arena_bytes = off;
-  if ((st = dalloc(h, &h->arena, h->arena_bytes)) != SGB_OK) return st;
+  if ((st = (world > 1 ? dalloc_raw(h, &h->arena, h->arena_bytes) : dalloc(h, &h->arena, h->arena_bytes))) != SGB_OK) return st;
   SGB_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
   for (int r = 0; r < kMaxRanks; ++r) h->peer_base[r] = nullptr;
   h->peer_base[rank] = h->arena;
@@ -476,17 +521,13 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   }
   if (np) SGB_CUDA(cudaMemcpyAsync(h->d_pose0, g->pose_est, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   if (nl) SGB_CUDA(cudaMemcpyAsync(h->d_lm0, g->lm_est, nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-#define UP(field, vec) if ((st = upload(h, &G.field, vec)) != SGB_OK) return st
-  UP(pose_of_l, P.pose_of_l); UP(lm_of_l, P.lm_of_l);
-  UP(pp_i, P.pp_i); UP(pp_j, P.pp_j); UP(pp_hi, P.pp_hi); UP(pp_hj, P.pp_hj);
-  UP(pp_e_ij, P.pp_e_ij); UP(pp_e_ji, P.pp_e_ji); UP(pp_dup, P.pp_dup);
-  UP(pl_p, P.pl_p); UP(pl_l, P.pl_l); UP(pl_hp, P.pl_hp); UP(pl_hl, P.pl_hl);
-  UP(pl_e_pl, P.pl_e_pl); UP(pl_e_lp, P.pl_e_lp); UP(pl_dup, P.pl_dup);
-  UP(pinc_ptr, P.pinc_ptr); UP(pinc, P.pinc); UP(linc_ptr, P.linc_ptr); UP(linc, P.linc);
-  UP(hpp_diag, P.hpp_diag); UP(lp_row2l, P.lp_row2l);
-  {  // edge data, component-major, local edges; EdgeSE2::setMeasurement caches the inverse
-    std::vector<double> zinv(3 * (size_t)P.n_pp), info(6 * (size_t)P.n_pp), phi(P.n_pp, 0.0);
-    for (int k = 0; k < P.n_pp; ++k) {
+  lap("arena+estimates");
+  // edge data, component-major, local edges; EdgeSE2::setMeasurement caches the inverse. The SoA transposes run on
+  // host threads while this thread uploads the symbolic maps.
+  std::vector<double> zinv(3 * (size_t)P.n_pp), info(6 * (size_t)P.n_pp), phi(P.n_pp, 0.0);
+  std::vector<double> z(2 * (size_t)P.n_pl), linfo(3 * (size_t)P.n_pl);
+  auto fill_pp = [&](int k0, int k1) {
+    for (int k = k0; k < k1; ++k) {
       int s = S.pp_src[P.pp_g[k]];
       double x = g->pp_z[3 * (size_t)s], y = g->pp_z[3 * (size_t)s + 1], th = g->pp_z[3 * (size_t)s + 2];
       double thi = normalize_theta(-th);
@@ -497,17 +538,48 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
       for (int c6 = 0; c6 < 6; ++c6) info[(size_t)c6 * P.n_pp + k] = g->pp_info[6 * (size_t)s + c6];
       if (g->pp_phi) phi[k] = g->pp_phi[s];
     }
-    UP(pp_zinv, zinv); UP(pp_info, info); UP(pp_phi, phi);
-    std::vector<double> z(2 * (size_t)P.n_pl), linfo(3 * (size_t)P.n_pl);
-    for (int k = 0; k < P.n_pl; ++k) {
+  };
+  auto fill_pl = [&](int k0, int k1) {
+    for (int k = k0; k < k1; ++k) {
       int s = S.pl_src[P.pl_g[k]];
       z[k] = g->pl_z[2 * (size_t)s];
       z[(size_t)P.n_pl + k] = g->pl_z[2 * (size_t)s + 1];
       for (int c3 = 0; c3 < 3; ++c3) linfo[(size_t)c3 * P.n_pl + k] = g->pl_info[3 * (size_t)s + c3];
     }
-    UP(pl_z, z); UP(pl_info, linfo);
+  };
+  std::vector<std::thread> workers;
+  {
+    const int nth = ((size_t)P.n_pp + P.n_pl > 200000) ? (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 0;
+    if (nth == 0) {
+      fill_pp(0, P.n_pp);
+      fill_pl(0, P.n_pl);
+    } else {
+      for (int t = 0; t < nth; ++t) {
+        int a0 = (int)((int64_t)P.n_pp * t / nth), a1 = (int)((int64_t)P.n_pp * (t + 1) / nth);
+        int b0 = (int)((int64_t)P.n_pl * t / nth), b1 = (int)((int64_t)P.n_pl * (t + 1) / nth);
+        workers.emplace_back([=, &fill_pp, &fill_pl]() { fill_pp(a0, a1); fill_pl(b0, b1); });
+      }
+    }
   }
+  struct Joiner {  // the workers reference locals of this frame: never leave it (early error returns) before they end
+    std::vector<std::thread>& w;
+    ~Joiner() { for (auto& t : w) if (t.joinable()) t.join(); }
+  } joiner{workers};
+#define UP(field, vec) if ((st = upload(h, &G.field, vec)) != SGB_OK) return st
+  UP(pose_of_l, P.pose_of_l); UP(lm_of_l, P.lm_of_l);
+  UP(pp_i, P.pp_i); UP(pp_j, P.pp_j); UP(pp_hi, P.pp_hi); UP(pp_hj, P.pp_hj);
+  UP(pp_e_ij, P.pp_e_ij); UP(pp_e_ji, P.pp_e_ji); UP(pp_dup, P.pp_dup);
+  UP(pl_p, P.pl_p); UP(pl_l, P.pl_l); UP(pl_hp, P.pl_hp); UP(pl_hl, P.pl_hl);
+  UP(pl_e_pl, P.pl_e_pl); UP(pl_e_lp, P.pl_e_lp); UP(pl_dup, P.pl_dup);
+  UP(pinc_ptr, P.pinc_ptr); UP(pinc, P.pinc); UP(linc_ptr, P.linc_ptr); UP(linc, P.linc);
+  UP(hpp_diag, P.hpp_diag); UP(lp_row2l, P.lp_row2l);
+  lap("upload maps");
+  for (auto& t : workers) t.join();
+  workers.clear();
+  UP(pp_zinv, zinv); UP(pp_info, info); UP(pp_phi, phi);
+  UP(pl_z, z); UP(pl_info, linfo);
 #undef UP
+  lap("edge data");
   if ((st = upload_sell(h, &G.Hpp, P.Hpp, 9)) != SGB_OK) return st;
   if ((st = upload_sell(h, &G.Hpl, P.Hpl, 6)) != SGB_OK) return st;
   if ((st = upload_sell(h, &G.Hlp, P.Hlp, 6)) != SGB_OK) return st;
@@ -528,6 +600,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   int want = std::max(1, (std::max(P.nP, P.nL) + kThreads - 1) / kThreads);
   h->pcg_blocks = std::min(std::min(limit, want), kMaxBlocks);
   SGB_CUDA(cudaStreamSynchronize(h->stream));
+  lap("matrices+sync");
   h->has_graph = true;
   h->lm_state_valid = false;
   return SGB_OK;
@@ -777,8 +850,8 @@ sgb_status sgb_push(sgb_handle* h) {
   SGB_CUDA(cudaSetDevice(h->device));
   double *p = nullptr, *l = nullptr;
   size_t np = 3 * (size_t)h->S.P_all, nl = 2 * (size_t)h->S.L_all;
-  if ((st = dalloc(h, &p, np)) != SGB_OK) return st;
-  if ((st = dalloc(h, &l, nl)) != SGB_OK) return st;
+  if ((st = dalloc_raw(h, &p, np)) != SGB_OK) return st;
+  if ((st = dalloc_raw(h, &l, nl)) != SGB_OK) return st;
   const DevGraph& G = h->G;
   if (np) SGB_CUDA(cudaMemcpyAsync(p, G.pose_buf[G.cur][G.rank], np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   if (nl) SGB_CUDA(cudaMemcpyAsync(l, G.lm_buf[G.cur][G.rank], nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));

@@ -23,6 +23,11 @@ namespace sgb {
 
 constexpr int kThreads = 256;
 constexpr int kMaxBlocks = 4096;  // partial-sum slots per reduction
+// persistent PCG kernel: CTAs per SM the register budget is sized for (the software-pipelined SpMV rows keep two
+// blocks' worth of loads in flight per thread and need ~80 registers)
+#ifndef SGB_PCG_MIN_BLOCKS
+#define SGB_PCG_MIN_BLOCKS 3
+#endif
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -85,6 +90,19 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
 }
 __device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 // All-reduce of up to 4 block-uniform doubles across the ranks (op 0 = sum, 1 = max), also a barrier: everything
 // this GPU wrote before the caller's preceding grid-wide sync is visible to the peers once they pass.
@@ -275,6 +293,23 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
   ++seq;
   epoch += nb;
   const int slot = (int)(seq & 1ull);
+  if (g.world == 1) {
+    // One GPU: flat barrier, gpu scope only. Every CTA deposits its partial (double-buffered by the parity of seq:
+    // a CTA can be at most one barrier ahead of the slowest reader), arrives with a release reduction, spins on an
+    // acquire load, and then sums ALL partials itself in index order -- the same value in every CTA, and no
+    // "last CTA reduces and publishes" hop on the critical path.
+    double* mypart = part + (size_t)slot * 2 * kMaxBlocks;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 0; k < nv; ++k) __stcg(&mypart[k * kMaxBlocks + blockIdx.x], vals[k]);
+      red_release_gpu_add_u64(bar, 1ull);
+      while (ld_acquire_gpu_u64(bar) < epoch) {
+      }
+    }
+    __syncthreads();
+    for (int k = 0; k < nv; ++k) vals[k] = reduce_partials(mypart + k * kMaxBlocks, (int)nb, sm);
+    return;
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     for (int k = 0; k < nv; ++k) part[k * kMaxBlocks + blockIdx.x] = vals[k];
@@ -311,10 +346,18 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
 // Preconditioned conjugate gradient on S = (Hpp + lambda I) - Hpl (Hll + lambda I)^-1 Hpl^T, M = blockdiag(S).
 // One launch per GPU runs the whole solve; every CTA of every rank evaluates the same scalars from the same sums, so
 // control flow is uniform across the grid and across the GPUs without a host round trip or a collective kernel.
-__global__ void __launch_bounds__(kThreads) k_pcg(DevGraph g, DevScalars* sc, double* part, unsigned long long* bar,
-                                                 PcgParams prm) {
+__global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g, DevScalars* sc, double* part,
+                                                                     unsigned long long* bar, PcgParams prm) {
   __shared__ double sm[32];
   __shared__ int s_last;
+  // wall time of the four phases of an iteration as seen by CTA 0 (barrier waits included), for profiles/
+  unsigned long long ph_ns[4] = {0, 0, 0, 0}, t_ph = globaltimer_ns();
+#define SGB_PHASE_LAP(i)                     \
+  do {                                       \
+    unsigned long long _t = globaltimer_ns(); \
+    ph_ns[i] += _t - t_ph;                   \
+    t_ph = _t;                               \
+  } while (0)
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
   const unsigned int nb = gridDim.x;
@@ -344,15 +387,18 @@ __global__ void __launch_bounds__(kThreads) k_pcg(DevGraph g, DevScalars* sc, do
   } else {
     const double target = prm.tol * prm.tol * rz0;
     flag = 1;
+    t_ph = globaltimer_ns();
     while (it < prm.maxit) {
       if (g.capL > 0) {
         for (int row = tid; row < g.nL; row += nthreads) schur_phaseA_row(g, row);
         grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, &s_last);  // every rank's t segment is complete
       }
+      SGB_PHASE_LAP(0);
       acc = 0.0;
       for (int lp = tid; lp < g.nP; lp += nthreads) acc += schur_phaseB_row(g, lp, lambda);
       double pq = block_sum(acc, sm);
       grid_xreduce(g, bar, nb, epoch, seq, part, &pq, 1, sm, &s_last);
+      SGB_PHASE_LAP(1);
       if (!(pq > 0.0)) {  // S not positive definite (or NaN): g2o's "Cholesky failure" analogue
         flag = 2;
         break;
@@ -372,6 +418,7 @@ __global__ void __launch_bounds__(kThreads) k_pcg(DevGraph g, DevScalars* sc, do
       }
       double rzn = block_sum(acc, sm);
       grid_xreduce(g, bar, nb, epoch, seq, part, &rzn, 1, sm, &s_last);
+      SGB_PHASE_LAP(2);
       ++it;
       if (!(rzn == rzn)) {
         flag = 2;
@@ -390,9 +437,12 @@ __global__ void __launch_bounds__(kThreads) k_pcg(DevGraph g, DevScalars* sc, do
           p[o] = g.z[o] + beta * p[o];
         }
       grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, &s_last);  // every rank's p segment is complete
+      SGB_PHASE_LAP(3);
     }
   }
+#undef SGB_PHASE_LAP
   if (tid == 0) {
+    for (int i = 0; i < 4; ++i) sc->pcg_phase_ns[i] += ph_ns[i];
     sc->xseq = seq;
     sc->rz0 = rz0;
     sc->rz = rz;

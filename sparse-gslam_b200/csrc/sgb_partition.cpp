@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <numeric>
+#include <thread>
 
 #include "sgb_types.h"
 
@@ -25,19 +26,36 @@ inline int sell_row_cols(const HostSell& M, int sell_row, std::vector<int32_t>& 
 inline int entry_k(const HostSell& M, int sell_row, int entry) { return (entry - M.sbase[sell_row >> 5]) >> 5; }
 inline int entry_of(const HostSell& M, int sell_row, int k) { return M.sbase[sell_row >> 5] + k * 32 + (sell_row & 31); }
 
-void build_local_sell(const std::vector<std::vector<int32_t>>& rows, HostSell& S) {
-  int n = (int)rows.size();
+// flat row lists (CSR): row r holds col[ptr[r] .. ptr[r+1])
+struct FlatRows {
+  std::vector<int32_t> ptr, col;
+  explicit FlatRows(int n = 0) : ptr(1, 0) { ptr.reserve((size_t)n + 1); }
+  void close_row() { ptr.push_back((int32_t)col.size()); }
+  int rows() const { return (int)ptr.size() - 1; }
+  int size(int r) const { return ptr[r + 1] - ptr[r]; }
+};
+
+// SELL row s of the result holds list row order[s] (identity when order is null)
+void build_local_sell(const FlatRows& rows, const std::vector<int32_t>* order, HostSell& S) {
+  int n = rows.rows();
   S.rows = n;
   S.nslices = (n + 31) / 32;
   S.sbase.assign(S.nslices + 1, 0);
   for (int s = 0; s < S.nslices; ++s) {
-    size_t w = 0;
-    for (int lane = 0; lane < 32 && s * 32 + lane < n; ++lane) w = std::max(w, rows[s * 32 + lane].size());
-    S.sbase[s + 1] = S.sbase[s] + (int)w * 32;
+    int w = 0;
+    for (int lane = 0; lane < 32 && s * 32 + lane < n; ++lane) {
+      int r = s * 32 + lane;
+      w = std::max(w, rows.size(order ? (*order)[r] : r));
+    }
+    S.sbase[s + 1] = S.sbase[s] + w * 32;
   }
   S.col.assign((size_t)S.sbase[S.nslices], -1);
-  for (int r = 0; r < n; ++r)
-    for (size_t k = 0; k < rows[r].size(); ++k) S.col[(size_t)S.sbase[r >> 5] + k * 32 + (r & 31)] = rows[r][k];
+  for (int r = 0; r < n; ++r) {
+    int lr = order ? (*order)[r] : r;
+    int32_t* dst = S.col.data() + (size_t)S.sbase[r >> 5] + (r & 31);
+    const int32_t* src = rows.col.data() + rows.ptr[lr];
+    for (int k = 0, m = rows.size(lr); k < m; ++k) dst[(size_t)k * 32] = src[k];
+  }
 }
 
 }  // namespace
@@ -84,6 +102,8 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
 
   // ---- local edges: owned (chi2 accounted here) first, then the halo edges; global order inside each group
   std::vector<int32_t> pp_g2l(S.n_pp, -1), pl_g2l(S.n_pl, -1);
+  P.pp_g.reserve(world == 1 ? S.n_pp : S.n_pp / world + 1024);
+  P.pl_g.reserve(world == 1 ? S.n_pl : S.n_pl / world + 1024);
   for (int pass = 0; pass < 2; ++pass) {
     for (int k = 0; k < S.n_pp; ++k) {
       int hi = S.pp_hi[k], hj = S.pp_hj[k];
@@ -111,54 +131,69 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
   P.n_pp = (int)P.pp_g.size();
   P.n_pl = (int)P.pl_g.size();
 
-  // ---- local SELL matrices with encoded columns
-  std::vector<int32_t> cols;
-  {
-    std::vector<std::vector<int32_t>> rows(P.nP), rows_pl(P.nP);
+  // ---- local SELL matrices with encoded columns (pose rows and landmark rows are independent: two host threads)
+  int64_t halo_p_pose = 0, halo_p_lm = 0;
+  auto build_pose_rows = [&]() {
+    std::vector<int32_t> cols;
+    FlatRows rows(P.nP), rows_pl(P.nP);
+    rows.col.reserve(S.Hpp.col.size() / world + 1024);
+    rows_pl.col.reserve(S.Hpl.col.size() / world + 1024);
     for (int l = 0; l < P.nP; ++l) {
       int hp = P.p_begin + l;
       sell_row_cols(S.Hpp, hp, cols);
       for (int c : cols) {
-        rows[l].push_back(enc_pose(c, P.chunkP));
-        if (owner_p(c) != rank) P.halo_p++;
+        rows.col.push_back(enc_pose(c, P.chunkP));
+        if (owner_p(c) != rank) halo_p_pose++;
       }
+      rows.close_row();
       sell_row_cols(S.Hpl, hp, cols);
       for (int c : cols) {
-        rows_pl[l].push_back(P.enc_lm[c]);
+        rows_pl.col.push_back(P.enc_lm[c]);
         if (lm_owner[c] != rank) P.halo_t++;
       }
+      rows_pl.close_row();
     }
-    build_local_sell(rows, P.Hpp);
-    build_local_sell(rows_pl, P.Hpl);
+    build_local_sell(rows, nullptr, P.Hpp);
+    build_local_sell(rows_pl, nullptr, P.Hpl);
     P.hpp_diag.resize(P.nP);
     for (int l = 0; l < P.nP; ++l) {
       int hp = P.p_begin + l;
       P.hpp_diag[l] = entry_of(P.Hpp, l, entry_k(S.Hpp, hp, S.hpp_diag[hp]));
     }
-  }
+  };
   std::vector<int32_t> lrow_of_local(P.nL, 0);  // local landmark -> Hlp row
-  {
+  auto build_lm_rows = [&]() {
+    std::vector<int32_t> cols;
     // owned landmarks sorted by descending observer count (stable) to keep the SELL padding small
-    std::vector<std::vector<int32_t>> obs(P.nL);
+    FlatRows obs(P.nL);
+    obs.col.reserve(S.Hlp.col.size() / world + 1024);
     for (int l = 0; l < P.nL; ++l) {
       sell_row_cols(S.Hlp, S.lp_h2row[P.lm_global[l]], cols);
       for (int c : cols) {
-        obs[l].push_back(enc_pose(c, P.chunkP));
-        if (owner_p(c) != rank) P.halo_p++;
+        obs.col.push_back(enc_pose(c, P.chunkP));
+        if (owner_p(c) != rank) halo_p_lm++;
       }
+      obs.close_row();
     }
     P.lp_row2l.resize(P.nL);
     std::iota(P.lp_row2l.begin(), P.lp_row2l.end(), 0);
-    std::stable_sort(P.lp_row2l.begin(), P.lp_row2l.end(), [&](int a, int b) { return obs[a].size() > obs[b].size(); });
-    std::vector<std::vector<int32_t>> rows(P.nL);
-    for (int r = 0; r < P.nL; ++r) {
-      rows[r] = obs[P.lp_row2l[r]];
-      lrow_of_local[P.lp_row2l[r]] = r;
-    }
-    build_local_sell(rows, P.Hlp);
+    std::stable_sort(P.lp_row2l.begin(), P.lp_row2l.end(), [&](int a, int b) { return obs.size(a) > obs.size(b); });
+    for (int r = 0; r < P.nL; ++r) lrow_of_local[P.lp_row2l[r]] = r;
+    build_local_sell(obs, &P.lp_row2l, P.Hlp);
+  };
+  const bool threaded = (size_t)P.n_pp + P.n_pl > 200000;
+  if (threaded) {
+    std::thread t(build_lm_rows);
+    build_pose_rows();
+    t.join();
+  } else {
+    build_pose_rows();
+    build_lm_rows();
   }
+  P.halo_p = halo_p_pose + halo_p_lm;
 
   // ---- per-edge arrays
+  auto build_pp_edges = [&]() {
   P.pp_i.resize(P.n_pp); P.pp_j.resize(P.n_pp); P.pp_hi.resize(P.n_pp); P.pp_hj.resize(P.n_pp);
   P.pp_e_ij.assign(P.n_pp, -1); P.pp_e_ji.assign(P.n_pp, -1); P.pp_dup.assign(P.n_pp, -1);
   for (int l = 0; l < P.n_pp; ++l) {
@@ -171,6 +206,8 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
       if (pose_local(hj)) P.pp_e_ji[l] = entry_of(P.Hpp, hj - P.p_begin, entry_k(S.Hpp, hj, S.pp_e_ji[k]));
     }
   }
+  };
+  auto build_pl_edges = [&]() {
   P.pl_p.resize(P.n_pl); P.pl_l.resize(P.n_pl); P.pl_hp.resize(P.n_pl); P.pl_hl.resize(P.n_pl);
   P.pl_e_pl.assign(P.n_pl, -1); P.pl_e_lp.assign(P.n_pl, -1); P.pl_dup.assign(P.n_pl, -1);
   for (int l = 0; l < P.n_pl; ++l) {
@@ -187,8 +224,11 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
     }
   }
 
+  };
   // ---- incidence lists of owned rows, local edge ids
+  auto build_incidence = [&]() {
   P.pinc_ptr.assign(P.nP + 1, 0);
+  P.pinc.reserve(P.nP > 0 ? (size_t)(S.pinc_ptr[P.p_begin + P.nP] - S.pinc_ptr[P.p_begin]) : 0);
   for (int l = 0; l < P.nP; ++l) {
     int hp = P.p_begin + l;
     for (int q = S.pinc_ptr[hp]; q < S.pinc_ptr[hp + 1]; ++q) {
@@ -206,7 +246,9 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
     P.linc_ptr[l + 1] = (int)P.linc.size();
   }
 
+  };
   // ---- reference-order export map
+  auto build_export = [&]() {
   P.blk_owner.resize(S.blk_row.size());
   P.blk_entry.assign(S.blk_row.size(), -1);
   for (size_t b = 0; b < S.blk_row.size(); ++b) {
@@ -224,6 +266,19 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
         P.blk_entry[b] = entry_of(Lc, hp - P.p_begin, entry_k(G, hp, S.blk_entry[b]));
       }
     }
+  }
+  };
+  if (threaded) {
+    std::thread t1(build_pp_edges), t2(build_incidence), t3(build_export);
+    build_pl_edges();
+    t1.join();
+    t2.join();
+    t3.join();
+  } else {
+    build_pp_edges();
+    build_pl_edges();
+    build_incidence();
+    build_export();
   }
   return SGB_OK;
 }

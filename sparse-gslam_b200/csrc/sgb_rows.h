@@ -351,22 +351,45 @@ SGB_HD bool setup_pose_row(const DevGraph& g, int lp, double lambda) {
 
 // ---------------------------------------------------------------------------------------------------------
 // implicit Schur-complement operator  q = (Hpp + lambda I) v - Hpl (Hll + lambda I)^-1 Hpl^T v
+//
+// The SELL row loops below are software-pipelined by hand: the column indices of the NEXT pair of blocks are
+// loaded before the current pair is consumed, and the (independent) value / gather loads of two blocks are issued
+// together, so that one thread keeps ~2 x 12 loads in flight instead of serialising "index -> gather -> FMA" per
+// block. Padding entries (col < 0) sit at the end of a row and contribute exact zeros; the order of the additions
+// is the plain k = 0, 1, 2, ... order, so results do not depend on the unrolling.
+SGB_HD int sell_col_or_pad(const int32_t* col, int e, bool valid) { return valid ? SGB_LDG(&col[e]) : -1; }
+
 // phase A (landmark-major): t_l = (Hll_l + lambda I)^-1 * sum_i Hpl_il^T v_i       row = local Hlp row
 // vtab[o] = pose-vector segment of rank o (p during PCG, x_p during back-substitution)
 SGB_HD void lm_gather_row(const DevGraph& g, int row, double* const* vtab, double* u0_out, double* u1_out) {
-  int slice = row >> 5, lane = row & 31;
-  int w = sell_width(g.Hlp, slice);
-  int base = g.Hlp.sbase[slice];
+  const int slice = row >> 5, lane = row & 31;
+  const int w = sell_width(g.Hlp, slice);
+  const int base = g.Hlp.sbase[slice] + lane;
+  const int32_t* col = g.Hlp.col;
   double u0 = 0, u1 = 0;
-  for (int k = 0; k < w; ++k) {
-    int e = base + k * 32 + lane;
-    int enc = SGB_LDG(&g.Hlp.col[e]);
-    if (enc < 0) continue;
-    const double* v = vtab[enc >> kOwnerShift] + 3 * (size_t)(enc & kLocalMask);
-    double v0 = SGB_LDCG(v), v1 = SGB_LDCG(v + 1), v2 = SGB_LDCG(v + 2);
-    const double* a = g.Hlp.vals + sell_vaddr(e, 6, 0);
-    u0 += SGB_LDG(a) * v0 + SGB_LDG(a + 64) * v1 + SGB_LDG(a + 128) * v2;
-    u1 += SGB_LDG(a + 32) * v0 + SGB_LDG(a + 96) * v1 + SGB_LDG(a + 160) * v2;
+  int enc0 = sell_col_or_pad(col, base, w > 0), enc1 = sell_col_or_pad(col, base + 32, w > 1);
+  for (int k = 0; k < w; k += 2) {
+    const int e0 = base + k * 32, e1 = e0 + 32;
+    const int n0 = sell_col_or_pad(col, e0 + 64, k + 2 < w), n1 = sell_col_or_pad(col, e1 + 64, k + 3 < w);
+    double v[2][3] = {{0, 0, 0}, {0, 0, 0}}, a[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    if (enc0 >= 0) {
+      const double* pv = vtab[enc0 >> kOwnerShift] + 3 * (size_t)(enc0 & kLocalMask);
+      const double* pa = g.Hlp.vals + sell_vaddr(e0, 6, 0);
+      for (int c = 0; c < 3; ++c) v[0][c] = SGB_LDCG(pv + c);
+      for (int c = 0; c < 6; ++c) a[0][c] = SGB_LDG(pa + 32 * c);
+    }
+    if (enc1 >= 0) {
+      const double* pv = vtab[enc1 >> kOwnerShift] + 3 * (size_t)(enc1 & kLocalMask);
+      const double* pa = g.Hlp.vals + sell_vaddr(e1, 6, 0);
+      for (int c = 0; c < 3; ++c) v[1][c] = SGB_LDCG(pv + c);
+      for (int c = 0; c < 6; ++c) a[1][c] = SGB_LDG(pa + 32 * c);
+    }
+    for (int u = 0; u < 2; ++u) {
+      u0 += a[u][0] * v[u][0] + a[u][2] * v[u][1] + a[u][4] * v[u][2];
+      u1 += a[u][1] * v[u][0] + a[u][3] * v[u][1] + a[u][5] * v[u][2];
+    }
+    enc0 = n0;
+    enc1 = n1;
   }
   *u0_out = u0;
   *u1_out = u1;
@@ -383,39 +406,67 @@ SGB_HD void schur_phaseA_row(const DevGraph& g, int row) {
 }
 // phase B (pose-major): q_i = lambda v_i + sum_j Hpp_ij v_j - sum_l Hpl_il t_l ; returns v_i . q_i  (v = p)
 SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda) {
-  int slice = lp >> 5, lane = lp & 31;
+  const int slice = lp >> 5, lane = lp & 31;
   const double* vown = g.p[g.rank] + 3 * (size_t)lp;
+  const int wpp = sell_width(g.Hpp, slice), bpp = g.Hpp.sbase[slice] + lane;
+  const bool has_pl = g.Hpl.rows > 0;
+  const int wpl = has_pl ? sell_width(g.Hpl, slice) : 0, bpl = has_pl ? g.Hpl.sbase[slice] + lane : 0;
+  const int32_t* cpp = g.Hpp.col;
+  const int32_t* cpl = g.Hpl.col;
+  int enc0 = sell_col_or_pad(cpp, bpp, wpp > 0), enc1 = sell_col_or_pad(cpp, bpp + 32, wpp > 1);
+  int l0 = sell_col_or_pad(cpl, bpl, wpl > 0), l1 = sell_col_or_pad(cpl, bpl + 32, wpl > 1);  // issued early
   double vi0 = SGB_LDCG(vown), vi1 = SGB_LDCG(vown + 1), vi2 = SGB_LDCG(vown + 2);
   double q0 = lambda * vi0, q1 = lambda * vi1, q2 = lambda * vi2;
-  {
-    int w = sell_width(g.Hpp, slice);
-    int base = g.Hpp.sbase[slice];
-    for (int k = 0; k < w; ++k) {
-      int e = base + k * 32 + lane;
-      int enc = SGB_LDG(&g.Hpp.col[e]);
-      if (enc < 0) continue;
-      const double* v = g.p[enc >> kOwnerShift] + 3 * (size_t)(enc & kLocalMask);
-      double v0 = SGB_LDCG(v), v1 = SGB_LDCG(v + 1), v2 = SGB_LDCG(v + 2);
-      const double* a = g.Hpp.vals + sell_vaddr(e, 9, 0);
-      q0 += SGB_LDG(a) * v0 + SGB_LDG(a + 32) * v1 + SGB_LDG(a + 64) * v2;
-      q1 += SGB_LDG(a + 96) * v0 + SGB_LDG(a + 128) * v1 + SGB_LDG(a + 160) * v2;
-      q2 += SGB_LDG(a + 192) * v0 + SGB_LDG(a + 224) * v1 + SGB_LDG(a + 256) * v2;
+  for (int k = 0; k < wpp; k += 2) {
+    const int e0 = bpp + k * 32, e1 = e0 + 32;
+    const int n0 = sell_col_or_pad(cpp, e0 + 64, k + 2 < wpp), n1 = sell_col_or_pad(cpp, e1 + 64, k + 3 < wpp);
+    double v[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    double a[2][9] = {{0, 0, 0, 0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0, 0, 0, 0}};
+    if (enc0 >= 0) {
+      const double* pv = g.p[enc0 >> kOwnerShift] + 3 * (size_t)(enc0 & kLocalMask);
+      const double* pa = g.Hpp.vals + sell_vaddr(e0, 9, 0);
+      for (int c = 0; c < 3; ++c) v[0][c] = SGB_LDCG(pv + c);
+      for (int c = 0; c < 9; ++c) a[0][c] = SGB_LDG(pa + 32 * c);
     }
+    if (enc1 >= 0) {
+      const double* pv = g.p[enc1 >> kOwnerShift] + 3 * (size_t)(enc1 & kLocalMask);
+      const double* pa = g.Hpp.vals + sell_vaddr(e1, 9, 0);
+      for (int c = 0; c < 3; ++c) v[1][c] = SGB_LDCG(pv + c);
+      for (int c = 0; c < 9; ++c) a[1][c] = SGB_LDG(pa + 32 * c);
+    }
+    for (int u = 0; u < 2; ++u) {
+      q0 += a[u][0] * v[u][0] + a[u][1] * v[u][1] + a[u][2] * v[u][2];
+      q1 += a[u][3] * v[u][0] + a[u][4] * v[u][1] + a[u][5] * v[u][2];
+      q2 += a[u][6] * v[u][0] + a[u][7] * v[u][1] + a[u][8] * v[u][2];
+    }
+    enc0 = n0;
+    enc1 = n1;
   }
-  if (g.Hpl.rows > 0) {
-    int w = sell_width(g.Hpl, slice);
-    int base = g.Hpl.sbase[slice];
-    for (int k = 0; k < w; ++k) {
-      int e = base + k * 32 + lane;
-      int enc = SGB_LDG(&g.Hpl.col[e]);
-      if (enc < 0) continue;
-      const double* tt = g.t[enc >> kOwnerShift] + 2 * (size_t)(enc & kLocalMask);
-      double t0 = SGB_LDCG(tt), t1 = SGB_LDCG(tt + 1);
-      const double* a = g.Hpl.vals + sell_vaddr(e, 6, 0);
-      q0 -= SGB_LDG(a) * t0 + SGB_LDG(a + 32) * t1;
-      q1 -= SGB_LDG(a + 64) * t0 + SGB_LDG(a + 96) * t1;
-      q2 -= SGB_LDG(a + 128) * t0 + SGB_LDG(a + 160) * t1;
+  for (int k = 0; k < wpl; k += 2) {
+    const int e0 = bpl + k * 32, e1 = e0 + 32;
+    const int n0 = sell_col_or_pad(cpl, e0 + 64, k + 2 < wpl), n1 = sell_col_or_pad(cpl, e1 + 64, k + 3 < wpl);
+    double tv[2][2] = {{0, 0}, {0, 0}}, a[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
+    if (l0 >= 0) {
+      const double* pt = g.t[l0 >> kOwnerShift] + 2 * (size_t)(l0 & kLocalMask);
+      const double* pa = g.Hpl.vals + sell_vaddr(e0, 6, 0);
+      tv[0][0] = SGB_LDCG(pt);
+      tv[0][1] = SGB_LDCG(pt + 1);
+      for (int c = 0; c < 6; ++c) a[0][c] = SGB_LDG(pa + 32 * c);
     }
+    if (l1 >= 0) {
+      const double* pt = g.t[l1 >> kOwnerShift] + 2 * (size_t)(l1 & kLocalMask);
+      const double* pa = g.Hpl.vals + sell_vaddr(e1, 6, 0);
+      tv[1][0] = SGB_LDCG(pt);
+      tv[1][1] = SGB_LDCG(pt + 1);
+      for (int c = 0; c < 6; ++c) a[1][c] = SGB_LDG(pa + 32 * c);
+    }
+    for (int u = 0; u < 2; ++u) {
+      q0 -= a[u][0] * tv[u][0] + a[u][1] * tv[u][1];
+      q1 -= a[u][2] * tv[u][0] + a[u][3] * tv[u][1];
+      q2 -= a[u][4] * tv[u][0] + a[u][5] * tv[u][1];
+    }
+    l0 = n0;
+    l1 = n1;
   }
   g.q[3 * (size_t)lp] = q0;
   g.q[3 * (size_t)lp + 1] = q1;

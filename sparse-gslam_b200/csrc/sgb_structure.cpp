@@ -1,42 +1,25 @@
 // sgb_structure.cpp -- see sgb_structure.h. Host-only, no CUDA.
+//
+// The whole symbolic phase is linear time: vertex pairs are grouped with counting sorts (bucket by the smaller
+// Hessian index, tiny in-bucket sorts), row lists are filled in an order that leaves them sorted, and every
+// scatter-map entry is known at fill time (no searches). The pose-pose part, the pose-line part and the
+// incidence lists are independent and run on three host threads. A 1M-pose / 5.5M-edge graph takes ~0.2 s.
 #include "sgb_structure.h"
 
 #include <algorithm>
 #include <numeric>
+#include <thread>
 
 namespace sgb {
 
 namespace {
 
-struct ERef {
-  int64_t seq;
-  int32_t type;  // 0 pose-pose, 1 pose-line
-  int32_t idx;   // index in the caller's arrays
-};
-
-// rows -> sorted unique column lists -> SELL-32 with per-row entry lookup
+// CSR row lists, columns ascending
 struct RowLists {
-  std::vector<int32_t> ptr, col;  // CSR, columns ascending
-  int find(int r, int c) const {
-    auto b = col.begin() + ptr[r], e = col.begin() + ptr[r + 1];
-    auto it = std::lower_bound(b, e, c);
-    return (it != e && *it == c) ? (int)(it - b) : -1;
-  }
+  std::vector<int32_t> ptr, col;
 };
 
-RowLists make_rows(int rows, std::vector<std::pair<int32_t, int32_t>>& rc) {
-  std::sort(rc.begin(), rc.end());
-  rc.erase(std::unique(rc.begin(), rc.end()), rc.end());
-  RowLists L;
-  L.ptr.assign(rows + 1, 0);
-  for (auto& p : rc) L.ptr[p.first + 1]++;
-  for (int r = 0; r < rows; ++r) L.ptr[r + 1] += L.ptr[r];
-  L.col.resize(rc.size());
-  for (size_t k = 0; k < rc.size(); ++k) L.col[k] = rc[k].second;  // already grouped by row, ascending
-  return L;
-}
-
-// SELL from row lists; row_of_sell[r] gives the logical row stored at SELL row r (identity when empty)
+// SELL from row lists; row_of_sell[r] gives the logical row stored at SELL row r (identity when null)
 void make_sell(const RowLists& L, int rows, const std::vector<int32_t>* row_of_sell, HostSell& S) {
   S.rows = rows;
   S.nslices = (rows + 31) / 32;
@@ -55,11 +38,61 @@ void make_sell(const RowLists& L, int rows, const std::vector<int32_t>* row_of_s
   for (int r = 0; r < rows; ++r) {
     int lr = row_of_sell ? (*row_of_sell)[r] : r;
     int s = r >> 5, lane = r & 31;
-    for (int k = 0; k < L.ptr[lr + 1] - L.ptr[lr]; ++k) S.col[(size_t)S.sbase[s] + k * 32 + lane] = L.col[L.ptr[lr] + k];
+    int32_t* dst = S.col.data() + (size_t)S.sbase[s] + lane;
+    const int32_t* src = L.col.data() + L.ptr[lr];
+    for (int k = 0, n = L.ptr[lr + 1] - L.ptr[lr]; k < n; ++k) dst[(size_t)k * 32] = src[k];
   }
 }
 
 inline int sell_entry(const HostSell& S, int sell_row, int k) { return S.sbase[sell_row >> 5] + k * 32 + (sell_row & 31); }
+
+// Vertex pairs (a, b) of the edges 0..n-1 (a = bucket key in [0, nbuckets), either < 0: skipped), grouped so that equal
+// pairs are adjacent and ordered by (a, b, edge index). O(n + nbuckets) plus tiny in-bucket sorts.
+struct PairItem {
+  int32_t b, k;
+};
+struct Grouped {
+  std::vector<int32_t> start;  // [nbuckets + 1]
+  std::vector<PairItem> items;
+};
+template <class KeyA, class KeyB>
+void group_pairs(int n, int nbuckets, KeyA key_a, KeyB key_b, Grouped& G) {
+  G.start.assign((size_t)nbuckets + 1, 0);
+  for (int k = 0; k < n; ++k) {
+    int a = key_a(k);
+    if (a >= 0 && key_b(k) >= 0) G.start[a + 1]++;
+  }
+  for (int a = 0; a < nbuckets; ++a) G.start[a + 1] += G.start[a];
+  G.items.resize((size_t)G.start[nbuckets]);
+  std::vector<int32_t> pos(G.start.begin(), G.start.end() - 1);
+  for (int k = 0; k < n; ++k) {
+    int a = key_a(k), b = key_b(k);
+    if (a >= 0 && b >= 0) G.items[(size_t)pos[a]++] = {b, k};
+  }
+  for (int a = 0; a < nbuckets; ++a) {
+    PairItem* lo = G.items.data() + G.start[a];
+    int m = G.start[a + 1] - G.start[a];
+    if (m <= 1) continue;
+    if (m <= 24) {  // stable insertion sort by b (k is already ascending inside a bucket)
+      for (int i = 1; i < m; ++i) {
+        PairItem v = lo[i];
+        int j = i - 1;
+        while (j >= 0 && lo[j].b > v.b) { lo[j + 1] = lo[j]; --j; }
+        lo[j + 1] = v;
+      }
+    } else {
+      std::stable_sort(lo, lo + m, [](const PairItem& x, const PairItem& y) { return x.b < y.b; });
+    }
+  }
+}
+
+// order of the active edges of one type: caller indices sorted by (seq, index); identity when seq is absent or sorted
+void order_by_seq(std::vector<int32_t>& idx, const int64_t* seq) {
+  if (!seq) return;
+  bool sorted = true;
+  for (size_t t = 1; t < idx.size() && sorted; ++t) sorted = seq[idx[t - 1]] <= seq[idx[t]];
+  if (!sorted) std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return seq[a] < seq[b]; });
+}
 
 }  // namespace
 
@@ -81,16 +114,17 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   auto lid = [&](int i) { return g.lm_id ? g.lm_id[i] : 10000000 + i; };
 
   if (g.n_pp + g.n_pl == 0) { err = "Attempt to initialize an empty graph"; return SGB_ERR_NOT_INITIALIZED; }
+  if (g.n_pp >= (1 << 29) || g.n_pl >= (1 << 29)) { err = "too many edges for the packed incidence encoding"; return SGB_ERR_UNSUPPORTED; }
 
-  // ---- active edges (level 0, all vertices in the set, not all fixed), sorted by internal id
-  std::vector<ERef> act;
-  act.reserve((size_t)g.n_pp + g.n_pl);
+  // ---- active edges (level 0, all vertices in the set, not all fixed), sorted by internal id within each type
   std::vector<char> pact(P, 0), lact(L, 0);
+  S.pp_src.reserve(g.n_pp);
+  S.pl_src.reserve(g.n_pl);
   for (int k = 0; k < g.n_pp; ++k) {
     int i = g.pp_i[k], j = g.pp_j[k];
     if (i < 0 || i >= P || j < 0 || j >= P || i == j) { err = "pose-pose edge with a bad vertex index"; return SGB_ERR_INVALID; }
     if (pfixed(i) && pfixed(j)) continue;
-    act.push_back({g.pp_seq ? g.pp_seq[k] : (int64_t)k, 0, k});
+    S.pp_src.push_back(k);
     pact[i] = pact[j] = 1;
     if (g.pp_phi && g.pp_phi[k] > 0.0) S.has_robust = true;
   }
@@ -98,22 +132,27 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     int p = g.pl_pose[k], l = g.pl_lm[k];
     if (p < 0 || p >= P || l < 0 || l >= L) { err = "pose-line edge with a bad vertex index"; return SGB_ERR_INVALID; }
     if (pfixed(p) && lfixed(l)) continue;
-    act.push_back({g.pl_seq ? g.pl_seq[k] : (int64_t)g.n_pp + k, 1, k});
+    S.pl_src.push_back(k);
     pact[p] = 1;
     lact[l] = 1;
   }
-  std::stable_sort(act.begin(), act.end(), [](const ERef& a, const ERef& b) {
-    if (a.seq != b.seq) return a.seq < b.seq;
-    if (a.type != b.type) return a.type < b.type;
-    return a.idx < b.idx;
-  });
+  order_by_seq(S.pp_src, g.pp_seq);
+  order_by_seq(S.pl_src, g.pl_seq);
+  S.n_pp = (int)S.pp_src.size();
+  S.n_pl = (int)S.pl_src.size();
+  // global insertion rank of an active edge (ties: pose-pose first, then caller index -- both orders are stable)
+  auto seq_pp = [&](int k) { return g.pp_seq ? g.pp_seq[S.pp_src[k]] : (int64_t)S.pp_src[k]; };
+  auto seq_pl = [&](int k) { return g.pl_seq ? g.pl_seq[S.pl_src[k]] : (int64_t)g.n_pp + S.pl_src[k]; };
 
   // ---- index mapping: active vertices sorted by id; fixed -> -1; nothing is marginalised
-  std::vector<int32_t> porder, lorder;
+  std::vector<int32_t>& porder = S.pose_of_h;
+  std::vector<int32_t>& lorder = S.lm_of_h;
   for (int i = 0; i < P; ++i) if (pact[i] && !pfixed(i)) porder.push_back(i);
   for (int i = 0; i < L; ++i) if (lact[i] && !lfixed(i)) lorder.push_back(i);
-  std::stable_sort(porder.begin(), porder.end(), [&](int a, int b) { return pid(a) < pid(b); });
-  std::stable_sort(lorder.begin(), lorder.end(), [&](int a, int b) { return lid(a) < lid(b); });
+  if (g.pose_id && !std::is_sorted(porder.begin(), porder.end(), [&](int a, int b) { return pid(a) < pid(b); }))
+    std::stable_sort(porder.begin(), porder.end(), [&](int a, int b) { return pid(a) < pid(b); });
+  if (g.lm_id && !std::is_sorted(lorder.begin(), lorder.end(), [&](int a, int b) { return lid(a) < lid(b); }))
+    std::stable_sort(lorder.begin(), lorder.end(), [&](int a, int b) { return lid(a) < lid(b); });
   if (!porder.empty() && !lorder.empty() && pid(porder.back()) >= lid(lorder.front())) {
     err = "unsupported vertex ordering: every pose id must be smaller than every landmark id (reference: drone.h:22)";
     return SGB_ERR_UNSUPPORTED;
@@ -123,8 +162,6 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   if (S.Pf + S.Lf == 0) { err = "0 vertices to optimize"; return SGB_ERR_NOT_INITIALIZED; }
   S.pose_h.assign(P, -1);
   S.lm_h.assign(L, -1);
-  S.pose_of_h = porder;
-  S.lm_of_h = lorder;
   for (int h = 0; h < S.Pf; ++h) S.pose_h[porder[h]] = h;
   for (int h = 0; h < S.Lf; ++h) S.lm_h[lorder[h]] = h;
   S.dim = 3 * S.Pf + 2 * S.Lf;
@@ -136,9 +173,6 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   for (int h = 0; h < S.Lf; ++h) { S.ord_kind[S.Pf + h] = 1; S.ord_index[S.Pf + h] = lorder[h]; S.ord_offset[S.Pf + h] = 3 * S.Pf + 2 * h; }
 
   // ---- per-type active edge arrays (insertion order)
-  for (auto& e : act) (e.type == 0 ? S.pp_src : S.pl_src).push_back(e.idx);
-  S.n_pp = (int)S.pp_src.size();
-  S.n_pl = (int)S.pl_src.size();
   S.pp_i.resize(S.n_pp); S.pp_j.resize(S.n_pp); S.pp_hi.resize(S.n_pp); S.pp_hj.resize(S.n_pp);
   S.pp_e_ij.assign(S.n_pp, -1); S.pp_e_ji.assign(S.n_pp, -1); S.pp_dup.assign(S.n_pp, -1);
   for (int k = 0; k < S.n_pp; ++k) {
@@ -154,8 +188,8 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     S.pl_hp[k] = S.pose_h[g.pl_pose[s]]; S.pl_hl[k] = S.lm_h[g.pl_lm[s]];
   }
 
-  // ---- incidence lists in global insertion order
-  {
+  // ---- incidence lists in global insertion order (two-way merge of the two edge types)
+  auto build_incidence = [&]() {
     S.pinc_ptr.assign(S.Pf + 1, 0);
     S.linc_ptr.assign(S.Lf + 1, 0);
     for (int k = 0; k < S.n_pp; ++k) {
@@ -172,8 +206,9 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     S.linc.resize(S.linc_ptr[S.Lf]);
     std::vector<int32_t> pp_pos(S.pinc_ptr.begin(), S.pinc_ptr.end() - 1), lp_pos(S.linc_ptr.begin(), S.linc_ptr.end() - 1);
     int kpp = 0, kpl = 0;
-    for (auto& e : act) {  // merged walk keeps the cross-type insertion order
-      if (e.type == 0) {
+    while (kpp < S.n_pp || kpl < S.n_pl) {
+      bool take_pp = kpl >= S.n_pl || (kpp < S.n_pp && seq_pp(kpp) <= seq_pl(kpl));
+      if (take_pp) {
         int k = kpp++;
         if (S.pp_hi[k] >= 0) S.pinc[pp_pos[S.pp_hi[k]]++] = (k << 2) | (0 << 1) | 0;
         if (S.pp_hj[k] >= 0) S.pinc[pp_pos[S.pp_hj[k]]++] = (k << 2) | (1 << 1) | 0;
@@ -183,114 +218,168 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
         if (S.pl_hl[k] >= 0) S.linc[lp_pos[S.pl_hl[k]]++] = k;
       }
     }
-  }
-  if (S.n_pp >= (1 << 29) || S.n_pl >= (1 << 29)) { err = "too many edges for the packed incidence encoding"; return SGB_ERR_UNSUPPORTED; }
+  };
 
-  // ---- pose-pose pairs: leader = first edge (insertion order) of an unordered free pair, others chained
-  std::vector<std::pair<int32_t, int32_t>> rc;
-  {
-    std::vector<std::pair<uint64_t, int32_t>> keyed;
-    for (int k = 0; k < S.n_pp; ++k) {
-      int a = S.pp_hi[k], b = S.pp_hj[k];
-      if (a < 0 || b < 0) continue;
-      uint64_t key = ((uint64_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b);
-      keyed.push_back({key, k});
-    }
-    std::stable_sort(keyed.begin(), keyed.end());  // ties keep insertion order (k ascending = seq ascending)
-    rc.reserve(2 * keyed.size() + S.Pf);
-    for (int h = 0; h < S.Pf; ++h) rc.push_back({h, h});
-    for (size_t t = 0; t < keyed.size(); ++t) {
-      bool leader = (t == 0) || keyed[t].first != keyed[t - 1].first;
-      if (leader) {
-        int a = (int)(keyed[t].first >> 32), b = (int)(keyed[t].first & 0xffffffffu);
-        rc.push_back({a, b});
-        rc.push_back({b, a});
-        S.n_pairs_pp++;
-      } else {
-        S.pp_dup[keyed[t - 1].second] = keyed[t].second;
+  // ---- pose-pose pairs: leader = first edge (insertion order) of an unordered free pair, others chained.
+  // Row r of Hpp = [cols < r ascending | r | cols > r ascending]; positions are known when they are filled.
+  std::vector<int32_t> bp_row, bp_col, bp_entry;  // reference block list, pose columns
+  auto build_pp = [&]() {
+    Grouped G;
+    group_pairs(S.n_pp, S.Pf, [&](int k) { int a = S.pp_hi[k], b = S.pp_hj[k]; return (a < 0 || b < 0) ? -1 : std::min(a, b); },
+                [&](int k) { return std::max(S.pp_hi[k], S.pp_hj[k]); }, G);
+    // leaders -> distinct pairs t = 0.. in (a, b) order
+    std::vector<int32_t> pa, pb, pk;
+    pa.reserve(G.items.size()); pb.reserve(G.items.size()); pk.reserve(G.items.size());
+    std::vector<int32_t> lc(S.Pf, 0), uc(S.Pf, 0);
+    for (int a = 0; a < S.Pf; ++a)
+      for (int q = G.start[a]; q < G.start[a + 1]; ++q) {
+        if (q > G.start[a] && G.items[q].b == G.items[q - 1].b) {
+          S.pp_dup[G.items[q - 1].k] = G.items[q].k;
+          continue;
+        }
+        pa.push_back(a); pb.push_back(G.items[q].b); pk.push_back(G.items[q].k);
+        uc[a]++; lc[G.items[q].b]++;
       }
+    const int np = (int)pa.size();
+    S.n_pairs_pp = np;
+    RowLists rows;
+    rows.ptr.assign(S.Pf + 1, 0);
+    for (int r = 0; r < S.Pf; ++r) rows.ptr[r + 1] = rows.ptr[r] + lc[r] + 1 + uc[r];
+    rows.col.resize(rows.ptr[S.Pf]);
+    std::vector<int32_t> lstart(S.Pf + 1, 0);
+    for (int r = 0; r < S.Pf; ++r) lstart[r + 1] = lstart[r] + lc[r];
+    std::vector<int32_t> low_pair(np), up_idx(np), low_idx(np), lpos(S.Pf, 0), upos(S.Pf, 0);
+    for (int r = 0; r < S.Pf; ++r) rows.col[rows.ptr[r] + lc[r]] = r;
+    for (int t = 0; t < np; ++t) {
+      int a = pa[t], b = pb[t];
+      low_idx[t] = lpos[b];
+      low_pair[lstart[b] + lpos[b]] = t;
+      rows.col[rows.ptr[b] + lpos[b]++] = a;
+      up_idx[t] = lc[a] + 1 + upos[a];
+      rows.col[rows.ptr[a] + lc[a] + 1 + upos[a]++] = b;
     }
-    RowLists rows = make_rows(S.Pf, rc);
     make_sell(rows, S.Pf, nullptr, S.Hpp);
     S.hpp_diag.resize(S.Pf);
-    for (int h = 0; h < S.Pf; ++h) S.hpp_diag[h] = sell_entry(S.Hpp, h, rows.find(h, h));
-    for (size_t t = 0; t < keyed.size(); ++t) {
-      bool leader = (t == 0) || keyed[t].first != keyed[t - 1].first;
-      if (!leader) continue;
-      int k = keyed[t].second;
-      int a = S.pp_hi[k], b = S.pp_hj[k];
-      S.pp_e_ij[k] = sell_entry(S.Hpp, a, rows.find(a, b));
-      S.pp_e_ji[k] = sell_entry(S.Hpp, b, rows.find(b, a));
+    for (int h = 0; h < S.Pf; ++h) S.hpp_diag[h] = sell_entry(S.Hpp, h, lc[h]);
+    for (int t = 0; t < np; ++t) {
+      int k = pk[t];
+      int e_up = sell_entry(S.Hpp, pa[t], up_idx[t]);    // block (row a, col b), a < b
+      int e_low = sell_entry(S.Hpp, pb[t], low_idx[t]);  // block (row b, col a)
+      bool fwd = S.pp_hi[k] == pa[t];
+      S.pp_e_ij[k] = fwd ? e_up : e_low;
+      S.pp_e_ji[k] = fwd ? e_low : e_up;
     }
-    // reference block list, pose columns
+    // reference block list, pose columns: column c holds rows r <= c ascending; block (r, c) lives in SELL row r
+    bp_row.resize((size_t)np + S.Pf); bp_col.resize(bp_row.size()); bp_entry.resize(bp_row.size());
+    size_t o = 0;
     for (int c = 0; c < S.Pf; ++c) {
-      for (int q = rows.ptr[c]; q < rows.ptr[c + 1]; ++q) {
-        int r = rows.col[q];  // symmetric pattern: the rows of column c are the columns of row c
-        if (r > c) break;
-        S.blk_row.push_back(r); S.blk_col.push_back(c); S.blk_nr.push_back(3); S.blk_nc.push_back(3);
-        S.blk_kind.push_back(0);
-        // values of block (row r, col c) live in row r's SELL row
-        S.blk_entry.push_back(sell_entry(S.Hpp, r, rows.find(r, c)));
+      for (int q = lstart[c]; q < lstart[c + 1]; ++q) {
+        int t = low_pair[q];
+        bp_row[o] = pa[t]; bp_col[o] = c; bp_entry[o] = sell_entry(S.Hpp, pa[t], up_idx[t]);
+        ++o;
       }
+      bp_row[o] = c; bp_col[o] = c; bp_entry[o] = S.hpp_diag[c];
+      ++o;
     }
-  }
+  };
+
   // ---- pose-line pairs
-  {
-    std::vector<std::pair<uint64_t, int32_t>> keyed;
-    for (int k = 0; k < S.n_pl; ++k) {
-      int a = S.pl_hp[k], b = S.pl_hl[k];
-      if (a < 0 || b < 0) continue;
-      keyed.push_back({((uint64_t)a << 32) | (uint32_t)b, k});
-    }
-    std::stable_sort(keyed.begin(), keyed.end());
-    std::vector<std::pair<int32_t, int32_t>> rc_pl, rc_lp;
-    for (size_t t = 0; t < keyed.size(); ++t) {
-      bool leader = (t == 0) || keyed[t].first != keyed[t - 1].first;
-      if (leader) {
-        int a = (int)(keyed[t].first >> 32), b = (int)(keyed[t].first & 0xffffffffu);
-        rc_pl.push_back({a, b});
-        rc_lp.push_back({b, a});
-        S.n_pairs_pl++;
-      } else {
-        S.pl_dup[keyed[t - 1].second] = keyed[t].second;
+  std::vector<int32_t> bl_row, bl_col, bl_nr, bl_kind, bl_entry;  // reference block list, landmark columns
+  auto build_pl = [&]() {
+    Grouped G;
+    group_pairs(S.n_pl, S.Pf, [&](int k) { return S.pl_hp[k]; }, [&](int k) { return S.pl_hl[k]; }, G);
+    std::vector<int32_t> pa, pb, pk;
+    pa.reserve(G.items.size()); pb.reserve(G.items.size()); pk.reserve(G.items.size());
+    RowLists rows_pl, rows_lp;
+    rows_pl.ptr.assign(S.Pf + 1, 0);
+    rows_lp.ptr.assign(S.Lf + 1, 0);
+    for (int a = 0; a < S.Pf; ++a)
+      for (int q = G.start[a]; q < G.start[a + 1]; ++q) {
+        if (q > G.start[a] && G.items[q].b == G.items[q - 1].b) {
+          S.pl_dup[G.items[q - 1].k] = G.items[q].k;
+          continue;
+        }
+        pa.push_back(a); pb.push_back(G.items[q].b); pk.push_back(G.items[q].k);
+        rows_pl.ptr[a + 1]++; rows_lp.ptr[G.items[q].b + 1]++;
       }
+    const int np = (int)pa.size();
+    S.n_pairs_pl = np;
+    for (int r = 0; r < S.Pf; ++r) rows_pl.ptr[r + 1] += rows_pl.ptr[r];
+    for (int r = 0; r < S.Lf; ++r) rows_lp.ptr[r + 1] += rows_lp.ptr[r];
+    rows_pl.col.resize(np);
+    rows_lp.col.resize(np);
+    std::vector<int32_t> idx_pl(np), idx_lp(np), lp_pair(np), pos_pl(S.Pf, 0), pos_lp(S.Lf, 0);
+    for (int t = 0; t < np; ++t) {  // pairs ascend by (pose, landmark): both row lists come out sorted
+      int a = pa[t], b = pb[t];
+      idx_pl[t] = pos_pl[a];
+      rows_pl.col[rows_pl.ptr[a] + pos_pl[a]++] = b;
+      idx_lp[t] = pos_lp[b];
+      lp_pair[rows_lp.ptr[b] + pos_lp[b]] = t;
+      rows_lp.col[rows_lp.ptr[b] + pos_lp[b]++] = a;
     }
-    RowLists rows_pl = make_rows(S.Pf, rc_pl);
-    RowLists rows_lp = make_rows(S.Lf, rc_lp);
     make_sell(rows_pl, S.Pf, nullptr, S.Hpl);
-    // landmark rows sorted by descending observer count so that a 32-row slice pads little
+    // landmark rows sorted by descending observer count (stable) so that a 32-row slice pads little
     S.lp_row2h.resize(S.Lf);
-    std::iota(S.lp_row2h.begin(), S.lp_row2h.end(), 0);
-    std::stable_sort(S.lp_row2h.begin(), S.lp_row2h.end(), [&](int a, int b) {
-      return rows_lp.ptr[a + 1] - rows_lp.ptr[a] > rows_lp.ptr[b + 1] - rows_lp.ptr[b];
-    });
+    {
+      int maxc = 0;
+      for (int l = 0; l < S.Lf; ++l) maxc = std::max(maxc, rows_lp.ptr[l + 1] - rows_lp.ptr[l]);
+      std::vector<int32_t> bstart((size_t)maxc + 2, 0);
+      for (int l = 0; l < S.Lf; ++l) bstart[(size_t)(maxc - (rows_lp.ptr[l + 1] - rows_lp.ptr[l])) + 1]++;
+      for (int c = 0; c <= maxc; ++c) bstart[c + 1] += bstart[c];
+      for (int l = 0; l < S.Lf; ++l) S.lp_row2h[bstart[maxc - (rows_lp.ptr[l + 1] - rows_lp.ptr[l])]++] = l;
+    }
     S.lp_h2row.assign(S.Lf, 0);
     for (int r = 0; r < S.Lf; ++r) S.lp_h2row[S.lp_row2h[r]] = r;
     make_sell(rows_lp, S.Lf, &S.lp_row2h, S.Hlp);
-    for (size_t t = 0; t < keyed.size(); ++t) {
-      bool leader = (t == 0) || keyed[t].first != keyed[t - 1].first;
-      if (!leader) continue;
-      int k = keyed[t].second;
-      int a = S.pl_hp[k], b = S.pl_hl[k];
-      S.pl_e_pl[k] = sell_entry(S.Hpl, a, rows_pl.find(a, b));
-      S.pl_e_lp[k] = sell_entry(S.Hlp, S.lp_h2row[b], rows_lp.find(b, a));
+    for (int t = 0; t < np; ++t) {
+      int k = pk[t];
+      S.pl_e_pl[k] = sell_entry(S.Hpl, pa[t], idx_pl[t]);
+      S.pl_e_lp[k] = sell_entry(S.Hlp, S.lp_h2row[pb[t]], idx_lp[t]);
     }
     // reference block list, landmark columns: pose rows ascending, then the diagonal
+    size_t nb = (size_t)np + S.Lf, o = 0;
+    bl_row.resize(nb); bl_col.resize(nb); bl_nr.resize(nb); bl_kind.resize(nb); bl_entry.resize(nb);
     for (int hl = 0; hl < S.Lf; ++hl) {
       int c = S.Pf + hl;
       for (int q = rows_lp.ptr[hl]; q < rows_lp.ptr[hl + 1]; ++q) {
-        int r = rows_lp.col[q];
-        S.blk_row.push_back(r); S.blk_col.push_back(c); S.blk_nr.push_back(3); S.blk_nc.push_back(2);
-        S.blk_kind.push_back(1);
-        S.blk_entry.push_back(sell_entry(S.Hpl, r, rows_pl.find(r, hl)));
+        int t = lp_pair[q];
+        bl_row[o] = pa[t]; bl_col[o] = c; bl_nr[o] = 3; bl_kind[o] = 1; bl_entry[o] = sell_entry(S.Hpl, pa[t], idx_pl[t]);
+        ++o;
       }
-      S.blk_row.push_back(c); S.blk_col.push_back(c); S.blk_nr.push_back(2); S.blk_nc.push_back(2);
-      S.blk_kind.push_back(2);
-      S.blk_entry.push_back(hl);
+      bl_row[o] = c; bl_col[o] = c; bl_nr[o] = 2; bl_kind[o] = 2; bl_entry[o] = hl;
+      ++o;
     }
+  };
+
+  if ((size_t)S.n_pp + S.n_pl > 200000) {
+    std::thread t1(build_incidence), t2(build_pp);
+    build_pl();
+    t1.join();
+    t2.join();
+  } else {
+    build_incidence();
+    build_pp();
+    build_pl();
   }
-  S.block_values = 0;
-  for (size_t k = 0; k < S.blk_row.size(); ++k) S.block_values += (int64_t)S.blk_nr[k] * S.blk_nc[k];
+
+  // ---- concatenated reference block list: pose columns, then landmark columns
+  size_t n0 = bp_row.size(), n1 = bl_row.size();
+  S.blk_row.resize(n0 + n1); S.blk_col.resize(n0 + n1); S.blk_nr.resize(n0 + n1); S.blk_nc.resize(n0 + n1);
+  S.blk_kind.resize(n0 + n1); S.blk_entry.resize(n0 + n1);
+  std::copy(bp_row.begin(), bp_row.end(), S.blk_row.begin());
+  std::copy(bp_col.begin(), bp_col.end(), S.blk_col.begin());
+  std::copy(bp_entry.begin(), bp_entry.end(), S.blk_entry.begin());
+  std::fill(S.blk_nr.begin(), S.blk_nr.begin() + n0, 3);
+  std::fill(S.blk_nc.begin(), S.blk_nc.begin() + n0, 3);
+  std::fill(S.blk_kind.begin(), S.blk_kind.begin() + n0, 0);
+  std::copy(bl_row.begin(), bl_row.end(), S.blk_row.begin() + n0);
+  std::copy(bl_col.begin(), bl_col.end(), S.blk_col.begin() + n0);
+  std::copy(bl_nr.begin(), bl_nr.end(), S.blk_nr.begin() + n0);
+  std::fill(S.blk_nc.begin() + n0, S.blk_nc.end(), 2);
+  std::copy(bl_kind.begin(), bl_kind.end(), S.blk_kind.begin() + n0);
+  std::copy(bl_entry.begin(), bl_entry.end(), S.blk_entry.begin() + n0);
+  S.block_values = 9 * (int64_t)n0;
+  for (size_t k = 0; k < n1; ++k) S.block_values += (int64_t)bl_nr[k] * 2;
   return SGB_OK;
 }
 

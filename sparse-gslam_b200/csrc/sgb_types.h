@@ -125,6 +125,7 @@ struct DevScalars {
   int32_t result;       // SGB_RESULT_*
   int32_t again;        // LM: run another trial
   int32_t pad;
+  unsigned long long pcg_phase_ns[4];  // k_pcg: accumulated wall time of phases A-D seen by CTA 0 (reset per optimize)
 };
 
 }  // namespace sgb

@@ -407,3 +407,19 @@ void hs_get_estimates(hs_handle* h, int rank, double* pose, double* lm) {
 void hs_chi2(hs_handle* h, double* chi2) { chi2_edges(h, h->cur, chi2); }
 
 }  // extern "C"
+
+// timing of the host symbolic phase alone (seconds): out[0] = build_structure, out[1] = partition(world, rank 0)
+#include <chrono>
+extern "C" int hs_time_structure(const sgb_graph_soa* g, int world, double* out) {
+  Structure S;
+  LocalPlan P;
+  std::string err;
+  auto t0 = std::chrono::steady_clock::now();
+  sgb_status st = build_structure(*g, S, err);
+  auto t1 = std::chrono::steady_clock::now();
+  if (st == SGB_OK) st = partition(S, world, 0, P, err);
+  auto t2 = std::chrono::steady_clock::now();
+  out[0] = std::chrono::duration<double>(t1 - t0).count();
+  out[1] = std::chrono::duration<double>(t2 - t1).count();
+  return st;
+}
