@@ -37,8 +37,15 @@ class IterStat(C.Structure):
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libsgo_oracle.so")
     src = os.path.join(_HERE, "sgo_oracle.cpp")
-    if force or not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so)):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s"])
+    def stale():
+        return not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so))
+
+    if force or stale():
+        import fcntl
+        with open(so + ".lock", "w") as lk:  # several test processes may get here at once
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if force or stale():
+                subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s"])
     return so
 
 

@@ -36,14 +36,18 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, s) for s in SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-        raise RuntimeError("nvcc failed building libsgb.so")
-    if verbose:
-        sys.stderr.write(res.stderr)
+    from ._buildlock import build_lock
+    with build_lock(LIB) as tmp:
+        if not force and not needs_build():  # another process built it while this one waited for the lock
+            return LIB
+        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp] + \
+              [os.path.join(CSRC, s) for s in SOURCES]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            sys.stderr.write(res.stdout + res.stderr)
+            raise RuntimeError("nvcc failed building libsgb.so")
+        if verbose:
+            sys.stderr.write(res.stderr)
     return LIB
 
 

@@ -131,6 +131,12 @@ sgb_status upload_sell(sgb_handle* h, Sell* out, const HostSell& s, int NC) {
   if (st != SGB_OK) return st;
   st = upload(h, &out->col, s.col);
   if (st != SGB_OK) return st;
+  out->srow = nullptr;
+  out->sshift = nullptr;
+  if (s.grouped()) {
+    if ((st = upload(h, &out->srow, s.srow)) != SGB_OK) return st;
+    if ((st = upload(h, &out->sshift, s.sshift)) != SGB_OK) return st;
+  }
   st = dalloc(h, &out->vals, (size_t)s.entries() * NC);
   if (st != SGB_OK) return st;
   SGB_CUDA(cudaMemsetAsync(out->vals, 0, std::max<size_t>((size_t)s.entries() * NC, 1) * sizeof(double), h->stream));
@@ -216,7 +222,7 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
 sgb_status launch_backsub_update(sgb_handle* h, int dst, double lambda_override, int use_override) {
   DevGraph& G = h->G;
   if (G.nL > 0) {
-    k_backsub<<<grid_for(G.nL), kThreads, 0, h->stream>>>(G);
+    k_backsub<<<grid_for(32 * G.Hlp.nslices), kThreads, 0, h->stream>>>(G);  // one warp per slice of the grouped Hlp
     h->tm.kernel_launches++;
   }
   k_update<<<grid_for(G.nP + G.nL), kThreads, 0, h->stream>>>(G, h->d_sc, dst, h->d_part_p, lambda_override, use_override);
@@ -572,7 +578,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   UP(pl_p, P.pl_p); UP(pl_l, P.pl_l); UP(pl_hp, P.pl_hp); UP(pl_hl, P.pl_hl);
   UP(pl_e_pl, P.pl_e_pl); UP(pl_e_lp, P.pl_e_lp); UP(pl_dup, P.pl_dup);
   UP(pinc_ptr, P.pinc_ptr); UP(pinc, P.pinc); UP(linc_ptr, P.linc_ptr); UP(linc, P.linc);
-  UP(hpp_diag, P.hpp_diag); UP(lp_row2l, P.lp_row2l);
+  UP(hpp_diag, P.hpp_diag);
   lap("upload maps");
   for (auto& t : workers) t.join();
   workers.clear();
@@ -597,7 +603,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   int per_sm = 0;
   SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, kThreads, 0));
   int limit = std::max(1, per_sm * h->sm_count);
-  int want = std::max(1, (std::max(P.nP, P.nL) + kThreads - 1) / kThreads);
+  int want = std::max(1, (std::max(P.nP, 32 * P.Hlp.nslices) + kThreads - 1) / kThreads);
   h->pcg_blocks = std::min(std::min(limit, want), kMaxBlocks);
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   lap("matrices+sync");
@@ -757,7 +763,7 @@ sgb_status sgb_solve_once(sgb_handle* h, double lambda, double* x, int32_t* pcg_
   if ((st = launch_setup(h, lambda, 1)) != SGB_OK) return st;
   if ((st = launch_pcg(h, lambda, 1)) != SGB_OK) return st;
   if (h->G.nL > 0) {
-    k_backsub<<<grid_for(h->G.nL), kThreads, 0, h->stream>>>(h->G);
+    k_backsub<<<grid_for(32 * h->G.Hlp.nslices), kThreads, 0, h->stream>>>(h->G);
     h->tm.kernel_launches++;
   }
   k_gn_control<<<1, 32, 0, h->stream>>>(h->G, h->d_sc);

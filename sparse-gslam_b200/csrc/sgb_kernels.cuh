@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g
     t_ph = globaltimer_ns();
     while (it < prm.maxit) {
       if (g.capL > 0) {
-        for (int row = tid; row < g.nL; row += nthreads) schur_phaseA_row(g, row);
+        for (int sl = tid >> 5; sl < g.Hlp.nslices; sl += nthreads >> 5) lm_slice_pass(g, sl, 0);
         grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, &s_last);  // every rank's t segment is complete
       }
       SGB_PHASE_LAP(0);
@@ -454,7 +454,8 @@ __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g
 
 // ------------------------------------------------------------------------------------------------ update
 __global__ void __launch_bounds__(kThreads) k_backsub(DevGraph g) {
-  for (int row = blockIdx.x * blockDim.x + threadIdx.x; row < g.nL; row += gridDim.x * blockDim.x) backsub_lm_row(g, row);
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; sl < g.Hlp.nslices; sl += nwarps) lm_slice_pass(g, sl, 1);
 }
 // SparseOptimizer::update into estimate buffer `dst` of every rank (the LM trial buffer, or the current one for GN)
 // + computeScale partials

@@ -2,6 +2,7 @@
 #include "sgb_partition.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
 #include <thread>
 
@@ -23,8 +24,8 @@ inline int sell_row_cols(const HostSell& M, int sell_row, std::vector<int32_t>& 
   }
   return (int)cols.size();
 }
-inline int entry_k(const HostSell& M, int sell_row, int entry) { return (entry - M.sbase[sell_row >> 5]) >> 5; }
-inline int entry_of(const HostSell& M, int sell_row, int k) { return M.sbase[sell_row >> 5] + k * 32 + (sell_row & 31); }
+inline int entry_k(const HostSell& M, int sell_row, int entry) { return M.k_of(sell_row, entry); }
+inline int entry_of(const HostSell& M, int sell_row, int k) { return M.entry(sell_row, k); }
 
 // flat row lists (CSR): row r holds col[ptr[r] .. ptr[r+1])
 struct FlatRows {
@@ -58,6 +59,53 @@ void build_local_sell(const FlatRows& rows, const std::vector<int32_t>* order, H
   }
 }
 
+inline int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+// Grouped SELL of the landmark-major matrix; the rows come sorted by descending length, so the first row of a
+// slice is its longest. A slice whose rows have up to `len` blocks gives each row
+// G = pow2_ceil(len / target_steps) lanes (<= 32), i.e. holds 32 / G rows: every warp task is then about
+// `target_steps` block-steps long whatever the observer count (20 observers per wall in a grid world, hundreds
+// for the hub landmarks of a corridor graph), which is what balances the landmark pass of the Schur product.
+void build_grouped_sell(const FlatRows& rows, int target_steps, HostSell& S) {
+  const int n = rows.rows();
+  S.rows = n;
+  S.sbase.assign(1, 0);
+  S.srow.clear();
+  S.sshift.clear();
+  S.row_slice.assign(n, 0);
+  for (int r = 0; r < n;) {
+    int len = rows.size(r);
+    int G = std::min(32, pow2_ceil((len + target_steps - 1) / std::max(1, target_steps)));
+    int rh = 32 / G, sh = 0;
+    while ((1 << sh) < rh) ++sh;
+    int w = (len + G - 1) / G * G;
+    int s = (int)S.sshift.size();
+    S.srow.push_back(r);
+    S.sshift.push_back(sh);
+    S.sbase.push_back(S.sbase.back() + w * rh);
+    for (int q = r; q < std::min(n, r + rh); ++q) S.row_slice[q] = s;
+    r += rh;
+  }
+  S.nslices = (int)S.sshift.size();
+  S.srow.push_back(n);
+  S.col.assign((size_t)S.sbase[S.nslices], -1);
+  for (int r = 0; r < n; ++r) {
+    const int32_t* src = rows.col.data() + rows.ptr[r];
+    for (int k = 0, m = rows.size(r); k < m; ++k) S.col[(size_t)S.entry(r, k)] = src[k];
+  }
+}
+
+// block-steps per lane in the landmark pass: a large matrix is throughput-bound (fewer, longer lane loops issue
+// fewer warp-steps), a small one latency-bound (more lanes per row shorten the dependent chain)
+int lm_target_steps(size_t blocks) {
+  static const int forced = [] {
+    const char* e = std::getenv("SGB_LM_STEPS");  // tuning knob
+    return e ? std::atoi(e) : 0;
+  }();
+  if (forced > 0) return forced;
+  return blocks >= ((size_t)1 << 20) ? 6 : 2;
+}
+
 }  // namespace
 
 sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std::string& err) {
@@ -80,14 +128,30 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
     if (hp < 0 || hl < 0) continue;
     if (lm_first[hl] < 0 || hp < lm_first[hl]) lm_first[hl] = hp;
   }
+  // Local landmark numbering = row order of the landmark-major matrix: per owner, descending observer count
+  // (stable in the Hessian index), so that the slices of the grouped SELL are uniform and no row -> landmark
+  // indirection is needed on the device. One stable counting sort over (owner, -count) covers every rank.
   std::vector<int32_t> count(world, 0);
   P.enc_lm.assign(S.Lf, 0);
-  for (int hl = 0; hl < S.Lf; ++hl) {
-    int o = lm_first[hl] >= 0 ? owner_p(lm_first[hl]) : 0;
-    lm_owner[hl] = o;
-    P.enc_lm[hl] = (o << kOwnerShift) | count[o];
-    if (o == rank) P.lm_global.push_back(hl);
-    count[o]++;
+  {
+    int maxc = 0;
+    for (int hl = 0; hl < S.Lf; ++hl) {
+      lm_owner[hl] = lm_first[hl] >= 0 ? owner_p(lm_first[hl]) : 0;
+      maxc = std::max(maxc, S.lp_ptr[hl + 1] - S.lp_ptr[hl]);
+    }
+    const size_t nb = (size_t)world * ((size_t)maxc + 1);
+    std::vector<int32_t> start(nb + 1, 0);
+    auto key = [&](int hl) { return (size_t)lm_owner[hl] * ((size_t)maxc + 1) + (size_t)(maxc - (S.lp_ptr[hl + 1] - S.lp_ptr[hl])); };
+    for (int hl = 0; hl < S.Lf; ++hl) start[key(hl) + 1]++;
+    for (size_t b = 0; b < nb; ++b) start[b + 1] += start[b];
+    std::vector<int32_t> sorted(S.Lf);
+    for (int hl = 0; hl < S.Lf; ++hl) sorted[start[key(hl)]++] = hl;
+    for (int q = 0; q < S.Lf; ++q) {
+      int hl = sorted[q], o = lm_owner[hl];
+      P.enc_lm[hl] = (o << kOwnerShift) | count[o];
+      if (o == rank) P.lm_global.push_back(hl);
+      count[o]++;
+    }
   }
   P.nL = count[rank];
   P.capL = *std::max_element(count.begin(), count.end());
@@ -161,25 +225,21 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
       P.hpp_diag[l] = entry_of(P.Hpp, l, entry_k(S.Hpp, hp, S.hpp_diag[hp]));
     }
   };
-  std::vector<int32_t> lrow_of_local(P.nL, 0);  // local landmark -> Hlp row
   auto build_lm_rows = [&]() {
     std::vector<int32_t> cols;
     // owned landmarks sorted by descending observer count (stable) to keep the SELL padding small
     FlatRows obs(P.nL);
-    obs.col.reserve(S.Hlp.col.size() / world + 1024);
+    obs.col.reserve(S.lp_col.size() / world + 1024);
     for (int l = 0; l < P.nL; ++l) {
-      sell_row_cols(S.Hlp, S.lp_h2row[P.lm_global[l]], cols);
-      for (int c : cols) {
+      int hl = P.lm_global[l];
+      for (int q = S.lp_ptr[hl]; q < S.lp_ptr[hl + 1]; ++q) {
+        int c = S.lp_col[q];
         obs.col.push_back(enc_pose(c, P.chunkP));
         if (owner_p(c) != rank) halo_p_lm++;
       }
       obs.close_row();
     }
-    P.lp_row2l.resize(P.nL);
-    std::iota(P.lp_row2l.begin(), P.lp_row2l.end(), 0);
-    std::stable_sort(P.lp_row2l.begin(), P.lp_row2l.end(), [&](int a, int b) { return obs.size(a) > obs.size(b); });
-    for (int r = 0; r < P.nL; ++r) lrow_of_local[P.lp_row2l[r]] = r;
-    build_local_sell(obs, &P.lp_row2l, P.Hlp);
+    build_grouped_sell(obs, lm_target_steps(obs.col.size()), P.Hlp);  // rows already sorted by descending length
   };
   const bool threaded = (size_t)P.n_pp + P.n_pl > 200000;
   if (threaded) {
@@ -219,7 +279,7 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
       if (pose_local(hp)) P.pl_e_pl[l] = entry_of(P.Hpl, hp - P.p_begin, entry_k(S.Hpl, hp, S.pl_e_pl[k]));
       if (lm_local(hl)) {
         int ll = P.enc_lm[hl] & kLocalMask;
-        P.pl_e_lp[l] = entry_of(P.Hlp, lrow_of_local[ll], entry_k(S.Hlp, S.lp_h2row[hl], S.pl_e_lp[k]));
+        P.pl_e_lp[l] = entry_of(P.Hlp, ll, S.pl_k_lp[k]);
       }
     }
   }

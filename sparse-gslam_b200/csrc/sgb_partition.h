@@ -25,7 +25,7 @@ struct LocalPlan {
   std::vector<int32_t> pl_p, pl_l, pl_hp, pl_hl, pl_e_pl, pl_e_lp, pl_dup;
   std::vector<int32_t> pinc_ptr, pinc, linc_ptr, linc;
   HostSell Hpp, Hpl, Hlp;
-  std::vector<int32_t> hpp_diag, lp_row2l;
+  std::vector<int32_t> hpp_diag;
   // reference-order export: for every block of Structure::blk_* the owner rank and the local entry
   std::vector<int32_t> blk_owner, blk_entry;
   // halo statistics (distinct remote entries this rank gathers per PCG iteration)

@@ -18,6 +18,19 @@
 #endif
 
 namespace sgb {
+// two consecutive doubles at a 16-byte aligned address with one L1-bypassing 128-bit load (one L2 request, not two)
+struct Pair64 { double a, b; };
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ Pair64 ldcg_pair(const double* p) {
+  double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+  return {v.x, v.y};
+}
+#else
+inline Pair64 ldcg_pair(const double* p) { return {p[0], p[1]}; }
+#endif
+}  // namespace sgb
+
+namespace sgb {
 
 struct LinAcc {
   double chi = 0.0;    // sum of e^T Omega e over the edges this row owns
@@ -359,18 +372,19 @@ SGB_HD bool setup_pose_row(const DevGraph& g, int lp, double lambda) {
 // is the plain k = 0, 1, 2, ... order, so results do not depend on the unrolling.
 SGB_HD int sell_col_or_pad(const int32_t* col, int e, bool valid) { return valid ? SGB_LDG(&col[e]) : -1; }
 
-// phase A (landmark-major): t_l = (Hll_l + lambda I)^-1 * sum_i Hpl_il^T v_i       row = local Hlp row
+// Landmark-major pass over one slice of the grouped Hlp (sgb_types.h): this lane's share of
+// u_l = sum_i Hpl_il^T v_i for row srow[slice] + lane / G. The G lanes of a row are then summed
+// with lm_group_sum (device: shuffles; host harness: the same butterfly over an array).
 // vtab[o] = pose-vector segment of rank o (p during PCG, x_p during back-substitution)
-SGB_HD void lm_gather_row(const DevGraph& g, int row, double* const* vtab, double* u0_out, double* u1_out) {
-  const int slice = row >> 5, lane = row & 31;
-  const int w = sell_width(g.Hlp, slice);
+SGB_HD void lm_gather_lane(const DevGraph& g, int slice, int lane, double* const* vtab, double* u0_out, double* u1_out) {
+  const int steps = (g.Hlp.sbase[slice + 1] - g.Hlp.sbase[slice]) >> 5;
   const int base = g.Hlp.sbase[slice] + lane;
   const int32_t* col = g.Hlp.col;
   double u0 = 0, u1 = 0;
-  int enc0 = sell_col_or_pad(col, base, w > 0), enc1 = sell_col_or_pad(col, base + 32, w > 1);
-  for (int k = 0; k < w; k += 2) {
-    const int e0 = base + k * 32, e1 = e0 + 32;
-    const int n0 = sell_col_or_pad(col, e0 + 64, k + 2 < w), n1 = sell_col_or_pad(col, e1 + 64, k + 3 < w);
+  int enc0 = sell_col_or_pad(col, base, steps > 0), enc1 = sell_col_or_pad(col, base + 32, steps > 1);
+  for (int j = 0; j < steps; j += 2) {
+    const int e0 = base + j * 32, e1 = e0 + 32;
+    const int n0 = sell_col_or_pad(col, e0 + 64, j + 2 < steps), n1 = sell_col_or_pad(col, e1 + 64, j + 3 < steps);
     double v[2][3] = {{0, 0, 0}, {0, 0, 0}}, a[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
     if (enc0 >= 0) {
       const double* pv = vtab[enc0 >> kOwnerShift] + 3 * (size_t)(enc0 & kLocalMask);
@@ -394,16 +408,83 @@ SGB_HD void lm_gather_row(const DevGraph& g, int row, double* const* vtab, doubl
   *u0_out = u0;
   *u1_out = u1;
 }
-SGB_HD void schur_phaseA_row(const DevGraph& g, int row) {
-  double u0, u1;
-  lm_gather_row(g, row, g.p, &u0, &u1);
-  int ll = g.lp_row2l[row];
-  const double* W = g.Hll_inv[g.rank];
-  double w11 = W[ll], w12 = W[(size_t)g.capL + ll], w22 = W[2 * (size_t)g.capL + ll];
-  double* t = g.t[g.rank];
-  t[2 * (size_t)ll] = w11 * u0 + w12 * u1;
-  t[2 * (size_t)ll + 1] = w12 * u0 + w22 * u1;
+#if defined(__CUDA_ARCH__)
+// butterfly over the G = 32 >> shift neighbouring lanes that share a row: every lane of the group ends with the sum
+__device__ __forceinline__ void lm_group_sum(int shift, double& u0, double& u1) {
+  for (int off = 1; off < (32 >> shift); off <<= 1) {
+    u0 += __shfl_xor_sync(0xffffffffu, u0, off);
+    u1 += __shfl_xor_sync(0xffffffffu, u1, off);
+  }
 }
+#else
+inline void lm_group_sum_host(int shift, double u0[32], double u1[32]) {
+  for (int off = 1; off < (32 >> shift); off <<= 1) {
+    double a[32], b[32];
+    for (int l = 0; l < 32; ++l) { a[l] = u0[l] + u0[l ^ off]; b[l] = u1[l] + u1[l ^ off]; }
+    for (int l = 0; l < 32; ++l) { u0[l] = a[l]; u1[l] = b[l]; }
+  }
+}
+#endif
+// Finish of a landmark row (= local landmark `ll`): mode 0, phase A of the Schur product, t_l = W_l u_l with
+// W_l = (Hll_l + lambda I)^-1; mode 1, back-substitution, x_l = W_l (b_l - u_l). The operands that do not depend on
+// the gather (W_l, b_l) are fetched by lm_row_prefetch BEFORE the gather loop so that their latency overlaps it.
+struct LmRowOperands {
+  double w11, w12, w22, b0, b1;
+};
+SGB_HD void lm_row_prefetch(const DevGraph& g, int ll, int mode, LmRowOperands& o) {
+  const double* W = g.Hll_inv[g.rank];
+  o.w11 = W[ll];
+  o.w12 = W[(size_t)g.capL + ll];
+  o.w22 = W[2 * (size_t)g.capL + ll];
+  o.b0 = o.b1 = 0.0;
+  if (mode == 1) {
+    const double* bl = g.b_l[g.rank];
+    o.b0 = bl[2 * (size_t)ll];
+    o.b1 = bl[2 * (size_t)ll + 1];
+  }
+}
+SGB_HD void lm_row_finish(const DevGraph& g, int ll, int mode, const LmRowOperands& o, double u0, double u1) {
+  if (mode == 0) {
+    double* t = g.t[g.rank];
+    t[2 * (size_t)ll] = o.w11 * u0 + o.w12 * u1;
+    t[2 * (size_t)ll + 1] = o.w12 * u0 + o.w22 * u1;
+  } else {
+    u0 = o.b0 - u0;
+    u1 = o.b1 - u1;
+    g.x_l[2 * (size_t)ll] = o.w11 * u0 + o.w12 * u1;
+    g.x_l[2 * (size_t)ll + 1] = o.w12 * u0 + o.w22 * u1;
+  }
+}
+// One slice of the landmark-major pass, executed by one warp (all 32 lanes must call): mode 0 = phase A on p,
+// mode 1 = back-substitution on x_p.
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void lm_slice_pass(const DevGraph& g, int slice, int mode) {
+  const int lane = threadIdx.x & 31;
+  const int sh = g.Hlp.sshift[slice];
+  const int row = g.Hlp.srow[slice] + (lane >> (5 - sh));
+  const bool writer = (lane & ((32 >> sh) - 1)) == 0 && row < g.Hlp.srow[slice + 1];
+  LmRowOperands o;
+  if (writer) lm_row_prefetch(g, row, mode, o);
+  double u0, u1;
+  lm_gather_lane(g, slice, lane, mode == 0 ? g.p : g.x_p, &u0, &u1);
+  lm_group_sum(sh, u0, u1);
+  if (writer) lm_row_finish(g, row, mode, o, u0, u1);
+}
+#else
+inline void lm_slice_pass(const DevGraph& g, int slice, int mode) {
+  double u0[32], u1[32];
+  for (int lane = 0; lane < 32; ++lane) lm_gather_lane(g, slice, lane, mode == 0 ? g.p : g.x_p, &u0[lane], &u1[lane]);
+  const int sh = g.Hlp.sshift[slice];
+  lm_group_sum_host(sh, u0, u1);
+  for (int rr = 0; rr < (1 << sh); ++rr) {
+    int row = g.Hlp.srow[slice] + rr, lane = rr << (5 - sh);
+    if (row >= g.Hlp.srow[slice + 1]) break;
+    LmRowOperands o;
+    lm_row_prefetch(g, row, mode, o);
+    lm_row_finish(g, row, mode, o, u0[lane], u1[lane]);
+  }
+}
+#endif
 // phase B (pose-major): q_i = lambda v_i + sum_j Hpp_ij v_j - sum_l Hpl_il t_l ; returns v_i . q_i  (v = p)
 SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda) {
   const int slice = lp >> 5, lane = lp & 31;
@@ -449,15 +530,17 @@ SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda) {
     if (l0 >= 0) {
       const double* pt = g.t[l0 >> kOwnerShift] + 2 * (size_t)(l0 & kLocalMask);
       const double* pa = g.Hpl.vals + sell_vaddr(e0, 6, 0);
-      tv[0][0] = SGB_LDCG(pt);
-      tv[0][1] = SGB_LDCG(pt + 1);
+      Pair64 tt = ldcg_pair(pt);
+      tv[0][0] = tt.a;
+      tv[0][1] = tt.b;
       for (int c = 0; c < 6; ++c) a[0][c] = SGB_LDG(pa + 32 * c);
     }
     if (l1 >= 0) {
       const double* pt = g.t[l1 >> kOwnerShift] + 2 * (size_t)(l1 & kLocalMask);
       const double* pa = g.Hpl.vals + sell_vaddr(e1, 6, 0);
-      tv[1][0] = SGB_LDCG(pt);
-      tv[1][1] = SGB_LDCG(pt + 1);
+      Pair64 tt = ldcg_pair(pt);
+      tv[1][0] = tt.a;
+      tv[1][1] = tt.b;
       for (int c = 0; c < 6; ++c) a[1][c] = SGB_LDG(pa + 32 * c);
     }
     for (int u = 0; u < 2; ++u) {
@@ -481,20 +564,6 @@ SGB_HD double precond_row(const DevGraph& g, int lp, const double r[3], double z
   z[1] = SGB_LDG(m + 3 * s) * r[0] + SGB_LDG(m + 4 * s) * r[1] + SGB_LDG(m + 5 * s) * r[2];
   z[2] = SGB_LDG(m + 6 * s) * r[0] + SGB_LDG(m + 7 * s) * r[1] + SGB_LDG(m + 8 * s) * r[2];
   return r[0] * z[0] + r[1] * z[1] + r[2] * z[2];
-}
-
-// back-substitution  x_l = (Hll_l + lambda I)^-1 (b_l - sum_i Hpl_il^T x_i)
-SGB_HD void backsub_lm_row(const DevGraph& g, int row) {
-  double u0, u1;
-  lm_gather_row(g, row, g.x_p, &u0, &u1);
-  int ll = g.lp_row2l[row];
-  const double* bl = g.b_l[g.rank];
-  u0 = bl[2 * (size_t)ll] - u0;
-  u1 = bl[2 * (size_t)ll + 1] - u1;
-  const double* W = g.Hll_inv[g.rank];
-  double w11 = W[ll], w12 = W[(size_t)g.capL + ll], w22 = W[2 * (size_t)g.capL + ll];
-  g.x_l[2 * (size_t)ll] = w11 * u0 + w12 * u1;
-  g.x_l[2 * (size_t)ll + 1] = w12 * u0 + w22 * u1;
 }
 
 // SparseOptimizer::update for one owned free vertex: reads the current estimate, writes the new one into buffer

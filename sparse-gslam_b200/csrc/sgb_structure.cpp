@@ -181,7 +181,7 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     S.pp_hi[k] = S.pose_h[g.pp_i[s]]; S.pp_hj[k] = S.pose_h[g.pp_j[s]];
   }
   S.pl_p.resize(S.n_pl); S.pl_l.resize(S.n_pl); S.pl_hp.resize(S.n_pl); S.pl_hl.resize(S.n_pl);
-  S.pl_e_pl.assign(S.n_pl, -1); S.pl_e_lp.assign(S.n_pl, -1); S.pl_dup.assign(S.n_pl, -1);
+  S.pl_e_pl.assign(S.n_pl, -1); S.pl_k_lp.assign(S.n_pl, -1); S.pl_dup.assign(S.n_pl, -1);
   for (int k = 0; k < S.n_pl; ++k) {
     int s = S.pl_src[k];
     S.pl_p[k] = g.pl_pose[s]; S.pl_l[k] = g.pl_lm[s];
@@ -318,23 +318,10 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
       rows_lp.col[rows_lp.ptr[b] + pos_lp[b]++] = a;
     }
     make_sell(rows_pl, S.Pf, nullptr, S.Hpl);
-    // landmark rows sorted by descending observer count (stable) so that a 32-row slice pads little
-    S.lp_row2h.resize(S.Lf);
-    {
-      int maxc = 0;
-      for (int l = 0; l < S.Lf; ++l) maxc = std::max(maxc, rows_lp.ptr[l + 1] - rows_lp.ptr[l]);
-      std::vector<int32_t> bstart((size_t)maxc + 2, 0);
-      for (int l = 0; l < S.Lf; ++l) bstart[(size_t)(maxc - (rows_lp.ptr[l + 1] - rows_lp.ptr[l])) + 1]++;
-      for (int c = 0; c <= maxc; ++c) bstart[c + 1] += bstart[c];
-      for (int l = 0; l < S.Lf; ++l) S.lp_row2h[bstart[maxc - (rows_lp.ptr[l + 1] - rows_lp.ptr[l])]++] = l;
-    }
-    S.lp_h2row.assign(S.Lf, 0);
-    for (int r = 0; r < S.Lf; ++r) S.lp_h2row[S.lp_row2h[r]] = r;
-    make_sell(rows_lp, S.Lf, &S.lp_row2h, S.Hlp);
     for (int t = 0; t < np; ++t) {
       int k = pk[t];
       S.pl_e_pl[k] = sell_entry(S.Hpl, pa[t], idx_pl[t]);
-      S.pl_e_lp[k] = sell_entry(S.Hlp, S.lp_h2row[pb[t]], idx_lp[t]);
+      S.pl_k_lp[k] = idx_lp[t];
     }
     // reference block list, landmark columns: pose rows ascending, then the diagonal
     size_t nb = (size_t)np + S.Lf, o = 0;
@@ -349,6 +336,8 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
       bl_row[o] = c; bl_col[o] = c; bl_nr[o] = 2; bl_kind[o] = 2; bl_entry[o] = hl;
       ++o;
     }
+    S.lp_ptr.swap(rows_lp.ptr);
+    S.lp_col.swap(rows_lp.col);
   };
 
   if ((size_t)S.n_pp + S.n_pl > 200000) {

@@ -14,11 +14,34 @@
 
 namespace sgb {
 
+// Sliced-ELL block pattern. Uniform form (pose-major matrices): 32-row slices, entry of (row, k) =
+// sbase[row / 32] + k * 32 + row % 32. Grouped form (the landmark-major matrix): slice s holds 2^sshift[s] rows
+// starting at srow[s] and gives each of them G = 32 >> sshift[s] lanes; the k-th block of its row rr sits at
+// sbase[s] + (k / G) * 32 + rr * G + k % G, so that a warp whose lane (rr * G + kk) walks k = kk, kk + G, ... reads 32
+// consecutive entries per step and neighbouring lanes hold neighbouring blocks of the same row.
 struct HostSell {
   int rows = 0, nslices = 0;
-  std::vector<int32_t> sbase;  // [nslices + 1]
+  std::vector<int32_t> sbase;  // [nslices + 1] entry offset of each slice (multiple of 32)
   std::vector<int32_t> col;    // [entries]
+  std::vector<int32_t> srow, sshift, row_slice;  // grouped form only: [nslices + 1], [nslices], [rows]
   int64_t entries() const { return (int64_t)col.size(); }
+  bool grouped() const { return !sshift.empty(); }
+  int slice_of(int row) const { return grouped() ? row_slice[row] : row >> 5; }
+  int shift(int s) const { return grouped() ? sshift[s] : 5; }
+  int first_row(int s) const { return grouped() ? srow[s] : s << 5; }
+  int width(int s) const { return (sbase[s + 1] - sbase[s]) >> shift(s); }  // blocks per row, padding included
+  int entry(int row, int k) const {
+    int s = slice_of(row);
+    if (!grouped()) return sbase[s] + (k << 5) + (row & 31);
+    int gsh = 5 - sshift[s], G = 1 << gsh;
+    return sbase[s] + ((k >> gsh) << 5) + ((row - srow[s]) << gsh) + (k & (G - 1));
+  }
+  int k_of(int row, int e) const {
+    int s = slice_of(row), d = e - sbase[s];
+    if (!grouped()) return d >> 5;
+    int gsh = 5 - sshift[s];
+    return ((d >> 5) << gsh) + (d & ((1 << gsh) - 1));
+  }
 };
 
 struct Structure {
@@ -31,12 +54,14 @@ struct Structure {
   std::vector<int32_t> pp_src, pl_src;
   // per active edge
   std::vector<int32_t> pp_i, pp_j, pp_hi, pp_hj, pp_e_ij, pp_e_ji, pp_dup;
-  std::vector<int32_t> pl_p, pl_l, pl_hp, pl_hl, pl_e_pl, pl_e_lp, pl_dup;
+  std::vector<int32_t> pl_p, pl_l, pl_hp, pl_hl, pl_e_pl, pl_k_lp, pl_dup;  // pl_k_lp: position in the landmark's row
   // incidence
   std::vector<int32_t> pinc_ptr, pinc, linc_ptr, linc;
   // matrices
-  HostSell Hpp, Hpl, Hlp;
-  std::vector<int32_t> hpp_diag, lp_row2h, lp_h2row;
+  HostSell Hpp, Hpl;
+  std::vector<int32_t> hpp_diag;
+  std::vector<int32_t> lp_ptr, lp_col;  // landmark-major row lists (CSR over free landmarks, observers ascending); the
+                                        // landmark-major SELL copy itself is laid out per rank by the partition planner
   // ---- g2o block structure (what "symbolic structure bit-exact" is checked on)
   std::vector<int32_t> ord_kind, ord_index, ord_offset;  // per Hessian index
   std::vector<int32_t> blk_row, blk_col, blk_nr, blk_nc; // column-major, rows ascending

@@ -19,12 +19,20 @@ constexpr int kLocalMask = (1 << kOwnerShift) - 1;
 // Entry e = sbase[slice] + k*32 + lane addresses the k-th block of row (slice*32 + lane); its NC values live at
 // vals[(e & ~31) * NC + c * 32 + (e & 31)], c = 0..NC-1, so that one warp reading component c of its k-th blocks
 // touches 32 consecutive doubles (one 256-byte, fully coalesced request).
+//
+// The landmark-major matrix uses the GROUPED form: slice s holds 2^sshift[s] rows starting at srow[s] and gives each
+// of them G = 32 >> sshift[s] lanes; lane (rr * G + kk) of the warp that owns the slice walks the blocks
+// k = kk, kk + G, ... of row srow[s] + rr, and entry sbase[s] + j*32 + lane is its j-th block -- the same "32
+// consecutive entries per warp step" addressing, with the row sum finished by a shuffle reduction over the G lanes.
+// Neighbouring lanes hold neighbouring observers of one landmark (consecutive key-frames), so the gathers coalesce.
 struct Sell {
   int32_t rows;          // number of (local) rows
   int32_t nslices;
   const int32_t* sbase;  // [nslices + 1] entry offset of each slice (multiple of 32)
   const int32_t* col;    // [entries] encoded column or -1 for padding
   double* vals;          // [entries * NC]
+  const int32_t* srow;   // grouped form: [nslices + 1] first row of each slice; NULL = uniform 32-row slices
+  const int32_t* sshift; // grouped form: [nslices] log2(rows in the slice)
 };
 
 // cross-rank signalling slots (one per rank, in the peer-mapped arena)
@@ -81,9 +89,8 @@ struct DevGraph {
   // ---- Hessian rows owned by this rank (un-reduced, lambda NOT included) and gradient
   Sell Hpp;                  // nP x Pf, 3x3 blocks row-major (NC = 9), both triangles; columns = encoded poses
   Sell Hpl;                  // nP x Lf, 3x2 blocks row-major (NC = 6); columns = encoded landmarks
-  Sell Hlp;                  // nL x Pf, the same 3x2 blocks (NC = 6), landmark-major; row r = local landmark lp_row2l[r]
+  Sell Hlp;                  // nL x Pf, the same 3x2 blocks (NC = 6), landmark-major; row r = local landmark r
   const int32_t* hpp_diag;   // [nP] Hpp entry of the diagonal block
-  const int32_t* lp_row2l;   // [nL] Hlp row -> local landmark
   double* Hll;               // [3][nL] (11,12,22), stride nL
   double* b_p;               // [3*nP]
   // ---- vectors other ranks gather from: tbl[rank] is this rank's own array

@@ -48,6 +48,8 @@ static void mk_sell(Rank* r, Sell* out, const HostSell& s, int NC) {
   out->sbase = r->I(s.sbase);
   out->col = r->I(s.col);
   out->vals = r->D((size_t)s.entries() * NC);
+  out->srow = s.grouped() ? r->I(s.srow) : nullptr;
+  out->sshift = s.grouped() ? r->I(s.sshift) : nullptr;
 }
 
 extern "C" {
@@ -80,7 +82,7 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
     G.pl_p = r->I(P.pl_p); G.pl_l = r->I(P.pl_l); G.pl_hp = r->I(P.pl_hp); G.pl_hl = r->I(P.pl_hl);
     G.pl_e_pl = r->I(P.pl_e_pl); G.pl_e_lp = r->I(P.pl_e_lp); G.pl_dup = r->I(P.pl_dup);
     G.pinc_ptr = r->I(P.pinc_ptr); G.pinc = r->I(P.pinc); G.linc_ptr = r->I(P.linc_ptr); G.linc = r->I(P.linc);
-    G.hpp_diag = r->I(P.hpp_diag); G.lp_row2l = r->I(P.lp_row2l);
+    G.hpp_diag = r->I(P.hpp_diag);
     double* zinv = r->D(3 * (size_t)P.n_pp); double* info = r->D(6 * (size_t)P.n_pp); double* phi = r->D(P.n_pp);
     for (int k = 0; k < P.n_pp; ++k) {
       int s = S.pp_src[P.pp_g[k]];
@@ -240,11 +242,11 @@ double hs_check_hlp(hs_handle* h) {
     const DevGraph& G = r->G;
     const LocalPlan& P = r->P;
     for (int row = 0; row < G.nL; ++row) {
-      int ll = P.lp_row2l[row];
+      int ll = row;
       int hl = P.lm_global[ll];
-      int slice = row >> 5, lane = row & 31, w = sell_width(G.Hlp, slice);
+      int w = P.Hlp.width(P.Hlp.slice_of(row));
       for (int k = 0; k < w; ++k) {
-        int e = G.Hlp.sbase[slice] + k * 32 + lane;
+        int e = P.Hlp.entry(row, k);
         int enc = G.Hlp.col[e];
         if (enc < 0) continue;
         int o = enc >> kOwnerShift, lp = enc & kLocalMask;
@@ -291,7 +293,7 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
     double target = h->tol * h->tol * rz0;
     flag = 1;
     while (it < h->maxit) {
-      if (any_lm) for (auto& rk : h->R) for (int row = 0; row < rk->G.nL; ++row) schur_phaseA_row(rk->G, row);
+      if (any_lm) for (auto& rk : h->R) for (int sl = 0; sl < rk->G.Hlp.nslices; ++sl) lm_slice_pass(rk->G, sl, 0);
       double pq = 0;
       for (auto& rk : h->R) for (int lp = 0; lp < rk->G.nP; ++lp) pq += schur_phaseB_row(rk->G, lp, lambda);
       if (!(pq > 0.0)) { flag = 2; break; }
@@ -318,7 +320,7 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
       }
     }
   }
-  for (auto& rk : h->R) for (int row = 0; row < rk->G.nL; ++row) backsub_lm_row(rk->G, row);
+  for (auto& rk : h->R) for (int sl = 0; sl < rk->G.Hlp.nslices; ++sl) lm_slice_pass(rk->G, sl, 1);
   if (iters) *iters = it;
   if (rel) *rel = rz0 > 0 ? std::sqrt(std::fabs(rz) / rz0) : 0.0;
   if (!ok) flag = 2;
