@@ -127,8 +127,8 @@ typedef struct sgb_timings {
   int64_t linearizations;
   int64_t kernel_launches;  /* kernels launched by this library */
   /* wall time inside the persistent PCG kernel, split by phase of an iteration (barrier waits included):
-   * [0] landmark-major pass t = W Hlp^T p, [1] pose-major pass q = S p and p.q, [2] x/r/z update and r.z,
-   * [3] search-direction update */
+   * [0] landmark-major pass t = W Hlp^T z, [1] pose-major pass w = S z and z.w, [2] the fused vector recurrences
+   * (d, s, x, r, z) and r.z, [3] start-up (x = 0, r = b, z = M^-1 r) */
   double pcg_phase_ms[4];
 } sgb_timings;
 

@@ -596,8 +596,8 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   if ((st = dalloc(h, &G.Minv, 9 * (size_t)P.nP)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.bt, n3)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.r, n3)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.z, n3)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.q, n3)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.d, n3)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.s, n3)) != SGB_OK) return st;
   SGB_CUDA(cudaMemsetAsync(h->d_sc, 0, sizeof(DevScalars), h->stream));
   // persistent PCG grid: every CTA must be co-resident
   int per_sm = 0;

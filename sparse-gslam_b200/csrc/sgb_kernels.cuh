@@ -325,8 +325,8 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
     if (threadIdx.x < g.world) {
       Mailbox* mb = g.mbox[threadIdx.x];
       for (int k = 0; k < nv; ++k) st_relaxed_sys_f64(&mb->val[slot][g.rank][k], loc[k]);
-      if (g.world > 1) __threadfence_system(); else __threadfence();
-      st_release_sys_u64(&mb->flag[slot][g.rank], seq);
+      st_release_sys_u64(&mb->flag[slot][g.rank], seq);  // release: orders the values and, through the CTA barriers
+                                                          // and the ticket, everything this GPU wrote in the phase
     }
   }
   const Mailbox* me = g.mbox[g.rank];
@@ -346,17 +346,35 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
 // Preconditioned conjugate gradient on S = (Hpp + lambda I) - Hpl (Hll + lambda I)^-1 Hpl^T, M = blockdiag(S).
 // One launch per GPU runs the whole solve; every CTA of every rank evaluates the same scalars from the same sums, so
 // control flow is uniform across the grid and across the GPUs without a host round trip or a collective kernel.
+//
+// Single-reduction (Chronopoulos-Gear) form: the operator is applied to the preconditioned residual z (kept in the
+// peer-visible slot g.p, which other ranks gather from), and the search direction d and s = S d follow by recurrence:
+//   gamma = r.z ; beta = gamma / gamma_old ; w = S z ; delta = z.w ; d = z + beta d ; s = w + beta s
+//   alpha = gamma / (delta - beta gamma / alpha_old) ; x += alpha d ; r -= alpha s ; z = M^-1 r
+// Mathematically the textbook PCG iterates (tests: same iteration counts and step accuracy on the C1-C3 graphs), with
+// THREE grid-wide (and cross-GPU) synchronisations per iteration instead of four, and the direction update folded
+// into the operator pass so that w never travels to memory:
+//   phase A  t = W Hlp^T z (landmark rows)                     | barrier: every rank's t is complete
+//   phase B  w = (Hpp + lambda) z - Hpl t, z.w, d and s rows   | barrier + all-reduce of delta
+//   phase C  x += alpha d, r -= alpha s, z = M^-1 r, r.z       | barrier + all-reduce of gamma: every z is complete
 __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g, DevScalars* sc, double* part,
                                                                      unsigned long long* bar, PcgParams prm) {
   __shared__ double sm[32];
   __shared__ int s_last;
-  // wall time of the four phases of an iteration as seen by CTA 0 (barrier waits included), for profiles/
-  unsigned long long ph_ns[4] = {0, 0, 0, 0}, t_ph = globaltimer_ns();
-#define SGB_PHASE_LAP(i)                     \
-  do {                                       \
-    unsigned long long _t = globaltimer_ns(); \
-    ph_ns[i] += _t - t_ph;                   \
-    t_ph = _t;                               \
+  // wall time of the three phases of an iteration as seen by thread 0 of each CTA (barrier waits included); CTA 0's
+  // copy is reported. Kept in shared memory: it is touched once per phase and must not cost registers.
+  __shared__ unsigned long long ph_ns[4], t_ph;
+  if (threadIdx.x == 0) {
+    ph_ns[0] = ph_ns[1] = ph_ns[2] = ph_ns[3] = 0;
+    t_ph = globaltimer_ns();
+  }
+#define SGB_PHASE_LAP(i)                        \
+  do {                                          \
+    if (threadIdx.x == 0) {                     \
+      unsigned long long _t = globaltimer_ns(); \
+      ph_ns[i] += _t - t_ph;                    \
+      t_ph = _t;                                \
+    }                                           \
   } while (0)
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int nthreads = gridDim.x * blockDim.x;
@@ -365,90 +383,87 @@ __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g
   unsigned long long seq = sc->xseq;
   const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   double* x = g.x_p[g.rank];
-  double* p = g.p[g.rank];
+  double* zin = g.p[g.rank];
 
-  // x = 0, r = bt, z = Minv r, p = z
+  // x = 0, r = bt, z = Minv r, d = s = 0
   double acc = 0.0;
   for (int lp = tid; lp < g.nP; lp += nthreads) {
     double r[3] = {g.bt[3 * (size_t)lp], g.bt[3 * (size_t)lp + 1], g.bt[3 * (size_t)lp + 2]}, z[3];
     acc += precond_row(g, lp, r, z);
     for (int c = 0; c < 3; ++c) {
-      x[3 * (size_t)lp + c] = 0.0;
-      g.r[3 * (size_t)lp + c] = r[c];
-      p[3 * (size_t)lp + c] = z[c];
+      size_t o = 3 * (size_t)lp + c;
+      x[o] = 0.0;
+      g.r[o] = r[c];
+      zin[o] = z[c];
+      g.d[o] = 0.0;
+      g.s[o] = 0.0;
     }
   }
-  double rz = block_sum(acc, sm);
-  grid_xreduce(g, bar, nb, epoch, seq, part, &rz, 1, sm, &s_last);  // also: every rank's p segment is complete
-  const double rz0 = rz;
-  int it = 0, flag = 0;
-  if (!(rz0 > 0.0)) {
-    flag = (rz0 == 0.0) ? 0 : 2;  // zero right-hand side: x = 0 is exact; negative / NaN: M not SPD
+  double gam = block_sum(acc, sm);
+  grid_xreduce(g, bar, nb, epoch, seq, part, &gam, 1, sm, &s_last);  // also: every rank's z segment is complete
+  SGB_PHASE_LAP(3);
+  const double gam0 = gam, target = prm.tol * prm.tol * gam0;
+  double gam_old = 0.0, alpha_old = 0.0;
+  int it = 0, flag = 1;
+  if (!(gam0 > 0.0)) {
+    flag = (gam0 == 0.0) ? 0 : 2;  // zero right-hand side: x = 0 is exact; negative / NaN: M not SPD
   } else {
-    const double target = prm.tol * prm.tol * rz0;
-    flag = 1;
-    t_ph = globaltimer_ns();
-    while (it < prm.maxit) {
+    while (true) {
+      if (!(gam == gam)) {
+        flag = 2;
+        break;
+      }
+      if (gam <= target) {
+        flag = 0;
+        break;
+      }
+      if (it >= prm.maxit) break;  // flag 1
+      const double beta = it == 0 ? 0.0 : gam / gam_old;
       if (g.capL > 0) {
         for (int sl = tid >> 5; sl < g.Hlp.nslices; sl += nthreads >> 5) lm_slice_pass(g, sl, 0);
         grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, &s_last);  // every rank's t segment is complete
       }
       SGB_PHASE_LAP(0);
       acc = 0.0;
-      for (int lp = tid; lp < g.nP; lp += nthreads) acc += schur_phaseB_row(g, lp, lambda);
-      double pq = block_sum(acc, sm);
-      grid_xreduce(g, bar, nb, epoch, seq, part, &pq, 1, sm, &s_last);
+      for (int lp = tid; lp < g.nP; lp += nthreads) acc += schur_phaseB_row(g, lp, lambda, beta);
+      double del = block_sum(acc, sm);
+      grid_xreduce(g, bar, nb, epoch, seq, part, &del, 1, sm, &s_last);
       SGB_PHASE_LAP(1);
-      if (!(pq > 0.0)) {  // S not positive definite (or NaN): g2o's "Cholesky failure" analogue
+      const double denom = it == 0 ? del : del - beta * gam / alpha_old;  // = d.S d
+      if (!(denom > 0.0)) {  // S not positive definite (or NaN): g2o's "Cholesky failure" analogue
         flag = 2;
         break;
       }
-      double alpha = rz / pq;
+      const double alpha = gam / denom;
       acc = 0.0;
       for (int lp = tid; lp < g.nP; lp += nthreads) {
         double r[3], z[3];
         for (int c = 0; c < 3; ++c) {
           size_t o = 3 * (size_t)lp + c;
-          x[o] += alpha * p[o];
-          r[c] = g.r[o] - alpha * g.q[o];
+          x[o] += alpha * g.d[o];
+          r[c] = g.r[o] - alpha * g.s[o];
           g.r[o] = r[c];
         }
         acc += precond_row(g, lp, r, z);
-        for (int c = 0; c < 3; ++c) g.z[3 * (size_t)lp + c] = z[c];
+        for (int c = 0; c < 3; ++c) zin[3 * (size_t)lp + c] = z[c];
       }
-      double rzn = block_sum(acc, sm);
-      grid_xreduce(g, bar, nb, epoch, seq, part, &rzn, 1, sm, &s_last);
-      SGB_PHASE_LAP(2);
       ++it;
-      if (!(rzn == rzn)) {
-        flag = 2;
-        break;
-      }
-      if (rzn <= target) {
-        rz = rzn;
-        flag = 0;
-        break;
-      }
-      double beta = rzn / rz;
-      rz = rzn;
-      for (int lp = tid; lp < g.nP; lp += nthreads)
-        for (int c = 0; c < 3; ++c) {
-          size_t o = 3 * (size_t)lp + c;
-          p[o] = g.z[o] + beta * p[o];
-        }
-      grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, &s_last);  // every rank's p segment is complete
-      SGB_PHASE_LAP(3);
+      gam_old = gam;
+      alpha_old = alpha;
+      gam = block_sum(acc, sm);
+      grid_xreduce(g, bar, nb, epoch, seq, part, &gam, 1, sm, &s_last);  // also: every rank's z segment is complete
+      SGB_PHASE_LAP(2);
     }
   }
 #undef SGB_PHASE_LAP
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) sc->pcg_phase_ns[i] += ph_ns[i];
     sc->xseq = seq;
-    sc->rz0 = rz0;
-    sc->rz = rz;
+    sc->rz0 = gam0;
+    sc->rz = gam;
     sc->pcg_iters = it;
     sc->pcg_flag = flag;
-    sc->pcg_rel = rz0 > 0.0 ? sqrt(fabs(rz) / rz0) : 0.0;
+    sc->pcg_rel = gam0 > 0.0 ? sqrt(fabs(gam) / gam0) : 0.0;
   }
 }
 

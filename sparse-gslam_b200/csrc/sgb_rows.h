@@ -485,8 +485,10 @@ inline void lm_slice_pass(const DevGraph& g, int slice, int mode) {
   }
 }
 #endif
-// phase B (pose-major): q_i = lambda v_i + sum_j Hpp_ij v_j - sum_l Hpl_il t_l ; returns v_i . q_i  (v = p)
-SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda) {
+// phase B (pose-major): w_i = lambda z_i + sum_j Hpp_ij z_j - sum_l Hpl_il t_l, followed by the two direction
+// recurrences of the single-reduction PCG for this row, d_i = z_i + beta d_i and s_i = w_i + beta s_i (so that w
+// itself never travels to memory); returns z_i . w_i. z = the peer-visible operator input g.p.
+SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double beta) {
   const int slice = lp >> 5, lane = lp & 31;
   const double* vown = g.p[g.rank] + 3 * (size_t)lp;
   const int wpp = sell_width(g.Hpp, slice), bpp = g.Hpp.sbase[slice] + lane;
@@ -551,9 +553,16 @@ SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda) {
     l0 = n0;
     l1 = n1;
   }
-  g.q[3 * (size_t)lp] = q0;
-  g.q[3 * (size_t)lp + 1] = q1;
-  g.q[3 * (size_t)lp + 2] = q2;
+  double* d = g.d + 3 * (size_t)lp;
+  double* sv = g.s + 3 * (size_t)lp;
+  const double d0 = vi0 + beta * d[0], d1 = vi1 + beta * d[1], d2 = vi2 + beta * d[2];
+  const double s0 = q0 + beta * sv[0], s1 = q1 + beta * sv[1], s2 = q2 + beta * sv[2];
+  d[0] = d0;
+  d[1] = d1;
+  d[2] = d2;
+  sv[0] = s0;
+  sv[1] = s1;
+  sv[2] = s2;
   return vi0 * q0 + vi1 * q1 + vi2 * q2;
 }
 // z_i = Minv_i r_i ; returns r_i . z_i

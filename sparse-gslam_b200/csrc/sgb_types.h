@@ -97,16 +97,16 @@ struct DevGraph {
   double* b_l[kMaxRanks];     // [2*capL] gradient of the owned landmarks
   double* Hll_inv[kMaxRanks]; // [3][capL] (Hll + lambda I)^-1, stride capL
   double* x_p[kMaxRanks];     // [3*capP] pose step
-  double* p[kMaxRanks];       // [3*capP] PCG search direction
+  double* p[kMaxRanks];       // [3*capP] the vector the Schur operator is applied to: the preconditioned residual z
   double* t[kMaxRanks];       // [2*capL] (Hll + lambda I)^-1 Hpl^T p
   Mailbox* mbox[kMaxRanks];
   // ---- local only
   double* x_l;               // [2*nL] landmark step
   double* Minv;              // [9][nP] block-Jacobi preconditioner = inverse of the Schur diagonal block
   double* bt;                // [3*nP] reduced right-hand side
-  double* r;
-  double* z;
-  double* q;
+  double* r;                 // residual
+  double* d;                 // search direction
+  double* s;                 // S d
 };
 
 // scalars of the optimiser kept on the device (LM / GN control, reductions); identical on every rank

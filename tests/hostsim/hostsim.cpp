@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -105,7 +106,7 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
     mk_sell(r, &G.Hpp, P.Hpp, 9); mk_sell(r, &G.Hpl, P.Hpl, 6); mk_sell(r, &G.Hlp, P.Hlp, 6);
     size_t n3 = 3 * (size_t)P.nP, n2 = 2 * (size_t)P.nL;
     G.Hll = r->D(3 * (size_t)P.nL); G.b_p = r->D(n3); G.x_l = r->D(n2);
-    G.Minv = r->D(9 * (size_t)P.nP); G.bt = r->D(n3); G.r = r->D(n3); G.z = r->D(n3); G.q = r->D(n3);
+    G.Minv = r->D(9 * (size_t)P.nP); G.bt = r->D(n3); G.r = r->D(n3); G.d = r->D(n3); G.s = r->D(n3);
     // the "arena": arrays other ranks reach into
     for (int b = 0; b < 2; ++b) {
       G.pose_buf[b][rk] = r->D(np); G.lm_buf[b][rk] = r->D(nl);
@@ -269,60 +270,64 @@ double hs_check_hlp(hs_handle* h) {
   return worst;
 }
 
-// mirrors k_setup_* + k_pcg + k_backsub; returns pcg flag (0 ok, 1 maxit, 2 breakdown), iterations in *iters
+// mirrors k_setup_* + k_pcg (single-reduction PCG, sgb_kernels.cuh) + k_backsub; returns the pcg flag (0 ok, 1 maxit,
+// 2 breakdown), iterations in *iters
 static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
   bool ok = true;
   for (auto& r : h->R) for (int ll = 0; ll < r->G.nL; ++ll) ok &= setup_lm_row(r->G, ll, lambda);
   for (auto& r : h->R) for (int lp = 0; lp < r->G.nP; ++lp) ok &= setup_pose_row(r->G, lp, lambda);
-  double rz = 0;
+  double gam = 0;
   for (auto& rk : h->R) {
     DevGraph& G = rk->G;
-    double* x = G.x_p[G.rank]; double* p = G.p[G.rank];
+    double* x = G.x_p[G.rank]; double* zin = G.p[G.rank];
     for (int lp = 0; lp < G.nP; ++lp) {
       double r[3] = {G.bt[3 * lp], G.bt[3 * lp + 1], G.bt[3 * lp + 2]}, z[3];
-      rz += precond_row(G, lp, r, z);
-      for (int c = 0; c < 3; ++c) { x[3 * lp + c] = 0; G.r[3 * lp + c] = r[c]; p[3 * lp + c] = z[c]; }
+      gam += precond_row(G, lp, r, z);
+      for (int c = 0; c < 3; ++c) { x[3 * lp + c] = 0; G.r[3 * lp + c] = r[c]; zin[3 * lp + c] = z[c]; G.d[3 * lp + c] = 0; G.s[3 * lp + c] = 0; }
     }
   }
-  double rz0 = rz;
+  double gam0 = gam, gam_old = 0, alpha_old = 0;
   int it = 0, flag = 0;
   bool any_lm = h->R[0]->G.capL > 0;
-  if (!(rz0 > 0.0)) {
-    flag = (rz0 == 0.0) ? 0 : 2;
+  if (!(gam0 > 0.0)) {
+    flag = (gam0 == 0.0) ? 0 : 2;
   } else {
-    double target = h->tol * h->tol * rz0;
+    double target = h->tol * h->tol * gam0;
     flag = 1;
-    while (it < h->maxit) {
+    while (true) {
+      if (!(gam == gam)) { flag = 2; break; }
+      if (gam <= target) { flag = 0; break; }
+      if (it >= h->maxit) { flag = 1; break; }
+      double beta = it == 0 ? 0.0 : gam / gam_old;
       if (any_lm) for (auto& rk : h->R) for (int sl = 0; sl < rk->G.Hlp.nslices; ++sl) lm_slice_pass(rk->G, sl, 0);
-      double pq = 0;
-      for (auto& rk : h->R) for (int lp = 0; lp < rk->G.nP; ++lp) pq += schur_phaseB_row(rk->G, lp, lambda);
-      if (!(pq > 0.0)) { flag = 2; break; }
-      double alpha = rz / pq, rzn = 0;
+      double del = 0;
+      for (auto& rk : h->R) for (int lp = 0; lp < rk->G.nP; ++lp) del += schur_phaseB_row(rk->G, lp, lambda, beta);
+      double denom = it == 0 ? del : del - beta * gam / alpha_old;
+      if (!(denom > 0.0)) { flag = 2; break; }
+      double alpha = gam / denom;
+      double gnew = 0;
       for (auto& rk : h->R) {
         DevGraph& G = rk->G;
-        double* x = G.x_p[G.rank]; double* p = G.p[G.rank];
+        double* x = G.x_p[G.rank]; double* zin = G.p[G.rank];
         for (int lp = 0; lp < G.nP; ++lp) {
           double r[3], z[3];
-          for (int c = 0; c < 3; ++c) { size_t o = 3 * (size_t)lp + c; x[o] += alpha * p[o]; r[c] = G.r[o] - alpha * G.q[o]; G.r[o] = r[c]; }
-          rzn += precond_row(G, lp, r, z);
-          for (int c = 0; c < 3; ++c) G.z[3 * (size_t)lp + c] = z[c];
+          for (int c = 0; c < 3; ++c) {
+            size_t o = 3 * (size_t)lp + c;
+            x[o] += alpha * G.d[o];
+            r[c] = G.r[o] - alpha * G.s[o];
+            G.r[o] = r[c];
+          }
+          gnew += precond_row(G, lp, r, z);
+          for (int c = 0; c < 3; ++c) zin[3 * (size_t)lp + c] = z[c];
         }
       }
       ++it;
-      if (!(rzn == rzn)) { flag = 2; break; }
-      if (rzn <= target) { rz = rzn; flag = 0; break; }
-      double beta = rzn / rz;
-      rz = rzn;
-      for (auto& rk : h->R) {
-        DevGraph& G = rk->G;
-        double* p = G.p[G.rank];
-        for (size_t o = 0; o < 3 * (size_t)G.nP; ++o) p[o] = G.z[o] + beta * p[o];
-      }
+      gam_old = gam; alpha_old = alpha; gam = gnew;
     }
   }
   for (auto& rk : h->R) for (int sl = 0; sl < rk->G.Hlp.nslices; ++sl) lm_slice_pass(rk->G, sl, 1);
   if (iters) *iters = it;
-  if (rel) *rel = rz0 > 0 ? std::sqrt(std::fabs(rz) / rz0) : 0.0;
+  if (rel) *rel = gam0 > 0 ? std::sqrt(std::fabs(gam) / gam0) : 0.0;
   if (!ok) flag = 2;
   return flag;
 }
