@@ -103,7 +103,7 @@ int lm_target_steps(size_t blocks) {
     return e ? std::atoi(e) : 0;
   }();
   if (forced > 0) return forced;
-  return blocks >= ((size_t)1 << 20) ? 6 : 2;
+  return blocks >= ((size_t)1 << 20) ? 10 : 2;
 }
 
 }  // namespace

@@ -11,9 +11,12 @@
 
 #if defined(__CUDA_ARCH__)
 #define SGB_LDG(p) __ldg(p)    // read-only for the lifetime of the kernel
+#define SGB_LDS(p) __ldcs(p)   // read-only AND touched once per pass (the Hessian block values streamed by the PCG):
+                               // evict-first, so the stream does not push the gathered vectors out of L1/L2
 #define SGB_LDCG(p) __ldcg(p)  // written by other CTAs (or, through NVLink, other GPUs) while the kernel runs: no L1
 #else
 #define SGB_LDG(p) (*(p))
+#define SGB_LDS(p) (*(p))
 #define SGB_LDCG(p) (*(p))
 #endif
 
@@ -376,39 +379,41 @@ SGB_HD int sell_col_or_pad(const int32_t* col, int e, bool valid) { return valid
 // u_l = sum_i Hpl_il^T v_i for row srow[slice] + lane / G. The G lanes of a row are then summed
 // with lm_group_sum (device: shuffles; host harness: the same butterfly over an array).
 // vtab[o] = pose-vector segment of rank o (p during PCG, x_p during back-substitution)
+#ifndef SGB_LM_UNROLL
+#define SGB_LM_UNROLL 2  // blocks whose loads one lane keeps in flight in the landmark pass
+#endif
 SGB_HD void lm_gather_lane(const DevGraph& g, int slice, int lane, double* const* vtab, double* u0_out, double* u1_out) {
+  constexpr int U = SGB_LM_UNROLL;
   const int steps = (g.Hlp.sbase[slice + 1] - g.Hlp.sbase[slice]) >> 5;
   const int base = g.Hlp.sbase[slice] + lane;
   const int32_t* col = g.Hlp.col;
   double u0 = 0, u1 = 0;
-  int enc0 = sell_col_or_pad(col, base, steps > 0), enc1 = sell_col_or_pad(col, base + 32, steps > 1);
-  for (int j = 0; j < steps; j += 2) {
-    const int e0 = base + j * 32, e1 = e0 + 32;
-    const int n0 = sell_col_or_pad(col, e0 + 64, j + 2 < steps), n1 = sell_col_or_pad(col, e1 + 64, j + 3 < steps);
-    double v[2][3] = {{0, 0, 0}, {0, 0, 0}}, a[2][6] = {{0, 0, 0, 0, 0, 0}, {0, 0, 0, 0, 0, 0}};
-    if (enc0 >= 0) {
-      const double* pv = vtab[enc0 >> kOwnerShift] + 3 * (size_t)(enc0 & kLocalMask);
-      const double* pa = g.Hlp.vals + sell_vaddr(e0, 6, 0);
-      for (int c = 0; c < 3; ++c) v[0][c] = SGB_LDCG(pv + c);
-      for (int c = 0; c < 6; ++c) a[0][c] = SGB_LDG(pa + 32 * c);
+  int enc[U];
+  for (int u = 0; u < U; ++u) enc[u] = sell_col_or_pad(col, base + 32 * u, u < steps);
+  for (int j = 0; j < steps; j += U) {
+    int nxt[U];
+    for (int u = 0; u < U; ++u) nxt[u] = sell_col_or_pad(col, base + (j + U + u) * 32, j + U + u < steps);
+    double v[U][3], a[U][6];
+    for (int u = 0; u < U; ++u) {
+      for (int c = 0; c < 3; ++c) v[u][c] = 0.0;
+      for (int c = 0; c < 6; ++c) a[u][c] = 0.0;
+      if (enc[u] >= 0) {
+        const double* pv = vtab[enc[u] >> kOwnerShift] + 3 * (size_t)(enc[u] & kLocalMask);
+        const double* pa = g.Hlp.vals + sell_vaddr(base + (j + u) * 32, 6, 0);
+        for (int c = 0; c < 3; ++c) v[u][c] = SGB_LDCG(pv + c);
+        for (int c = 0; c < 6; ++c) a[u][c] = SGB_LDS(pa + 32 * c);
+      }
     }
-    if (enc1 >= 0) {
-      const double* pv = vtab[enc1 >> kOwnerShift] + 3 * (size_t)(enc1 & kLocalMask);
-      const double* pa = g.Hlp.vals + sell_vaddr(e1, 6, 0);
-      for (int c = 0; c < 3; ++c) v[1][c] = SGB_LDCG(pv + c);
-      for (int c = 0; c < 6; ++c) a[1][c] = SGB_LDG(pa + 32 * c);
-    }
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       u0 += a[u][0] * v[u][0] + a[u][2] * v[u][1] + a[u][4] * v[u][2];
       u1 += a[u][1] * v[u][0] + a[u][3] * v[u][1] + a[u][5] * v[u][2];
     }
-    enc0 = n0;
-    enc1 = n1;
+    for (int u = 0; u < U; ++u) enc[u] = nxt[u];
   }
   *u0_out = u0;
   *u1_out = u1;
 }
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
 // butterfly over the G = 32 >> shift neighbouring lanes that share a row: every lane of the group ends with the sum
 __device__ __forceinline__ void lm_group_sum(int shift, double& u0, double& u1) {
   for (int off = 1; off < (32 >> shift); off <<= 1) {
@@ -416,7 +421,8 @@ __device__ __forceinline__ void lm_group_sum(int shift, double& u0, double& u1) 
     u1 += __shfl_xor_sync(0xffffffffu, u1, off);
   }
 }
-#else
+#endif
+#if !defined(__CUDA_ARCH__)
 inline void lm_group_sum_host(int shift, double u0[32], double u1[32]) {
   for (int off = 1; off < (32 >> shift); off <<= 1) {
     double a[32], b[32];
@@ -509,13 +515,13 @@ SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double 
       const double* pv = g.p[enc0 >> kOwnerShift] + 3 * (size_t)(enc0 & kLocalMask);
       const double* pa = g.Hpp.vals + sell_vaddr(e0, 9, 0);
       for (int c = 0; c < 3; ++c) v[0][c] = SGB_LDCG(pv + c);
-      for (int c = 0; c < 9; ++c) a[0][c] = SGB_LDG(pa + 32 * c);
+      for (int c = 0; c < 9; ++c) a[0][c] = SGB_LDS(pa + 32 * c);
     }
     if (enc1 >= 0) {
       const double* pv = g.p[enc1 >> kOwnerShift] + 3 * (size_t)(enc1 & kLocalMask);
       const double* pa = g.Hpp.vals + sell_vaddr(e1, 9, 0);
       for (int c = 0; c < 3; ++c) v[1][c] = SGB_LDCG(pv + c);
-      for (int c = 0; c < 9; ++c) a[1][c] = SGB_LDG(pa + 32 * c);
+      for (int c = 0; c < 9; ++c) a[1][c] = SGB_LDS(pa + 32 * c);
     }
     for (int u = 0; u < 2; ++u) {
       q0 += a[u][0] * v[u][0] + a[u][1] * v[u][1] + a[u][2] * v[u][2];
@@ -535,7 +541,7 @@ SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double 
       Pair64 tt = ldcg_pair(pt);
       tv[0][0] = tt.a;
       tv[0][1] = tt.b;
-      for (int c = 0; c < 6; ++c) a[0][c] = SGB_LDG(pa + 32 * c);
+      for (int c = 0; c < 6; ++c) a[0][c] = SGB_LDS(pa + 32 * c);
     }
     if (l1 >= 0) {
       const double* pt = g.t[l1 >> kOwnerShift] + 2 * (size_t)(l1 & kLocalMask);
@@ -543,7 +549,7 @@ SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double 
       Pair64 tt = ldcg_pair(pt);
       tv[1][0] = tt.a;
       tv[1][1] = tt.b;
-      for (int c = 0; c < 6; ++c) a[1][c] = SGB_LDG(pa + 32 * c);
+      for (int c = 0; c < 6; ++c) a[1][c] = SGB_LDS(pa + 32 * c);
     }
     for (int u = 0; u < 2; ++u) {
       q0 -= a[u][0] * tv[u][0] + a[u][1] * tv[u][1];
