@@ -47,6 +47,16 @@ struct sgb_handle {
   // (cudaFree/cudaMalloc of ~60 arrays cost up to 0.5 s on a 1M-pose graph).
   struct Slab { char* base; size_t cap, off; };
   std::vector<Slab> slabs;
+  // pinned staging ring for host -> device uploads of pageable caller / planner memory (a pageable cudaMemcpy
+  // runs at a fraction of the PCIe rate); the host copies chunk k+1 while the DMA engine moves chunk k
+  static constexpr int kStages = 4;
+  static constexpr size_t kStageBytes = (size_t)8 << 20;
+  // component-major edge data assembled on the host before its upload; kept between calls so that a re-initialised
+  // graph of similar size does not page-fault ~300 MB of fresh allocations again
+  std::vector<double> e_zinv, e_info, e_phi, e_z, e_linfo;
+  char* stage[kStages] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t stage_ev[kStages] = {nullptr, nullptr, nullptr, nullptr};
+  int stage_cur = 0;
   // peer-mapped arena: estimates (2 buffers), p, x_p, t, b_l, Hll_inv, mailbox -- same offsets on every rank
   char* arena = nullptr;
   size_t arena_bytes = 0;
@@ -115,12 +125,29 @@ sgb_status dalloc(sgb_handle* h, T** out, size_t n) {
   *out = (T*)p;
   return SGB_OK;
 }
+// host (pageable) -> device on the handle's stream, through the pinned staging ring
+sgb_status h2d(sgb_handle* h, void* dst, const void* src, size_t bytes) {
+  if (bytes < ((size_t)256 << 10) || !h->stage[0]) {
+    SGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
+    return SGB_OK;
+  }
+  for (size_t off = 0; off < bytes; off += sgb_handle::kStageBytes) {
+    size_t n = std::min(sgb_handle::kStageBytes, bytes - off);
+    int b = h->stage_cur;
+    h->stage_cur = (b + 1) % sgb_handle::kStages;
+    SGB_CUDA(cudaEventSynchronize(h->stage_ev[b]));  // the previous transfer out of this buffer has finished
+    std::memcpy(h->stage[b], (const char*)src + off, n);
+    SGB_CUDA(cudaMemcpyAsync((char*)dst + off, h->stage[b], n, cudaMemcpyHostToDevice, h->stream));
+    SGB_CUDA(cudaEventRecord(h->stage_ev[b], h->stream));
+  }
+  return SGB_OK;
+}
 template <class T>
 sgb_status upload(sgb_handle* h, const T** out, const std::vector<T>& v) {
   T* d = nullptr;
   sgb_status s = dalloc(h, &d, v.size());
   if (s != SGB_OK) return s;
-  if (!v.empty()) SGB_CUDA(cudaMemcpyAsync(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+  if (!v.empty() && (s = h2d(h, d, v.data(), v.size() * sizeof(T))) != SGB_OK) return s;
   *out = d;
   return SGB_OK;
 }
@@ -429,6 +456,10 @@ sgb_status sgb_create(const sgb_options* opt, sgb_handle** out) {
   if ((e = cudaMalloc((void**)&h->d_part_l, pb)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc((void**)&h->d_part_e, pb)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc((void**)&h->d_bar, sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
+  for (int b = 0; b < sgb_handle::kStages; ++b) {
+    if ((e = cudaMallocHost((void**)&h->stage[b], sgb_handle::kStageBytes)) != cudaSuccess) return fail("cudaMallocHost", e);
+    if ((e = cudaEventCreateWithFlags(&h->stage_ev[b], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
+  }
   *out = h;
   return SGB_OK;
 }
@@ -446,6 +477,10 @@ void sgb_destroy(sgb_handle* h) {
   cudaFree(h->d_part_l);
   cudaFree(h->d_part_e);
   cudaFree(h->d_bar);
+  for (int b = 0; b < sgb_handle::kStages; ++b) {
+    if (h->stage[b]) cudaFreeHost(h->stage[b]);
+    if (h->stage_ev[b]) cudaEventDestroy(h->stage_ev[b]);
+  }
   for (auto& ev : h->ev.e) cudaEventDestroy(ev);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -521,17 +556,25 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   h->connected = (world == 1);
   if ((st = dalloc(h, &h->d_pose0, np)) != SGB_OK) return st;
   if ((st = dalloc(h, &h->d_lm0, nl)) != SGB_OK) return st;
-  for (int bsel = 0; bsel < 2; ++bsel) {
-    if (np) SGB_CUDA(cudaMemcpyAsync(G.pose_buf[bsel][rank], g->pose_est, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (nl) SGB_CUDA(cudaMemcpyAsync(G.lm_buf[bsel][rank], g->lm_est, nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (np) {
+    if ((st = h2d(h, h->d_pose0, g->pose_est, np * sizeof(double))) != SGB_OK) return st;
+    for (int bsel = 0; bsel < 2; ++bsel)
+      SGB_CUDA(cudaMemcpyAsync(G.pose_buf[bsel][rank], h->d_pose0, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   }
-  if (np) SGB_CUDA(cudaMemcpyAsync(h->d_pose0, g->pose_est, np * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-  if (nl) SGB_CUDA(cudaMemcpyAsync(h->d_lm0, g->lm_est, nl * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  if (nl) {
+    if ((st = h2d(h, h->d_lm0, g->lm_est, nl * sizeof(double))) != SGB_OK) return st;
+    for (int bsel = 0; bsel < 2; ++bsel)
+      SGB_CUDA(cudaMemcpyAsync(G.lm_buf[bsel][rank], h->d_lm0, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  }
   lap("arena+estimates");
   // edge data, component-major, local edges; EdgeSE2::setMeasurement caches the inverse. The SoA transposes run on
   // host threads while this thread uploads the symbolic maps.
-  std::vector<double> zinv(3 * (size_t)P.n_pp), info(6 * (size_t)P.n_pp), phi(P.n_pp, 0.0);
-  std::vector<double> z(2 * (size_t)P.n_pl), linfo(3 * (size_t)P.n_pl);
+  std::vector<double>&zinv = h->e_zinv, &info = h->e_info, &phi = h->e_phi, &z = h->e_z, &linfo = h->e_linfo;
+  zinv.resize(3 * (size_t)P.n_pp);
+  info.resize(6 * (size_t)P.n_pp);
+  phi.resize(P.n_pp);
+  z.resize(2 * (size_t)P.n_pl);
+  linfo.resize(3 * (size_t)P.n_pl);
   auto fill_pp = [&](int k0, int k1) {
     for (int k = k0; k < k1; ++k) {
       int s = S.pp_src[P.pp_g[k]];
@@ -542,7 +585,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
       zinv[(size_t)P.n_pp + k] = sn * (-x) + c * (-y);
       zinv[2 * (size_t)P.n_pp + k] = thi;
       for (int c6 = 0; c6 < 6; ++c6) info[(size_t)c6 * P.n_pp + k] = g->pp_info[6 * (size_t)s + c6];
-      if (g->pp_phi) phi[k] = g->pp_phi[s];
+      phi[k] = g->pp_phi ? g->pp_phi[s] : 0.0;
     }
   };
   auto fill_pl = [&](int k0, int k1) {
@@ -675,7 +718,7 @@ sgb_status sgb_get_structure_info(const sgb_handle* h, sgb_structure_info* o) {
   o->n_free = S.Pf + S.Lf;
   o->n_free_poses = S.Pf;
   o->n_free_landmarks = S.Lf;
-  o->n_blocks = (int32_t)S.blk_row.size();
+  o->n_blocks = (int32_t)S.n_blocks;
   o->scalar_dim = S.dim;
   o->n_active_pp = S.n_pp;
   o->n_active_pl = S.n_pl;
@@ -688,6 +731,7 @@ sgb_status sgb_get_structure(const sgb_handle* h, int32_t* kind, int32_t* index,
                              int32_t* bc, int32_t* bnr, int32_t* bnc, int32_t* ph, int32_t* lh) {
   if (!h) return SGB_ERR_INVALID;
   if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
+  build_block_list(const_cast<sgb_handle*>(h)->S);  // built on first use; the handle is not shared between threads
   const Structure& S = h->S;
   auto cp = [](int32_t* dst, const std::vector<int32_t>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(int32_t)); };
   cp(kind, S.ord_kind); cp(index, S.ord_index); cp(offset, S.ord_offset);
@@ -728,6 +772,7 @@ sgb_status sgb_linearize(sgb_handle* h, double* b, double* Hblocks, double* chi2
   if (chi2) { chi2[0] = h->h_sc->chi2; chi2[1] = h->h_sc->chi2_robust; }
   if (b && (st = gather_owned_vector(h, G.b_p, G.b_l[P.rank], b)) != SGB_OK) return st;
   if (Hblocks) {
+    build_export(h->S, h->LP);
     std::vector<double> hpp((size_t)P.Hpp.entries() * 9), hpl((size_t)P.Hpl.entries() * 6), hll(3 * (size_t)P.nL);
     if (!hpp.empty()) SGB_CUDA(cudaMemcpy(hpp.data(), G.Hpp.vals, hpp.size() * sizeof(double), cudaMemcpyDeviceToHost));
     if (!hpl.empty()) SGB_CUDA(cudaMemcpy(hpl.data(), G.Hpl.vals, hpl.size() * sizeof(double), cudaMemcpyDeviceToHost));

@@ -106,6 +106,69 @@ int lm_target_steps(size_t blocks) {
   return blocks >= ((size_t)1 << 20) ? 10 : 2;
 }
 
+// world == 1: the local plan IS the global structure -- same rows, same edge order, same pose-major SELL layout;
+// only the landmark numbering (row order of the landmark-major matrix) differs from the Hessian order. Plain copies
+// on four host threads instead of the general owner/halo classification.
+sgb_status partition_single(const Structure& S, LocalPlan& P) {
+  P.n_pp = P.n_pp_owned = S.n_pp;
+  P.n_pl = P.n_pl_owned = S.n_pl;
+  auto pose_side = [&]() {
+    P.pp_g.resize(S.n_pp);
+    std::iota(P.pp_g.begin(), P.pp_g.end(), 0);
+    P.pp_i = S.pp_i; P.pp_j = S.pp_j; P.pp_hi = S.pp_hi; P.pp_hj = S.pp_hj;
+    P.pp_e_ij = S.pp_e_ij; P.pp_e_ji = S.pp_e_ji; P.pp_dup = S.pp_dup;
+    P.Hpp = S.Hpp;  // enc_pose(c) == c for a single owner
+    P.hpp_diag = S.hpp_diag;
+  };
+  auto hpl_side = [&]() {
+    P.Hpl = S.Hpl;
+    for (auto& c : P.Hpl.col)
+      if (c >= 0) c = P.enc_lm[c];
+    P.pinc_ptr = S.pinc_ptr;
+    P.pinc = S.pinc;
+  };
+  auto lm_side = [&]() {
+    FlatRows obs(P.nL);
+    obs.col.reserve(S.lp_col.size());
+    for (int l = 0; l < P.nL; ++l) {
+      int hl = P.lm_global[l];
+      obs.col.insert(obs.col.end(), S.lp_col.begin() + S.lp_ptr[hl], S.lp_col.begin() + S.lp_ptr[hl + 1]);
+      obs.close_row();
+    }
+    build_grouped_sell(obs, lm_target_steps(obs.col.size()), P.Hlp);
+    P.linc_ptr.assign(P.nL + 1, 0);
+    P.linc.reserve(S.linc.size());
+    for (int l = 0; l < P.nL; ++l) {
+      int hl = P.lm_global[l];
+      P.linc.insert(P.linc.end(), S.linc.begin() + S.linc_ptr[hl], S.linc.begin() + S.linc_ptr[hl + 1]);
+      P.linc_ptr[l + 1] = (int)P.linc.size();
+    }
+    // needs Hlp: the landmark-major entry of every leading pose-line edge
+    P.pl_e_lp.assign(S.n_pl, -1);
+    for (int k = 0; k < S.n_pl; ++k)
+      if (S.pl_e_pl[k] >= 0) P.pl_e_lp[k] = P.Hlp.entry(P.enc_lm[S.pl_hl[k]] & kLocalMask, S.pl_k_lp[k]);
+  };
+  auto pl_side = [&]() {
+    P.pl_g.resize(S.n_pl);
+    std::iota(P.pl_g.begin(), P.pl_g.end(), 0);
+    P.pl_p = S.pl_p; P.pl_l = S.pl_l; P.pl_hp = S.pl_hp; P.pl_hl = S.pl_hl;
+    P.pl_e_pl = S.pl_e_pl; P.pl_dup = S.pl_dup;
+  };
+  if ((size_t)S.n_pp + S.n_pl > 200000) {
+    std::thread t1(pose_side), t2(hpl_side), t3(pl_side);
+    lm_side();
+    t1.join();
+    t2.join();
+    t3.join();
+  } else {
+    pose_side();
+    hpl_side();
+    pl_side();
+    lm_side();
+  }
+  return SGB_OK;
+}
+
 }  // namespace
 
 sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std::string& err) {
@@ -160,6 +223,8 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
   for (int l = 0; l < P.nP; ++l) P.pose_of_l[l] = S.pose_of_h[P.p_begin + l];
   P.lm_of_l.resize(P.nL);
   for (int l = 0; l < P.nL; ++l) P.lm_of_l[l] = S.lm_of_h[P.lm_global[l]];
+
+  if (world == 1) return partition_single(S, P);
 
   auto pose_local = [&](int hp) { return hp >= 0 && owner_p(hp) == rank; };
   auto lm_local = [&](int hl) { return hl >= 0 && lm_owner[hl] == rank; };
@@ -307,40 +372,43 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
   }
 
   };
-  // ---- reference-order export map
-  auto build_export = [&]() {
+  if (threaded) {
+    std::thread t1(build_pp_edges), t2(build_incidence);
+    build_pl_edges();
+    t1.join();
+    t2.join();
+  } else {
+    build_pp_edges();
+    build_pl_edges();
+    build_incidence();
+  }
+  return SGB_OK;
+}
+
+// where every block of the reference-order list lives: owner rank and, on the owner, the local entry
+void build_export(Structure& S, LocalPlan& P) {
+  if (P.export_built) return;
+  build_block_list(S);
+  auto owner_p = [&](int hp) { return hp / P.chunkP; };
   P.blk_owner.resize(S.blk_row.size());
   P.blk_entry.assign(S.blk_row.size(), -1);
   for (size_t b = 0; b < S.blk_row.size(); ++b) {
     int kind = S.blk_kind[b];
     if (kind == 2) {
-      int hl = S.blk_entry[b];
-      P.blk_owner[b] = lm_owner[hl];
-      if (lm_owner[hl] == rank) P.blk_entry[b] = P.enc_lm[hl] & kLocalMask;
+      int hl = S.blk_entry[b], o = P.enc_lm[hl] >> kOwnerShift;
+      P.blk_owner[b] = o;
+      if (o == P.rank) P.blk_entry[b] = P.enc_lm[hl] & kLocalMask;
     } else {
       int hp = S.blk_row[b];  // block (row r, col c) is stored in pose row r
       P.blk_owner[b] = owner_p(hp);
-      if (owner_p(hp) == rank) {
+      if (owner_p(hp) == P.rank) {
         const HostSell& G = kind == 0 ? S.Hpp : S.Hpl;
         const HostSell& Lc = kind == 0 ? P.Hpp : P.Hpl;
         P.blk_entry[b] = entry_of(Lc, hp - P.p_begin, entry_k(G, hp, S.blk_entry[b]));
       }
     }
   }
-  };
-  if (threaded) {
-    std::thread t1(build_pp_edges), t2(build_incidence), t3(build_export);
-    build_pl_edges();
-    t1.join();
-    t2.join();
-    t3.join();
-  } else {
-    build_pp_edges();
-    build_pl_edges();
-    build_incidence();
-    build_export();
-  }
-  return SGB_OK;
+  P.export_built = true;
 }
 
 }  // namespace sgb

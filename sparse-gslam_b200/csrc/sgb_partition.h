@@ -28,6 +28,7 @@ struct LocalPlan {
   std::vector<int32_t> hpp_diag;
   // reference-order export: for every block of Structure::blk_* the owner rank and the local entry
   std::vector<int32_t> blk_owner, blk_entry;
+  bool export_built = false;  // filled on demand by build_export()
   // halo statistics (distinct remote entries this rank gathers per PCG iteration)
   int64_t halo_p = 0, halo_t = 0;
 };
@@ -35,5 +36,7 @@ struct LocalPlan {
 inline int enc_pose(int hp, int chunkP) { return ((hp / chunkP) << 26) | (hp % chunkP); }
 
 sgb_status partition(const Structure& S, int world, int rank, LocalPlan& out, std::string& err);
+// fills Structure::blk_* and LocalPlan::blk_owner / blk_entry (idempotent); only the parity hooks need it
+void build_export(Structure& S, LocalPlan& P);
 
 }  // namespace sgb

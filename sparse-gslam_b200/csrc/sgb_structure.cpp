@@ -7,6 +7,9 @@
 #include "sgb_structure.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <thread>
 
@@ -97,7 +100,16 @@ void order_by_seq(std::vector<int32_t>& idx, const int64_t* seq) {
 }  // namespace
 
 sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& err) {
+  static const bool prof = std::getenv("SGB_PROFILE") != nullptr;
+  auto tp0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char* what) {
+    if (!prof) return;
+    auto t = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[build_structure] %-14s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(t - tp0).count());
+    tp0 = t;
+  };
   S = Structure();
+  lap("reset");
   const int P = g.n_poses, L = g.n_landmarks;
   if (P < 0 || L < 0 || g.n_pp < 0 || g.n_pl < 0) { err = "negative size"; return SGB_ERR_INVALID; }
   if ((P > 0 && !g.pose_est) || (L > 0 && !g.lm_est)) { err = "missing estimates"; return SGB_ERR_INVALID; }
@@ -136,6 +148,7 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     pact[p] = 1;
     lact[l] = 1;
   }
+  lap("active scan");
   order_by_seq(S.pp_src, g.pp_seq);
   order_by_seq(S.pl_src, g.pl_seq);
   S.n_pp = (int)S.pp_src.size();
@@ -144,6 +157,7 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   auto seq_pp = [&](int k) { return g.pp_seq ? g.pp_seq[S.pp_src[k]] : (int64_t)S.pp_src[k]; };
   auto seq_pl = [&](int k) { return g.pl_seq ? g.pl_seq[S.pl_src[k]] : (int64_t)g.n_pp + S.pl_src[k]; };
 
+  lap("edge order");
   // ---- index mapping: active vertices sorted by id; fixed -> -1; nothing is marginalised
   std::vector<int32_t>& porder = S.pose_of_h;
   std::vector<int32_t>& lorder = S.lm_of_h;
@@ -172,6 +186,7 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   for (int h = 0; h < S.Pf; ++h) { S.ord_kind[h] = 0; S.ord_index[h] = porder[h]; S.ord_offset[h] = 3 * h; }
   for (int h = 0; h < S.Lf; ++h) { S.ord_kind[S.Pf + h] = 1; S.ord_index[S.Pf + h] = lorder[h]; S.ord_offset[S.Pf + h] = 3 * S.Pf + 2 * h; }
 
+  lap("index mapping");
   // ---- per-type active edge arrays (insertion order)
   S.pp_i.resize(S.n_pp); S.pp_j.resize(S.n_pp); S.pp_hi.resize(S.n_pp); S.pp_hj.resize(S.n_pp);
   S.pp_e_ij.assign(S.n_pp, -1); S.pp_e_ji.assign(S.n_pp, -1); S.pp_dup.assign(S.n_pp, -1);
@@ -188,6 +203,7 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     S.pl_hp[k] = S.pose_h[g.pl_pose[s]]; S.pl_hl[k] = S.lm_h[g.pl_lm[s]];
   }
 
+  lap("edge arrays");
   // ---- incidence lists in global insertion order (two-way merge of the two edge types)
   auto build_incidence = [&]() {
     S.pinc_ptr.assign(S.Pf + 1, 0);
@@ -222,7 +238,6 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
 
   // ---- pose-pose pairs: leader = first edge (insertion order) of an unordered free pair, others chained.
   // Row r of Hpp = [cols < r ascending | r | cols > r ascending]; positions are known when they are filled.
-  std::vector<int32_t> bp_row, bp_col, bp_entry;  // reference block list, pose columns
   auto build_pp = [&]() {
     Grouped G;
     group_pairs(S.n_pp, S.Pf, [&](int k) { int a = S.pp_hi[k], b = S.pp_hj[k]; return (a < 0 || b < 0) ? -1 : std::min(a, b); },
@@ -269,22 +284,9 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
       S.pp_e_ij[k] = fwd ? e_up : e_low;
       S.pp_e_ji[k] = fwd ? e_low : e_up;
     }
-    // reference block list, pose columns: column c holds rows r <= c ascending; block (r, c) lives in SELL row r
-    bp_row.resize((size_t)np + S.Pf); bp_col.resize(bp_row.size()); bp_entry.resize(bp_row.size());
-    size_t o = 0;
-    for (int c = 0; c < S.Pf; ++c) {
-      for (int q = lstart[c]; q < lstart[c + 1]; ++q) {
-        int t = low_pair[q];
-        bp_row[o] = pa[t]; bp_col[o] = c; bp_entry[o] = sell_entry(S.Hpp, pa[t], up_idx[t]);
-        ++o;
-      }
-      bp_row[o] = c; bp_col[o] = c; bp_entry[o] = S.hpp_diag[c];
-      ++o;
-    }
   };
 
   // ---- pose-line pairs
-  std::vector<int32_t> bl_row, bl_col, bl_nr, bl_kind, bl_entry;  // reference block list, landmark columns
   auto build_pl = [&]() {
     Grouped G;
     group_pairs(S.n_pl, S.Pf, [&](int k) { return S.pl_hp[k]; }, [&](int k) { return S.pl_hl[k]; }, G);
@@ -323,19 +325,6 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
       S.pl_e_pl[k] = sell_entry(S.Hpl, pa[t], idx_pl[t]);
       S.pl_k_lp[k] = idx_lp[t];
     }
-    // reference block list, landmark columns: pose rows ascending, then the diagonal
-    size_t nb = (size_t)np + S.Lf, o = 0;
-    bl_row.resize(nb); bl_col.resize(nb); bl_nr.resize(nb); bl_kind.resize(nb); bl_entry.resize(nb);
-    for (int hl = 0; hl < S.Lf; ++hl) {
-      int c = S.Pf + hl;
-      for (int q = rows_lp.ptr[hl]; q < rows_lp.ptr[hl + 1]; ++q) {
-        int t = lp_pair[q];
-        bl_row[o] = pa[t]; bl_col[o] = c; bl_nr[o] = 3; bl_kind[o] = 1; bl_entry[o] = sell_entry(S.Hpl, pa[t], idx_pl[t]);
-        ++o;
-      }
-      bl_row[o] = c; bl_col[o] = c; bl_nr[o] = 2; bl_kind[o] = 2; bl_entry[o] = hl;
-      ++o;
-    }
     S.lp_ptr.swap(rows_lp.ptr);
     S.lp_col.swap(rows_lp.col);
   };
@@ -351,25 +340,48 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     build_pl();
   }
 
-  // ---- concatenated reference block list: pose columns, then landmark columns
-  size_t n0 = bp_row.size(), n1 = bl_row.size();
-  S.blk_row.resize(n0 + n1); S.blk_col.resize(n0 + n1); S.blk_nr.resize(n0 + n1); S.blk_nc.resize(n0 + n1);
-  S.blk_kind.resize(n0 + n1); S.blk_entry.resize(n0 + n1);
-  std::copy(bp_row.begin(), bp_row.end(), S.blk_row.begin());
-  std::copy(bp_col.begin(), bp_col.end(), S.blk_col.begin());
-  std::copy(bp_entry.begin(), bp_entry.end(), S.blk_entry.begin());
-  std::fill(S.blk_nr.begin(), S.blk_nr.begin() + n0, 3);
-  std::fill(S.blk_nc.begin(), S.blk_nc.begin() + n0, 3);
-  std::fill(S.blk_kind.begin(), S.blk_kind.begin() + n0, 0);
-  std::copy(bl_row.begin(), bl_row.end(), S.blk_row.begin() + n0);
-  std::copy(bl_col.begin(), bl_col.end(), S.blk_col.begin() + n0);
-  std::copy(bl_nr.begin(), bl_nr.end(), S.blk_nr.begin() + n0);
-  std::fill(S.blk_nc.begin() + n0, S.blk_nc.end(), 2);
-  std::copy(bl_kind.begin(), bl_kind.end(), S.blk_kind.begin() + n0);
-  std::copy(bl_entry.begin(), bl_entry.end(), S.blk_entry.begin() + n0);
-  S.block_values = 9 * (int64_t)n0;
-  for (size_t k = 0; k < n1; ++k) S.block_values += (int64_t)bl_nr[k] * 2;
+  lap("inc+pp+pl");
+  // the reference-order block list itself (sgb_get_structure, the parity hooks) is built on demand: build_block_list
+  S.n_blocks = (int64_t)S.Pf + S.n_pairs_pp + S.n_pairs_pl + S.Lf;
+  S.block_values = 9 * ((int64_t)S.Pf + S.n_pairs_pp) + 6 * S.n_pairs_pl + 4 * (int64_t)S.Lf;
+  lap("block list");
   return SGB_OK;
+}
+
+// g2o's SparseBlockMatrix iteration order: block columns ascending, inside a column the rows
+// ascending, upper triangle only; pose columns first, then the landmark columns (pose rows, then the diagonal).
+void build_block_list(Structure& S) {
+  if (S.blocks_built) return;
+  const size_t nb = (size_t)S.n_blocks;
+  S.blk_row.resize(nb); S.blk_col.resize(nb); S.blk_nr.resize(nb); S.blk_nc.resize(nb);
+  S.blk_kind.resize(nb); S.blk_entry.resize(nb);
+  auto find_in_row = [](const HostSell& M, int row, int col) {
+    for (int k = 0, w = M.width(M.slice_of(row)); k < w; ++k) {
+      int e = M.entry(row, k);
+      if (M.col[e] == col) return e;
+    }
+    return -1;
+  };
+  size_t o = 0;
+  auto put = [&](int r, int c, int nr, int nc, int kind, int entry) {
+    S.blk_row[o] = r; S.blk_col[o] = c; S.blk_nr[o] = nr; S.blk_nc[o] = nc; S.blk_kind[o] = kind; S.blk_entry[o] = entry;
+    ++o;
+  };
+  for (int c = 0; c < S.Pf; ++c) {
+    // the pattern is symmetric: the rows of column c are the columns of row c (stored ascending)
+    for (int k = 0, w = S.Hpp.width(S.Hpp.slice_of(c)); k < w; ++k) {
+      int r = S.Hpp.col[S.Hpp.entry(c, k)];
+      if (r < 0 || r >= c) break;
+      put(r, c, 3, 3, 0, find_in_row(S.Hpp, r, c));  // the values of block (r, c) live in SELL row r
+    }
+    put(c, c, 3, 3, 0, S.hpp_diag[c]);
+  }
+  for (int hl = 0; hl < S.Lf; ++hl) {
+    int c = S.Pf + hl;
+    for (int q = S.lp_ptr[hl]; q < S.lp_ptr[hl + 1]; ++q) put(S.lp_col[q], c, 3, 2, 1, find_in_row(S.Hpl, S.lp_col[q], hl));
+    put(c, c, 2, 2, 2, hl);
+  }
+  S.blocks_built = true;
 }
 
 }  // namespace sgb

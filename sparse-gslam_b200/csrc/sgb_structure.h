@@ -67,12 +67,15 @@ struct Structure {
   std::vector<int32_t> blk_row, blk_col, blk_nr, blk_nc; // column-major, rows ascending
   // where each reference block lives on the device: kind 0 = Hpp entry, 1 = Hpl entry, 2 = Hll (index = hl)
   std::vector<int32_t> blk_kind, blk_entry;
-  int64_t block_values = 0;
+  int64_t n_blocks = 0, block_values = 0;
+  bool blocks_built = false;  // blk_* are filled on demand by build_block_list()
   // algorithmic sizes for the roofline
   int64_t n_pairs_pp = 0, n_pairs_pl = 0;   // distinct off-diagonal blocks
 };
 
 // Returns SGB_OK or an error code with a message. seq arrays may be NULL.
 sgb_status build_structure(const sgb_graph_soa& g, Structure& out, std::string& err);
+// fills Structure::blk_* (idempotent); only the structure / parity hooks of the C ABI need it
+void build_block_list(Structure& S);
 
 }  // namespace sgb

@@ -61,6 +61,7 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
   sgb_status st = build_structure(*g, h->S, h->err);
   if (status) *status = st;
   if (st != SGB_OK) return h;
+  build_block_list(h->S);
   const Structure& S = h->S;
   h->tol = tol > 0 ? tol : 1e-10;
   h->maxit = maxit > 0 ? maxit : std::max(100, 12 * S.Pf);
@@ -70,6 +71,7 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
     Rank* r = h->R.back().get();
     st = partition(S, h->world, rk, r->P, h->err);
     if (st != SGB_OK) { if (status) *status = st; return h; }
+    build_export(h->S, r->P);
     const LocalPlan& P = r->P;
     DevGraph& G = r->G;
     std::memset(&G, 0, sizeof G);
