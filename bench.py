@@ -147,6 +147,8 @@ def cpu_reference_run(workload, steps, warmup, quiet=False):
                   "sparse LDLt; iterations/s scaled by P_sample/P_full = 1/100 (linear extrapolation, optimistic for a "
                   "direct solver)")
         algo, iters = ALGO_LM, LM_ITERS
+    elif workload == "c4":
+        return cpu_reference_c4(steps, warmup)
     else:
         g, a, iters, _ = make_workload(workload)
         full_P = g.P
@@ -169,6 +171,138 @@ def cpu_reference_run(workload, steps, warmup, quiet=False):
     value = its / total * scale if total > 0 else 0.0
     return dict(value=value, unit="LM iterations/s", cores=1, kind="port", sample=sample, sample_ms_per_step=1e3 * total / max(1, len(times)),
                 sample_steps=len(times), host_cores=os.cpu_count())
+
+
+C4_GRAPHS_PER_GPU = 128  # BASELINE config 4: 1 024 independent windows over 8 GPUs
+
+
+def lm_bytes_per_iteration(g, st_info, pcg_iters, trials):
+    """Algorithmic bytes of LM iterations: B_lin + per trial (n_pcg * B_pcg + B_chi + update)."""
+    P, L = st_info["n_free_poses"], st_info["n_free_landmarks"]
+    e_o, e_l = g.n_pp, g.n_pl
+    b_lin = 80 * e_o + 48 * e_l + 120 * P + 64 * L + 72 * e_o + 48 * e_l
+    b_chi = 80 * e_o + 48 * e_l + 24 * P + 16 * L
+    b_pcg = 76 * (P + 2 * e_o) + 2 * 52 * e_l + 56 * L + 384 * P
+    return b_lin, b_chi + 2 * (24 * P + 16 * L), b_pcg
+
+
+def run_c4(args, rank, world, local_rank, warmup):
+    """BASELINE config 4: batched independent aces-shaped windows, C4_GRAPHS_PER_GPU per GPU, no exchange between
+    ranks (weak scaling). One step = sgb_optimize_batch(LM-15) over this rank's graphs."""
+    import torch
+    import torch.distributed as dist
+    from sparse_gslam_b200 import SparseOptimizerB200, capi
+    from sparse_gslam_b200 import graphgen as gg
+    from sparse_gslam_b200.optimizer import optimize_batch
+    n = C4_GRAPHS_PER_GPU
+    graphs = [gg.make_c4_window(seed=1000 + rank * n + i) for i in range(n)]
+    opts = [SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC, pcg_tolerance=args.pcg_tol, device=local_rank)
+            for _ in range(n)]
+
+    def init_all():
+        for o, g in zip(opts, graphs):
+            assert o.initialize_optimization(g)
+
+    t0 = time.perf_counter()
+    init_all()
+    t_setgraph = time.perf_counter() - t0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        optimize_batch(opts, LM_ITERS, resident=True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    dev_ms, tot_iters, pcg_iters, trials = 0.0, 0, 0, 0
+    for _ in range(args.steps):
+        done, stats = optimize_batch(opts, LM_ITERS, resident=True)
+        tot_iters += sum(max(d, 0) for d in done)
+        dev_ms += opts[0].timings()["total_ms"]
+        pcg_iters += sum(o.timings()["pcg_iters"] for o in opts)
+    barrier()
+    clocks = sampler.stop()
+    e2e = None
+    if not args.no_e2e:
+        h2d = sum(graph_h2d_bytes(g) for g in graphs)
+        d2h = sum(int(g.pose_est.nbytes + g.lm_est.nbytes) for g in graphs)
+        e_steps, e_iters = max(1, min(args.steps, 3)), 0
+        barrier()
+        te0 = time.perf_counter()
+        for _ in range(e_steps):
+            init_all()
+            done, _ = optimize_batch(opts, LM_ITERS)
+            for o in opts:
+                o.estimates()
+            e_iters += sum(max(d, 0) for d in done)
+        barrier()
+        te = time.perf_counter() - te0
+        e2e = [e_iters, te, h2d, d2h, e_steps]
+    if world > 1:
+        tt = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ss = torch.tensor([float(tot_iters), float(e2e[0]) if e2e else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(ss, op=dist.ReduceOp.SUM)
+        dev_ms_max, all_iters = float(tt[0]), float(ss[0])
+        if e2e:
+            te_t = torch.tensor([e2e[1]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(te_t, op=dist.ReduceOp.MAX)
+            e2e[0], e2e[1] = float(ss[1]), float(te_t[0])
+    else:
+        dev_ms_max, all_iters = dev_ms, float(tot_iters)
+    if rank != 0:
+        return
+    peak, peak_src = measured_peaks()
+    value = all_iters / (dev_ms_max * 1e-3)
+    line = {
+        "metric": "LM iterations/s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": args.steps,
+        "warmup": warmup, "ms_per_step": dev_ms_max / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"C4 batched aces-shaped windows: {n} independent graphs per GPU x {world} GPU(s) "
+                               f"(P=128, L=64, E_o=127, E_l=400 each), LM-15, one thread block per graph",
+                   "algorithm": "LM", "iterations_per_step": LM_ITERS, "jacobian": "analytic",
+                   "pcg_tolerance": args.pcg_tol, "l2": "graphs fit L2 (latency-bound config; see DESIGN.md)",
+                   "parallelism": f"{world} GPU(s), independent graphs, no data-path exchange"},
+        "optimize_ms": dev_ms_max / max(1, args.steps), "lm_iterations": tot_iters, "graphs_per_gpu": n,
+        "set_graph_s": t_setgraph, "gpu_launches": args.steps, "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "k_lm_block", "achieved": None, "peak": peak, "unit": "GB/s", "frac": None,
+                     "traffic": None, "peak_source": peak_src, "pcg_iterations": pcg_iters,
+                     "note": "one CTA per graph, working set L1/L2-resident: latency-bound, not an HBM roofline case"},
+    }
+    if e2e:
+        line["e2e"] = {"value": e2e[0] / e2e[1], "unit": "LM iterations/s", "h2d_bytes_per_step": e2e[2] * world,
+                       "d2h_bytes_per_step": e2e[3] * world, "ms_per_step": 1e3 * e2e[1] / e2e[4], "steps": e2e[4]}
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference_run("c4", 1, 0)
+    print(json.dumps(line))
+
+
+def cpu_reference_c4(steps, warmup, sample=16):
+    """CPU oracle on a sample of the C4 windows, one after the other on one core (the reference is single-threaded)."""
+    from oracle.cpu_oracle import ALGO_LM, JAC_G2O_NUMERIC, Oracle
+    from sparse_gslam_b200 import graphgen as gg
+    graphs = [gg.make_c4_window(seed=1000 + i) for i in range(sample)]
+    total, its, n = 0.0, 0, 0
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        k = 0
+        for g in graphs:
+            o = Oracle(g)
+            o.initialize_optimization()
+            m, _ = o.optimize(LM_ITERS, ALGO_LM, JAC_G2O_NUMERIC)
+            k += max(m, 0)
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            total += dt
+            its += k
+            n += 1
+    return dict(value=its / total if total > 0 else 0.0, unit="LM iterations/s", cores=1, kind="port",
+                sample=f"{sample} of the C4 windows (seeds 1000..), optimize(15) each, g2o-numeric Jacobians + exact sparse "
+                       "LDLt, sequential on one core; iterations/s is per core and independent of the batch size",
+                sample_ms_per_step=1e3 * total / max(1, n), sample_steps=n, host_cores=os.cpu_count())
 
 
 def main():
@@ -209,6 +343,12 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    if args.workload.lower() == "c4":
+        run_c4(args, rank, world, local_rank, warmup)
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     from sparse_gslam_b200 import dist as sdist
     g, algo, iters, desc = make_workload(args.workload, rank, world)

@@ -212,6 +212,22 @@ sgb_status sgb_get_timings(const sgb_handle* h, sgb_timings* out);
 sgb_status sgb_optimize_resident(sgb_handle* h, int32_t algo, int32_t max_iters, int32_t* iters_done,
                                  sgb_iter_stat* stats);
 
+/* Batched SparseOptimizer::optimize for n INDEPENDENT optimisers (n handles, each with its own graph set by
+ * sgb_set_graph, all on the same device): one kernel launch, one thread block per graph, the complete LM / GN loop
+ * on the device (no host round trip per trial). This is the B200 form of the reference's sliding-window use -- one
+ * small landmark graph re-optimised per key-frame (drone.cpp:146-156, submap_loop_closer.cpp:256-262 keeps the
+ * window small) -- when many such windows (robots, sessions, replays) are optimised at once. Results per handle are
+ * what n separate sgb_optimize calls give (same arithmetic per row; reductions are block-local). The graphs should
+ * be small enough for one thread block each (a few thousand vertices); larger ones still run, just slowly.
+ * iters_done[n]: g2o's optimize() return value per graph; last_stats[n] (may be NULL): the last iteration's stats.
+ * Estimates stay on the device: read them with sgb_get_estimates per handle. */
+sgb_status sgb_optimize_batch(sgb_handle* const* handles, int32_t n, int32_t algo, int32_t max_iters,
+                              int32_t* iters_done, sgb_iter_stat* last_stats);
+/* the same with the estimates of every graph first reset on the device to the ones given to sgb_set_graph
+ * (benchmarking: repeated runs from the same start, nothing copied back) */
+sgb_status sgb_optimize_batch_resident(sgb_handle* const* handles, int32_t n, int32_t algo, int32_t max_iters,
+                                       int32_t* iters_done, sgb_iter_stat* last_stats);
+
 #ifdef __cplusplus
 }
 #endif

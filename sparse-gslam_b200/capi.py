@@ -17,7 +17,7 @@ EXPORTS = [
     "sgb_set_graph", "sgb_get_structure_info", "sgb_get_structure", "sgb_linearize", "sgb_solve_once", "sgb_optimize",
     "sgb_step", "sgb_get_estimates", "sgb_set_estimates", "sgb_push", "sgb_pop", "sgb_discard_top", "sgb_chi2",
     "sgb_get_timings", "sgb_optimize_resident", "sgb_set_graph_partitioned", "sgb_comm_get_handle", "sgb_comm_connect",
-    "sgb_get_partition_info",
+    "sgb_get_partition_info", "sgb_optimize_batch", "sgb_optimize_batch_resident",
 ]
 
 
@@ -113,5 +113,7 @@ def load() -> C.CDLL:
         getattr(L, f).argtypes = [vp]
     L.sgb_chi2.argtypes = [vp, vp]
     L.sgb_get_timings.argtypes = [vp, C.POINTER(Timings)]
+    for f in ("sgb_optimize_batch", "sgb_optimize_batch_resident"):
+        getattr(L, f).argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
     _lib = L
     return L

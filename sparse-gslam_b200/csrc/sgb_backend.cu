@@ -118,7 +118,7 @@ sgb_status dalloc(sgb_handle* h, T** out, size_t n) {
     }
   size_t total = 0;
   for (auto& sl : h->slabs) total += sl.cap;
-  size_t cap = std::max(bytes, std::max<size_t>(total / 2, (size_t)8 << 20));
+  size_t cap = std::max(bytes, std::max<size_t>(total / 2, (size_t)1 << 20));
   void* p = nullptr;
   SGB_CUDA(cudaMalloc(&p, cap));
   h->slabs.push_back({(char*)p, cap, bytes});
@@ -127,9 +127,15 @@ sgb_status dalloc(sgb_handle* h, T** out, size_t n) {
 }
 // host (pageable) -> device on the handle's stream, through the pinned staging ring
 sgb_status h2d(sgb_handle* h, void* dst, const void* src, size_t bytes) {
-  if (bytes < ((size_t)256 << 10) || !h->stage[0]) {
+  if (bytes < ((size_t)256 << 10)) {
     SGB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, h->stream));
     return SGB_OK;
+  }
+  if (!h->stage[0]) {  // first large upload of this handle (handles of small graphs never pin memory)
+    for (int b = 0; b < sgb_handle::kStages; ++b) {
+      SGB_CUDA(cudaMallocHost((void**)&h->stage[b], sgb_handle::kStageBytes));
+      SGB_CUDA(cudaEventCreateWithFlags(&h->stage_ev[b], cudaEventDisableTiming));
+    }
   }
   for (size_t off = 0; off < bytes; off += sgb_handle::kStageBytes) {
     size_t n = std::min(sgb_handle::kStageBytes, bytes - off);
@@ -456,10 +462,7 @@ sgb_status sgb_create(const sgb_options* opt, sgb_handle** out) {
   if ((e = cudaMalloc((void**)&h->d_part_l, pb)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc((void**)&h->d_part_e, pb)) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMalloc((void**)&h->d_bar, sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc", e);
-  for (int b = 0; b < sgb_handle::kStages; ++b) {
-    if ((e = cudaMallocHost((void**)&h->stage[b], sgb_handle::kStageBytes)) != cudaSuccess) return fail("cudaMallocHost", e);
-    if ((e = cudaEventCreateWithFlags(&h->stage_ev[b], cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
-  }
+
   *out = h;
   return SGB_OK;
 }
@@ -953,6 +956,108 @@ sgb_status sgb_chi2(sgb_handle* h, double* chi2) {
   if ((st = read_scalars(h)) != SGB_OK) return st;
   if (chi2) { chi2[0] = h->h_sc->chi2; chi2[1] = h->h_sc->chi2_robust; }
   return SGB_OK;
+}
+
+static sgb_status optimize_batch_impl(sgb_handle* const* hs, int32_t n, int32_t algo, int32_t max_iters,
+                                      int32_t* iters_done, sgb_iter_stat* last_stats, bool reset) {
+  if (!hs || n <= 0) return SGB_ERR_INVALID;
+  sgb_handle* h = hs[0];  // errors are reported on the first handle; its stream carries the launch
+  if (!h) return SGB_ERR_INVALID;
+  if (algo != SGB_ALGO_LM && algo != SGB_ALGO_GN) { h->err = "unknown algorithm"; return SGB_ERR_INVALID; }
+  for (int i = 0; i < n; ++i) {
+    if (iters_done) iters_done[i] = -1;
+    if (!hs[i] || !hs[i]->has_graph) { h->err = "batch: a handle has no graph (initializeOptimization not called)"; return SGB_ERR_NOT_INITIALIZED; }
+    if (hs[i]->device != h->device) { h->err = "batch: all handles must live on the same device"; return SGB_ERR_INVALID; }
+    if (hs[i]->LP.world != 1) { h->err = "batch: partitioned graphs are not batched"; return SGB_ERR_UNSUPPORTED; }
+  }
+  SGB_CUDA(cudaSetDevice(h->device));
+  cudaStream_t s = h->stream;
+  for (int i = 0; i < n; ++i) {  // work queued earlier on the other handles' streams must be finished
+    if (hs[i] != h) SGB_CUDA(cudaStreamSynchronize(hs[i]->stream));
+    if (reset) {
+      sgb_handle* q = hs[i];
+      size_t np = 3 * (size_t)q->S.P_all * sizeof(double), nl = 2 * (size_t)q->S.L_all * sizeof(double);
+      for (int b = 0; b < 2; ++b) {
+        if (np) SGB_CUDA(cudaMemcpyAsync(q->G.pose_buf[b][0], q->d_pose0, np, cudaMemcpyDeviceToDevice, s));
+        if (nl) SGB_CUDA(cudaMemcpyAsync(q->G.lm_buf[b][0], q->d_lm0, nl, cudaMemcpyDeviceToDevice, s));
+      }
+    }
+  }
+  std::vector<BatchItem> items(n);
+  for (int i = 0; i < n; ++i) {
+    items[i].g = hs[i]->G;
+    items[i].sc = hs[i]->d_sc;
+  }
+  BatchItem* d_items = nullptr;
+  BatchResult* d_res = nullptr;
+  SGB_CUDA(cudaMalloc((void**)&d_items, sizeof(BatchItem) * (size_t)n));
+  SGB_CUDA(cudaMalloc((void**)&d_res, sizeof(BatchResult) * (size_t)n));
+  std::vector<BatchResult> res(n);
+  BatchParams prm;
+  prm.algo = algo;
+  prm.max_iters = max_iters;
+  prm.max_trials = h->opt.lm_max_trials > 0 ? h->opt.lm_max_trials : 10;
+  prm.tau = h->opt.lm_tau > 0 ? h->opt.lm_tau : 1e-5;
+  prm.user_lambda = h->opt.lm_user_lambda;
+  prm.pcg.tol = h->opt.pcg_tolerance > 0 ? h->opt.pcg_tolerance : 1e-10;
+  prm.pcg.maxit = h->opt.pcg_max_iters;
+  prm.pcg.lambda_override = 0.0;
+  prm.pcg.use_override = 0;
+  cudaEvent_t t0, t1;
+  SGB_CUDA(cudaEventCreate(&t0));
+  SGB_CUDA(cudaEventCreate(&t1));
+  cudaError_t e = cudaMemcpyAsync(d_items, items.data(), sizeof(BatchItem) * (size_t)n, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) e = cudaEventRecord(t0, s);
+  if (e == cudaSuccess) {
+    k_lm_block<<<n, kThreads, 0, s>>>(d_items, prm, d_res);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaEventRecord(t1, s);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(res.data(), d_res, sizeof(BatchResult) * (size_t)n, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  float ms = 0.f;
+  if (e == cudaSuccess) cudaEventElapsedTime(&ms, t0, t1);
+  cudaEventDestroy(t0);
+  cudaEventDestroy(t1);
+  cudaFree(d_items);
+  cudaFree(d_res);
+  if (e != cudaSuccess) {
+    h->err = std::string("sgb_optimize_batch: ") + cudaGetErrorString(e);
+    return SGB_ERR_CUDA;
+  }
+  for (int i = 0; i < n; ++i) {
+    sgb_handle* q = hs[i];
+    q->G.cur = res[i].cur;
+    q->lm_state_valid = false;
+    std::memset(&q->tm, 0, sizeof q->tm);
+    q->tm.total_ms = ms;  // the launch is shared: every handle reports the batch time
+    q->tm.pcg_iters = res[i].pcg_iters_total;
+    q->tm.trials = res[i].trials;
+    q->tm.kernel_launches = (i == 0) ? 1 : 0;
+    if (iters_done) iters_done[i] = res[i].iters_done;
+    if (last_stats) {
+      sgb_iter_stat& st = last_stats[i];
+      st.iteration = std::max(0, res[i].iters_done - 1);
+      st.trials = res[i].trials;
+      st.result = res[i].result;
+      st.pcg_iters = res[i].pcg_iters;
+      st.chi2 = res[i].chi2;
+      st.lambda = res[i].lambda;
+      st.rho = res[i].rho;
+      st.chi2_before = res[i].chi2_before;
+      st.pcg_residual = res[i].pcg_rel;
+    }
+  }
+  return SGB_OK;
+}
+
+sgb_status sgb_optimize_batch(sgb_handle* const* handles, int32_t n, int32_t algo, int32_t max_iters, int32_t* iters_done,
+                              sgb_iter_stat* last_stats) {
+  return optimize_batch_impl(handles, n, algo, max_iters, iters_done, last_stats, false);
+}
+sgb_status sgb_optimize_batch_resident(sgb_handle* const* handles, int32_t n, int32_t algo, int32_t max_iters,
+                                       int32_t* iters_done, sgb_iter_stat* last_stats) {
+  return optimize_batch_impl(handles, n, algo, max_iters, iters_done, last_stats, true);
 }
 
 sgb_status sgb_get_timings(const sgb_handle* h, sgb_timings* out) {

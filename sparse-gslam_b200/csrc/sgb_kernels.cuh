@@ -290,6 +290,10 @@ struct PcgParams {
 __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long long* bar, unsigned int nb,
                                              unsigned long long& epoch, unsigned long long& seq, double* part,
                                              double* vals, int nv, double* sm, int* s_last) {
+  if (bar == nullptr) {  // the whole solve runs in ONE thread block (batched small graphs): a block barrier is enough,
+    __syncthreads();     // the values are already block-wide sums
+    return;
+  }
   ++seq;
   epoch += nb;
   const int slot = (int)(seq & 1ull);
@@ -357,31 +361,26 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
 //   phase A  t = W Hlp^T z (landmark rows)                     | barrier: every rank's t is complete
 //   phase B  w = (Hpp + lambda) z - Hpl t, z.w, d and s rows   | barrier + all-reduce of delta
 //   phase C  x += alpha d, r -= alpha s, z = M^-1 r, r.z       | barrier + all-reduce of gamma: every z is complete
-__global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g, DevScalars* sc, double* part,
-                                                                     unsigned long long* bar, PcgParams prm) {
-  __shared__ double sm[32];
-  __shared__ int s_last;
-  // wall time of the three phases of an iteration as seen by thread 0 of each CTA (barrier waits included); CTA 0's
-  // copy is reported. Kept in shared memory: it is touched once per phase and must not cost registers.
-  __shared__ unsigned long long ph_ns[4], t_ph;
-  if (threadIdx.x == 0) {
-    ph_ns[0] = ph_ns[1] = ph_ns[2] = ph_ns[3] = 0;
-    t_ph = globaltimer_ns();
-  }
+struct PcgOut {
+  double gam0, gam;
+  int iters, flag;
+};
+// The solve itself, shared by the persistent multi-CTA kernel (k_pcg: tid / nthreads span the grid, `bar` is the grid
+// barrier counter) and the one-CTA-per-graph batched kernel (k_lm_block: tid / nthreads span the block, bar == NULL).
+// ph_ns / t_ph: shared-memory phase timers of the calling CTA.
+__device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, const int nthreads, const unsigned int nb,
+                                          double* part, unsigned long long* bar, unsigned long long& seq,
+                                          const PcgParams& prm, const double lambda, double* sm, int* s_last,
+                                          unsigned long long* ph_ns, unsigned long long* t_ph, PcgOut& out) {
 #define SGB_PHASE_LAP(i)                        \
   do {                                          \
     if (threadIdx.x == 0) {                     \
       unsigned long long _t = globaltimer_ns(); \
-      ph_ns[i] += _t - t_ph;                    \
-      t_ph = _t;                                \
+      ph_ns[i] += _t - *t_ph;                   \
+      *t_ph = _t;                               \
     }                                           \
   } while (0)
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int nthreads = gridDim.x * blockDim.x;
-  const unsigned int nb = gridDim.x;
   unsigned long long epoch = 0;
-  unsigned long long seq = sc->xseq;
-  const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   double* x = g.x_p[g.rank];
   double* zin = g.p[g.rank];
 
@@ -400,7 +399,7 @@ __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g
     }
   }
   double gam = block_sum(acc, sm);
-  grid_xreduce(g, bar, nb, epoch, seq, part, &gam, 1, sm, &s_last);  // also: every rank's z segment is complete
+  grid_xreduce(g, bar, nb, epoch, seq, part, &gam, 1, sm, s_last);  // also: every rank's z segment is complete
   SGB_PHASE_LAP(3);
   const double gam0 = gam, target = prm.tol * prm.tol * gam0;
   double gam_old = 0.0, alpha_old = 0.0;
@@ -421,13 +420,13 @@ __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g
       const double beta = it == 0 ? 0.0 : gam / gam_old;
       if (g.capL > 0) {
         for (int sl = tid >> 5; sl < g.Hlp.nslices; sl += nthreads >> 5) lm_slice_pass(g, sl, 0);
-        grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, &s_last);  // every rank's t segment is complete
+        grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, s_last);  // every rank's t segment is complete
       }
       SGB_PHASE_LAP(0);
       acc = 0.0;
       for (int lp = tid; lp < g.nP; lp += nthreads) acc += schur_phaseB_row(g, lp, lambda, beta);
       double del = block_sum(acc, sm);
-      grid_xreduce(g, bar, nb, epoch, seq, part, &del, 1, sm, &s_last);
+      grid_xreduce(g, bar, nb, epoch, seq, part, &del, 1, sm, s_last);
       SGB_PHASE_LAP(1);
       const double denom = it == 0 ? del : del - beta * gam / alpha_old;  // = d.S d
       if (!(denom > 0.0)) {  // S not positive definite (or NaN): g2o's "Cholesky failure" analogue
@@ -451,19 +450,41 @@ __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g
       gam_old = gam;
       alpha_old = alpha;
       gam = block_sum(acc, sm);
-      grid_xreduce(g, bar, nb, epoch, seq, part, &gam, 1, sm, &s_last);  // also: every rank's z segment is complete
+      grid_xreduce(g, bar, nb, epoch, seq, part, &gam, 1, sm, s_last);  // also: every rank's z segment is complete
       SGB_PHASE_LAP(2);
     }
   }
 #undef SGB_PHASE_LAP
+  out.gam0 = gam0;
+  out.gam = gam;
+  out.iters = it;
+  out.flag = flag;
+}
+
+__global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g, DevScalars* sc, double* part,
+                                                                     unsigned long long* bar, PcgParams prm) {
+  __shared__ double sm[32];
+  __shared__ int s_last;
+  // wall time of the three phases of an iteration as seen by thread 0 of each CTA (barrier waits included); CTA 0's
+  // copy is reported. Kept in shared memory: it is touched once per phase and must not cost registers.
+  __shared__ unsigned long long ph_ns[4], t_ph;
+  if (threadIdx.x == 0) {
+    ph_ns[0] = ph_ns[1] = ph_ns[2] = ph_ns[3] = 0;
+    t_ph = globaltimer_ns();
+  }
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long seq = sc->xseq;
+  const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
+  PcgOut out;
+  pcg_solve(g, tid, gridDim.x * blockDim.x, gridDim.x, part, bar, seq, prm, lambda, sm, &s_last, ph_ns, &t_ph, out);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) sc->pcg_phase_ns[i] += ph_ns[i];
     sc->xseq = seq;
-    sc->rz0 = gam0;
-    sc->rz = gam;
-    sc->pcg_iters = it;
-    sc->pcg_flag = flag;
-    sc->pcg_rel = gam0 > 0.0 ? sqrt(fabs(gam) / gam0) : 0.0;
+    sc->rz0 = out.gam0;
+    sc->rz = out.gam;
+    sc->pcg_iters = out.iters;
+    sc->pcg_flag = out.flag;
+    sc->pcg_rel = out.gam0 > 0.0 ? sqrt(fabs(out.gam) / out.gam0) : 0.0;
   }
 }
 
@@ -489,7 +510,47 @@ __global__ void __launch_bounds__(kThreads) k_update(DevGraph g, DevScalars* sc,
   if (threadIdx.x == 0) part[2 * kMaxBlocks + blockIdx.x] = s;
 }
 
-// OptimizationAlgorithmLevenberg::solve, the part after the trial's chi2 is known
+// OptimizationAlgorithmLevenberg::solve, the part after the trial's chi2 is known: gain ratio, lambda /
+// nu update, accept / reject, Terminate conditions, with g2o's constants. c / cr = activeChi2 / activeRobustChi2 of the
+// trial estimates, scale = computeScale sum, solve_ok = the linear solve did not break down. One thread.
+__device__ __forceinline__ void lm_control_update(DevScalars* sc, double c, double cr, double scale, bool solve_ok,
+                                                  int max_trials) {
+  sc->chi2 = c;
+  sc->chi2_robust = cr;
+  double tempChi = solve_ok ? cr : DBL_MAX;
+  double rho = sc->current_chi - tempChi;
+  scale += 1e-3;
+  rho /= scale;
+  sc->scale = scale;
+  sc->temp_chi = tempChi;
+  double lambda = sc->lambda, ni = sc->ni;
+  int accepted = 0;
+  bool lambda_finite = true;
+  if (rho > 0.0 && isfinite(tempChi)) {
+    double a = 2.0 * rho - 1.0;
+    double alpha = 1.0 - a * a * a;
+    alpha = fmin(alpha, 2.0 / 3.0);
+    double scaleFactor = fmax(1.0 / 3.0, alpha);
+    lambda *= scaleFactor;
+    ni = 2.0;
+    sc->current_chi = tempChi;
+    accepted = 1;
+  } else {
+    lambda *= ni;
+    ni *= 2.0;
+    lambda_finite = isfinite(lambda);
+  }
+  int trials = sc->trials + (lambda_finite ? 1 : 0);  // g2o breaks out before qmax++ when lambda overflows
+  sc->lambda = lambda;
+  sc->ni = ni;
+  sc->rho = rho;
+  sc->accepted = accepted;
+  sc->trials = trials;
+  int again = (rho < 0.0 && trials < max_trials && lambda_finite) ? 1 : 0;
+  sc->again = again;
+  if (!again) sc->result = (trials == max_trials || rho == 0.0 || !lambda_finite) ? 2 : 1;
+  sc->setup_fail = 0;
+}
 __global__ void __launch_bounds__(kThreads) k_lm_control(DevGraph g, DevScalars* sc, const double* part_chi, int nb_chi,
                                                         const double* part_scale, int nb_scale, int max_trials) {
   __shared__ double sm[32];
@@ -504,43 +565,7 @@ __global__ void __launch_bounds__(kThreads) k_lm_control(DevGraph g, DevScalars*
   xreduce(g, ++seq, &fail, 1, 1, true);
   if (threadIdx.x == 0) {
     sc->xseq = seq;
-    double c = v[0], cr = v[1], scale = v[2];
-    sc->chi2 = c;
-    sc->chi2_robust = cr;
-    bool ok2 = (sc->pcg_flag != 2) && (fail == 0.0);
-    double tempChi = ok2 ? cr : DBL_MAX;
-    double rho = sc->current_chi - tempChi;
-    scale += 1e-3;
-    rho /= scale;
-    sc->scale = scale;
-    sc->temp_chi = tempChi;
-    double lambda = sc->lambda, ni = sc->ni;
-    int accepted = 0;
-    bool lambda_finite = true;
-    if (rho > 0.0 && isfinite(tempChi)) {
-      double a = 2.0 * rho - 1.0;
-      double alpha = 1.0 - a * a * a;
-      alpha = fmin(alpha, 2.0 / 3.0);
-      double scaleFactor = fmax(1.0 / 3.0, alpha);
-      lambda *= scaleFactor;
-      ni = 2.0;
-      sc->current_chi = tempChi;
-      accepted = 1;
-    } else {
-      lambda *= ni;
-      ni *= 2.0;
-      lambda_finite = isfinite(lambda);
-    }
-    int trials = sc->trials + (lambda_finite ? 1 : 0);  // g2o breaks out before qmax++ when lambda overflows
-    sc->lambda = lambda;
-    sc->ni = ni;
-    sc->rho = rho;
-    sc->accepted = accepted;
-    sc->trials = trials;
-    int again = (rho < 0.0 && trials < max_trials && lambda_finite) ? 1 : 0;
-    sc->again = again;
-    if (!again) sc->result = (trials == max_trials || rho == 0.0 || !lambda_finite) ? 2 : 1;
-    sc->setup_fail = 0;
+    lm_control_update(sc, v[0], v[1], v[2], (sc->pcg_flag != 2) && (fail == 0.0), max_trials);
   }
 }
 // Gauss-Newton: the solve succeeded iff no rank saw a breakdown
@@ -554,6 +579,156 @@ __global__ void k_gn_control(DevGraph g, DevScalars* sc) {
     bool ok = (sc->pcg_flag != 2) && (fail == 0.0);
     sc->result = ok ? 1 : -1;
     sc->setup_fail = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ batched graphs
+// SparseOptimizer::optimize() for MANY small independent graphs (the sliding-window landmark graphs the reference
+// re-optimises once per key-frame, drone.cpp:146-156): ONE launch, one thread block per graph, the complete LM / GN
+// loop on the device -- linearise, damp, Schur set-up, PCG, back-substitution, update, chi2 of the trial, gain ratio
+// and lambda control -- with block barriers where the single-graph path has kernel boundaries or grid barriers. The
+// per-row bodies (sgb_rows.h), the PCG (pcg_solve) and the LM control (lm_control_update) are the very same code.
+struct BatchItem {
+  DevGraph g;
+  DevScalars* sc;  // the handle's scalar block (kept coherent for later sgb_chi2 / sgb_step calls)
+};
+struct BatchParams {
+  int algo, max_iters, max_trials;
+  double tau, user_lambda;
+  PcgParams pcg;   // maxit <= 0: per graph, max(100, 12 * free poses)
+};
+struct BatchResult {
+  int iters_done, result, cur, trials, pcg_iters /* last iteration */, pcg_iters_total;
+  double chi2, lambda, rho, chi2_before, pcg_rel;
+};
+
+__global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, BatchParams prm, BatchResult* results) {
+  __shared__ DevGraph g;
+  __shared__ DevScalars sc;
+  __shared__ double sm[32];
+  __shared__ int s_last, s_ok;
+  __shared__ unsigned long long ph_ns[4], t_ph;
+  {  // this block's graph descriptor -> shared memory (word copy)
+    const int* src = reinterpret_cast<const int*>(&items[blockIdx.x].g);
+    int* dst = reinterpret_cast<int*>(&g);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevGraph) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    const int* s2 = reinterpret_cast<const int*>(items[blockIdx.x].sc);
+    int* d2 = reinterpret_cast<int*>(&sc);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevScalars) / sizeof(int)); i += blockDim.x) d2[i] = s2[i];
+    if (threadIdx.x == 0) {
+      ph_ns[0] = ph_ns[1] = ph_ns[2] = ph_ns[3] = 0;
+      t_ph = 0;
+    }
+  }
+  __syncthreads();
+  const int tid = threadIdx.x, nth = blockDim.x;
+  PcgParams pcg = prm.pcg;
+  if (pcg.maxit <= 0) pcg.maxit = max(100, 12 * g.nP);
+  unsigned long long seq = 0;
+  int done = 0, result = 1, pcg_total = 0, pcg_all = 0, trials_last = 0;
+  double chi_before = 0.0;
+  for (int iter = 0; iter < prm.max_iters && result == 1; ++iter) {
+    // ---- linearise + assemble at the current estimates
+    LinAcc acc;
+    for (int lp = tid; lp < g.nP; lp += nth) lin_pose_row(g, lp, acc);
+    for (int ll = tid; ll < g.nL; ll += nth) lin_lm_row(g, ll, acc);
+    const double c = block_sum(acc.chi, sm), cr = block_sum(acc.chi_r, sm), md = block_max(acc.maxd, sm);
+    if (tid == 0) {
+      sc.chi2 = c;
+      sc.chi2_robust = sc.chi_lin = sc.current_chi = sc.temp_chi = cr;
+      sc.max_diag = md;
+      sc.trials = 0;
+      sc.rho = 0.0;
+      sc.again = 0;
+      sc.setup_fail = 0;
+      if (prm.algo == 0 && iter == 0) {  // OptimizationAlgorithmLevenberg::computeLambdaInit
+        sc.lambda = prm.user_lambda > 0.0 ? prm.user_lambda : prm.tau * md;
+        sc.ni = 2.0;
+      }
+    }
+    __syncthreads();
+    chi_before = cr;
+    pcg_total = 0;
+    while (true) {  // LM: trials of this iteration; GN: exactly one pass
+      const double lambda = prm.algo == 0 ? sc.lambda : 0.0;
+      const int dst = prm.algo == 0 ? (g.cur ^ 1) : g.cur;
+      bool ok = true;
+      for (int ll = tid; ll < g.nL; ll += nth) ok &= setup_lm_row(g, ll, lambda);
+      __syncthreads();
+      for (int lp = tid; lp < g.nP; lp += nth) ok &= setup_pose_row(g, lp, lambda);
+      if (tid == 0) s_ok = 1;
+      __syncthreads();
+      if (!ok) atomicAnd(&s_ok, 0);
+      PcgOut po;
+      pcg_solve(g, tid, nth, 1u, nullptr, nullptr, seq, pcg, lambda, sm, &s_last, ph_ns, &t_ph, po);
+      pcg_total += po.iters;
+      pcg_all += po.iters;
+      // ---- back-substitution, update into the trial (LM) or current (GN) estimates, computeScale
+      for (int sl = tid >> 5; sl < g.Hlp.nslices; sl += nth >> 5) lm_slice_pass(g, sl, 1);
+      __syncthreads();
+      double s = 0.0;
+      for (int v = tid; v < g.nP + g.nL; v += nth)
+        s += v < g.nP ? update_pose_row(g, v, lambda, dst) : update_lm_row(g, v - g.nP, lambda, dst);
+      const double scale = block_sum(s, sm);
+      __syncthreads();
+      const bool solve_ok = po.flag != 2 && s_ok != 0;
+      if (prm.algo != 0) {  // Gauss-Newton
+        if (tid == 0) {
+          sc.pcg_iters = po.iters;
+          sc.pcg_flag = po.flag;
+          sc.pcg_rel = po.gam0 > 0.0 ? sqrt(fabs(po.gam) / po.gam0) : 0.0;
+          sc.result = solve_ok ? 1 : -1;
+        }
+        __syncthreads();
+        break;
+      }
+      // ---- chi2 of the trial estimates + LM control
+      const double* pose = g.pose_buf[dst][g.rank];
+      const double* lm = g.lm_buf[dst][g.rank];
+      double tc = 0.0, tcr = 0.0;
+      for (int k = tid; k < g.n_pp_owned + g.n_pl_owned; k += nth) {
+        if (k < g.n_pp_owned) {
+          double a, b;
+          pp_chi(g, k, pose, &a, &b);
+          tc += a;
+          tcr += b;
+        } else {
+          double a = pl_chi(g, k - g.n_pp_owned, pose, lm);
+          tc += a;
+          tcr += a;
+        }
+      }
+      tc = block_sum(tc, sm);
+      tcr = block_sum(tcr, sm);
+      if (tid == 0) {
+        sc.pcg_iters = po.iters;
+        sc.pcg_flag = po.flag;
+        sc.pcg_rel = po.gam0 > 0.0 ? sqrt(fabs(po.gam) / po.gam0) : 0.0;
+        lm_control_update(&sc, tc, tcr, scale, solve_ok, prm.max_trials);
+        if (sc.accepted) g.cur ^= 1;  // discardTop: the trial estimates become current
+      }
+      __syncthreads();
+      if (!sc.again) break;
+    }
+    result = sc.result;
+    trials_last = prm.algo == 0 ? sc.trials : 1;
+    ++done;
+  }
+  if (tid == 0) {
+    BatchResult r;
+    r.iters_done = result == -1 ? 0 : done;
+    r.result = result;
+    r.cur = g.cur;
+    r.trials = trials_last;
+    r.pcg_iters = pcg_total;
+    r.pcg_iters_total = pcg_all;
+    r.chi2 = prm.algo == 0 ? sc.current_chi : sc.chi2_robust;
+    r.lambda = prm.algo == 0 ? sc.lambda : 0.0;
+    r.rho = prm.algo == 0 ? sc.rho : 0.0;
+    r.chi2_before = chi_before;
+    r.pcg_rel = sc.pcg_rel;
+    results[blockIdx.x] = r;
+    *items[blockIdx.x].sc = sc;
   }
 }
 

@@ -206,3 +206,23 @@ class SparseOptimizerB200:
         t = capi.Timings()
         self._check(self.L.sgb_get_timings(self.h, C.byref(t)))
         return t.as_dict()
+
+
+def optimize_batch(optimizers, iters, resident=False):
+    """One launch for many independent optimisers (sgb_optimize_batch): one thread block per graph, the whole LM / GN
+    loop on the device. All optimisers must share the algorithm and the device. Returns (g2o return values, last
+    iteration's stats) per optimiser."""
+    n = len(optimizers)
+    if n == 0:
+        return [], []
+    L = optimizers[0].L
+    algo = optimizers[0].algo
+    assert all(o.algo == algo for o in optimizers), "one algorithm per batch"
+    hs = (C.c_void_p * n)(*[o.h for o in optimizers])
+    done = (C.c_int32 * n)()
+    stats = (capi.IterStat * n)()
+    f = L.sgb_optimize_batch_resident if resident else L.sgb_optimize_batch
+    st = f(C.cast(hs, C.c_void_p), n, algo, iters, C.cast(done, C.c_void_p), C.cast(stats, C.c_void_p))
+    if st != capi.OK:
+        raise SgbError(st, L.sgb_last_error(optimizers[0].h).decode())
+    return [done[i] for i in range(n)], [stats[i].as_dict() for i in range(n)]

@@ -195,3 +195,43 @@ def test_c5_slice_properties():
     po, lo = o.estimates()
     pg, lg = a.estimates()
     assert pose_err(pg, po) < 1e-6 and rel_err(lg, lo) < 1e-6
+
+
+def test_batched_optimize_matches_individual_and_oracle():
+    """sgb_optimize_batch (one thread block per graph, whole LM loop on the device) gives what separate optimize()
+    calls give, for LM on C4-style windows of different sizes and for GN + DCS on their pose graphs."""
+    from sparse_gslam_b200.optimizer import optimize_batch
+    graphs = [gg.make_c4_window(seed=1000 + i) for i in range(5)] + [gg.make_small(seed=7), gg.make_small(seed=8, P=60, L=10, E_l=120, n_closures=3)]
+    for algo, iters, mk in ((capi.ALGO_LM, 15, lambda g: g), (capi.ALGO_GN, 6, lambda g: g.pose_only(phi=1.0))):
+        gs = [mk(g) for g in graphs]
+        batch = []
+        for g in gs:
+            o = SparseOptimizerB200(algo, jacobian_mode=capi.JAC_ANALYTIC)
+            assert o.initialize_optimization(g)
+            batch.append(o)
+        done, stats = optimize_batch(batch, iters)
+        for g, o, n_b, s_b in zip(gs, batch, done, stats):
+            one = SparseOptimizerB200(algo, jacobian_mode=capi.JAC_ANALYTIC)
+            one.initialize_optimization(g)
+            n_1, s_1 = one.optimize(iters)
+            assert n_b == n_1
+            p1, l1 = one.estimates()
+            pb, lb = o.estimates()
+            assert pose_err(pb, p1) < 1e-8
+            if l1.size:
+                assert rel_err(lb, l1) < 1e-8
+            np.testing.assert_allclose(o.active_chi2()[0], one.active_chi2()[0], rtol=1e-8)
+            np.testing.assert_allclose(s_b["chi2"], s_1[-1]["chi2"], rtol=1e-8)
+            orc = Oracle(g)
+            orc.initialize_optimization()
+            orc.optimize(iters, ALGO_LM if algo == capi.ALGO_LM else ALGO_GN, JAC[capi.JAC_ANALYTIC])
+            po, lo = orc.estimates()
+            assert pose_err(pb, po) < 1e-6
+            np.testing.assert_allclose(o.active_chi2()[0], orc.chi2()[0], rtol=1e-6)
+
+
+def test_batched_optimize_rejects_bad_batches():
+    from sparse_gslam_b200.optimizer import optimize_batch
+    a = SparseOptimizerB200(capi.ALGO_LM)
+    with pytest.raises(Exception):
+        optimize_batch([a], 3)   # no graph set: "forgot to call initializeOptimization()"
