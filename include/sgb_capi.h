@@ -228,6 +228,19 @@ sgb_status sgb_optimize_batch(sgb_handle* const* handles, int32_t n, int32_t alg
 sgb_status sgb_optimize_batch_resident(sgb_handle* const* handles, int32_t n, int32_t algo, int32_t max_iters,
                                        int32_t* iters_done, sgb_iter_stat* last_stats);
 
+/* ---- graph fixture / wire format: g2o text files with the types of this path ----
+ * VERTEX_SE2, EDGE_SE2, FIX as g2o writes them; VERTEX_RHOTHETA id rho theta and
+ * EDGE_SE2_RHOTHETA pose line rho theta I11 I12 I22 for the reference's custom types (tags registered at
+ * vertex_rhotheta.cpp:43 / edge_se2_rhotheta.cpp:24, whose read/write are empty in the reference);
+ * ROBUST_KERNEL_DCS k delta for the DCS kernel of the k-th EDGE_SE2 line. Host only: works without a GPU.
+ * sgb_g2o_load: *out owns the arrays; sgb_g2o_view fills an sgb_graph_soa with pointers into it (valid until
+ * sgb_g2o_free). errbuf (may be NULL) receives "file:line: message" on failure. */
+typedef struct sgb_graph_file sgb_graph_file;
+sgb_status sgb_g2o_load(const char* path, sgb_graph_file** out, char* errbuf, int32_t errlen);
+void sgb_g2o_view(const sgb_graph_file* f, sgb_graph_soa* out);
+void sgb_g2o_free(sgb_graph_file* f);
+sgb_status sgb_g2o_save(const char* path, const sgb_graph_soa* g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,7 +17,8 @@ EXPORTS = [
     "sgb_set_graph", "sgb_get_structure_info", "sgb_get_structure", "sgb_linearize", "sgb_solve_once", "sgb_optimize",
     "sgb_step", "sgb_get_estimates", "sgb_set_estimates", "sgb_push", "sgb_pop", "sgb_discard_top", "sgb_chi2",
     "sgb_get_timings", "sgb_optimize_resident", "sgb_set_graph_partitioned", "sgb_comm_get_handle", "sgb_comm_connect",
-    "sgb_get_partition_info", "sgb_optimize_batch", "sgb_optimize_batch_resident",
+    "sgb_get_partition_info", "sgb_optimize_batch", "sgb_optimize_batch_resident", "sgb_g2o_load", "sgb_g2o_view",
+    "sgb_g2o_free", "sgb_g2o_save",
 ]
 
 
@@ -115,5 +116,9 @@ def load() -> C.CDLL:
     L.sgb_get_timings.argtypes = [vp, C.POINTER(Timings)]
     for f in ("sgb_optimize_batch", "sgb_optimize_batch_resident"):
         getattr(L, f).argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp, vp]
+    L.sgb_g2o_load.argtypes = [C.c_char_p, C.POINTER(vp), C.c_char_p, C.c_int32]
+    L.sgb_g2o_view.argtypes = [vp, C.POINTER(GraphSoA)]
+    L.sgb_g2o_free.argtypes = [vp]
+    L.sgb_g2o_save.argtypes = [C.c_char_p, C.POINTER(GraphSoA)]
     _lib = L
     return L

@@ -14,6 +14,8 @@ from __future__ import annotations
 
 from dataclasses import dataclass, field
 
+import os
+
 import numpy as np
 
 LANDMARK_ID0 = 10_000_000  # reference include/drone.h:22
@@ -580,3 +582,56 @@ def make(config: str, seed: int | None = None, **kw) -> Graph:
     if config == "small":
         return make_small(0 if seed is None else seed, **kw)
     raise ValueError(config)
+
+
+# ----------------------------------------------------------------------------- g2o text files (C ABI: sgb_g2o_*)
+def save_g2o(g: Graph, path: str) -> None:
+    """Write `g` as a g2o text file (VERTEX_SE2 / VERTEX_RHOTHETA / EDGE_SE2 / EDGE_SE2_RHOTHETA / FIX) through
+    sgb_g2o_save."""
+    import ctypes as C
+
+    from . import capi
+    from .optimizer import pack_graph
+    s, keep = pack_graph(g)
+    st = capi.load().sgb_g2o_save(path.encode(), C.byref(s))
+    if st != capi.OK:
+        raise OSError(f"sgb_g2o_save({path}) failed with status {st}")
+
+
+def load_g2o(path: str, name: str | None = None) -> Graph:
+    """Read a g2o text file through sgb_g2o_load into a Graph (ground truth unknown: filled with NaN)."""
+    import ctypes as C
+
+    from . import capi
+    L = capi.load()
+    f = C.c_void_p()
+    err = C.create_string_buffer(512)
+    st = L.sgb_g2o_load(path.encode(), C.byref(f), err, len(err))
+    if st != capi.OK:
+        raise ValueError(err.value.decode() or f"sgb_g2o_load failed with status {st}")
+    try:
+        s = capi.GraphSoA()
+        L.sgb_g2o_view(f, C.byref(s))
+
+        def arr(ptr, n, ct, shape=None):
+            if n == 0 or not ptr:
+                a = np.zeros(0, dtype=np.dtype(ct))
+            else:
+                a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(n,)).copy()
+            return a.reshape(shape) if shape is not None else a
+
+        P, Lm, npp, npl = s.n_poses, s.n_landmarks, s.n_pp, s.n_pl
+        return Graph(
+            name=name or os.path.basename(path),
+            pose_id=arr(s.pose_id, P, C.c_int32), pose_est=arr(s.pose_est, 3 * P, C.c_double, (P, 3)),
+            pose_fixed=arr(s.pose_fixed, P, C.c_uint8), pose_gt=np.full((P, 3), np.nan),
+            lm_id=arr(s.lm_id, Lm, C.c_int32), lm_est=arr(s.lm_est, 2 * Lm, C.c_double, (Lm, 2)),
+            lm_fixed=arr(s.lm_fixed, Lm, C.c_uint8), lm_gt=np.full((Lm, 2), np.nan),
+            pp_i=arr(s.pp_i, npp, C.c_int32), pp_j=arr(s.pp_j, npp, C.c_int32),
+            pp_z=arr(s.pp_z, 3 * npp, C.c_double, (npp, 3)), pp_info=arr(s.pp_info, 6 * npp, C.c_double, (npp, 6)),
+            pp_phi=arr(s.pp_phi, npp, C.c_double), pp_seq=arr(s.pp_seq, npp, C.c_int64),
+            pl_pose=arr(s.pl_pose, npl, C.c_int32), pl_lm=arr(s.pl_lm, npl, C.c_int32),
+            pl_z=arr(s.pl_z, 2 * npl, C.c_double, (npl, 2)), pl_info=arr(s.pl_info, 3 * npl, C.c_double, (npl, 3)),
+            pl_seq=arr(s.pl_seq, npl, C.c_int64), meta=dict(source=path))
+    finally:
+        L.sgb_g2o_free(f)
