@@ -57,9 +57,10 @@ def _worker(rank, world, port, q):
     q.put((rank, out))
 
 
-@pytest.mark.skipif(_ngpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_partitioned_matches_single_gpu(world):
+    if _ngpus() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
     from sparse_gslam_b200 import SparseOptimizerB200, capi
     from sparse_gslam_b200 import graphgen as gg
