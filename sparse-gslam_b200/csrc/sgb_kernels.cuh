@@ -323,9 +323,11 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
   }
   __syncthreads();
   if (*s_last) {
-    __threadfence();
     double loc[2] = {0.0, 0.0};
-    for (int k = 0; k < nv; ++k) loc[k] = reduce_partials(part + k * kMaxBlocks, (int)nb, sm);
+    if (nv > 0) {  // a pure barrier (nv == 0) publishes right away
+      __threadfence();
+      for (int k = 0; k < nv; ++k) loc[k] = reduce_partials(part + k * kMaxBlocks, (int)nb, sm);
+    }
     if (threadIdx.x < g.world) {
       Mailbox* mb = g.mbox[threadIdx.x];
       for (int k = 0; k < nv; ++k) st_relaxed_sys_f64(&mb->val[slot][g.rank][k], loc[k]);
