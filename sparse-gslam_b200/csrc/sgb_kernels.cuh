@@ -421,12 +421,11 @@ __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, cons
       if (it >= prm.maxit) break;  // flag 1
       const double beta = it == 0 ? 0.0 : gam / gam_old;
       if (g.capL > 0) {
-        for (int sl = tid >> 5; sl < g.Hlp.nslices; sl += nthreads >> 5) lm_slice_pass(g, sl, 0);
+        lm_slices_pass(g, tid >> 5, nthreads >> 5, 0);
         grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, s_last);  // every rank's t segment is complete
       }
       SGB_PHASE_LAP(0);
-      acc = 0.0;
-      for (int lp = tid; lp < g.nP; lp += nthreads) acc += schur_phaseB_row(g, lp, lambda, beta);
+      acc = schur_phaseB_rows(g, tid, nthreads, lambda, beta);
       double del = block_sum(acc, sm);
       grid_xreduce(g, bar, nb, epoch, seq, part, &del, 1, sm, s_last);
       SGB_PHASE_LAP(1);

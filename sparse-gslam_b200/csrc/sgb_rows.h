@@ -382,10 +382,25 @@ SGB_HD int sell_col_or_pad(const int32_t* col, int e, bool valid) { return valid
 #ifndef SGB_LM_UNROLL
 #define SGB_LM_UNROLL 2  // blocks whose loads one lane keeps in flight in the landmark pass
 #endif
-SGB_HD void lm_gather_lane(const DevGraph& g, int slice, int lane, double* const* vtab, double* u0_out, double* u1_out) {
+// what a warp needs to know about a slice of the grouped Hlp before it can issue the first useful load; the
+// persistent kernel fetches it one task ahead so that it is off the chain of dependent latencies
+struct LmSliceMeta {
+  int e_begin, steps, shift, row0, row_end;
+};
+SGB_HD LmSliceMeta lm_slice_meta(const DevGraph& g, int slice) {
+  LmSliceMeta m;
+  m.e_begin = g.Hlp.sbase[slice];
+  m.steps = (g.Hlp.sbase[slice + 1] - m.e_begin) >> 5;
+  m.shift = g.Hlp.sshift[slice];
+  m.row0 = g.Hlp.srow[slice];
+  m.row_end = g.Hlp.srow[slice + 1];
+  return m;
+}
+SGB_HD void lm_gather_lane(const DevGraph& g, const LmSliceMeta& m, int lane, double* const* vtab, double* u0_out,
+                           double* u1_out) {
   constexpr int U = SGB_LM_UNROLL;
-  const int steps = (g.Hlp.sbase[slice + 1] - g.Hlp.sbase[slice]) >> 5;
-  const int base = g.Hlp.sbase[slice] + lane;
+  const int steps = m.steps;
+  const int base = m.e_begin + lane;
   const int32_t* col = g.Hlp.col;
   double u0 = 0, u1 = 0;
   int enc[U];
@@ -464,22 +479,38 @@ SGB_HD void lm_row_finish(const DevGraph& g, int ll, int mode, const LmRowOperan
 // One slice of the landmark-major pass, executed by one warp (all 32 lanes must call): mode 0 = phase A on p,
 // mode 1 = back-substitution on x_p.
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ void lm_slice_pass(const DevGraph& g, int slice, int mode) {
+__device__ __forceinline__ void lm_slice_pass(const DevGraph& g, const LmSliceMeta& m, int mode) {
   const int lane = threadIdx.x & 31;
-  const int sh = g.Hlp.sshift[slice];
-  const int row = g.Hlp.srow[slice] + (lane >> (5 - sh));
-  const bool writer = (lane & ((32 >> sh) - 1)) == 0 && row < g.Hlp.srow[slice + 1];
+  const int sh = m.shift;
+  const int row = m.row0 + (lane >> (5 - sh));
+  const bool writer = (lane & ((32 >> sh) - 1)) == 0 && row < m.row_end;
   LmRowOperands o;
   if (writer) lm_row_prefetch(g, row, mode, o);
   double u0, u1;
-  lm_gather_lane(g, slice, lane, mode == 0 ? g.p : g.x_p, &u0, &u1);
+  lm_gather_lane(g, m, lane, mode == 0 ? g.p : g.x_p, &u0, &u1);
   lm_group_sum(sh, u0, u1);
   if (writer) lm_row_finish(g, row, mode, o, u0, u1);
+}
+__device__ __forceinline__ void lm_slice_pass(const DevGraph& g, int slice, int mode) {
+  lm_slice_pass(g, lm_slice_meta(g, slice), mode);
+}
+// the slices sl0, sl0 + stride, ... of one warp, with the next slice's descriptor fetched while the current one runs
+__device__ __forceinline__ void lm_slices_pass(const DevGraph& g, int sl0, int stride, int mode) {
+  const int n = g.Hlp.nslices;
+  if (sl0 >= n) return;
+  LmSliceMeta m = lm_slice_meta(g, sl0);
+  for (int sl = sl0; sl < n; sl += stride) {
+    LmSliceMeta nxt = m;
+    if (sl + stride < n) nxt = lm_slice_meta(g, sl + stride);
+    lm_slice_pass(g, m, mode);
+    m = nxt;
+  }
 }
 #else
 inline void lm_slice_pass(const DevGraph& g, int slice, int mode) {
   double u0[32], u1[32];
-  for (int lane = 0; lane < 32; ++lane) lm_gather_lane(g, slice, lane, mode == 0 ? g.p : g.x_p, &u0[lane], &u1[lane]);
+  const LmSliceMeta m = lm_slice_meta(g, slice);
+  for (int lane = 0; lane < 32; ++lane) lm_gather_lane(g, m, lane, mode == 0 ? g.p : g.x_p, &u0[lane], &u1[lane]);
   const int sh = g.Hlp.sshift[slice];
   lm_group_sum_host(sh, u0, u1);
   for (int rr = 0; rr < (1 << sh); ++rr) {
@@ -490,16 +521,31 @@ inline void lm_slice_pass(const DevGraph& g, int slice, int mode) {
     lm_row_finish(g, row, mode, o, u0[lane], u1[lane]);
   }
 }
+inline void lm_slices_pass(const DevGraph& g, int sl0, int stride, int mode) {
+  for (int sl = sl0; sl < g.Hlp.nslices; sl += stride) lm_slice_pass(g, sl, mode);
+}
 #endif
 // phase B (pose-major): w_i = lambda z_i + sum_j Hpp_ij z_j - sum_l Hpl_il t_l, followed by the two direction
 // recurrences of the single-reduction PCG for this row, d_i = z_i + beta d_i and s_i = w_i + beta s_i (so that w
 // itself never travels to memory); returns z_i . w_i. z = the peer-visible operator input g.p.
-SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double beta) {
+struct PoseRowMeta {  // first entry and width of a pose row in Hpp and Hpl (fetched one row ahead by the PCG kernel)
+  int bpp, wpp, bpl, wpl;
+};
+SGB_HD PoseRowMeta pose_row_meta(const DevGraph& g, int lp) {
   const int slice = lp >> 5, lane = lp & 31;
-  const double* vown = g.p[g.rank] + 3 * (size_t)lp;
-  const int wpp = sell_width(g.Hpp, slice), bpp = g.Hpp.sbase[slice] + lane;
+  PoseRowMeta m;
+  m.wpp = sell_width(g.Hpp, slice);
+  m.bpp = g.Hpp.sbase[slice] + lane;
   const bool has_pl = g.Hpl.rows > 0;
-  const int wpl = has_pl ? sell_width(g.Hpl, slice) : 0, bpl = has_pl ? g.Hpl.sbase[slice] + lane : 0;
+  m.wpl = has_pl ? sell_width(g.Hpl, slice) : 0;
+  m.bpl = has_pl ? g.Hpl.sbase[slice] + lane : 0;
+  return m;
+}
+SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, const PoseRowMeta& m, double lambda, double beta) {
+  const double* vown = g.p[g.rank] + 3 * (size_t)lp;
+  const int wpp = m.wpp, bpp = m.bpp, wpl = m.wpl, bpl = m.bpl;
+  double* d = g.d + 3 * (size_t)lp;
+  double* sv = g.s + 3 * (size_t)lp;
   const int32_t* cpp = g.Hpp.col;
   const int32_t* cpl = g.Hpl.col;
   int enc0 = sell_col_or_pad(cpp, bpp, wpp > 0), enc1 = sell_col_or_pad(cpp, bpp + 32, wpp > 1);
@@ -559,10 +605,11 @@ SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double 
     l0 = n0;
     l1 = n1;
   }
-  double* d = g.d + 3 * (size_t)lp;
-  double* sv = g.s + 3 * (size_t)lp;
-  const double d0 = vi0 + beta * d[0], d1 = vi1 + beta * d[1], d2 = vi2 + beta * d[2];
-  const double s0 = q0 + beta * sv[0], s1 = q1 + beta * sv[1], s2 = q2 + beta * sv[2];
+  // (fetching these six operands, or the next row's descriptor, ahead of the row loops was measured: the extra live
+  // registers cost more in spills at the 80-register budget than the shorter dependency chain gains)
+  const double dold0 = d[0], dold1 = d[1], dold2 = d[2], sold0 = sv[0], sold1 = sv[1], sold2 = sv[2];
+  const double d0 = vi0 + beta * dold0, d1 = vi1 + beta * dold1, d2 = vi2 + beta * dold2;
+  const double s0 = q0 + beta * sold0, s1 = q1 + beta * sold1, s2 = q2 + beta * sold2;
   d[0] = d0;
   d[1] = d1;
   d[2] = d2;
@@ -570,6 +617,15 @@ SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double 
   sv[1] = s1;
   sv[2] = s2;
   return vi0 * q0 + vi1 * q1 + vi2 * q2;
+}
+SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double beta) {
+  return schur_phaseB_row(g, lp, pose_row_meta(g, lp), lambda, beta);
+}
+// the rows lp0, lp0 + stride, ... of one thread
+SGB_HD double schur_phaseB_rows(const DevGraph& g, int lp0, int stride, double lambda, double beta) {
+  double acc = 0.0;
+  for (int lp = lp0; lp < g.nP; lp += stride) acc += schur_phaseB_row(g, lp, pose_row_meta(g, lp), lambda, beta);
+  return acc;
 }
 // z_i = Minv_i r_i ; returns r_i . z_i
 SGB_HD double precond_row(const DevGraph& g, int lp, const double r[3], double z[3]) {
