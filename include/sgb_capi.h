@@ -241,6 +241,104 @@ void sgb_g2o_view(const sgb_graph_file* f, sgb_graph_soa* out);
 void sgb_g2o_free(sgb_graph_file* f);
 sgb_status sgb_g2o_save(const char* path, const sgb_graph_soa* g);
 
+/* ---- device-resident graph values -------------------------------------------------------------
+ * sgb_set_graph with the VALUES (estimates, measurements, information matrices) already in device memory: the host
+ * symbolic phase only needs the index arrays of `indices` (n_*, ids, fixed flags, pp_i/pp_j, pl_pose/pl_lm, *_seq;
+ * its value pointers are ignored and may be NULL); the values are gathered on the device. Edge k of the index arrays
+ * reads its values from device slot pp_slot[k] / pl_slot[k] (HOST int arrays; NULL = slot k), so a store that keeps
+ * removed edges in place can hand over the active ones without compacting its value arrays. Single GPU. */
+typedef struct sgb_device_values {
+  const double* pose_est;   /* DEVICE [3*n_poses] */
+  const double* lm_est;     /* DEVICE [2*n_landmarks] */
+  const double* pp_z;       /* DEVICE [3*slots] */
+  const double* pp_info;    /* DEVICE [6*slots] */
+  const double* pp_phi;     /* DEVICE [slots] or NULL */
+  const int32_t* pp_slot;   /* HOST [n_pp] or NULL */
+  const double* pl_z;       /* DEVICE [2*slots] */
+  const double* pl_info;    /* DEVICE [3*slots] */
+  const int32_t* pl_slot;   /* HOST [n_pl] or NULL */
+  int32_t has_robust;       /* any pp_phi > 0 */
+  int32_t reserved;
+} sgb_device_values;
+sgb_status sgb_set_graph_device(sgb_handle* h, const sgb_graph_soa* indices, const sgb_device_values* dv);
+
+/* ---- the pose graph and its edits, on the device ----------------------------------------------
+ * Device-resident counterpart of the reference's PoseGraph (include/graphs.h:27-40: deque of pose + odometry edge,
+ * all_closures) with the three edits the reference makes around setup_pose_opt's optimiser, so that a loop closure
+ * costs an upload of ONE edge instead of the whole pose graph:
+ *   sgb_pg_append_from_lm   submap_loop_closer.cpp:206-223  copy the newly optimised landmark-graph poses: odometry
+ *                           edge measurement = (previous lm estimate)^-1 * (this lm estimate), information copied,
+ *                           new vertex estimate = previous pose-graph estimate * measurement (chained)
+ *   sgb_pg_add_closure      submap_loop_closer.cpp:272-285  EdgeSE2 between two existing vertices, DCS kernel
+ *   sgb_pg_optimize         submap_loop_closer.cpp:286-288 / log_runner.cpp:203-204  initializeOptimization +
+ *                           optimize(20): host symbolic phase on the store's index mirror, values gathered on the device
+ *   sgb_pg_prune_closures   log_runner.cpp:182-190  computeError + chi2() of every closure (no robust kernel);
+ *                           chi2 > threshold (11.345 in the reference) removes the edge
+ * Vertices are addressed by their position in the store (0 = the fixed first pose, drone.cpp:68-75). */
+typedef struct sgb_pose_graph sgb_pose_graph;
+sgb_status sgb_pg_create(int32_t device /* -1 = current */, sgb_pose_graph** out);
+void sgb_pg_destroy(sgb_pose_graph* pg);
+const char* sgb_pg_last_error(const sgb_pose_graph* pg);
+/* empties the store and adds the fixed first vertex */
+sgb_status sgb_pg_reset(sgb_pose_graph* pg, int32_t first_id, const double first_est[3]);
+/* lm: a handle whose graph is the landmark graph (estimates on the device); lm_first = array index of the first pose
+ * to copy (>= 1: its predecessor supplies the relative measurement), count poses are copied; ids (HOST, NULL =
+ * consecutive after the last id); info HOST [6*count] = upper triangles of the landmark graph's odometry edges */
+sgb_status sgb_pg_append_from_lm(sgb_pose_graph* pg, sgb_handle* lm, int32_t lm_first, int32_t count,
+                                 const int32_t* ids, const double* info);
+/* the same edit from HOST estimates ([3*(count+1)]: predecessor first) when the landmark graph lives elsewhere */
+sgb_status sgb_pg_append_from_host(sgb_pose_graph* pg, const double* lm_est, int32_t count, const int32_t* ids,
+                                   const double* info);
+sgb_status sgb_pg_add_closure(sgb_pose_graph* pg, int32_t from, int32_t to, const double z[3], const double info[6],
+                              double dcs_phi, int32_t* closure_index /* may be NULL */);
+/* solver: any handle on the same device (its previous graph is replaced); the optimised estimates are written back
+ * into the store on the device. iters_done / stats as in sgb_optimize. */
+sgb_status sgb_pg_optimize(sgb_pose_graph* pg, sgb_handle* solver, int32_t algo, int32_t max_iters,
+                           int32_t* iters_done, sgb_iter_stat* stats);
+/* chi2_out [n_closures] (may be NULL): chi2 of every closure ever added (removed ones: their chi2 when removed);
+ * active_out [n_closures] (may be NULL): 1 = still in the graph */
+sgb_status sgb_pg_prune_closures(sgb_pose_graph* pg, double threshold, int32_t* n_removed, double* chi2_out,
+                                 uint8_t* active_out);
+typedef struct sgb_pg_info {
+  int32_t n_poses, n_edges /* odometry + closures, removed ones included */, n_closures, n_active_closures;
+  double last_edit_ms;      /* device time of the kernels of the last edit (CUDA events) */
+  int64_t kernel_launches;  /* kernels launched by the store so far */
+} sgb_pg_info;
+sgb_status sgb_pg_get_info(const sgb_pose_graph* pg, sgb_pg_info* out);
+/* copies the store to the host; any pointer may be NULL. pp_* cover all n_edges slots in insertion order. */
+sgb_status sgb_pg_download(sgb_pose_graph* pg, int32_t* pose_id, double* pose_est, int32_t* pp_i, int32_t* pp_j,
+                           double* pp_z, double* pp_info, double* pp_phi, uint8_t* pp_active, uint8_t* pp_is_closure);
+
+/* ---- information-matrix producers as batch kernels --------------------------------------------
+ * Stateless: HOST buffers in and out, `device` = CUDA ordinal (-1 = current); kernel_ms (may be NULL) receives the
+ * device time of the kernels alone (CUDA events), the call itself includes the copies.
+ *
+ * sgb_odom_information: OdomErrorPropagator<double> (include/odom_error_propagator.h:18-46) run over n_seg key-frame
+ * intervals -- reset(), step() for every odometry delta of the interval (drone.cpp:84,143) -- giving per interval the
+ * odometry edge's measurement (accumulated pose, drone.cpp:127), the covariance and its inverse, the edge's
+ * information (drone.cpp:128). deltas [3*seg_ptr[n_seg]] (dx, dy, dtheta in the previous frame), seg_ptr [n_seg+1]. */
+sgb_status sgb_odom_information(int32_t device, const double* deltas, const int32_t* seg_ptr, int32_t n_seg,
+                                double std_x, double std_y, double std_w, double* z_out /* [3*n_seg] */,
+                                double* cov_out /* [9*n_seg] row-major, may be NULL */,
+                                double* info_out /* [6*n_seg] upper triangle */, double* kernel_ms);
+/* sgb_scan_point_covariances: the covariance of every scan point of a multi-scan window in the frame of the newest
+ * scan (src/multicloud2.cpp:56-83, single precision like the reference): n_windows windows of n_scans scans of
+ * scan_size beams. deltas [n_windows][n_scans-1][3] = odometry between consecutive scans (scan i is propagated through
+ * deltas i..n_scans-2); beam_cos_sin [2*scan_size]; pts [n_windows][n_scans][scan_size][2] (non-finite = no return).
+ * Out per point: cov [4] row-major, rhotheta [2], valid (0 for non-finite points, whose outputs are zero). */
+sgb_status sgb_scan_point_covariances(int32_t device, const double* deltas, int32_t n_windows, int32_t n_scans,
+                                      int32_t scan_size, const float* beam_cos_sin, const float* pts, float std_x,
+                                      float std_y, float std_w, float var_r, float* cov_out, float* rhotheta_out,
+                                      uint8_t* valid_out, double* kernel_ms);
+/* sgb_line_fit_information: LineSegment::leastSqFit (src/ls_extractor/src/impl/smc.cpp:30-68, single precision) for
+ * n_seg segments: rho/theta, its 2x2 covariance from the per-point covariances, and the pose-line edge information
+ * cov.cast<double>().inverse() (drone.cpp:203). pts [2*seg_ptr[n_seg]], pcov [4*...] row-major, seg_ptr [n_seg+1]. */
+sgb_status sgb_line_fit_information(int32_t device, const float* pts, const float* pcov, const int32_t* seg_ptr,
+                                    int32_t n_seg, float* rhotheta_out /* [2*n_seg] */, float* cov_out /* [4*n_seg] */,
+                                    double* info_out /* [3*n_seg] 11,12,22 */, double* kernel_ms);
+/* message of the last failure of a stateless call on this thread */
+const char* sgb_frontend_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

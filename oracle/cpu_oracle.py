@@ -36,9 +36,9 @@ class IterStat(C.Structure):
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libsgo_oracle.so")
-    src = os.path.join(_HERE, "sgo_oracle.cpp")
+    srcs = [os.path.join(_HERE, f) for f in ("sgo_oracle.cpp", "sgo_frontend.cpp", "sgo_oracle.h")]
     def stale():
-        return not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so))
+        return not os.path.exists(so) or any(os.path.exists(f) and os.path.getmtime(f) > os.path.getmtime(so) for f in srcs)
 
     if force or stale():
         import fcntl
@@ -207,3 +207,71 @@ class Oracle:
         o = np.zeros(4)
         self.L.sgo_last_profile(self.h, _p(o))
         return dict(nnzL=o[0], t_lin=o[1], t_solve=o[2], t_total=o[3])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# rows either side of the optimiser (oracle/sgo_frontend.cpp)
+def _f64(a):
+    return np.ascontiguousarray(a, np.float64)
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, np.int32)
+
+
+def pg_append(prev_pg_est, lm_est):
+    """submap_loop_closer.cpp:206-223. lm_est [(count+1), 3], predecessor first -> (z [count,3], est [count,3])."""
+    L = lib()
+    lm = _f64(lm_est).reshape(-1, 3)
+    count = lm.shape[0] - 1
+    z, est = np.zeros((count, 3)), np.zeros((count, 3))
+    prev = _f64(prev_pg_est)
+    L.sgo_pg_append(_p(prev), _p(lm), C.c_int32(count), _p(z), _p(est))
+    return z, est
+
+
+def closure_chi2(est, ei, ej, z, info6):
+    """log_runner.cpp:182-184: un-robustified chi2 of EdgeSE2 edges at `est`."""
+    L = lib()
+    est, ei, ej, z, info6 = _f64(est), _i32(ei), _i32(ej), _f64(z), _f64(info6)
+    out = np.zeros(len(ei))
+    L.sgo_closure_chi2(_p(est), _p(ei), _p(ej), _p(z), _p(info6), C.c_int32(len(ei)), _p(out))
+    return out
+
+
+def odom_information(deltas, seg_ptr, std_x, std_y, std_w):
+    L = lib()
+    deltas, seg_ptr = _f64(deltas), _i32(seg_ptr)
+    n = len(seg_ptr) - 1
+    z, cov, info = np.zeros((n, 3)), np.zeros((n, 3, 3)), np.zeros((n, 6))
+    L.sgo_odom_information(_p(deltas), _p(seg_ptr), C.c_int32(n), C.c_double(std_x), C.c_double(std_y), C.c_double(std_w),
+                           _p(z), _p(cov), _p(info))
+    return z, cov, info
+
+
+def scan_point_covariances(deltas, beam_cos_sin, pts, std_x, std_y, std_w, var_r):
+    """pts [n_windows, n_scans, scan_size, 2] float32; deltas [n_windows, n_scans-1, 3]."""
+    L = lib()
+    pts = _f32(pts)
+    nw, ns, sz = pts.shape[:3]
+    deltas, beam = _f64(deltas), _f32(beam_cos_sin)
+    cov = np.zeros((nw, ns, sz, 4), np.float32)
+    rt = np.zeros((nw, ns, sz, 2), np.float32)
+    valid = np.zeros((nw, ns, sz), np.uint8)
+    L.sgo_scan_point_covariances(_p(deltas), C.c_int32(nw), C.c_int32(ns), C.c_int32(sz), _p(beam), _p(pts),
+                                 C.c_float(std_x), C.c_float(std_y), C.c_float(std_w), C.c_float(var_r), _p(cov), _p(rt),
+                                 _p(valid))
+    return cov, rt, valid
+
+
+def line_fit_information(pts, pcov, seg_ptr):
+    L = lib()
+    pts, pcov, seg_ptr = _f32(pts), _f32(pcov), _i32(seg_ptr)
+    n = len(seg_ptr) - 1
+    rt, cov, info = np.zeros((n, 2), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 3))
+    L.sgo_line_fit_information(_p(pts), _p(pcov), _p(seg_ptr), C.c_int32(n), _p(rt), _p(cov), _p(info))
+    return rt, cov, info

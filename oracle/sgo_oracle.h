@@ -111,6 +111,23 @@ int sgo_solve_once(sgo_handle*, int jac_mode, double lambda, double* x);
 /* timing / diagnostics of the last optimize: factor nnz, seconds in linearise / factor+solve */
 void sgo_last_profile(sgo_handle*, double* out /*[4]: nnzL, t_lin, t_solve, t_total*/);
 
+/* ---- rows either side of the optimiser (oracle/sgo_frontend.cpp) ---- */
+/* submap_loop_closer.cpp:206-223; lm_est [3*(count+1)] predecessor first; z_out / est_out [3*count] */
+void sgo_pg_append(const double* prev_pg_est, const double* lm_est, int32_t count, double* z_out, double* est_out);
+/* log_runner.cpp:182-184; per edge k: vertices ei[k], ej[k], z [3*n], info6 [6*n] */
+void sgo_closure_chi2(const double* est, const int32_t* ei, const int32_t* ej, const double* z, const double* info6,
+                      int32_t n, double* chi_out);
+/* odom_error_propagator.h + drone.cpp:84,127-128,143 */
+void sgo_odom_information(const double* deltas, const int32_t* seg_ptr, int32_t n_seg, double std_x, double std_y,
+                          double std_w, double* z_out, double* cov_out /* may be NULL */, double* info_out);
+/* multicloud2.cpp:56-83 */
+void sgo_scan_point_covariances(const double* deltas, int32_t n_windows, int32_t n_scans, int32_t scan_size,
+                                const float* beam_cos_sin, const float* pts, float std_x, float std_y, float std_w,
+                                float var_r, float* cov_out, float* rhotheta_out, uint8_t* valid_out);
+/* smc.cpp:30-68 + drone.cpp:203 */
+void sgo_line_fit_information(const float* pts, const float* pcov, const int32_t* seg_ptr, int32_t n_seg,
+                              float* rhotheta_out, float* cov_out, double* info_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,8 @@ recipe. Importing the package does not need a GPU; creating an optimiser does, a
 from . import capi, graphgen  # noqa: F401
 from .capi import ALGO_GN, ALGO_LM, JAC_ANALYTIC, JAC_G2O_NUMERIC  # noqa: F401
 from .optimizer import SgbError, SparseOptimizerB200  # noqa: F401
+from .posegraph import PoseGraphB200  # noqa: F401
+from . import frontend  # noqa: F401
 
-__all__ = ["capi", "graphgen", "SparseOptimizerB200", "SgbError", "ALGO_LM", "ALGO_GN", "JAC_G2O_NUMERIC",
+__all__ = ["capi", "graphgen", "frontend", "SparseOptimizerB200", "PoseGraphB200", "SgbError", "ALGO_LM", "ALGO_GN", "JAC_G2O_NUMERIC",
            "JAC_ANALYTIC"]

@@ -12,8 +12,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsgb.so")
-SOURCES = ["sgb_backend.cu", "sgb_structure.cpp", "sgb_partition.cpp", "sgb_g2o_io.cpp"]
-HEADERS = ["sgb_kernels.cuh", "sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h", "sgb_partition.h", "../../include/sgb_capi.h"]
+SOURCES = ["sgb_backend.cu", "sgb_posegraph.cu", "sgb_frontend.cu", "sgb_structure.cpp", "sgb_partition.cpp", "sgb_g2o_io.cpp"]
+HEADERS = ["sgb_kernels.cuh", "sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h", "sgb_partition.h", "sgb_edits.h", "sgb_internal.h", "../../include/sgb_capi.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
               "-shared"]
 

@@ -19,6 +19,10 @@ EXPORTS = [
     "sgb_get_timings", "sgb_optimize_resident", "sgb_set_graph_partitioned", "sgb_comm_get_handle", "sgb_comm_connect",
     "sgb_get_partition_info", "sgb_optimize_batch", "sgb_optimize_batch_resident", "sgb_g2o_load", "sgb_g2o_view",
     "sgb_g2o_free", "sgb_g2o_save",
+    "sgb_set_graph_device", "sgb_pg_create", "sgb_pg_destroy", "sgb_pg_last_error", "sgb_pg_reset",
+    "sgb_pg_append_from_lm", "sgb_pg_append_from_host", "sgb_pg_add_closure", "sgb_pg_optimize",
+    "sgb_pg_prune_closures", "sgb_pg_get_info", "sgb_pg_download",
+    "sgb_odom_information", "sgb_scan_point_covariances", "sgb_line_fit_information", "sgb_frontend_last_error",
 ]
 
 
@@ -76,6 +80,20 @@ class PartitionInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class DeviceValues(C.Structure):
+    _fields_ = [("pose_est", C.c_void_p), ("lm_est", C.c_void_p), ("pp_z", C.c_void_p), ("pp_info", C.c_void_p),
+                ("pp_phi", C.c_void_p), ("pp_slot", C.c_void_p), ("pl_z", C.c_void_p), ("pl_info", C.c_void_p),
+                ("pl_slot", C.c_void_p), ("has_robust", C.c_int32), ("reserved", C.c_int32)]
+
+
+class PgInfo(C.Structure):
+    _fields_ = [("n_poses", C.c_int32), ("n_edges", C.c_int32), ("n_closures", C.c_int32),
+                ("n_active_closures", C.c_int32), ("last_edit_ms", C.c_double), ("kernel_launches", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
 _lib = None
 
 
@@ -120,5 +138,24 @@ def load() -> C.CDLL:
     L.sgb_g2o_view.argtypes = [vp, C.POINTER(GraphSoA)]
     L.sgb_g2o_free.argtypes = [vp]
     L.sgb_g2o_save.argtypes = [C.c_char_p, C.POINTER(GraphSoA)]
+    L.sgb_set_graph_device.argtypes = [vp, C.POINTER(GraphSoA), C.POINTER(DeviceValues)]
+    L.sgb_pg_create.argtypes = [C.c_int32, C.POINTER(vp)]
+    L.sgb_pg_destroy.argtypes = [vp]
+    L.sgb_pg_last_error.argtypes = [vp]
+    L.sgb_pg_last_error.restype = C.c_char_p
+    L.sgb_pg_reset.argtypes = [vp, C.c_int32, vp]
+    L.sgb_pg_append_from_lm.argtypes = [vp, vp, C.c_int32, C.c_int32, vp, vp]
+    L.sgb_pg_append_from_host.argtypes = [vp, vp, C.c_int32, vp, vp]
+    L.sgb_pg_add_closure.argtypes = [vp, C.c_int32, C.c_int32, vp, vp, C.c_double, C.POINTER(C.c_int32)]
+    L.sgb_pg_optimize.argtypes = [vp, vp, C.c_int32, C.c_int32, C.POINTER(C.c_int32), vp]
+    L.sgb_pg_prune_closures.argtypes = [vp, C.c_double, C.POINTER(C.c_int32), vp, vp]
+    L.sgb_pg_get_info.argtypes = [vp, C.POINTER(PgInfo)]
+    L.sgb_pg_download.argtypes = [vp] + [vp] * 9
+    L.sgb_odom_information.argtypes = [C.c_int32, vp, vp, C.c_int32, C.c_double, C.c_double, C.c_double, vp, vp, vp,
+                                       C.POINTER(C.c_double)]
+    L.sgb_scan_point_covariances.argtypes = [C.c_int32, vp, C.c_int32, C.c_int32, C.c_int32, vp, vp, C.c_float, C.c_float,
+                                             C.c_float, C.c_float, vp, vp, vp, C.POINTER(C.c_double)]
+    L.sgb_line_fit_information.argtypes = [C.c_int32, vp, vp, vp, C.c_int32, vp, vp, vp, C.POINTER(C.c_double)]
+    L.sgb_frontend_last_error.restype = C.c_char_p
     _lib = L
     return L

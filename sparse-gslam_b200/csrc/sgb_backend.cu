@@ -17,6 +17,7 @@
 #include <vector>
 
 #include "../../include/sgb_capi.h"
+#include "sgb_internal.h"
 #include "sgb_kernels.cuh"
 #include "sgb_partition.h"
 #include "sgb_structure.h"
@@ -511,8 +512,47 @@ static void fill_peer_tables(sgb_handle* h) {
   }
 }
 
-static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int world, int rank) {
-  if (!h || !g) return SGB_ERR_INVALID;
+// Edge values that already live on the device (sgb_set_graph_device): gather them into the component-major local-edge
+// arrays, one thread per local edge; EdgeSE2::setMeasurement's cached inverse is formed here as on the host path.
+__global__ void __launch_bounds__(kThreads) k_gather_pp(const int32_t* __restrict__ slot, int n, const double* __restrict__ z,
+                                                       const double* __restrict__ info, const double* __restrict__ phi,
+                                                       double* __restrict__ zinv_o, double* __restrict__ info_o,
+                                                       double* __restrict__ phi_o) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    size_t s = (size_t)slot[k];
+    double x = z[3 * s], y = z[3 * s + 1], th = z[3 * s + 2];
+    double thi = normalize_theta(-th);
+    double c = cos(thi), sn = sin(thi);
+    zinv_o[k] = c * (-x) - sn * (-y);
+    zinv_o[(size_t)n + k] = sn * (-x) + c * (-y);
+    zinv_o[2 * (size_t)n + k] = thi;
+    for (int c6 = 0; c6 < 6; ++c6) info_o[(size_t)c6 * n + k] = info[6 * s + c6];
+    phi_o[k] = phi ? phi[s] : 0.0;
+  }
+}
+__global__ void __launch_bounds__(kThreads) k_gather_pl(const int32_t* __restrict__ slot, int n, const double* __restrict__ z,
+                                                       const double* __restrict__ info, double* __restrict__ z_o,
+                                                       double* __restrict__ info_o) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    size_t s = (size_t)slot[k];
+    z_o[k] = z[2 * s];
+    z_o[(size_t)n + k] = z[2 * s + 1];
+    for (int c3 = 0; c3 < 3; ++c3) info_o[(size_t)c3 * n + k] = info[3 * s + c3];
+  }
+}
+
+static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int world, int rank,
+                                 const sgb_device_values* dv = nullptr) {
+  if (!h || !g_in) return SGB_ERR_INVALID;
+  // device-resident values: the host symbolic phase only reads the index arrays; give it non-NULL value pointers
+  // (never dereferenced on the host) so that its argument checks are the same on both paths
+  sgb_graph_soa g_local = *g_in;
+  if (dv) {
+    g_local.pose_est = dv->pose_est; g_local.lm_est = dv->lm_est;
+    g_local.pp_z = dv->pp_z; g_local.pp_info = dv->pp_info; g_local.pp_phi = nullptr;
+    g_local.pl_z = dv->pl_z; g_local.pl_info = dv->pl_info;
+  }
+  const sgb_graph_soa* g = &g_local;
   static const bool prof = std::getenv("SGB_PROFILE") != nullptr;  // per-phase host timing of this call on stderr
   auto tp0 = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -528,6 +568,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   sgb_status st = build_structure(*g, h->S, h->err);
   if (st != SGB_OK) return st;
   lap("build_structure");
+  if (dv && dv->has_robust) h->S.has_robust = true;
   st = partition(h->S, world, rank, h->LP, h->err);
   if (st != SGB_OK) return st;
   lap("partition");
@@ -560,12 +601,14 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   if ((st = dalloc(h, &h->d_pose0, np)) != SGB_OK) return st;
   if ((st = dalloc(h, &h->d_lm0, nl)) != SGB_OK) return st;
   if (np) {
-    if ((st = h2d(h, h->d_pose0, g->pose_est, np * sizeof(double))) != SGB_OK) return st;
+    if (dv) SGB_CUDA(cudaMemcpyAsync(h->d_pose0, dv->pose_est, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    else if ((st = h2d(h, h->d_pose0, g->pose_est, np * sizeof(double))) != SGB_OK) return st;
     for (int bsel = 0; bsel < 2; ++bsel)
       SGB_CUDA(cudaMemcpyAsync(G.pose_buf[bsel][rank], h->d_pose0, np * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   }
   if (nl) {
-    if ((st = h2d(h, h->d_lm0, g->lm_est, nl * sizeof(double))) != SGB_OK) return st;
+    if (dv) SGB_CUDA(cudaMemcpyAsync(h->d_lm0, dv->lm_est, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    else if ((st = h2d(h, h->d_lm0, g->lm_est, nl * sizeof(double))) != SGB_OK) return st;
     for (int bsel = 0; bsel < 2; ++bsel)
       SGB_CUDA(cudaMemcpyAsync(G.lm_buf[bsel][rank], h->d_lm0, nl * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
   }
@@ -573,11 +616,37 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   // edge data, component-major, local edges; EdgeSE2::setMeasurement caches the inverse. The SoA transposes run on
   // host threads while this thread uploads the symbolic maps.
   std::vector<double>&zinv = h->e_zinv, &info = h->e_info, &phi = h->e_phi, &z = h->e_z, &linfo = h->e_linfo;
-  zinv.resize(3 * (size_t)P.n_pp);
-  info.resize(6 * (size_t)P.n_pp);
-  phi.resize(P.n_pp);
-  z.resize(2 * (size_t)P.n_pl);
-  linfo.resize(3 * (size_t)P.n_pl);
+  if (dv) {  // values stay on the device: upload only the slot of every local edge and gather there
+    std::vector<int32_t> slot_pp(P.n_pp), slot_pl(P.n_pl);
+    for (int k = 0; k < P.n_pp; ++k) {
+      int s = S.pp_src[P.pp_g[k]];
+      slot_pp[k] = dv->pp_slot ? dv->pp_slot[s] : s;
+    }
+    for (int k = 0; k < P.n_pl; ++k) {
+      int s = S.pl_src[P.pl_g[k]];
+      slot_pl[k] = dv->pl_slot ? dv->pl_slot[s] : s;
+    }
+    const int32_t *d_spp = nullptr, *d_spl = nullptr;
+    double *d_zinv = nullptr, *d_info = nullptr, *d_phi = nullptr, *d_z = nullptr, *d_linfo = nullptr;
+    if ((st = upload(h, &d_spp, slot_pp)) != SGB_OK) return st;
+    if ((st = upload(h, &d_spl, slot_pl)) != SGB_OK) return st;
+    if ((st = dalloc(h, &d_zinv, 3 * (size_t)P.n_pp)) != SGB_OK) return st;
+    if ((st = dalloc(h, &d_info, 6 * (size_t)P.n_pp)) != SGB_OK) return st;
+    if ((st = dalloc(h, &d_phi, (size_t)P.n_pp)) != SGB_OK) return st;
+    if ((st = dalloc(h, &d_z, 2 * (size_t)P.n_pl)) != SGB_OK) return st;
+    if ((st = dalloc(h, &d_linfo, 3 * (size_t)P.n_pl)) != SGB_OK) return st;
+    if (P.n_pp > 0) k_gather_pp<<<grid_for(P.n_pp), kThreads, 0, h->stream>>>(d_spp, P.n_pp, dv->pp_z, dv->pp_info, dv->pp_phi, d_zinv, d_info, d_phi);
+    if (P.n_pl > 0) k_gather_pl<<<grid_for(P.n_pl), kThreads, 0, h->stream>>>(d_spl, P.n_pl, dv->pl_z, dv->pl_info, d_z, d_linfo);
+    SGB_CUDA(cudaGetLastError());
+    G.pp_zinv = d_zinv; G.pp_info = d_info; G.pp_phi = d_phi; G.pl_z = d_z; G.pl_info = d_linfo;
+    SGB_CUDA(cudaStreamSynchronize(h->stream));  // slot_pp / slot_pl are locals
+  }
+  const size_t h_pp = dv ? 0 : (size_t)P.n_pp, h_pl = dv ? 0 : (size_t)P.n_pl;  // edges whose values come from the host
+  zinv.resize(3 * h_pp);
+  info.resize(6 * h_pp);
+  phi.resize(h_pp);
+  z.resize(2 * h_pl);
+  linfo.resize(3 * h_pl);
   auto fill_pp = [&](int k0, int k1) {
     for (int k = k0; k < k1; ++k) {
       int s = S.pp_src[P.pp_g[k]];
@@ -601,8 +670,10 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   };
   std::vector<std::thread> workers;
   {
-    const int nth = ((size_t)P.n_pp + P.n_pl > 200000) ? (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 0;
-    if (nth == 0) {
+    const int nth = (h_pp + h_pl > 200000) ? (int)std::min(8u, std::max(1u, std::thread::hardware_concurrency() / 2)) : 0;
+    if (dv) {
+      // nothing to transpose on the host
+    } else if (nth == 0) {
       fill_pp(0, P.n_pp);
       fill_pl(0, P.n_pl);
     } else {
@@ -628,8 +699,10 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
   lap("upload maps");
   for (auto& t : workers) t.join();
   workers.clear();
-  UP(pp_zinv, zinv); UP(pp_info, info); UP(pp_phi, phi);
-  UP(pl_z, z); UP(pl_info, linfo);
+  if (!dv) {
+    UP(pp_zinv, zinv); UP(pp_info, info); UP(pp_phi, phi);
+    UP(pl_z, z); UP(pl_info, linfo);
+  }
 #undef UP
   lap("edge data");
   if ((st = upload_sell(h, &G.Hpp, P.Hpp, 9)) != SGB_OK) return st;
@@ -659,6 +732,16 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g, int worl
 }
 
 sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g) { return set_graph_impl(h, g, 1, 0); }
+
+sgb_status sgb_set_graph_device(sgb_handle* h, const sgb_graph_soa* indices, const sgb_device_values* dv) {
+  if (!h || !indices || !dv) return SGB_ERR_INVALID;
+  if ((indices->n_poses > 0 && !dv->pose_est) || (indices->n_landmarks > 0 && !dv->lm_est) ||
+      (indices->n_pp > 0 && (!dv->pp_z || !dv->pp_info)) || (indices->n_pl > 0 && (!dv->pl_z || !dv->pl_info))) {
+    h->err = "sgb_set_graph_device: missing device value array";
+    return SGB_ERR_INVALID;
+  }
+  return set_graph_impl(h, indices, 1, 0, dv);
+}
 
 sgb_status sgb_set_graph_partitioned(sgb_handle* h, const sgb_graph_soa* g, int32_t world, int32_t rank) {
   return set_graph_impl(h, g, world, rank);
@@ -1067,3 +1150,19 @@ sgb_status sgb_get_timings(const sgb_handle* h, sgb_timings* out) {
 }
 
 }  // extern "C"
+
+namespace sgb {
+bool handle_view(sgb_handle* h, HandleView* out) {
+  if (!h || !h->has_graph) return false;
+  out->device = h->device;
+  out->stream = h->stream;
+  out->n_poses = h->S.P_all;
+  out->n_landmarks = h->S.L_all;
+  out->pose_est = h->G.pose_buf[h->G.cur][h->G.rank];
+  out->lm_est = h->G.lm_buf[h->G.cur][h->G.rank];
+  return true;
+}
+void handle_set_error(sgb_handle* h, const std::string& msg) {
+  if (h) h->err = msg;
+}
+}  // namespace sgb

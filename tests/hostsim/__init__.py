@@ -18,10 +18,10 @@ _lib = None
 
 def build():
     csrc = os.path.join(ROOT, "sparse-gslam_b200", "csrc")
-    srcs = [os.path.join(HERE, "hostsim.cpp"), os.path.join(csrc, "sgb_structure.cpp"),
-            os.path.join(csrc, "sgb_partition.cpp")]
+    srcs = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "hostsim_edits.cpp"),
+            os.path.join(csrc, "sgb_structure.cpp"), os.path.join(csrc, "sgb_partition.cpp")]
     deps = srcs + [os.path.join(csrc, f) for f in
-                   ("sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h", "sgb_partition.h")]
+                   ("sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h", "sgb_partition.h", "sgb_edits.h")]
     def fresh():
         return os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps)
 
@@ -56,6 +56,12 @@ def lib():
         L.hs_check_hlp.argtypes = [vp]
         L.hs_check_hlp.restype = C.c_double
         L.hs_chi2.argtypes = [vp, vp]
+        L.hs_pg_append.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+        L.hs_closure_chi2.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
+        L.hs_odom_information.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_double, vp, vp, vp]
+        L.hs_scan_point_covariances.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float,
+                                                C.c_float, vp, vp, vp]
+        L.hs_line_fit_information.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -129,3 +135,51 @@ class HostSim:
         c = np.zeros(2)
         self.L.hs_chi2(self.h, _p(c))
         return float(c[0]), float(c[1])
+
+
+# ---- bodies of sgb_edits.h with the kernels' work decomposition (hostsim_edits.cpp)
+def _c(a, dt):
+    return np.ascontiguousarray(a, dt)
+
+
+def pg_append(prev, lm_est, threads=512):
+    lm = _c(lm_est, np.float64).reshape(-1, 3)
+    n = lm.shape[0] - 1
+    z, est = np.zeros((n, 3)), np.zeros((n, 3))
+    prev = _c(prev, np.float64)
+    lib().hs_pg_append(_p(prev), _p(lm), n, threads, _p(z), _p(est))
+    return z, est
+
+
+def closure_chi2(est, ei, ej, z, info6):
+    est, ei, ej, z, info6 = _c(est, np.float64), _c(ei, np.int32), _c(ej, np.int32), _c(z, np.float64), _c(info6, np.float64)
+    out = np.zeros(len(ei))
+    lib().hs_closure_chi2(_p(est), _p(ei), _p(ej), _p(z), _p(info6), len(ei), _p(out))
+    return out
+
+
+def odom_information(deltas, seg_ptr, std_x, std_y, std_w):
+    deltas, seg_ptr = _c(deltas, np.float64), _c(seg_ptr, np.int32)
+    n = len(seg_ptr) - 1
+    z, cov, info = np.zeros((n, 3)), np.zeros((n, 3, 3)), np.zeros((n, 6))
+    lib().hs_odom_information(_p(deltas), _p(seg_ptr), n, std_x, std_y, std_w, _p(z), _p(cov), _p(info))
+    return z, cov, info
+
+
+def scan_point_covariances(deltas, beam, pts, std_x, std_y, std_w, var_r):
+    pts = _c(pts, np.float32)
+    nw, ns, sz = pts.shape[:3]
+    deltas, beam = _c(deltas, np.float64), _c(beam, np.float32)
+    cov, rt = np.zeros((nw, ns, sz, 4), np.float32), np.zeros((nw, ns, sz, 2), np.float32)
+    valid = np.zeros((nw, ns, sz), np.uint8)
+    lib().hs_scan_point_covariances(_p(deltas), nw, ns, sz, _p(beam), _p(pts), std_x, std_y, std_w, var_r, _p(cov), _p(rt),
+                                    _p(valid))
+    return cov, rt, valid
+
+
+def line_fit_information(pts, pcov, seg_ptr):
+    pts, pcov, seg_ptr = _c(pts, np.float32), _c(pcov, np.float32), _c(seg_ptr, np.int32)
+    n = len(seg_ptr) - 1
+    rt, cov, info = np.zeros((n, 2), np.float32), np.zeros((n, 4), np.float32), np.zeros((n, 3))
+    lib().hs_line_fit_information(_p(pts), _p(pcov), _p(seg_ptr), n, _p(rt), _p(cov), _p(info))
+    return rt, cov, info
