@@ -52,6 +52,13 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.t_mark = None
+
+    def mark(self):
+        """Start of the timed region: nvidia-smi needs ~0.5 s to come up, so the sampler is started during the warm-up
+        and only the samples that arrive after mark() are reported (if a very short timed region saw none, the last
+        warm-up samples -- same kernels, same load -- are used and the fact is recorded)."""
+        self.t_mark = time.perf_counter()
 
     def start(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
@@ -68,7 +75,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -80,7 +87,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        window = "timed region"
+        lines = [ln for (t, ln) in self.lines if self.t_mark is None or t >= self.t_mark]
+        if len(lines) < 2 and self.t_mark is not None:
+            lines = [ln for (_, ln) in self.lines[-5:]]
+            window = "timed region + end of warm-up (timed region shorter than the sampling period)"
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
                 continue
@@ -93,7 +105,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": float(np.max(mx)) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
 def make_workload(name, rank=0, world=1):
@@ -388,6 +400,113 @@ def run_stream(args, warmup):
     print(json.dumps(line))
 
 
+def run_edits(args, warmup):
+    """SURVEY.md 8f N3 + N4 at the size of the C5 graph: the producers of its information matrices (1M odometry
+    intervals, 1M line segments, 3.6M scan points) and the pose-graph copy of its 1M-pose chain, each through the C ABI
+    with HOST buffers (e2e) and with the device time of the kernels alone (resident). Units = information matrices
+    (odometry + pose-line edges), point covariances and re-measured poses produced per second. The CPU oracle runs the
+    same rows on a 1/20 sample, one thread like the reference."""
+    from oracle import cpu_oracle as co
+    from sparse_gslam_b200 import frontend as fe
+    from sparse_gslam_b200.posegraph import PoseGraphB200
+    rng = np.random.default_rng(5)
+    n_kf, steps_per_kf = 1_000_000, 10
+    deltas = np.stack([0.05 + 0.01 * rng.normal(size=n_kf * steps_per_kf), 0.002 * rng.normal(size=n_kf * steps_per_kf),
+                       0.01 * rng.normal(size=n_kf * steps_per_kf)], 1)
+    seg = (np.arange(n_kf + 1) * steps_per_kf).astype(np.int32)
+    n_seg, ppl = 1_000_000, 16
+    t = np.tile(np.linspace(-1.0, 1.0, ppl), n_seg)
+    th = np.repeat(rng.uniform(-np.pi, np.pi, n_seg), ppl)
+    rho = np.repeat(rng.uniform(0.5, 5.0, n_seg), ppl)
+    lpts = np.stack([rho * np.cos(th) - t * np.sin(th), rho * np.sin(th) + t * np.cos(th)], 1)
+    lpts = (lpts + 0.01 * rng.normal(size=lpts.shape)).astype(np.float32)
+    lcov = np.tile(np.array([1e-4, 1e-5, 1e-5, 2e-4], np.float32), (n_seg * ppl, 1))
+    lseg = (np.arange(n_seg + 1) * ppl).astype(np.int32)
+    nw, ns, sz = 1000, 10, 360
+    ang = np.linspace(-np.pi, np.pi, sz, endpoint=False)
+    beam = np.stack([np.cos(ang), np.sin(ang)], 1).astype(np.float32)
+    sdel = np.stack([0.05 + 0.01 * rng.normal(size=(nw, ns - 1)), 0.002 * rng.normal(size=(nw, ns - 1)),
+                     0.01 * rng.normal(size=(nw, ns - 1))], -1)
+    r = rng.uniform(0.5, 5.0, size=(nw, ns, sz)).astype(np.float32)
+    spts = np.stack([r * beam[:, 0], r * beam[:, 1]], -1).astype(np.float32)
+    d = np.stack([0.5 + 0.02 * rng.normal(size=n_kf), 0.02 * rng.normal(size=n_kf), 0.2 * rng.normal(size=n_kf)], 1)
+    a = np.concatenate([[0.3], 0.3 + np.cumsum(d[:, 2])])
+    chain = np.stack([np.concatenate([[0.0], np.cumsum(d[:, 0] * np.cos(a[:-1]) - d[:, 1] * np.sin(a[:-1]))]),
+                      np.concatenate([[0.0], np.cumsum(d[:, 0] * np.sin(a[:-1]) + d[:, 1] * np.cos(a[:-1]))]),
+                      a - 2 * np.pi * np.floor((a + np.pi) / (2 * np.pi))], 1)
+    cinfo = np.tile(np.array([2500.0, 0, 0, 2500.0, 0, 1e4]), (n_kf, 1))
+    pg = PoseGraphB200()
+
+    def chain_copy():
+        pg.reset(chain[0], 0)
+        pg.append_from_host(chain, cinfo)
+        return pg.info()["last_edit_ms"]
+
+    # algorithmic bytes per unit (each array once): see DESIGN.md section 8
+    rows = [
+        ("k_odom_information", n_kf, 24 * steps_per_kf + 4 + 24 + 72 + 48,
+         lambda: fe.odom_information(deltas, seg, 0.02, 0.02, 0.01)[3],
+         lambda k: co.odom_information(deltas[:k * steps_per_kf], seg[:k + 1], 0.02, 0.02, 0.01)),
+        ("k_line_fit", n_seg, 24 * ppl + 4 + 8 + 16 + 24,
+         lambda: fe.line_fit_information(lpts, lcov, lseg)[3],
+         lambda k: co.line_fit_information(lpts[:k * ppl], lcov[:k * ppl], lseg[:k + 1])),
+        ("k_scan_frames+k_scan_points", nw * ns * sz, 8 + 16 + 8 + 1,
+         lambda: fe.scan_point_covariances(sdel, beam, spts, 0.02, 0.02, 0.01, 9e-4)[3],
+         lambda k: co.scan_point_covariances(sdel[:max(1, k // (ns * sz))], beam, spts[:max(1, k // (ns * sz))], 0.02, 0.02, 0.01, 9e-4)),
+        ("k_pg_remeasure+k_pg_chain", n_kf, 24 + 24 + 24 + 24,
+         chain_copy,
+         lambda k: co.pg_append(chain[0], chain[:k + 1])),
+    ]
+    peak, peak_src = measured_peaks()
+    sampler = ClockSampler(0)
+    sampler.start()
+    for _ in range(warmup):
+        for (_, _, _, f, _) in rows:
+            f()
+    sampler.mark()
+    out, tot_units, tot_wall, tot_kernel = [], 0, 0.0, 0.0
+    for (name, units, bpu, f, cpu) in rows:
+        kms, wall = 0.0, 0.0
+        for _ in range(args.steps):
+            t0 = time.perf_counter()
+            kms += f()
+            wall += time.perf_counter() - t0
+        kms /= args.steps
+        wall /= args.steps
+        gbs = units * bpu / (kms * 1e-3) / 1e9
+        rec = {"kernel": name, "units": units, "kernel_ms": kms, "e2e_ms": 1e3 * wall, "units_per_s": units / (kms * 1e-3),
+               "e2e_units_per_s": units / wall, "algorithmic_bytes_per_unit": bpu, "achieved_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+        if not args.no_cpu_baseline:
+            k = max(1, units // 20)
+            t0 = time.perf_counter()
+            cpu(k)
+            rec["cpu_units_per_s"] = k / (time.perf_counter() - t0)
+        out.append(rec)
+        tot_units += units
+        tot_wall += wall
+        tot_kernel += kms * 1e-3
+    clocks = sampler.stop()
+    top = max(out, key=lambda r: r["kernel_ms"])
+    line = {"metric": "producer + edit rows/s", "value": tot_units / tot_kernel, "unit": "rows/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": 1e3 * tot_kernel, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 (odometry, pose chain) / f32 (scan points, line fit: the reference's types)", "data": "synthetic",
+            "config": {"workload": "N3+N4 rows at C5 size: 1M odometry intervals x 10 deltas, 1M line segments x 16 points, "
+                                   "1000 windows x 10 scans x 360 beams, copy of a 1M-pose chain into the pose graph",
+                       "l2": "inputs larger than L2 except the scan points (29 MB)"},
+            "kernels": out, "gpu_launches": 6 * args.steps, "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": top["kernel"], "achieved": top["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                         "frac": top["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src},
+            "e2e": {"value": tot_units / tot_wall, "unit": "rows/s",
+                    "h2d_bytes_per_step": int(deltas.nbytes + seg.nbytes + lpts.nbytes + lcov.nbytes + lseg.nbytes + sdel.nbytes +
+                                              spts.nbytes + beam.nbytes + chain.nbytes + cinfo.nbytes),
+                    "d2h_bytes_per_step": int(n_kf * (24 + 72 + 48) + n_seg * (8 + 16 + 24) + nw * ns * sz * 25)}}
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = {"value": sum(r["units"] for r in out) / sum(r["units"] / r["cpu_units_per_s"] for r in out),
+                                "unit": "rows/s", "cores": 1, "kind": "port",
+                                "sample": "the first 1/20 of every row's input on the CPU oracle (oracle/sgo_frontend.cpp)"}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,6 +553,12 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    if args.workload.lower() == "edits":
+        if rank == 0:
+            run_edits(args, warmup)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     if args.workload.lower() == "c4":
         run_c4(args, rank, world, local_rank, warmup)
         if world > 1:
@@ -467,11 +592,12 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- resident (device-timed) ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(warmup):
         opt.optimize(iters, resident=True)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
+    sampler.mark()
     tot_iters = 0
     agg = dict(linearize_ms=0.0, setup_ms=0.0, pcg_ms=0.0, update_ms=0.0, total_ms=0.0, pcg_iters=0, trials=0,
                linearizations=0, kernel_launches=0)
@@ -479,6 +605,7 @@ def main():
     wall0 = time.perf_counter()
     for _ in range(args.steps):
         n, stats = opt.optimize(iters, resident=True)
+        last_stats = stats
         tot_iters += max(n, 0)
         t = opt.timings()
         for k in agg:
@@ -543,7 +670,10 @@ def main():
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_pcg_iteration": b_iter, "pcg_iterations": agg["pcg_iters"],
                 "pcg_launches": agg["trials"], "share_of_step": agg["pcg_ms"] / dev_ms if dev_ms > 0 else None,
-                "pcg_phase_us_per_iteration": [1e3 * v / max(1, agg["pcg_iters"]) for v in pcg_phase]}
+                "pcg_phase_us_per_iteration": [1e3 * v / max(1, agg["pcg_iters"]) for v in pcg_phase],
+                # PCG iterations of every k_pcg launch of one step, in launch order (maps an ncu capture of launch #k
+                # to its algorithmic bytes)
+                "pcg_iterations_per_lm_iteration": [int(x["pcg_iters"]) for x in last_stats]}
     line = {
         "metric": "LM iterations/s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": dev_ms_max / max(1, args.steps), "higher_is_better": True,
