@@ -184,10 +184,30 @@ SGB_HD void check_rho_theta_f(float rt[2]) {  // ls_extractor/utils.h:23-30
     if (rt[1] > pi) rt[1] -= 2.0f * pi;
   }
 }
+struct F2 { float x, y; };
+struct F4 { float a, b, c, d; };
+// one 8-byte / 16-byte load per point / per covariance (pts is 8-byte, pcov 16-byte aligned: segment offsets are whole points)
+SGB_HD F2 ld_pt(const float* p) {
+#if defined(__CUDA_ARCH__)
+  float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return F2{v.x, v.y};
+#else
+  return F2{p[0], p[1]};
+#endif
+}
+SGB_HD F4 ld_cov(const float* p) {
+#if defined(__CUDA_ARCH__)
+  float4 v = __ldg(reinterpret_cast<const float4*>(p));
+  return F4{v.x, v.y, v.z, v.w};
+#else
+  return F4{p[0], p[1], p[2], p[3]};
+#endif
+}
 SGB_HD void line_fit(const float* pts, const float* pcov, int n, float rhotheta[2], float cov[4]) {
   float sx = 0.0f, sy = 0.0f, sxy = 0.0f, sxx = 0.0f, syy = 0.0f;
   for (int i = 0; i < n; ++i) {
-    float x = pts[2 * (size_t)i], y = pts[2 * (size_t)i + 1];
+    F2 pt = ld_pt(pts + 2 * (size_t)i);
+    float x = pt.x, y = pt.y;
     sx += x;
     sy += y;
     sxy += x * y;
@@ -211,15 +231,16 @@ SGB_HD void line_fit(const float* pts, const float* pcov, int n, float rhotheta[
   float denum = (float)(1.0 / (double)(d * d + 4 * sxy * sxy));
   float ct_n = ct / nf, st_n = st / nf;
   for (int i = 0; i < n; ++i) {
-    float dx = xbar - pts[2 * (size_t)i], dy = ybar - pts[2 * (size_t)i + 1];
+    F2 pt = ld_pt(pts + 2 * (size_t)i);
+    float dx = xbar - pt.x, dy = ybar - pt.y;
     float a10 = (dy * d + 2 * sxy * dx) * denum;
     float a11 = (dx * d - 2 * sxy * dy) * denum;
     float a00 = ct_n - xbar_st * a10 + ybar_ct * a10;
     float a01 = st_n - xbar_st * a11 + ybar_ct * a11;
-    const float* C = pcov + 4 * (size_t)i;
+    const F4 C = ld_cov(pcov + 4 * (size_t)i);
     // cov += Ai * C * Ai^T, (Ai * C) first
-    float m00 = a00 * C[0] + a01 * C[2], m01 = a00 * C[1] + a01 * C[3];
-    float m10 = a10 * C[0] + a11 * C[2], m11 = a10 * C[1] + a11 * C[3];
+    float m00 = a00 * C.a + a01 * C.c, m01 = a00 * C.b + a01 * C.d;
+    float m10 = a10 * C.a + a11 * C.c, m11 = a10 * C.b + a11 * C.d;
     cov[0] += m00 * a00 + m01 * a01;
     cov[1] += m00 * a10 + m01 * a11;
     cov[2] += m10 * a00 + m11 * a01;

@@ -21,44 +21,91 @@ using namespace sgb;
 namespace {
 
 constexpr int kPgThreads = 256;
-constexpr int kChainThreads = 512;
+constexpr int kChainThreads = 512;  // the single block that scans the tile products
+constexpr int kTileItems = 8;       // poses per thread
+constexpr int kTile = kPgThreads * kTileItems;
 
-// one thread per copied pose: z_k = lm[k]^-1 * lm[k+1] (lm points at the predecessor of the first copied pose)
-__global__ void __launch_bounds__(kPgThreads) k_pg_remeasure(const double* __restrict__ lm, int count, double* __restrict__ z_out) {
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
-    Se2 z = relative_measurement(lm + 3 * (size_t)k, lm + 3 * (size_t)(k + 1));
-    se2_store(z_out + 3 * (size_t)k, z);
-  }
-}
-
-// est[k] = est[-1] * z_0 * ... * z_k for k = 0..count-1 (est points at the first new vertex, est - 3 is the previous
-// vertex): an inclusive scan under SE2 composition. ONE thread block: every thread composes a contiguous chunk, the
-// chunk products are scanned in shared memory (Hillis-Steele, fixed order => deterministic), then every thread walks its
-// chunk again from its prefix. The reference composes strictly left to right; SE2 composition is associative, so the
-// two agree up to rounding (tests: 1e-12).
-__global__ void __launch_bounds__(kChainThreads) k_pg_chain(double* __restrict__ est, const double* __restrict__ z, int count) {
-  __shared__ double sx[2][kChainThreads], sy[2][kChainThreads], sth[2][kChainThreads];
-  const int t = threadIdx.x, T = blockDim.x;
-  const int chunk = (count + T - 1) / T;
-  const int k0 = min(count, t * chunk), k1 = min(count, k0 + chunk);
-  Se2 loc{0.0, 0.0, 0.0};
-  for (int k = k0; k < k1; ++k) loc = se2_mul(loc, se2_load(z + 3 * (size_t)k));
+// Inclusive scan of one SE2 element per thread under composition (Hillis-Steele in shared memory, fixed order =>
+// deterministic). Returns this thread's inclusive value; *excl (may be NULL) receives the exclusive one (identity for
+// thread 0). NT = blockDim.x.
+template <int NT>
+__device__ __forceinline__ Se2 block_scan_se2(Se2 v, double (*sx)[NT], double (*sy)[NT], double (*sth)[NT], Se2* excl) {
+  const int t = threadIdx.x;
   int cur = 0;
-  sx[0][t] = loc.x; sy[0][t] = loc.y; sth[0][t] = loc.th;
+  sx[0][t] = v.x; sy[0][t] = v.y; sth[0][t] = v.th;
   __syncthreads();
-  for (int off = 1; off < T; off <<= 1) {
-    Se2 v{sx[cur][t], sy[cur][t], sth[cur][t]};
-    if (t >= off) v = se2_mul(Se2{sx[cur][t - off], sy[cur][t - off], sth[cur][t - off]}, v);
-    sx[cur ^ 1][t] = v.x; sy[cur ^ 1][t] = v.y; sth[cur ^ 1][t] = v.th;
+  for (int off = 1; off < NT; off <<= 1) {
+    Se2 w{sx[cur][t], sy[cur][t], sth[cur][t]};
+    if (t >= off) w = se2_mul(Se2{sx[cur][t - off], sy[cur][t - off], sth[cur][t - off]}, w);
+    sx[cur ^ 1][t] = w.x; sy[cur ^ 1][t] = w.y; sth[cur ^ 1][t] = w.th;
     cur ^= 1;
     __syncthreads();
   }
-  Se2 run = se2_load(est - 3);  // the vertex the chain hangs from
-  if (t > 0) run = se2_mul(run, Se2{sx[cur][t - 1], sy[cur][t - 1], sth[cur][t - 1]});
+  if (excl) *excl = t > 0 ? Se2{sx[cur][t - 1], sy[cur][t - 1], sth[cur][t - 1]} : Se2{0.0, 0.0, 0.0};
+  return Se2{sx[cur][t], sy[cur][t], sth[cur][t]};
+}
+
+// The chain copy est[k] = est[-1] * z_0 * ... * z_k, z_k = lm[k]^-1 * lm[k+1] (submap_loop_closer.cpp:206-223) is an
+// inclusive scan under SE2 composition. Reduce-then-scan over tiles of kTile poses, three launches:
+//   k_pg_remeasure  one thread per kTileItems consecutive poses: the re-measured z (written once) and their product;
+//                   the block's ordered product goes to tile_prod[tile]
+//   k_pg_scan_tiles ONE block: tile_prefix[tile] = est[-1] * prod(tile_prod[0..tile))
+//   k_pg_apply      per tile: scan of the thread products in shared memory, then every thread walks its poses from its
+//                   prefix and writes the estimates
+// The reference composes strictly left to right; composition is associative, so the two agree up to rounding (tests:
+// 1e-11 relative on the host bodies, 1e-7 m over 1e6 compositions on the device).
+__global__ void __launch_bounds__(kPgThreads) k_pg_remeasure(const double* __restrict__ lm, int count, double* __restrict__ z_out,
+                                                            double* __restrict__ tile_prod) {
+  __shared__ double sx[2][kPgThreads], sy[2][kPgThreads], sth[2][kPgThreads];
+  const int k0 = min(count, blockIdx.x * kTile + threadIdx.x * kTileItems), k1 = min(count, k0 + kTileItems);
+  Se2 loc{0.0, 0.0, 0.0};
   for (int k = k0; k < k1; ++k) {
-    run = se2_mul(run, se2_load(z + 3 * (size_t)k));
-    se2_store(est + 3 * (size_t)k, run);
+    Se2 z = relative_measurement(lm + 3 * (size_t)k, lm + 3 * (size_t)(k + 1));
+    se2_store(z_out + 3 * (size_t)k, z);
+    loc = se2_mul(loc, z);
   }
+  Se2 incl = block_scan_se2<kPgThreads>(loc, sx, sy, sth, nullptr);
+  if (threadIdx.x == kPgThreads - 1) se2_store(tile_prod + 3 * (size_t)blockIdx.x, incl);
+}
+__global__ void __launch_bounds__(kChainThreads) k_pg_scan_tiles(const double* __restrict__ prev, const double* __restrict__ tile_prod,
+                                                                int ntiles, double* __restrict__ tile_prefix) {
+  __shared__ double sx[2][kChainThreads], sy[2][kChainThreads], sth[2][kChainThreads];
+  const int t = threadIdx.x;
+  const int chunk = (ntiles + kChainThreads - 1) / kChainThreads;
+  const int k0 = min(ntiles, t * chunk), k1 = min(ntiles, k0 + chunk);
+  Se2 loc{0.0, 0.0, 0.0};
+  for (int k = k0; k < k1; ++k) loc = se2_mul(loc, se2_load(tile_prod + 3 * (size_t)k));
+  Se2 excl;
+  block_scan_se2<kChainThreads>(loc, sx, sy, sth, &excl);
+  Se2 run = se2_load(prev);  // the vertex the chain hangs from
+  if (t > 0) run = se2_mul(run, excl);
+  for (int k = k0; k < k1; ++k) {
+    se2_store(tile_prefix + 3 * (size_t)k, run);
+    run = se2_mul(run, se2_load(tile_prod + 3 * (size_t)k));
+  }
+}
+__global__ void __launch_bounds__(kPgThreads) k_pg_apply(const double* __restrict__ z, const double* __restrict__ tile_prefix, int count,
+                                                        double* __restrict__ est) {
+  __shared__ double sx[2][kPgThreads], sy[2][kPgThreads], sth[2][kPgThreads];
+  const int k0 = min(count, blockIdx.x * kTile + threadIdx.x * kTileItems), k1 = min(count, k0 + kTileItems);
+  Se2 zz[kTileItems];
+  Se2 loc{0.0, 0.0, 0.0};
+#pragma unroll
+  for (int i = 0; i < kTileItems; ++i)
+    if (k0 + i < k1) {
+      zz[i] = se2_load(z + 3 * (size_t)(k0 + i));
+      loc = se2_mul(loc, zz[i]);
+    }
+  Se2 excl;
+  block_scan_se2<kPgThreads>(loc, sx, sy, sth, &excl);
+  Se2 run = se2_load(tile_prefix + 3 * (size_t)blockIdx.x);
+  if (threadIdx.x > 0) run = se2_mul(run, excl);
+#pragma unroll
+  for (int i = 0; i < kTileItems; ++i)
+    if (k0 + i < k1) {
+      run = se2_mul(run, zz[i]);
+      se2_store(est + 3 * (size_t)(k0 + i), run);
+    }
 }
 
 // one thread per active closure: chi2 = e^T Omega e at the current estimates (no robust kernel), flag = chi2 > thr
@@ -90,6 +137,8 @@ struct sgb_pose_graph {
   int capP = 0, capE = 0;
   // scratch
   double* d_tmp = nullptr;  // staging for host estimates / closure chi2
+  double* d_tiles = nullptr;  // [2][3*tiles] tile products and prefixes of the chain scan
+  size_t cap_tiles = 0;
   int32_t* d_slots = nullptr;
   uint8_t* d_flags = nullptr;
   size_t cap_tmp = 0, cap_slots = 0;
@@ -174,20 +223,29 @@ sgb_status append_impl(sgb_pose_graph* pg, const double* lm_dev, int count, cons
     ni[k] = p0 - 1 + k;
     nj[k] = p0 + k;
   }
+  const int ntiles = (count + kTile - 1) / kTile;
+  if ((size_t)ntiles > pg->cap_tiles) {
+    if (pg->d_tiles) cudaFree(pg->d_tiles);
+    pg->d_tiles = nullptr;
+    pg->cap_tiles = 0;
+    PG_CUDA(cudaMalloc((void**)&pg->d_tiles, 6 * (size_t)ntiles * sizeof(double)));  // products, then prefixes
+    pg->cap_tiles = (size_t)ntiles;
+  }
   PG_CUDA(cudaMemcpyAsync(pg->d_info + 6 * (size_t)e0, info, 6 * (size_t)count * sizeof(double), cudaMemcpyHostToDevice, pg->stream));
   PG_CUDA(cudaMemsetAsync(pg->d_phi + e0, 0, (size_t)count * sizeof(double), pg->stream));
   PG_CUDA(cudaMemcpyAsync(pg->d_ei + e0, ni.data(), (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, pg->stream));
   PG_CUDA(cudaMemcpyAsync(pg->d_ej + e0, nj.data(), (size_t)count * sizeof(int32_t), cudaMemcpyHostToDevice, pg->stream));
   PG_CUDA(cudaEventRecord(pg->ev0, pg->stream));
-  k_pg_remeasure<<<pg_grid(count), kPgThreads, 0, pg->stream>>>(lm_dev, count, pg->d_z + 3 * (size_t)e0);
-  k_pg_chain<<<1, kChainThreads, 0, pg->stream>>>(pg->d_est + 3 * (size_t)p0, pg->d_z + 3 * (size_t)e0, count);
+  k_pg_remeasure<<<ntiles, kPgThreads, 0, pg->stream>>>(lm_dev, count, pg->d_z + 3 * (size_t)e0, pg->d_tiles);
+  k_pg_scan_tiles<<<1, kChainThreads, 0, pg->stream>>>(pg->d_est + 3 * (size_t)(p0 - 1), pg->d_tiles, ntiles, pg->d_tiles + 3 * (size_t)ntiles);
+  k_pg_apply<<<ntiles, kPgThreads, 0, pg->stream>>>(pg->d_z + 3 * (size_t)e0, pg->d_tiles + 3 * (size_t)ntiles, count, pg->d_est + 3 * (size_t)p0);
   PG_CUDA(cudaGetLastError());
   PG_CUDA(cudaEventRecord(pg->ev1, pg->stream));
   PG_CUDA(cudaStreamSynchronize(pg->stream));  // ni / nj / info are the caller's and this frame's
   float ms = 0.f;
   cudaEventElapsedTime(&ms, pg->ev0, pg->ev1);
   pg->last_edit_ms = ms;
-  pg->launches += 2;
+  pg->launches += 3;
   int next_id = pg->id.back() + 1;
   for (int k = 0; k < count; ++k) {
     pg->id.push_back(ids ? ids[k] : next_id + k);
@@ -224,7 +282,7 @@ void sgb_pg_destroy(sgb_pose_graph* pg) {
   cudaSetDevice(pg->device);
   if (pg->stream) cudaStreamSynchronize(pg->stream);
   for (void* p : {(void*)pg->d_est, (void*)pg->d_z, (void*)pg->d_info, (void*)pg->d_phi, (void*)pg->d_ei, (void*)pg->d_ej,
-                  (void*)pg->d_tmp, (void*)pg->d_slots, (void*)pg->d_flags})
+                  (void*)pg->d_tmp, (void*)pg->d_slots, (void*)pg->d_flags, (void*)pg->d_tiles})
     if (p) cudaFree(p);
   if (pg->ev0) cudaEventDestroy(pg->ev0);
   if (pg->ev1) cudaEventDestroy(pg->ev1);

@@ -77,6 +77,7 @@ class PoseGraphB200:
         done = C.c_int32(-1)
         st = self.L.sgb_pg_optimize(self.pg, self.solver.h, self.solver.algo, iters, C.byref(done), C.cast(stats, C.c_void_p))
         self._check(st)
+        self.solver.P, self.solver.Lm = self.info()["n_poses"], 0  # the solver now holds this graph
         n = done.value
         return n, [stats[i].as_dict() for i in range(max(n, 0))]
 

@@ -56,7 +56,7 @@ def lib():
         L.hs_check_hlp.argtypes = [vp]
         L.hs_check_hlp.restype = C.c_double
         L.hs_chi2.argtypes = [vp, vp]
-        L.hs_pg_append.argtypes = [vp, vp, C.c_int, C.c_int, vp, vp]
+        L.hs_pg_append.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.hs_closure_chi2.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
         L.hs_odom_information.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_double, vp, vp, vp]
         L.hs_scan_point_covariances.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_float, C.c_float, C.c_float,
@@ -142,12 +142,12 @@ def _c(a, dt):
     return np.ascontiguousarray(a, dt)
 
 
-def pg_append(prev, lm_est, threads=512):
+def pg_append(prev, lm_est, threads=256, items=8, scan_threads=512):
     lm = _c(lm_est, np.float64).reshape(-1, 3)
     n = lm.shape[0] - 1
     z, est = np.zeros((n, 3)), np.zeros((n, 3))
     prev = _c(prev, np.float64)
-    lib().hs_pg_append(_p(prev), _p(lm), n, threads, _p(z), _p(est))
+    lib().hs_pg_append(_p(prev), _p(lm), n, threads, items, scan_threads, _p(z), _p(est))
     return z, est
 
 

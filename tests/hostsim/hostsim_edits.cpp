@@ -1,8 +1,9 @@
 // hostsim_edits.cpp -- TEST HARNESS ONLY (never shipped, never loaded by the sparse_gslam_b200 package).
 // Executes the bodies of sparse-gslam_b200/csrc/sgb_edits.h on the host with the kernels' work decomposition
-// (sgb_posegraph.cu, sgb_frontend.cu): one "thread" per element, and for the pose chain the same chunk / shared-memory
-// scan / re-walk structure as k_pg_chain with T virtual threads, so the CPU-only tier checks the arithmetic and the scan
-// against the oracle before GPU time is spent.
+// (sgb_posegraph.cu, sgb_frontend.cu): one "thread" per element, and for the pose chain the same tiled
+// reduce-then-scan structure (k_pg_remeasure / k_pg_scan_tiles / k_pg_apply) with virtual threads, so the CPU-only tier
+// checks the arithmetic and the scan against the oracle before GPU time is spent.
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <vector>
@@ -13,33 +14,71 @@ using namespace sgb;
 
 extern "C" {
 
-void hs_pg_append(const double* prev, const double* lm, int count, int T, double* z_out, double* est_out) {
-  for (int k = 0; k < count; ++k) se2_store(z_out + 3 * (size_t)k, relative_measurement(lm + 3 * (size_t)k, lm + 3 * (size_t)(k + 1)));
-  // k_pg_chain with T virtual threads
-  const int chunk = (count + T - 1) / T;
-  std::vector<Se2> buf[2] = {std::vector<Se2>(T), std::vector<Se2>(T)};
-  auto k0 = [&](int t) { return std::min(count, t * chunk); };
-  auto k1 = [&](int t) { return std::min(count, k0(t) + chunk); };
-  for (int t = 0; t < T; ++t) {
-    Se2 loc{0.0, 0.0, 0.0};
-    for (int k = k0(t); k < k1(t); ++k) loc = se2_mul(loc, se2_load(z_out + 3 * (size_t)k));
-    buf[0][t] = loc;
+// inclusive Hillis-Steele scan over n elements (one per virtual thread), as block_scan_se2 does in shared memory
+static void hillis_steele(std::vector<Se2>& v) {
+  const int n = (int)v.size();
+  std::vector<Se2> w(n);
+  for (int off = 1; off < n; off <<= 1) {
+    for (int t = 0; t < n; ++t) w[t] = t >= off ? se2_mul(v[t - off], v[t]) : v[t];
+    v.swap(w);
   }
-  int cur = 0;
-  for (int off = 1; off < T; off <<= 1) {
+}
+// k_pg_remeasure / k_pg_scan_tiles / k_pg_apply with T threads per tile, `items` poses per thread, T2 scan threads
+void hs_pg_append(const double* prev, const double* lm, int count, int T, int items, int T2, double* z_out, double* est_out) {
+  const int tile = T * items, ntiles = (count + tile - 1) / tile;
+  std::vector<Se2> tile_prod(ntiles), tile_prefix(ntiles);
+  for (int b = 0; b < ntiles; ++b) {  // k_pg_remeasure
+    std::vector<Se2> loc(T);
     for (int t = 0; t < T; ++t) {
-      Se2 v = buf[cur][t];
-      if (t >= off) v = se2_mul(buf[cur][t - off], v);
-      buf[cur ^ 1][t] = v;
+      int k0 = std::min(count, b * tile + t * items), k1 = std::min(count, k0 + items);
+      Se2 l{0.0, 0.0, 0.0};
+      for (int k = k0; k < k1; ++k) {
+        Se2 z = relative_measurement(lm + 3 * (size_t)k, lm + 3 * (size_t)(k + 1));
+        se2_store(z_out + 3 * (size_t)k, z);
+        l = se2_mul(l, z);
+      }
+      loc[t] = l;
     }
-    cur ^= 1;
+    hillis_steele(loc);
+    tile_prod[b] = loc[T - 1];
   }
-  for (int t = 0; t < T; ++t) {
-    Se2 run = se2_load(prev);
-    if (t > 0) run = se2_mul(run, buf[cur][t - 1]);
-    for (int k = k0(t); k < k1(t); ++k) {
-      run = se2_mul(run, se2_load(z_out + 3 * (size_t)k));
-      se2_store(est_out + 3 * (size_t)k, run);
+  {  // k_pg_scan_tiles
+    const int chunk = (ntiles + T2 - 1) / T2;
+    std::vector<Se2> loc(T2);
+    for (int t = 0; t < T2; ++t) {
+      int k0 = std::min(ntiles, t * chunk), k1 = std::min(ntiles, k0 + chunk);
+      Se2 l{0.0, 0.0, 0.0};
+      for (int k = k0; k < k1; ++k) l = se2_mul(l, tile_prod[k]);
+      loc[t] = l;
+    }
+    hillis_steele(loc);
+    for (int t = 0; t < T2; ++t) {
+      int k0 = std::min(ntiles, t * chunk), k1 = std::min(ntiles, k0 + chunk);
+      Se2 run = se2_load(prev);
+      if (t > 0) run = se2_mul(run, loc[t - 1]);
+      for (int k = k0; k < k1; ++k) {
+        tile_prefix[k] = run;
+        run = se2_mul(run, tile_prod[k]);
+      }
+    }
+  }
+  for (int b = 0; b < ntiles; ++b) {  // k_pg_apply
+    std::vector<Se2> loc(T);
+    for (int t = 0; t < T; ++t) {
+      int k0 = std::min(count, b * tile + t * items), k1 = std::min(count, k0 + items);
+      Se2 l{0.0, 0.0, 0.0};
+      for (int k = k0; k < k1; ++k) l = se2_mul(l, se2_load(z_out + 3 * (size_t)k));
+      loc[t] = l;
+    }
+    hillis_steele(loc);
+    for (int t = 0; t < T; ++t) {
+      int k0 = std::min(count, b * tile + t * items), k1 = std::min(count, k0 + items);
+      Se2 run = tile_prefix[b];
+      if (t > 0) run = se2_mul(run, loc[t - 1]);
+      for (int k = k0; k < k1; ++k) {
+        run = se2_mul(run, se2_load(z_out + 3 * (size_t)k));
+        se2_store(est_out + 3 * (size_t)k, run);
+      }
     }
   }
 }

@@ -246,13 +246,14 @@ def test_oracle_scan_point_covariances_matches_numpy():
 
 
 # ------------------------------------------------------------------------------------------------ product bodies (host) vs oracle
-@pytest.mark.parametrize("n,threads", [(1, 512), (37, 512), (600, 512), (5000, 512), (100, 8)])
-def test_bodies_pg_append(n, threads):
+@pytest.mark.parametrize("n,threads,items,scan", [(1, 256, 8, 512), (37, 256, 8, 512), (2048, 256, 8, 512), (2049, 256, 8, 512),
+                                                  (9000, 256, 8, 512), (700, 8, 2, 4), (1000, 4, 3, 2)])
+def test_bodies_pg_append(n, threads, items, scan):
     rng = np.random.default_rng(n)
     lm = rand_chain(rng, n + 1)
     prev = np.array([-4.0, 7.0, -3.1])
     z0, e0 = co.pg_append(prev, lm)
-    z1, e1 = hostsim.pg_append(prev, lm, threads)
+    z1, e1 = hostsim.pg_append(prev, lm, threads, items, scan)
     pose_close(z1, z0, 1e-13)
     pose_close(e1, e0, 1e-11)  # the scan re-associates the SE2 products
 
@@ -442,7 +443,10 @@ def test_set_graph_device_equals_host_path():
     assert a.initialize_optimization(h)
     la = a.linearize()
     lb = pg.solver.linearize()  # the store's solver holds the device-gathered graph at the same estimates
-    assert np.array_equal(la["H"], lb["H"]) and np.array_equal(la["b"], lb["b"]) and np.array_equal(la["chi2"], lb["chi2"])
+    # not bit-equal: the cached inverse measurement is formed with the device's sincos on one path, glibc's on the other
+    np.testing.assert_allclose(lb["H"], la["H"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(lb["b"], la["b"], rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(lb["chi2"], la["chi2"], rtol=1e-12)
 
 
 @gpu
