@@ -186,6 +186,27 @@ sgb_status sgb_linearize(sgb_handle* h, double* b, double* Hblocks, double* chi2
  * x [scalar_dim] in Hessian order; pcg_iters / rel_residual may be NULL. */
 sgb_status sgb_solve_once(sgb_handle* h, double lambda, double* x, int32_t* pcg_iters, double* rel_residual);
 
+/* ---- LinearSolver level (the narrower drop-in) ------------------------------------------------------
+ * What g2o::LinearSolver<MatrixType>::solve(const SparseBlockMatrix<MatrixType>& A, number_t* x, number_t* b) needs
+ * (the object the reference builds as LinearSolverEigen at graphs.cpp:11,19): the caller -- g2o's own BlockSolver --
+ * keeps linearisation, damping and the LM logic; only (A, b) -> x runs here (Schur elimination of the 2x2 blocks,
+ * block-Jacobi PCG on the reduced 3x3-block system). A is the upper triangle in g2o's SparseBlockMatrix order: block
+ * columns, rows ascending within a column, every block column-major (Eigen); 3x3 pose blocks first, then 2x2 landmark
+ * blocks, off-diagonal blocks pose-pose or pose-landmark (what BlockSolver<-1,2> / BlockSolver<3,3> produce for this
+ * repo's graphs). sgb_linear_set_pattern = LinearSolver::init() + the pattern analysis of the first solve (once per
+ * optimize()); sgb_linear_solve = solve(): values in pattern order, b and x [3*n3 + 2*n2]; returns
+ * SGB_ERR_SOLVE_FAILED where LinearSolverEigen returns false (matrix not positive definite). The handle's graph, if
+ * any, is replaced. */
+typedef struct sgb_block_matrix {
+  int32_t n_block_cols;      /* = block rows */
+  const int32_t* block_dim;  /* [n] 3 or 2, all 3s first */
+  const int32_t* col_ptr;    /* [n+1] */
+  const int32_t* row_idx;    /* [col_ptr[n]] block row <= block column, ascending within a column */
+} sgb_block_matrix;
+sgb_status sgb_linear_set_pattern(sgb_handle* h, const sgb_block_matrix* A);
+sgb_status sgb_linear_solve(sgb_handle* h, const double* values, const double* b, double* x, int32_t* pcg_iters,
+                            double* rel_residual);
+
 /* SparseOptimizer::optimize(iters, online): returns through *iters_done what g2o returns
  * (iterations run; 0 on Fail; -1 if not initialised). stats may be NULL or hold max_iters entries.
  * Estimates stay resident on the device and are also copied back (sgb_get_estimates). */

@@ -20,6 +20,44 @@ void setup_pose_opt(g2o::SparseOptimizer& opt) {
   opt.setComputeBatchStatistics(false);
 }
 
+// ---- the narrower drop-in: LinearSolverB200 behind g2o's own BlockSolver (graphs.cpp:11 / :19 with one changed word)
+static int linear_solver_example() {
+  // H of 3 poses + 2 landmarks: block-tridiagonal pose part, every pose sees landmark 0, pose 2 sees landmark 1
+  const int rbi[5] = {3, 6, 9, 11, 13};
+  g2o::SparseBlockMatrix<g2o::MatrixX> A(rbi, rbi, 5, 5);
+  std::mt19937 rng(7);
+  std::uniform_real_distribution<double> u(-1.0, 1.0);
+  auto fill = [&](int r, int c) {
+    auto* b = A.block(r, c, true);
+    for (int j = 0; j < b->cols(); ++j)
+      for (int i = 0; i < b->rows(); ++i) (*b)(i, j) = (r == c) ? ((i == j) ? 12.0 : ((i < j) ? 0.3 * (i + j + 1) : 0.0)) : u(rng);
+    if (r == c)
+      for (int j = 0; j < b->cols(); ++j)
+        for (int i = j + 1; i < b->rows(); ++i) (*b)(i, j) = (*b)(j, i);  // symmetric diagonal blocks
+  };
+  for (int k = 0; k < 5; ++k) fill(k, k);
+  fill(0, 1); fill(1, 2); fill(0, 3); fill(1, 3); fill(2, 3); fill(2, 4);
+  double b[13], x[13], dense[13][13] = {};
+  for (double& v : b) v = u(rng);
+  for (int c = 0; c < 5; ++c)
+    for (const auto& kv : A.blockCols()[c])
+      for (int j = 0; j < kv.second->cols(); ++j)
+        for (int i = 0; i < kv.second->rows(); ++i) {
+          int gi = A.rowBaseOfBlock(kv.first) + i, gj = A.colBaseOfBlock(c) + j;
+          dense[gi][gj] = dense[gj][gi] = (*kv.second)(i, j);
+        }
+  g2o::LinearSolverB200<g2o::MatrixX> solver;
+  if (!solver.init() || !solver.solve(A, x, b)) return 3;
+  double worst = 0.0;
+  for (int i = 0; i < 13; ++i) {
+    double r = -b[i];
+    for (int j = 0; j < 13; ++j) r += dense[i][j] * x[j];
+    worst = std::max(worst, std::fabs(r));
+  }
+  std::printf("LinearSolverB200: %d PCG iterations, max |Ax - b| = %.3e\n", solver.lastPcgIterations(), worst);
+  return worst < 1e-8 ? 0 : 4;
+}
+
 int main() {
   g2o::SparseOptimizer opt;
   setup_lm_opt(opt);
@@ -75,5 +113,6 @@ int main() {
               poses.back().estimate()[1], poses.back().estimate()[2]);
   opt.discardTop();
   delete opt.algorithm();
-  return (n > 0 && chi2_after < 400.0) ? 0 : 2;
+  if (!(n > 0 && chi2_after < 400.0)) return 2;
+  return linear_solver_example();
 }

@@ -9,7 +9,8 @@
 // (addVertex, addEdge, initializeOptimization, updateInitialization, optimize, push, pop, discardTop,
 // computeActiveErrors, activeChi2, activeRobustChi2, setAlgorithm, algorithm, setVerbose,
 // setComputeBatchStatistics, activeVertices, activeEdges, indexMapping) and the two custom types of the reference
-// (VertexRhoTheta, EdgeSE2RhoTheta; reference include/g2o_bindings/*.h).
+// (VertexRhoTheta, EdgeSE2RhoTheta; reference include/g2o_bindings/*.h); SparseBlockMatrix / LinearSolver as far as
+// a LinearSolver plugin reads them.
 #pragma once
 #include <algorithm>
 #include <array>
@@ -172,6 +173,58 @@ class BaseBinaryEdgeLite : public OptimizableGraph::Edge {
 class EdgeSE2 : public BaseBinaryEdgeLite<3, SE2, Matrix3> {};
 // reference include/g2o_bindings/edge_se2_rhotheta.h
 class EdgeSE2RhoTheta : public BaseBinaryEdgeLite<2, Vector2, Matrix2> {};
+
+// ---- the LinearSolver level (g2o/core/sparse_block_matrix.h, g2o/core/linear_solver.h): only the members the
+// adapter's LinearSolverB200 reads
+struct MatrixX {  // dynamic, column-major like Eigen::MatrixXd
+  int r = 0, c = 0;
+  std::vector<number_t> d;
+  MatrixX() = default;
+  MatrixX(int rows, int cols) : r(rows), c(cols), d((size_t)rows * cols, 0.0) {}
+  int rows() const { return r; }
+  int cols() const { return c; }
+  const number_t* data() const { return d.data(); }
+  number_t& operator()(int i, int j) { return d[(size_t)j * r + i]; }
+  number_t operator()(int i, int j) const { return d[(size_t)j * r + i]; }
+};
+template <class MatrixType>
+class SparseBlockMatrix {
+ public:
+  using SparseMatrixBlock = MatrixType;
+  using IntBlockMap = std::map<int, SparseMatrixBlock*>;
+  // rbi / cbi: cumulative END index of every block row / column (g2o convention)
+  SparseBlockMatrix(const int* rbi, const int* cbi, int rb, int cb) : _rowBlockIndices(rbi, rbi + rb), _colBlockIndices(cbi, cbi + cb), _blockCols(cb) {}
+  ~SparseBlockMatrix() { for (auto& col : _blockCols) for (auto& kv : col) delete kv.second; }
+  SparseBlockMatrix(const SparseBlockMatrix&) = delete;
+  SparseBlockMatrix& operator=(const SparseBlockMatrix&) = delete;
+  int rows() const { return _rowBlockIndices.empty() ? 0 : _rowBlockIndices.back(); }
+  int cols() const { return _colBlockIndices.empty() ? 0 : _colBlockIndices.back(); }
+  int rowsOfBlock(int r) const { return r ? _rowBlockIndices[r] - _rowBlockIndices[r - 1] : _rowBlockIndices[0]; }
+  int colsOfBlock(int c) const { return c ? _colBlockIndices[c] - _colBlockIndices[c - 1] : _colBlockIndices[0]; }
+  int rowBaseOfBlock(int r) const { return r ? _rowBlockIndices[r - 1] : 0; }
+  int colBaseOfBlock(int c) const { return c ? _colBlockIndices[c - 1] : 0; }
+  const std::vector<int>& rowBlockIndices() const { return _rowBlockIndices; }
+  const std::vector<int>& colBlockIndices() const { return _colBlockIndices; }
+  const std::vector<IntBlockMap>& blockCols() const { return _blockCols; }
+  SparseMatrixBlock* block(int r, int c, bool alloc = false) {
+    auto it = _blockCols[c].find(r);
+    if (it != _blockCols[c].end()) return it->second;
+    if (!alloc) return nullptr;
+    auto* b = new SparseMatrixBlock(rowsOfBlock(r), colsOfBlock(c));
+    _blockCols[c].emplace(r, b);
+    return b;
+  }
+ private:
+  std::vector<int> _rowBlockIndices, _colBlockIndices;
+  std::vector<IntBlockMap> _blockCols;
+};
+template <class MatrixType>
+class LinearSolver {
+ public:
+  virtual ~LinearSolver() = default;
+  virtual bool init() = 0;
+  virtual bool solve(const SparseBlockMatrix<MatrixType>& A, number_t* x, number_t* b) = 0;
+};
 
 class SparseOptimizer;
 class OptimizationAlgorithm {

@@ -171,4 +171,68 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
   sgb_iter_stat _last{};
 };
 
+// The narrower drop-in: only the innermost object of graphs.cpp:11,19 changes,
+//     g2o::make_unique<LinearSolverEigen<PoseMatrixType>>()   becomes   g2o::make_unique<LinearSolverB200<PoseMatrixType>>()
+// g2o's BlockSolver keeps linearisation, damping and the LM logic on the host and hands the damped block matrix over
+// once per trial; the solve itself (Schur elimination + PCG) runs on the device. init() is called once per optimize()
+// (like LinearSolverEigen's, it forgets the pattern analysis).
+template <typename MatrixType>
+class LinearSolverB200 : public LinearSolver<MatrixType> {
+ public:
+  explicit LinearSolverB200(const sgb_options* options = nullptr) {
+    sgb_options o;
+    sgb_default_options(&o);
+    if (options) o = *options;
+    if (sgb_create(&o, &_h) != SGB_OK) {
+      std::fprintf(stderr, "LinearSolverB200: sgb_create failed (no CUDA device? there is no CPU fallback)\n");
+      _h = nullptr;
+    }
+  }
+  ~LinearSolverB200() override { if (_h) sgb_destroy(_h); }
+  LinearSolverB200(const LinearSolverB200&) = delete;
+  LinearSolverB200& operator=(const LinearSolverB200&) = delete;
+
+  bool init() override {
+    _pattern = false;
+    return _h != nullptr;
+  }
+  bool solve(const SparseBlockMatrix<MatrixType>& A, number_t* x, number_t* b) override {
+    if (!_h) return false;
+    const auto& cols = A.blockCols();
+    const int n = (int)cols.size();
+    if (!_pattern) {
+      std::vector<int32_t> dim(n), col_ptr(n + 1, 0), row_idx;
+      for (int c = 0; c < n; ++c) {
+        dim[c] = A.colsOfBlock(c);
+        for (const auto& kv : cols[c])
+          if (kv.first <= c) row_idx.push_back(kv.first);  // upper triangle, rows ascending (std::map order)
+        col_ptr[c + 1] = (int32_t)row_idx.size();
+      }
+      sgb_block_matrix M{n, dim.data(), col_ptr.data(), row_idx.data()};
+      if (sgb_linear_set_pattern(_h, &M) != SGB_OK) {
+        std::fprintf(stderr, "LinearSolverB200::solve: %s\n", sgb_last_error(_h));
+        return false;
+      }
+      _pattern = true;
+    }
+    _values.clear();
+    for (int c = 0; c < n; ++c)
+      for (const auto& kv : cols[c]) {
+        if (kv.first > c) continue;
+        const auto& blk = *kv.second;  // column-major
+        _values.insert(_values.end(), blk.data(), blk.data() + (size_t)blk.rows() * blk.cols());
+      }
+    sgb_status st = sgb_linear_solve(_h, _values.data(), b, x, &_pcg_iters, nullptr);
+    if (st != SGB_OK && st != SGB_ERR_SOLVE_FAILED) std::fprintf(stderr, "LinearSolverB200::solve: %s\n", sgb_last_error(_h));
+    return st == SGB_OK;
+  }
+  int lastPcgIterations() const { return _pcg_iters; }
+
+ private:
+  sgb_handle* _h = nullptr;
+  bool _pattern = false;
+  int32_t _pcg_iters = 0;
+  std::vector<double> _values;
+};
+
 }  // namespace g2o

@@ -19,7 +19,7 @@ EXPORTS = [
     "sgb_get_timings", "sgb_optimize_resident", "sgb_set_graph_partitioned", "sgb_comm_get_handle", "sgb_comm_connect",
     "sgb_get_partition_info", "sgb_optimize_batch", "sgb_optimize_batch_resident", "sgb_g2o_load", "sgb_g2o_view",
     "sgb_g2o_free", "sgb_g2o_save",
-    "sgb_set_graph_device", "sgb_pg_create", "sgb_pg_destroy", "sgb_pg_last_error", "sgb_pg_reset",
+    "sgb_linear_set_pattern", "sgb_linear_solve", "sgb_set_graph_device", "sgb_pg_create", "sgb_pg_destroy", "sgb_pg_last_error", "sgb_pg_reset",
     "sgb_pg_append_from_lm", "sgb_pg_append_from_host", "sgb_pg_add_closure", "sgb_pg_optimize",
     "sgb_pg_prune_closures", "sgb_pg_get_info", "sgb_pg_download",
     "sgb_odom_information", "sgb_scan_point_covariances", "sgb_line_fit_information", "sgb_frontend_last_error",
@@ -80,6 +80,10 @@ class PartitionInfo(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class BlockMatrix(C.Structure):
+    _fields_ = [("n_block_cols", C.c_int32), ("block_dim", C.c_void_p), ("col_ptr", C.c_void_p), ("row_idx", C.c_void_p)]
+
+
 class DeviceValues(C.Structure):
     _fields_ = [("pose_est", C.c_void_p), ("lm_est", C.c_void_p), ("pp_z", C.c_void_p), ("pp_info", C.c_void_p),
                 ("pp_phi", C.c_void_p), ("pp_slot", C.c_void_p), ("pl_z", C.c_void_p), ("pl_info", C.c_void_p),
@@ -138,6 +142,8 @@ def load() -> C.CDLL:
     L.sgb_g2o_view.argtypes = [vp, C.POINTER(GraphSoA)]
     L.sgb_g2o_free.argtypes = [vp]
     L.sgb_g2o_save.argtypes = [C.c_char_p, C.POINTER(GraphSoA)]
+    L.sgb_linear_set_pattern.argtypes = [vp, C.POINTER(BlockMatrix)]
+    L.sgb_linear_solve.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.sgb_set_graph_device.argtypes = [vp, C.POINTER(GraphSoA), C.POINTER(DeviceValues)]
     L.sgb_pg_create.argtypes = [C.c_int32, C.POINTER(vp)]
     L.sgb_pg_destroy.argtypes = [vp]

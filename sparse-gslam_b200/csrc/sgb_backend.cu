@@ -74,6 +74,15 @@ struct sgb_handle {
   double* d_lm0 = nullptr;
   std::vector<std::pair<double*, double*>> stack;  // SparseOptimizer::push/pop backups (device)
   int pcg_blocks = 1;
+  // LinearSolver-level entry (sgb_linear_set_pattern / sgb_linear_solve): per input block its value offset, kind and
+  // the SELL entries it lands in; device copies live in the pooled memory of the current graph
+  struct LinearMap {
+    bool valid = false;
+    int n_blocks = 0, n3 = 0, n2 = 0;
+    int64_t n_values = 0;
+    const int32_t *d_off = nullptr, *d_e1 = nullptr, *d_e2 = nullptr, *d_kind = nullptr, *d_lmg = nullptr;
+    double *d_vals = nullptr, *d_b = nullptr;
+  } lin;
   sgb_timings tm;
   PhaseEvents ev;
   bool lm_state_valid = false;
@@ -541,6 +550,52 @@ __global__ void __launch_bounds__(kThreads) k_gather_pl(const int32_t* __restric
   }
 }
 
+// ---- LinearSolver-level entry: block values handed over in g2o's SparseBlockMatrix order ----------------------------
+// one thread per input block: copies its values (column-major, like Eigen) into the SELL / Hll slots of the device
+// layout. kind 0 = pose diagonal (Hpp entry e1), 1 = landmark diagonal (Hll index e1), 2 = pose-pose off-diagonal
+// (Hpp entry e1 holds the block, e2 its transpose), 3 = pose-landmark (Hpl entry e1 and Hlp entry e2, same 3x2 block)
+__global__ void __launch_bounds__(kThreads) k_scatter_blocks(DevGraph g, const double* __restrict__ vals, int n,
+                                                            const int32_t* __restrict__ off, const int32_t* __restrict__ e1,
+                                                            const int32_t* __restrict__ e2, const int32_t* __restrict__ kind) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const double* in = vals + off[k];
+    const int a1 = e1[k], a2 = e2[k], kd = kind[k];
+    if (kd == 0) {
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) g.Hpp.vals[sell_vaddr(a1, 9, 3 * a + b)] = in[b * 3 + a];
+    } else if (kd == 1) {
+      g.Hll[a1] = in[0];
+      g.Hll[(size_t)g.nL + a1] = in[2];
+      g.Hll[2 * (size_t)g.nL + a1] = in[3];
+    } else if (kd == 2) {
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          g.Hpp.vals[sell_vaddr(a1, 9, 3 * a + b)] = in[b * 3 + a];
+          g.Hpp.vals[sell_vaddr(a2, 9, 3 * a + b)] = in[a * 3 + b];
+        }
+    } else {
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 2; ++b) {
+          double v = in[b * 3 + a];
+          g.Hpl.vals[sell_vaddr(a1, 6, 2 * a + b)] = v;
+          g.Hlp.vals[sell_vaddr(a2, 6, 2 * a + b)] = v;
+        }
+    }
+  }
+}
+// right-hand side in Hessian order -> b_p (poses, same order) and b_l (landmarks in the device's row order)
+__global__ void __launch_bounds__(kThreads) k_scatter_rhs(DevGraph g, const double* __restrict__ b, const int32_t* __restrict__ lmg) {
+  const int n3 = 3 * g.nP, n = n3 + 2 * g.nL;
+  double* bl = g.b_l[g.rank];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (i < n3) g.b_p[i] = b[i];
+    else {
+      int q = i - n3, l = q >> 1, c = q & 1;
+      bl[q] = b[n3 + 2 * lmg[l] + c];
+    }
+  }
+}
+
 static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int world, int rank,
                                  const sgb_device_values* dv = nullptr) {
   if (!h || !g_in) return SGB_ERR_INVALID;
@@ -564,6 +619,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   SGB_CUDA(cudaSetDevice(h->device));
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   free_graph(h);
+  h->lin = sgb_handle::LinearMap();
   lap("free");
   sgb_status st = build_structure(*g, h->S, h->err);
   if (st != SGB_OK) return st;
@@ -906,6 +962,135 @@ sgb_status sgb_solve_once(sgb_handle* h, double lambda, double* x, int32_t* pcg_
   if (x && (st = gather_owned_vector(h, h->G.x_p[h->LP.rank], h->G.x_l, x)) != SGB_OK) return st;
   if (!ok) {
     h->err = "linear solve failed (system not positive definite)";
+    return SGB_ERR_SOLVE_FAILED;
+  }
+  return SGB_OK;
+}
+
+
+sgb_status sgb_linear_set_pattern(sgb_handle* h, const sgb_block_matrix* A) {
+  if (!h || !A || A->n_block_cols <= 0 || !A->block_dim || !A->col_ptr || !A->row_idx) return SGB_ERR_INVALID;
+  const int n = A->n_block_cols;
+  int n3 = 0;
+  while (n3 < n && A->block_dim[n3] == 3) ++n3;
+  for (int i = n3; i < n; ++i)
+    if (A->block_dim[i] != 2) { h->err = "linear: block dimensions must be 3 (poses) followed by 2 (landmarks)"; return SGB_ERR_UNSUPPORTED; }
+  const int n2 = n - n3;
+  if (n3 == 0) { h->err = "linear: a matrix without 3x3 pose blocks is not supported"; return SGB_ERR_UNSUPPORTED; }
+  // The matrix of a graph whose edges are its off-diagonal blocks has exactly this pattern: build that graph and let
+  // the ordinary symbolic phase lay it out. A vertex without off-diagonal blocks hangs from an extra FIXED pose (no row).
+  std::vector<int32_t> pp_i, pp_j, pl_p, pl_l, blk_edge((size_t)A->col_ptr[n], -1), deg(n, 0);
+  std::vector<char> has_diag(n, 0);
+  for (int c = 0; c < n; ++c) {
+    int prev = -1;
+    for (int q = A->col_ptr[c]; q < A->col_ptr[c + 1]; ++q) {
+      int r = A->row_idx[q];
+      if (r < 0 || r > c || r <= prev) { h->err = "linear: rows must be ascending and in the upper triangle"; return SGB_ERR_INVALID; }
+      prev = r;
+      if (r == c) { has_diag[c] = 1; continue; }
+      ++deg[r]; ++deg[c];
+      if (c < n3) { blk_edge[q] = (int32_t)pp_i.size(); pp_i.push_back(r); pp_j.push_back(c); }
+      else if (r < n3) { blk_edge[q] = (int32_t)pl_p.size(); pl_p.push_back(r); pl_l.push_back(c - n3); }
+      else { h->err = "linear: landmark-landmark off-diagonal blocks are not supported"; return SGB_ERR_UNSUPPORTED; }
+    }
+    if (!has_diag[c]) { h->err = "linear: missing diagonal block"; return SGB_ERR_INVALID; }
+  }
+  bool need_anchor = false;
+  for (int v = 0; v < n; ++v) need_anchor |= deg[v] == 0;
+  const int P = n3 + (need_anchor ? 1 : 0);
+  if (need_anchor)
+    for (int v = 0; v < n; ++v)
+      if (deg[v] == 0) {
+        if (v < n3) { pp_i.push_back(n3); pp_j.push_back(v); }
+        else { pl_p.push_back(n3); pl_l.push_back(v - n3); }
+      }
+  std::vector<double> pose_est(3 * (size_t)P, 0.0), lm_est(2 * (size_t)std::max(n2, 1), 0.0);
+  std::vector<uint8_t> fixed(P, 0);
+  if (need_anchor) fixed[n3] = 1;
+  std::vector<double> zpp(3 * pp_i.size() + 1, 0.0), ipp(6 * pp_i.size() + 1, 0.0), zpl(2 * pl_p.size() + 1, 0.0), ipl(3 * pl_p.size() + 1, 0.0);
+  sgb_graph_soa g;
+  std::memset(&g, 0, sizeof g);
+  g.n_poses = P; g.pose_est = pose_est.data(); g.pose_fixed = fixed.data();
+  g.n_landmarks = n2; g.lm_est = lm_est.data();
+  g.n_pp = (int32_t)pp_i.size(); g.pp_i = pp_i.data(); g.pp_j = pp_j.data(); g.pp_z = zpp.data(); g.pp_info = ipp.data();
+  g.n_pl = (int32_t)pl_p.size(); g.pl_pose = pl_p.data(); g.pl_lm = pl_l.data(); g.pl_z = zpl.data(); g.pl_info = ipl.data();
+  sgb_status st = set_graph_impl(h, &g, 1, 0);
+  if (st != SGB_OK) return st;
+  const Structure& S = h->S;
+  const LocalPlan& LP = h->LP;
+  if (S.Pf != n3 || S.Lf != n2) { h->err = "linear: internal error (free vertex count)"; return SGB_ERR_INVALID; }
+  std::vector<int32_t> loc_pp(pp_i.size(), -1), loc_pl(pl_p.size(), -1), lm_local(n2, -1);
+  for (int k = 0; k < LP.n_pp; ++k) loc_pp[S.pp_src[LP.pp_g[k]]] = k;
+  for (int k = 0; k < LP.n_pl; ++k) loc_pl[S.pl_src[LP.pl_g[k]]] = k;
+  for (int l = 0; l < LP.nL; ++l) lm_local[LP.lm_global[l]] = l;
+  const int nb = A->col_ptr[n];
+  std::vector<int32_t> off(nb), e1(nb, -1), e2(nb, -1), kind(nb);
+  int64_t o = 0;
+  for (int c = 0; c < n; ++c)
+    for (int q = A->col_ptr[c]; q < A->col_ptr[c + 1]; ++q) {
+      int r = A->row_idx[q];
+      if (o > INT32_MAX) { h->err = "linear: more than 2^31 values"; return SGB_ERR_UNSUPPORTED; }
+      off[q] = (int32_t)o;
+      o += (int64_t)A->block_dim[r] * A->block_dim[c];
+      if (r == c) {
+        if (c < n3) { kind[q] = 0; e1[q] = LP.hpp_diag[c]; }
+        else { kind[q] = 1; e1[q] = lm_local[c - n3]; }
+      } else if (c < n3) {
+        int k = loc_pp[blk_edge[q]];
+        kind[q] = 2; e1[q] = LP.pp_e_ij[k]; e2[q] = LP.pp_e_ji[k];
+      } else {
+        int k = loc_pl[blk_edge[q]];
+        kind[q] = 3; e1[q] = LP.pl_e_pl[k]; e2[q] = LP.pl_e_lp[k];
+      }
+      if (e1[q] < 0 || (kind[q] >= 2 && e2[q] < 0)) { h->err = "linear: internal error (block without a slot)"; return SGB_ERR_INVALID; }
+    }
+  auto& L = h->lin;
+  L.n_blocks = nb; L.n3 = n3; L.n2 = n2; L.n_values = o;
+  if ((st = upload(h, &L.d_off, off)) != SGB_OK) return st;
+  if ((st = upload(h, &L.d_e1, e1)) != SGB_OK) return st;
+  if ((st = upload(h, &L.d_e2, e2)) != SGB_OK) return st;
+  if ((st = upload(h, &L.d_kind, kind)) != SGB_OK) return st;
+  if ((st = upload(h, &L.d_lmg, LP.lm_global)) != SGB_OK) return st;
+  if ((st = dalloc(h, &L.d_vals, (size_t)o)) != SGB_OK) return st;
+  if ((st = dalloc(h, &L.d_b, (size_t)S.dim)) != SGB_OK) return st;
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  L.valid = true;
+  return SGB_OK;
+}
+
+sgb_status sgb_linear_solve(sgb_handle* h, const double* values, const double* b, double* x, int32_t* pcg_iters, double* rel) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  if (!h->lin.valid) { h->err = "linear: call sgb_linear_set_pattern first"; return SGB_ERR_NOT_INITIALIZED; }
+  if (!values || !b || !x) return SGB_ERR_INVALID;
+  SGB_CUDA(cudaSetDevice(h->device));
+  auto& L = h->lin;
+  std::memset(&h->tm, 0, sizeof h->tm);
+  if ((st = h2d(h, L.d_vals, values, (size_t)L.n_values * sizeof(double))) != SGB_OK) return st;
+  if ((st = h2d(h, L.d_b, b, (size_t)h->S.dim * sizeof(double))) != SGB_OK) return st;
+  cudaEvent_t t0 = h->ev.e[0], t1 = h->ev.e[1];
+  SGB_CUDA(cudaEventRecord(t0, h->stream));
+  k_scatter_blocks<<<grid_for(L.n_blocks), kThreads, 0, h->stream>>>(h->G, L.d_vals, L.n_blocks, L.d_off, L.d_e1, L.d_e2, L.d_kind);
+  k_scatter_rhs<<<grid_for(h->S.dim), kThreads, 0, h->stream>>>(h->G, L.d_b, L.d_lmg);
+  h->tm.kernel_launches += 2;
+  SGB_CUDA(cudaGetLastError());
+  if ((st = launch_setup(h, 0.0, 1)) != SGB_OK) return st;   // lambda is already inside A (BlockSolver::setLambda)
+  if ((st = launch_pcg(h, 0.0, 1)) != SGB_OK) return st;
+  if (h->G.nL > 0) {
+    k_backsub<<<grid_for(32 * h->G.Hlp.nslices), kThreads, 0, h->stream>>>(h->G);
+    h->tm.kernel_launches++;
+  }
+  k_gn_control<<<1, 32, 0, h->stream>>>(h->G, h->d_sc);
+  h->tm.kernel_launches++;
+  SGB_CUDA(cudaEventRecord(t1, h->stream));
+  if ((st = read_scalars(h)) != SGB_OK) return st;
+  h->tm.total_ms = ev_ms(t0, t1);
+  h->tm.pcg_iters = h->h_sc->pcg_iters;
+  if (pcg_iters) *pcg_iters = h->h_sc->pcg_iters;
+  if (rel) *rel = h->h_sc->pcg_rel;
+  if ((st = gather_owned_vector(h, h->G.x_p[h->LP.rank], h->G.x_l, x)) != SGB_OK) return st;
+  if (h->h_sc->result != 1) {
+    h->err = "linear solve failed (matrix not positive definite)";  // LinearSolver::solve() == false
     return SGB_ERR_SOLVE_FAILED;
   }
   return SGB_OK;

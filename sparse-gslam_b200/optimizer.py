@@ -226,3 +226,39 @@ def optimize_batch(optimizers, iters, resident=False):
     if st != capi.OK:
         raise SgbError(st, L.sgb_last_error(optimizers[0].h).decode())
     return [done[i] for i in range(n)], [stats[i].as_dict() for i in range(n)]
+
+
+class LinearSolverB200:
+    """Mirror of g2o::LinearSolver<MatrixType> as the reference instantiates it (LinearSolverEigen, graphs.cpp:11,19):
+    init() forgets the pattern, solve(A, b) analyses the pattern on the first call after init() and solves. A is the
+    upper triangle in g2o's SparseBlockMatrix order: (block_dim [n], col_ptr [n+1], row_idx [nnzb], values)."""
+
+    def __init__(self, device=-1, pcg_tolerance=1e-10, pcg_max_iters=0):
+        self.opt = SparseOptimizerB200(capi.ALGO_GN, device=device, pcg_tolerance=pcg_tolerance, pcg_max_iters=pcg_max_iters)
+        self._have_pattern = False
+        self.last = {}
+
+    def init(self) -> bool:
+        self._have_pattern = False
+        return True
+
+    def solve(self, block_dim, col_ptr, row_idx, values, b):
+        """Returns (ok, x); ok == False is LinearSolver::solve() == false (matrix not positive definite)."""
+        L, h = self.opt.L, self.opt.h
+        if not self._have_pattern:
+            bd = np.ascontiguousarray(block_dim, np.int32)
+            cp = np.ascontiguousarray(col_ptr, np.int32)
+            ri = np.ascontiguousarray(row_idx, np.int32)
+            A = capi.BlockMatrix(len(bd), _p(bd), _p(cp), _p(ri))
+            self.opt._check(L.sgb_linear_set_pattern(h, C.byref(A)))
+            self._have_pattern = True
+        values = np.ascontiguousarray(values, np.float64)
+        b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros_like(b)
+        it, rel = C.c_int32(0), C.c_double(0.0)
+        st = L.sgb_linear_solve(h, _p(values), _p(b), _p(x), C.byref(it), C.byref(rel))
+        self.last = dict(pcg_iters=it.value, rel_residual=rel.value)
+        if st == capi.ERR_SOLVE_FAILED:
+            return False, x
+        self.opt._check(st)
+        return True, x

@@ -238,3 +238,49 @@ def test_batched_optimize_rejects_bad_batches():
     a = SparseOptimizerB200(capi.ALGO_LM)
     with pytest.raises(Exception):
         optimize_batch([a], 3)   # no graph set: "forgot to call initializeOptimization()"
+
+
+def _block_matrix_from_oracle(o, lam):
+    """(block_dim, col_ptr, row_idx, values, b) of H + lam*I in g2o's SparseBlockMatrix order, from the oracle."""
+    st = o.structure()
+    lin = o.linearize(JAC_ANALYTIC)
+    n = st["n_free"]
+    dim = np.where(st["kind"] == 0, 3, 2).astype(np.int32)
+    col_ptr = np.zeros(n + 1, np.int32)
+    np.add.at(col_ptr, st["col"] + 1, 1)
+    col_ptr = np.cumsum(col_ptr).astype(np.int32)
+    vals = lin["H"].copy()
+    off = 0
+    for r, c, nr, nc in zip(st["row"], st["col"], st["nrows"], st["ncols"]):
+        if r == c:
+            for d in range(nr):
+                vals[off + d * nr + d] += lam
+        off += nr * nc
+    return dim, col_ptr, st["row"].astype(np.int32), vals, lin["b"].copy()
+
+
+@pytest.mark.parametrize("name,lam", [("small", 1e-3), ("c1", 1.0), ("c1poses", 1e-2)])
+def test_linear_solver_level_drop_in(name, lam):
+    """SURVEY 8b narrower drop-in: LinearSolver::solve(A, x, b) with A handed over in g2o's block order."""
+    from sparse_gslam_b200.optimizer import LinearSolverB200
+    g = gg.make_c1().pose_only(phi=10.0) if name == "c1poses" else gg.make(name)
+    o = Oracle(g)
+    assert o.initialize_optimization()
+    dim, col_ptr, row_idx, vals, b = _block_matrix_from_oracle(o, lam)
+    ls = LinearSolverB200()
+    assert ls.init()
+    ok, x = ls.solve(dim, col_ptr, row_idx, vals, b)
+    assert ok
+    ok_o, xo = o.solve_once(lam, JAC_ANALYTIC)
+    assert ok_o
+    assert rel_err(x, xo) < 1e-7, (rel_err(x, xo), ls.last)
+    # second solve on the same pattern with other values (what every LM trial does): A' = A + I on the diagonal
+    dim2, _, _, vals2, _ = _block_matrix_from_oracle(o, lam + 1.0)
+    ok, x2 = ls.solve(dim, col_ptr, row_idx, vals2, b)
+    ok_o, xo2 = o.solve_once(lam + 1.0, JAC_ANALYTIC)
+    assert ok and rel_err(x2, xo2) < 1e-7
+    # not positive definite -> solve() == false, like LinearSolverEigen
+    bad = vals.copy()
+    bad[0] = -abs(bad[0]) - 1.0
+    ok, _ = ls.solve(dim, col_ptr, row_idx, bad, b)
+    assert not ok
