@@ -83,6 +83,9 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned 
   asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
   double v;
   asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -322,6 +325,7 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
     *s_last = (ticket == epoch - 1ull) ? 1 : 0;
   }
   __syncthreads();
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
   if (*s_last) {
     double loc[2] = {0.0, 0.0};
     if (nv > 0) {  // a pure barrier (nv == 0) publishes right away
@@ -330,23 +334,50 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
     }
     if (threadIdx.x < g.world) {
       Mailbox* mb = g.mbox[threadIdx.x];
-      for (int k = 0; k < nv; ++k) st_relaxed_sys_f64(&mb->val[slot][g.rank][k], loc[k]);
-      st_release_sys_u64(&mb->flag[slot][g.rank], seq);  // release: orders the values and, through the CTA barriers
-                                                          // and the ticket, everything this GPU wrote in the phase
+      if (nv == 0) {
+        st_release_sys_u64(&mb->flag[slot][g.rank], seq);  // release: through the CTA barriers and the ticket, everything
+                                                            // this GPU wrote in the phase
+      } else {
+        // everything this GPU wrote in the phase went to its OWN memory (peers read it through NVLink): one system
+        // fence orders it, then the values travel with their own flags -- no second fence behind a remote store
+        __threadfence_system();
+        for (int k = 0; k < nv; ++k) {
+          unsigned long long bits = (unsigned long long)__double_as_longlong(loc[k]);
+          st_relaxed_sys_u64(&mb->ll[slot][g.rank][k][0], (bits & 0xffffffffull) | tag);
+          st_relaxed_sys_u64(&mb->ll[slot][g.rank][k][1], (bits >> 32) | tag);
+        }
+      }
     }
   }
   const Mailbox* me = g.mbox[g.rank];
+  if (nv == 0) {
+    if (threadIdx.x < g.world) {
+      while (ld_relaxed_sys_u64(&me->flag[slot][threadIdx.x]) < seq) {
+      }
+      __threadfence();
+    }
+    __syncthreads();
+    return;
+  }
+  __syncthreads();  // the last CTA's reduce_partials is done with sm
   if (threadIdx.x < g.world) {
-    while (ld_relaxed_sys_u64(&me->flag[slot][threadIdx.x]) < seq) {
+    for (int k = 0; k < nv; ++k) {
+      unsigned long long lo, hi;
+      do {
+        lo = ld_relaxed_sys_u64(&me->ll[slot][threadIdx.x][k][0]);
+        hi = ld_relaxed_sys_u64(&me->ll[slot][threadIdx.x][k][1]);
+      } while ((lo & 0xffffffff00000000ull) != tag || (hi & 0xffffffff00000000ull) != tag);
+      sm[threadIdx.x * 2 + k] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
     }
     __threadfence();
   }
   __syncthreads();
   for (int k = 0; k < nv; ++k) {
     double acc = 0.0;
-    for (int o = 0; o < g.world; ++o) acc += ld_relaxed_sys_f64(&me->val[slot][o][k]);
+    for (int o = 0; o < g.world; ++o) acc += sm[o * 2 + k];  // rank order: the same sum on every CTA of every rank
     vals[k] = acc;
   }
+  __syncthreads();  // sm is reused by the caller's next block_sum
 }
 
 // Preconditioned conjugate gradient on S = (Hpp + lambda I) - Hpl (Hll + lambda I)^-1 Hpl^T, M = blockdiag(S).

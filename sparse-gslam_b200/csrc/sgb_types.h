@@ -39,6 +39,10 @@ struct Sell {
 struct Mailbox {
   unsigned long long flag[2][kMaxRanks];  // [parity][source rank] = sequence number of the last message
   double val[2][kMaxRanks][4];
+  // flag-in-data slots of the persistent PCG kernel's reductions: value k of source rank r travels as two 8-byte words
+  // {low 32 bits of the double | seq << 32} and {high 32 bits | seq << 32}; an 8-byte store is single-copy atomic, so the
+  // reader needs no separate flag and the writer no fence between value and flag (one NVLink round trip less)
+  unsigned long long ll[2][kMaxRanks][2][2];
 };
 
 struct DevGraph {
