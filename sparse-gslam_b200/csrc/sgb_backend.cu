@@ -74,6 +74,7 @@ struct sgb_handle {
   double* d_lm0 = nullptr;
   std::vector<std::pair<double*, double*>> stack;  // SparseOptimizer::push/pop backups (device)
   int pcg_blocks = 1;
+  int pcg_cluster = 0;  // > 0: the PCG grid is one thread-block cluster of this many CTAs (small graph, one GPU)
   // LinearSolver-level entry (sgb_linear_set_pattern / sgb_linear_solve): per input block its value offset, kind and
   // the SELL entries it lands in; device copies live in the pooled memory of the current graph
   struct LinearMap {
@@ -257,8 +258,23 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   prm.lambda_override = lambda_override;
   prm.use_override = use_override;
   SGB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), h->stream));
-  void* args[] = {&G, &sc, &part, &bar, &prm};
-  SGB_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(h->pcg_blocks), dim3(kThreads), args, 0, h->stream));
+  if (h->pcg_cluster > 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->pcg_cluster);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = h->pcg_cluster;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_cluster, G, sc, part, bar, prm));
+  } else {
+    void* args[] = {&G, &sc, &part, &bar, &prm};
+    SGB_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(h->pcg_blocks), dim3(kThreads), args, 0, h->stream));
+  }
   h->tm.kernel_launches++;
   return SGB_OK;
 }
@@ -780,6 +796,29 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   int limit = std::max(1, per_sm * h->sm_count);
   int want = std::max(1, (std::max(P.nP, 32 * P.Hlp.nslices) + kThreads - 1) / kThreads);
   h->pcg_blocks = std::min(std::min(limit, want), kMaxBlocks);
+  // a graph that fits <= 16 CTAs runs its PCG as one thread-block cluster (hardware barrier, partials through DSMEM)
+  h->pcg_cluster = 0;
+  static const bool no_cluster = std::getenv("SGB_NO_CLUSTER") != nullptr;
+  if (world == 1 && want <= 16 && !no_cluster) {
+    int cb = 1;
+    while (cb < want) cb <<= 1;
+    static bool attr_ok = cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (cb <= 8 || attr_ok) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cb);
+      cfg.blockDim = dim3(kThreads);
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cb;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_cluster, &cfg) == cudaSuccess && nclusters >= 1) h->pcg_cluster = cb;
+    }
+    cudaGetLastError();  // a refused cluster shape is not an error: the cooperative grid is used instead
+  }
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   lap("matrices+sync");
   h->has_graph = true;

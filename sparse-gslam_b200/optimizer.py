@@ -106,6 +106,29 @@ class SparseOptimizerB200:
         self.P, self.Lm = s.n_poses, s.n_landmarks
         return True
 
+    def initialize_optimization_device(self, g, dev, pp_slot=None, pl_slot=None, has_robust=None) -> bool:
+        """sgb_set_graph_device: the index arrays of `g` on the host, the values already in device memory. `dev` maps
+        pose_est / lm_est / pp_z / pp_info / pp_phi / pl_z / pl_info to device pointers (ints; e.g. torch tensors'
+        data_ptr()); pp_slot / pl_slot (host int arrays) give the device slot of every edge of `g`."""
+        s, keep = pack_graph(g)
+        dv = capi.DeviceValues()
+        for k in ("pose_est", "lm_est", "pp_z", "pp_info", "pp_phi", "pl_z", "pl_info"):
+            setattr(dv, k, dev.get(k) or None)
+        if pp_slot is not None:
+            pp_slot = np.ascontiguousarray(pp_slot, np.int32)
+            dv.pp_slot = _p(pp_slot)
+        if pl_slot is not None:
+            pl_slot = np.ascontiguousarray(pl_slot, np.int32)
+            dv.pl_slot = _p(pl_slot)
+        dv.has_robust = int(bool(np.any(g.pp_phi > 0)) if has_robust is None else has_robust)
+        st = self.L.sgb_set_graph_device(self.h, C.byref(s), C.byref(dv))
+        if st == capi.ERR_NOT_INITIALIZED:
+            return False
+        self._check(st)
+        self.g = g
+        self.P, self.Lm = s.n_poses, s.n_landmarks
+        return True
+
     def initialize_partitioned(self, g, world, rank, exchange):
         """Row-block partition across `world` GPUs (one process per GPU). `exchange(blob: bytes) -> list[bytes]` must
         return every rank's 64-byte blob in rank order (e.g. torch.distributed.all_gather_object)."""

@@ -517,3 +517,41 @@ def test_producers_empty_and_bad_arguments():
         fe.odom_information(np.zeros((3, 3)), [0, 2, 1], 0.1, 0.1, 0.1)
     with pytest.raises(SgbError):
         fe.line_fit_information(np.zeros((3, 2)), np.zeros((3, 4)), [1, 3])
+
+
+@gpu
+@pytest.mark.parametrize("name", ["small", "c1"])
+def test_set_graph_device_full_graph_with_slots(name):
+    """Pose + line-landmark graph whose values live in device memory in a DIFFERENT order than the index arrays (slot
+    lists): same linearisation and the same LM-15 result as the host path."""
+    import torch
+    from sparse_gslam_b200 import SparseOptimizerB200, capi
+    g = gg.make(name)
+    rng = np.random.default_rng(3)
+    perm_pp, perm_pl = rng.permutation(g.n_pp), rng.permutation(g.n_pl)  # device slot of edge k
+    def dev_edges(a, perm):
+        out = np.empty_like(a)
+        out[perm] = a
+        return torch.from_numpy(np.ascontiguousarray(out)).cuda()
+    t = dict(pose_est=torch.from_numpy(np.ascontiguousarray(g.pose_est)).cuda(), lm_est=torch.from_numpy(np.ascontiguousarray(g.lm_est)).cuda(),
+             pp_z=dev_edges(g.pp_z, perm_pp), pp_info=dev_edges(g.pp_info, perm_pp), pp_phi=dev_edges(g.pp_phi, perm_pp),
+             pl_z=dev_edges(g.pl_z, perm_pl), pl_info=dev_edges(g.pl_info, perm_pl))
+    torch.cuda.synchronize()
+    a = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
+    assert a.initialize_optimization(g)
+    b = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
+    assert b.initialize_optimization_device(g, {k: v.data_ptr() for k, v in t.items()}, perm_pp, perm_pl)
+    sa, sb = a.structure(), b.structure()
+    for k in ("kind", "index", "offset", "row", "col", "nrows", "ncols"):
+        assert np.array_equal(sa[k], sb[k])
+    la, lb = a.linearize(), b.linearize()
+    np.testing.assert_allclose(lb["H"], la["H"], rtol=1e-12, atol=1e-9)
+    np.testing.assert_allclose(lb["b"], la["b"], rtol=1e-9, atol=1e-7)
+    np.testing.assert_allclose(lb["chi2"], la["chi2"], rtol=1e-12)
+    na, _ = a.optimize(15)
+    nb, _ = b.optimize(15)
+    assert na == nb
+    pa, la_ = a.estimates()
+    pb, lb_ = b.estimates()
+    pose_close(pb, pa, 1e-8)
+    assert np.abs(lb_ - la_).max() < 1e-8 * max(1.0, np.abs(la_).max())
