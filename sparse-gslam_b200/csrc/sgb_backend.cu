@@ -818,6 +818,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
       if (cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_cluster, &cfg) == cudaSuccess && nclusters >= 1) h->pcg_cluster = cb;
     }
     cudaGetLastError();  // a refused cluster shape is not an error: the cooperative grid is used instead
+    if (prof) std::fprintf(stderr, "[sgb_set_graph] pcg cluster %d (wanted %d CTAs)\n", h->pcg_cluster, want);
   }
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   lap("matrices+sync");

@@ -284,3 +284,75 @@ def test_linear_solver_level_drop_in(name, lam):
     bad[0] = -abs(bad[0]) - 1.0
     ok, _ = ls.solve(dim, col_ptr, row_idx, bad, b)
     assert not ok
+
+
+def _numpy_chi2(g):
+    """activeChi2 of a graph, vectorised numpy (independent of the oracle and of the device code)."""
+    xi, xj = g.pose_est[g.pp_i], g.pose_est[g.pp_j]
+    e = gg.se2_between(g.pp_z, gg.se2_between(xi, xj))
+    u = g.pp_info
+    c_pp = (u[:, 0] * e[:, 0] ** 2 + u[:, 3] * e[:, 1] ** 2 + u[:, 5] * e[:, 2] ** 2 +
+            2 * (u[:, 1] * e[:, 0] * e[:, 1] + u[:, 2] * e[:, 0] * e[:, 2] + u[:, 4] * e[:, 1] * e[:, 2]))
+    pred = gg.line_in_pose_frame(g.pose_est[g.pl_pose], g.lm_est[g.pl_lm])
+    d = g.pl_z - pred
+    d[:, 1] = gg.wrap(d[:, 1])
+    v = g.pl_info
+    c_pl = v[:, 0] * d[:, 0] ** 2 + 2 * v[:, 1] * d[:, 0] * d[:, 1] + v[:, 2] * d[:, 1] ** 2
+    return float(c_pp.sum() + c_pl.sum())
+
+
+def _blocks_to_csr(st, vals):
+    """Symmetric scipy CSR from the block list in g2o order (upper triangle, column-major blocks)."""
+    import scipy.sparse as sp
+    nr, nc = st["nrows"].astype(np.int64), st["ncols"].astype(np.int64)
+    size = nr * nc
+    start = np.concatenate([[0], np.cumsum(size)[:-1]])
+    ro, co = st["offset"][st["row"]].astype(np.int64), st["offset"][st["col"]].astype(np.int64)
+    rows, cols, data = [], [], []
+    for (a, b) in ((3, 3), (3, 2), (2, 2)):
+        m = np.flatnonzero((nr == a) & (nc == b))
+        if m.size == 0:
+            continue
+        k = np.arange(a * b)
+        i, j = k % a, k // a  # column-major inside a block
+        idx = start[m][:, None] + k[None, :]
+        r = ro[m][:, None] + i[None, :]
+        c = co[m][:, None] + j[None, :]
+        offd = (st["row"][m] != st["col"][m])[:, None] & np.ones_like(r, bool)
+        rows += [r.ravel(), c[offd]]
+        cols += [c.ravel(), r[offd]]
+        data += [vals[idx].ravel(), vals[idx][offd]]
+    n = int(st["dim"])
+    return sp.coo_matrix((np.concatenate(data), (np.concatenate(rows), np.concatenate(cols))), shape=(n, n)).tocsr()
+
+
+@pytest.mark.slow
+def test_c5_full_size_properties():
+    """BASELINE's 1M-pose graph at full size, through properties that need no per-entry oracle run: chi2 against a
+    vectorised numpy restatement; the damped solve's residual ||(H + lambda I) x - b|| with H exported in g2o's block
+    order and multiplied by scipy on the host; chi2 never increases over accepted LM steps; push / pop restores."""
+    g = gg.make_c5()
+    a = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
+    assert a.initialize_optimization(g)
+    c_gpu = a.active_chi2()[0]
+    c_np = _numpy_chi2(g)
+    assert abs(c_gpu - c_np) <= 1e-9 * c_np, (c_gpu, c_np)
+    st = a.structure()
+    assert st["n_free_poses"] == g.P - 1 and st["n_free_landmarks"] == g.L and st["dim"] == 3 * (g.P - 1) + 2 * g.L
+    lin = a.linearize()
+    np.testing.assert_allclose(lin["chi2"][0], c_np, rtol=1e-9)
+    H = _blocks_to_csr(st, lin["H"])
+    assert abs(H - H.T).max() <= 1e-12 * abs(H).max()  # diagonal blocks A^T Omega A are symmetric up to rounding
+    lam = 1.0
+    ok, x, iters, rel = a.solve_once(lam)
+    assert ok and rel <= 1e-10
+    r = H @ x + lam * x - lin["b"]
+    assert np.linalg.norm(r) <= 1e-8 * np.linalg.norm(lin["b"]), np.linalg.norm(r) / np.linalg.norm(lin["b"])
+    a.push()
+    n, stats = a.optimize(3)
+    assert n == 3
+    chis = [lin["chi2"][1]] + [s["chi2"] for s in stats]
+    assert all(y <= x_ * (1 + 1e-12) for x_, y in zip(chis, chis[1:])) and chis[-1] < 0.9 * chis[0]
+    a.pop()
+    p, l = a.estimates()
+    assert np.array_equal(p, g.pose_est) and np.array_equal(l, g.lm_est)
