@@ -74,6 +74,7 @@ struct sgb_handle {
   double* d_lm0 = nullptr;
   std::vector<std::pair<double*, double*>> stack;  // SparseOptimizer::push/pop backups (device)
   int pcg_blocks = 1;
+  bool no_small = std::getenv("SGB_NO_SMALL") != nullptr;  // tuning runs: always the throughput build of k_pcg
   int pcg_cluster = 0;  // > 0: the PCG grid is one thread-block cluster of this many CTAs (small graph, one GPU)
   // LinearSolver-level entry (sgb_linear_set_pattern / sgb_linear_solve): per input block its value offset, kind and
   // the SELL entries it lands in; device copies live in the pooled memory of the current graph
@@ -273,7 +274,10 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
     SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_cluster, G, sc, part, bar, prm));
   } else {
     void* args[] = {&G, &sc, &part, &bar, &prm};
-    SGB_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(h->pcg_blocks), dim3(kThreads), args, 0, h->stream));
+    // at most one CTA per SM and a single GPU: the latency-oriented build of the same kernel
+    const bool small = h->pcg_blocks <= h->sm_count && G.world == 1 && !h->no_small;
+    SGB_CUDA(cudaLaunchCooperativeKernel(small ? (void*)k_pcg_small : (void*)k_pcg, dim3(h->pcg_blocks), dim3(kThreads), args, 0,
+                                         h->stream));
   }
   h->tm.kernel_launches++;
   return SGB_OK;

@@ -433,6 +433,7 @@ struct PcgOut {
 // The solve itself, shared by the persistent multi-CTA kernel (k_pcg: tid / nthreads span the grid, `bar` is the grid
 // barrier counter) and the one-CTA-per-graph batched kernel (k_lm_block: tid / nthreads span the block, bar == NULL).
 // ph_ns / t_ph: shared-memory phase timers of the calling CTA.
+template <int U = 2>  // blocks in flight per thread in the pose-major pass (see schur_phaseB_row_u)
 __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, const int nthreads, const unsigned int nb,
                                           double* part, unsigned long long* bar, unsigned long long& seq,
                                           const PcgParams& prm, const double lambda, double* sm, int* s_last,
@@ -489,7 +490,7 @@ __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, cons
         grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, s_last, cl_part);  // every rank's t segment is complete
       }
       SGB_PHASE_LAP(0);
-      acc = schur_phaseB_rows(g, tid, nthreads, lambda, beta);
+      acc = schur_phaseB_rows_u<U>(g, tid, nthreads, lambda, beta);
       double del = block_sum(acc, sm);
       grid_xreduce(g, bar, nb, epoch, seq, part, &del, 1, sm, s_last, cl_part);
       SGB_PHASE_LAP(1);
@@ -553,11 +554,39 @@ __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g
   }
 }
 
+// The same kernel for a graph whose grid is at most one CTA per SM (every thread owns at most one pose row and the
+// graph sits in L2): occupancy is irrelevant, the dependent-latency chain of a row is what counts, so the pose-major
+// pass keeps eight blocks in flight (up to 255 registers).
+__global__ void __launch_bounds__(kThreads, 1) k_pcg_small(DevGraph g, DevScalars* sc, double* part, unsigned long long* bar,
+                                                          PcgParams prm) {
+  __shared__ double sm[32];
+  __shared__ int s_last;
+  __shared__ unsigned long long ph_ns[4], t_ph;
+  if (threadIdx.x == 0) {
+    ph_ns[0] = ph_ns[1] = ph_ns[2] = ph_ns[3] = 0;
+    t_ph = globaltimer_ns();
+  }
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long seq = sc->xseq;
+  const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
+  PcgOut out;
+  pcg_solve<8>(g, tid, gridDim.x * blockDim.x, gridDim.x, part, bar, seq, prm, lambda, sm, &s_last, ph_ns, &t_ph, out);
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) sc->pcg_phase_ns[i] += ph_ns[i];
+    sc->xseq = seq;
+    sc->rz0 = out.gam0;
+    sc->rz = out.gam;
+    sc->pcg_iters = out.iters;
+    sc->pcg_flag = out.flag;
+    sc->pcg_rel = out.gam0 > 0.0 ? sqrt(fabs(out.gam) / out.gam0) : 0.0;
+  }
+}
+
 // The same solve for a graph small enough for ONE thread-block cluster (launched with a cluster dimension equal to the
 // grid, <= 16 CTAs, one GPU): see grid_xreduce. bar must be non-NULL only to tell pcg_solve that the grid has more than
 // one CTA; it is never dereferenced on this path.
-__global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg_cluster(DevGraph g, DevScalars* sc, double* part,
-                                                                             unsigned long long* bar, PcgParams prm) {
+__global__ void __launch_bounds__(kThreads, 1) k_pcg_cluster(DevGraph g, DevScalars* sc, double* part,
+                                                            unsigned long long* bar, PcgParams prm) {
   __shared__ double sm[32];
   __shared__ double cl_part[4];
   __shared__ int s_last;
@@ -570,7 +599,7 @@ __global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg_cluster(De
   unsigned long long seq = sc->xseq;
   const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   PcgOut out;
-  pcg_solve(g, tid, gridDim.x * blockDim.x, gridDim.x, part, bar, seq, prm, lambda, sm, &s_last, ph_ns, &t_ph, out, cl_part);
+  pcg_solve<8>(g, tid, gridDim.x * blockDim.x, gridDim.x, part, bar, seq, prm, lambda, sm, &s_last, ph_ns, &t_ph, out, cl_part);
   if (tid == 0) {
     for (int i = 0; i < 4; ++i) sc->pcg_phase_ns[i] += ph_ns[i];
     sc->xseq = seq;

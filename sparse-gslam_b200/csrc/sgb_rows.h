@@ -621,10 +621,101 @@ SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, const PoseRowMeta& m, 
 SGB_HD double schur_phaseB_row(const DevGraph& g, int lp, double lambda, double beta) {
   return schur_phaseB_row(g, lp, pose_row_meta(g, lp), lambda, beta);
 }
+// The same row with U blocks in flight instead of two. On a graph that fits L2 a row is a chain of dependent L2
+// latencies -- one per pair of blocks above -- and a thread owns a single row, so registers are not scarce: with U = 8 a
+// whole row of Hpp (and of Hpl) is requested at once. Blocks are accumulated in the same order with the same expressions,
+// so the result is bit-identical to the two-block version (padding adds +0.0).
+template <int U>
+SGB_HD double schur_phaseB_row_u(const DevGraph& g, int lp, const PoseRowMeta& m, double lambda, double beta) {
+  const double* vown = g.p[g.rank] + 3 * (size_t)lp;
+  const int wpp = m.wpp, bpp = m.bpp, wpl = m.wpl, bpl = m.bpl;
+  double* d = g.d + 3 * (size_t)lp;
+  double* sv = g.s + 3 * (size_t)lp;
+  const int32_t* cpp = g.Hpp.col;
+  const int32_t* cpl = g.Hpl.col;
+  int enc[U], ln[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) enc[u] = sell_col_or_pad(cpp, bpp + 32 * u, wpp > u);
+#pragma unroll
+  for (int u = 0; u < U; ++u) ln[u] = sell_col_or_pad(cpl, bpl + 32 * u, wpl > u);
+  // the six operands of the direction recurrences are requested up front as well
+  const double dold0 = SGB_LDCG(d), dold1 = SGB_LDCG(d + 1), dold2 = SGB_LDCG(d + 2);
+  const double sold0 = SGB_LDCG(sv), sold1 = SGB_LDCG(sv + 1), sold2 = SGB_LDCG(sv + 2);
+  double vi0 = SGB_LDCG(vown), vi1 = SGB_LDCG(vown + 1), vi2 = SGB_LDCG(vown + 2);
+  double q0 = lambda * vi0, q1 = lambda * vi1, q2 = lambda * vi2;
+  for (int k = 0; k < wpp; k += U) {
+    int nx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) nx[u] = sell_col_or_pad(cpp, bpp + 32 * (k + U + u), k + U + u < wpp);
+    double v[U][3], a[U][9];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      for (int c = 0; c < 3; ++c) v[u][c] = 0.0;
+      for (int c = 0; c < 9; ++c) a[u][c] = 0.0;
+      if (enc[u] >= 0) {
+        const double* pv = g.p[enc[u] >> kOwnerShift] + 3 * (size_t)(enc[u] & kLocalMask);
+        const double* pa = g.Hpp.vals + sell_vaddr(bpp + 32 * (k + u), 9, 0);
+        for (int c = 0; c < 3; ++c) v[u][c] = SGB_LDCG(pv + c);
+        for (int c = 0; c < 9; ++c) a[u][c] = SGB_LDG(pa + 32 * c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      q0 += a[u][0] * v[u][0] + a[u][1] * v[u][1] + a[u][2] * v[u][2];
+      q1 += a[u][3] * v[u][0] + a[u][4] * v[u][1] + a[u][5] * v[u][2];
+      q2 += a[u][6] * v[u][0] + a[u][7] * v[u][1] + a[u][8] * v[u][2];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) enc[u] = nx[u];
+  }
+  for (int k = 0; k < wpl; k += U) {
+    int nx[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) nx[u] = sell_col_or_pad(cpl, bpl + 32 * (k + U + u), k + U + u < wpl);
+    double tv[U][2], a[U][6];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      tv[u][0] = tv[u][1] = 0.0;
+      for (int c = 0; c < 6; ++c) a[u][c] = 0.0;
+      if (ln[u] >= 0) {
+        const double* pt = g.t[ln[u] >> kOwnerShift] + 2 * (size_t)(ln[u] & kLocalMask);
+        const double* pa = g.Hpl.vals + sell_vaddr(bpl + 32 * (k + u), 6, 0);
+        Pair64 tt = ldcg_pair(pt);
+        tv[u][0] = tt.a;
+        tv[u][1] = tt.b;
+        for (int c = 0; c < 6; ++c) a[u][c] = SGB_LDG(pa + 32 * c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      q0 -= a[u][0] * tv[u][0] + a[u][1] * tv[u][1];
+      q1 -= a[u][2] * tv[u][0] + a[u][3] * tv[u][1];
+      q2 -= a[u][4] * tv[u][0] + a[u][5] * tv[u][1];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) ln[u] = nx[u];
+  }
+  const double d0 = vi0 + beta * dold0, d1 = vi1 + beta * dold1, d2 = vi2 + beta * dold2;
+  const double s0 = q0 + beta * sold0, s1 = q1 + beta * sold1, s2 = q2 + beta * sold2;
+  d[0] = d0;
+  d[1] = d1;
+  d[2] = d2;
+  sv[0] = s0;
+  sv[1] = s1;
+  sv[2] = s2;
+  return vi0 * q0 + vi1 * q1 + vi2 * q2;
+}
 // the rows lp0, lp0 + stride, ... of one thread
 SGB_HD double schur_phaseB_rows(const DevGraph& g, int lp0, int stride, double lambda, double beta) {
   double acc = 0.0;
   for (int lp = lp0; lp < g.nP; lp += stride) acc += schur_phaseB_row(g, lp, pose_row_meta(g, lp), lambda, beta);
+  return acc;
+}
+template <int U>
+SGB_HD double schur_phaseB_rows_u(const DevGraph& g, int lp0, int stride, double lambda, double beta) {
+  if (U <= 2) return schur_phaseB_rows(g, lp0, stride, lambda, beta);
+  double acc = 0.0;
+  for (int lp = lp0; lp < g.nP; lp += stride) acc += schur_phaseB_row_u<(U > 2 ? U : 4)>(g, lp, pose_row_meta(g, lp), lambda, beta);
   return acc;
 }
 // z_i = Minv_i r_i ; returns r_i . z_i
