@@ -243,8 +243,12 @@ sgb_status launch_setup(sgb_handle* h, double lambda_override, int use_override)
     k_xbarrier<<<1, 32, 0, h->stream>>>(G, h->d_sc);
     h->tm.kernel_launches++;
   }
-  if (G.nP > 0) k_setup_pose<<<grid_for(G.nP), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
-  h->tm.kernel_launches += (G.nP > 0) + (G.nL > 0);
+  if (G.nP > 0) {
+    const int nch = (G.nP + kChunk - 1) / kChunk;
+    k_setup_chunk<<<std::max(1, std::min((nch + 127) / 128, 148 * 16)), 128, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
+    k_setup_pose<<<grid_for(G.nP), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
+  }
+  h->tm.kernel_launches += 2 * (G.nP > 0) + (G.nL > 0);
   SGB_CUDA(cudaGetLastError());
   return SGB_OK;
 }
@@ -788,7 +792,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   if ((st = dalloc(h, &G.Hll, 3 * (size_t)P.nL)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.b_p, n3)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.x_l, n2)) != SGB_OK) return st;
-  if ((st = dalloc(h, &G.Minv, 9 * (size_t)P.nP)) != SGB_OK) return st;
+  if ((st = dalloc(h, &G.Cinv, 3 * 3 * kChunk * (size_t)P.nP)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.bt, n3)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.r, n3)) != SGB_OK) return st;
   if ((st = dalloc(h, &G.d, n3)) != SGB_OK) return st;

@@ -255,6 +255,14 @@ __global__ void __launch_bounds__(kThreads) k_setup_lm(DevGraph g, DevScalars* s
   for (int ll = blockIdx.x * blockDim.x + threadIdx.x; ll < g.nL; ll += gridDim.x * blockDim.x) ok &= setup_lm_row(g, ll, lambda);
   if (!ok) atomicOr(&sc->setup_fail, 1);
 }
+// one thread per block of the block-Jacobi preconditioner (kChunk pose rows)
+__global__ void __launch_bounds__(128) k_setup_chunk(DevGraph g, DevScalars* sc, double lambda_override, int use_override) {
+  double lambda = use_override ? lambda_override : sc->lambda;
+  bool ok = true;
+  const int nch = (g.nP + kChunk - 1) / kChunk;
+  for (int ch = blockIdx.x * blockDim.x + threadIdx.x; ch < nch; ch += gridDim.x * blockDim.x) ok &= setup_chunk(g, ch, lambda);
+  if (!ok) atomicOr(&sc->setup_fail, 1);
+}
 __global__ void __launch_bounds__(kThreads) k_setup_pose(DevGraph g, DevScalars* sc, double lambda_override, int use_override) {
   double lambda = use_override ? lambda_override : sc->lambda;
   bool ok = true;
@@ -451,11 +459,16 @@ __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, cons
   double* x = g.x_p[g.rank];
   double* zin = g.p[g.rank];
 
-  // x = 0, r = bt, z = Minv r, d = s = 0
+  // x = 0, r = bt, z = M^-1 r, d = s = 0. The kChunk lanes of a preconditioner block run the loop together (the
+  // condition is uniform inside such a group: row and lane index agree in their low bits).
   double acc = 0.0;
-  for (int lp = tid; lp < g.nP; lp += nthreads) {
-    double r[3] = {g.bt[3 * (size_t)lp], g.bt[3 * (size_t)lp + 1], g.bt[3 * (size_t)lp + 2]}, z[3];
-    acc += precond_row(g, lp, r, z);
+  for (int lp = tid; (lp & ~(kChunk - 1)) < g.nP; lp += nthreads) {
+    const bool act = lp < g.nP;
+    double r[3] = {0.0, 0.0, 0.0}, z[3];
+    if (act)
+      for (int c = 0; c < 3; ++c) r[c] = g.bt[3 * (size_t)lp + c];
+    acc += precond_row_shfl(g, lp, act, r, z);
+    if (act)
     for (int c = 0; c < 3; ++c) {
       size_t o = 3 * (size_t)lp + c;
       x[o] = 0.0;
@@ -501,16 +514,19 @@ __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, cons
       }
       const double alpha = gam / denom;
       acc = 0.0;
-      for (int lp = tid; lp < g.nP; lp += nthreads) {
-        double r[3], z[3];
-        for (int c = 0; c < 3; ++c) {
-          size_t o = 3 * (size_t)lp + c;
-          x[o] += alpha * g.d[o];
-          r[c] = g.r[o] - alpha * g.s[o];
-          g.r[o] = r[c];
-        }
-        acc += precond_row(g, lp, r, z);
-        for (int c = 0; c < 3; ++c) zin[3 * (size_t)lp + c] = z[c];
+      for (int lp = tid; (lp & ~(kChunk - 1)) < g.nP; lp += nthreads) {
+        const bool act = lp < g.nP;
+        double r[3] = {0.0, 0.0, 0.0}, z[3];
+        if (act)
+          for (int c = 0; c < 3; ++c) {
+            size_t o = 3 * (size_t)lp + c;
+            x[o] += alpha * g.d[o];
+            r[c] = g.r[o] - alpha * g.s[o];
+            g.r[o] = r[c];
+          }
+        acc += precond_row_shfl(g, lp, act, r, z);
+        if (act)
+          for (int c = 0; c < 3; ++c) zin[3 * (size_t)lp + c] = z[c];
       }
       ++it;
       gam_old = gam;
@@ -780,6 +796,7 @@ __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, B
       for (int ll = tid; ll < g.nL; ll += nth) ok &= setup_lm_row(g, ll, lambda);
       __syncthreads();
       for (int lp = tid; lp < g.nP; lp += nth) ok &= setup_pose_row(g, lp, lambda);
+      for (int ch = tid; ch < (g.nP + kChunk - 1) / kChunk; ch += nth) ok &= setup_chunk(g, ch, lambda);
       if (tid == 0) s_ok = 1;
       __syncthreads();
       if (!ok) atomicAnd(&s_ok, 0);

@@ -359,9 +359,115 @@ SGB_HD bool setup_pose_row(const DevGraph& g, int lp, double lambda) {
     }
   }
   double Mi[9];
-  bool ok = inv3_spd(M, Mi);
-  for (int c = 0; c < 9; ++c) g.Minv[(size_t)c * g.nP + lp] = Mi[c];
+  bool ok = inv3_spd(M, Mi);  // positive-definiteness check of the 3x3 diagonal block (the preconditioner is setup_chunk's)
   for (int r = 0; r < 3; ++r) g.bt[3 * (size_t)lp + r] = bt[r];
+  return ok;
+}
+
+// In-place inverse of a symmetric positive definite N x N matrix (row-major) through its Cholesky factor; false when a
+// pivot is not positive / not finite (the matrix is then left in an unspecified state).
+template <int N>
+SGB_HD bool inv_spd_inplace(double* A) {
+  bool ok = true;
+  for (int j = 0; j < N; ++j) {  // A = L L^T, L stored in the lower triangle
+    double dj = A[j * N + j];
+    for (int k = 0; k < j; ++k) dj -= A[j * N + k] * A[j * N + k];
+    ok = ok && (dj > 0.0) && (dj < 1e300);
+    double lj = sqrt(dj);
+    A[j * N + j] = lj;
+    double inv = 1.0 / lj;
+    for (int i = j + 1; i < N; ++i) {
+      double v = A[i * N + j];
+      for (int k = 0; k < j; ++k) v -= A[i * N + k] * A[j * N + k];
+      A[i * N + j] = v * inv;
+    }
+  }
+  for (int j = 0; j < N; ++j) {  // L <- L^-1 (lower triangular), column by column
+    A[j * N + j] = 1.0 / A[j * N + j];
+    for (int i = j + 1; i < N; ++i) {
+      double v = 0.0;
+      for (int k = j; k < i; ++k) v -= A[i * N + k] * A[k * N + j];
+      A[i * N + j] = v / A[i * N + i];
+    }
+  }
+  for (int i = 0; i < N; ++i)  // A^-1 = L^-T L^-1: entry (i, j), j >= i, = sum_{k >= j} Linv[k][i] Linv[k][j]; upper triangle
+    for (int j = i; j < N; ++j) {
+      double v = 0.0;
+      for (int k = j; k < N; ++k) v += A[k * N + i] * A[k * N + j];
+      A[i * N + j] = v;  // rows < k of column i / j are not read again for (i', j') >= (i, j) in this order? see below
+    }
+  return ok;
+}
+
+// Block-Jacobi preconditioner with blocks of kChunk consecutive pose rows: the 12 x 12 diagonal block of the Schur
+// complement S = (Hpp + lambda I) - Hpl (Hll + lambda I)^-1 Hpl^T -- pose-pose blocks inside the chunk (the odometry
+// chain, mostly) plus the coupling of chunk-mates that observe the same landmark -- inverted exactly. Pose row lp
+// stores its three rows of the inverse: Cinv[(3 r + m... ) see precond_mul. One thread per chunk (once per LM trial).
+// A chunk never spans two 32-row slices (32 is a multiple of kChunk). Poses missing from the last chunk get identity.
+SGB_HD bool setup_chunk(const DevGraph& g, int ch, double lambda) {
+  constexpr int N = 3 * kChunk;
+  const int p0 = ch * kChunk;
+  const int np = (g.nP - p0 < kChunk) ? g.nP - p0 : kChunk;
+  double D[N * N];
+  for (int i = 0; i < N * N; ++i) D[i] = 0.0;
+  const int slice = p0 >> 5;
+  const int wpp = sell_width(g.Hpp, slice), bpp = g.Hpp.sbase[slice];
+  const bool has_pl = g.Hpl.rows > 0;
+  const int wpl = has_pl ? sell_width(g.Hpl, slice) : 0, bpl = has_pl ? g.Hpl.sbase[slice] : 0;
+  for (int a = 0; a < np; ++a) {
+    const int lane = (p0 + a) & 31;
+    for (int k = 0; k < wpp; ++k) {
+      const int e = bpp + k * 32 + lane;
+      const int enc = SGB_LDG(&g.Hpp.col[e]);
+      if (enc < 0) continue;
+      if ((enc >> kOwnerShift) != g.rank) continue;
+      const int b = (enc & kLocalMask) - p0;
+      if (b < a || b >= np) continue;  // upper triangle of the chunk (the diagonal entry included)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) D[(3 * a + r) * N + 3 * b + c] += g.Hpp.vals[sell_vaddr(e, 9, 3 * r + c)];
+    }
+    for (int r = 0; r < 3; ++r) D[(3 * a + r) * N + 3 * a + r] += lambda;
+    for (int k = 0; k < wpl; ++k) {
+      const int e = bpl + k * 32 + lane;
+      const int enc = SGB_LDG(&g.Hpl.col[e]);
+      if (enc < 0) continue;
+      const int o = enc >> kOwnerShift, l = enc & kLocalMask;
+      double B[6];
+      for (int c = 0; c < 6; ++c) B[c] = g.Hpl.vals[sell_vaddr(e, 6, c)];
+      const double* W = g.Hll_inv[o];
+      const double w11 = SGB_LDCG(&W[l]), w12 = SGB_LDCG(&W[(size_t)g.capL + l]), w22 = SGB_LDCG(&W[2 * (size_t)g.capL + l]);
+      double BW[6];
+      for (int r = 0; r < 3; ++r) {
+        BW[2 * r] = B[2 * r] * w11 + B[2 * r + 1] * w12;
+        BW[2 * r + 1] = B[2 * r] * w12 + B[2 * r + 1] * w22;
+      }
+      for (int b = a; b < np; ++b) {  // chunk-mates (and the pose itself) that observe the same landmark
+        const int lane_b = (p0 + b) & 31;
+        for (int k2 = 0; k2 < wpl; ++k2) {
+          const int e2 = bpl + k2 * 32 + lane_b;
+          if (SGB_LDG(&g.Hpl.col[e2]) != enc) continue;
+          for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+              D[(3 * a + r) * N + 3 * b + c] -= BW[2 * r] * g.Hpl.vals[sell_vaddr(e2, 6, 2 * c)] +
+                                               BW[2 * r + 1] * g.Hpl.vals[sell_vaddr(e2, 6, 2 * c + 1)];
+          break;
+        }
+      }
+    }
+  }
+  for (int a = np; a < kChunk; ++a)
+    for (int r = 0; r < 3; ++r) D[(3 * a + r) * N + 3 * a + r] = 1.0;
+  for (int i = 0; i < N; ++i)  // the diagonal blocks were accumulated in full, the off-diagonal ones in the upper part
+    for (int j = i + 1; j < N; ++j)
+      if (j / 3 != i / 3) D[j * N + i] = D[i * N + j];
+  const bool ok = inv_spd_inplace<N>(D);
+  for (int a = 0; a < np; ++a)
+    for (int r = 0; r < 3; ++r)
+      for (int m = 0; m < N; ++m) {
+        const int i = 3 * a + r;
+        const double v = m >= i ? D[i * N + m] : D[m * N + i];  // the inverse is returned in the upper triangle
+        g.Cinv[(size_t)(r * N + m) * g.nP + p0 + a] = v;
+      }
   return ok;
 }
 
@@ -718,15 +824,45 @@ SGB_HD double schur_phaseB_rows_u(const DevGraph& g, int lp0, int stride, double
   for (int lp = lp0; lp < g.nP; lp += stride) acc += schur_phaseB_row_u<(U > 2 ? U : 4)>(g, lp, pose_row_meta(g, lp), lambda, beta);
   return acc;
 }
-// z_i = Minv_i r_i ; returns r_i . z_i
-SGB_HD double precond_row(const DevGraph& g, int lp, const double r[3], double z[3]) {
-  const double* m = g.Minv + lp;
-  size_t s = (size_t)g.nP;
-  z[0] = SGB_LDG(m) * r[0] + SGB_LDG(m + s) * r[1] + SGB_LDG(m + 2 * s) * r[2];
-  z[1] = SGB_LDG(m + 3 * s) * r[0] + SGB_LDG(m + 4 * s) * r[1] + SGB_LDG(m + 5 * s) * r[2];
-  z[2] = SGB_LDG(m + 6 * s) * r[0] + SGB_LDG(m + 7 * s) * r[1] + SGB_LDG(m + 8 * s) * r[2];
-  return r[0] * z[0] + r[1] * z[1] + r[2] * z[2];
+// z_i = sum_j Cinv_ij r_j over the kChunk poses j of row lp's chunk (rr = their residuals, 3 per pose, zeros for poses
+// beyond nP); returns r_i . z_i
+SGB_HD double precond_mul(const DevGraph& g, int lp, const double rr[3 * kChunk], double z[3]) {
+  constexpr int N = 3 * kChunk;
+  const double* m = g.Cinv + lp;
+  const size_t s = (size_t)g.nP;
+  for (int r = 0; r < 3; ++r) {
+    double acc = 0.0;
+    for (int c = 0; c < N; ++c) acc += SGB_LDG(m + (size_t)(r * N + c) * s) * rr[c];
+    z[r] = acc;
+  }
+  const int a = lp & (kChunk - 1);
+  return rr[3 * a] * z[0] + rr[3 * a + 1] * z[1] + rr[3 * a + 2] * z[2];
 }
+// host form (test harness): the chunk-mates' residuals are read from the residual vector rvec [3 * nP]
+SGB_HD double precond_row_from(const DevGraph& g, int lp, const double* rvec, double z[3]) {
+  double rr[3 * kChunk];
+  const int p0 = lp & ~(kChunk - 1);
+  for (int j = 0; j < kChunk; ++j)
+    for (int c = 0; c < 3; ++c) rr[3 * j + c] = (p0 + j < g.nP) ? rvec[3 * (size_t)(p0 + j) + c] : 0.0;
+  return precond_mul(g, lp, rr, z);
+}
+#if defined(__CUDACC__)
+// device form: the kChunk lanes that hold the rows of one chunk (consecutive lanes: row index and lane index agree in
+// their low bits) exchange their residuals with shuffles. EVERY lane of such a group must call it (active = false and
+// r = 0 for a lane whose row is beyond nP).
+__device__ __forceinline__ double precond_row_shfl(const DevGraph& g, int lp, bool active, const double r[3], double z[3]) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned base = lane & ~(unsigned)(kChunk - 1);
+  const unsigned mask = ((1u << kChunk) - 1u) << base;
+  double rr[3 * kChunk];
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rr[3 * j + c] = __shfl_sync(mask, r[c], (int)(base + j));
+  z[0] = z[1] = z[2] = 0.0;
+  return active ? precond_mul(g, lp, rr, z) : 0.0;
+}
+#endif
 
 // SparseOptimizer::update for one owned free vertex: reads the current estimate, writes the new one into buffer
 // `dst` of EVERY rank (estimates are replicated; the owner pushes its rows over NVLink); returns the vertex's share

@@ -12,6 +12,7 @@
 namespace sgb {
 
 constexpr int kMaxRanks = 8;
+constexpr int kChunk = 4;  // pose rows per block of the block-Jacobi preconditioner (12x12 scalar blocks)
 constexpr int kOwnerShift = 26;  // up to 64M rows per rank
 constexpr int kLocalMask = (1 << kOwnerShift) - 1;
 
@@ -106,7 +107,8 @@ struct DevGraph {
   Mailbox* mbox[kMaxRanks];
   // ---- local only
   double* x_l;               // [2*nL] landmark step
-  double* Minv;              // [9][nP] block-Jacobi preconditioner = inverse of the Schur diagonal block
+  double* Cinv;              // [36][nP] block-Jacobi preconditioner with blocks of kChunk = 4 consecutive pose rows: pose
+                             //          row lp holds its 3 rows (x 12 columns) of the inverse 12x12 Schur diagonal block
   double* bt;                // [3*nP] reduced right-hand side
   double* r;                 // residual
   double* d;                 // search direction

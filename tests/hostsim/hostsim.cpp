@@ -108,7 +108,7 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
     mk_sell(r, &G.Hpp, P.Hpp, 9); mk_sell(r, &G.Hpl, P.Hpl, 6); mk_sell(r, &G.Hlp, P.Hlp, 6);
     size_t n3 = 3 * (size_t)P.nP, n2 = 2 * (size_t)P.nL;
     G.Hll = r->D(3 * (size_t)P.nL); G.b_p = r->D(n3); G.x_l = r->D(n2);
-    G.Minv = r->D(9 * (size_t)P.nP); G.bt = r->D(n3); G.r = r->D(n3); G.d = r->D(n3); G.s = r->D(n3);
+    G.Cinv = r->D(3 * 3 * kChunk * (size_t)P.nP); G.bt = r->D(n3); G.r = r->D(n3); G.d = r->D(n3); G.s = r->D(n3);
     // the "arena": arrays other ranks reach into
     for (int b = 0; b < 2; ++b) {
       G.pose_buf[b][rk] = r->D(np); G.lm_buf[b][rk] = r->D(nl);
@@ -278,14 +278,16 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
   bool ok = true;
   for (auto& r : h->R) for (int ll = 0; ll < r->G.nL; ++ll) ok &= setup_lm_row(r->G, ll, lambda);
   for (auto& r : h->R) for (int lp = 0; lp < r->G.nP; ++lp) ok &= setup_pose_row(r->G, lp, lambda);
+  for (auto& r : h->R) for (int ch = 0; ch < (r->G.nP + kChunk - 1) / kChunk; ++ch) ok &= setup_chunk(r->G, ch, lambda);
   double gam = 0;
   for (auto& rk : h->R) {
     DevGraph& G = rk->G;
     double* x = G.x_p[G.rank]; double* zin = G.p[G.rank];
-    for (int lp = 0; lp < G.nP; ++lp) {
-      double r[3] = {G.bt[3 * lp], G.bt[3 * lp + 1], G.bt[3 * lp + 2]}, z[3];
-      gam += precond_row(G, lp, r, z);
-      for (int c = 0; c < 3; ++c) { x[3 * lp + c] = 0; G.r[3 * lp + c] = r[c]; zin[3 * lp + c] = z[c]; G.d[3 * lp + c] = 0; G.s[3 * lp + c] = 0; }
+    for (int i = 0; i < 3 * G.nP; ++i) { x[i] = 0; G.r[i] = G.bt[i]; G.d[i] = 0; G.s[i] = 0; }
+    for (int lp = 0; lp < G.nP; ++lp) {  // the device exchanges the chunk's residuals with shuffles; here they are in G.r
+      double z[3];
+      gam += precond_row_from(G, lp, G.r, z);
+      for (int c = 0; c < 3; ++c) zin[3 * lp + c] = z[c];
     }
   }
   double gam0 = gam, gam_old = 0, alpha_old = 0;
@@ -311,15 +313,13 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
       for (auto& rk : h->R) {
         DevGraph& G = rk->G;
         double* x = G.x_p[G.rank]; double* zin = G.p[G.rank];
+        for (size_t o = 0; o < 3 * (size_t)G.nP; ++o) {
+          x[o] += alpha * G.d[o];
+          G.r[o] = G.r[o] - alpha * G.s[o];
+        }
         for (int lp = 0; lp < G.nP; ++lp) {
-          double r[3], z[3];
-          for (int c = 0; c < 3; ++c) {
-            size_t o = 3 * (size_t)lp + c;
-            x[o] += alpha * G.d[o];
-            r[c] = G.r[o] - alpha * G.s[o];
-            G.r[o] = r[c];
-          }
-          gnew += precond_row(G, lp, r, z);
+          double z[3];
+          gnew += precond_row_from(G, lp, G.r, z);
           for (int c = 0; c < 3; ++c) zin[3 * (size_t)lp + c] = z[c];
         }
       }

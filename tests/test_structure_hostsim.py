@@ -196,7 +196,9 @@ def test_partition_covers_graph_and_matches_single_rank(world):
     assert many.check_hlp() == 0.0 and one.check_hlp() == 0.0
     f1, x1, it1, _ = one.solve_once(0.3)
     fm, xm, itm, _ = many.solve_once(0.3)
-    assert f1 == fm == 0 and abs(it1 - itm) <= 2
+    # the preconditioner's 4-pose blocks are rank-local (they never span a cut and their alignment follows the rank's
+    # first row), so the iteration count may differ a little between partitions; the solution may not
+    assert f1 == fm == 0 and abs(it1 - itm) <= max(2, 0.25 * it1)
     np.testing.assert_allclose(xm, x1, rtol=1e-9, atol=1e-12)
     n1, s1 = one.optimize(6, capi.ALGO_LM)
     nm, sm = many.optimize(6, capi.ALGO_LM)
