@@ -139,12 +139,12 @@ def graph_h2d_bytes(g):
 def pcg_bytes_per_iteration(st):
     """Algorithmic bytes of one PCG iteration on the implicit Schur complement:
     Hpp blocks 76 B (72 values + 4 index), Hpl blocks 52 B read twice (pose-major and landmark-major pass),
-    (Hll+lambda I)^-1 24 B and t 2x16 B per landmark, vectors 312 B per pose and the preconditioner 288 B per pose
-    (three rows of the inverse 12x12 block of the pose's 4-row chunk; 72 B with the former 3x3 blocks)."""
+    (Hll+lambda I)^-1 24 B and t 2x16 B per landmark, vectors 312 B per pose and the preconditioner 144 B per pose
+    (three rows of the inverse 12x12 block of the pose's 4-row chunk, single precision; 72 B with the former 3x3 blocks)."""
     P, L = st["n_free_poses"], st["n_free_landmarks"]
     nnzb_pp = P + 2 * st["n_pairs_pp"]
     n_pl = st["n_pairs_pl"]
-    return 76 * nnzb_pp + 2 * 52 * n_pl + 56 * L + (312 + 288) * P
+    return 76 * nnzb_pp + 2 * 52 * n_pl + 56 * L + (312 + 144) * P
 
 
 def cpu_reference_run(workload, steps, warmup, quiet=False):

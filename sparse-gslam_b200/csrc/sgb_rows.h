@@ -466,7 +466,8 @@ SGB_HD bool setup_chunk(const DevGraph& g, int ch, double lambda) {
       for (int m = 0; m < N; ++m) {
         const int i = 3 * a + r;
         const double v = m >= i ? D[i * N + m] : D[m * N + i];  // the inverse is returned in the upper triangle
-        g.Cinv[(size_t)(r * N + m) * g.nP + p0 + a] = v;
+        const int idx = r * N + m;  // 36 entries per pose row = 9 float4, float4 q of pose lp at index q * nP + lp
+        g.Cinv[((size_t)(idx >> 2) * g.nP + p0 + a) * 4 + (idx & 3)] = (float)v;
       }
   return ok;
 }
@@ -828,11 +829,22 @@ SGB_HD double schur_phaseB_rows_u(const DevGraph& g, int lp0, int stride, double
 // beyond nP); returns r_i . z_i
 SGB_HD double precond_mul(const DevGraph& g, int lp, const double rr[3 * kChunk], double z[3]) {
   constexpr int N = 3 * kChunk;
-  const double* m = g.Cinv + lp;
-  const size_t s = (size_t)g.nP;
+  float ci[3 * N];  // nine 16-byte streaming loads, consecutive lanes = consecutive 16-byte words
+#pragma unroll
+  for (int q = 0; q < (3 * N) / 4; ++q) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(g.Cinv) + (size_t)q * g.nP + lp);
+    ci[4 * q] = v.x; ci[4 * q + 1] = v.y; ci[4 * q + 2] = v.z; ci[4 * q + 3] = v.w;
+#else
+    const float* v = g.Cinv + ((size_t)q * g.nP + lp) * 4;
+    ci[4 * q] = v[0]; ci[4 * q + 1] = v[1]; ci[4 * q + 2] = v[2]; ci[4 * q + 3] = v[3];
+#endif
+  }
+#pragma unroll
   for (int r = 0; r < 3; ++r) {
     double acc = 0.0;
-    for (int c = 0; c < N; ++c) acc += SGB_LDG(m + (size_t)(r * N + c) * s) * rr[c];
+#pragma unroll
+    for (int c = 0; c < N; ++c) acc += (double)ci[r * N + c] * rr[c];
     z[r] = acc;
   }
   const int a = lp & (kChunk - 1);

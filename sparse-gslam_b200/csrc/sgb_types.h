@@ -107,8 +107,11 @@ struct DevGraph {
   Mailbox* mbox[kMaxRanks];
   // ---- local only
   double* x_l;               // [2*nL] landmark step
-  double* Cinv;              // [36][nP] block-Jacobi preconditioner with blocks of kChunk = 4 consecutive pose rows: pose
-                             //          row lp holds its 3 rows (x 12 columns) of the inverse 12x12 Schur diagonal block
+  float* Cinv;               // [9][nP] float4: block-Jacobi preconditioner with blocks of kChunk = 4 consecutive pose rows: pose
+                             //          row lp holds its 3 rows (x 12 columns) of the inverse 12x12 Schur diagonal block.
+                             //          Stored in SINGLE precision (the products are formed in double): a preconditioner
+                             //          only has to be symmetric positive definite -- (i, j) and (j, i) are rounded from
+                             //          the same double -- and it does not enter the solution the PCG converges to
   double* bt;                // [3*nP] reduced right-hand side
   double* r;                 // residual
   double* d;                 // search direction

@@ -27,6 +27,7 @@ struct Rank {
   LocalPlan P;
   DevGraph G;
   std::vector<std::vector<double>> dbl;
+  std::vector<std::vector<float>> flt;
   std::vector<std::vector<int32_t>> ints;
   double* D(size_t n) { dbl.emplace_back(std::max<size_t>(n, 1), 0.0); return dbl.back().data(); }
   const int32_t* I(const std::vector<int32_t>& v) { ints.push_back(v); if (ints.back().empty()) ints.back().push_back(0); return ints.back().data(); }
@@ -108,7 +109,7 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
     mk_sell(r, &G.Hpp, P.Hpp, 9); mk_sell(r, &G.Hpl, P.Hpl, 6); mk_sell(r, &G.Hlp, P.Hlp, 6);
     size_t n3 = 3 * (size_t)P.nP, n2 = 2 * (size_t)P.nL;
     G.Hll = r->D(3 * (size_t)P.nL); G.b_p = r->D(n3); G.x_l = r->D(n2);
-    G.Cinv = r->D(3 * 3 * kChunk * (size_t)P.nP); G.bt = r->D(n3); G.r = r->D(n3); G.d = r->D(n3); G.s = r->D(n3);
+    r->flt.emplace_back(3 * 3 * kChunk * (size_t)std::max(P.nP, 1), 0.0f); G.Cinv = r->flt.back().data(); G.bt = r->D(n3); G.r = r->D(n3); G.d = r->D(n3); G.s = r->D(n3);
     // the "arena": arrays other ranks reach into
     for (int b = 0; b < 2; ++b) {
       G.pose_buf[b][rk] = r->D(np); G.lm_buf[b][rk] = r->D(nl);
