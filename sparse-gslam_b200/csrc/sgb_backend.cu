@@ -649,7 +649,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   if (st != SGB_OK) return st;
   lap("build_structure");
   if (dv && dv->has_robust) h->S.has_robust = true;
-  st = partition(h->S, world, rank, h->LP, h->err);
+  st = partition_consume(h->S, world, rank, h->LP, h->err);
   if (st != SGB_OK) return st;
   lap("partition");
   const Structure& S = h->S;

@@ -109,14 +109,18 @@ int lm_target_steps(size_t blocks) {
 // world == 1: the local plan IS the global structure -- same rows, same edge order, same pose-major SELL layout;
 // only the landmark numbering (row order of the landmark-major matrix) differs from the Hessian order. Plain copies
 // on four host threads instead of the general owner/halo classification.
-sgb_status partition_single(const Structure& S, LocalPlan& P) {
+// `consume` (the product path: the Structure belongs to the handle and nobody reads these arrays again): the per-edge
+// arrays and the incidence lists are MOVED into the plan instead of copied (~250 MB on the 1M-pose graph).
+sgb_status partition_single(const Structure& S, LocalPlan& P, Structure* consume) {
   P.n_pp = P.n_pp_owned = S.n_pp;
   P.n_pl = P.n_pl_owned = S.n_pl;
   auto pose_side = [&]() {
     P.pp_g.resize(S.n_pp);
     std::iota(P.pp_g.begin(), P.pp_g.end(), 0);
-    P.pp_i = S.pp_i; P.pp_j = S.pp_j; P.pp_hi = S.pp_hi; P.pp_hj = S.pp_hj;
-    P.pp_e_ij = S.pp_e_ij; P.pp_e_ji = S.pp_e_ji; P.pp_dup = S.pp_dup;
+    if (!consume) {
+      P.pp_i = S.pp_i; P.pp_j = S.pp_j; P.pp_hi = S.pp_hi; P.pp_hj = S.pp_hj;
+      P.pp_e_ij = S.pp_e_ij; P.pp_e_ji = S.pp_e_ji; P.pp_dup = S.pp_dup;
+    }
     P.Hpp = S.Hpp;  // enc_pose(c) == c for a single owner
     P.hpp_diag = S.hpp_diag;
   };
@@ -124,8 +128,10 @@ sgb_status partition_single(const Structure& S, LocalPlan& P) {
     P.Hpl = S.Hpl;
     for (auto& c : P.Hpl.col)
       if (c >= 0) c = P.enc_lm[c];
-    P.pinc_ptr = S.pinc_ptr;
-    P.pinc = S.pinc;
+    if (!consume) {
+      P.pinc_ptr = S.pinc_ptr;
+      P.pinc = S.pinc;
+    }
   };
   auto lm_side = [&]() {
     FlatRows obs(P.nL);
@@ -151,8 +157,10 @@ sgb_status partition_single(const Structure& S, LocalPlan& P) {
   auto pl_side = [&]() {
     P.pl_g.resize(S.n_pl);
     std::iota(P.pl_g.begin(), P.pl_g.end(), 0);
-    P.pl_p = S.pl_p; P.pl_l = S.pl_l; P.pl_hp = S.pl_hp; P.pl_hl = S.pl_hl;
-    P.pl_e_pl = S.pl_e_pl; P.pl_dup = S.pl_dup;
+    if (!consume) {
+      P.pl_p = S.pl_p; P.pl_l = S.pl_l; P.pl_hp = S.pl_hp; P.pl_hl = S.pl_hl;
+      P.pl_e_pl = S.pl_e_pl; P.pl_dup = S.pl_dup;
+    }
   };
   if ((size_t)S.n_pp + S.n_pl > 200000) {
     std::thread t1(pose_side), t2(hpl_side), t3(pl_side);
@@ -166,12 +174,27 @@ sgb_status partition_single(const Structure& S, LocalPlan& P) {
     pl_side();
     lm_side();
   }
+  if (consume) {  // after the threads: lm_side reads S.pl_e_pl / S.pl_hl
+    Structure& M = *consume;
+    P.pp_i.swap(M.pp_i); P.pp_j.swap(M.pp_j); P.pp_hi.swap(M.pp_hi); P.pp_hj.swap(M.pp_hj);
+    P.pp_e_ij.swap(M.pp_e_ij); P.pp_e_ji.swap(M.pp_e_ji); P.pp_dup.swap(M.pp_dup);
+    P.pinc_ptr.swap(M.pinc_ptr); P.pinc.swap(M.pinc);
+    P.pl_p.swap(M.pl_p); P.pl_l.swap(M.pl_l); P.pl_hp.swap(M.pl_hp); P.pl_hl.swap(M.pl_hl);
+    P.pl_e_pl.swap(M.pl_e_pl); P.pl_dup.swap(M.pl_dup);
+  }
   return SGB_OK;
 }
 
 }  // namespace
 
+static sgb_status partition_impl(const Structure& S, int world, int rank, LocalPlan& P, std::string& err, Structure* consume);
 sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std::string& err) {
+  return partition_impl(S, world, rank, P, err, nullptr);
+}
+sgb_status partition_consume(Structure& S, int world, int rank, LocalPlan& P, std::string& err) {
+  return partition_impl(S, world, rank, P, err, world == 1 ? &S : nullptr);
+}
+static sgb_status partition_impl(const Structure& S, int world, int rank, LocalPlan& P, std::string& err, Structure* consume) {
   P = LocalPlan();
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) { err = "bad world/rank"; return SGB_ERR_INVALID; }
   P.world = world;
@@ -224,7 +247,7 @@ sgb_status partition(const Structure& S, int world, int rank, LocalPlan& P, std:
   P.lm_of_l.resize(P.nL);
   for (int l = 0; l < P.nL; ++l) P.lm_of_l[l] = S.lm_of_h[P.lm_global[l]];
 
-  if (world == 1) return partition_single(S, P);
+  if (world == 1) return partition_single(S, P, consume);
 
   auto pose_local = [&](int hp) { return hp >= 0 && owner_p(hp) == rank; };
   auto lm_local = [&](int hl) { return hl >= 0 && lm_owner[hl] == rank; };

@@ -36,6 +36,9 @@ struct LocalPlan {
 inline int enc_pose(int hp, int chunkP) { return ((hp / chunkP) << 26) | (hp % chunkP); }
 
 sgb_status partition(const Structure& S, int world, int rank, LocalPlan& out, std::string& err);
+// the same for a Structure nobody else reads afterwards: with world == 1 its per-edge arrays (pp_*, pl_*, pinc*) are
+// moved into the plan and left empty in S (pp_src / pl_src, the SELL patterns and the index maps stay)
+sgb_status partition_consume(Structure& S, int world, int rank, LocalPlan& out, std::string& err);
 // fills Structure::blk_* and LocalPlan::blk_owner / blk_entry (idempotent); only the parity hooks need it
 void build_export(Structure& S, LocalPlan& P);
 

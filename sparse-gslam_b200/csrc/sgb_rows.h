@@ -369,13 +369,14 @@ SGB_HD bool setup_pose_row(const DevGraph& g, int lp, double lambda) {
 template <int N>
 SGB_HD bool inv_spd_inplace(double* A) {
   bool ok = true;
+  double rinv[N];  // 1 / L[j][j]: one division per pivot, none in the inner loops
   for (int j = 0; j < N; ++j) {  // A = L L^T, L stored in the lower triangle
     double dj = A[j * N + j];
     for (int k = 0; k < j; ++k) dj -= A[j * N + k] * A[j * N + k];
     ok = ok && (dj > 0.0) && (dj < 1e300);
-    double lj = sqrt(dj);
-    A[j * N + j] = lj;
-    double inv = 1.0 / lj;
+    const double lj = sqrt(dj);
+    const double inv = 1.0 / lj;
+    rinv[j] = inv;
     for (int i = j + 1; i < N; ++i) {
       double v = A[i * N + j];
       for (int k = 0; k < j; ++k) v -= A[i * N + k] * A[j * N + k];
@@ -383,18 +384,18 @@ SGB_HD bool inv_spd_inplace(double* A) {
     }
   }
   for (int j = 0; j < N; ++j) {  // L <- L^-1 (lower triangular), column by column
-    A[j * N + j] = 1.0 / A[j * N + j];
+    A[j * N + j] = rinv[j];
     for (int i = j + 1; i < N; ++i) {
       double v = 0.0;
       for (int k = j; k < i; ++k) v -= A[i * N + k] * A[k * N + j];
-      A[i * N + j] = v / A[i * N + i];
+      A[i * N + j] = v * rinv[i];
     }
   }
-  for (int i = 0; i < N; ++i)  // A^-1 = L^-T L^-1: entry (i, j), j >= i, = sum_{k >= j} Linv[k][i] Linv[k][j]; upper triangle
-    for (int j = i; j < N; ++j) {
+  for (int i = 0; i < N; ++i)  // A^-1 = L^-T L^-1 into the UPPER triangle: (i, j), j >= i, = sum_{k >= j} Linv[k][i] Linv[k][j];
+    for (int j = i; j < N; ++j) {  // only lower-triangle entries of rows >= j are read, none of them written before
       double v = 0.0;
       for (int k = j; k < N; ++k) v += A[k * N + i] * A[k * N + j];
-      A[i * N + j] = v;  // rows < k of column i / j are not read again for (i', j') >= (i, j) in this order? see below
+      A[i * N + j] = v;
     }
   return ok;
 }

@@ -187,20 +187,34 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   for (int h = 0; h < S.Lf; ++h) { S.ord_kind[S.Pf + h] = 1; S.ord_index[S.Pf + h] = lorder[h]; S.ord_offset[S.Pf + h] = 3 * S.Pf + 2 * h; }
 
   lap("index mapping");
-  // ---- per-type active edge arrays (insertion order)
+  // ---- per-type active edge arrays (insertion order); independent per edge: split over host threads when large
   S.pp_i.resize(S.n_pp); S.pp_j.resize(S.n_pp); S.pp_hi.resize(S.n_pp); S.pp_hj.resize(S.n_pp);
-  S.pp_e_ij.assign(S.n_pp, -1); S.pp_e_ji.assign(S.n_pp, -1); S.pp_dup.assign(S.n_pp, -1);
-  for (int k = 0; k < S.n_pp; ++k) {
-    int s = S.pp_src[k];
-    S.pp_i[k] = g.pp_i[s]; S.pp_j[k] = g.pp_j[s];
-    S.pp_hi[k] = S.pose_h[g.pp_i[s]]; S.pp_hj[k] = S.pose_h[g.pp_j[s]];
-  }
   S.pl_p.resize(S.n_pl); S.pl_l.resize(S.n_pl); S.pl_hp.resize(S.n_pl); S.pl_hl.resize(S.n_pl);
-  S.pl_e_pl.assign(S.n_pl, -1); S.pl_k_lp.assign(S.n_pl, -1); S.pl_dup.assign(S.n_pl, -1);
-  for (int k = 0; k < S.n_pl; ++k) {
-    int s = S.pl_src[k];
-    S.pl_p[k] = g.pl_pose[s]; S.pl_l[k] = g.pl_lm[s];
-    S.pl_hp[k] = S.pose_h[g.pl_pose[s]]; S.pl_hl[k] = S.lm_h[g.pl_lm[s]];
+  auto fill_edges = [&](int a0, int a1, int b0, int b1) {
+    for (int k = a0; k < a1; ++k) {
+      int s = S.pp_src[k];
+      S.pp_i[k] = g.pp_i[s]; S.pp_j[k] = g.pp_j[s];
+      S.pp_hi[k] = S.pose_h[g.pp_i[s]]; S.pp_hj[k] = S.pose_h[g.pp_j[s]];
+    }
+    for (int k = b0; k < b1; ++k) {
+      int s = S.pl_src[k];
+      S.pl_p[k] = g.pl_pose[s]; S.pl_l[k] = g.pl_lm[s];
+      S.pl_hp[k] = S.pose_h[g.pl_pose[s]]; S.pl_hl[k] = S.lm_h[g.pl_lm[s]];
+    }
+  };
+  if ((size_t)S.n_pp + S.n_pl > 200000) {
+    const int nth = 4;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nth; ++t)
+      th.emplace_back(fill_edges, (int)((int64_t)S.n_pp * t / nth), (int)((int64_t)S.n_pp * (t + 1) / nth),
+                      (int)((int64_t)S.n_pl * t / nth), (int)((int64_t)S.n_pl * (t + 1) / nth));
+    S.pp_e_ij.assign(S.n_pp, -1); S.pp_e_ji.assign(S.n_pp, -1); S.pp_dup.assign(S.n_pp, -1);
+    S.pl_e_pl.assign(S.n_pl, -1); S.pl_k_lp.assign(S.n_pl, -1); S.pl_dup.assign(S.n_pl, -1);
+    for (auto& t : th) t.join();
+  } else {
+    fill_edges(0, S.n_pp, 0, S.n_pl);
+    S.pp_e_ij.assign(S.n_pp, -1); S.pp_e_ji.assign(S.n_pp, -1); S.pp_dup.assign(S.n_pp, -1);
+    S.pl_e_pl.assign(S.n_pl, -1); S.pl_k_lp.assign(S.n_pl, -1); S.pl_dup.assign(S.n_pl, -1);
   }
 
   lap("edge arrays");
@@ -330,8 +344,13 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   };
 
   if ((size_t)S.n_pp + S.n_pl > 200000) {
-    std::thread t1(build_incidence), t2(build_pp);
-    build_pl();
+    auto timed = [&](const char* what, auto&& f) {
+      auto t0 = std::chrono::steady_clock::now();
+      f();
+      if (prof) std::fprintf(stderr, "[build_structure]   %-12s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
+    std::thread t1([&] { timed("incidence", build_incidence); }), t2([&] { timed("pose-pose", build_pp); });
+    timed("pose-line", build_pl);
     t1.join();
     t2.join();
   } else {
