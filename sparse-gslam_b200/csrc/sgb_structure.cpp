@@ -72,20 +72,31 @@ void group_pairs(int n, int nbuckets, KeyA key_a, KeyB key_b, Grouped& G) {
     int a = key_a(k), b = key_b(k);
     if (a >= 0 && b >= 0) G.items[(size_t)pos[a]++] = {b, k};
   }
-  for (int a = 0; a < nbuckets; ++a) {
-    PairItem* lo = G.items.data() + G.start[a];
-    int m = G.start[a + 1] - G.start[a];
-    if (m <= 1) continue;
-    if (m <= 24) {  // stable insertion sort by b (k is already ascending inside a bucket)
-      for (int i = 1; i < m; ++i) {
-        PairItem v = lo[i];
-        int j = i - 1;
-        while (j >= 0 && lo[j].b > v.b) { lo[j + 1] = lo[j]; --j; }
-        lo[j + 1] = v;
+  auto sort_buckets = [&](int a0, int a1) {
+    for (int a = a0; a < a1; ++a) {
+      PairItem* lo = G.items.data() + G.start[a];
+      int m = G.start[a + 1] - G.start[a];
+      if (m <= 1) continue;
+      if (m <= 24) {  // stable insertion sort by b (k is already ascending inside a bucket)
+        for (int i = 1; i < m; ++i) {
+          PairItem v = lo[i];
+          int j = i - 1;
+          while (j >= 0 && lo[j].b > v.b) { lo[j + 1] = lo[j]; --j; }
+          lo[j + 1] = v;
+        }
+      } else {
+        std::stable_sort(lo, lo + m, [](const PairItem& x, const PairItem& y) { return x.b < y.b; });
       }
-    } else {
-      std::stable_sort(lo, lo + m, [](const PairItem& x, const PairItem& y) { return x.b < y.b; });
     }
+  };
+  if (n > 1000000) {  // buckets are independent: two more host threads on the big graphs
+    const int c1 = nbuckets / 3, c2 = 2 * (nbuckets / 3);
+    std::thread t1(sort_buckets, 0, c1), t2(sort_buckets, c1, c2);
+    sort_buckets(c2, nbuckets);
+    t1.join();
+    t2.join();
+  } else {
+    sort_buckets(0, nbuckets);
   }
 }
 
@@ -324,20 +335,33 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     for (int r = 0; r < S.Lf; ++r) rows_lp.ptr[r + 1] += rows_lp.ptr[r];
     rows_pl.col.resize(np);
     rows_lp.col.resize(np);
-    std::vector<int32_t> idx_pl(np), idx_lp(np), lp_pair(np), pos_pl(S.Pf, 0), pos_lp(S.Lf, 0);
-    for (int t = 0; t < np; ++t) {  // pairs ascend by (pose, landmark): both row lists come out sorted
-      int a = pa[t], b = pb[t];
-      idx_pl[t] = pos_pl[a];
-      rows_pl.col[rows_pl.ptr[a] + pos_pl[a]++] = b;
-      idx_lp[t] = pos_lp[b];
-      lp_pair[rows_lp.ptr[b] + pos_lp[b]] = t;
-      rows_lp.col[rows_lp.ptr[b] + pos_lp[b]++] = a;
-    }
-    make_sell(rows_pl, S.Pf, nullptr, S.Hpl);
-    for (int t = 0; t < np; ++t) {
-      int k = pk[t];
-      S.pl_e_pl[k] = sell_entry(S.Hpl, pa[t], idx_pl[t]);
-      S.pl_k_lp[k] = idx_lp[t];
+    std::vector<int32_t> idx_pl(np), pos_pl(S.Pf, 0);
+    // pairs ascend by (pose, landmark): both row lists come out sorted. The landmark-major lists (scattered writes)
+    // are filled on a second thread while this one builds the pose-major SELL.
+    auto lm_major = [&]() {
+      std::vector<int32_t> pos_lp(S.Lf, 0);
+      for (int t = 0; t < np; ++t) {
+        int a = pa[t], b = pb[t];
+        S.pl_k_lp[pk[t]] = pos_lp[b];
+        rows_lp.col[rows_lp.ptr[b] + pos_lp[b]++] = a;
+      }
+    };
+    auto pose_major = [&]() {
+      for (int t = 0; t < np; ++t) {
+        int a = pa[t];
+        idx_pl[t] = pos_pl[a];
+        rows_pl.col[rows_pl.ptr[a] + pos_pl[a]++] = pb[t];
+      }
+      make_sell(rows_pl, S.Pf, nullptr, S.Hpl);
+      for (int t = 0; t < np; ++t) S.pl_e_pl[pk[t]] = sell_entry(S.Hpl, pa[t], idx_pl[t]);
+    };
+    if (np > 1000000) {
+      std::thread t(lm_major);
+      pose_major();
+      t.join();
+    } else {
+      lm_major();
+      pose_major();
     }
     S.lp_ptr.swap(rows_lp.ptr);
     S.lp_col.swap(rows_lp.col);
