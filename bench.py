@@ -660,15 +660,18 @@ def main():
     pcg_bytes = b_iter * agg["pcg_iters"]
     pcg_s = agg["pcg_ms"] * 1e-3
     achieved = pcg_bytes / pcg_s / 1e9 if pcg_s > 0 else 0.0
-    traffic = None
+    # DRAM bytes (read + write) of ONE ncu-captured k_pcg launch of this workload (profiles/pcg_traffic.json, with the
+    # PCG iterations of that launch, so that it can be set against that launch's algorithmic bytes); null if no capture
+    traffic, traffic_detail = None, None
     tp = os.path.join(ROOT, "profiles", "pcg_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and world == 1:
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            traffic_detail = json.load(open(tp)).get(args.workload)
+            traffic = traffic_detail["dram_bytes_per_launch"] if traffic_detail else None
         except Exception:
-            traffic = None
+            traffic, traffic_detail = None, None
     roofline = {"bound": "hbm", "kernel": "k_pcg", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "traffic_detail": traffic_detail, "peak_source": peak_src,
                 "algorithmic_bytes_per_pcg_iteration": b_iter, "pcg_iterations": agg["pcg_iters"],
                 "pcg_launches": agg["trials"], "share_of_step": agg["pcg_ms"] / dev_ms if dev_ms > 0 else None,
                 "pcg_phase_us_per_iteration": [1e3 * v / max(1, agg["pcg_iters"]) for v in pcg_phase],
