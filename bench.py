@@ -108,13 +108,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "window": window}
 
 
+C5_DESC = "C5 synthetic 1M-pose grid world (P=1e6, L=2e5, E_o~1.5e6, E_l=4e6), LM-15"
+
+
 def make_workload(name, rank=0, world=1):
     from sparse_gslam_b200 import capi
     from sparse_gslam_b200 import graphgen as gg
     name = name.lower()
     if name == "c5":
         g = gg.make_c5()
-        return g, capi.ALGO_LM, LM_ITERS, "C5 synthetic 1M-pose grid world (P=1e6, L=2e5, E_o~1.5e6, E_l=4e6), LM-15"
+        return g, capi.ALGO_LM, LM_ITERS, C5_DESC
     if name == "c5s":  # small C5 used by CI-style quick runs
         g = gg.make_c5(rows=200, cols=200)
         return g, capi.ALGO_LM, LM_ITERS, "C5-shaped 200x200 grid world (P=4e4), LM-15"
@@ -529,10 +532,26 @@ def main():
         if rank != 0:
             return
         r = cpu_reference_run(args.workload, max(1, args.steps), 1)
+        # the same config as the GPU arm's line (the workload description, algorithm and iteration count)
+        wl = args.workload.lower()
+        if wl == "c5":
+            desc, algo_name, iters = C5_DESC, "LM", LM_ITERS
+        elif wl == "c4":
+            desc = (f"C4 batched aces-shaped windows: {C4_GRAPHS_PER_GPU} independent graphs per GPU x {args.gpus} GPU(s) "
+                    "(P=128, L=64, E_l=400 each), LM-15")
+            algo_name, iters = "LM", LM_ITERS
+        elif wl in ("stream", "edits"):
+            desc, algo_name, iters = wl, "LM", LM_ITERS
+        else:
+            from sparse_gslam_b200 import capi as _capi
+            _, a, iters, desc = make_workload(wl)
+            algo_name = "LM" if a == _capi.ALGO_LM else "GN+DCS"
         line = {"impl": "reference", "metric": "LM iterations/s", "value": r["value"], "unit": "LM iterations/s",
                 "n_gpus": args.gpus, "steps": r["sample_steps"], "warmup": 1, "ms_per_step": r["sample_ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": args.workload}, "cpu_baseline": r,
+                "config": {"workload": desc, "algorithm": algo_name, "iterations_per_step": iters,
+                           "jacobian": "g2o-numeric (the reference's default)", "parallelism": "host CPU, 1 thread (g2o + Eigen Simplicial are serial)"},
+                "cpu_baseline": r,
                 "e2e": {"value": r["value"], "unit": "LM iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
