@@ -266,7 +266,13 @@ sgb_status sgb_pg_create(int32_t device, sgb_pose_graph** out) {
   *out = nullptr;
   if (sgb_device_count() <= 0) return SGB_ERR_NO_DEVICE;  // no CPU path
   sgb_pose_graph* pg = new sgb_pose_graph();
-  auto fail = [&](cudaError_t) { delete pg; return SGB_ERR_CUDA; };
+  auto fail = [&](cudaError_t) {
+    if (pg->ev0) cudaEventDestroy(pg->ev0);
+    if (pg->ev1) cudaEventDestroy(pg->ev1);
+    if (pg->stream) cudaStreamDestroy(pg->stream);
+    delete pg;
+    return SGB_ERR_CUDA;
+  };
   cudaError_t e;
   if (device >= 0 && (e = cudaSetDevice(device)) != cudaSuccess) return fail(e);
   if ((e = cudaGetDevice(&pg->device)) != cudaSuccess) return fail(e);
