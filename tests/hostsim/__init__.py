@@ -56,6 +56,7 @@ def lib():
         L.hs_check_hlp.argtypes = [vp]
         L.hs_check_hlp.restype = C.c_double
         L.hs_chi2.argtypes = [vp, vp]
+        L.hs_preconditioner.argtypes = [vp, C.c_double, vp]
         L.hs_pg_append.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.hs_closure_chi2.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
         L.hs_odom_information.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_double, vp, vp, vp]
@@ -127,6 +128,12 @@ class HostSim:
         self.L.hs_partition_stats(self.h, _p(o))
         keys = ("nP", "nL", "n_pp", "n_pl", "n_pp_owned", "n_pl_owned", "halo_p", "halo_t")
         return [dict(zip(keys, map(int, row))) for row in o]
+
+    def preconditioner(self, lam, n_free_poses):
+        """Rows of the inverse 12x12 Schur diagonal blocks as the kernels store them: [nP, 3, 12] float32 (rank 0)."""
+        out = np.zeros((n_free_poses, 3, 12), np.float32)
+        rc = self.L.hs_preconditioner(self.h, float(lam), _p(out))
+        return rc == 0, out
 
     def check_hlp(self):
         return float(self.L.hs_check_hlp(self.h))

@@ -416,6 +416,19 @@ void hs_get_estimates(hs_handle* h, int rank, double* pose, double* lm) {
 }
 void hs_chi2(hs_handle* h, double* chi2) { chi2_edges(h, h->cur, chi2); }
 
+// block-Jacobi preconditioner of rank 0 after a set-up at `lambda` (linearises first): out [nP][3][12], row-major
+int hs_preconditioner(hs_handle* h, double lambda, float* out) {
+  double chi[3];
+  linearize(h, chi);
+  bool ok = true;
+  for (auto& r : h->R) for (int ll = 0; ll < r->G.nL; ++ll) ok &= setup_lm_row(r->G, ll, lambda);
+  const DevGraph& G = h->R[0]->G;
+  for (int ch = 0; ch < (G.nP + kChunk - 1) / kChunk; ++ch) ok &= setup_chunk(G, ch, lambda);
+  for (int lp = 0; lp < G.nP; ++lp)
+    for (int idx = 0; idx < 9 * kChunk; ++idx) out[(size_t)lp * 9 * kChunk + idx] = G.Cinv[((size_t)(idx >> 2) * G.nP + lp) * 4 + (idx & 3)];
+  return ok ? 0 : 1;
+}
+
 }  // extern "C"
 
 // timing of the host symbolic phase alone (seconds): out[0] = build_structure, out[1] = partition(world, rank 0)

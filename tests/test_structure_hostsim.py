@@ -235,3 +235,31 @@ def test_more_ranks_than_rows():
     many.optimize(3, capi.ALGO_LM)
     one.optimize(3, capi.ALGO_LM)
     np.testing.assert_allclose(many.estimates(3)[0], one.estimates()[0], atol=1e-12)
+
+
+@pytest.mark.parametrize("lam", [1e-3, 10.0])
+def test_preconditioner_blocks_are_the_inverse_schur_diagonal_blocks(lam):
+    """setup_chunk against numpy: S = Hpp + lam I - Hpl (Hll + lam I)^-1 Hpl^T from the oracle's dense Hessian, cut into
+    4-pose (12x12) diagonal blocks, inverted; the kernels store the rows in single precision."""
+    from oracle.cpu_oracle import JAC_ANALYTIC, Oracle
+    g = gg.make_small(seed=5, P=63, L=12, E_l=170, n_closures=6)  # 62 free poses: the last chunk is partial
+    o = Oracle(g)
+    assert o.initialize_optimization()
+    st = o.structure()
+    lin = o.linearize(JAC_ANALYTIC)
+    H = o.dense_hessian(lin, st)
+    nP = int((st["kind"] == 0).sum())
+    n3 = 3 * nP
+    Hd = H + lam * np.eye(H.shape[0])
+    S = Hd[:n3, :n3] - Hd[:n3, n3:] @ np.linalg.inv(Hd[n3:, n3:]) @ Hd[n3:, :n3]
+    hs = hostsim.HostSim(g, jac_numeric=False)
+    ok, C = hs.preconditioner(lam, nP)
+    assert ok and nP % 4 != 0
+    for c0 in range(0, nP, 4):
+        c1 = min(nP, c0 + 4)
+        Dinv = np.linalg.inv(S[3 * c0:3 * c1, 3 * c0:3 * c1])
+        for p in range(c0, c1):
+            got = C[p].astype(np.float64)[:, :3 * (c1 - c0)]
+            ref = Dinv[3 * (p - c0):3 * (p - c0) + 3, :]
+            assert np.abs(got - ref).max() <= 2e-6 * np.abs(Dinv).max(), (c0, p)
+            assert np.all(C[p][:, 3 * (c1 - c0):] == 0)  # no coupling to the poses missing from a partial chunk
