@@ -1325,7 +1325,8 @@ static sgb_status optimize_batch_impl(sgb_handle* const* hs, int32_t n, int32_t 
   cudaError_t e = cudaMemcpyAsync(d_items, items.data(), sizeof(BatchItem) * (size_t)n, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaEventRecord(t0, s);
   if (e == cudaSuccess) {
-    k_lm_block<<<n, kThreads, 0, s>>>(d_items, prm, d_res);
+    if (n <= h->sm_count) k_lm_block<8><<<n, kThreads, 0, s>>>(d_items, prm, d_res);
+    else k_lm_block<2><<<n, kThreads, 0, s>>>(d_items, prm, d_res);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaEventRecord(t1, s);

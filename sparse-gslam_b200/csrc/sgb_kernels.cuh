@@ -742,6 +742,9 @@ struct BatchResult {
   double chi2, lambda, rho, chi2_before, pcg_rel;
 };
 
+// U = blocks in flight per thread in the pose-major pass: 8 when the batch has at most one graph per SM (registers are
+// free, the latency chain of a row is what counts), 2 otherwise (more resident CTAs per SM)
+template <int U>
 __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, BatchParams prm, BatchResult* results) {
   __shared__ DevGraph g;
   __shared__ DevScalars sc;
@@ -801,7 +804,7 @@ __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, B
       __syncthreads();
       if (!ok) atomicAnd(&s_ok, 0);
       PcgOut po;
-      pcg_solve(g, tid, nth, 1u, nullptr, nullptr, seq, pcg, lambda, sm, &s_last, ph_ns, &t_ph, po);
+      pcg_solve<U>(g, tid, nth, 1u, nullptr, nullptr, seq, pcg, lambda, sm, &s_last, ph_ns, &t_ph, po);
       pcg_total += po.iters;
       pcg_all += po.iters;
       // ---- back-substitution, update into the trial (LM) or current (GN) estimates, computeScale
