@@ -1,11 +1,11 @@
 """Host experiment behind the choice of the block-Jacobi block size: PCG iterations on the Schur
 complement of the oracle's Hessian for preconditioner blocks of 1..32 consecutive poses. Test infrastructure (uses the oracle)."""
-import sys, time; sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests')
+import sys, time; import os; ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, scipy.sparse as sp, scipy.sparse.linalg as spl
 from oracle.cpu_oracle import Oracle, JAC_ANALYTIC
 from sparse_gslam_b200 import graphgen as gg
 import importlib.util
-spec=importlib.util.spec_from_file_location("tgp","/root/repo/tests/test_gpu_parity.py"); m=importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+spec=importlib.util.spec_from_file_location("tgp",os.path.join(ROOT, 'tests', 'test_gpu_parity.py')); m=importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
 
 def schur(H, b, nP3, lam):
     n=H.shape[0]
