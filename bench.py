@@ -315,10 +315,36 @@ def cpu_reference_c4(steps, warmup, sample=16):
             total += dt
             its += k
             n += 1
+    # the fair multi-core companion of the batched GPU number -- one graph per host thread on all cores
+    # (the oracle is handle-based C++ behind ctypes, which releases the GIL)
+    from concurrent.futures import ThreadPoolExecutor
+    cores = os.cpu_count() or 1
+    many = [gg.make_c4_window(seed=1000 + i) for i in range(max(sample, 4 * cores))]
+
+    oracles = [Oracle(g) for g in many]  # built outside the timed region: packing the graph is Python (holds the GIL)
+    for o in oracles:
+        o.initialize_optimization()
+
+    def one(o):
+        o.set_estimates(o.g.pose_est, o.g.lm_est)
+        m, _ = o.optimize(LM_ITERS, ALGO_LM, JAC_G2O_NUMERIC)
+        return max(m, 0)
+
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        list(ex.map(one, oracles))  # warm-up
+        its_all, dt_all = 0, 0.0
+        for _ in range(3):  # best of three: the host threads of a shared box are not always spread over the cores
+            t0 = time.perf_counter()
+            k = sum(ex.map(one, oracles))
+            dt = time.perf_counter() - t0
+            if dt_all == 0.0 or k / dt > its_all / dt_all:
+                its_all, dt_all = k, dt
     return dict(value=its / total if total > 0 else 0.0, unit="LM iterations/s", cores=1, kind="port",
                 sample=f"{sample} of the C4 windows (seeds 1000..), optimize(15) each, g2o-numeric Jacobians + exact sparse "
                        "LDLt, sequential on one core; iterations/s is per core and independent of the batch size",
-                sample_ms_per_step=1e3 * total / max(1, n), sample_steps=n, host_cores=os.cpu_count())
+                sample_ms_per_step=1e3 * total / max(1, n), sample_steps=n, host_cores=os.cpu_count(),
+                all_cores=dict(value=its_all / dt_all if dt_all > 0 else 0.0, unit="LM iterations/s", cores=cores,
+                               sample=f"{len(many)} windows, one graph per host thread on {cores} threads"))
 
 
 class _OracleBackend:
