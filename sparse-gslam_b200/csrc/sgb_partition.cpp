@@ -133,6 +133,15 @@ sgb_status partition_single(const Structure& S, LocalPlan& P, Structure* consume
       P.pinc = S.pinc;
     }
   };
+  auto linc_side = [&]() {  // incidence lists of the landmarks in the plan's row order (independent of the SELL build)
+    P.linc_ptr.assign(P.nL + 1, 0);
+    P.linc.reserve(S.linc.size());
+    for (int l = 0; l < P.nL; ++l) {
+      int hl = P.lm_global[l];
+      P.linc.insert(P.linc.end(), S.linc.begin() + S.linc_ptr[hl], S.linc.begin() + S.linc_ptr[hl + 1]);
+      P.linc_ptr[l + 1] = (int)P.linc.size();
+    }
+  };
   auto lm_side = [&]() {
     FlatRows obs(P.nL);
     obs.col.reserve(S.lp_col.size());
@@ -142,17 +151,19 @@ sgb_status partition_single(const Structure& S, LocalPlan& P, Structure* consume
       obs.close_row();
     }
     build_grouped_sell(obs, lm_target_steps(obs.col.size()), P.Hlp);
-    P.linc_ptr.assign(P.nL + 1, 0);
-    P.linc.reserve(S.linc.size());
-    for (int l = 0; l < P.nL; ++l) {
-      int hl = P.lm_global[l];
-      P.linc.insert(P.linc.end(), S.linc.begin() + S.linc_ptr[hl], S.linc.begin() + S.linc_ptr[hl + 1]);
-      P.linc_ptr[l + 1] = (int)P.linc.size();
-    }
-    // needs Hlp: the landmark-major entry of every leading pose-line edge
+    // needs Hlp: the landmark-major entry of every leading pose-line edge (independent per edge: two threads when large)
     P.pl_e_lp.assign(S.n_pl, -1);
-    for (int k = 0; k < S.n_pl; ++k)
-      if (S.pl_e_pl[k] >= 0) P.pl_e_lp[k] = P.Hlp.entry(P.enc_lm[S.pl_hl[k]] & kLocalMask, S.pl_k_lp[k]);
+    auto entries = [&](int k0, int k1) {
+      for (int k = k0; k < k1; ++k)
+        if (S.pl_e_pl[k] >= 0) P.pl_e_lp[k] = P.Hlp.entry(P.enc_lm[S.pl_hl[k]] & kLocalMask, S.pl_k_lp[k]);
+    };
+    if (S.n_pl > 1000000) {
+      std::thread t(entries, 0, S.n_pl / 2);
+      entries(S.n_pl / 2, S.n_pl);
+      t.join();
+    } else {
+      entries(0, S.n_pl);
+    }
   };
   auto pl_side = [&]() {
     P.pl_g.resize(S.n_pl);
@@ -163,15 +174,17 @@ sgb_status partition_single(const Structure& S, LocalPlan& P, Structure* consume
     }
   };
   if ((size_t)S.n_pp + S.n_pl > 200000) {
-    std::thread t1(pose_side), t2(hpl_side), t3(pl_side);
+    std::thread t1(pose_side), t2(hpl_side), t3(pl_side), t4(linc_side);
     lm_side();
     t1.join();
     t2.join();
     t3.join();
+    t4.join();
   } else {
     pose_side();
     hpl_side();
     pl_side();
+    linc_side();
     lm_side();
   }
   if (consume) {  // after the threads: lm_side reads S.pl_e_pl / S.pl_hl

@@ -37,13 +37,26 @@ void make_sell(const RowLists& L, int rows, const std::vector<int32_t>* row_of_s
     }
     S.sbase[s + 1] = S.sbase[s] + w * 32;
   }
-  S.col.assign((size_t)S.sbase[S.nslices], -1);
-  for (int r = 0; r < rows; ++r) {
-    int lr = row_of_sell ? (*row_of_sell)[r] : r;
-    int s = r >> 5, lane = r & 31;
-    int32_t* dst = S.col.data() + (size_t)S.sbase[s] + lane;
-    const int32_t* src = L.col.data() + L.ptr[lr];
-    for (int k = 0, n = L.ptr[lr + 1] - L.ptr[lr]; k < n; ++k) dst[(size_t)k * 32] = src[k];
+  S.col.resize((size_t)S.sbase[S.nslices]);
+  // slices are disjoint ranges of S.col: padding fill and column scatter on two host threads for the big matrices
+  auto fill = [&](int s0, int s1) {
+    std::fill(S.col.begin() + S.sbase[s0], S.col.begin() + S.sbase[s1], -1);
+    const int r1 = std::min(rows, s1 * 32);
+    for (int r = s0 * 32; r < r1; ++r) {
+      int lr = row_of_sell ? (*row_of_sell)[r] : r;
+      int s = r >> 5, lane = r & 31;
+      int32_t* dst = S.col.data() + (size_t)S.sbase[s] + lane;
+      const int32_t* src = L.col.data() + L.ptr[lr];
+      for (int k = 0, n = L.ptr[lr + 1] - L.ptr[lr]; k < n; ++k) dst[(size_t)k * 32] = src[k];
+    }
+  };
+  if (rows > 400000) {
+    const int mid = S.nslices / 2;
+    std::thread t(fill, 0, mid);
+    fill(mid, S.nslices);
+    t.join();
+  } else {
+    fill(0, S.nslices);
   }
 }
 
@@ -300,14 +313,23 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     }
     make_sell(rows, S.Pf, nullptr, S.Hpp);
     S.hpp_diag.resize(S.Pf);
-    for (int h = 0; h < S.Pf; ++h) S.hpp_diag[h] = sell_entry(S.Hpp, h, lc[h]);
-    for (int t = 0; t < np; ++t) {
-      int k = pk[t];
-      int e_up = sell_entry(S.Hpp, pa[t], up_idx[t]);    // block (row a, col b), a < b
-      int e_low = sell_entry(S.Hpp, pb[t], low_idx[t]);  // block (row b, col a)
-      bool fwd = S.pp_hi[k] == pa[t];
-      S.pp_e_ij[k] = fwd ? e_up : e_low;
-      S.pp_e_ji[k] = fwd ? e_low : e_up;
+    auto entries = [&](int t0, int t1, int h0, int h1) {  // independent per pair / per row
+      for (int h = h0; h < h1; ++h) S.hpp_diag[h] = sell_entry(S.Hpp, h, lc[h]);
+      for (int t = t0; t < t1; ++t) {
+        int k = pk[t];
+        int e_up = sell_entry(S.Hpp, pa[t], up_idx[t]);    // block (row a, col b), a < b
+        int e_low = sell_entry(S.Hpp, pb[t], low_idx[t]);  // block (row b, col a)
+        bool fwd = S.pp_hi[k] == pa[t];
+        S.pp_e_ij[k] = fwd ? e_up : e_low;
+        S.pp_e_ji[k] = fwd ? e_low : e_up;
+      }
+    };
+    if (np > 400000) {
+      std::thread t(entries, 0, np / 2, 0, S.Pf / 2);
+      entries(np / 2, np, S.Pf / 2, S.Pf);
+      t.join();
+    } else {
+      entries(0, np, 0, S.Pf);
     }
   };
 
