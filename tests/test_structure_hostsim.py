@@ -263,3 +263,100 @@ def test_preconditioner_blocks_are_the_inverse_schur_diagonal_blocks(lam):
             ref = Dinv[3 * (p - c0):3 * (p - c0) + 3, :]
             assert np.abs(got - ref).max() <= 2e-6 * np.abs(Dinv).max(), (c0, p)
             assert np.all(C[p][:, 3 * (c1 - c0):] == 0)  # no coupling to the poses missing from a partial chunk
+
+
+def _random_graph(rng):
+    """Small random graph with the collisions the structure builder has to get right: duplicate and reversed edges,
+    several fixed poses, fixed landmarks, unobserved (inactive) vertices, shuffled ids, shuffled insertion ranks."""
+    P, L = int(rng.integers(2, 40)), int(rng.integers(0, 9))
+    gt = np.cumsum(rng.normal(size=(P, 3)) * [0.5, 0.2, 0.2], axis=0)
+    lines = np.stack([rng.uniform(0.5, 6.0, L), rng.uniform(-np.pi, np.pi, L)], 1) if L else np.zeros((0, 2))
+    n_pp = int(rng.integers(1, 3 * P))
+    pp_i = rng.integers(0, P, n_pp)
+    pp_j = (pp_i + rng.integers(1, P, n_pp)) % P
+    if n_pp > 3:  # duplicates and a reversed duplicate
+        pp_i[-1], pp_j[-1] = pp_i[0], pp_j[0]
+        pp_i[-2], pp_j[-2] = pp_j[1], pp_i[1]
+    n_pl = int(rng.integers(0, 4 * P)) if L else 0
+    pl_p, pl_l = rng.integers(0, P, n_pl), rng.integers(0, max(L, 1), n_pl)
+    if n_pl > 2:
+        pl_p[-1], pl_l[-1] = pl_p[0], pl_l[0]
+    z_pp = gg.se2_between(gt[pp_i], gt[pp_j]) + rng.normal(size=(n_pp, 3)) * 0.02
+    z_pl = (gg.line_in_pose_frame(gt[pl_p], lines[pl_l]) + rng.normal(size=(n_pl, 2)) * 0.02) if n_pl else np.zeros((0, 2))
+    def spd(n, d):
+        out = []
+        for _ in range(n):
+            a = rng.normal(size=(d, d))
+            m = a @ a.T + d * np.eye(d)
+            out.append([m[0, 0], m[0, 1], m[0, 2], m[1, 1], m[1, 2], m[2, 2]] if d == 3 else [m[0, 0], m[0, 1], m[1, 1]])
+        return np.array(out, np.float64).reshape(n, 6 if d == 3 else 3)
+    pose_fixed = (rng.random(P) < 0.15).astype(np.uint8)
+    pose_fixed[0] = 1
+    lm_fixed = (rng.random(L) < 0.15).astype(np.uint8)
+    pid = rng.permutation(P).astype(np.int32) * 3  # ids define the Hessian order, not the array positions
+    lid = (gg.LANDMARK_ID0 + rng.permutation(L) * 2).astype(np.int32)
+    seq = rng.permutation(n_pp + n_pl).astype(np.int64)
+    return gg.Graph(name="fuzz", pose_id=pid, pose_est=gt + rng.normal(size=(P, 3)) * 0.05, pose_fixed=pose_fixed, pose_gt=gt,
+                    lm_id=lid, lm_est=lines + rng.normal(size=(L, 2)) * 0.02, lm_fixed=lm_fixed, lm_gt=lines,
+                    pp_i=pp_i.astype(np.int32), pp_j=pp_j.astype(np.int32), pp_z=z_pp, pp_info=spd(n_pp, 3),
+                    pp_phi=np.where(rng.random(n_pp) < 0.3, 1.0, 0.0), pp_seq=seq[:n_pp],
+                    pl_pose=pl_p.astype(np.int32), pl_lm=pl_l.astype(np.int32), pl_z=z_pl, pl_info=spd(n_pl, 2), pl_seq=seq[n_pp:])
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_graphs_structure_and_system_match_oracle(seed):
+    """Fuzz of the host symbolic phase + the row bodies against the oracle: index mapping, block list (bit-exact), H, b,
+    chi2 and one damped solve on random graphs full of collisions (duplicates, reversed edges, fixed and inactive vertices,
+    permuted ids and insertion ranks, DCS on a random subset)."""
+    from oracle.cpu_oracle import JAC_ANALYTIC, Oracle
+    g = _random_graph(np.random.default_rng(1000 + seed))
+    o = Oracle(g)
+    hs = hostsim.HostSim(g, jac_numeric=False, tol=1e-12)
+    ok_o = o.initialize_optimization()
+    if not ok_o:
+        assert hs.status != capi.OK
+        return
+    assert hs.status == capi.OK, hs.error
+    so, sh = o.structure(), hs.structure()
+    for k in ("n_free", "n_blocks", "dim"):
+        assert so[k] == sh[k], k
+    for k in ("kind", "index", "offset", "row", "col", "nrows", "ncols", "pose_hidx", "lm_hidx"):
+        assert np.array_equal(so[k], sh[k]), k
+    lo, lh = o.linearize(JAC_ANALYTIC), hs.linearize()
+    scale = max(1.0, np.abs(lo["H"]).max())
+    assert np.abs(lh["H"] - lo["H"]).max() <= 1e-12 * scale
+    assert np.abs(lh["b"] - lo["b"]).max() <= 1e-11 * max(1.0, np.abs(lo["b"]).max())
+    np.testing.assert_allclose(lh["chi2"], lo["chi2"], rtol=1e-12)
+    lam = 10.0  # damped enough for every random graph to be positive definite
+    ok, xo = o.solve_once(lam, JAC_ANALYTIC)
+    f, xh, it, rel = hs.solve_once(lam)
+    assert ok and f == 0, (ok, f)
+    assert np.abs(xh - xo).max() <= 1e-8 * max(1e-3, np.abs(xo).max())
+
+
+@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("world", [2, 3])
+def test_random_graphs_partitioned_match_single_rank(seed, world):
+    """The same fuzz through the row-block partition planner: `world` virtual ranks against one."""
+    g = _random_graph(np.random.default_rng(2000 + seed))
+    one = hostsim.HostSim(g, jac_numeric=False, tol=1e-12)
+    many = hostsim.HostSim(g, jac_numeric=False, tol=1e-12, world=world)
+    assert one.status == many.status
+    if one.status != capi.OK:
+        return
+    l1, lm = one.linearize(), many.linearize()
+    np.testing.assert_array_equal(lm["H"], l1["H"])
+    np.testing.assert_array_equal(lm["b"], l1["b"])
+    assert many.check_hlp() == 0.0
+    f1, x1, _, _ = one.solve_once(10.0)
+    fm, xm, _, _ = many.solve_once(10.0)
+    assert f1 == fm == 0
+    assert np.abs(xm - x1).max() <= 1e-8 * max(1e-3, np.abs(x1).max())
+    n1, _ = one.optimize(3, capi.ALGO_LM)
+    nm, _ = many.optimize(3, capi.ALGO_LM)
+    assert n1 == nm
+    p1, q1 = one.estimates()
+    for r in range(world):
+        pm, qm = many.estimates(r)
+        np.testing.assert_allclose(pm, p1, atol=1e-8)
+        np.testing.assert_allclose(qm, q1, atol=1e-8)
