@@ -356,3 +356,36 @@ def test_c5_full_size_properties():
     a.pop()
     p, l = a.estimates()
     assert np.array_equal(p, g.pose_est) and np.array_equal(l, g.lm_est)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_graphs_gpu_match_oracle(seed):
+    """The collision fuzz of tests/test_structure_hostsim.py through the C ABI on the device: structure bit-exact,
+    H / b / chi2 to 1e-12, one damped solve to 1e-7, LM-5 final state to 1e-6."""
+    from test_structure_hostsim import _random_graph
+    g = _random_graph(np.random.default_rng(1000 + seed))
+    o = Oracle(g)
+    opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC, pcg_tolerance=1e-12)
+    ok_o = o.initialize_optimization()
+    ok_g = opt.initialize_optimization(g)
+    assert ok_o == ok_g
+    if not ok_o:
+        return
+    so, sg = o.structure(), opt.structure()
+    for k in STRUCT_KEYS:
+        assert np.array_equal(so[k], sg[k]), k
+    lo, lg = o.linearize(JAC_ANALYTIC), opt.linearize()
+    assert rel_err(lg["H"], lo["H"]) < 1e-12 and rel_err(lg["b"], lo["b"]) < 1e-11
+    np.testing.assert_allclose(lg["chi2"], lo["chi2"], rtol=1e-12)
+    ok, xo = o.solve_once(10.0, JAC_ANALYTIC)
+    okg, xg, _, _ = opt.solve_once(10.0)
+    assert ok and okg
+    assert np.abs(xg - xo).max() <= 1e-7 * max(1e-3, np.abs(xo).max())
+    n_o, st_o = o.optimize(5, ALGO_LM, JAC_ANALYTIC)
+    n_g, st_g = opt.optimize(5)
+    if n_o == n_g == 5 and all(s["trials"] == 1 for s in st_o):
+        po, lo_ = o.estimates()
+        pg, lg_ = opt.estimates()
+        assert pose_err(pg, po) < 1e-6
+        if g.L:
+            assert rel_err(lg_, lo_) < 1e-6
