@@ -1396,6 +1396,7 @@ bool handle_view(sgb_handle* h, HandleView* out) {
   out->lm_est = h->G.lm_buf[h->G.cur][h->G.rank];
   return true;
 }
+int handle_device(const sgb_handle* h) { return h ? h->device : -1; }
 void handle_set_error(sgb_handle* h, const std::string& msg) {
   if (h) h->err = msg;
 }

@@ -18,6 +18,8 @@ struct HandleView {
 };
 // false when the handle has no graph
 bool handle_view(sgb_handle* h, HandleView* out);
+// CUDA device of a handle (valid before any graph is set)
+int handle_device(const sgb_handle* h);
 void handle_set_error(sgb_handle* h, const std::string& msg);
 
 }  // namespace sgb

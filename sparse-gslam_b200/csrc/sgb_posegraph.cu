@@ -365,6 +365,7 @@ sgb_status sgb_pg_optimize(sgb_pose_graph* pg, sgb_handle* solver, int32_t algo,
                            sgb_iter_stat* stats) {
   if (iters_done) *iters_done = -1;
   if (!pg || !solver) return SGB_ERR_INVALID;
+  if (handle_device(solver) != pg->device) { pg->err = "optimize: the solver handle lives on another device than the store"; return SGB_ERR_INVALID; }
   PG_CUDA(cudaSetDevice(pg->device));
   const int P = (int)pg->id.size();
   std::vector<int32_t> ci, cj, slot;
