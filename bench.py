@@ -679,6 +679,11 @@ def main():
         h2d = graph_h2d_bytes(g)
         d2h = int(g.pose_est.nbytes + g.lm_est.nbytes)
         e_iters, e_steps = 0, max(1, min(args.steps, 3))
+        # one untimed end-to-end step first (the resident warm-up does not touch the host path: heap growth and first-touch
+        # page faults of the ~1 GB of host-side structure arrays belong to the first call only)
+        assert init_graph()
+        opt.optimize(iters)
+        opt.estimates()
         barrier()
         te0 = time.perf_counter()
         for _ in range(e_steps):
