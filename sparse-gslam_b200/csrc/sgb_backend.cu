@@ -299,7 +299,7 @@ sgb_status launch_backsub_update(sgb_handle* h, int dst, double lambda_override,
     k_backsub<<<grid_for(32 * G.Hlp.nslices), kThreads, 0, h->stream>>>(G);  // one warp per slice of the grouped Hlp
     h->tm.kernel_launches++;
   }
-  k_update<<<grid_for(G.nP + G.nL), kThreads, 0, h->stream>>>(G, h->d_sc, dst, h->d_part_p, lambda_override, use_override);
+  k_update<<<grid_for(G.nP + G.nL_owned), kThreads, 0, h->stream>>>(G, h->d_sc, dst, h->d_part_p, lambda_override, use_override);
   h->tm.kernel_launches++;
   if (G.world > 1) {  // every replica of the estimates has received every owner's rows
     k_xbarrier<<<1, 32, 0, h->stream>>>(G, h->d_sc);
@@ -368,7 +368,7 @@ sgb_status do_step(sgb_handle* h, int algo, int iteration, int* result, sgb_iter
       if ((st = launch_backsub_update(h, G.cur ^ 1, 0.0, 0)) != SGB_OK) return st;
       if ((st = launch_chi2(h, G.cur ^ 1)) != SGB_OK) return st;
       k_lm_control<<<1, kThreads, 0, s>>>(G, h->d_sc, h->d_part_e, grid_for(G.n_pp_owned + G.n_pl_owned), h->d_part_p,
-                                          grid_for(G.nP + G.nL), max_trials);
+                                          grid_for(G.nP + G.nL_owned), max_trials);
       h->tm.kernel_launches++;
       SGB_CUDA(cudaGetLastError());
       SGB_CUDA(cudaEventRecord(h->ev.e[4], s));
@@ -664,6 +664,8 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   DevGraph& G = h->G;
   std::memset(&G, 0, sizeof G);
   G.world = world; G.rank = rank; G.nP = P.nP; G.nL = P.nL; G.capP = P.capP; G.capL = P.capL;
+  G.nL_owned = P.nL_owned;
+  G.ghosts = (world > 1 && partition_ghost_landmarks()) ? 1 : 0;
   G.P_all = S.P_all; G.L_all = S.L_all; G.n_pp = P.n_pp; G.n_pl = P.n_pl;
   G.n_pp_owned = P.n_pp_owned; G.n_pl_owned = P.n_pl_owned;
   G.has_robust = S.has_robust ? 1 : 0;
@@ -947,7 +949,7 @@ static sgb_status gather_owned_vector(sgb_handle* h, const double* dp, const dou
   if (P.nL) {
     std::vector<double> tmp(2 * (size_t)P.nL);
     SGB_CUDA(cudaMemcpy(tmp.data(), dl, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost));
-    for (int l = 0; l < P.nL; ++l) {
+    for (int l = 0; l < P.nL_owned; ++l) {  // ghost rows belong to their owners' share
       size_t o = 3 * (size_t)S.Pf + 2 * (size_t)P.lm_global[l];
       out[o] = tmp[2 * (size_t)l];
       out[o + 1] = tmp[2 * (size_t)l + 1];

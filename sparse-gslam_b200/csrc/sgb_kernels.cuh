@@ -301,7 +301,8 @@ struct PcgParams {
 // after it (fence before the ticket, fence + release store by the publisher, L1-bypassing loads afterwards).
 __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long long* bar, unsigned int nb,
                                              unsigned long long& epoch, unsigned long long& seq, double* part,
-                                             double* vals, int nv, double* sm, int* s_last, double* cl_part = nullptr) {
+                                             double* vals, int nv, double* sm, int* s_last, double* cl_part = nullptr,
+                                             bool local_only = false) {
   if (cl_part != nullptr) {
     // Small graph: the whole grid is ONE thread-block cluster (<= 16 CTAs). The hardware cluster barrier (release /
     // acquire at cluster scope, ~0.2 us) replaces the barrier through global memory (~1.8 us), and the partial sums
@@ -340,8 +341,9 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
   ++seq;
   epoch += nb;
   const int slot = (int)(seq & 1ull);
-  if (g.world == 1) {
-    // One GPU: flat barrier, gpu scope only. Every CTA deposits its partial (double-buffered by the parity of seq:
+  if (g.world == 1 || local_only) {
+    // One GPU (or a barrier that only has to span this GPU: with ghost landmarks nobody reads another rank's t):
+    // flat barrier, gpu scope only. Every CTA deposits its partial (double-buffered by the parity of seq:
     // a CTA can be at most one barrier ahead of the slowest reader), arrives with a release reduction, spins on an
     // acquire load, and then sums ALL partials itself in index order -- the same value in every CTA, and no
     // "last CTA reduces and publishes" hop on the critical path.
@@ -500,7 +502,8 @@ __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, cons
       const double beta = it == 0 ? 0.0 : gam / gam_old;
       if (g.capL > 0) {
         lm_slices_pass(g, tid >> 5, nthreads >> 5, 0);
-        grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, s_last, cl_part);  // every rank's t segment is complete
+        // every rank's t segment is complete; with ghost landmarks t is only read on the GPU that wrote it
+        grid_xreduce(g, bar, nb, epoch, seq, part, nullptr, 0, sm, s_last, cl_part, g.world > 1 && g.ghosts != 0);
       }
       SGB_PHASE_LAP(0);
       acc = schur_phaseB_rows_u<U>(g, tid, nthreads, lambda, beta);
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(kThreads) k_update(DevGraph g, DevScalars* sc,
   __shared__ double sm[32];
   double lambda = use_override ? lambda_override : sc->lambda;
   double s = 0.0;
-  int n = g.nP + g.nL;
+  int n = g.nP + g.nL_owned;  // ghost landmark rows are updated by their owners
   for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < n; v += gridDim.x * blockDim.x) {
     if (v < g.nP) s += update_pose_row(g, v, lambda, dst);
     else s += update_lm_row(g, v - g.nP, lambda, dst);
@@ -811,7 +814,7 @@ __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, B
       for (int sl = tid >> 5; sl < g.Hlp.nslices; sl += nth >> 5) lm_slice_pass(g, sl, 1);
       __syncthreads();
       double s = 0.0;
-      for (int v = tid; v < g.nP + g.nL; v += nth)
+      for (int v = tid; v < g.nP + g.nL_owned; v += nth)
         s += v < g.nP ? update_pose_row(g, v, lambda, dst) : update_lm_row(g, v - g.nP, lambda, dst);
       const double scale = block_sum(s, sm);
       __syncthreads();

@@ -10,6 +10,16 @@
 
 namespace sgb {
 
+static int g_ghosts = -1;  // -1: not decided yet (environment), 0 / 1
+void partition_use_ghost_landmarks(bool on) { g_ghosts = on ? 1 : 0; }
+bool partition_ghost_landmarks() {
+  if (g_ghosts < 0) {
+    const char* e = std::getenv("SGB_GHOST_LANDMARKS");
+    g_ghosts = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_ghosts == 1;
+}
+
 namespace {
 
 // the k-th stored block of a SELL row and its column; returns the row width
@@ -77,6 +87,17 @@ void build_grouped_sell(const FlatRows& rows, int target_steps, HostSell& S) {
     int len = rows.size(r);
     int G = std::min(32, pow2_ceil((len + target_steps - 1) / std::max(1, target_steps)));
     int rh = 32 / G, sh = 0;
+    // the rows of one run come sorted by descending length; where two runs meet (owned rows, then ghost rows) a later
+    // row of the slice may be longer than its first: widen until the slice's longest row fits
+    for (bool grown = true; grown;) {
+      grown = false;
+      for (int q = r + 1; q < std::min(n, r + rh); ++q)
+        if (rows.size(q) > len) { len = rows.size(q); grown = true; }
+      if (grown) {
+        G = std::min(32, pow2_ceil((len + target_steps - 1) / std::max(1, target_steps)));
+        rh = 32 / G;
+      }
+    }
     while ((1 << sh) < rh) ++sh;
     int w = (len + G - 1) / G * G;
     int s = (int)S.sshift.size();
@@ -252,8 +273,35 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
       count[o]++;
     }
   }
-  P.nL = count[rank];
+  P.nL = P.nL_owned = count[rank];
   P.capL = *std::max_element(count.begin(), count.end());
+  // global free landmark -> row on THIS rank (owned rows first, then the ghost copies), -1 = not kept here
+  std::vector<int32_t> loc_lm(S.Lf, -1);
+  for (int l = 0; l < P.nL_owned; ++l) loc_lm[P.lm_global[l]] = l;
+  if (world > 1 && partition_ghost_landmarks()) {
+    std::vector<int32_t> nghost(world, 0), mine;
+    std::vector<char> seen(world);
+    for (int hl = 0; hl < S.Lf; ++hl) {
+      std::fill(seen.begin(), seen.end(), 0);
+      for (int q = S.lp_ptr[hl]; q < S.lp_ptr[hl + 1]; ++q) {
+        int o = owner_p(S.lp_col[q]);
+        if (o == lm_owner[hl] || seen[o]) continue;
+        seen[o] = 1;
+        nghost[o]++;
+        if (o == rank) mine.push_back(hl);
+      }
+    }
+    std::stable_sort(mine.begin(), mine.end(), [&](int a, int b) {
+      return S.lp_ptr[a + 1] - S.lp_ptr[a] > S.lp_ptr[b + 1] - S.lp_ptr[b];
+    });
+    for (int hl : mine) {
+      loc_lm[hl] = (int)P.lm_global.size();
+      P.lm_global.push_back(hl);
+    }
+    P.nL = (int)P.lm_global.size();
+    P.capL = 0;
+    for (int r = 0; r < world; ++r) P.capL = std::max(P.capL, count[r] + nghost[r]);
+  }
   if (P.capL > kLocalMask) { err = "too many landmarks per rank for the column encoding"; return SGB_ERR_UNSUPPORTED; }
   P.pose_of_l.resize(P.nP);
   for (int l = 0; l < P.nP; ++l) P.pose_of_l[l] = S.pose_of_h[P.p_begin + l];
@@ -263,7 +311,10 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
   if (world == 1) return partition_single(S, P, consume);
 
   auto pose_local = [&](int hp) { return hp >= 0 && owner_p(hp) == rank; };
-  auto lm_local = [&](int hl) { return hl >= 0 && lm_owner[hl] == rank; };
+  P.enc_lm_here.resize(S.Lf);
+  for (int hl = 0; hl < S.Lf; ++hl) P.enc_lm_here[hl] = loc_lm[hl] >= 0 ? ((rank << kOwnerShift) | loc_lm[hl]) : P.enc_lm[hl];
+  auto lm_local = [&](int hl) { return hl >= 0 && loc_lm[hl] >= 0; };          // owned or ghost row here
+  auto lm_owned = [&](int hl) { return hl >= 0 && lm_owner[hl] == rank; };
 
   // ---- local edges: owned (chi2 accounted here) first, then the halo edges; global order inside each group
   std::vector<int32_t> pp_g2l(S.n_pp, -1), pl_g2l(S.n_pl, -1);
@@ -286,7 +337,7 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
       int hp = S.pl_hp[k], hl = S.pl_hl[k];
       bool local = pose_local(hp) || lm_local(hl);
       if (!local) continue;
-      bool owned = hp >= 0 ? pose_local(hp) : lm_local(hl);
+      bool owned = hp >= 0 ? pose_local(hp) : lm_owned(hl);
       if ((pass == 0) != owned) continue;
       pl_g2l[k] = (int)P.pl_g.size();
       P.pl_g.push_back(k);
@@ -313,8 +364,8 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
       rows.close_row();
       sell_row_cols(S.Hpl, hp, cols);
       for (int c : cols) {
-        rows_pl.col.push_back(P.enc_lm[c]);
-        if (lm_owner[c] != rank) P.halo_t++;
+        rows_pl.col.push_back(P.enc_lm_here[c]);
+        if (loc_lm[c] < 0) P.halo_t++;
       }
       rows_pl.close_row();
     }
@@ -378,10 +429,7 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
     int hp = S.pl_hp[k], hl = S.pl_hl[k];
     if (S.pl_e_pl[k] >= 0) {
       if (pose_local(hp)) P.pl_e_pl[l] = entry_of(P.Hpl, hp - P.p_begin, entry_k(S.Hpl, hp, S.pl_e_pl[k]));
-      if (lm_local(hl)) {
-        int ll = P.enc_lm[hl] & kLocalMask;
-        P.pl_e_lp[l] = entry_of(P.Hlp, ll, S.pl_k_lp[k]);
-      }
+      if (lm_local(hl)) P.pl_e_lp[l] = entry_of(P.Hlp, loc_lm[hl], S.pl_k_lp[k]);
     }
   }
 

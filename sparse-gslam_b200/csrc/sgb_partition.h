@@ -15,11 +15,14 @@ struct LocalPlan {
   int world = 1, rank = 0;
   int chunkP = 0;            // pose rows per rank (last rank may own fewer)
   int nP = 0, nL = 0, capP = 0, capL = 0;
+  int nL_owned = 0;          // the first nL_owned landmark rows are owned; the rest are ghost copies (see below)
   int p_begin = 0;           // first global free pose owned
   int n_pp = 0, n_pl = 0, n_pp_owned = 0, n_pl_owned = 0;
   std::vector<int32_t> pose_of_l, lm_of_l;       // local row -> vertex array index
   std::vector<int32_t> lm_global;                // local landmark -> global free landmark
   std::vector<int32_t> enc_lm;                   // [Lf] global free landmark -> encoded (owner, local)
+  std::vector<int32_t> enc_lm_here;              // [Lf] the same as THIS rank's matrices encode it: its own row when it
+                                                 //      keeps the landmark (owned or ghost), the owner's otherwise
   std::vector<int32_t> pp_g, pl_g;               // local edge -> global ACTIVE edge index (Structure order)
   std::vector<int32_t> pp_i, pp_j, pp_hi, pp_hj, pp_e_ij, pp_e_ji, pp_dup;
   std::vector<int32_t> pl_p, pl_l, pl_hp, pl_hl, pl_e_pl, pl_e_lp, pl_dup;
@@ -32,6 +35,14 @@ struct LocalPlan {
   // halo statistics (distinct remote entries this rank gathers per PCG iteration)
   int64_t halo_p = 0, halo_t = 0;
 };
+
+// Ghost landmarks (world > 1, opt-in): a rank also keeps a full copy of the row of every landmark its poses observe
+// but another rank owns -- all its edges (linearised locally from the replicated estimates), its Hll / W / b_l / t.
+// The pose-major pass then never reads a landmark quantity of another rank, and the barrier after the landmark pass
+// of the PCG only has to span the GPU. Updates, chi2 and the exported system stay with the owner.
+// Default: off, or the environment variable SGB_GHOST_LANDMARKS=1.
+void partition_use_ghost_landmarks(bool on);
+bool partition_ghost_landmarks();
 
 inline int enc_pose(int hp, int chunkP) { return ((hp / chunkP) << 26) | (hp % chunkP); }
 

@@ -286,7 +286,7 @@ SGB_HD void lin_lm_row(const DevGraph& g, int ll, LinAcc& acc) {
     h22 += BtO[2] * t.B[1] + BtO[3] * t.B[3];
     b0 += t.B[0] * t.omr[0] + t.B[2] * t.omr[1];
     b1 += t.B[1] * t.omr[0] + t.B[3] * t.omr[1];
-    if (SGB_LDG(&g.pl_hp[k]) < 0) {  // pose fixed: chi2 owned by the landmark row
+    if (SGB_LDG(&g.pl_hp[k]) < 0 && ll < g.nL_owned) {  // pose fixed: chi2 owned by the landmark row (of the owner)
       acc.chi += t.chi;
       acc.chi_r += t.chi;
     }

@@ -49,7 +49,10 @@ struct Mailbox {
 struct DevGraph {
   // ---- partition
   int32_t world, rank;
-  int32_t nP, nL;        // rows owned by this rank: free poses / free landmarks
+  int32_t nP, nL;        // rows kept by this rank: free poses / free landmarks (landmarks: owned rows first, then ghosts)
+  int32_t nL_owned;      // landmark rows [0, nL_owned) are owned (updated, exported, chi2-accounted here); [nL_owned, nL)
+                         // are ghost copies of rows other ranks own (sgb_partition.h); == nL unless ghosts are enabled
+  int32_t ghosts;        // 1: ghost landmarks are in use, the pose-major pass reads no landmark quantity of another rank
   int32_t capP, capL;    // max rows owned by any rank (array strides in the arena)
   int32_t P_all, L_all;  // all vertices (array order of sgb_set_graph); estimates are replicated on every rank
   int32_t n_pp, n_pl;    // local edges: incident to an owned row

@@ -56,6 +56,7 @@ def lib():
         L.hs_check_hlp.argtypes = [vp]
         L.hs_check_hlp.restype = C.c_double
         L.hs_chi2.argtypes = [vp, vp]
+        L.hs_use_ghost_landmarks.argtypes = [C.c_int]
         L.hs_preconditioner.argtypes = [vp, C.c_double, vp]
         L.hs_pg_append.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.hs_closure_chi2.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
@@ -65,6 +66,11 @@ def lib():
         L.hs_line_fit_information.argtypes = [vp, vp, vp, C.c_int, vp, vp, vp]
         _lib = L
     return _lib
+
+
+def use_ghost_landmarks(on: bool):
+    """Planner switch (sgb_partition.h): ghost copies of the landmark rows other ranks own. Process-global."""
+    lib().hs_use_ghost_landmarks(int(bool(on)))
 
 
 class HostSim:

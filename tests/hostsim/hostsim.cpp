@@ -56,6 +56,8 @@ static void mk_sell(Rank* r, Sell* out, const HostSell& s, int NC) {
 
 extern "C" {
 
+void hs_use_ghost_landmarks(int on) { partition_use_ghost_landmarks(on != 0); }
+
 hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int maxit, int world, int* status) {
   hs_handle* h = new hs_handle();
   h->world = std::max(1, world);
@@ -77,6 +79,7 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
     DevGraph& G = r->G;
     std::memset(&G, 0, sizeof G);
     G.world = h->world; G.rank = rk; G.nP = P.nP; G.nL = P.nL; G.capP = P.capP; G.capL = P.capL;
+    G.nL_owned = P.nL_owned; G.ghosts = (h->world > 1 && partition_ghost_landmarks()) ? 1 : 0;
     G.P_all = S.P_all; G.L_all = S.L_all; G.n_pp = P.n_pp; G.n_pl = P.n_pl;
     G.n_pp_owned = P.n_pp_owned; G.n_pl_owned = P.n_pl_owned;
     G.has_robust = S.has_robust; G.jac_numeric = jac_numeric; G.cur = 0;
@@ -200,7 +203,7 @@ static void gather_vec(hs_handle* h, bool step, double* out) {
     const double* dp = step ? G.x_p[G.rank] : G.b_p;
     const double* dl = step ? G.x_l : G.b_l[G.rank];
     for (int l = 0; l < 3 * P.nP; ++l) out[3 * (size_t)P.p_begin + l] = dp[l];
-    for (int l = 0; l < P.nL; ++l) {
+    for (int l = 0; l < P.nL_owned; ++l) {
       size_t o = 3 * (size_t)S.Pf + 2 * (size_t)P.lm_global[l];
       out[o] = dl[2 * l];
       out[o + 1] = dl[2 * l + 1];
@@ -260,7 +263,7 @@ double hs_check_hlp(hs_handle* h) {
         bool found = false;
         for (int k2 = 0; k2 < w2; ++k2) {
           int e2 = Q.G.Hpl.sbase[s2] + k2 * 32 + l2;
-          if (Q.G.Hpl.col[e2] == r->P.enc_lm[hl]) {
+          if (Q.G.Hpl.col[e2] == (Q.P.enc_lm_here.empty() ? Q.P.enc_lm[hl] : Q.P.enc_lm_here[hl])) {
             for (int c = 0; c < 6; ++c) worst = std::max(worst, std::fabs(Q.G.Hpl.vals[sell_vaddr(e2, 6, c)] - G.Hlp.vals[sell_vaddr(e, 6, c)]));
             found = true;
           }
@@ -348,7 +351,7 @@ static double update_all(hs_handle* h, double lambda, int dst) {
   for (auto& rk : h->R) {
     DevGraph& G = rk->G;
     for (int lp = 0; lp < G.nP; ++lp) scale += update_pose_row(G, lp, lambda, dst);
-    for (int ll = 0; ll < G.nL; ++ll) scale += update_lm_row(G, ll, lambda, dst);
+    for (int ll = 0; ll < G.nL_owned; ++ll) scale += update_lm_row(G, ll, lambda, dst);
   }
   return scale;
 }

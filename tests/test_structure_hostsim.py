@@ -360,3 +360,70 @@ def test_random_graphs_partitioned_match_single_rank(seed, world):
         pm, qm = many.estimates(r)
         np.testing.assert_allclose(pm, p1, atol=1e-8)
         np.testing.assert_allclose(qm, q1, atol=1e-8)
+
+
+@pytest.fixture
+def ghost_landmarks():
+    hostsim.use_ghost_landmarks(True)
+    yield
+    hostsim.use_ghost_landmarks(False)
+
+
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
+def test_ghost_landmarks_match_single_rank(world, ghost_landmarks):
+    """Opt-in planner mode (sgb_partition.h): every rank keeps a full copy of the landmark rows its poses observe. No
+    landmark quantity is read from another rank any more (halo_t == 0), and the system, the solve and the LM trajectory
+    are the single-rank ones."""
+    g = gg.make_small(seed=3, P=120, L=20, E_l=300, n_closures=10)
+    hostsim.use_ghost_landmarks(False)
+    one = hostsim.HostSim(g, jac_numeric=False, tol=1e-12)
+    plain = hostsim.HostSim(g, jac_numeric=False, tol=1e-12, world=world)
+    hostsim.use_ghost_landmarks(True)
+    many = hostsim.HostSim(g, jac_numeric=False, tol=1e-12, world=world)
+    assert many.status == capi.OK, many.error
+    ps, pp = many.partition_stats(), plain.partition_stats()
+    assert all(p["halo_t"] == 0 for p in ps) and any(p["halo_t"] > 0 for p in pp)
+    assert sum(p["nL"] for p in ps) > sum(p["nL"] for p in pp)          # the ghost rows
+    assert sum(p["n_pl_owned"] for p in ps) == g.n_pl and sum(p["n_pp_owned"] for p in ps) == g.n_pp
+    l1, lm = one.linearize(), many.linearize()
+    np.testing.assert_array_equal(lm["H"], l1["H"])
+    np.testing.assert_array_equal(lm["b"], l1["b"])
+    np.testing.assert_allclose(lm["chi2"], l1["chi2"], rtol=1e-13)
+    assert many.check_hlp() == 0.0
+    f1, x1, it1, _ = one.solve_once(0.3)
+    fm, xm, itm, _ = many.solve_once(0.3)
+    assert f1 == fm == 0 and abs(it1 - itm) <= max(2, 0.25 * it1)
+    np.testing.assert_allclose(xm, x1, rtol=1e-9, atol=1e-12)
+    n1, s1 = one.optimize(6, capi.ALGO_LM)
+    nm, sm = many.optimize(6, capi.ALGO_LM)
+    assert n1 == nm and [s["trials"] for s in s1] == [s["trials"] for s in sm]
+    np.testing.assert_allclose([s["chi2"] for s in sm], [s["chi2"] for s in s1], rtol=1e-9)
+    p1, q1 = one.estimates()
+    for r in range(world):
+        pm, qm = many.estimates(r)
+        np.testing.assert_allclose(pm, p1, atol=1e-9)
+        np.testing.assert_allclose(qm, q1, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_ghost_landmarks_fuzz(seed, ghost_landmarks):
+    g = _random_graph(np.random.default_rng(3000 + seed))
+    hostsim.use_ghost_landmarks(False)
+    one = hostsim.HostSim(g, jac_numeric=False, tol=1e-12)
+    hostsim.use_ghost_landmarks(True)
+    many = hostsim.HostSim(g, jac_numeric=False, tol=1e-12, world=3)
+    assert one.status == many.status
+    if one.status != capi.OK:
+        return
+    l1, lm = one.linearize(), many.linearize()
+    np.testing.assert_array_equal(lm["H"], l1["H"])
+    np.testing.assert_array_equal(lm["b"], l1["b"])
+    np.testing.assert_allclose(lm["chi2"], l1["chi2"], rtol=1e-12)
+    assert many.check_hlp() == 0.0
+    f1, x1, _, _ = one.solve_once(10.0)
+    fm, xm, _, _ = many.solve_once(10.0)
+    assert f1 == fm == 0
+    assert np.abs(xm - x1).max() <= 1e-8 * max(1e-3, np.abs(x1).max())
+    assert one.optimize(3, capi.ALGO_LM)[0] == many.optimize(3, capi.ALGO_LM)[0]
+    np.testing.assert_allclose(many.estimates(2)[0], one.estimates()[0], atol=1e-8)
+    np.testing.assert_allclose(many.estimates(1)[1], one.estimates()[1], atol=1e-8)
