@@ -152,6 +152,9 @@ const char* sgb_version(void);
 int32_t sgb_device_count(void);
 void sgb_default_options(sgb_options* opt);
 
+/* The first sgb_create of a process also raises glibc's mmap / trim thresholds (mallopt) so that the large host-side
+ * symbolic arrays of sgb_set_graph are recycled between calls instead of being unmapped and page-faulted in again;
+ * performance-only, process-wide, disabled by SGB_KEEP_HOST_MEMORY=0 in the environment. */
 sgb_status sgb_create(const sgb_options* opt /* NULL = defaults */, sgb_handle** out);
 void sgb_destroy(sgb_handle* h);
 const char* sgb_last_error(const sgb_handle* h);

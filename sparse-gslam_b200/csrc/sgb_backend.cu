@@ -5,6 +5,7 @@
 //   SparseOptimizer::optimize -> OptimizationAlgorithm{Levenberg,GaussNewton}::solve, called by the reference at
 //   src/sparse_gslam/src/drone.cpp:150,155, submap_loop_closer.cpp:287, log_runner.cpp:204.
 #include <cuda_runtime.h>
+#include <malloc.h>
 
 #include <algorithm>
 #include <chrono>
@@ -469,6 +470,21 @@ void sgb_default_options(sgb_options* o) {
 sgb_status sgb_create(const sgb_options* opt, sgb_handle** out) {
   if (!out) return SGB_ERR_INVALID;
   *out = nullptr;
+  {
+    // sgb_set_graph builds ~1 GB of host-side symbolic arrays on a 1M-pose graph and frees them at the next call
+    // (the reference re-initialises once per key-frame). With glibc's defaults every array above the mmap threshold
+    // is unmapped and page-faulted in again each time (~20 % of the host symbolic phase): keep freed memory in the
+    // heap instead. Process-wide and performance-only; SGB_KEEP_HOST_MEMORY=0 leaves malloc alone.
+    static const bool once = [] {
+      const char* e = std::getenv("SGB_KEEP_HOST_MEMORY");
+      if (!(e && e[0] == '0')) {
+        mallopt(M_MMAP_THRESHOLD, 1 << 30);
+        mallopt(M_TRIM_THRESHOLD, 1 << 30);  // int arguments: 1 GiB is the largest power of two that fits
+      }
+      return true;
+    }();
+    (void)once;
+  }
   if (sgb_device_count() <= 0) return SGB_ERR_NO_DEVICE;  // no CPU fallback by design
   sgb_handle* h = new sgb_handle();
   if (opt) h->opt = *opt; else sgb_default_options(&h->opt);
