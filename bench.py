@@ -557,6 +557,11 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
+        if args.workload.lower() in ("stream", "edits"):
+            # these side workloads time their CPU arm inside the GPU line itself (cpu_baseline / per-kernel cpu_units_per_s)
+            print(json.dumps({"impl": "reference", "unavailable": f"--workload {args.workload} reports its CPU arm in the "
+                              "cpu_baseline of its own line; the reference arm exists for c1..c5"}))
+            return
         r = cpu_reference_run(args.workload, max(1, args.steps), 1)
         # the same config as the GPU arm's line (the workload description, algorithm and iteration count)
         wl = args.workload.lower()
