@@ -559,3 +559,65 @@ def test_set_graph_device_full_graph_with_slots(name):
     assert np.abs(lb_ - la_).max() < 1e-6 * max(1.0, np.abs(la_).max())
     ca, cb = a.active_chi2()[0], b.active_chi2()[0]
     assert abs(ca - cb) <= 1e-6 * ca
+
+
+# ------------------------------------------------------------------------------------------------ edge cases (host bodies vs oracle)
+def _same(a, b, rtol, atol=0.0):
+    """allclose that also demands the same NaN / inf pattern (degenerate inputs must degenerate the same way)."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(np.isinf(a), np.isinf(b))
+    m = np.isfinite(a)
+    np.testing.assert_allclose(a[m], b[m], rtol=rtol, atol=atol)
+
+
+def test_edge_cases_line_fit():
+    segs = []
+    segs.append(np.array([[1.0, 2.0]]))                                   # one point: no direction, 0/0 in the covariance
+    segs.append(np.array([[1.0, 2.0], [2.0, 2.0]]))                       # two points
+    segs.append(np.stack([np.linspace(-1, 1, 9), np.full(9, 3.0)], 1))    # exactly horizontal, zero residual
+    segs.append(np.stack([np.full(9, -2.5), np.linspace(-1, 1, 9)], 1))   # exactly vertical, rho < 0 before the flip
+    segs.append(np.stack([np.linspace(0, 4, 30), np.linspace(0, 4, 30)], 1) * [1, 1] + [0, 1e-3])  # diagonal
+    segs.append(np.stack([500 + np.linspace(0, 2, 40), 300 + 0.5 * np.linspace(0, 2, 40)], 1))      # far from the origin
+    pts = np.concatenate(segs).astype(np.float32)
+    seg = np.concatenate([[0], np.cumsum([len(s) for s in segs])]).astype(np.int32)
+    cov = np.tile(np.array([1e-4, 2e-5, 2e-5, 3e-4], np.float32), (len(pts), 1))
+    a, b = hostsim.line_fit_information(pts, cov, seg), co.line_fit_information(pts, cov, seg)
+    _same(a[0], b[0], 1e-5, 1e-6)
+    _same(a[1], b[1], 1e-4, 1e-12)
+    _same(a[2], b[2], 1e-3)
+    assert np.all(b[0][2:, 0] >= 0)
+
+
+def test_edge_cases_odometry_and_scan_points():
+    deltas = np.array([[0.0, 0.0, 0.0], [0.0, 0.0, 0.5], [-0.1, 0.02, -0.3], [0.2, 0.0, 0.0], [0.0, 0.1, 0.0],
+                       [0.3, -0.1, 3.2], [0.1, 0.0, 3.1]])                 # standing still, turning on the spot, reversing,
+    seg = np.array([0, 0, 1, 2, 3, 5, 7], np.int32)                        # sideways motion, a turn past +-pi
+    a, b = hostsim.odom_information(deltas, seg, 0.1, 0.05, 0.2), co.odom_information(deltas, seg, 0.1, 0.05, 0.2)
+    pose_close(a[0], b[0], 1e-13)
+    _same(a[1], b[1], 1e-12, 1e-22)
+    _same(a[2], b[2], 1e-9)
+    assert np.all(np.abs(b[0][:, 2]) <= np.pi)
+    # scan points: a single scan per window (no odometry in between), a window without any return
+    beam = np.stack([np.cos(np.linspace(-1, 1, 7)), np.sin(np.linspace(-1, 1, 7))], 1).astype(np.float32)
+    pts = np.full((2, 1, 7, 2), np.inf, np.float32)
+    pts[0, 0] = beam * 2.0
+    a = hostsim.scan_point_covariances(np.zeros((2, 0, 3)), beam, pts, 0.1, 0.05, 0.2, 9e-4)
+    b = co.scan_point_covariances(np.zeros((2, 0, 3)), beam, pts, 0.1, 0.05, 0.2, 9e-4)
+    assert np.array_equal(a[2], b[2]) and a[2][0].all() and not a[2][1].any()
+    _same(a[0], b[0], 1e-6, 1e-12)
+    _same(a[1], b[1], 1e-6, 1e-7)
+    assert np.all(a[0][1] == 0) and np.all(a[1][1] == 0)
+
+
+def test_edge_cases_chain_copy():
+    # headings right at the wrap, a chain that turns through +-pi several times
+    lm = np.array([[0.0, 0.0, np.pi - 1e-12], [0.5, 0.0, -np.pi], [1.0, 0.1, np.pi - 1e-9], [1.5, 0.1, -np.pi + 1e-9],
+                   [2.0, 0.2, 3.0], [2.5, 0.2, -3.0]])
+    prev = np.array([10.0, -3.0, -np.pi])
+    z0, e0 = co.pg_append(prev, lm)
+    z1, e1 = hostsim.pg_append(prev, lm, 4, 2, 2)
+    pose_close(z1, z0, 1e-13)
+    pose_close(e1, e0, 1e-12)
+    assert np.all((z0[:, 2] >= -np.pi) & (z0[:, 2] < np.pi)) and np.all((e0[:, 2] >= -np.pi) & (e0[:, 2] < np.pi))
+    z, e = hostsim.pg_append(prev, lm[:1])  # nothing to copy
+    assert z.shape == (0, 3) and e.shape == (0, 3)
