@@ -546,6 +546,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SGB_WORKLOAD", "c5"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N>1 comparison with the one-GPU result")
     ap.add_argument("--pcg-tol", type=float, default=1e-10)
     ap.add_argument("--stream-frames", type=int, default=400, help="key-frames replayed by --workload stream")
     args = ap.parse_args()
@@ -705,6 +706,37 @@ def main():
         e2e = {"value": e_iters / te, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": 1e3 * te / e_steps, "steps": e_steps}
 
+    # ---------------- multi-GPU correctness inside the scaling run itself ----------------
+    # The partitioned job's final state (estimates are replicated on every rank) against the SAME optimize() on ONE GPU,
+    # run by rank 0 on its own device after the timed regions: final chi2, largest pose / landmark difference, LM and
+    # PCG iteration counts. The scaling record then carries its own correctness evidence.
+    parity = None
+    if world > 1 and not args.no_parity:
+        opt.optimize(iters, resident=True)
+        chi_n = opt.active_chi2()          # collective: every rank takes part in the cross-GPU reduction
+        p_n, l_n = opt.estimates()
+        t_n = opt.timings()
+        barrier()
+        if rank == 0:
+            one = SparseOptimizerB200(algo, jacobian_mode=capi.JAC_ANALYTIC, pcg_tolerance=args.pcg_tol, device=local_rank)
+            assert one.initialize_optimization(g)
+            n1, _ = one.optimize(iters)
+            chi_1 = one.active_chi2()
+            p_1, l_1 = one.estimates()
+            t_1 = one.timings()
+            one.close()
+            dth = p_n[:, 2] - p_1[:, 2]
+            dth -= 2 * np.pi * np.round(dth / (2 * np.pi))
+            parity = {"chi2_n": chi_n[0], "chi2_1": chi_1[0], "chi2_rel": abs(chi_n[0] - chi_1[0]) / max(abs(chi_1[0]), 1e-300),
+                      "max_pose_xy_delta": float(np.abs(p_n[:, :2] - p_1[:, :2]).max()),
+                      "max_pose_theta_delta": float(np.abs(dth).max()),
+                      "max_landmark_delta": float(np.abs(l_n - l_1).max()) if l_1.size else 0.0,
+                      "pcg_iterations": [int(t_n["pcg_iters"]), int(t_1["pcg_iters"])],
+                      "lm_trials": [int(t_n["trials"]), int(t_1["trials"])],
+                      "ok": bool(abs(chi_n[0] - chi_1[0]) <= 1e-6 * abs(chi_1[0]) and
+                                 np.abs(p_n[:, :2] - p_1[:, :2]).max() <= 1e-6 * max(1.0, float(np.abs(p_1[:, :2]).max())))}
+        barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -753,6 +785,8 @@ def main():
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if parity is not None:
+        line["parity_vs_n1"] = parity
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_reference_run(args.workload, 1, 0)
     print(json.dumps(line))

@@ -125,11 +125,12 @@ __device__ __forceinline__ void xreduce(const DevGraph& g, unsigned long long se
   }
   const Mailbox* me = g.mbox[g.rank];
   if (t < g.world) {
-    // relaxed polling (an acquire here would issue a system-scope fence per probe); everything read after the
-    // barrier is fetched with L1-bypassing loads (ld.cg / ld.relaxed.sys), so no stale line can be observed
+    // relaxed polling (an acquire per probe would issue a system-scope fence per probe), then ONE system-scope fence:
+    // the peer published with st.release.sys, so relaxed observation + fence.acq_rel.sys is the morally-strong
+    // acquire pattern of the PTX memory model -- everything the peer wrote before its release is visible afterwards
     while (ld_relaxed_sys_u64(&me->flag[slot][t]) < seq) {
     }
-    __threadfence();
+    __threadfence_system();
   }
   __syncthreads();
   double out[4];
@@ -396,7 +397,7 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
     if (threadIdx.x < g.world) {
       while (ld_relaxed_sys_u64(&me->flag[slot][threadIdx.x]) < seq) {
       }
-      __threadfence();
+      __threadfence_system();  // acquire side of the peer's st.release.sys (see xreduce)
     }
     __syncthreads();
     return;
@@ -411,7 +412,7 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
       } while ((lo & 0xffffffff00000000ull) != tag || (hi & 0xffffffff00000000ull) != tag);
       sm[threadIdx.x * 2 + k] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
     }
-    __threadfence();
+    __threadfence_system();  // the publisher fenced (system scope) before its flag-in-data stores: acquire side
   }
   __syncthreads();
   for (int k = 0; k < nv; ++k) {

@@ -18,8 +18,38 @@ def _ngpus():
         return 0
 
 
-def _worker(rank, world, port, q):
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _collect(procs, q, world, timeout=600):
+    """One result per rank; a worker that dies (non-zero exit code) fails the test at once instead of stalling q.get."""
+    import queue
+    import time
+    res, t0 = {}, time.time()
+    while len(res) < world:
+        try:
+            r, out = q.get(timeout=2)
+            res[r] = out
+        except queue.Empty:
+            dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+            if dead or time.time() - t0 > timeout:
+                for p in procs:
+                    if p.is_alive():
+                        p.kill()
+                raise AssertionError(f"multi-GPU workers failed: exit codes {[p.exitcode for p in procs]}")
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    return res
+
+
+def _worker(rank, world, port, q, ghosts):
     sys.path.insert(0, ROOT)
+    os.environ["SGB_GHOST_LANDMARKS"] = "1" if ghosts else "0"
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -57,8 +87,9 @@ def _worker(rank, world, port, q):
     q.put((rank, out))
 
 
+@pytest.mark.parametrize("ghosts", [0, 1])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_partitioned_matches_single_gpu(world):
+def test_partitioned_matches_single_gpu(world, ghosts):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -66,14 +97,11 @@ def test_partitioned_matches_single_gpu(world):
     from sparse_gslam_b200 import graphgen as gg
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29700 + os.getpid() % 200
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, ghosts)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=600) for _ in range(world))
-    for p in procs:
-        p.join(timeout=120)
-        assert p.exitcode == 0
+    res = _collect(procs, q, world)
     g = gg.make_c5(rows=40, cols=40)
     one = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
     one.initialize_optimization(g)
