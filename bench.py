@@ -399,6 +399,8 @@ def run_stream(args, warmup):
         one_pass(be)
     sampler = ClockSampler(0)
     sampler.start()
+    for k in be.prof:
+        be.prof[k] = 0
     tot, its, kfs, h2d, d2h = 0.0, 0, 0, 0, 0
     for _ in range(args.steps):
         dt, s = one_pass(be)
@@ -422,6 +424,11 @@ def run_stream(args, warmup):
                          "traffic": None, "peak_source": peak_src, "note": "per-call overhead dominated (small growing graph)"},
             "e2e": {"value": its / tot, "unit": "LM iterations/s", "h2d_bytes_per_step": h2d // max(1, args.steps),
                     "d2h_bytes_per_step": d2h // max(1, args.steps)}}
+    calls = max(1, be.prof["calls"])
+    line["per_keyframe"] = {k[:-2] + "_ms": 1e3 * v / calls for k, v in be.prof.items() if k.endswith("_s")}
+    line["per_keyframe"].update({"device_ms": be.prof["device_ms"] / calls, "pcg_iters": be.prof["pcg_iters"] / calls,
+                                 "lm_trials": be.prof["trials"] / calls, "kernel_launches": be.prof["kernel_launches"] / calls})
+    line["gpu_launches"] = int(be.prof["kernel_launches"])
     if not args.no_cpu_baseline:
         dt, s = one_pass(_OracleBackend())
         line["cpu_baseline"] = dict(value=sum(r.iterations for r in s.log) / dt, unit="LM iterations/s", cores=1, kind="port",

@@ -210,6 +210,18 @@ sgb_status sgb_linear_set_pattern(sgb_handle* h, const sgb_block_matrix* A);
 sgb_status sgb_linear_solve(sgb_handle* h, const double* values, const double* b, double* x, int32_t* pcg_iters,
                             double* rel_residual);
 
+/* g2o::OptimizationAlgorithm::computeMarginals(SparseBlockMatrix<MatrixX>& spinv, const std::vector<std::pair<int,int>>&
+ * blockIndices) -- pure virtual in libg2o 2020.5.29 (g2o/core/optimization_algorithm.h), reached by
+ * SparseOptimizer::computeMarginals; the reference's algorithms implement it through BlockSolver::computeMarginals ->
+ * LinearSolver::solvePattern. Block (block_row[k], block_col[k]) (Hessian indices of sgb_get_structure) of the INVERSE
+ * of the un-damped Hessian at the current estimates, k = 0..n_blocks-1; out_values receives the blocks one after the
+ * other in request order, each column-major (dim(row) x dim(col), dim = 3 for poses, 2 for landmarks). Computed
+ * column by column: H x = e_j solved on the device with the Schur + PCG path (lambda = 0), one solve per scalar
+ * column of every distinct block column requested. SGB_ERR_SOLVE_FAILED when H is not positive definite (g2o returns
+ * false). Single GPU. */
+sgb_status sgb_compute_marginals(sgb_handle* h, int32_t n_blocks, const int32_t* block_row, const int32_t* block_col,
+                                 double* out_values);
+
 /* SparseOptimizer::optimize(iters, online): returns through *iters_done what g2o returns
  * (iterations run; 0 on Fail; -1 if not initialised). stats may be NULL or hold max_iters entries.
  * Estimates stay resident on the device and are also copied back (sgb_get_estimates). */

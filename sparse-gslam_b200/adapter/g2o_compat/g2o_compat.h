@@ -5,7 +5,8 @@
 // instead and define SGB_USE_REAL_G2O: the adapter only uses the members declared below.
 //
 // Covered: HyperGraph::{Vertex,Edge,VertexSet,EdgeSet}, OptimizableGraph::{Vertex,Edge}, SE2, VertexSE2, EdgeSE2,
-// RobustKernelDCS, OptimizationAlgorithm (init / solve / updateStructure / computeMarginals), SparseOptimizer
+// RobustKernelDCS, OptimizationAlgorithm (init / solve / updateStructure / computeMarginals: the four pure virtuals,
+// exact signatures), SparseOptimizer
 // (addVertex, addEdge, initializeOptimization, updateInitialization, optimize, push, pop, discardTop,
 // computeActiveErrors, activeChi2, activeRobustChi2, setAlgorithm, algorithm, setVerbose,
 // setComputeBatchStatistics, activeVertices, activeEdges, indexMapping) and the two custom types of the reference
@@ -193,10 +194,27 @@ class SparseBlockMatrix {
   using SparseMatrixBlock = MatrixType;
   using IntBlockMap = std::map<int, SparseMatrixBlock*>;
   // rbi / cbi: cumulative END index of every block row / column (g2o convention)
-  SparseBlockMatrix(const int* rbi, const int* cbi, int rb, int cb) : _rowBlockIndices(rbi, rbi + rb), _colBlockIndices(cbi, cbi + cb), _blockCols(cb) {}
-  ~SparseBlockMatrix() { for (auto& col : _blockCols) for (auto& kv : col) delete kv.second; }
+  SparseBlockMatrix(const int* rbi, const int* cbi, int rb, int cb, bool hasStorage = true)
+      : _rowBlockIndices(rbi, rbi + rb), _colBlockIndices(cbi, cbi + cb), _blockCols(cb) { (void)hasStorage; }
+  SparseBlockMatrix() = default;
+  ~SparseBlockMatrix() { clearBlocks(); }
   SparseBlockMatrix(const SparseBlockMatrix&) = delete;
   SparseBlockMatrix& operator=(const SparseBlockMatrix&) = delete;
+  // g2o's solvers hand a freshly constructed matrix back by assignment (MarginalCovarianceCholesky::computeCovariance)
+  SparseBlockMatrix& operator=(SparseBlockMatrix&& o) noexcept {
+    if (this != &o) {
+      clearBlocks();
+      _rowBlockIndices = std::move(o._rowBlockIndices);
+      _colBlockIndices = std::move(o._colBlockIndices);
+      _blockCols = std::move(o._blockCols);
+      o._blockCols.clear();
+    }
+    return *this;
+  }
+  const SparseMatrixBlock* block(int r, int c) const {
+    auto it = _blockCols[c].find(r);
+    return it == _blockCols[c].end() ? nullptr : it->second;
+  }
   int rows() const { return _rowBlockIndices.empty() ? 0 : _rowBlockIndices.back(); }
   int cols() const { return _colBlockIndices.empty() ? 0 : _colBlockIndices.back(); }
   int rowsOfBlock(int r) const { return r ? _rowBlockIndices[r] - _rowBlockIndices[r - 1] : _rowBlockIndices[0]; }
@@ -215,6 +233,7 @@ class SparseBlockMatrix {
     return b;
   }
  private:
+  void clearBlocks() { for (auto& col : _blockCols) for (auto& kv : col) delete kv.second; _blockCols.clear(); }
   std::vector<int> _rowBlockIndices, _colBlockIndices;
   std::vector<IntBlockMap> _blockCols;
 };
@@ -233,8 +252,11 @@ class OptimizationAlgorithm {
   virtual ~OptimizationAlgorithm() = default;
   virtual bool init(bool online = false) = 0;
   virtual SolverResult solve(int iteration, bool online = false) = 0;
-  virtual bool computeMarginals(void* /*SparseBlockMatrix<MatrixX>&*/, const std::vector<std::pair<int, int>>&) { return false; }
+  // the four pure virtuals of libg2o 2020.5.29's g2o/core/optimization_algorithm.h, with their exact signatures: a
+  // plugin that misses one of them is abstract here exactly as it is against the real headers
+  virtual bool computeMarginals(SparseBlockMatrix<MatrixX>& spinv, const std::vector<std::pair<int, int>>& blockIndices) = 0;
   virtual bool updateStructure(const std::vector<HyperGraph::Vertex*>& vset, const HyperGraph::EdgeSet& edges) = 0;
+  virtual void printVerbose(std::ostream& os) const { (void)os; }
   void setOptimizer(SparseOptimizer* o) { _optimizer = o; }
   SparseOptimizer* optimizer() const { return _optimizer; }
  protected:
@@ -301,6 +323,15 @@ class SparseOptimizer : public OptimizableGraph {
     }
     if (result == OptimizationAlgorithm::Fail) return 0;
     return cj;
+  }
+  // SparseOptimizer::computeMarginals(spinv, blockIndices) / (spinv, vertex): forwarded to the algorithm, as in g2o
+  bool computeMarginals(SparseBlockMatrix<MatrixX>& spinv, const std::vector<std::pair<int, int>>& blockIndices) {
+    return _algorithm->computeMarginals(spinv, blockIndices);
+  }
+  bool computeMarginals(SparseBlockMatrix<MatrixX>& spinv, const OptimizableGraph::Vertex* v) {
+    if (v->hessianIndex() < 0) return false;
+    std::vector<std::pair<int, int>> idx(1, std::make_pair(v->hessianIndex(), v->hessianIndex()));
+    return computeMarginals(spinv, idx);
   }
   void push() { for (auto* v : _activeVertices) v->push(); }
   void pop() { for (auto* v : _activeVertices) v->pop(); }

@@ -80,6 +80,50 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
     return _h != nullptr;
   }
 
+  // Pure virtual in g2o::OptimizationAlgorithm (libg2o 2020.5.29, g2o/core/optimization_algorithm.h); the algorithms the
+  // reference installs (graphs.cpp:9-23) implement it as BlockSolver::computeMarginals -> LinearSolver::solvePattern.
+  // blockIndices holds (row, col) Hessian indices of the optimizer's index mapping; spinv is re-created with the
+  // optimizer's block layout and receives one dense block per request: the block of the inverse of the Hessian at the
+  // vertices' current estimates, each column solved for on the device (sgb_compute_marginals).
+  bool computeMarginals(SparseBlockMatrix<MatrixX>& spinv, const std::vector<std::pair<int, int>>& blockIndices) override {
+    if (!_h || !_optimizer) return false;
+    const auto& iv = _optimizer->indexMapping();
+    const int n = (int)iv.size();
+    if (n == 0) return false;
+    if (!_uploaded && !upload()) return false;   // computeMarginals before any optimize(): flatten the graph now
+    if (_hidx_of.empty() && !buildHessianIndexMap()) return false;
+    if (!sendEstimates()) return false;
+    std::vector<int> rbi(n);
+    int acc = 0;
+    for (int i = 0; i < n; ++i) { acc += iv[i]->dimension(); rbi[i] = acc; }
+    spinv = SparseBlockMatrix<MatrixX>(rbi.data(), rbi.data(), n, n, true);
+    std::vector<int32_t> br, bc;
+    for (const auto& rc : blockIndices) {
+      if (rc.first < 0 || rc.first >= n || rc.second < 0 || rc.second >= n) return false;
+      auto ir = _hidx_of.find(iv[rc.first]), ic = _hidx_of.find(iv[rc.second]);
+      if (ir == _hidx_of.end() || ic == _hidx_of.end()) return false;
+      br.push_back(ir->second);
+      bc.push_back(ic->second);
+    }
+    size_t total = 0;
+    for (const auto& rc : blockIndices) total += (size_t)iv[rc.first]->dimension() * iv[rc.second]->dimension();
+    std::vector<double> vals(total ? total : 1);
+    sgb_status st = sgb_compute_marginals(_h, (int32_t)br.size(), br.data(), bc.data(), vals.data());
+    if (st != SGB_OK) {
+      std::fprintf(stderr, "OptimizationAlgorithmB200::computeMarginals: %s\n", sgb_last_error(_h));
+      return false;
+    }
+    size_t o = 0;
+    for (const auto& rc : blockIndices) {
+      auto* blk = spinv.block(rc.first, rc.second, true);
+      const int nr = iv[rc.first]->dimension(), nc = iv[rc.second]->dimension();
+      for (int j = 0; j < nc; ++j)
+        for (int i = 0; i < nr; ++i) (*blk)(i, j) = vals[o + (size_t)j * nr + i];
+      o += (size_t)nr * nc;
+    }
+    return true;
+  }
+
   const sgb_iter_stat& lastIteration() const { return _last; }
   sgb_handle* handle() const { return _h; }
 
@@ -145,7 +189,18 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
     g.pl_seq = pl_seq.data();
     sgb_status st = sgb_set_graph(_h, &g);
     if (st != SGB_OK) { std::fprintf(stderr, "OptimizationAlgorithmB200::init: %s\n", sgb_last_error(_h)); return false; }
+    _hidx_of.clear();  // rebuilt on demand by computeMarginals
+    _uploaded = true;
     _fresh = true;
+    return true;
+  }
+  // vertex -> Hessian index of the backend's structure (what sgb_compute_marginals addresses blocks by)
+  bool buildHessianIndexMap() {
+    std::vector<int32_t> ph(_poses.size()), lh(_lms.size());
+    if (sgb_get_structure(_h, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, ph.data(), lh.data()) != SGB_OK) return false;
+    _hidx_of.clear();
+    for (size_t i = 0; i < _poses.size(); ++i) if (ph[i] >= 0) _hidx_of[_poses[i]] = ph[i];
+    for (size_t i = 0; i < _lms.size(); ++i) if (lh[i] >= 0) _hidx_of[_lms[i]] = lh[i];
     return true;
   }
   void gatherEstimates() {
@@ -165,9 +220,10 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
 
   int _algo;
   sgb_handle* _h = nullptr;
-  bool _fresh = false;
+  bool _fresh = false, _uploaded = false;
   std::vector<OptimizableGraph::Vertex*> _poses, _lms;
   std::vector<double> _pose_est, _lm_est;
+  std::unordered_map<const HyperGraph::Vertex*, int32_t> _hidx_of;
   sgb_iter_stat _last{};
 };
 

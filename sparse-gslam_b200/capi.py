@@ -144,6 +144,7 @@ def load() -> C.CDLL:
     L.sgb_g2o_save.argtypes = [C.c_char_p, C.POINTER(GraphSoA)]
     L.sgb_linear_set_pattern.argtypes = [vp, C.POINTER(BlockMatrix)]
     L.sgb_linear_solve.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
+    L.sgb_compute_marginals.argtypes = [vp, C.c_int32, vp, vp, vp]
     L.sgb_set_graph_device.argtypes = [vp, C.POINTER(GraphSoA), C.POINTER(DeviceValues)]
     L.sgb_pg_create.argtypes = [C.c_int32, C.POINTER(vp)]
     L.sgb_pg_destroy.argtypes = [vp]

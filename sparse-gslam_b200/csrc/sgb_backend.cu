@@ -946,7 +946,8 @@ sgb_status sgb_get_structure(const sgb_handle* h, int32_t* kind, int32_t* index,
                              int32_t* bc, int32_t* bnr, int32_t* bnc, int32_t* ph, int32_t* lh) {
   if (!h) return SGB_ERR_INVALID;
   if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
-  build_block_list(const_cast<sgb_handle*>(h)->S);  // built on first use; the handle is not shared between threads
+  if (kind || index || offset || br || bc || bnr || bnc)  // the per-vertex Hessian indices alone need no block list
+    build_block_list(const_cast<sgb_handle*>(h)->S);  // built on first use; the handle is not shared between threads
   const Structure& S = h->S;
   auto cp = [](int32_t* dst, const std::vector<int32_t>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(int32_t)); };
   cp(kind, S.ord_kind); cp(index, S.ord_index); cp(offset, S.ord_offset);
@@ -1167,6 +1168,81 @@ sgb_status sgb_linear_solve(sgb_handle* h, const double* values, const double* b
     return SGB_ERR_SOLVE_FAILED;
   }
   return SGB_OK;
+}
+
+sgb_status sgb_compute_marginals(sgb_handle* h, int32_t n_blocks, const int32_t* block_row, const int32_t* block_col,
+                                 double* out_values) {
+  sgb_status st = need_graph(h);
+  if (st != SGB_OK) return st;
+  if (n_blocks < 0 || (n_blocks > 0 && (!block_row || !block_col || !out_values))) return SGB_ERR_INVALID;
+  if (h->LP.world != 1) { h->err = "marginals: single GPU only"; return SGB_ERR_UNSUPPORTED; }
+  SGB_CUDA(cudaSetDevice(h->device));
+  const Structure& S = h->S;
+  const int nf = S.Pf + S.Lf;
+  auto bdim = [&](int i) { return i < S.Pf ? 3 : 2; };
+  auto boff = [&](int i) { return i < S.Pf ? 3 * i : 3 * S.Pf + 2 * (i - S.Pf); };
+  std::vector<size_t> out_off(n_blocks);
+  size_t total = 0;
+  for (int k = 0; k < n_blocks; ++k) {
+    if (block_row[k] < 0 || block_row[k] >= nf || block_col[k] < 0 || block_col[k] >= nf) {
+      h->err = "marginals: block index out of range";
+      return SGB_ERR_INVALID;
+    }
+    out_off[k] = total;
+    total += (size_t)bdim(block_row[k]) * bdim(block_col[k]);
+  }
+  if (n_blocks == 0) return SGB_OK;
+  // requests grouped by block column: every scalar column of H^-1 is solved for once
+  std::vector<int32_t> order(n_blocks);
+  for (int k = 0; k < n_blocks; ++k) order[k] = k;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return block_col[a] < block_col[b]; });
+  if ((st = launch_linearize(h)) != SGB_OK) return st;   // H at the current estimates (b_p / b_l are overwritten below)
+  if ((st = launch_finalize_lin(h, 0)) != SGB_OK) return st;
+  double* d_rhs = nullptr;
+  int32_t* d_lmg = nullptr;
+  SGB_CUDA(cudaMalloc((void**)&d_rhs, std::max<size_t>(S.dim, 1) * sizeof(double)));
+  cudaError_t ce = cudaMalloc((void**)&d_lmg, std::max<size_t>(h->LP.lm_global.size(), 1) * sizeof(int32_t));
+  if (ce != cudaSuccess) { cudaFree(d_rhs); h->err = cudaGetErrorString(ce); return SGB_ERR_CUDA; }
+  auto cleanup = [&]() { cudaFree(d_rhs); cudaFree(d_lmg); };
+  if (!h->LP.lm_global.empty())
+    cudaMemcpyAsync(d_lmg, h->LP.lm_global.data(), h->LP.lm_global.size() * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+  std::vector<double> x(S.dim);
+  st = SGB_OK;
+  for (size_t q = 0; q < order.size() && st == SGB_OK;) {
+    const int c = block_col[order[q]];
+    size_t q_end = q;
+    while (q_end < order.size() && block_col[order[q_end]] == c) ++q_end;
+    for (int d = 0; d < bdim(c) && st == SGB_OK; ++d) {
+      const double one = 1.0;
+      cudaMemsetAsync(d_rhs, 0, (size_t)S.dim * sizeof(double), h->stream);
+      cudaMemcpyAsync(d_rhs + boff(c) + d, &one, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+      k_scatter_rhs<<<grid_for(S.dim), kThreads, 0, h->stream>>>(h->G, d_rhs, d_lmg);
+      h->tm.kernel_launches++;
+      if ((st = launch_setup(h, 0.0, 1)) != SGB_OK) break;
+      if ((st = launch_pcg(h, 0.0, 1)) != SGB_OK) break;
+      if (h->G.nL > 0) {
+        k_backsub<<<grid_for(32 * h->G.Hlp.nslices), kThreads, 0, h->stream>>>(h->G);
+        h->tm.kernel_launches++;
+      }
+      k_gn_control<<<1, 32, 0, h->stream>>>(h->G, h->d_sc);
+      h->tm.kernel_launches++;
+      if ((st = read_scalars(h)) != SGB_OK) break;
+      if (h->h_sc->result != 1) {
+        h->err = "marginals: Hessian not positive definite";
+        st = SGB_ERR_SOLVE_FAILED;
+        break;
+      }
+      if ((st = gather_owned_vector(h, h->G.x_p[0], h->G.x_l, x.data())) != SGB_OK) break;
+      for (size_t t = q; t < q_end; ++t) {
+        const int k = order[t], r = block_row[k], nr = bdim(r);
+        for (int i = 0; i < nr; ++i) out_values[out_off[k] + (size_t)d * nr + i] = x[boff(r) + i];
+      }
+    }
+    q = q_end;
+  }
+  cudaStreamSynchronize(h->stream);
+  cleanup();
+  return st;
 }
 
 sgb_status sgb_optimize(sgb_handle* h, int32_t algo, int32_t max_iters, int32_t online, int32_t* iters_done,

@@ -95,6 +95,12 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
 __device__ __forceinline__ void st_relaxed_sys_f64(double* p, double v) {
   asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
+// One-directional system-scope fences (PTX ISA 8.6+). Acquire side of a relaxed poll that observed a peer's release:
+// SASS = CCTL.IVALL only (invalidate L1), no MEMBAR -- against MEMBAR.SC.SYS for __threadfence_system(), which cost
+// ~3 us per cross-GPU barrier when it was tried here (2 GPUs, C5: 130 -> 159 us per PCG iteration). Release side:
+// MEMBAR.ALL.SYS (everything this thread observed or wrote is performed system-wide before the stores that follow).
+__device__ __forceinline__ void fence_acquire_sys() { asm volatile("fence.acquire.sys;" ::: "memory"); }
+__device__ __forceinline__ void fence_release_sys() { asm volatile("fence.release.sys;" ::: "memory"); }
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -120,17 +126,16 @@ __device__ __forceinline__ void xreduce(const DevGraph& g, unsigned long long se
   if (pusher && t < g.world) {
     Mailbox* mb = g.mbox[t];
     for (int k = 0; k < nv; ++k) st_relaxed_sys_f64(&mb->val[slot][g.rank][k], vals[k]);
-    __threadfence_system();
-    st_release_sys_u64(&mb->flag[slot][g.rank], seq);
+    st_release_sys_u64(&mb->flag[slot][g.rank], seq);  // release: orders the value stores above (same thread) before the flag
   }
   const Mailbox* me = g.mbox[g.rank];
   if (t < g.world) {
-    // relaxed polling (an acquire per probe would issue a system-scope fence per probe), then ONE system-scope fence:
-    // the peer published with st.release.sys, so relaxed observation + fence.acq_rel.sys is the morally-strong
-    // acquire pattern of the PTX memory model -- everything the peer wrote before its release is visible afterwards
+    // relaxed polling, then ONE system-scope acquire fence: the peer published with st.release.sys, so relaxed
+    // observation + fence.acquire.sys is the morally-strong acquire pattern of the PTX memory model -- everything the
+    // peer wrote before its release is visible afterwards
     while (ld_relaxed_sys_u64(&me->flag[slot][t]) < seq) {
     }
-    __threadfence_system();
+    fence_acquire_sys();
   }
   __syncthreads();
   double out[4];
@@ -339,9 +344,14 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
     __syncthreads();     // the values are already block-wide sums
     return;
   }
-  ++seq;
   epoch += nb;
-  const int slot = (int)(seq & 1ull);
+  // A barrier that only spans this GPU must not consume a cross-rank sequence number: the mailbox slots alternate with
+  // the parity of seq, and "a rank is at most one cross-rank barrier ahead" only holds if consecutive CROSS-RANK
+  // barriers take consecutive numbers (with the local barrier counted, phases C(k) and B(k+1) shared a slot and a fast
+  // rank overwrote values a slow rank was still waiting for: the 2-GPU C5 run with ghost landmarks hung). Its own
+  // partial-sum slot alternates with the number of barriers this CTA has passed.
+  if (!(g.world == 1 || local_only)) ++seq;
+  const int slot = (g.world == 1 || local_only) ? (int)((epoch / nb) & 1ull) : (int)(seq & 1ull);
   if (g.world == 1 || local_only) {
     // One GPU (or a barrier that only has to span this GPU: with ghost landmarks nobody reads another rank's t):
     // flat barrier, gpu scope only. Every CTA deposits its partial (double-buffered by the parity of seq:
@@ -382,8 +392,8 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
                                                             // this GPU wrote in the phase
       } else {
         // everything this GPU wrote in the phase went to its OWN memory (peers read it through NVLink): one system
-        // fence orders it, then the values travel with their own flags -- no second fence behind a remote store
-        __threadfence_system();
+        // release fence orders it, then the values travel with their own flags -- no second fence behind a remote store
+        fence_release_sys();
         for (int k = 0; k < nv; ++k) {
           unsigned long long bits = (unsigned long long)__double_as_longlong(loc[k]);
           st_relaxed_sys_u64(&mb->ll[slot][g.rank][k][0], (bits & 0xffffffffull) | tag);
@@ -397,7 +407,7 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
     if (threadIdx.x < g.world) {
       while (ld_relaxed_sys_u64(&me->flag[slot][threadIdx.x]) < seq) {
       }
-      __threadfence_system();  // acquire side of the peer's st.release.sys (see xreduce)
+      fence_acquire_sys();  // acquire side of the peer's st.release.sys (see xreduce)
     }
     __syncthreads();
     return;
@@ -412,7 +422,7 @@ __device__ __forceinline__ void grid_xreduce(const DevGraph& g, unsigned long lo
       } while ((lo & 0xffffffff00000000ull) != tag || (hi & 0xffffffff00000000ull) != tag);
       sm[threadIdx.x * 2 + k] = __longlong_as_double((long long)((lo & 0xffffffffull) | (hi << 32)));
     }
-    __threadfence_system();  // the publisher fenced (system scope) before its flag-in-data stores: acquire side
+    fence_acquire_sys();  // the publisher fenced (release, system scope) before its flag-in-data stores: acquire side
   }
   __syncthreads();
   for (int k = 0; k < nv; ++k) {

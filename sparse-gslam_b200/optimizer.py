@@ -185,6 +185,25 @@ class SparseOptimizerB200:
             self._check(rc)
         return rc == capi.OK, x, it.value, rel.value
 
+    def compute_marginals(self, block_pairs):
+        """g2o::SparseOptimizer::computeMarginals: blocks (row, col) -- Hessian indices -- of the inverse Hessian at the
+        current estimates. Returns (ok, list of numpy blocks); ok == False where g2o returns false (H not SPD)."""
+        st = self.structure()
+        nfp = st["n_free_poses"]
+        rows = np.ascontiguousarray([p[0] for p in block_pairs], np.int32)
+        cols = np.ascontiguousarray([p[1] for p in block_pairs], np.int32)
+        dims = [(3 if r < nfp else 2, 3 if c < nfp else 2) for r, c in zip(rows, cols)]
+        out = np.zeros(max(1, sum(a * b for a, b in dims)))
+        rc = self.L.sgb_compute_marginals(self.h, len(rows), _p(rows), _p(cols), _p(out))
+        if rc == capi.ERR_SOLVE_FAILED:
+            return False, []
+        self._check(rc)
+        blocks, o = [], 0
+        for a, b in dims:
+            blocks.append(out[o:o + a * b].reshape(b, a).T.copy())  # column-major
+            o += a * b
+        return True, blocks
+
     def optimize(self, iters, online=False, resident=False):
         """Returns (g2o return value, per-iteration stats)."""
         stats = (capi.IterStat * max(1, iters))()

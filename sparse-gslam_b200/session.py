@@ -74,32 +74,47 @@ def stream_from_graph(g: gg.Graph, corrupt_at: dict[int, int] | None = None) -> 
 
 
 class GpuBackend:
-    """The product path: one sgb handle, estimates resident on the device between the calls of one key-frame."""
+    """The product path: one sgb handle, estimates resident on the device between the calls of one key-frame.
+    `prof` accumulates the wall time of every protocol call and the device-side counters of optimize()."""
 
     def __init__(self, jacobian_mode=capi.JAC_G2O_NUMERIC, device=-1):
         from .optimizer import SparseOptimizerB200
         self.opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=jacobian_mode, device=device)
+        self.prof = dict(initialize_s=0.0, push_s=0.0, optimize_s=0.0, chi2_s=0.0, pop_discard_s=0.0, estimates_s=0.0,
+                         device_ms=0.0, pcg_iters=0, trials=0, kernel_launches=0, calls=0)
 
-    def initialize(self, g) -> bool:
-        return self.opt.initialize_optimization(g)
+    def _timed(self, key, f, *a, **k):
+        t0 = time.perf_counter()
+        r = f(*a, **k)
+        self.prof[key] += time.perf_counter() - t0
+        return r
+
+    def initialize(self, g, online=False, n_new_poses=0, n_new_landmarks=0, n_new_pp=0, n_new_pl=0) -> bool:
+        return self._timed("initialize_s", self.opt.initialize_optimization, g)
 
     def push(self):
-        self.opt.push()
+        self._timed("push_s", self.opt.push)
 
     def pop(self):
-        self.opt.pop()
+        self._timed("pop_discard_s", self.opt.pop)
 
     def discard_top(self):
-        self.opt.discard_top()
+        self._timed("pop_discard_s", self.opt.discard_top)
 
     def optimize(self, iters, online):
-        return self.opt.optimize(iters, online=online)[0]
+        n = self._timed("optimize_s", self.opt.optimize, iters, online=online)[0]
+        t = self.opt.timings()
+        self.prof["device_ms"] += t["total_ms"]
+        for k in ("pcg_iters", "trials", "kernel_launches"):
+            self.prof[k] += t[k]
+        self.prof["calls"] += 1
+        return n
 
     def active_chi2(self):
-        return self.opt.active_chi2()[0]
+        return self._timed("chi2_s", self.opt.active_chi2)[0]
 
     def estimates(self):
-        return self.opt.estimates()
+        return self._timed("estimates_s", self.opt.estimates)
 
 
 @dataclass

@@ -37,10 +37,47 @@ def converged_prefix(stats):
     return n
 
 
-@pytest.mark.parametrize("name", ["small", "c4", "c1"])
+def make_config(name):
+    """BASELINE configs by name; "c5s" = a 60x60-cell slice of the C5 grid world (the oracle finishes it in seconds)."""
+    return gg.make_c5(rows=60, cols=60) if name == "c5s" else gg.make(name)
+
+
+_BAND = {}
+
+
+def numeric_band(name, g, iters):
+    """Reproducibility band of the REFERENCE ALGORITHM under g2o's numeric Jacobians (delta = 1e-9), measured here and now:
+    the oracle is run from the initial estimates and from the initial estimates perturbed by ~1 ulp (relative
+    1e-15 * N(0,1)); the largest difference of the two final states is what last-bit input noise does to the reference's
+    own result (central differences turn 1e-16 into ~1e-7 Jacobian noise, chaotically in the input bits, and LM carries
+    it to the fixed point). tests/experiments/numeric_spread.py: C1 2.2e-6 / 1.7e-7 (poses / landmarks), C2 2.1e-6 /
+    5.2e-6, against 1e-15 / 1e-13 with analytic Jacobians. No realisation of the algorithm -- g2o built by another
+    compiler included -- can be asked to agree with another one more closely than this band."""
+    key = (name, iters)
+    if key not in _BAND:
+        def run(p0, l0):
+            o = Oracle(g)
+            o.initialize_optimization()
+            o.set_estimates(p0, l0)
+            o.optimize(iters, ALGO_LM, JAC_G2O_NUMERIC)
+            return o.estimates() + (o.chi2()[0],)
+        pa, la, ca = run(g.pose_est, g.lm_est)
+        bp = bl = bc = 0.0
+        for seed in range(2):
+            rng = np.random.default_rng(seed)
+            p0 = g.pose_est * (1.0 + 1e-15 * rng.normal(size=g.pose_est.shape))
+            p0[g.pose_fixed != 0] = g.pose_est[g.pose_fixed != 0]
+            l0 = g.lm_est * (1.0 + 1e-15 * rng.normal(size=g.lm_est.shape))
+            pb, lb, cb = run(p0, l0)
+            bp, bl, bc = max(bp, pose_err(pb, pa)), max(bl, rel_err(lb, la)), max(bc, abs(cb - ca) / ca)
+        _BAND[key] = (bp, bl, bc)
+    return _BAND[key]
+
+
+@pytest.mark.parametrize("name", ["small", "c4", "c1", "c2", "c3", "c5s"])
 @pytest.mark.parametrize("jac", [capi.JAC_G2O_NUMERIC, capi.JAC_ANALYTIC])
 def test_structure_linearize_chi2(name, jac):
-    g = gg.make(name)
+    g = make_config(name)
     o = Oracle(g)
     assert o.initialize_optimization()
     opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=jac)
@@ -76,12 +113,35 @@ def test_damped_solve_matches_exact_cholesky(name):
         assert rel_err(xg, xo) < 1e-8
 
 
+@pytest.mark.parametrize("name,bound", [("c1", 3.5e-10), ("c2", 3.5e-9), ("c3", 3.5e-10), ("c5s", 1e-9)])
+def test_default_tolerance_step_error_vs_exact_ldlt(name, bound):
+    """with the DEFAULT PCG tolerance (1e-10) the damped step differs from the exact sparse LDLt
+    step (what LinearSolverEigen computes) by <= 3.5e-9 relative on the ill-conditioned corridor graph C2 and
+    <= 3.5e-10 on the other configs -- at a late-LM lambda (the small-lambda solves are the hard ones) and at lambda_0."""
+    g = make_config(name)
+    o = Oracle(g)
+    o.initialize_optimization()
+    opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)  # default tolerance
+    opt.initialize_optimization(g)
+    lam0 = 1e-5 * np.abs(o.linearize(JAC_ANALYTIC)["H"]).max()
+    for lam in (lam0, lam0 * 3.0 ** -10):
+        ok, xo = o.solve_once(lam, JAC_ANALYTIC)
+        okg, xg, iters, rel = opt.solve_once(lam)
+        assert ok and okg and iters > 0 and rel <= 1e-10
+        err = float(np.abs(xg - xo).max()) / float(np.abs(xo).max())
+        assert err < bound, (name, lam, iters, err)
+
+
 @pytest.mark.parametrize("name,jac", [("small", capi.JAC_ANALYTIC), ("small", capi.JAC_G2O_NUMERIC),
                                       ("c4", capi.JAC_G2O_NUMERIC), ("c1", capi.JAC_G2O_NUMERIC),
-                                      ("c1", capi.JAC_ANALYTIC), ("c3", capi.JAC_ANALYTIC)])
+                                      ("c1", capi.JAC_ANALYTIC), ("c2", capi.JAC_ANALYTIC), ("c2", capi.JAC_G2O_NUMERIC),
+                                      ("c3", capi.JAC_ANALYTIC), ("c3", capi.JAC_G2O_NUMERIC),
+                                      ("c5s", capi.JAC_ANALYTIC), ("c5s", capi.JAC_G2O_NUMERIC)])
 def test_lm15_final_state_parity(name, jac):
-    """optimize(15) as drone.cpp:150 does: final poses, landmarks and chi2 within 1e-6 relative of the oracle."""
-    g = gg.make(name)
+    """optimize(15) as drone.cpp:150 does, on every BASELINE config in both Jacobian modes: final poses, landmarks and
+    chi2 within 1e-6 relative of the oracle (north_star); in g2o-numeric mode within the reference algorithm's own
+    reproducibility band when that is wider (numeric_band: measured in this test, never assumed)."""
+    g = make_config(name)
     o = Oracle(g)
     o.initialize_optimization()
     n_o, s_o = o.optimize(15, ALGO_LM, JAC[jac])
@@ -102,13 +162,15 @@ def test_lm15_final_state_parity(name, jac):
             np.testing.assert_allclose(b["lambda_"], a["lambda_"], rtol=1e-4)
     po, lo = o.estimates()
     pg, lg = opt.estimates()
-    # analytic mode: 1e-6 relative (north_star). g2o-numeric mode: the reference's own central differences make its
-    # result reproducible only to a few 1e-6 (two CPU restatements of it differ by 1.9e-6 mid-trajectory, see
-    # tests/test_oracle.py::test_lm_trace_cpp_equals_numpy), so the bound there is 5e-6.
-    tol = 5e-6 if jac == capi.JAC_G2O_NUMERIC else 1e-6
-    assert pose_err(pg, po) < tol
-    assert rel_err(lg, lo) < tol
-    np.testing.assert_allclose(opt.active_chi2()[0], o.chi2()[0], rtol=1e-6)
+    # analytic mode: 1e-6 relative (north_star), no exceptions. g2o-numeric mode: 1e-6, or 3x the band inside which the
+    # oracle itself reproduces its result when its input moves by one ulp (numeric_band) where that is wider.
+    tol_p = tol_l = tol_c = 1e-6
+    if jac == capi.JAC_G2O_NUMERIC:
+        bp, bl, bc = numeric_band(name, g, 15)
+        tol_p, tol_l, tol_c = max(1e-6, 3 * bp), max(1e-6, 3 * bl), max(1e-6, 3 * bc)
+    assert pose_err(pg, po) < tol_p, (pose_err(pg, po), tol_p)
+    assert rel_err(lg, lo) < tol_l, (rel_err(lg, lo), tol_l)
+    np.testing.assert_allclose(opt.active_chi2()[0], o.chi2()[0], rtol=tol_c)
     # caller protocol: pop() restores the pre-optimisation estimates (drone.cpp:180)
     opt.pop()
     pg, lg = opt.estimates()
@@ -116,10 +178,13 @@ def test_lm15_final_state_parity(name, jac):
     np.testing.assert_array_equal(lg, g.lm_est)
 
 
-@pytest.mark.parametrize("name", ["small", "c1"])
+@pytest.mark.parametrize("name", ["small", "c1", "c2", "c3"])
 def test_gn20_dcs_pose_graph_parity(name):
-    """optimize(20) with DCS closures as submap_loop_closer.cpp:287 does."""
+    """optimize(20) with DCS closures as submap_loop_closer.cpp:287 does; C2 carries the reference's own
+    phi = 0.75 (datasets/mit-killian/slam.yaml:38)."""
     g = gg.make(name)
+    if name == "c2":
+        assert g.meta["dcs_phi"] == 0.75
     gp = g.pose_only(phi=g.meta.get("dcs_phi", 1.0))
     o = Oracle(gp)
     o.initialize_optimization()
