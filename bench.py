@@ -637,13 +637,23 @@ def main():
     t0 = time.perf_counter()
     assert init_graph()
     t_setgraph = time.perf_counter() - t0
-    st = opt.structure()
-    # distinct off-diagonal pairs from the block list
-    kinds = st["kind"]
-    nP = st["n_free_poses"]
-    offd = st["row"] != st["col"]
-    st["n_pairs_pp"] = int(np.sum(offd & (st["col"] < nP)))
-    st["n_pairs_pl"] = int(np.sum(offd & (st["col"] >= nP)))
+    if world == 1:
+        st = opt.structure()
+        # distinct off-diagonal pairs from the block list
+        nP = st["n_free_poses"]
+        offd = st["row"] != st["col"]
+        st["n_pairs_pp"] = int(np.sum(offd & (st["col"] < nP)))
+        st["n_pairs_pl"] = int(np.sum(offd & (st["col"] >= nP)))
+    else:
+        # every rank only holds its own share of the structure (rank-filtered symbolic phase): count the distinct free
+        # vertex pairs of the WHOLE graph from the edge lists, the same quantities the one-GPU block list gives
+        pf, lf = g.pose_fixed == 0, g.lm_fixed == 0
+        a, b = np.minimum(g.pp_i, g.pp_j).astype(np.int64), np.maximum(g.pp_i, g.pp_j).astype(np.int64)
+        m = pf[g.pp_i] & pf[g.pp_j]
+        mpl = pf[g.pl_pose] & lf[g.pl_lm]
+        st = {"n_free_poses": int(pf.sum()), "n_free_landmarks": int(lf.sum()),
+              "n_pairs_pp": int(np.unique(a[m] * g.P + b[m]).size),
+              "n_pairs_pl": int(np.unique(g.pl_pose[mpl].astype(np.int64) * g.L + g.pl_lm[mpl]).size)}
 
     def barrier():
         if world > 1:

@@ -1,10 +1,15 @@
 // example_graphs.cpp -- what the reference's src/sparse_gslam/src/graphs.cpp + the optimiser calls of
 // drone.cpp:146-165 look like on the B200 backend. Builds a small landmark graph through the g2o-style API, runs
-// initializeOptimization(); push(); optimize(15); computeActiveErrors(); activeChi2(), and prints the result.
+// initializeOptimization(); push(); optimize(15); computeActiveErrors(); activeChi2(); computeMarginals, then the pose
+// graph of submap_loop_closer.cpp:204-288 through setup_pose_opt + optimize(20) with DCS closures, and prints the results.
+// With a file prefix as argument it also dumps both graphs (g2o text) and the final estimates: tests/test_adapter.py
+// feeds the dumped graphs to the CPU oracle and compares.
 // Compile:  g++ -std=c++17 example_graphs.cpp -I../../include -L.. -lsgb -Wl,-rpath,'$ORIGIN/..' -o example_graphs
 #include <cstdio>
 #include <deque>
 #include <random>
+#include <string>
+#include <vector>
 
 #include "sgb_g2o_adapter.h"
 
@@ -58,7 +63,32 @@ static int linear_solver_example() {
   return worst < 1e-8 ? 0 : 4;
 }
 
-int main() {
+// ---- dumps: the graph as g2o text (the wire format of sgb_g2o_load, line order = insertion order) and the estimates, so that
+// the parity test can hand the very same graph to the CPU oracle and compare final states (tests/test_adapter.py)
+static void dump_vertices(std::FILE* f, std::deque<g2o::VertexSE2>& poses, std::deque<g2o::VertexRhoTheta>& lms) {
+  for (auto& v : poses) std::fprintf(f, "VERTEX_SE2 %d %.17g %.17g %.17g\n", v.id(), v.estimate()[0], v.estimate()[1], v.estimate()[2]);
+  for (auto& v : lms) std::fprintf(f, "VERTEX_RHOTHETA %d %.17g %.17g\n", v.id(), v.estimate()[0], v.estimate()[1]);
+  for (auto& v : poses) if (v.fixed()) std::fprintf(f, "FIX %d\n", v.id());
+}
+static void dump_pp(std::FILE* f, g2o::EdgeSE2& e) {
+  const auto& I = e.information();
+  std::fprintf(f, "EDGE_SE2 %d %d %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g %.17g\n", e.vertex(0)->id(), e.vertex(1)->id(),
+               e.measurement()[0], e.measurement()[1], e.measurement()[2], I(0, 0), I(0, 1), I(0, 2), I(1, 1), I(1, 2), I(2, 2));
+}
+static void dump_pl(std::FILE* f, g2o::EdgeSE2RhoTheta& e) {
+  const auto& I = e.information();
+  std::fprintf(f, "EDGE_SE2_RHOTHETA %d %d %.17g %.17g %.17g %.17g %.17g\n", e.vertex(0)->id(), e.vertex(1)->id(),
+               e.measurement()[0], e.measurement()[1], I(0, 0), I(0, 1), I(1, 1));
+}
+static void dump_estimates(std::FILE* f, const char* tag, std::deque<g2o::VertexSE2>& poses, std::deque<g2o::VertexRhoTheta>& lms) {
+  for (auto& v : poses) std::fprintf(f, "%s POSE %d %.17g %.17g %.17g\n", tag, v.id(), v.estimate()[0], v.estimate()[1], v.estimate()[2]);
+  for (auto& v : lms) std::fprintf(f, "%s LINE %d %.17g %.17g\n", tag, v.id(), v.estimate()[0], v.estimate()[1]);
+}
+
+// usage: example_graphs [dump-prefix]   (with a prefix: <prefix>_lm.g2o, <prefix>_pose.g2o, <prefix>_result.txt are written)
+int main(int argc, char** argv) {
+  const std::string prefix = argc > 1 ? argv[1] : "";
+  std::FILE* res = prefix.empty() ? nullptr : std::fopen((prefix + "_result.txt").c_str(), "w");
   g2o::SparseOptimizer opt;
   setup_lm_opt(opt);
   std::deque<g2o::VertexSE2> poses;
@@ -77,6 +107,7 @@ int main() {
     lms.back().setEstimate(e);
     opt.addVertex(&lms.back());
   }
+  std::vector<std::pair<int, int>> edge_log;  // insertion order: (type, index)
   for (int k = 0; k < P; ++k) {
     poses.emplace_back();
     poses.back().setId(k);
@@ -90,6 +121,7 @@ int main() {
       odom.back().setMeasurement(g2o::SE2(0.5 + 0.02 * n01(rng), 0.02 * n01(rng), 0.01 * n01(rng)));
       odom.back().information()(0, 0) = 2500; odom.back().information()(1, 1) = 2500; odom.back().information()(2, 2) = 10000;
       opt.addEdge(&odom.back());
+      edge_log.emplace_back(0, (int)odom.size() - 1);
     }
     for (int l = 0; l < 2; ++l) {
       obs.emplace_back();
@@ -101,7 +133,15 @@ int main() {
       obs.back().setMeasurement(z);
       obs.back().information()(0, 0) = 1111; obs.back().information()(1, 1) = 2500;
       opt.addEdge(&obs.back());
+      edge_log.emplace_back(1, (int)obs.size() - 1);
     }
+  }
+  if (!prefix.empty()) {
+    std::FILE* f = std::fopen((prefix + "_lm.g2o").c_str(), "w");
+    if (!f) return 10;
+    dump_vertices(f, poses, lms);
+    for (auto& tk : edge_log) tk.first == 0 ? dump_pp(f, odom[tk.second]) : dump_pl(f, obs[tk.second]);
+    std::fclose(f);
   }
   // ---- drone.cpp:146-165
   if (!opt.initializeOptimization()) return 1;
@@ -111,8 +151,97 @@ int main() {
   double chi2_after = opt.activeChi2();
   std::printf("optimize returned %d, chi2 = %.6f, last pose = (%.4f, %.4f, %.4f)\n", n, chi2_after, poses.back().estimate()[0],
               poses.back().estimate()[1], poses.back().estimate()[2]);
+  if (res) {
+    std::fprintf(res, "LM ITERATIONS %d\nLM CHI2 %.17g\n", n, chi2_after);
+    dump_estimates(res, "LM", poses, lms);
+  }
+  // ---- SparseOptimizer::computeMarginals -> OptimizationAlgorithm::computeMarginals (pure virtual in g2o): marginal
+  // covariance blocks of the last pose, of the first landmark and their cross block
+  {
+    g2o::SparseBlockMatrix<g2o::MatrixX> spinv;
+    const int hp = poses.back().hessianIndex(), hl = lms.front().hessianIndex();
+    std::vector<std::pair<int, int>> want = {{hp, hp}, {hl, hl}, {hp, hl}};
+    if (!opt.computeMarginals(spinv, want)) return 5;
+    const g2o::MatrixX* bp = spinv.block(hp, hp);
+    const g2o::MatrixX* bl = spinv.block(hl, hl);
+    const g2o::MatrixX* bx = spinv.block(hp, hl);
+    if (!bp || !bl || !bx || bp->rows() != 3 || bl->rows() != 2 || bx->rows() != 3 || bx->cols() != 2) return 6;
+    std::printf("marginals: var(x, y, theta) of the last pose = (%.3e, %.3e, %.3e), var(rho, alpha) of wall 0 = (%.3e, %.3e)\n",
+                (*bp)(0, 0), (*bp)(1, 1), (*bp)(2, 2), (*bl)(0, 0), (*bl)(1, 1));
+    if (!((*bp)(0, 0) > 0 && (*bp)(1, 1) > 0 && (*bp)(2, 2) > 0 && (*bl)(0, 0) > 0 && (*bl)(1, 1) > 0)) return 7;
+    if (std::fabs((*bp)(0, 1) - (*bp)(1, 0)) > 1e-9 * ((*bp)(0, 0) + (*bp)(1, 1))) return 8;  // symmetric
+    if (res) {
+      std::fprintf(res, "MARGINAL %d %d", hp, hp);
+      for (int j = 0; j < 3; ++j) for (int i = 0; i < 3; ++i) std::fprintf(res, " %.17g", (*bp)(i, j));
+      std::fprintf(res, "\nMARGINAL %d %d", hl, hl);
+      for (int j = 0; j < 2; ++j) for (int i = 0; i < 2; ++i) std::fprintf(res, " %.17g", (*bl)(i, j));
+      std::fprintf(res, "\nMARGINAL %d %d", hp, hl);
+      for (int j = 0; j < 2; ++j) for (int i = 0; i < 3; ++i) std::fprintf(res, " %.17g", (*bx)(i, j));
+      std::fprintf(res, "\n");
+    }
+  }
   opt.discardTop();
   delete opt.algorithm();
   if (!(n > 0 && chi2_after < 400.0)) return 2;
+
+  // ---- the pose graph: setup_pose_opt + submap_loop_closer.cpp:204-288 (poses and odometry copied from the optimised
+  // landmark graph, DCS closure edges) + optimize(20)
+  g2o::SparseOptimizer popt;
+  setup_pose_opt(popt);
+  std::deque<g2o::VertexSE2> pposes;
+  std::deque<g2o::EdgeSE2> pedges;
+  std::deque<g2o::RobustKernelDCS> kernels;
+  for (int k = 0; k < P; ++k) {
+    pposes.emplace_back();
+    pposes.back().setId(k);
+    pposes.back().setEstimate(poses[k].estimate());
+    if (k == 0) pposes.back().setFixed(true);
+    popt.addVertex(&pposes.back());
+    if (k > 0) {
+      pedges.emplace_back();
+      pedges.back().vertices()[0] = &pposes[k - 1];
+      pedges.back().vertices()[1] = &pposes[k];
+      pedges.back().setMeasurement(poses[k - 1].estimate().inverse() * poses[k].estimate());   // submap_loop_closer.cpp:216
+      pedges.back().information() = odom[k - 1].information();                                // :217
+      popt.addEdge(&pedges.back());
+    }
+  }
+  const int closures[3][2] = {{2, 30}, {5, 38}, {10, 25}};
+  for (int c = 0; c < 3; ++c) {
+    const int a = closures[c][0], b = closures[c][1];
+    pedges.emplace_back();
+    pedges.back().vertices()[0] = &pposes[a];
+    pedges.back().vertices()[1] = &pposes[b];
+    g2o::SE2 rel = poses[a].estimate().inverse() * poses[b].estimate();
+    // the last closure is a false one (far off): DCS must down-weight it
+    pedges.back().setMeasurement(g2o::SE2(rel[0] + (c == 2 ? 1.5 : 0.02 * n01(rng)), rel[1] + (c == 2 ? -1.0 : 0.02 * n01(rng)), rel[2] + 0.01 * n01(rng)));
+    pedges.back().information()(0, 0) = 400; pedges.back().information()(1, 1) = 400; pedges.back().information()(2, 2) = 2500;
+    kernels.emplace_back();
+    kernels.back().setDelta(0.75);                                                            // datasets/mit-killian/slam.yaml:38
+    pedges.back().setRobustKernel(&kernels.back());                                           // submap_loop_closer.cpp:279-281
+    popt.addEdge(&pedges.back());
+  }
+  if (!prefix.empty()) {
+    std::FILE* f = std::fopen((prefix + "_pose.g2o").c_str(), "w");
+    if (!f) return 10;
+    std::deque<g2o::VertexRhoTheta> none;
+    dump_vertices(f, pposes, none);
+    for (auto& e : pedges) dump_pp(f, e);
+    int k = 0;
+    for (auto& e : pedges) { if (e.robustKernel()) std::fprintf(f, "ROBUST_KERNEL_DCS %d %.17g\n", k, e.robustKernel()->delta()); ++k; }
+    std::fclose(f);
+  }
+  if (!popt.initializeOptimization()) return 11;
+  int np = popt.optimize(20);
+  popt.computeActiveErrors();
+  std::printf("pose graph: optimize returned %d, chi2 = %.6f (robust %.6f)\n", np, popt.activeChi2(), popt.activeRobustChi2());
+  if (res) {
+    std::fprintf(res, "GN ITERATIONS %d\nGN CHI2 %.17g\n", np, popt.activeChi2());
+    std::deque<g2o::VertexRhoTheta> none;
+    dump_estimates(res, "GN", pposes, none);
+    std::fclose(res);
+  }
+  delete popt.algorithm();
+  if (np != 20) return 12;
   return linear_solver_example();
 }

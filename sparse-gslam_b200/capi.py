@@ -19,6 +19,7 @@ EXPORTS = [
     "sgb_get_timings", "sgb_optimize_resident", "sgb_set_graph_partitioned", "sgb_comm_get_handle", "sgb_comm_connect",
     "sgb_get_partition_info", "sgb_optimize_batch", "sgb_optimize_batch_resident", "sgb_g2o_load", "sgb_g2o_view",
     "sgb_g2o_free", "sgb_g2o_save",
+    "sgb_compute_marginals",
     "sgb_linear_set_pattern", "sgb_linear_solve", "sgb_set_graph_device", "sgb_pg_create", "sgb_pg_destroy", "sgb_pg_last_error", "sgb_pg_reset",
     "sgb_pg_append_from_lm", "sgb_pg_append_from_host", "sgb_pg_add_closure", "sgb_pg_optimize",
     "sgb_pg_prune_closures", "sgb_pg_get_info", "sgb_pg_download",

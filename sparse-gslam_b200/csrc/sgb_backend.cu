@@ -668,7 +668,13 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   free_graph(h);
   h->lin = sgb_handle::LinearMap();
   lap("free");
-  sgb_status st = build_structure(*g, h->S, h->err);
+  // Multi-GPU with ghost landmark rows: every rank runs the per-edge part of the symbolic phase on the edges IT needs only
+  // (~1/world of the graph) -- the scan of the active vertices and the index mapping stay global, so Hessian indices are
+  // the reference's. SGB_PARTITION_FULL=1 keeps the whole structure on every rank (the structure / Hessian export hooks
+  // of the parity tests need it).
+  static const bool full_env = [] { const char* e = std::getenv("SGB_PARTITION_FULL"); return e && e[0] == '1'; }();
+  const bool filtered = world > 1 && partition_ghost_landmarks() && !full_env;
+  sgb_status st = build_structure(*g, h->S, h->err, filtered ? world : 1, filtered ? rank : 0);
   if (st != SGB_OK) return st;
   lap("build_structure");
   if (dv && dv->has_robust) h->S.has_robust = true;
@@ -694,8 +700,10 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   h->off_pose[0] = take(np); h->off_pose[1] = take(np);
   h->off_lm[0] = take(nl); h->off_lm[1] = take(nl);
   h->off_p = take(3 * (size_t)P.capP); h->off_xp = take(3 * (size_t)P.capP);
-  h->off_t = take(2 * (size_t)P.capL); h->off_bl = take(2 * (size_t)P.capL); h->off_hllinv = take(3 * (size_t)P.capL);
   h->off_mbox = off; off = align256(off + sizeof(Mailbox));
+  // landmark-sized arrays last: with ghost rows their stride capL is the rank's own row count (nobody else reads them),
+  // so only the offsets above -- functions of global quantities -- have to agree between the ranks
+  h->off_t = take(2 * (size_t)P.capL); h->off_bl = take(2 * (size_t)P.capL); h->off_hllinv = take(3 * (size_t)P.capL);
   h->arena_bytes = off;
   if ((st = (world > 1 ? dalloc_raw(h, &h->arena, h->arena_bytes) : dalloc(h, &h->arena, h->arena_bytes))) != SGB_OK) return st;
   SGB_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
@@ -946,7 +954,11 @@ sgb_status sgb_get_structure(const sgb_handle* h, int32_t* kind, int32_t* index,
                              int32_t* bc, int32_t* bnr, int32_t* bnc, int32_t* ph, int32_t* lh) {
   if (!h) return SGB_ERR_INVALID;
   if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
-  if (kind || index || offset || br || bc || bnr || bnc)  // the per-vertex Hessian indices alone need no block list
+  if ((br || bc || bnr || bnc) && h->S.filtered) {
+    const_cast<sgb_handle*>(h)->err = "the block list needs the whole structure on this rank: set SGB_PARTITION_FULL=1";
+    return SGB_ERR_UNSUPPORTED;
+  }
+  if (br || bc || bnr || bnc)  // the Hessian order and the per-vertex indices alone need no block list
     build_block_list(const_cast<sgb_handle*>(h)->S);  // built on first use; the handle is not shared between threads
   const Structure& S = h->S;
   auto cp = [](int32_t* dst, const std::vector<int32_t>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(int32_t)); };
@@ -987,6 +999,10 @@ sgb_status sgb_linearize(sgb_handle* h, double* b, double* Hblocks, double* chi2
   DevGraph& G = h->G;
   if (chi2) { chi2[0] = h->h_sc->chi2; chi2[1] = h->h_sc->chi2_robust; }
   if (b && (st = gather_owned_vector(h, G.b_p, G.b_l[P.rank], b)) != SGB_OK) return st;
+  if (Hblocks && h->S.filtered) {
+    h->err = "the Hessian export needs the whole structure on this rank: set SGB_PARTITION_FULL=1";
+    return SGB_ERR_UNSUPPORTED;
+  }
   if (Hblocks) {
     build_export(h->S, h->LP);
     std::vector<double> hpp((size_t)P.Hpp.entries() * 9), hpl((size_t)P.Hpl.entries() * 6), hll(3 * (size_t)P.nL);

@@ -15,7 +15,7 @@ void partition_use_ghost_landmarks(bool on) { g_ghosts = on ? 1 : 0; }
 bool partition_ghost_landmarks() {
   if (g_ghosts < 0) {
     const char* e = std::getenv("SGB_GHOST_LANDMARKS");
-    g_ghosts = (e && e[0] == '1') ? 1 : 0;
+    g_ghosts = (e && e[0] == '0') ? 0 : 1;
   }
   return g_ghosts == 1;
 }
@@ -233,7 +233,11 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
   if (world < 1 || world > kMaxRanks || rank < 0 || rank >= world) { err = "bad world/rank"; return SGB_ERR_INVALID; }
   P.world = world;
   P.rank = rank;
-  P.chunkP = std::max(1, (S.Pf + world - 1) / world);
+  P.chunkP = partition_chunk(S.Pf, world);
+  if (S.filtered && (S.fworld != world || S.frank != rank)) { err = "structure was filtered for another rank"; return SGB_ERR_INVALID; }
+  if (S.filtered && !(world > 1 && partition_ghost_landmarks())) { err = "a rank-filtered structure needs ghost landmark rows"; return SGB_ERR_INVALID; }
+  // landmarks this rank knows about: all of them, or (filtered build) the ones it keeps a row of
+  auto present = [&](int hl) { return !S.filtered || S.lm_present[hl] != 0; };
   if (P.chunkP > kLocalMask) { err = "too many rows per rank for the column encoding"; return SGB_ERR_UNSUPPORTED; }
   auto owner_p = [&](int hp) { return hp / P.chunkP; };
   P.p_begin = std::min(S.Pf, rank * P.chunkP);
@@ -252,21 +256,24 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
   // (stable in the Hessian index), so that the slices of the grouped SELL are uniform and no row -> landmark
   // indirection is needed on the device. One stable counting sort over (owner, -count) covers every rank.
   std::vector<int32_t> count(world, 0);
-  P.enc_lm.assign(S.Lf, 0);
+  P.enc_lm.assign(S.Lf, -1);  // stays -1 for a landmark this rank knows nothing about (filtered build)
   {
     int maxc = 0;
     for (int hl = 0; hl < S.Lf; ++hl) {
-      lm_owner[hl] = lm_first[hl] >= 0 ? owner_p(lm_first[hl]) : 0;
+      lm_owner[hl] = !present(hl) ? -1 : (lm_first[hl] >= 0 ? owner_p(lm_first[hl]) : 0);
       maxc = std::max(maxc, S.lp_ptr[hl + 1] - S.lp_ptr[hl]);
     }
     const size_t nb = (size_t)world * ((size_t)maxc + 1);
     std::vector<int32_t> start(nb + 1, 0);
     auto key = [&](int hl) { return (size_t)lm_owner[hl] * ((size_t)maxc + 1) + (size_t)(maxc - (S.lp_ptr[hl + 1] - S.lp_ptr[hl])); };
-    for (int hl = 0; hl < S.Lf; ++hl) start[key(hl) + 1]++;
+    int n_present = 0;
+    for (int hl = 0; hl < S.Lf; ++hl)
+      if (lm_owner[hl] >= 0) { start[key(hl) + 1]++; ++n_present; }
     for (size_t b = 0; b < nb; ++b) start[b + 1] += start[b];
-    std::vector<int32_t> sorted(S.Lf);
-    for (int hl = 0; hl < S.Lf; ++hl) sorted[start[key(hl)]++] = hl;
-    for (int q = 0; q < S.Lf; ++q) {
+    std::vector<int32_t> sorted(n_present);
+    for (int hl = 0; hl < S.Lf; ++hl)
+      if (lm_owner[hl] >= 0) sorted[start[key(hl)]++] = hl;
+    for (int q = 0; q < n_present; ++q) {
       int hl = sorted[q], o = lm_owner[hl];
       P.enc_lm[hl] = (o << kOwnerShift) | count[o];
       if (o == rank) P.lm_global.push_back(hl);
@@ -282,6 +289,7 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
     std::vector<int32_t> nghost(world, 0), mine;
     std::vector<char> seen(world);
     for (int hl = 0; hl < S.Lf; ++hl) {
+      if (lm_owner[hl] < 0) continue;
       std::fill(seen.begin(), seen.end(), 0);
       for (int q = S.lp_ptr[hl]; q < S.lp_ptr[hl + 1]; ++q) {
         int o = owner_p(S.lp_col[q]);
@@ -299,8 +307,9 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
       P.lm_global.push_back(hl);
     }
     P.nL = (int)P.lm_global.size();
-    P.capL = 0;
-    for (int r = 0; r < world; ++r) P.capL = std::max(P.capL, count[r] + nghost[r]);
+    // with ghost rows no landmark-sized array is read by another rank: its stride is this rank's own row count (a
+    // filtered build does not even know the other ranks' counts)
+    P.capL = P.nL;
   }
   if (P.capL > kLocalMask) { err = "too many landmarks per rank for the column encoding"; return SGB_ERR_UNSUPPORTED; }
   P.pose_of_l.resize(P.nP);
@@ -313,6 +322,7 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
   auto pose_local = [&](int hp) { return hp >= 0 && owner_p(hp) == rank; };
   P.enc_lm_here.resize(S.Lf);
   for (int hl = 0; hl < S.Lf; ++hl) P.enc_lm_here[hl] = loc_lm[hl] >= 0 ? ((rank << kOwnerShift) | loc_lm[hl]) : P.enc_lm[hl];
+  // (filtered build: an absent landmark keeps enc -1 and is never referenced -- none of this rank's poses observes it)
   auto lm_local = [&](int hl) { return hl >= 0 && loc_lm[hl] >= 0; };          // owned or ghost row here
   auto lm_owned = [&](int hl) { return hl >= 0 && lm_owner[hl] == rank; };
 
@@ -479,7 +489,7 @@ void build_export(Structure& S, LocalPlan& P) {
   for (size_t b = 0; b < S.blk_row.size(); ++b) {
     int kind = S.blk_kind[b];
     if (kind == 2) {
-      int hl = S.blk_entry[b], o = P.enc_lm[hl] >> kOwnerShift;
+      int hl = S.blk_entry[b], o = P.enc_lm[hl] < 0 ? -1 : (P.enc_lm[hl] >> kOwnerShift);
       P.blk_owner[b] = o;
       if (o == P.rank) P.blk_entry[b] = P.enc_lm[hl] & kLocalMask;
     } else {

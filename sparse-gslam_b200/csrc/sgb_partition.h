@@ -40,7 +40,9 @@ struct LocalPlan {
 // but another rank owns -- all its edges (linearised locally from the replicated estimates), its Hll / W / b_l / t.
 // The pose-major pass then never reads a landmark quantity of another rank, and the barrier after the landmark pass
 // of the PCG only has to span the GPU. Updates, chi2 and the exported system stay with the owner.
-// Default: off, or the environment variable SGB_GHOST_LANDMARKS=1.
+// Default: on (validated on 2 and 8 GPUs, round 2); SGB_GHOST_LANDMARKS=0 in the environment or
+// partition_use_ghost_landmarks(false) select the owner-only layout, where the pose-major pass gathers t / W / b_l of
+// remote landmarks through NVLink.
 void partition_use_ghost_landmarks(bool on);
 bool partition_ghost_landmarks();
 

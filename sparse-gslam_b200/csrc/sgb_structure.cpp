@@ -123,7 +123,7 @@ void order_by_seq(std::vector<int32_t>& idx, const int64_t* seq) {
 
 }  // namespace
 
-sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& err) {
+sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& err, int world, int rank) {
   static const bool prof = std::getenv("SGB_PROFILE") != nullptr;
   auto tp0 = std::chrono::steady_clock::now();
   auto lap = [&](const char* what) {
@@ -153,14 +153,20 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   if (g.n_pp >= (1 << 29) || g.n_pl >= (1 << 29)) { err = "too many edges for the packed incidence encoding"; return SGB_ERR_UNSUPPORTED; }
 
   // ---- active edges (level 0, all vertices in the set, not all fixed), sorted by internal id within each type
+  const bool filtered = world > 1;
+  S.filtered = filtered;
+  S.fworld = filtered ? world : 1;
+  S.frank = filtered ? rank : 0;
   std::vector<char> pact(P, 0), lact(L, 0);
-  S.pp_src.reserve(g.n_pp);
-  S.pl_src.reserve(g.n_pl);
+  if (!filtered) {
+    S.pp_src.reserve(g.n_pp);
+    S.pl_src.reserve(g.n_pl);
+  }
   for (int k = 0; k < g.n_pp; ++k) {
     int i = g.pp_i[k], j = g.pp_j[k];
     if (i < 0 || i >= P || j < 0 || j >= P || i == j) { err = "pose-pose edge with a bad vertex index"; return SGB_ERR_INVALID; }
     if (pfixed(i) && pfixed(j)) continue;
-    S.pp_src.push_back(k);
+    if (!filtered) S.pp_src.push_back(k);
     pact[i] = pact[j] = 1;
     if (g.pp_phi && g.pp_phi[k] > 0.0) S.has_robust = true;
   }
@@ -168,20 +174,16 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     int p = g.pl_pose[k], l = g.pl_lm[k];
     if (p < 0 || p >= P || l < 0 || l >= L) { err = "pose-line edge with a bad vertex index"; return SGB_ERR_INVALID; }
     if (pfixed(p) && lfixed(l)) continue;
-    S.pl_src.push_back(k);
+    if (!filtered) S.pl_src.push_back(k);
     pact[p] = 1;
     lact[l] = 1;
   }
   lap("active scan");
-  order_by_seq(S.pp_src, g.pp_seq);
-  order_by_seq(S.pl_src, g.pl_seq);
-  S.n_pp = (int)S.pp_src.size();
-  S.n_pl = (int)S.pl_src.size();
   // global insertion rank of an active edge (ties: pose-pose first, then caller index -- both orders are stable)
+  // (the lambdas are used after S.pp_src / S.pl_src have been filled, further down for the filtered build)
   auto seq_pp = [&](int k) { return g.pp_seq ? g.pp_seq[S.pp_src[k]] : (int64_t)S.pp_src[k]; };
   auto seq_pl = [&](int k) { return g.pl_seq ? g.pl_seq[S.pl_src[k]] : (int64_t)g.n_pp + S.pl_src[k]; };
 
-  lap("edge order");
   // ---- index mapping: active vertices sorted by id; fixed -> -1; nothing is marginalised
   std::vector<int32_t>& porder = S.pose_of_h;
   std::vector<int32_t>& lorder = S.lm_of_h;
@@ -211,6 +213,45 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
   for (int h = 0; h < S.Lf; ++h) { S.ord_kind[S.Pf + h] = 1; S.ord_index[S.Pf + h] = lorder[h]; S.ord_offset[S.Pf + h] = 3 * S.Pf + 2 * h; }
 
   lap("index mapping");
+  if (filtered) {
+    // ---- the edges this rank needs, selected with the GLOBAL Hessian indices just computed: pose-pose edges with an
+    // endpoint in its row block; every edge of a landmark that one of its poses observes (the rank keeps a full copy of
+    // that landmark's row: owned or ghost, sgb_partition.h). A landmark without any free observer belongs to rank 0.
+    const int chunk = partition_chunk(S.Pf, world);
+    auto mine = [&](int h) { return h >= 0 && h / chunk == rank; };
+    std::vector<char> keep(L, 0), free_obs(L, 0);
+    for (int k = 0; k < g.n_pl; ++k) {
+      int p = g.pl_pose[k], l = g.pl_lm[k];
+      if (pfixed(p) && lfixed(l)) continue;
+      int hp = S.pose_h[p];
+      if (hp >= 0) {
+        free_obs[l] = 1;
+        if (mine(hp)) keep[l] = 1;
+      }
+    }
+    if (rank == 0)
+      for (int l = 0; l < L; ++l)
+        if (lact[l] && !free_obs[l]) keep[l] = 1;
+    for (int k = 0; k < g.n_pp; ++k) {
+      int i = g.pp_i[k], j = g.pp_j[k];
+      if (pfixed(i) && pfixed(j)) continue;
+      if (mine(S.pose_h[i]) || mine(S.pose_h[j])) S.pp_src.push_back(k);
+    }
+    for (int k = 0; k < g.n_pl; ++k) {
+      int p = g.pl_pose[k], l = g.pl_lm[k];
+      if (pfixed(p) && lfixed(l)) continue;
+      if (mine(S.pose_h[p]) || (S.lm_h[l] >= 0 && keep[l])) S.pl_src.push_back(k);
+    }
+    S.lm_present.assign(S.Lf, 0);
+    for (int l = 0; l < L; ++l)
+      if (S.lm_h[l] >= 0 && keep[l]) S.lm_present[S.lm_h[l]] = 1;
+    lap("rank filter");
+  }
+  order_by_seq(S.pp_src, g.pp_seq);
+  order_by_seq(S.pl_src, g.pl_seq);
+  S.n_pp = (int)S.pp_src.size();
+  S.n_pl = (int)S.pl_src.size();
+  lap("edge order");
   // ---- per-type active edge arrays (insertion order); independent per edge: split over host threads when large
   S.pp_i.resize(S.n_pp); S.pp_j.resize(S.n_pp); S.pp_hi.resize(S.n_pp); S.pp_hj.resize(S.n_pp);
   S.pl_p.resize(S.n_pl); S.pl_l.resize(S.n_pl); S.pl_hp.resize(S.n_pl); S.pl_hl.resize(S.n_pl);

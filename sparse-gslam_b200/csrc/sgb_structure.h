@@ -47,6 +47,12 @@ struct HostSell {
 struct Structure {
   int P_all = 0, L_all = 0, Pf = 0, Lf = 0, n_pp = 0, n_pl = 0, dim = 0;
   bool has_robust = false;
+  // Rank-filtered build (multi-GPU with ghost landmark rows): the index mapping is the global one, but only the edges
+  // rank `frank` of `fworld` needs were kept -- pose-pose edges with an endpoint in its row block, and every edge of a
+  // landmark one of its poses observes. Rows of other ranks are empty; lm_present marks the landmarks this rank keeps.
+  bool filtered = false;
+  int fworld = 1, frank = 0;
+  std::vector<char> lm_present;             // [Lf], filtered builds only
   // vertex maps
   std::vector<int32_t> pose_h, lm_h;        // array index -> free index (-1 fixed / inactive)
   std::vector<int32_t> pose_of_h, lm_of_h;  // free index -> array index
@@ -74,7 +80,12 @@ struct Structure {
 };
 
 // Returns SGB_OK or an error code with a message. seq arrays may be NULL.
-sgb_status build_structure(const sgb_graph_soa& g, Structure& out, std::string& err);
+// world > 1 requests the rank-filtered build described at Structure::filtered: the scan of the active vertices and the
+// index mapping still cover the whole graph (so Hessian indices are the reference's), everything per edge -- the bulk of
+// the symbolic phase -- only covers the edges rank `rank` needs, i.e. ~1/world of the work per process.
+sgb_status build_structure(const sgb_graph_soa& g, Structure& out, std::string& err, int world = 1, int rank = 0);
+// free-pose rows per rank of the row-block partition (the one formula both the filter and the planner use)
+inline int partition_chunk(int Pf, int world) { int c = (Pf + world - 1) / world; return c < 1 ? 1 : c; }
 // fills Structure::blk_* (idempotent); only the structure / parity hooks of the C ABI need it
 void build_block_list(Structure& S);
 

@@ -167,16 +167,24 @@ class SparseOptimizerB200:
                     n_free_poses=info.n_free_poses, n_free_landmarks=info.n_free_landmarks,
                     n_active_pp=info.n_active_pp, n_active_pl=info.n_active_pl)
 
-    def linearize(self):
-        st = self.structure()
+    def structure_info(self):
+        info = capi.StructureInfo()
+        self._check(self.L.sgb_get_structure_info(self.h, C.byref(info)))
+        return dict(n_free=info.n_free, n_blocks=info.n_blocks, dim=info.scalar_dim, block_values=info.block_values,
+                    n_free_poses=info.n_free_poses, n_free_landmarks=info.n_free_landmarks)
+
+    def linearize(self, hessian=True):
+        """hessian=False skips the block export (a rank-filtered multi-GPU handle only holds its own share of the
+        structure and cannot lay its blocks out in the reference's global order)."""
+        st = self.structure_info()
         b = np.zeros(st["dim"])
-        H = np.zeros(st["block_values"])
+        H = np.zeros(st["block_values"]) if hessian else None
         chi = np.zeros(2)
         self._check(self.L.sgb_linearize(self.h, _p(b), _p(H), _p(chi)))
         return dict(b=b, H=H, chi2=chi)
 
     def solve_once(self, lam):
-        st = self.structure()
+        st = self.structure_info()
         x = np.zeros(st["dim"])
         it = C.c_int32()
         rel = C.c_double()

@@ -57,6 +57,9 @@ def lib():
         L.hs_check_hlp.restype = C.c_double
         L.hs_chi2.argtypes = [vp, vp]
         L.hs_use_ghost_landmarks.argtypes = [C.c_int]
+        L.hs_use_filtered_structure.argtypes = [C.c_int]
+        L.hs_time_symbolic.argtypes = [C.POINTER(capi.GraphSoA), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.hs_time_symbolic.restype = C.c_double
         L.hs_preconditioner.argtypes = [vp, C.c_double, vp]
         L.hs_pg_append.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.hs_closure_chi2.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
@@ -71,6 +74,19 @@ def lib():
 def use_ghost_landmarks(on: bool):
     """Planner switch (sgb_partition.h): ghost copies of the landmark rows other ranks own. Process-global."""
     lib().hs_use_ghost_landmarks(int(bool(on)))
+
+
+def use_filtered_structure(on: bool):
+    """Every virtual rank builds its own rank-filtered structure (what libsgb does on > 1 GPUs with ghost rows)."""
+    lib().hs_use_filtered_structure(int(bool(on)))
+
+
+def time_symbolic(g, world, rank, filtered):
+    """(ms, local pose-pose edges, local pose-line edges) of one rank's host symbolic phase."""
+    s, keep = pack_graph(g)
+    a, b = C.c_int(), C.c_int()
+    ms = lib().hs_time_symbolic(C.byref(s), world, rank, int(filtered), C.byref(a), C.byref(b))
+    return ms, a.value, b.value
 
 
 class HostSim:
@@ -130,9 +146,9 @@ class HostSim:
         return p, l
 
     def partition_stats(self):
-        o = np.zeros((self.world, 8), np.int64)
+        o = np.zeros((self.world, 9), np.int64)
         self.L.hs_partition_stats(self.h, _p(o))
-        keys = ("nP", "nL", "n_pp", "n_pl", "n_pp_owned", "n_pl_owned", "halo_p", "halo_t")
+        keys = ("nP", "nL", "n_pp", "n_pl", "n_pp_owned", "n_pl_owned", "halo_p", "halo_t", "nL_owned")
         return [dict(zip(keys, map(int, row))) for row in o]
 
     def preconditioner(self, lam, n_free_poses):

@@ -9,6 +9,7 @@
 // The product library libsgb.so does not contain this file and has no CPU path.
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -24,6 +25,7 @@
 using namespace sgb;
 
 struct Rank {
+  Structure Sr;  // this rank's own (filtered) structure when the rank-filtered symbolic phase is simulated
   LocalPlan P;
   DevGraph G;
   std::vector<std::vector<double>> dbl;
@@ -57,6 +59,9 @@ static void mk_sell(Rank* r, Sell* out, const HostSell& s, int NC) {
 extern "C" {
 
 void hs_use_ghost_landmarks(int on) { partition_use_ghost_landmarks(on != 0); }
+static bool g_filtered = false;
+// every virtual rank builds its own rank-filtered structure (build_structure(..., world, rank)), as libsgb does on >1 GPUs
+void hs_use_filtered_structure(int on) { g_filtered = on != 0; }
 
 hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int maxit, int world, int* status) {
   hs_handle* h = new hs_handle();
@@ -65,13 +70,18 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
   if (status) *status = st;
   if (st != SGB_OK) return h;
   build_block_list(h->S);
-  const Structure& S = h->S;
   h->tol = tol > 0 ? tol : 1e-10;
-  h->maxit = maxit > 0 ? maxit : std::max(100, 12 * S.Pf);
-  size_t np = 3 * (size_t)S.P_all, nl = 2 * (size_t)S.L_all;
+  h->maxit = maxit > 0 ? maxit : std::max(100, 12 * h->S.Pf);
+  size_t np = 3 * (size_t)h->S.P_all, nl = 2 * (size_t)h->S.L_all;
+  const bool filtered = g_filtered && h->world > 1 && partition_ghost_landmarks();
   for (int rk = 0; rk < h->world; ++rk) {
     h->R.emplace_back(new Rank());
     Rank* r = h->R.back().get();
+    if (filtered) {
+      st = build_structure(*g, r->Sr, h->err, h->world, rk);
+      if (st != SGB_OK) { if (status) *status = st; return h; }
+    }
+    const Structure& S = filtered ? r->Sr : h->S;
     st = partition(S, h->world, rk, r->P, h->err);
     if (st != SGB_OK) { if (status) *status = st; return h; }
     build_export(h->S, r->P);
@@ -132,6 +142,19 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
     }
   return h;
 }
+// wall time (ms) of the host symbolic phase of ONE rank: build_structure (+ rank filter) and the partition plan
+double hs_time_symbolic(const sgb_graph_soa* g, int world, int rank, int filtered, int* n_pp, int* n_pl) {
+  Structure S;
+  LocalPlan P;
+  std::string err;
+  auto t0 = std::chrono::steady_clock::now();
+  if (build_structure(*g, S, err, filtered ? world : 1, filtered ? rank : 0) != SGB_OK) return -1.0;
+  if (partition_consume(S, world, rank, P, err) != SGB_OK) return -2.0;
+  double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  if (n_pp) *n_pp = P.n_pp;
+  if (n_pl) *n_pl = P.n_pl;
+  return ms;
+}
 void hs_destroy(hs_handle* h) { delete h; }
 const char* hs_error(hs_handle* h) { return h->err.c_str(); }
 
@@ -164,8 +187,8 @@ void hs_sell_stats(hs_handle* h, int64_t* out /*[6]*/) {
 void hs_partition_stats(hs_handle* h, int64_t* out) {
   for (int k = 0; k < h->world; ++k) {
     const LocalPlan& P = h->R[k]->P;
-    int64_t v[8] = {P.nP, P.nL, P.n_pp, P.n_pl, P.n_pp_owned, P.n_pl_owned, P.halo_p, P.halo_t};
-    std::copy(v, v + 8, out + 8 * k);
+    int64_t v[9] = {P.nP, P.nL, P.n_pp, P.n_pl, P.n_pp_owned, P.n_pl_owned, P.halo_p, P.halo_t, P.nL_owned};
+    std::copy(v, v + 9, out + 9 * k);
   }
 }
 
@@ -221,8 +244,12 @@ void hs_linearize(hs_handle* h, double* b, double* Hblocks, double* chi2) {
     size_t o = 0;
     for (size_t k = 0; k < S.blk_row.size(); ++k) {
       int kind = S.blk_kind[k];
-      // every rank agrees on the owner; take the values from it
-      int owner = h->R[0]->P.blk_owner[k];
+      // the owner is the rank that names itself (with rank-filtered structures a rank only knows the owners of the
+      // blocks it has something to do with); take the values from it
+      int owner = -1;
+      for (int rk = 0; rk < h->world && owner < 0; ++rk)
+        if (h->R[rk]->P.blk_owner[k] == rk) owner = rk;
+      if (owner < 0) { o += (kind == 0 ? 9 : kind == 1 ? 6 : 4); continue; }
       const Rank& R = *h->R[owner];
       int e = R.P.blk_entry[k];
       const DevGraph& G = R.G;
@@ -296,7 +323,8 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
   }
   double gam0 = gam, gam_old = 0, alpha_old = 0;
   int it = 0, flag = 0;
-  bool any_lm = h->R[0]->G.capL > 0;
+  bool any_lm = false;  // with ghost rows capL is a per-rank quantity
+  for (auto& rk : h->R) any_lm = any_lm || rk->G.capL > 0;
   if (!(gam0 > 0.0)) {
     flag = (gam0 == 0.0) ? 0 : 2;
   } else {

@@ -20,6 +20,8 @@ def _worker(rank, world, port, q):
     from sparse_gslam_b200 import dist as sdist
     from sparse_gslam_b200 import graphgen as gg
     g = gg.make_small(seed=3, P=120, L=20, E_l=300, n_closures=10)
+    hostsim.use_ghost_landmarks(True)       # the product's default layout on > 1 GPUs: ghost landmark rows, and every
+    hostsim.use_filtered_structure(True)    # process runs the symbolic phase on its own share of the edges only
     hs = hostsim.HostSim(g, jac_numeric=False, world=world)
     mine = hs.partition_stats()[rank]
     blob = bytes([rank]) * 64
@@ -45,5 +47,6 @@ def test_two_rank_partition_and_handle_exchange():
         assert p.exitcode == 0
     for rank, blobs, stats in res:
         assert blobs == [bytes([r]) * 64 for r in range(world)]       # rank order preserved
-        assert sum(s["nP"] for s in stats) == 119 and sum(s["nL"] for s in stats) == 20
+        assert sum(s["nP"] for s in stats) == 119 and sum(s["nL_owned"] for s in stats) == 20
+        assert sum(s["nL"] for s in stats) > 20 and all(s["halo_t"] == 0 for s in stats)   # ghost rows, no remote landmark reads
         assert sum(s["n_pl_owned"] for s in stats) == 300

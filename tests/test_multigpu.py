@@ -47,9 +47,17 @@ def _collect(procs, q, world, timeout=600):
     return res
 
 
-def _worker(rank, world, port, q, ghosts):
+LAYOUTS = {  # planner mode of the partitioned path -> environment of the workers
+    "owner-only": {"SGB_GHOST_LANDMARKS": "0"},                              # remote t / W / b_l gathered over NVLink
+    "ghost-rows": {"SGB_GHOST_LANDMARKS": "1", "SGB_PARTITION_FULL": "1"},   # ghost landmark rows, whole structure per rank
+    "ghost-rows-filtered": {"SGB_GHOST_LANDMARKS": "1", "SGB_PARTITION_FULL": "0"},  # the default: per-rank symbolic phase
+}
+
+
+def _worker(rank, world, port, q, layout):
     sys.path.insert(0, ROOT)
-    os.environ["SGB_GHOST_LANDMARKS"] = "1" if ghosts else "0"
+    os.environ.update(LAYOUTS[layout])
+    export_h = layout != "ghost-rows-filtered"   # a rank-filtered handle cannot export blocks in the global order
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -64,7 +72,7 @@ def _worker(rank, world, port, q, ghosts):
     opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC, device=rank)
     assert opt.initialize_partitioned(g, world, rank, sdist.exchange_blobs)
     out["info"] = opt.partition_info()
-    lin = opt.linearize()
+    lin = opt.linearize(hessian=export_h)
     out["H"], out["b"], out["chi2"] = lin["H"], lin["b"], lin["chi2"]
     sdist.barrier()
     ok, x, it, rel = opt.solve_once(50.0)
@@ -87,9 +95,9 @@ def _worker(rank, world, port, q, ghosts):
     q.put((rank, out))
 
 
-@pytest.mark.parametrize("ghosts", [0, 1])
+@pytest.mark.parametrize("layout", list(LAYOUTS))
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_partitioned_matches_single_gpu(world, ghosts):
+def test_partitioned_matches_single_gpu(world, layout):
     if _ngpus() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
@@ -98,7 +106,7 @@ def test_partitioned_matches_single_gpu(world, ghosts):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, ghosts)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, layout)) for r in range(world)]
     for p in procs:
         p.start()
     res = _collect(procs, q, world)
@@ -106,9 +114,10 @@ def test_partitioned_matches_single_gpu(world, ghosts):
     one = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
     one.initialize_optimization(g)
     lin = one.linearize()
-    H = sum(res[r]["H"] for r in range(world))
     b = sum(res[r]["b"] for r in range(world))
-    np.testing.assert_array_equal(H, lin["H"])     # each block is written by exactly one rank, same arithmetic
+    if res[0]["H"] is not None:
+        H = sum(res[r]["H"] for r in range(world))
+        np.testing.assert_array_equal(H, lin["H"])     # each block is written by exactly one rank, same arithmetic
     np.testing.assert_array_equal(b, lin["b"])
     for r in range(world):
         np.testing.assert_allclose(res[r]["chi2"], lin["chi2"], rtol=1e-13)

@@ -21,6 +21,18 @@ def assert_same_structure(so, sh):
         assert np.array_equal(so[k], sh[k]), k
 
 
+@pytest.fixture(autouse=True)
+def _owner_only_layout_unless_requested():
+    """The planner's default is ghost landmark rows; the tests of the owner-only layout (halo gathers of t / W / b_l)
+    switch them off, the `ghost_landmarks` fixture switches them back on."""
+    hostsim.use_ghost_landmarks(False)
+    hostsim.use_filtered_structure(False)
+    yield
+    hostsim.use_ghost_landmarks(False)
+    hostsim.use_filtered_structure(False)
+
+
+
 @pytest.mark.parametrize("maker", [lambda: gg.make_small(seed=0), lambda: gg.make_small(seed=7, P=120, L=20, E_l=300, n_closures=10),
                                    lambda: gg.make_c4_window(1003), lambda: gg.make_c5(rows=20, cols=20),
                                    lambda: gg.make_c1().pose_only(phi=10.0)])
@@ -362,18 +374,22 @@ def test_random_graphs_partitioned_match_single_rank(seed, world):
         np.testing.assert_allclose(qm, q1, atol=1e-8)
 
 
-@pytest.fixture
-def ghost_landmarks():
+@pytest.fixture(params=[False, True], ids=["whole-structure", "rank-filtered"])
+def ghost_landmarks(request):
+    """Ghost landmark rows on; `rank-filtered`: every virtual rank also builds its own structure from the edges it needs
+    only (build_structure(..., world, rank)), the way libsgb runs the symbolic phase on > 1 GPUs."""
     hostsim.use_ghost_landmarks(True)
+    hostsim.use_filtered_structure(request.param)
     yield
+    hostsim.use_filtered_structure(False)
     hostsim.use_ghost_landmarks(False)
 
 
 @pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_ghost_landmarks_match_single_rank(world, ghost_landmarks):
-    """Opt-in planner mode (sgb_partition.h): every rank keeps a full copy of the landmark rows its poses observe. No
-    landmark quantity is read from another rank any more (halo_t == 0), and the system, the solve and the LM trajectory
-    are the single-rank ones."""
+    """Planner mode with ghost rows (sgb_partition.h): every rank keeps a full copy of the landmark rows its poses
+    observe. No landmark quantity is read from another rank any more (halo_t == 0), and the system, the solve and the LM
+    trajectory are the single-rank ones -- also when every rank only ever saw its own share of the edges."""
     g = gg.make_small(seed=3, P=120, L=20, E_l=300, n_closures=10)
     hostsim.use_ghost_landmarks(False)
     one = hostsim.HostSim(g, jac_numeric=False, tol=1e-12)
