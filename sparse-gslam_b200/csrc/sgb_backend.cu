@@ -62,7 +62,15 @@ struct sgb_handle {
   // peer-mapped arena: estimates (2 buffers), p, x_p, t, b_l, Hll_inv, mailbox -- same offsets on every rank
   char* arena = nullptr;
   size_t arena_bytes = 0;
-  size_t off_pose[2] = {0, 0}, off_lm[2] = {0, 0}, off_p = 0, off_xp = 0, off_t = 0, off_bl = 0, off_hllinv = 0, off_mbox = 0;
+  // Layout of a rank's arena, kept in its first bytes so that peers can read it after opening the IPC handle: array
+  // sizes that depend on rank-local quantities (halo slots, ghost rows) then need no agreement between the ranks.
+  struct ArenaHeader {
+    unsigned long long magic;
+    unsigned long long off_pose[2], off_lm[2], off_p, off_xp, off_mbox, off_t, off_bl, off_hllinv;
+    int32_t halo_base[kMaxRanks], halo_cnt[kMaxRanks];  // this rank's halo: slots [base[o], base[o] + cnt[o]) come from rank o
+  };
+  static constexpr unsigned long long kArenaMagic = 0x5347424152454e41ull;  // "SGBARENA"
+  ArenaHeader layout[kMaxRanks];  // [rank] = this rank's own layout; peers' filled by sgb_comm_connect
   void* peer_base[kMaxRanks] = {nullptr};
   bool connected = false;
   DevScalars* d_sc = nullptr;
@@ -552,19 +560,23 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 static void fill_peer_tables(sgb_handle* h) {
   DevGraph& G = h->G;
+  const int me = h->LP.rank;
   for (int r = 0; r < kMaxRanks; ++r) {
     char* base = (char*)h->peer_base[r];
-    if (!base) base = h->arena;  // unconnected slots alias this rank (never dereferenced: owners < world)
+    // unconnected slots alias this rank (never dereferenced: owners < world)
+    const sgb_handle::ArenaHeader& L = base ? h->layout[r] : h->layout[me];
+    if (!base) base = h->arena;
     for (int bsel = 0; bsel < 2; ++bsel) {
-      G.pose_buf[bsel][r] = (double*)(base + h->off_pose[bsel]);
-      G.lm_buf[bsel][r] = (double*)(base + h->off_lm[bsel]);
+      G.pose_buf[bsel][r] = (double*)(base + L.off_pose[bsel]);
+      G.lm_buf[bsel][r] = (double*)(base + L.off_lm[bsel]);
     }
-    G.p[r] = (double*)(base + h->off_p);
-    G.x_p[r] = (double*)(base + h->off_xp);
-    G.t[r] = (double*)(base + h->off_t);
-    G.b_l[r] = (double*)(base + h->off_bl);
-    G.Hll_inv[r] = (double*)(base + h->off_hllinv);
-    G.mbox[r] = (Mailbox*)(base + h->off_mbox);
+    G.p[r] = (double*)(base + L.off_p);
+    G.x_p[r] = (double*)(base + L.off_xp);
+    G.t[r] = (double*)(base + L.off_t);
+    G.b_l[r] = (double*)(base + L.off_bl);
+    G.Hll_inv[r] = (double*)(base + L.off_hllinv);
+    G.mbox[r] = (Mailbox*)(base + L.off_mbox);
+    G.halo_base_at[r] = base ? L.halo_base[me] : 0;
   }
 }
 
@@ -694,19 +706,24 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   G.jac_numeric = h->opt.jacobian_mode == SGB_JAC_G2O_NUMERIC ? 1 : 0;
   G.cur = 0;
   // ---- arena (identical layout on every rank: sizes depend on global quantities only)
+  G.pushed = P.pushed ? 1 : 0;
   size_t np = 3 * (size_t)S.P_all, nl = 2 * (size_t)S.L_all;
-  size_t off = 0;
+  size_t off = align256(sizeof(sgb_handle::ArenaHeader));
   auto take = [&](size_t doubles) { size_t o = off; off = align256(off + std::max<size_t>(doubles, 1) * sizeof(double)); return o; };
-  h->off_pose[0] = take(np); h->off_pose[1] = take(np);
-  h->off_lm[0] = take(nl); h->off_lm[1] = take(nl);
-  h->off_p = take(3 * (size_t)P.capP); h->off_xp = take(3 * (size_t)P.capP);
-  h->off_mbox = off; off = align256(off + sizeof(Mailbox));
-  // landmark-sized arrays last: with ghost rows their stride capL is the rank's own row count (nobody else reads them),
-  // so only the offsets above -- functions of global quantities -- have to agree between the ranks
-  h->off_t = take(2 * (size_t)P.capL); h->off_bl = take(2 * (size_t)P.capL); h->off_hllinv = take(3 * (size_t)P.capL);
+  sgb_handle::ArenaHeader& AL = h->layout[rank];
+  std::memset(&AL, 0, sizeof AL);
+  AL.magic = sgb_handle::kArenaMagic;
+  AL.off_pose[0] = take(np); AL.off_pose[1] = take(np);
+  AL.off_lm[0] = take(nl); AL.off_lm[1] = take(nl);
+  // p and x_p: the rank's own rows, then the halo copies of the remote rows its matrices reference (pushed halos)
+  AL.off_p = take(3 * ((size_t)P.capP + P.nH)); AL.off_xp = take(3 * ((size_t)P.capP + P.nH));
+  AL.off_mbox = off; off = align256(off + sizeof(Mailbox));
+  AL.off_t = take(2 * (size_t)P.capL); AL.off_bl = take(2 * (size_t)P.capL); AL.off_hllinv = take(3 * (size_t)P.capL);
+  for (int r = 0; r < kMaxRanks; ++r) { AL.halo_base[r] = P.halo_base[r]; AL.halo_cnt[r] = P.halo_cnt[r]; }
   h->arena_bytes = off;
   if ((st = (world > 1 ? dalloc_raw(h, &h->arena, h->arena_bytes) : dalloc(h, &h->arena, h->arena_bytes))) != SGB_OK) return st;
   SGB_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
+  SGB_CUDA(cudaMemcpyAsync(h->arena, &AL, sizeof AL, cudaMemcpyHostToDevice, h->stream));  // h->layout outlives the copy
   for (int r = 0; r < kMaxRanks; ++r) h->peer_base[r] = nullptr;
   h->peer_base[rank] = h->arena;
   fill_peer_tables(h);
@@ -809,6 +826,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   UP(pl_e_pl, P.pl_e_pl); UP(pl_e_lp, P.pl_e_lp); UP(pl_dup, P.pl_dup);
   UP(pinc_ptr, P.pinc_ptr); UP(pinc, P.pinc); UP(linc_ptr, P.linc_ptr); UP(linc, P.linc);
   UP(hpp_diag, P.hpp_diag);
+  if (P.pushed) { UP(send_ptr, P.send_ptr); UP(send_dst, P.send_dst); }
   lap("upload maps");
   for (auto& t : workers) t.join();
   workers.clear();
@@ -911,6 +929,15 @@ sgb_status sgb_comm_connect(sgb_handle* h, const void* handles, int32_t world) {
       return SGB_ERR_COMM;
     }
     h->peer_base[r] = p;
+    // the peer's arena layout sits in its first bytes (written by its sgb_set_graph, which synchronised its stream)
+    SGB_CUDA(cudaMemcpy(&h->layout[r], p, sizeof(sgb_handle::ArenaHeader), cudaMemcpyDeviceToHost));
+    if (h->layout[r].magic != sgb_handle::kArenaMagic) { h->err = "peer arena without a layout header (version mismatch?)"; return SGB_ERR_COMM; }
+    // pushed halos: the rows this rank pushes to r must be exactly the slots r reserved for it
+    if (h->LP.pushed && h->layout[r].halo_cnt[h->LP.rank] != h->LP.send_cnt[r]) {
+      h->err = "halo plan mismatch between ranks (" + std::to_string(h->LP.send_cnt[r]) + " rows to push, " +
+               std::to_string(h->layout[r].halo_cnt[h->LP.rank]) + " slots reserved by the peer)";
+      return SGB_ERR_COMM;
+    }
   }
   fill_peer_tables(h);
   h->connected = true;

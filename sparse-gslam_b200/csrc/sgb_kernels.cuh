@@ -481,14 +481,19 @@ __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, cons
     if (act)
       for (int c = 0; c < 3; ++c) r[c] = g.bt[3 * (size_t)lp + c];
     acc += precond_row_shfl(g, lp, act, r, z);
-    if (act)
-    for (int c = 0; c < 3; ++c) {
-      size_t o = 3 * (size_t)lp + c;
-      x[o] = 0.0;
-      g.r[o] = r[c];
-      zin[o] = z[c];
-      g.d[o] = 0.0;
-      g.s[o] = 0.0;
+    if (act) {
+      for (int c = 0; c < 3; ++c) {
+        size_t o = 3 * (size_t)lp + c;
+        x[o] = 0.0;
+        g.r[o] = r[c];
+        zin[o] = z[c];
+        g.d[o] = 0.0;
+        g.s[o] = 0.0;
+      }
+      if (g.pushed) {
+        const double x0[3] = {0.0, 0.0, 0.0};
+        push_halo_row(g, lp, z, x0);
+      }
     }
   }
   double gam = block_sum(acc, sm);
@@ -530,17 +535,20 @@ __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, cons
       acc = 0.0;
       for (int lp = tid; (lp & ~(kChunk - 1)) < g.nP; lp += nthreads) {
         const bool act = lp < g.nP;
-        double r[3] = {0.0, 0.0, 0.0}, z[3];
+        double r[3] = {0.0, 0.0, 0.0}, z[3], xn[3] = {0.0, 0.0, 0.0};
         if (act)
           for (int c = 0; c < 3; ++c) {
             size_t o = 3 * (size_t)lp + c;
-            x[o] += alpha * g.d[o];
+            xn[c] = x[o] + alpha * g.d[o];
+            x[o] = xn[c];
             r[c] = g.r[o] - alpha * g.s[o];
             g.r[o] = r[c];
           }
         acc += precond_row_shfl(g, lp, act, r, z);
-        if (act)
+        if (act) {
           for (int c = 0; c < 3; ++c) zin[3 * (size_t)lp + c] = z[c];
+          if (g.pushed) push_halo_row(g, lp, z, xn);
+        }
       }
       ++it;
       gam_old = gam;

@@ -10,6 +10,15 @@
 
 namespace sgb {
 
+static int g_pushed = -1;
+void partition_use_pushed_halos(bool on) { g_pushed = on ? 1 : 0; }
+bool partition_pushed_halos() {
+  if (g_pushed < 0) {
+    const char* e = std::getenv("SGB_PUSHED_HALOS");
+    g_pushed = (e && e[0] == '0') ? 0 : 1;
+  }
+  return g_pushed == 1;
+}
 static int g_ghosts = -1;  // -1: not decided yet (environment), 0 / 1
 void partition_use_ghost_landmarks(bool on) { g_ghosts = on ? 1 : 0; }
 bool partition_ghost_landmarks() {
@@ -359,9 +368,9 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
 
   // ---- local SELL matrices with encoded columns (pose rows and landmark rows are independent: two host threads)
   int64_t halo_p_pose = 0, halo_p_lm = 0;
+  FlatRows rows(P.nP), rows_pl(P.nP), obs(P.nL);
   auto build_pose_rows = [&]() {
     std::vector<int32_t> cols;
-    FlatRows rows(P.nP), rows_pl(P.nP);
     rows.col.reserve(S.Hpp.col.size() / world + 1024);
     rows_pl.col.reserve(S.Hpl.col.size() / world + 1024);
     for (int l = 0; l < P.nP; ++l) {
@@ -379,6 +388,8 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
       }
       rows_pl.close_row();
     }
+  };
+  auto finish_pose_rows = [&]() {
     build_local_sell(rows, nullptr, P.Hpp);
     build_local_sell(rows_pl, nullptr, P.Hpl);
     P.hpp_diag.resize(P.nP);
@@ -388,9 +399,7 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
     }
   };
   auto build_lm_rows = [&]() {
-    std::vector<int32_t> cols;
     // owned landmarks sorted by descending observer count (stable) to keep the SELL padding small
-    FlatRows obs(P.nL);
     obs.col.reserve(S.lp_col.size() / world + 1024);
     for (int l = 0; l < P.nL; ++l) {
       int hl = P.lm_global[l];
@@ -401,6 +410,8 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
       }
       obs.close_row();
     }
+  };
+  auto finish_lm_rows = [&]() {
     build_grouped_sell(obs, lm_target_steps(obs.col.size()), P.Hlp);  // rows already sorted by descending length
   };
   const bool threaded = (size_t)P.n_pp + P.n_pl > 200000;
@@ -413,6 +424,78 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
     build_lm_rows();
   }
   P.halo_p = halo_p_pose + halo_p_lm;
+
+  // ---- pushed pose halos (sgb_partition.h): with ghost rows the only remote quantities left in the operator passes are
+  // pose-vector entries; give them local halo slots and work out who has to push what to whom
+  P.pushed = world > 1 && partition_ghost_landmarks() && partition_pushed_halos();
+  if (P.pushed) {
+    auto glob = [&](int enc) { return (enc >> kOwnerShift) * P.chunkP + (enc & kLocalMask); };
+    std::vector<int32_t>& need = P.halo_src;
+    for (int enc : rows.col) if ((enc >> kOwnerShift) != rank) need.push_back(glob(enc));
+    for (int enc : obs.col) if ((enc >> kOwnerShift) != rank) need.push_back(glob(enc));
+    std::sort(need.begin(), need.end());
+    need.erase(std::unique(need.begin(), need.end()), need.end());
+    P.nH = (int)need.size();
+    if ((int64_t)P.capP + P.nH > kLocalMask) { err = "too many halo rows for the column encoding"; return SGB_ERR_UNSUPPORTED; }
+    for (int hp : need) P.halo_cnt[owner_p(hp)]++;
+    for (int o = 1; o < world; ++o) P.halo_base[o] = P.halo_base[o - 1] + P.halo_cnt[o - 1];
+    auto slot_enc = [&](int enc) {
+      int s = (int)(std::lower_bound(need.begin(), need.end(), glob(enc)) - need.begin());
+      return (rank << kOwnerShift) | (P.capP + s);
+    };
+    // sender side, before the columns are re-encoded: rows with a pose-pose block in a row of q ...
+    std::vector<std::vector<int32_t>> send_rows(world);
+    for (int l = 0; l < P.nP; ++l)
+      for (int q = rows.ptr[l]; q < rows.ptr[l + 1]; ++q) {
+        int o = rows.col[q] >> kOwnerShift;
+        if (o != rank) send_rows[o].push_back(l);
+      }
+    // ... and rows that observe a landmark some pose of q observes (q keeps a full copy of that landmark's row)
+    {
+      std::vector<char> has(world);
+      for (int lr = 0; lr < P.nL; ++lr) {
+        std::fill(has.begin(), has.end(), 0);
+        bool any_remote = false;
+        for (int q = obs.ptr[lr]; q < obs.ptr[lr + 1]; ++q) {
+          int o = obs.col[q] >> kOwnerShift;
+          has[o] = 1;
+          any_remote |= o != rank;
+        }
+        if (!any_remote) continue;
+        for (int q = obs.ptr[lr]; q < obs.ptr[lr + 1]; ++q) {
+          if ((obs.col[q] >> kOwnerShift) != rank) continue;
+          int l = obs.col[q] & kLocalMask;
+          for (int o = 0; o < world; ++o)
+            if (has[o] && o != rank) send_rows[o].push_back(l);
+        }
+      }
+    }
+    std::vector<int32_t> cnt(P.nP + 1, 0);
+    for (int o = 0; o < world; ++o) {
+      auto& v = send_rows[o];
+      std::sort(v.begin(), v.end());
+      v.erase(std::unique(v.begin(), v.end()), v.end());
+      P.send_cnt[o] = (int32_t)v.size();
+      for (int l : v) cnt[l + 1]++;
+    }
+    P.send_ptr.assign(P.nP + 1, 0);
+    for (int l = 0; l < P.nP; ++l) P.send_ptr[l + 1] = P.send_ptr[l] + cnt[l + 1];
+    P.send_dst.assign(P.send_ptr[P.nP], 0);
+    std::vector<int32_t> pos(P.send_ptr.begin(), P.send_ptr.end() - 1);
+    for (int o = 0; o < world; ++o)
+      for (size_t k = 0; k < send_rows[o].size(); ++k) P.send_dst[pos[send_rows[o][k]]++] = (o << kOwnerShift) | (int32_t)k;
+    // the gathers become local
+    for (auto& enc : rows.col) if ((enc >> kOwnerShift) != rank) enc = slot_enc(enc);
+    for (auto& enc : obs.col) if ((enc >> kOwnerShift) != rank) enc = slot_enc(enc);
+  }
+  if (threaded) {
+    std::thread t(finish_lm_rows);
+    finish_pose_rows();
+    t.join();
+  } else {
+    finish_pose_rows();
+    finish_lm_rows();
+  }
 
   // ---- per-edge arrays
   auto build_pp_edges = [&]() {

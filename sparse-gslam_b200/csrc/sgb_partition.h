@@ -34,6 +34,22 @@ struct LocalPlan {
   bool export_built = false;  // filled on demand by build_export()
   // halo statistics (distinct remote entries this rank gathers per PCG iteration)
   int64_t halo_p = 0, halo_t = 0;
+  // ---- pushed pose halos (ghost-row layout, world > 1). The pose-vector entries other ranks need (operator input z and
+  // step x of boundary rows) are WRITTEN into the consumers' memory by their owner at the end of the vector-update phase
+  // instead of being gathered through NVLink in the two operator passes: every column of the local matrices that names
+  // a pose of another rank is re-encoded as (this rank, capP + slot) and reads a halo copy kept behind the rank's own
+  // rows. halo_src = the global free-pose indices of the slots, ascending, i.e. grouped by source rank:
+  // [halo_base[o], halo_base[o] + halo_cnt[o]) come from rank o. The sender side follows from the symmetry of the
+  // structure (Hpp is symmetric; a landmark row lists all observers): rank r pushes its row i to rank q iff row i has a
+  // pose-pose block with a row of q, or observes a landmark that some pose of q observes. send_dst[send_ptr[l] ..
+  // send_ptr[l+1]) = (q << kOwnerShift) | k: local row l is the k-th of this rank's rows in q's halo. Both sides sort by
+  // global index, so the k-th pushed row lands in slot halo_base_q[r] + k; the counts are cross-checked at connect time.
+  bool pushed = false;
+  int nH = 0;
+  std::vector<int32_t> halo_src;
+  int32_t halo_base[8] = {0, 0, 0, 0, 0, 0, 0, 0}, halo_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<int32_t> send_ptr, send_dst;
+  int32_t send_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // rows this rank pushes to every other rank
 };
 
 // Ghost landmarks (world > 1, opt-in): a rank also keeps a full copy of the row of every landmark its poses observe
@@ -45,6 +61,9 @@ struct LocalPlan {
 // remote landmarks through NVLink.
 void partition_use_ghost_landmarks(bool on);
 bool partition_ghost_landmarks();
+// Pushed pose halos (LocalPlan::pushed; needs ghost rows). Default on; SGB_PUSHED_HALOS=0 keeps the NVLink gathers.
+void partition_use_pushed_halos(bool on);
+bool partition_pushed_halos();
 
 inline int enc_pose(int hp, int chunkP) { return ((hp / chunkP) << 26) | (hp % chunkP); }
 

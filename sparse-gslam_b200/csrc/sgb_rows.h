@@ -877,6 +877,29 @@ __device__ __forceinline__ double precond_row_shfl(const DevGraph& g, int lp, bo
 }
 #endif
 
+// Pushed pose halos (sgb_partition.h): the owner of row lp writes the row's new operator input z and step x into the halo
+// copies of every rank whose matrices reference the row. Plain strong stores through the peer mapping: they are ordered
+// before the cross-rank barrier that ends the phase by the barrier's release chain (CTA barrier -> gpu-scope fence +
+// ticket -> system-scope release of the publishing CTA), so the consumer's gathers after the barrier read them locally.
+SGB_HD void push_halo_row(const DevGraph& g, int lp, const double z[3], const double x[3]) {
+  const int b = SGB_LDG(&g.send_ptr[lp]), e = SGB_LDG(&g.send_ptr[lp + 1]);
+  for (int k = b; k < e; ++k) {
+    const int enc = SGB_LDG(&g.send_dst[k]);
+    const int q = enc >> kOwnerShift;
+    const size_t o = 3 * ((size_t)g.capP + (size_t)g.halo_base_at[q] + (size_t)(enc & kLocalMask));
+    double* pz = g.p[q] + o;
+    double* px = g.x_p[q] + o;
+#if defined(__CUDA_ARCH__)
+    for (int c = 0; c < 3; ++c) {
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(pz + c), "d"(z[c]) : "memory");
+      asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(px + c), "d"(x[c]) : "memory");
+    }
+#else
+    for (int c = 0; c < 3; ++c) { pz[c] = z[c]; px[c] = x[c]; }
+#endif
+  }
+}
+
 // SparseOptimizer::update for one owned free vertex: reads the current estimate, writes the new one into buffer
 // `dst` of EVERY rank (estimates are replicated; the owner pushes its rows over NVLink); returns the vertex's share
 // of computeScale = sum_j x_j (lambda x_j + b_j)

@@ -60,7 +60,13 @@ struct DevGraph {
   int32_t has_robust;    // any DCS edge
   int32_t jac_numeric;   // 1 = g2o central differences for pose-line edges
   int32_t cur;           // which estimate buffer is current (0/1); the other one holds the LM trial
-  int32_t pad0;
+  int32_t pushed;        // 1: pose halos are pushed (sgb_partition.h): p / x_p of this rank hold, behind the capP own rows,
+                         // copies of the remote rows its matrices reference, written by their owners; no remote gathers
+  // ---- pushed halos: destinations of the owned rows other ranks need (CSR over the owned rows)
+  const int32_t* send_ptr;            // [nP + 1]
+  const int32_t* send_dst;            // (destination rank << kOwnerShift) | k: this row is the k-th row of this rank in
+                                      // the destination's halo
+  int32_t halo_base_at[kMaxRanks];    // first halo slot of this rank's rows on every destination (exchanged at connect)
   // ---- estimates, replicated: est[buffer][rank] -> [3*P_all] / [2*L_all]; est[b][rank] is this rank's copy
   double* pose_buf[2][kMaxRanks];
   double* lm_buf[2][kMaxRanks];

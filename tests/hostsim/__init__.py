@@ -146,9 +146,9 @@ class HostSim:
         return p, l
 
     def partition_stats(self):
-        o = np.zeros((self.world, 9), np.int64)
+        o = np.zeros((self.world, 11), np.int64)
         self.L.hs_partition_stats(self.h, _p(o))
-        keys = ("nP", "nL", "n_pp", "n_pl", "n_pp_owned", "n_pl_owned", "halo_p", "halo_t", "nL_owned")
+        keys = ("nP", "nL", "n_pp", "n_pl", "n_pp_owned", "n_pl_owned", "halo_p", "halo_t", "nL_owned", "remote_cols", "nH")
         return [dict(zip(keys, map(int, row))) for row in o]
 
     def preconditioner(self, lam, n_free_poses):

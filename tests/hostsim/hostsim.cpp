@@ -129,7 +129,9 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
       std::copy(g->pose_est, g->pose_est + np, G.pose_buf[b][rk]);
       std::copy(g->lm_est, g->lm_est + nl, G.lm_buf[b][rk]);
     }
-    G.p[rk] = r->D(3 * (size_t)P.capP); G.x_p[rk] = r->D(3 * (size_t)P.capP);
+    G.p[rk] = r->D(3 * ((size_t)P.capP + P.nH)); G.x_p[rk] = r->D(3 * ((size_t)P.capP + P.nH));  // own rows + halo copies
+    G.pushed = P.pushed ? 1 : 0;
+    if (P.pushed) { G.send_ptr = r->I(P.send_ptr); G.send_dst = r->I(P.send_dst); }
     G.t[rk] = r->D(2 * (size_t)P.capL); G.b_l[rk] = r->D(2 * (size_t)P.capL); G.Hll_inv[rk] = r->D(3 * (size_t)P.capL);
   }
   // "sgb_comm_connect": cross-link the peer tables
@@ -139,6 +141,12 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
       const DevGraph& B = h->R[b]->G;
       for (int s = 0; s < 2; ++s) { A.pose_buf[s][b] = B.pose_buf[s][b]; A.lm_buf[s][b] = B.lm_buf[s][b]; }
       A.p[b] = B.p[b]; A.x_p[b] = B.x_p[b]; A.t[b] = B.t[b]; A.b_l[b] = B.b_l[b]; A.Hll_inv[b] = B.Hll_inv[b];
+      // pushed halos: where rank a's rows start in rank b's halo; the two sides of the plan must agree (sgb_comm_connect)
+      A.halo_base_at[b] = h->R[b]->P.halo_base[a];
+      if (a != b && h->R[a]->P.pushed && h->R[b]->P.halo_cnt[a] != h->R[a]->P.send_cnt[b]) {
+        h->err = "halo plan mismatch between ranks";
+        if (status) *status = SGB_ERR_COMM;
+      }
     }
   return h;
 }
@@ -187,8 +195,11 @@ void hs_sell_stats(hs_handle* h, int64_t* out /*[6]*/) {
 void hs_partition_stats(hs_handle* h, int64_t* out) {
   for (int k = 0; k < h->world; ++k) {
     const LocalPlan& P = h->R[k]->P;
-    int64_t v[9] = {P.nP, P.nL, P.n_pp, P.n_pl, P.n_pp_owned, P.n_pl_owned, P.halo_p, P.halo_t, P.nL_owned};
-    std::copy(v, v + 9, out + 9 * k);
+    int64_t remote = 0;  // matrix columns that still name a row of another rank (0 with pushed halos)
+    for (int32_t c : P.Hpp.col) remote += c >= 0 && (c >> kOwnerShift) != P.rank;
+    for (int32_t c : P.Hlp.col) remote += c >= 0 && (c >> kOwnerShift) != P.rank;
+    int64_t v[11] = {P.nP, P.nL, P.n_pp, P.n_pl, P.n_pp_owned, P.n_pl_owned, P.halo_p, P.halo_t, P.nL_owned, remote, P.nH};
+    std::copy(v, v + 11, out + 11 * k);
   }
 }
 
@@ -284,6 +295,11 @@ double hs_check_hlp(hs_handle* h) {
         int enc = G.Hlp.col[e];
         if (enc < 0) continue;
         int o = enc >> kOwnerShift, lp = enc & kLocalMask;
+        if (P.pushed && lp >= P.capP) {  // a halo copy: the slot names the global row
+          int hp = P.halo_src[lp - P.capP];
+          o = hp / P.chunkP;
+          lp = hp % P.chunkP;
+        }
         const Rank& Q = *h->R[o];
         // find hl in pose row lp of rank o
         int s2 = lp >> 5, l2 = lp & 31, w2 = sell_width(Q.G.Hpl, s2);
@@ -319,6 +335,8 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
       double z[3];
       gam += precond_row_from(G, lp, G.r, z);
       for (int c = 0; c < 3; ++c) zin[3 * lp + c] = z[c];
+      const double x0[3] = {0.0, 0.0, 0.0};
+      if (G.pushed) push_halo_row(G, lp, z, x0);
     }
   }
   double gam0 = gam, gam_old = 0, alpha_old = 0;
@@ -353,6 +371,7 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
           double z[3];
           gnew += precond_row_from(G, lp, G.r, z);
           for (int c = 0; c < 3; ++c) zin[3 * (size_t)lp + c] = z[c];
+          if (G.pushed) push_halo_row(G, lp, z, x + 3 * (size_t)lp);
         }
       }
       ++it;

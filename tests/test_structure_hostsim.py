@@ -399,6 +399,8 @@ def test_ghost_landmarks_match_single_rank(world, ghost_landmarks):
     assert many.status == capi.OK, many.error
     ps, pp = many.partition_stats(), plain.partition_stats()
     assert all(p["halo_t"] == 0 for p in ps) and any(p["halo_t"] > 0 for p in pp)
+    # pushed pose halos: no column of a rank's matrices names a row of another rank any more, the halo copies do
+    assert all(p["remote_cols"] == 0 and p["nH"] > 0 for p in ps) and any(p["remote_cols"] > 0 for p in pp)
     assert sum(p["nL"] for p in ps) > sum(p["nL"] for p in pp)          # the ghost rows
     assert sum(p["n_pl_owned"] for p in ps) == g.n_pl and sum(p["n_pp_owned"] for p in ps) == g.n_pp
     l1, lm = one.linearize(), many.linearize()
