@@ -72,6 +72,16 @@ struct sgb_handle {
   static constexpr unsigned long long kArenaMagic = 0x5347424152454e41ull;  // "SGBARENA"
   ArenaHeader layout[kMaxRanks];  // [rank] = this rank's own layout; peers' filled by sgb_comm_connect
   void* peer_base[kMaxRanks] = {nullptr};
+  // Multi-GPU arenas are recycled like the rest of the graph memory (the reference re-initialises once per key-frame):
+  // the exported allocation only grows, its IPC handle is exported once, and a peer mapping is kept open for as long as
+  // the peer keeps presenting the same handle -- cudaMalloc / cudaIpcOpenMemHandle / cudaIpcCloseMemHandle / cudaFree of
+  // 8 ranks x 7 peers were a third of the end-to-end step at 8 GPUs.
+  char* arena_raw = nullptr;
+  size_t arena_raw_cap = 0;
+  bool arena_exported = false;
+  cudaIpcMemHandle_t arena_handle;
+  void* peer_map[kMaxRanks] = {nullptr};          // open IPC mappings (survive sgb_set_graph)
+  cudaIpcMemHandle_t peer_handle[kMaxRanks];      // the handle each mapping was opened from
   bool connected = false;
   DevScalars* d_sc = nullptr;
   DevScalars* h_sc = nullptr;  // pinned
@@ -204,11 +214,14 @@ sgb_status upload_sell(sgb_handle* h, Sell* out, const HostSell& s, int NC) {
   return SGB_OK;
 }
 
-void free_graph(sgb_handle* h) {
+void close_peers(sgb_handle* h) {
   for (int r = 0; r < kMaxRanks; ++r) {
-    if (h->peer_base[r] && r != h->LP.rank) cudaIpcCloseMemHandle(h->peer_base[r]);
-    h->peer_base[r] = nullptr;
+    if (h->peer_map[r]) cudaIpcCloseMemHandle(h->peer_map[r]);
+    h->peer_map[r] = nullptr;
   }
+}
+void free_graph(sgb_handle* h) {
+  for (int r = 0; r < kMaxRanks; ++r) h->peer_base[r] = nullptr;  // the mappings themselves stay open (peer_map)
   h->connected = false;
   h->arena = nullptr;
   for (void* p : h->allocs) cudaFree(p);
@@ -537,6 +550,8 @@ void sgb_destroy(sgb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   free_graph(h);
+  close_peers(h);
+  if (h->arena_raw) cudaFree(h->arena_raw);
   for (auto& sl : h->slabs) cudaFree(sl.base);
   h->slabs.clear();
   cudaFree(h->d_sc);
@@ -721,7 +736,20 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   AL.off_t = take(2 * (size_t)P.capL); AL.off_bl = take(2 * (size_t)P.capL); AL.off_hllinv = take(3 * (size_t)P.capL);
   for (int r = 0; r < kMaxRanks; ++r) { AL.halo_base[r] = P.halo_base[r]; AL.halo_cnt[r] = P.halo_cnt[r]; }
   h->arena_bytes = off;
-  if ((st = (world > 1 ? dalloc_raw(h, &h->arena, h->arena_bytes) : dalloc(h, &h->arena, h->arena_bytes))) != SGB_OK) return st;
+  if (world > 1) {
+    if (h->arena_raw_cap < h->arena_bytes) {  // grow-only, with head-room for the next (slightly larger) graph
+      if (h->arena_raw) SGB_CUDA(cudaFree(h->arena_raw));
+      h->arena_raw = nullptr;
+      h->arena_raw_cap = 0;
+      h->arena_exported = false;
+      size_t cap = h->arena_bytes + h->arena_bytes / 4;
+      SGB_CUDA(cudaMalloc((void**)&h->arena_raw, cap));
+      h->arena_raw_cap = cap;
+    }
+    h->arena = h->arena_raw;
+  } else if ((st = dalloc(h, &h->arena, h->arena_bytes)) != SGB_OK) {
+    return st;
+  }
   SGB_CUDA(cudaMemsetAsync(h->arena, 0, h->arena_bytes, h->stream));
   SGB_CUDA(cudaMemcpyAsync(h->arena, &AL, sizeof AL, cudaMemcpyHostToDevice, h->stream));  // h->layout outlives the copy
   for (int r = 0; r < kMaxRanks; ++r) h->peer_base[r] = nullptr;
@@ -906,10 +934,18 @@ sgb_status sgb_comm_get_handle(sgb_handle* h, void* out64) {
   if (!h || !out64) return SGB_ERR_INVALID;
   if (!h->has_graph) return SGB_ERR_NOT_INITIALIZED;
   SGB_CUDA(cudaSetDevice(h->device));
-  cudaIpcMemHandle_t mh;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
-  SGB_CUDA(cudaIpcGetMemHandle(&mh, h->arena));
-  std::memcpy(out64, &mh, 64);
+  if (h->LP.world == 1 || h->arena != h->arena_raw) {  // a single-rank arena lives in the pooled memory: export it as it is
+    cudaIpcMemHandle_t mh;
+    SGB_CUDA(cudaIpcGetMemHandle(&mh, h->arena));
+    std::memcpy(out64, &mh, 64);
+    return SGB_OK;
+  }
+  if (!h->arena_exported) {
+    SGB_CUDA(cudaIpcGetMemHandle(&h->arena_handle, h->arena_raw));
+    h->arena_exported = true;
+  }
+  std::memcpy(out64, &h->arena_handle, 64);
   return SGB_OK;
 }
 
@@ -922,11 +958,17 @@ sgb_status sgb_comm_connect(sgb_handle* h, const void* handles, int32_t world) {
     if (r == h->LP.rank) continue;
     cudaIpcMemHandle_t mh;
     std::memcpy(&mh, (const char*)handles + 64 * (size_t)r, 64);
-    void* p = nullptr;
-    cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
-    if (e != cudaSuccess) {
-      h->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
-      return SGB_ERR_COMM;
+    void* p = h->peer_map[r];
+    if (!p || std::memcmp(&mh, &h->peer_handle[r], 64) != 0) {  // a new (or re-allocated) peer arena
+      if (p) cudaIpcCloseMemHandle(p);
+      h->peer_map[r] = p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) {
+        h->err = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e);
+        return SGB_ERR_COMM;
+      }
+      h->peer_map[r] = p;
+      h->peer_handle[r] = mh;
     }
     h->peer_base[r] = p;
     // the peer's arena layout sits in its first bytes (written by its sgb_set_graph, which synchronised its stream)
