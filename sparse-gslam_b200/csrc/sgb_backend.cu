@@ -93,6 +93,7 @@ struct sgb_handle {
   double* d_lm0 = nullptr;
   std::vector<std::pair<double*, double*>> stack;  // SparseOptimizer::push/pop backups (device)
   int pcg_blocks = 1;
+  int pcg_threads = kThreads;  // threads per CTA of the persistent PCG kernel (256 / 288 / 320, see k_pcg)
   bool no_small = std::getenv("SGB_NO_SMALL") != nullptr;  // tuning runs: always the throughput build of k_pcg
   int pcg_cluster = 0;  // > 0: the PCG grid is one thread-block cluster of this many CTAs (small graph, one GPU)
   // LinearSolver-level entry (sgb_linear_set_pattern / sgb_linear_solve): per input block its value offset, kind and
@@ -308,9 +309,10 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   } else {
     void* args[] = {&G, &sc, &part, &bar, &prm};
     // at most one CTA per SM and a single GPU: the latency-oriented build of the same kernel
-    const bool small = h->pcg_blocks <= h->sm_count && G.world == 1 && !h->no_small;
-    SGB_CUDA(cudaLaunchCooperativeKernel(small ? (void*)k_pcg_small : (void*)k_pcg, dim3(h->pcg_blocks), dim3(kThreads), args, 0,
-                                         h->stream));
+    const bool small = h->pcg_blocks <= h->sm_count && G.world == 1 && !h->no_small && h->pcg_threads == kThreads;
+    void* fn = small ? (void*)k_pcg_small
+                     : (h->pcg_threads == 320 ? (void*)k_pcg<320> : h->pcg_threads == 288 ? (void*)k_pcg<288> : (void*)k_pcg<256>);
+    SGB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(h->pcg_blocks), dim3(small ? kThreads : h->pcg_threads), args, 0, h->stream));
   }
   h->tm.kernel_launches++;
   return SGB_OK;
@@ -878,11 +880,33 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   if ((st = dalloc(h, &G.s, n3)) != SGB_OK) return st;
   SGB_CUDA(cudaMemsetAsync(h->d_sc, 0, sizeof(DevScalars), h->stream));
   // persistent PCG grid: every CTA must be co-resident
-  int per_sm = 0;
-  SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, kThreads, 0));
-  int limit = std::max(1, per_sm * h->sm_count);
-  int want = std::max(1, (std::max(P.nP, 32 * P.Hlp.nslices) + kThreads - 1) / kThreads);
-  h->pcg_blocks = std::min(std::min(limit, want), kMaxBlocks);
+  // Threads per CTA: the block size whose grid needs the fewest rows per thread (ceil), larger blocks paying a small
+  // penalty for their smaller register budget; ties go to the smaller block. SGB_PCG_THREADS forces one (tuning runs).
+  {
+    static const int forced = [] { const char* e = std::getenv("SGB_PCG_THREADS"); return e ? std::atoi(e) : 0; }();
+    const int items = std::max(P.nP, 32 * P.Hlp.nslices);
+    const int cand[3] = {256, 288, 320};
+    const double pen[3] = {1.0, 1.04, 1.15};
+    double best = 0.0;
+    int best_bt = kThreads, best_blocks = 1;
+    for (int c = 0; c < 3; ++c) {
+      if (forced > 0 && cand[c] != forced) continue;
+      int per_sm = 0;
+      const void* fn = cand[c] == 320 ? (const void*)k_pcg<320> : cand[c] == 288 ? (const void*)k_pcg<288> : (const void*)k_pcg<256>;
+      SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, cand[c], 0));
+      const int limit = std::max(1, per_sm * h->sm_count);
+      const int want = std::max(1, (items + cand[c] - 1) / cand[c]);
+      const int blocks = std::min(std::min(limit, want), kMaxBlocks);
+      const double threads = (double)blocks * cand[c];
+      const double cost = std::ceil(std::max(1, P.nP) / threads) * pen[c];
+      if (best == 0.0 || cost < best - 1e-9) { best = cost; best_bt = cand[c]; best_blocks = blocks; }
+    }
+    h->pcg_threads = best_bt;
+    h->pcg_blocks = best_blocks;
+    if (prof) std::fprintf(stderr, "[sgb_set_graph] pcg grid %d x %d threads (%d rows, %.2f rows per thread)\n", h->pcg_blocks,
+                           h->pcg_threads, P.nP, P.nP / ((double)h->pcg_blocks * h->pcg_threads));
+  }
+  const int want = std::max(1, (std::max(P.nP, 32 * P.Hlp.nslices) + kThreads - 1) / kThreads);
   // a graph that fits <= 16 CTAs runs its PCG as one thread-block cluster (hardware barrier, partials through DSMEM)
   h->pcg_cluster = 0;
   static const bool no_cluster = std::getenv("SGB_NO_CLUSTER") != nullptr;

@@ -565,8 +565,14 @@ __device__ __forceinline__ void pcg_solve(const DevGraph& g, const int tid, cons
   out.flag = flag;
 }
 
-__global__ void __launch_bounds__(kThreads, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g, DevScalars* sc, double* part,
-                                                                     unsigned long long* bar, PcgParams prm) {
+// BT = threads per CTA. The persistent grid is three CTAs per SM; a thread owns the rows tid, tid + nthreads, ... and a
+// phase lasts as long as its busiest thread, so the phase time is quantised in whole rows: 125 000 rows (one of eight
+// ranks of the 1M-pose graph) over 3 x 148 x 256 = 113 664 threads is TWO rows for every thread that matters, over
+// 3 x 148 x 288 = 127 872 threads it is one. The host picks the block size that minimises ceil(rows / threads) (the
+// register budget shrinks with the block: 80 / 72 / 64 registers for 256 / 288 / 320 threads).
+template <int BT>
+__global__ void __launch_bounds__(BT, SGB_PCG_MIN_BLOCKS) k_pcg(DevGraph g, DevScalars* sc, double* part,
+                                                                unsigned long long* bar, PcgParams prm) {
   __shared__ double sm[32];
   __shared__ int s_last;
   // wall time of the three phases of an iteration as seen by thread 0 of each CTA (barrier waits included); CTA 0's
