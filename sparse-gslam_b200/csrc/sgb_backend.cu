@@ -21,6 +21,7 @@
 #include "sgb_internal.h"
 #include "sgb_kernels.cuh"
 #include "sgb_partition.h"
+#include "sgb_resident.cuh"
 #include "sgb_structure.h"
 
 using namespace sgb;
@@ -96,6 +97,7 @@ struct sgb_handle {
   int pcg_threads = kThreads;  // threads per CTA of the persistent PCG kernel (256 / 288 / 320, see k_pcg)
   bool no_small = std::getenv("SGB_NO_SMALL") != nullptr;  // tuning runs: always the throughput build of k_pcg
   int pcg_cluster = 0;  // > 0: the PCG grid is one thread-block cluster of this many CTAs (small graph, one GPU)
+  ResPlan res;          // valid: the graph fits one cluster's shared memory -> the cluster-resident solve (sgb_resident.cuh)
   // LinearSolver-level entry (sgb_linear_set_pattern / sgb_linear_solve): per input block its value offset, kind and
   // the SELL entries it lands in; device copies live in the pooled memory of the current graph
   struct LinearMap {
@@ -293,7 +295,22 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   prm.lambda_override = lambda_override;
   prm.use_override = use_override;
   SGB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), h->stream));
-  if (h->pcg_cluster > 0) {
+  if (h->res.valid) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(h->res.ncta);
+    cfg.blockDim = dim3(h->res.bt);
+    cfg.dynamicSmemBytes = (size_t)h->res.bytes;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = h->res.ncta;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ResPlan rp = h->res;
+    SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res, G, sc, prm, rp));
+  } else if (h->pcg_cluster > 0) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->pcg_cluster);
     cfg.blockDim = dim3(kThreads);
@@ -889,8 +906,14 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
     const double pen[3] = {1.0, 1.04, 1.15};
     double best = 0.0;
     int best_bt = kThreads, best_blocks = 1;
+    // only where whole rows per thread matter: with more than three rows per thread the phases are bandwidth-bound and the
+    // 256-thread build with its 80 registers wins (C5 on one GPU: 41.9 / 40.6 / 39.6 LM it/s with 256 / 288 / 320 threads)
+    int per_sm256 = 0;
+    SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm256, (const void*)k_pcg<256>, 256, 0));
+    const bool quantised = (double)P.nP / ((double)std::max(1, per_sm256) * h->sm_count * 256.0) <= 3.0;
     for (int c = 0; c < 3; ++c) {
       if (forced > 0 && cand[c] != forced) continue;
+      if (forced <= 0 && c > 0 && !quantised) continue;
       int per_sm = 0;
       const void* fn = cand[c] == 320 ? (const void*)k_pcg<320> : cand[c] == 288 ? (const void*)k_pcg<288> : (const void*)k_pcg<256>;
       SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, cand[c], 0));
@@ -930,6 +953,54 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
     }
     cudaGetLastError();  // a refused cluster shape is not an error: the cooperative grid is used instead
     if (prof) std::fprintf(stderr, "[sgb_set_graph] pcg cluster %d (wanted %d CTAs)\n", h->pcg_cluster, want);
+  }
+  // a graph whose per-CTA share of the matrices fits the shared memory of a cluster: the cluster-resident solve
+  h->res = ResPlan();
+  static const bool no_res = std::getenv("SGB_NO_RESIDENT") != nullptr;
+  if (world == 1 && !no_res && !no_cluster && P.nP > 0) {
+    static const bool np_ok = cudaFuncSetAttribute(k_pcg_res, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    auto cap_of = [](const HostSell& M, int spc, int ncta) {
+      int cap = 0;
+      for (int c = 0; c < ncta; ++c) {
+        int s0 = std::min(M.nslices, c * spc), s1 = std::min(M.nslices, (c + 1) * spc);
+        cap = std::max(cap, M.sbase[s1] - M.sbase[s0]);
+      }
+      return cap;
+    };
+    for (int bt : {256, 128, 64}) {
+      const int spc = bt / 32;
+      int need = std::max((P.nP + bt - 1) / bt, (P.Hlp.nslices + spc - 1) / spc);
+      int cb = 1;
+      while (cb < need) cb <<= 1;
+      if (cb > 16 || (cb > 8 && !np_ok)) continue;
+      ResPlan rp;
+      rp.valid = 0; rp.bt = bt; rp.ncta = cb;
+      rp.cap_pp = cap_of(P.Hpp, spc, cb); rp.cap_pl = cap_of(P.Hpl, spc, cb); rp.cap_lp = cap_of(P.Hlp, spc, cb);
+      rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
+      rp.bytes = (int)res_offsets(rp).total;
+      if (rp.bytes > 224 * 1024) continue;
+      if (cudaFuncSetAttribute(k_pcg_res, cudaFuncAttributeMaxDynamicSharedMemorySize, rp.bytes) != cudaSuccess) { cudaGetLastError(); continue; }
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cb);
+      cfg.blockDim = dim3(bt);
+      cfg.dynamicSmemBytes = (size_t)rp.bytes;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cb;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_res, &cfg) == cudaSuccess && nclusters >= 1) {
+        rp.valid = 1;
+        h->res = rp;
+        break;
+      }
+      cudaGetLastError();
+    }
+    if (prof) std::fprintf(stderr, "[sgb_set_graph] resident solve: %s (%d CTAs x %d threads, %d bytes of shared memory)\n",
+                           h->res.valid ? "yes" : "no", h->res.ncta, h->res.bt, h->res.bytes);
   }
   SGB_CUDA(cudaStreamSynchronize(h->stream));
   lap("matrices+sync");

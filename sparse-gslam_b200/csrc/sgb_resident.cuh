@@ -1,0 +1,294 @@
+// sgb_resident.cuh -- the PCG solve for a graph that fits ONE thread-block cluster, with everything on chip.
+//
+// A small graph (the growing landmark graph the reference re-optimises once per key-frame, drone.cpp:146-156; the
+// intel-lab-sized graphs of BASELINE config 1) is latency-bound: with the matrices in L2 a PCG iteration is three
+// barriers plus three chains of dependent L2 round trips (index -> gather -> multiply), ~10 us, and an optimize(15) of
+// a 300-pose graph runs ~2000 such iterations. Here the cluster keeps, for the whole solve,
+//   * every CTA's own rows of Hpp / Hpl (pose-major) and its own slices of Hlp (landmark-major) in shared memory
+//     (column indices and block values: they are constant during a solve),
+//   * a full copy of the two vectors the operator gathers from -- the preconditioned residual z and t = W Hlp^T z --
+//     in the shared memory of EVERY CTA: the thread that produces an entry stores it into all copies through
+//     distributed shared memory, so every gather is a local shared-memory read,
+//   * the per-row state (x, r, d, s) in registers of the thread that owns the row, the row's preconditioner rows in the
+//     shared memory of its CTA,
+// and synchronises with the hardware cluster barrier. Nothing but the final x travels to global memory.
+// One thread owns one pose row, one warp one slice of the landmark-major matrix (the host sizes the cluster for that).
+// The arithmetic per row is that of sgb_rows.h (same expressions, same order of the blocks).
+#pragma once
+#include "sgb_kernels.cuh"
+
+namespace sgb {
+
+struct ResPlan {   // host-computed, the same for every CTA of the launch
+  int valid;
+  int bt;          // threads = pose rows per CTA (multiple of 32)
+  int ncta;        // cluster size
+  int cap_pp, cap_pl, cap_lp;  // SELL entries of the largest per-CTA share
+  int nz, nt;      // doubles of the replicated vectors z (3 per pose) and t (2 per landmark), padded to even
+  int bytes;       // dynamic shared memory per CTA
+};
+
+// byte offsets inside the dynamic shared memory (doubles first, then floats, then ints: natural alignment)
+struct ResOffsets {
+  size_t vpp, vpl, vlp, z, t, cinv, cpp, cpl, clp, total;
+};
+__host__ __device__ inline ResOffsets res_offsets(const ResPlan& p) {
+  ResOffsets o;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t r = off; off += (bytes + 15) & ~(size_t)15; return r; };
+  o.vpp = take((size_t)p.cap_pp * 9 * 8);
+  o.vpl = take((size_t)p.cap_pl * 6 * 8);
+  o.vlp = take((size_t)p.cap_lp * 6 * 8);
+  o.z = take((size_t)p.nz * 8);
+  o.t = take((size_t)p.nt * 8);
+  o.cinv = take((size_t)p.bt * 9 * 16);
+  o.cpp = take((size_t)p.cap_pp * 4);
+  o.cpl = take((size_t)p.cap_pl * 4);
+  o.clp = take((size_t)p.cap_lp * 4);
+  o.total = off;
+  return o;
+}
+
+#if defined(__CUDACC__)
+// z_i = sum_j Cinv_ij r_j with the row's nine float4 in shared memory (layout [q][row of the CTA])
+__device__ __forceinline__ double precond_row_res(const float4* cinv_s, int bt, int lr, bool active, const double r[3], double z[3]) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned base = lane & ~(unsigned)(kChunk - 1);
+  const unsigned mask = ((1u << kChunk) - 1u) << base;
+  double rr[3 * kChunk];
+#pragma unroll
+  for (int j = 0; j < kChunk; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) rr[3 * j + c] = __shfl_sync(mask, r[c], (int)(base + j));
+  z[0] = z[1] = z[2] = 0.0;
+  if (!active) return 0.0;
+  constexpr int N = 3 * kChunk;
+  float ci[3 * N];
+#pragma unroll
+  for (int q = 0; q < (3 * N) / 4; ++q) {
+    const float4 v = cinv_s[q * bt + lr];
+    ci[4 * q] = v.x; ci[4 * q + 1] = v.y; ci[4 * q + 2] = v.z; ci[4 * q + 3] = v.w;
+  }
+#pragma unroll
+  for (int rrow = 0; rrow < 3; ++rrow) {
+    double acc = 0.0;
+#pragma unroll
+    for (int c = 0; c < N; ++c) acc += (double)ci[rrow * N + c] * rr[c];
+    z[rrow] = acc;
+  }
+  const int a = (int)(lane & (kChunk - 1));
+  return rr[3 * a] * z[0] + rr[3 * a + 1] * z[1] + rr[3 * a + 2] * z[2];
+}
+
+// cooperative copy global -> shared by the whole CTA
+template <class T>
+__device__ __forceinline__ void stage_copy(T* dst, const T* src, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
+// The whole solve of one damped system on a single GPU, launched as ONE cluster of rp.ncta CTAs of rp.bt threads with
+// rp.bytes of dynamic shared memory. Same recurrences, same scalars and the same exit flags as pcg_solve (sgb_kernels.cuh).
+__global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
+  namespace cg = cooperative_groups;
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  __shared__ double sm[32];
+  __shared__ double cl_part[4];
+  __shared__ int s_last;
+  cg::cluster_group cl = cg::this_cluster();
+  const ResOffsets of = res_offsets(rp);
+  double* vpp = reinterpret_cast<double*>(res_smem + of.vpp);
+  double* vpl = reinterpret_cast<double*>(res_smem + of.vpl);
+  double* vlp = reinterpret_cast<double*>(res_smem + of.vlp);
+  double* z_s = reinterpret_cast<double*>(res_smem + of.z);
+  double* t_s = reinterpret_cast<double*>(res_smem + of.t);
+  float4* cinv_s = reinterpret_cast<float4*>(res_smem + of.cinv);
+  int32_t* cpp = reinterpret_cast<int32_t*>(res_smem + of.cpp);
+  int32_t* cpl = reinterpret_cast<int32_t*>(res_smem + of.cpl);
+  int32_t* clp = reinterpret_cast<int32_t*>(res_smem + of.clp);
+
+  const int bt = rp.bt, ncta = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int spc = bt >> 5;  // 32-row slices per CTA
+  const bool has_pl = g.Hpl.rows > 0;
+  // ---- this CTA's share of the matrices -> shared memory
+  const int ns_p = g.Hpp.nslices;
+  const int sp0 = min(ns_p, cta * spc), sp1 = min(ns_p, (cta + 1) * spc);
+  const int e0pp = g.Hpp.sbase[sp0], npp = g.Hpp.sbase[sp1] - e0pp;
+  const int e0pl = has_pl ? g.Hpl.sbase[sp0] : 0, npl = has_pl ? g.Hpl.sbase[sp1] - e0pl : 0;
+  const int ns_l = g.Hlp.nslices;
+  const int sl0 = min(ns_l, cta * spc), sl1 = min(ns_l, (cta + 1) * spc);
+  const int e0lp = ns_l > 0 ? g.Hlp.sbase[sl0] : 0, nlp = ns_l > 0 ? g.Hlp.sbase[sl1] - e0lp : 0;
+  stage_copy(cpp, g.Hpp.col + e0pp, npp);
+  stage_copy(vpp, g.Hpp.vals + (size_t)e0pp * 9, npp * 9);
+  if (has_pl) {
+    stage_copy(cpl, g.Hpl.col + e0pl, npl);
+    stage_copy(vpl, g.Hpl.vals + (size_t)e0pl * 6, npl * 6);
+  }
+  if (nlp > 0) {
+    stage_copy(clp, g.Hlp.col + e0lp, nlp);
+    stage_copy(vlp, g.Hlp.vals + (size_t)e0lp * 6, nlp * 6);
+  }
+  const int row0 = cta * bt;
+  const int lr = (int)threadIdx.x, lp = row0 + lr;
+  const bool act = lp < g.nP;
+  if (act) {
+    const float4* cg4 = reinterpret_cast<const float4*>(g.Cinv);
+#pragma unroll
+    for (int q = 0; q < 9; ++q) cinv_s[q * bt + lr] = cg4[(size_t)q * g.nP + lp];
+  }
+  // ---- per-thread constants of the solve
+  const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
+  const int slice = lp >> 5, lane = lp & 31;
+  int wpp = 0, bpp = 0, wpl = 0, bpl = 0;
+  if (act) {
+    wpp = sell_width(g.Hpp, slice);
+    bpp = g.Hpp.sbase[slice] - e0pp + lane;
+    if (has_pl) {
+      wpl = sell_width(g.Hpl, slice);
+      bpl = g.Hpl.sbase[slice] - e0pl + lane;
+    }
+  }
+  // landmark-major slice of this warp
+  const int wsl = cta * spc + (lr >> 5);
+  const bool has_slice = wsl < ns_l;
+  int lm_e = 0, lm_steps = 0, lm_sh = 0, lm_row = 0;
+  bool lm_writer = false;
+  double w11 = 0.0, w12 = 0.0, w22 = 0.0;
+  if (has_slice) {
+    lm_e = g.Hlp.sbase[wsl] - e0lp + (lr & 31);
+    lm_steps = (g.Hlp.sbase[wsl + 1] - g.Hlp.sbase[wsl]) >> 5;
+    lm_sh = g.Hlp.sshift[wsl];
+    lm_row = g.Hlp.srow[wsl] + ((lr & 31) >> (5 - lm_sh));
+    lm_writer = ((lr & 31) & ((32 >> lm_sh) - 1)) == 0 && lm_row < g.Hlp.srow[wsl + 1];
+    if (lm_writer) {
+      const double* W = g.Hll_inv[g.rank];
+      w11 = W[lm_row];
+      w12 = W[(size_t)g.capL + lm_row];
+      w22 = W[2 * (size_t)g.capL + lm_row];
+    }
+  }
+  unsigned long long seq = sc->xseq, epoch = 0;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sc);  // non-NULL marker only: never dereferenced on the cluster path
+  double* part = nullptr;
+
+  // ---- x = 0, r = bt, z = M^-1 r, d = s = 0
+  double x[3] = {0.0, 0.0, 0.0}, r[3] = {0.0, 0.0, 0.0}, d[3] = {0.0, 0.0, 0.0}, s[3] = {0.0, 0.0, 0.0}, z[3];
+  if (act)
+    for (int c = 0; c < 3; ++c) r[c] = g.bt[3 * (size_t)lp + c];
+  __syncthreads();  // cinv_s of the chunk-mates is complete
+  double acc = precond_row_res(cinv_s, bt, lr, act, r, z);
+  cl.sync();  // nobody writes into another CTA's shared memory before that CTA has started
+  if (act)
+    for (int rk = 0; rk < ncta; ++rk) {
+      double* zr = cl.map_shared_rank(z_s, rk) + 3 * lp;
+      zr[0] = z[0]; zr[1] = z[1]; zr[2] = z[2];
+    }
+  double gam = block_sum(acc, sm);
+  grid_xreduce(g, bar, (unsigned)ncta, epoch, seq, part, &gam, 1, sm, &s_last, cl_part);  // also: every copy of z is complete
+  const double gam0 = gam, target = prm.tol * prm.tol * gam0;
+  double gam_old = 0.0, alpha_old = 0.0;
+  int it = 0, flag = 1;
+  if (!(gam0 > 0.0)) {
+    flag = (gam0 == 0.0) ? 0 : 2;
+  } else {
+    while (true) {
+      if (!(gam == gam)) { flag = 2; break; }
+      if (gam <= target) { flag = 0; break; }
+      if (it >= prm.maxit) break;
+      const double beta = it == 0 ? 0.0 : gam / gam_old;
+      // ---- phase A: t = W Hlp^T z, this warp's slice
+      if (ns_l > 0) {
+        if (has_slice) {
+          double u0 = 0.0, u1 = 0.0;
+          for (int j = 0; j < lm_steps; ++j) {
+            const int e = lm_e + 32 * j;
+            const int col = clp[e];
+            if (col >= 0) {
+              const double* pv = z_s + 3 * (col & kLocalMask);
+              const double* pa = vlp + (size_t)(e & ~31) * 6 + (e & 31);
+              const double v0 = pv[0], v1 = pv[1], v2 = pv[2];
+              u0 += pa[0] * v0 + pa[64] * v1 + pa[128] * v2;
+              u1 += pa[32] * v0 + pa[96] * v1 + pa[160] * v2;
+            }
+          }
+          lm_group_sum(lm_sh, u0, u1);
+          if (lm_writer) {
+            const double t0 = w11 * u0 + w12 * u1, t1 = w12 * u0 + w22 * u1;
+            for (int rk = 0; rk < ncta; ++rk) {
+              double* tr = cl.map_shared_rank(t_s, rk) + 2 * lm_row;
+              tr[0] = t0;
+              tr[1] = t1;
+            }
+          }
+        }
+        grid_xreduce(g, bar, (unsigned)ncta, epoch, seq, part, nullptr, 0, sm, &s_last, cl_part);  // every copy of t is complete
+      }
+      // ---- phase B: w = (Hpp + lambda) z - Hpl t, delta = z.w, d = z + beta d, s = w + beta s
+      acc = 0.0;
+      if (act) {
+        const double vi0 = z[0], vi1 = z[1], vi2 = z[2];  // this row's z is still in registers
+        double q0 = lambda * vi0, q1 = lambda * vi1, q2 = lambda * vi2;
+        for (int k = 0; k < wpp; ++k) {
+          const int e = bpp + 32 * k;
+          const int col = cpp[e];
+          if (col < 0) continue;
+          const double* pv = z_s + 3 * (col & kLocalMask);
+          const double* pa = vpp + (size_t)(e & ~31) * 9 + (e & 31);
+          const double v0 = pv[0], v1 = pv[1], v2 = pv[2];
+          q0 += pa[0] * v0 + pa[32] * v1 + pa[64] * v2;
+          q1 += pa[96] * v0 + pa[128] * v1 + pa[160] * v2;
+          q2 += pa[192] * v0 + pa[224] * v1 + pa[256] * v2;
+        }
+        for (int k = 0; k < wpl; ++k) {
+          const int e = bpl + 32 * k;
+          const int col = cpl[e];
+          if (col < 0) continue;
+          const double* pt = t_s + 2 * (col & kLocalMask);
+          const double* pa = vpl + (size_t)(e & ~31) * 6 + (e & 31);
+          const double t0 = pt[0], t1 = pt[1];
+          q0 -= pa[0] * t0 + pa[32] * t1;
+          q1 -= pa[64] * t0 + pa[96] * t1;
+          q2 -= pa[128] * t0 + pa[160] * t1;
+        }
+        d[0] = vi0 + beta * d[0]; d[1] = vi1 + beta * d[1]; d[2] = vi2 + beta * d[2];
+        s[0] = q0 + beta * s[0]; s[1] = q1 + beta * s[1]; s[2] = q2 + beta * s[2];
+        acc = vi0 * q0 + vi1 * q1 + vi2 * q2;
+      }
+      double del = block_sum(acc, sm);
+      grid_xreduce(g, bar, (unsigned)ncta, epoch, seq, part, &del, 1, sm, &s_last, cl_part);
+      const double denom = it == 0 ? del : del - beta * gam / alpha_old;
+      if (!(denom > 0.0)) { flag = 2; break; }
+      const double alpha = gam / denom;
+      // ---- phase C: x += alpha d, r -= alpha s, z = M^-1 r, gamma = r.z; the new z goes into every CTA's copy
+      if (act)
+        for (int c = 0; c < 3; ++c) {
+          x[c] += alpha * d[c];
+          r[c] -= alpha * s[c];
+        }
+      acc = precond_row_res(cinv_s, bt, lr, act, r, z);
+      if (act)
+        for (int rk = 0; rk < ncta; ++rk) {
+          double* zr = cl.map_shared_rank(z_s, rk) + 3 * lp;
+          zr[0] = z[0]; zr[1] = z[1]; zr[2] = z[2];
+        }
+      ++it;
+      gam_old = gam;
+      alpha_old = alpha;
+      gam = block_sum(acc, sm);
+      grid_xreduce(g, bar, (unsigned)ncta, epoch, seq, part, &gam, 1, sm, &s_last, cl_part);  // every copy of z is complete
+    }
+  }
+  if (act)
+    for (int c = 0; c < 3; ++c) g.x_p[g.rank][3 * (size_t)lp + c] = x[c];
+  if (lp == 0) {
+    sc->xseq = seq;
+    sc->rz0 = gam0;
+    sc->rz = gam;
+    sc->pcg_iters = it;
+    sc->pcg_flag = flag;
+    sc->pcg_rel = gam0 > 0.0 ? sqrt(fabs(gam) / gam0) : 0.0;
+  }
+  cl.sync();  // no CTA may exit while another one can still write into (or read from) its shared memory
+}
+#endif
+
+}  // namespace sgb

@@ -32,8 +32,8 @@ LM_ITERS = 15         # drone.cpp:150,155
 
 def chi2_quantile(q: float, dof: int) -> float:
     """boost::math::quantile(chi_squared(dof), q)"""
-    from scipy.stats import chi2
-    return float(chi2.ppf(q, dof))
+    from scipy.special import chdtri   # the inverse survival function scipy.stats.chi2.ppf wraps, without its argument checks
+    return float(chdtri(dof, 1.0 - q))
 
 
 @dataclass
@@ -131,61 +131,105 @@ class FrameLog:
     seconds: float
 
 
+class _Grow:
+    """Append-only 2-D array with amortised O(1) appends (the deques of `LandmarkGraph`, graphs.h:15-27)."""
+
+    def __init__(self, cols, dtype):
+        self.a = np.zeros((64, cols), dtype)
+        self.n = 0
+
+    def append(self, row):
+        if self.n == len(self.a):
+            self.a = np.concatenate([self.a, np.zeros_like(self.a)])
+        self.a[self.n] = row
+        self.n += 1
+
+    def truncate(self, n):
+        self.n = n
+
+    def view(self):
+        return self.a[:self.n]
+
+
 class LandmarkGraphSession:
     """Host-side `LandmarkGraph` + the per-key-frame protocol of `Drone::msgCallback`."""
 
     def __init__(self, backend, quantile: float = GATE_QUANTILE, iters: int = LM_ITERS):
         self.backend = backend
         self.quantile, self.iters = quantile, iters
-        self.pose_est = np.zeros((0, 3))
-        self.lm_est = np.zeros((0, 2))
+        self._pose = _Grow(3, np.float64)
+        self._lm = _Grow(2, np.float64)
         self.lm_key: list[int] = []              # landmark array index -> stream key
         self.key_lm: dict[int, int] = {}
-        self.pp = dict(i=[], j=[], z=[], info=[], seq=[])
-        self.pl = dict(p=[], l=[], z=[], info=[], seq=[])
+        # edges: index columns, values, insertion rank
+        self._pp_ij, self._pp_z, self._pp_info, self._pp_seq = _Grow(2, np.int32), _Grow(3, np.float64), _Grow(6, np.float64), _Grow(1, np.int64)
+        self._pl_pl, self._pl_z, self._pl_info, self._pl_seq = _Grow(2, np.int32), _Grow(2, np.float64), _Grow(3, np.float64), _Grow(1, np.int64)
         self.seq = 0
         self.need_reinit = True
         self.log: list[FrameLog] = []
 
+    @property
+    def pp(self):
+        """pose-pose (odometry) edges so far, insertion order"""
+        ij = self._pp_ij.view()
+        return dict(i=ij[:, 0], j=ij[:, 1], z=self._pp_z.view(), info=self._pp_info.view(), seq=self._pp_seq.view()[:, 0])
+
+    @property
+    def pl(self):
+        """pose-line edges so far, insertion order"""
+        pl = self._pl_pl.view()
+        return dict(p=pl[:, 0], l=pl[:, 1], z=self._pl_z.view(), info=self._pl_info.view(), seq=self._pl_seq.view()[:, 0])
+
+    @property
+    def pose_est(self):
+        return self._pose.view()
+
+    @property
+    def lm_est(self):
+        return self._lm.view()
+
     # -- graph assembly (drone.cpp:115-143, 193-246)
     def graph(self) -> gg.Graph:
-        P, L = len(self.pose_est), len(self.lm_est)
+        P, L = self._pose.n, self._lm.n
         fixed = np.zeros(P, np.uint8)
         if P:
             fixed[0] = 1                          # first pose fixed (drone.cpp:66)
-        f64 = np.float64
+        ij, pl = self._pp_ij.view(), self._pl_pl.view()
+        c = np.ascontiguousarray
         return gg.Graph(
-            name="landmark-graph", pose_id=np.arange(P, dtype=np.int32), pose_est=self.pose_est.copy(), pose_fixed=fixed,
-            pose_gt=np.full((P, 3), np.nan), lm_id=(10_000_000 + np.arange(L)).astype(np.int32), lm_est=self.lm_est.copy(),
-            lm_fixed=np.zeros(L, np.uint8), lm_gt=np.full((L, 2), np.nan),
-            pp_i=np.asarray(self.pp["i"], np.int32), pp_j=np.asarray(self.pp["j"], np.int32),
-            pp_z=np.asarray(self.pp["z"], f64).reshape(-1, 3), pp_info=np.asarray(self.pp["info"], f64).reshape(-1, 6),
-            pp_phi=np.zeros(len(self.pp["i"])), pp_seq=np.asarray(self.pp["seq"], np.int64),
-            pl_pose=np.asarray(self.pl["p"], np.int32), pl_lm=np.asarray(self.pl["l"], np.int32),
-            pl_z=np.asarray(self.pl["z"], f64).reshape(-1, 2), pl_info=np.asarray(self.pl["info"], f64).reshape(-1, 3),
-            pl_seq=np.asarray(self.pl["seq"], np.int64))
+            name="landmark-graph", pose_id=np.arange(P, dtype=np.int32), pose_est=self._pose.view().copy(), pose_fixed=fixed,
+            pose_gt=None, lm_id=np.arange(10_000_000, 10_000_000 + L, dtype=np.int32), lm_est=self._lm.view().copy(),
+            lm_fixed=np.zeros(L, np.uint8), lm_gt=None,
+            pp_i=c(ij[:, 0]), pp_j=c(ij[:, 1]), pp_z=self._pp_z.view(), pp_info=self._pp_info.view(),
+            pp_phi=np.zeros(len(ij)), pp_seq=self._pp_seq.view()[:, 0],
+            pl_pose=c(pl[:, 0]), pl_lm=c(pl[:, 1]), pl_z=self._pl_z.view(), pl_info=self._pl_info.view(),
+            pl_seq=self._pl_seq.view()[:, 0])
 
     def add_keyframe(self, kf: KeyFrame) -> FrameLog:
         t0 = time.perf_counter()
-        p = len(self.pose_est)
-        self.pose_est = np.vstack([self.pose_est, kf.pose_init[None, :]])
+        p = self._pose.n
+        self._pose.append(kf.pose_init)
         if kf.odom_z is not None and p > 0:
-            for key, v in zip(("i", "j", "z", "info", "seq"), (p - 1, p, kf.odom_z, kf.odom_info, self.seq)):
-                self.pp[key].append(v)
+            self._pp_ij.append((p - 1, p))
+            self._pp_z.append(kf.odom_z)
+            self._pp_info.append(kf.odom_info)
+            self._pp_seq.append(self.seq)
             self.seq += 1
-        first_new_edge, first_new_lm = len(self.pl["p"]), len(self.lm_est)
+        first_new_edge, first_new_lm = self._pl_pl.n, self._lm.n
         for key_, z, info, init in zip(kf.obs_lm, kf.obs_z, kf.obs_info, kf.obs_init):
             key_ = int(key_)
             if key_ not in self.key_lm:               # mergeLine found no match: new landmark (drone.cpp:236-247)
-                self.key_lm[key_] = len(self.lm_est)
+                self.key_lm[key_] = self._lm.n
                 self.lm_key.append(key_)
-                self.lm_est = np.vstack([self.lm_est, init[None, :]])
-            for k2, v in zip(("p", "l", "z", "info", "seq"), (p, self.key_lm[key_], z, info, self.seq)):
-                self.pl[k2].append(v)
+                self._lm.append(init)
+            self._pl_pl.append((p, self.key_lm[key_]))
+            self._pl_z.append(z)
+            self._pl_info.append(info)
+            self._pl_seq.append(self.seq)
             self.seq += 1
-        n_edges = len(self.pp["i"]) + len(self.pl["p"])
-        if n_edges == 0:                              # nothing to optimise yet (first key-frame without segments)
-            rec = FrameLog(p, True, 0, 0.0, 0, 0.0, p + 1, len(self.lm_est), 0, time.perf_counter() - t0)
+        n_pp, n_pl = self._pp_ij.n, self._pl_pl.n
+        if n_pp + n_pl == 0:                          # nothing to optimise yet (first key-frame without segments)
+            rec = FrameLog(p, True, 0, 0.0, 0, 0.0, p + 1, self._lm.n, 0, time.perf_counter() - t0)
             self.log.append(rec)
             return rec
         g = self.graph()
@@ -197,31 +241,32 @@ class LandmarkGraphSession:
             self.backend.push()
             iters = self.backend.optimize(self.iters, online)
         self.need_reinit = False
-        dof = 3 * len(self.pp["i"]) + 2 * len(self.pl["p"])   # sum of the active edges' dimensions
+        dof = 3 * n_pp + 2 * n_pl                     # sum of the active edges' dimensions
         chi2 = self.backend.active_chi2() if ok else 0.0
         gate = chi2_quantile(self.quantile, dof)
         accepted = not (chi2 > gate)
         if not accepted:
             # reject the data association of this key-frame: drop its pose-line edges and the landmarks they created,
             # restore the estimates, re-initialise next time (drone.cpp:168-181)
-            for k2 in self.pl:
-                del self.pl[k2][first_new_edge:]
+            for a in (self._pl_pl, self._pl_z, self._pl_info, self._pl_seq):
+                a.truncate(first_new_edge)
             for key_ in self.lm_key[first_new_lm:]:
                 del self.key_lm[key_]
             del self.lm_key[first_new_lm:]
             if ok:
                 self.backend.pop()
                 pe, le = self.backend.estimates()
-                self.pose_est = pe
-                self.lm_est = le[:first_new_lm]
-            else:
-                self.lm_est = self.lm_est[:first_new_lm]
+                self._pose.view()[:] = pe
+                self._lm.view()[:first_new_lm] = le[:first_new_lm]
+            self._lm.truncate(first_new_lm)
             self.need_reinit = True
         elif ok:
             self.backend.discard_top()
-            self.pose_est, self.lm_est = self.backend.estimates()
-        rec = FrameLog(p, accepted, iters, chi2, dof, gate, len(self.pose_est), len(self.lm_est),
-                       len(self.pp["i"]) + len(self.pl["p"]), time.perf_counter() - t0)
+            pe, le = self.backend.estimates()
+            self._pose.view()[:] = pe
+            self._lm.view()[:] = le
+        rec = FrameLog(p, accepted, iters, chi2, dof, gate, self._pose.n, self._lm.n, self._pp_ij.n + self._pl_pl.n,
+                       time.perf_counter() - t0)
         self.log.append(rec)
         return rec
 

@@ -158,8 +158,9 @@ def test_lm15_final_state_parity(name, jac):
         np.testing.assert_allclose(b["chi2"], a["chi2"], rtol=1e-6)
         # lambda's update factor 1-(2 rho-1)^3 uses rho = (chi - chi_new)/scale, a ratio of two vanishing numbers once
         # chi2 has stopped moving; compare it only while an iteration still changes chi2 noticeably
+        # (g2o-numeric mode: rho inherits the ~1e-7 Jacobian noise of the central differences, amplified by the cube)
         if (a["chi2_before"] - a["chi2"]) > 1e-3 * a["chi2"]:
-            np.testing.assert_allclose(b["lambda_"], a["lambda_"], rtol=1e-4)
+            np.testing.assert_allclose(b["lambda_"], a["lambda_"], rtol=1e-3 if jac == capi.JAC_G2O_NUMERIC else 1e-4)
     po, lo = o.estimates()
     pg, lg = opt.estimates()
     # analytic mode: 1e-6 relative (north_star), no exceptions. g2o-numeric mode: 1e-6, or 3x the band inside which the
