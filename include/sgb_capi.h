@@ -57,7 +57,8 @@ typedef struct sgb_options {
   double lm_tau;            /* lambda0 = tau * max|diag H|; <=0 -> 1e-5 (g2o default) */
   double lm_user_lambda;    /* >0 overrides lambda0 (g2o userLambdaInit) */
   int32_t lm_max_trials;    /* <=0 -> 10 (g2o maxTrialsAfterFailure) */
-  int32_t reserved;
+  int32_t incremental;      /* != 0: the handle keeps what sgb_update_graph needs (an index mirror of the graph on the host
+                             * and the raw edge values on the device); 0 (default): sgb_set_graph keeps nothing of the caller's */
 } sgb_options;
 
 /* Host SoA graph. Edges reference vertices by ARRAY INDEX; ids only define g2o's vertex
@@ -163,6 +164,40 @@ const char* sgb_last_error(const sgb_handle* h);
  * builds g2o's index mapping (active vertices sorted by id, fixed -> -1) and block
  * structure on the host, the symbolic scatter map, and uploads everything. */
 sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g);
+/* SparseOptimizer::updateInitialization(vset, eset) + OptimizationAlgorithm::updateStructure (the online path the
+ * reference takes once per accepted key-frame, drone.cpp:152-156: `updateInitialization(new_vset, new_eset); push();
+ * optimize(15, true)`): extends the graph of the last sgb_set_graph / sgb_update_graph by NEW vertices and NEW edges.
+ * Only the delta crosses the boundary: the estimates of the existing vertices stay what they are on the device (the
+ * result of the previous optimize()), the values of the existing edges are already there, the new ones are appended
+ * in insertion order; the symbolic maps are re-derived on the host from the handle's index mirror and the values are
+ * gathered on the device. New vertices are numbered after the existing ones (array index = old count + position);
+ * edge endpoints index the extended arrays. Hessian indices follow the reference's batch rule (active vertices by id)
+ * -- g2o itself appends new vertices in pointer order, which no two runs reproduce. Needs sgb_options.incremental.
+ * Any backup of sgb_push is dropped (the reference pushes after updateInitialization). Single GPU. */
+typedef struct sgb_graph_delta {
+  int32_t n_new_poses;
+  const int32_t* pose_id;    /* NULL: id = array index */
+  const double* pose_est;    /* [3*n_new_poses] */
+  const uint8_t* pose_fixed; /* NULL: none */
+  int32_t n_new_landmarks;
+  const int32_t* lm_id;      /* NULL: id = 10000000 + array index */
+  const double* lm_est;      /* [2*n_new_landmarks] */
+  const uint8_t* lm_fixed;
+  int32_t n_new_pp;
+  const int32_t* pp_i;       /* array indices into the EXTENDED vertex arrays */
+  const int32_t* pp_j;
+  const double* pp_z;
+  const double* pp_info;
+  const double* pp_phi;      /* NULL = no robust kernel */
+  const int64_t* pp_seq;     /* insertion rank; NULL = after every existing edge, pose-pose before pose-line */
+  int32_t n_new_pl;
+  const int32_t* pl_pose;
+  const int32_t* pl_lm;
+  const double* pl_z;
+  const double* pl_info;
+  const int64_t* pl_seq;
+} sgb_graph_delta;
+sgb_status sgb_update_graph(sgb_handle* h, const sgb_graph_delta* d);
 /* Multi-GPU, one process per GPU: every rank passes the SAME whole graph; rank r keeps the free-pose rows
  * [r*ceil(Pf/world), ...) of the reduced system and the landmarks first observed from them. Afterwards the ranks
  * exchange sgb_comm_get_handle() blobs (64 bytes each, e.g. with torch.distributed.all_gather) and call

@@ -181,6 +181,57 @@ int main(int argc, char** argv) {
     }
   }
   opt.discardTop();
+  // ---- the online path of drone.cpp:152-156: two more key-frames arrive; updateInitialization(new vertices, new edges);
+  // push(); optimize(15, true). Only the new vertices and edges travel to the device (sgb_update_graph).
+  for (int step = 0; step < 2; ++step) {
+    g2o::HyperGraph::VertexSet vset;
+    g2o::HyperGraph::EdgeSet eset;
+    const int k = (int)poses.size();
+    poses.emplace_back();
+    poses.back().setId(k);
+    poses.back().setEstimate(poses[k - 1].estimate() * g2o::SE2(0.5, 0.0, 0.0));
+    opt.addVertex(&poses.back());
+    vset.insert(&poses.back());
+    odom.emplace_back();
+    odom.back().vertices()[0] = &poses[k - 1];
+    odom.back().vertices()[1] = &poses[k];
+    odom.back().setMeasurement(g2o::SE2(0.5 + 0.02 * n01(rng), 0.02 * n01(rng), 0.01 * n01(rng)));
+    odom.back().information()(0, 0) = 2500; odom.back().information()(1, 1) = 2500; odom.back().information()(2, 2) = 10000;
+    opt.addEdge(&odom.back());
+    eset.insert(&odom.back());
+    edge_log.emplace_back(0, (int)odom.size() - 1);
+    for (int l = 0; l < 2; ++l) {
+      obs.emplace_back();
+      obs.back().vertices()[0] = &poses[k];
+      obs.back().vertices()[1] = &lms[l];
+      g2o::Vector2 z;
+      z[0] = (l == 0 ? 2.0 : 25.0 - 0.5 * k) + 0.03 * n01(rng);
+      z[1] = walls[l][1] + 0.02 * n01(rng);
+      obs.back().setMeasurement(z);
+      obs.back().information()(0, 0) = 1111; obs.back().information()(1, 1) = 2500;
+      opt.addEdge(&obs.back());
+      eset.insert(&obs.back());
+      edge_log.emplace_back(1, (int)obs.size() - 1);
+    }
+    if (step == 1 && !prefix.empty()) {   // the graph the last online optimize() starts from
+      std::FILE* f = std::fopen((prefix + "_online.g2o").c_str(), "w");
+      if (!f) return 10;
+      dump_vertices(f, poses, lms);
+      for (auto& tk : edge_log) tk.first == 0 ? dump_pp(f, odom[tk.second]) : dump_pl(f, obs[tk.second]);
+      std::fclose(f);
+    }
+    if (!opt.updateInitialization(vset, eset)) return 13;
+    opt.push();
+    int non = opt.optimize(15, true);
+    opt.computeActiveErrors();
+    std::printf("online key-frame %d: optimize returned %d, chi2 = %.6f\n", k, non, opt.activeChi2());
+    if (non <= 0) return 14;
+    opt.discardTop();
+    if (step == 1 && res) {
+      std::fprintf(res, "ON ITERATIONS %d\nON CHI2 %.17g\n", non, opt.activeChi2());
+      dump_estimates(res, "ON", poses, lms);
+    }
+  }
   delete opt.algorithm();
   if (!(n > 0 && chi2_after < 400.0)) return 2;
 

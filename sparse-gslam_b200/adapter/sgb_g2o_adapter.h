@@ -15,6 +15,7 @@
 // Compiles against real g2o headers (define SGB_USE_REAL_G2O and include them first) or against
 // g2o_compat/g2o_compat.h (this repository's tests). Links libsgb.so only.
 #pragma once
+#include <algorithm>
 #include <cstdio>
 #include <unordered_map>
 #include <vector>
@@ -35,7 +36,9 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
   explicit OptimizationAlgorithmB200(int algo, const sgb_options* options = nullptr) : _algo(algo) {
     sgb_options o;
     sgb_default_options(&o);
+    o.incremental = 1;  // the landmark graph grows by updateInitialization once per key-frame (drone.cpp:152-153)
     if (options) o = *options;
+    _incremental = o.incremental != 0;
     sgb_status st = sgb_create(&o, &_h);
     if (st != SGB_OK) {
       std::fprintf(stderr, "OptimizationAlgorithmB200: sgb_create failed with status %d (no CUDA device? there is no CPU fallback)\n", (int)st);
@@ -48,12 +51,17 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
 
   // OptimizationAlgorithmWithHessian::init: here the whole symbolic phase (index mapping is the optimizer's)
   bool init(bool online = false) override {
-    (void)online;
     if (!_h || !_optimizer) return false;
 #ifndef SGB_USE_REAL_G2O
     _optimizer->setErrorEvaluator(this);
 #endif
-    return upload();
+    // online: updateStructure() has already extended the device-resident graph by the new vertices and edges
+    if (online && _extended) {
+      _extended = false;
+      return true;
+    }
+    _extended = false;
+    return upload(false);
   }
 
   SolverResult solve(int iteration, bool online = false) override {
@@ -75,9 +83,17 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
     return result == SGB_RESULT_OK ? OK : (result == SGB_RESULT_TERMINATE ? Terminate : Fail);
   }
 
+  // OptimizationAlgorithmWithHessian::updateStructure (reached from SparseOptimizer::updateInitialization, drone.cpp:153):
+  // the optimizer's active sets already contain the new vertices and edges. The active graph is flattened again on the
+  // host; when the graph the device holds is a prefix of it (the reference only ever appends: new pose, new landmarks,
+  // new edges) only the tail travels (sgb_update_graph) and the estimates of the old vertices stay on the device.
   bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) override {
-    // online path: the structure is re-derived (in insertion order) at the next init(); nothing to patch here
-    return _h != nullptr;
+    if (!_h || !_optimizer) return false;
+    _extended = false;
+    if (!_incremental || !_uploaded) return true;   // nothing resident to extend: init() uploads the whole graph
+    if (!upload(true)) return false;
+    _extended = true;
+    return true;
   }
 
   // Pure virtual in g2o::OptimizationAlgorithm (libg2o 2020.5.29, g2o/core/optimization_algorithm.h); the algorithms the
@@ -142,10 +158,15 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
   }
 
  private:
-  bool upload() {
+  // flattens the optimizer's active graph; extend == true: send only what lies beyond the graph the device holds, if that
+  // graph is a prefix of the new one (same vertices and edges in the same order), otherwise the whole graph
+  bool upload(bool extend = false) {
     const auto& verts = _optimizer->activeVertices();
     const auto& edges = _optimizer->activeEdges();
-    _poses.clear(); _lms.clear();
+    std::vector<OptimizableGraph::Vertex*> old_poses, old_lms;
+    old_poses.swap(_poses); old_lms.swap(_lms);
+    std::vector<const HyperGraph::Edge*> old_pp, old_pl;
+    old_pp.swap(_pp_edges); old_pl.swap(_pl_edges);
     std::unordered_map<const HyperGraph::Vertex*, int> pidx, lidx;
     std::vector<int32_t> pose_id, lm_id;
     std::vector<uint8_t> pose_fixed, lm_fixed;
@@ -170,6 +191,7 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
         pp_info.insert(pp_info.end(), {I(0, 0), I(0, 1), I(0, 2), I(1, 1), I(1, 2), I(2, 2)});
         pp_phi.push_back(e->robustKernel() ? e->robustKernel()->delta() : 0.0);  // the reference only uses RobustKernelDCS
         pp_seq.push_back(e->internalId());
+        _pp_edges.push_back(e);
       } else if (e->dimension() == 2) {
         auto* ee = static_cast<EdgeSE2RhoTheta*>(e);
         pl_p.push_back(pidx.at(e->vertex(0))); pl_l.push_back(lidx.at(e->vertex(1)));
@@ -178,7 +200,26 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
         const auto& I = ee->information();
         pl_info.insert(pl_info.end(), {I(0, 0), I(0, 1), I(1, 1)});
         pl_seq.push_back(e->internalId());
+        _pl_edges.push_back(e);
       } else { std::fprintf(stderr, "OptimizationAlgorithmB200: unsupported edge dimension %d\n", e->dimension()); return false; }
+    }
+    auto is_prefix = [](const auto& a, const auto& b) { return a.size() <= b.size() && std::equal(a.begin(), a.end(), b.begin()); };
+    if (extend && _uploaded && is_prefix(old_poses, _poses) && is_prefix(old_lms, _lms) && is_prefix(old_pp, _pp_edges) &&
+        is_prefix(old_pl, _pl_edges)) {
+      const size_t P0 = old_poses.size(), L0 = old_lms.size(), E0 = old_pp.size(), F0 = old_pl.size();
+      sgb_graph_delta d{};
+      d.n_new_poses = (int32_t)(_poses.size() - P0); d.pose_id = pose_id.data() + P0; d.pose_est = _pose_est.data() + 3 * P0; d.pose_fixed = pose_fixed.data() + P0;
+      d.n_new_landmarks = (int32_t)(_lms.size() - L0); d.lm_id = lm_id.data() + L0; d.lm_est = _lm_est.data() + 2 * L0; d.lm_fixed = lm_fixed.data() + L0;
+      d.n_new_pp = (int32_t)(pp_i.size() - E0); d.pp_i = pp_i.data() + E0; d.pp_j = pp_j.data() + E0; d.pp_z = pp_z.data() + 3 * E0;
+      d.pp_info = pp_info.data() + 6 * E0; d.pp_phi = pp_phi.data() + E0; d.pp_seq = pp_seq.data() + E0;
+      d.n_new_pl = (int32_t)(pl_p.size() - F0); d.pl_pose = pl_p.data() + F0; d.pl_lm = pl_l.data() + F0; d.pl_z = pl_z.data() + 2 * F0;
+      d.pl_info = pl_info.data() + 3 * F0; d.pl_seq = pl_seq.data() + F0;
+      sgb_status su = sgb_update_graph(_h, &d);
+      if (su != SGB_OK) { std::fprintf(stderr, "OptimizationAlgorithmB200::updateStructure: %s\n", sgb_last_error(_h)); return false; }
+      // the host may have moved old estimates since the last solve (pop() after a rejected key-frame): solve() re-sends them
+      _hidx_of.clear();
+      _fresh = false;
+      return true;
     }
     sgb_graph_soa g{};
     g.n_poses = (int32_t)_poses.size(); g.pose_id = pose_id.data(); g.pose_est = _pose_est.data(); g.pose_fixed = pose_fixed.data();
@@ -220,7 +261,8 @@ class OptimizationAlgorithmB200 : public OptimizationAlgorithm
 
   int _algo;
   sgb_handle* _h = nullptr;
-  bool _fresh = false, _uploaded = false;
+  bool _fresh = false, _uploaded = false, _incremental = false, _extended = false;
+  std::vector<const HyperGraph::Edge*> _pp_edges, _pl_edges;   // edges of the device-resident graph, in its order
   std::vector<OptimizableGraph::Vertex*> _poses, _lms;
   std::vector<double> _pose_est, _lm_est;
   std::unordered_map<const HyperGraph::Vertex*, int32_t> _hidx_of;

@@ -19,7 +19,7 @@ EXPORTS = [
     "sgb_get_timings", "sgb_optimize_resident", "sgb_set_graph_partitioned", "sgb_comm_get_handle", "sgb_comm_connect",
     "sgb_get_partition_info", "sgb_optimize_batch", "sgb_optimize_batch_resident", "sgb_g2o_load", "sgb_g2o_view",
     "sgb_g2o_free", "sgb_g2o_save",
-    "sgb_compute_marginals",
+    "sgb_compute_marginals", "sgb_update_graph",
     "sgb_linear_set_pattern", "sgb_linear_solve", "sgb_set_graph_device", "sgb_pg_create", "sgb_pg_destroy", "sgb_pg_last_error", "sgb_pg_reset",
     "sgb_pg_append_from_lm", "sgb_pg_append_from_host", "sgb_pg_add_closure", "sgb_pg_optimize",
     "sgb_pg_prune_closures", "sgb_pg_get_info", "sgb_pg_download",
@@ -30,7 +30,7 @@ EXPORTS = [
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("jacobian_mode", C.c_int32), ("pcg_tolerance", C.c_double),
                 ("pcg_max_iters", C.c_int32), ("verbose", C.c_int32), ("lm_tau", C.c_double),
-                ("lm_user_lambda", C.c_double), ("lm_max_trials", C.c_int32), ("reserved", C.c_int32)]
+                ("lm_user_lambda", C.c_double), ("lm_max_trials", C.c_int32), ("incremental", C.c_int32)]
 
 
 class GraphSoA(C.Structure):
@@ -42,6 +42,16 @@ class GraphSoA(C.Structure):
         ("n_pl", C.c_int32), ("pl_pose", C.c_void_p), ("pl_lm", C.c_void_p), ("pl_z", C.c_void_p),
         ("pl_info", C.c_void_p), ("pl_seq", C.c_void_p),
     ]
+
+
+class GraphDelta(C.Structure):
+    """sgb_graph_delta: the new vertices / edges of sgb_update_graph"""
+    _fields_ = [("n_new_poses", C.c_int32), ("pose_id", C.c_void_p), ("pose_est", C.c_void_p), ("pose_fixed", C.c_void_p),
+                ("n_new_landmarks", C.c_int32), ("lm_id", C.c_void_p), ("lm_est", C.c_void_p), ("lm_fixed", C.c_void_p),
+                ("n_new_pp", C.c_int32), ("pp_i", C.c_void_p), ("pp_j", C.c_void_p), ("pp_z", C.c_void_p),
+                ("pp_info", C.c_void_p), ("pp_phi", C.c_void_p), ("pp_seq", C.c_void_p),
+                ("n_new_pl", C.c_int32), ("pl_pose", C.c_void_p), ("pl_lm", C.c_void_p), ("pl_z", C.c_void_p),
+                ("pl_info", C.c_void_p), ("pl_seq", C.c_void_p)]
 
 
 class IterStat(C.Structure):
@@ -146,6 +156,7 @@ def load() -> C.CDLL:
     L.sgb_linear_set_pattern.argtypes = [vp, C.POINTER(BlockMatrix)]
     L.sgb_linear_solve.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int32), C.POINTER(C.c_double)]
     L.sgb_compute_marginals.argtypes = [vp, C.c_int32, vp, vp, vp]
+    L.sgb_update_graph.argtypes = [vp, C.POINTER(GraphDelta)]
     L.sgb_set_graph_device.argtypes = [vp, C.POINTER(GraphSoA), C.POINTER(DeviceValues)]
     L.sgb_pg_create.argtypes = [C.c_int32, C.POINTER(vp)]
     L.sgb_pg_destroy.argtypes = [vp]

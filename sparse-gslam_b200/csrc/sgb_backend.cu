@@ -107,6 +107,19 @@ struct sgb_handle {
     const int32_t *d_off = nullptr, *d_e1 = nullptr, *d_e2 = nullptr, *d_kind = nullptr, *d_lmg = nullptr;
     double *d_vals = nullptr, *d_b = nullptr;
   } lin;
+  // ---- the online path (sgb_update_graph, opt.incremental): index mirror of the graph on the host, raw values on the
+  // device in grow-only arrays of their own (the pooled memory is recycled by every re-planning)
+  struct Online {
+    bool valid = false;
+    std::vector<int32_t> pose_id, lm_id, pp_i, pp_j, pl_pose, pl_lm;
+    std::vector<uint8_t> pose_fixed, lm_fixed;
+    std::vector<int64_t> pp_seq, pl_seq;
+    int64_t next_seq = 0;
+    bool any_phi = false;
+    double *d_pose = nullptr, *d_lm = nullptr, *d_pp_z = nullptr, *d_pp_info = nullptr, *d_pp_phi = nullptr, *d_pl_z = nullptr,
+           *d_pl_info = nullptr;
+    size_t cap_pose = 0, cap_lm = 0, cap_pp = 0, cap_pl = 0;  // in vertices / edges
+  } on;
   sgb_timings tm;
   PhaseEvents ev;
   bool lm_state_valid = false;
@@ -483,6 +496,8 @@ sgb_status do_optimize(sgb_handle* h, int algo, int max_iters, int* iters_done, 
 
 extern "C" {
 
+static void online_free(sgb_handle* h);
+
 const char* sgb_version(void) { return "sparse-gslam_b200 0.1 (sm_100a)"; }
 
 int32_t sgb_device_count(void) {
@@ -569,6 +584,7 @@ void sgb_destroy(sgb_handle* h) {
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   free_graph(h);
+  online_free(h);
   close_peers(h);
   if (h->arena_raw) cudaFree(h->arena_raw);
   for (auto& sl : h->slabs) cudaFree(sl.base);
@@ -1009,7 +1025,146 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   return SGB_OK;
 }
 
-sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g) { return set_graph_impl(h, g, 1, 0); }
+// grow-only device array of the online store: keeps the first `keep` elements when it has to move
+static sgb_status online_reserve(sgb_handle* h, double** p, size_t* cap, size_t need, size_t width, size_t keep) {
+  if (need <= *cap) return SGB_OK;
+  size_t ncap = std::max(need + need / 2, (size_t)256);
+  double* q = nullptr;
+  SGB_CUDA(cudaMalloc((void**)&q, ncap * width * sizeof(double)));
+  if (*p && keep) SGB_CUDA(cudaMemcpyAsync(q, *p, keep * width * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (*p) {
+    SGB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(*p);
+  }
+  *p = q;
+  *cap = ncap;
+  return SGB_OK;
+}
+static void online_free(sgb_handle* h) {
+  auto& O = h->on;
+  for (double** p : {&O.d_pose, &O.d_lm, &O.d_pp_z, &O.d_pp_info, &O.d_pp_phi, &O.d_pl_z, &O.d_pl_info}) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+  }
+  O = sgb_handle::Online();
+}
+// (re-)plans the graph held by the online store: host symbolic phase on the index mirror, values gathered on the device
+static sgb_status online_replan(sgb_handle* h) {
+  auto& O = h->on;
+  sgb_graph_soa g;
+  std::memset(&g, 0, sizeof g);
+  g.n_poses = (int32_t)O.pose_id.size(); g.pose_id = O.pose_id.data(); g.pose_fixed = O.pose_fixed.data();
+  g.n_landmarks = (int32_t)O.lm_id.size(); g.lm_id = O.lm_id.data(); g.lm_fixed = O.lm_fixed.data();
+  g.n_pp = (int32_t)O.pp_i.size(); g.pp_i = O.pp_i.data(); g.pp_j = O.pp_j.data(); g.pp_seq = O.pp_seq.data();
+  g.n_pl = (int32_t)O.pl_pose.size(); g.pl_pose = O.pl_pose.data(); g.pl_lm = O.pl_lm.data(); g.pl_seq = O.pl_seq.data();
+  sgb_device_values dv;
+  std::memset(&dv, 0, sizeof dv);
+  dv.pose_est = O.d_pose; dv.lm_est = O.d_lm;
+  dv.pp_z = O.d_pp_z; dv.pp_info = O.d_pp_info; dv.pp_phi = O.d_pp_phi;
+  dv.pl_z = O.d_pl_z; dv.pl_info = O.d_pl_info;
+  dv.has_robust = O.any_phi ? 1 : 0;
+  return set_graph_impl(h, &g, 1, 0, &dv);
+}
+// appends vertices / edges to the store: index mirror on the host, values to the device arrays (H2D of the delta only)
+static sgb_status online_append(sgb_handle* h, const sgb_graph_delta* d) {
+  auto& O = h->on;
+  const size_t P0 = O.pose_id.size(), L0 = O.lm_id.size(), E0 = O.pp_i.size(), F0 = O.pl_pose.size();
+  const size_t nP = (size_t)d->n_new_poses, nL = (size_t)d->n_new_landmarks, nE = (size_t)d->n_new_pp, nF = (size_t)d->n_new_pl;
+  if ((nP && !d->pose_est) || (nL && !d->lm_est) || (nE && (!d->pp_i || !d->pp_j || !d->pp_z || !d->pp_info)) ||
+      (nF && (!d->pl_pose || !d->pl_lm || !d->pl_z || !d->pl_info))) {
+    h->err = "graph delta with missing arrays";
+    return SGB_ERR_INVALID;
+  }
+  for (size_t k = 0; k < nE; ++k)
+    if (d->pp_i[k] < 0 || d->pp_j[k] < 0 || (size_t)d->pp_i[k] >= P0 + nP || (size_t)d->pp_j[k] >= P0 + nP) { h->err = "graph delta: pose-pose edge with a bad vertex index"; return SGB_ERR_INVALID; }
+  for (size_t k = 0; k < nF; ++k)
+    if (d->pl_pose[k] < 0 || d->pl_lm[k] < 0 || (size_t)d->pl_pose[k] >= P0 + nP || (size_t)d->pl_lm[k] >= L0 + nL) { h->err = "graph delta: pose-line edge with a bad vertex index"; return SGB_ERR_INVALID; }
+  sgb_status st;
+  if ((st = online_reserve(h, &O.d_pose, &O.cap_pose, P0 + nP, 3, P0)) != SGB_OK) return st;
+  if ((st = online_reserve(h, &O.d_lm, &O.cap_lm, L0 + nL, 2, L0)) != SGB_OK) return st;
+  { size_t c1 = O.cap_pp, c2 = O.cap_pp, c3 = O.cap_pp;
+    if ((st = online_reserve(h, &O.d_pp_z, &c1, E0 + nE, 3, E0)) != SGB_OK) return st;
+    if ((st = online_reserve(h, &O.d_pp_info, &c2, E0 + nE, 6, E0)) != SGB_OK) return st;
+    if ((st = online_reserve(h, &O.d_pp_phi, &c3, E0 + nE, 1, E0)) != SGB_OK) return st;
+    O.cap_pp = c1; }
+  { size_t c1 = O.cap_pl, c2 = O.cap_pl;
+    if ((st = online_reserve(h, &O.d_pl_z, &c1, F0 + nF, 2, F0)) != SGB_OK) return st;
+    if ((st = online_reserve(h, &O.d_pl_info, &c2, F0 + nF, 3, F0)) != SGB_OK) return st;
+    O.cap_pl = c1; }
+  if (nP && (st = h2d(h, O.d_pose + 3 * P0, d->pose_est, 3 * nP * sizeof(double))) != SGB_OK) return st;
+  if (nL && (st = h2d(h, O.d_lm + 2 * L0, d->lm_est, 2 * nL * sizeof(double))) != SGB_OK) return st;
+  if (nE) {
+    if ((st = h2d(h, O.d_pp_z + 3 * E0, d->pp_z, 3 * nE * sizeof(double))) != SGB_OK) return st;
+    if ((st = h2d(h, O.d_pp_info + 6 * E0, d->pp_info, 6 * nE * sizeof(double))) != SGB_OK) return st;
+    if (d->pp_phi) { if ((st = h2d(h, O.d_pp_phi + E0, d->pp_phi, nE * sizeof(double))) != SGB_OK) return st; }
+    else SGB_CUDA(cudaMemsetAsync(O.d_pp_phi + E0, 0, nE * sizeof(double), h->stream));
+  }
+  if (nF) {
+    if ((st = h2d(h, O.d_pl_z + 2 * F0, d->pl_z, 2 * nF * sizeof(double))) != SGB_OK) return st;
+    if ((st = h2d(h, O.d_pl_info + 3 * F0, d->pl_info, 3 * nF * sizeof(double))) != SGB_OK) return st;
+  }
+  SGB_CUDA(cudaStreamSynchronize(h->stream));  // the caller may free its arrays when the call returns
+  for (size_t i = 0; i < nP; ++i) { O.pose_id.push_back(d->pose_id ? d->pose_id[i] : (int32_t)(P0 + i)); O.pose_fixed.push_back(d->pose_fixed ? d->pose_fixed[i] : 0); }
+  for (size_t i = 0; i < nL; ++i) { O.lm_id.push_back(d->lm_id ? d->lm_id[i] : (int32_t)(10000000 + L0 + i)); O.lm_fixed.push_back(d->lm_fixed ? d->lm_fixed[i] : 0); }
+  for (size_t k = 0; k < nE; ++k) {
+    O.pp_i.push_back(d->pp_i[k]); O.pp_j.push_back(d->pp_j[k]);
+    O.pp_seq.push_back(d->pp_seq ? d->pp_seq[k] : O.next_seq + (int64_t)k);
+    if (d->pp_phi && d->pp_phi[k] > 0.0) O.any_phi = true;
+  }
+  for (size_t k = 0; k < nF; ++k) {
+    O.pl_pose.push_back(d->pl_pose[k]); O.pl_lm.push_back(d->pl_lm[k]);
+    O.pl_seq.push_back(d->pl_seq ? d->pl_seq[k] : O.next_seq + (int64_t)(nE + k));
+  }
+  for (size_t k = 0; k < nE; ++k) O.next_seq = std::max(O.next_seq, O.pp_seq[E0 + k] + 1);
+  for (size_t k = 0; k < nF; ++k) O.next_seq = std::max(O.next_seq, O.pl_seq[F0 + k] + 1);
+  return SGB_OK;
+}
+
+sgb_status sgb_set_graph(sgb_handle* h, const sgb_graph_soa* g) {
+  if (!h || !g) return SGB_ERR_INVALID;
+  if (!h->opt.incremental) return set_graph_impl(h, g, 1, 0);
+  // incremental handle: the graph goes into the online store first, then it is planned from there
+  SGB_CUDA(cudaSetDevice(h->device));
+  SGB_CUDA(cudaStreamSynchronize(h->stream));
+  auto& O = h->on;
+  O.pose_id.clear(); O.lm_id.clear(); O.pp_i.clear(); O.pp_j.clear(); O.pl_pose.clear(); O.pl_lm.clear();
+  O.pose_fixed.clear(); O.lm_fixed.clear(); O.pp_seq.clear(); O.pl_seq.clear();
+  O.next_seq = 0; O.any_phi = false; O.valid = false;
+  sgb_graph_delta d;
+  std::memset(&d, 0, sizeof d);
+  d.n_new_poses = g->n_poses; d.pose_id = g->pose_id; d.pose_est = g->pose_est; d.pose_fixed = g->pose_fixed;
+  d.n_new_landmarks = g->n_landmarks; d.lm_id = g->lm_id; d.lm_est = g->lm_est; d.lm_fixed = g->lm_fixed;
+  d.n_new_pp = g->n_pp; d.pp_i = g->pp_i; d.pp_j = g->pp_j; d.pp_z = g->pp_z; d.pp_info = g->pp_info; d.pp_phi = g->pp_phi; d.pp_seq = g->pp_seq;
+  d.n_new_pl = g->n_pl; d.pl_pose = g->pl_pose; d.pl_lm = g->pl_lm; d.pl_z = g->pl_z; d.pl_info = g->pl_info; d.pl_seq = g->pl_seq;
+  // sgb_graph_soa's default insertion rank: pose-pose edges in array order, then the pose-line edges
+  std::vector<int64_t> seq_pp, seq_pl;
+  if (!g->pp_seq) { seq_pp.resize(std::max(0, g->n_pp)); for (int k = 0; k < g->n_pp; ++k) seq_pp[k] = k; d.pp_seq = seq_pp.data(); }
+  if (!g->pl_seq) { seq_pl.resize(std::max(0, g->n_pl)); for (int k = 0; k < g->n_pl; ++k) seq_pl[k] = (int64_t)g->n_pp + k; d.pl_seq = seq_pl.data(); }
+  if (g->n_poses < 0 || g->n_landmarks < 0 || g->n_pp < 0 || g->n_pl < 0) { h->err = "negative size"; return SGB_ERR_INVALID; }
+  sgb_status st = online_append(h, &d);
+  if (st != SGB_OK) return st;
+  if ((st = online_replan(h)) != SGB_OK) return st;
+  O.valid = true;
+  return SGB_OK;
+}
+
+sgb_status sgb_update_graph(sgb_handle* h, const sgb_graph_delta* d) {
+  if (!h || !d) return SGB_ERR_INVALID;
+  if (!h->opt.incremental) { h->err = "sgb_update_graph needs a handle created with sgb_options.incremental != 0"; return SGB_ERR_UNSUPPORTED; }
+  if (!h->has_graph || !h->on.valid) { h->err = "sgb_update_graph: no graph to extend (call sgb_set_graph first)"; return SGB_ERR_NOT_INITIALIZED; }
+  if (d->n_new_poses < 0 || d->n_new_landmarks < 0 || d->n_new_pp < 0 || d->n_new_pl < 0) { h->err = "negative size"; return SGB_ERR_INVALID; }
+  SGB_CUDA(cudaSetDevice(h->device));
+  auto& O = h->on;
+  // the estimates of the existing vertices are the ones on the device: move them into the store before the pooled
+  // memory that holds them is recycled by the re-planning
+  const size_t P0 = O.pose_id.size(), L0 = O.lm_id.size();
+  const DevGraph& G = h->G;
+  if (P0) SGB_CUDA(cudaMemcpyAsync(O.d_pose, G.pose_buf[G.cur][G.rank], 3 * P0 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  if (L0) SGB_CUDA(cudaMemcpyAsync(O.d_lm, G.lm_buf[G.cur][G.rank], 2 * L0 * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+  sgb_status st = online_append(h, d);
+  if (st != SGB_OK) return st;
+  return online_replan(h);
+}
 
 sgb_status sgb_set_graph_device(sgb_handle* h, const sgb_graph_soa* indices, const sgb_device_values* dv) {
   if (!h || !indices || !dv) return SGB_ERR_INVALID;

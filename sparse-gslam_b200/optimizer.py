@@ -61,7 +61,7 @@ class SparseOptimizerB200:
     """One optimiser handle = one of the reference's two graphs (LandmarkGraph.opt / PoseGraph.opt, graphs.h:19-40)."""
 
     def __init__(self, algo=capi.ALGO_LM, jacobian_mode=capi.JAC_G2O_NUMERIC, pcg_tolerance=1e-10, pcg_max_iters=0,
-                 device=-1, lm_user_lambda=0.0):
+                 device=-1, lm_user_lambda=0.0, incremental=False):
         self.L = capi.load()
         if self.L.sgb_device_count() <= 0:
             raise SgbError(capi.ERR_NO_DEVICE, "no CUDA device: the backend has no CPU path")
@@ -72,6 +72,7 @@ class SparseOptimizerB200:
         opt.pcg_tolerance = pcg_tolerance
         opt.pcg_max_iters = pcg_max_iters
         opt.lm_user_lambda = lm_user_lambda
+        opt.incremental = int(bool(incremental))
         self.algo = algo
         self.h = C.c_void_p()
         st = self.L.sgb_create(C.byref(opt), C.byref(self.h))
@@ -104,6 +105,33 @@ class SparseOptimizerB200:
         self._check(st)
         self.g = g
         self.P, self.Lm = s.n_poses, s.n_landmarks
+        return True
+
+    def update_initialization(self, g, n_new_poses, n_new_landmarks, n_new_pp, n_new_pl) -> bool:
+        """g2o: updateInitialization(new vertices, new edges) (drone.cpp:152-153). `g` is the EXTENDED graph whose last
+        n_new_* vertices / edges are new; only those cross the boundary (sgb_update_graph), the estimates of the
+        existing vertices stay what they are on the device. Needs incremental=True at construction."""
+        def tail(a, n, dt):
+            a = np.ascontiguousarray(a[len(a) - n:], dtype=dt)
+            return a
+
+        P, Lm, E, F = len(g.pose_est), len(g.lm_est), len(g.pp_i), len(g.pl_pose)
+        keep = [tail(g.pose_id, n_new_poses, np.int32), tail(g.pose_est, n_new_poses, np.float64), tail(g.pose_fixed, n_new_poses, np.uint8),
+                tail(g.lm_id, n_new_landmarks, np.int32), tail(g.lm_est, n_new_landmarks, np.float64), tail(g.lm_fixed, n_new_landmarks, np.uint8),
+                tail(g.pp_i, n_new_pp, np.int32), tail(g.pp_j, n_new_pp, np.int32), tail(g.pp_z, n_new_pp, np.float64),
+                tail(g.pp_info, n_new_pp, np.float64), tail(g.pp_phi, n_new_pp, np.float64), tail(g.pp_seq, n_new_pp, np.int64),
+                tail(g.pl_pose, n_new_pl, np.int32), tail(g.pl_lm, n_new_pl, np.int32), tail(g.pl_z, n_new_pl, np.float64),
+                tail(g.pl_info, n_new_pl, np.float64), tail(g.pl_seq, n_new_pl, np.int64)]
+        d = capi.GraphDelta()
+        d.n_new_poses, d.n_new_landmarks, d.n_new_pp, d.n_new_pl = n_new_poses, n_new_landmarks, n_new_pp, n_new_pl
+        (d.pose_id, d.pose_est, d.pose_fixed, d.lm_id, d.lm_est, d.lm_fixed, d.pp_i, d.pp_j, d.pp_z, d.pp_info, d.pp_phi,
+         d.pp_seq, d.pl_pose, d.pl_lm, d.pl_z, d.pl_info, d.pl_seq) = [_p(a) for a in keep]
+        st = self.L.sgb_update_graph(self.h, C.byref(d))
+        if st == capi.ERR_NOT_INITIALIZED:
+            return False
+        self._check(st)
+        self.g = g
+        self.P, self.Lm = P, Lm
         return True
 
     def initialize_optimization_device(self, g, dev, pp_slot=None, pl_slot=None, has_robust=None) -> bool:

@@ -77,9 +77,10 @@ class GpuBackend:
     """The product path: one sgb handle, estimates resident on the device between the calls of one key-frame.
     `prof` accumulates the wall time of every protocol call and the device-side counters of optimize()."""
 
-    def __init__(self, jacobian_mode=capi.JAC_G2O_NUMERIC, device=-1):
+    def __init__(self, jacobian_mode=capi.JAC_G2O_NUMERIC, device=-1, incremental=True):
         from .optimizer import SparseOptimizerB200
-        self.opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=jacobian_mode, device=device)
+        self.incremental = incremental
+        self.opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=jacobian_mode, device=device, incremental=incremental)
         self.prof = dict(initialize_s=0.0, push_s=0.0, optimize_s=0.0, chi2_s=0.0, pop_discard_s=0.0, estimates_s=0.0,
                          device_ms=0.0, pcg_iters=0, trials=0, kernel_launches=0, calls=0)
 
@@ -90,6 +91,11 @@ class GpuBackend:
         return r
 
     def initialize(self, g, online=False, n_new_poses=0, n_new_landmarks=0, n_new_pp=0, n_new_pl=0) -> bool:
+        """initializeOptimization() (online == False: the whole graph from host buffers) or updateInitialization(new
+        vertices, new edges) (online: only the delta crosses the boundary, drone.cpp:152-153)."""
+        if online and self.incremental:
+            self.prof["online_updates"] = self.prof.get("online_updates", 0) + 1
+            return self._timed("initialize_s", self.opt.update_initialization, g, n_new_poses, n_new_landmarks, n_new_pp, n_new_pl)
         return self._timed("initialize_s", self.opt.initialize_optimization, g)
 
     def push(self):
@@ -166,6 +172,9 @@ class LandmarkGraphSession:
         self._pl_pl, self._pl_z, self._pl_info, self._pl_seq = _Grow(2, np.int32), _Grow(2, np.float64), _Grow(3, np.float64), _Grow(1, np.int64)
         self.seq = 0
         self.need_reinit = True
+        self._planned = (0, 0, 0, 0)             # vertices / edges of the graph the backend holds
+        import inspect
+        self._backend_online = "online" in inspect.signature(backend.initialize).parameters
         self.log: list[FrameLog] = []
 
     @property
@@ -235,7 +244,13 @@ class LandmarkGraphSession:
         g = self.graph()
         # initializeOptimization() / updateInitialization(new_vset, new_eset); push(); optimize(15, online)
         online = not self.need_reinit
-        ok = self.backend.initialize(g)
+        if self._backend_online:
+            ok = self.backend.initialize(g, online=online, n_new_poses=self._pose.n - self._planned[0],
+                                         n_new_landmarks=self._lm.n - self._planned[1], n_new_pp=n_pp - self._planned[2],
+                                         n_new_pl=n_pl - self._planned[3])
+        else:   # a backend that only knows initializeOptimization (the oracle arm of the tests / bench)
+            ok = self.backend.initialize(g)
+        self._planned = (self._pose.n, self._lm.n, n_pp, n_pl)   # what the backend's graph holds now
         iters = 0
         if ok:
             self.backend.push()

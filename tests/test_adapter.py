@@ -30,7 +30,7 @@ def test_adapter_compiles_and_fails_loudly_without_gpu():
 
 
 def _parse_result(path):
-    out = {"LM": {"POSE": {}, "LINE": {}}, "GN": {"POSE": {}, "LINE": {}}, "MARGINAL": []}
+    out = {"LM": {"POSE": {}, "LINE": {}}, "GN": {"POSE": {}, "LINE": {}}, "ON": {"POSE": {}, "LINE": {}}, "MARGINAL": []}
     for ln in open(path):
         f = ln.split()
         if f[0] == "MARGINAL":
@@ -84,6 +84,23 @@ def test_adapter_matches_oracle_on_the_reference_call_sequence(tmp_path):
         blk = vals.reshape(dim[c_], dim[r_]).T   # column-major
         ref = Hinv[off[r_]:off[r_] + dim[r_], off[c_]:off[c_] + dim[c_]]
         assert np.abs(blk - ref).max() <= 1e-5 * np.abs(ref).max(), (r_, c_, blk, ref)
+    # ---- the online path (updateInitialization + optimize(15, true), drone.cpp:152-156): the oracle optimises the dumped
+    # extended graph from the same estimates with a full initializeOptimization
+    assert "online key-frame" in r.stdout
+    gon = gg.load_g2o(prefix + "_online.g2o")
+    assert gon.P == g.P + 2 and len(gon.pl_pose) == len(g.pl_pose) + 4
+    oo = Oracle(gon)
+    assert oo.initialize_optimization()
+    n_on, _ = oo.optimize(15, ALGO_LM, JAC_G2O_NUMERIC)
+    assert n_on >= 1 and res["ON"]["ITERATIONS"] >= 1
+    pon, lon = oo.estimates()
+    pa2 = np.array([res["ON"]["POSE"][int(i)] for i in gon.pose_id])
+    la2 = np.array([res["ON"]["LINE"][int(i)] for i in gon.lm_id])
+    d = pa2 - pon
+    d[:, 2] = gg.wrap(d[:, 2])
+    assert np.abs(d).max() / max(1.0, float(np.abs(pon[:, :2]).max())) < 1e-6, np.abs(d).max()
+    assert np.abs(la2 - lon).max() / max(1.0, float(np.abs(lon).max())) < 1e-6
+    assert abs(res["ON"]["CHI2"] - oo.chi2()[0]) <= 1e-6 * oo.chi2()[0]
     # ---- pose graph, GN-20 + DCS
     gp = gg.load_g2o(prefix + "_pose.g2o")
     assert (gp.pp_phi > 0).sum() == 3 and float(gp.pp_phi.max()) == 0.75

@@ -81,3 +81,62 @@ def test_gpu_session_matches_oracle_session(jac_gpu, jac_cpu, tol):
     d[:, 2] = gg.wrap(d[:, 2])
     assert np.abs(d).max() / scale < tol
     assert np.abs(gpu.lm_est - ref.lm_est).max() / max(1.0, float(np.abs(ref.lm_est).max())) < tol
+
+
+@pytest.mark.gpu
+def test_online_update_equals_full_reinitialisation():
+    """sgb_update_graph (updateInitialization, drone.cpp:152-153): extending the device-resident graph by the new
+    key-frames' vertices and edges gives exactly what a full initializeOptimization of the extended graph gives when it
+    starts from the same estimates -- same structure, same values, so the same LM trajectory bit for bit -- and the
+    session takes that path for every accepted key-frame."""
+    from sparse_gslam_b200 import SparseOptimizerB200
+    g, frames = _stream(corrupt=False)
+    s = LandmarkGraphSession(OracleBackend(JAC_ANALYTIC))   # only used to assemble the graphs of key-frames 0..k
+    s.run(frames[:20])
+    ga = s.graph()
+    counts_a = (len(ga.pose_est), len(ga.lm_est), len(ga.pp_i), len(ga.pl_pose))
+    a = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC, incremental=True)
+    assert a.initialize_optimization(ga)
+    a.optimize(15)
+    pa, la = a.estimates()
+    # five more key-frames appended on the host side without optimising in between
+    s2 = LandmarkGraphSession(OracleBackend(JAC_ANALYTIC))
+    s2.run(frames[:20])
+    class _NoOpt(OracleBackend):
+        def initialize(self, g):
+            self.g = g
+            return False
+    s2.backend = _NoOpt()
+    s2._backend_online = False
+    for kf in frames[20:25]:
+        s2.add_keyframe(kf)
+    gb = s2.graph()
+    nb = (len(gb.pose_est), len(gb.lm_est), len(gb.pp_i), len(gb.pl_pose))
+    new = tuple(y - x for x, y in zip(counts_a, nb))
+    assert all(n > 0 for n in (new[0], new[2], new[3]))
+    # the extended graph starts from the optimised estimates of the old vertices
+    gb.pose_est[:counts_a[0]] = pa
+    gb.lm_est[:counts_a[1]] = la
+    assert a.update_initialization(gb, *new)
+    a.push()
+    n_on, st_on = a.optimize(15, online=True)
+    p_on, l_on = a.estimates()
+    full = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
+    assert full.initialize_optimization(gb)
+    n_full, st_full = full.optimize(15)
+    p_full, l_full = full.estimates()
+    assert n_on == n_full and [x["trials"] for x in st_on] == [x["trials"] for x in st_full]
+    np.testing.assert_array_equal(p_on, p_full)
+    np.testing.assert_array_equal(l_on, l_full)
+    assert np.array_equal(a.structure()["row"], full.structure()["row"])
+    a.pop()                                   # the caller protocol keeps working on the extended graph
+    p_back, _ = a.estimates()
+    np.testing.assert_array_equal(p_back[:counts_a[0]], pa)
+    # a handle without the option refuses, with a message
+    from sparse_gslam_b200 import SgbError
+    with pytest.raises(SgbError):
+        full.update_initialization(gb, 0, 0, 0, 0)
+    # the session uses the online path for every accepted key-frame after the first
+    be = GpuBackend(jacobian_mode=capi.JAC_ANALYTIC)
+    LandmarkGraphSession(be).run(frames[:12])
+    assert be.prof.get("online_updates", 0) >= 9
