@@ -98,6 +98,7 @@ struct sgb_handle {
   bool no_small = std::getenv("SGB_NO_SMALL") != nullptr;  // tuning runs: always the throughput build of k_pcg
   int pcg_cluster = 0;  // > 0: the PCG grid is one thread-block cluster of this many CTAs (small graph, one GPU)
   ResPlan res;          // valid: the graph fits one cluster's shared memory -> the cluster-resident solve (sgb_resident.cuh)
+  ResPlan res_block;    // valid: the graph fits ONE 256-thread CTA -> the resident solve inside the batched kernel
   // LinearSolver-level entry (sgb_linear_set_pattern / sgb_linear_solve): per input block its value offset, kind and
   // the SELL entries it lands in; device copies live in the pooled memory of the current graph
   struct LinearMap {
@@ -308,7 +309,12 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   prm.lambda_override = lambda_override;
   prm.use_override = use_override;
   SGB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), h->stream));
-  if (h->res.valid) {
+  static const bool no_res1 = std::getenv("SGB_NO_RESIDENT1") != nullptr;
+  if (h->res_block.valid && G.world == 1 && !no_res1) {  // the whole graph in ONE CTA: block barriers only
+    ResPlan rp = h->res_block;
+    k_pcg_res1<<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+    SGB_CUDA(cudaGetLastError());
+  } else if (h->res.valid) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(h->res.ncta);
     cfg.blockDim = dim3(h->res.bt);
@@ -993,6 +999,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
       rp.valid = 0; rp.bt = bt; rp.ncta = cb;
       rp.cap_pp = cap_of(P.Hpp, spc, cb); rp.cap_pl = cap_of(P.Hpl, spc, cb); rp.cap_lp = cap_of(P.Hlp, spc, cb);
       rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
+      rp.cap_sl = spc; rp.cap_lr = 32 * spc;  // a slice holds at most 32 landmark rows
       rp.bytes = (int)res_offsets(rp).total;
       if (rp.bytes > 224 * 1024) continue;
       if (cudaFuncSetAttribute(k_pcg_res, cudaFuncAttributeMaxDynamicSharedMemorySize, rp.bytes) != cudaSuccess) { cudaGetLastError(); continue; }
@@ -1012,6 +1019,22 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
         rp.valid = 1;
         h->res = rp;
         break;
+      }
+      cudaGetLastError();
+    }
+    {  // the same question for one 256-thread CTA (sgb_optimize_batch: one graph per CTA)
+      h->res_block = ResPlan();
+      ResPlan rp;
+      rp.valid = 0; rp.bt = kThreads; rp.ncta = 1;
+      rp.cap_pp = cap_of(P.Hpp, kThreads / 32, 1); rp.cap_pl = cap_of(P.Hpl, kThreads / 32, 1);
+      rp.cap_lp = (int)P.Hlp.entries();  // a single CTA keeps every landmark-major slice
+      rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
+      rp.cap_sl = std::max(1, P.Hlp.nslices); rp.cap_lr = std::max(1, P.nL);
+      rp.bytes = (int)res_offsets(rp).total;
+      if (P.nP <= kThreads && rp.bytes <= 200 * 1024 &&
+          cudaFuncSetAttribute(k_pcg_res1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess) {
+        rp.valid = 1;
+        h->res_block = rp;
       }
       cudaGetLastError();
     }
@@ -1736,9 +1759,23 @@ static sgb_status optimize_batch_impl(sgb_handle* const* hs, int32_t n, int32_t 
     }
   }
   std::vector<BatchItem> items(n);
+  int smem_bytes = 0;
   for (int i = 0; i < n; ++i) {
     items[i].g = hs[i]->G;
     items[i].sc = hs[i]->d_sc;
+    const ResPlan& r = hs[i]->res_block;
+    items[i].res = ResPlanFwd{r.valid, r.bt, r.ncta, r.cap_pp, r.cap_pl, r.cap_lp, r.nz, r.nt, r.bytes, r.cap_sl, r.cap_lr};
+    if (r.valid) smem_bytes = std::max(smem_bytes, r.bytes);
+  }
+  static_assert(sizeof(ResPlanFwd) == sizeof(ResPlan), "ResPlanFwd mirrors ResPlan");
+  if (smem_bytes > 0) {
+    cudaError_t ea = n <= h->sm_count ? cudaFuncSetAttribute(k_lm_block<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes)
+                                      : cudaFuncSetAttribute(k_lm_block<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (ea != cudaSuccess) {  // no room: every graph takes the global-memory solve
+      cudaGetLastError();
+      smem_bytes = 0;
+      for (auto& it : items) it.res.valid = 0;
+    }
   }
   BatchItem* d_items = nullptr;
   BatchResult* d_res = nullptr;
@@ -1761,8 +1798,8 @@ static sgb_status optimize_batch_impl(sgb_handle* const* hs, int32_t n, int32_t 
   cudaError_t e = cudaMemcpyAsync(d_items, items.data(), sizeof(BatchItem) * (size_t)n, cudaMemcpyHostToDevice, s);
   if (e == cudaSuccess) e = cudaEventRecord(t0, s);
   if (e == cudaSuccess) {
-    if (n <= h->sm_count) k_lm_block<8><<<n, kThreads, 0, s>>>(d_items, prm, d_res);
-    else k_lm_block<2><<<n, kThreads, 0, s>>>(d_items, prm, d_res);
+    if (n <= h->sm_count) k_lm_block<8><<<n, kThreads, smem_bytes, s>>>(d_items, prm, d_res);
+    else k_lm_block<2><<<n, kThreads, smem_bytes, s>>>(d_items, prm, d_res);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaEventRecord(t1, s);

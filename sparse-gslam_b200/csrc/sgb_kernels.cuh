@@ -756,9 +756,13 @@ __global__ void k_gn_control(DevGraph g, DevScalars* sc) {
 // loop on the device -- linearise, damp, Schur set-up, PCG, back-substitution, update, chi2 of the trial, gain ratio
 // and lambda control -- with block barriers where the single-graph path has kernel boundaries or grid barriers. The
 // per-row bodies (sgb_rows.h), the PCG (pcg_solve) and the LM control (lm_control_update) are the very same code.
+struct ResPlanFwd {  // = ResPlan of sgb_resident.cuh (declared here so that BatchItem can carry one)
+  int valid, bt, ncta, cap_pp, cap_pl, cap_lp, nz, nt, bytes, cap_sl, cap_lr;
+};
 struct BatchItem {
   DevGraph g;
   DevScalars* sc;  // the handle's scalar block (kept coherent for later sgb_chi2 / sgb_step calls)
+  ResPlanFwd res;  // valid: the graph fits the shared memory of its CTA -> the resident solve (sgb_resident.cuh)
 };
 struct BatchParams {
   int algo, max_iters, max_trials;
@@ -772,8 +776,14 @@ struct BatchResult {
 
 // U = blocks in flight per thread in the pose-major pass: 8 when the batch has at most one graph per SM (registers are
 // free, the latency chain of a row is what counts), 2 otherwise (more resident CTAs per SM)
+// the CTA-resident solve of sgb_resident.cuh (defined there; this header is included first)
+__device__ void pcg_resident_block(const DevGraph& g, const PcgParams& prm, double lambda, const ResPlanFwd& rp,
+                                   unsigned char* res_smem, double* sm, int* s_last, unsigned long long& seq, PcgOut& out);
+
 template <int U>
 __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, BatchParams prm, BatchResult* results) {
+  extern __shared__ __align__(16) unsigned char lm_block_smem[];
+  __shared__ ResPlanFwd res;
   __shared__ DevGraph g;
   __shared__ DevScalars sc;
   __shared__ double sm[32];
@@ -789,6 +799,7 @@ __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, B
     if (threadIdx.x == 0) {
       ph_ns[0] = ph_ns[1] = ph_ns[2] = ph_ns[3] = 0;
       t_ph = 0;
+      res = items[blockIdx.x].res;
     }
   }
   __syncthreads();
@@ -832,7 +843,13 @@ __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, B
       __syncthreads();
       if (!ok) atomicAnd(&s_ok, 0);
       PcgOut po;
-      pcg_solve<U>(g, tid, nth, 1u, nullptr, nullptr, seq, pcg, lambda, sm, &s_last, ph_ns, &t_ph, po);
+      if (res.valid) {
+        __syncthreads();  // Hll_inv, bt and the preconditioner rows written above are complete
+        pcg_resident_block(g, pcg, lambda, res, lm_block_smem, sm, &s_last, seq, po);
+        __syncthreads();  // x_p is complete
+      } else {
+        pcg_solve<U>(g, tid, nth, 1u, nullptr, nullptr, seq, pcg, lambda, sm, &s_last, ph_ns, &t_ph, po);
+      }
       pcg_total += po.iters;
       pcg_all += po.iters;
       // ---- back-substitution, update into the trial (LM) or current (GN) estimates, computeScale

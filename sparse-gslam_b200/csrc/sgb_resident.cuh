@@ -26,11 +26,12 @@ struct ResPlan {   // host-computed, the same for every CTA of the launch
   int cap_pp, cap_pl, cap_lp;  // SELL entries of the largest per-CTA share
   int nz, nt;      // doubles of the replicated vectors z (3 per pose) and t (2 per landmark), padded to even
   int bytes;       // dynamic shared memory per CTA
+  int cap_sl, cap_lr;  // landmark-major slices / landmark rows of the largest per-CTA share
 };
 
 // byte offsets inside the dynamic shared memory (doubles first, then floats, then ints: natural alignment)
 struct ResOffsets {
-  size_t vpp, vpl, vlp, z, t, cinv, cpp, cpl, clp, total;
+  size_t vpp, vpl, vlp, z, t, w, cinv, cpp, cpl, clp, meta, total;
 };
 __host__ __device__ inline ResOffsets res_offsets(const ResPlan& p) {
   ResOffsets o;
@@ -41,10 +42,12 @@ __host__ __device__ inline ResOffsets res_offsets(const ResPlan& p) {
   o.vlp = take((size_t)p.cap_lp * 6 * 8);
   o.z = take((size_t)p.nz * 8);
   o.t = take((size_t)p.nt * 8);
+  o.w = take((size_t)p.cap_lr * 3 * 8);
   o.cinv = take((size_t)p.bt * 9 * 16);
   o.cpp = take((size_t)p.cap_pp * 4);
   o.cpl = take((size_t)p.cap_pl * 4);
   o.clp = take((size_t)p.cap_lp * 4);
+  o.meta = take((size_t)p.cap_sl * 5 * 4);
   o.total = off;
   return o;
 }
@@ -86,15 +89,15 @@ __device__ __forceinline__ void stage_copy(T* dst, const T* src, int n) {
   for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
 }
 
-// The whole solve of one damped system on a single GPU, launched as ONE cluster of rp.ncta CTAs of rp.bt threads with
-// rp.bytes of dynamic shared memory. Same recurrences, same scalars and the same exit flags as pcg_solve (sgb_kernels.cuh).
-__global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
+// The solve itself. CL = true: the calling grid is ONE cluster of rp.ncta CTAs (k_pcg_res); CL = false: a single CTA
+// owns the whole graph (the batched kernel k_lm_block_res: one graph per CTA), the cluster barrier becomes a block
+// barrier and "every CTA's copy" is the CTA's own. rp.bt = blockDim.x threads, rp.bytes of dynamic shared memory at
+// `res_smem`. Same recurrences, scalars and exit flags as pcg_solve (sgb_kernels.cuh). x is written to g.x_p.
+template <bool CL>
+__device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgParams& prm, const double lambda, const ResPlan& rp,
+                                                   unsigned char* res_smem, double* sm, double* cl_part, int* s_last,
+                                                   unsigned long long& seq, PcgOut& out) {
   namespace cg = cooperative_groups;
-  extern __shared__ __align__(16) unsigned char res_smem[];
-  __shared__ double sm[32];
-  __shared__ double cl_part[4];
-  __shared__ int s_last;
-  cg::cluster_group cl = cg::this_cluster();
   const ResOffsets of = res_offsets(rp);
   double* vpp = reinterpret_cast<double*>(res_smem + of.vpp);
   double* vpl = reinterpret_cast<double*>(res_smem + of.vpl);
@@ -105,8 +108,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
   int32_t* cpp = reinterpret_cast<int32_t*>(res_smem + of.cpp);
   int32_t* cpl = reinterpret_cast<int32_t*>(res_smem + of.cpl);
   int32_t* clp = reinterpret_cast<int32_t*>(res_smem + of.clp);
+  double* w_s = reinterpret_cast<double*>(res_smem + of.w);       // [3][landmark rows of this CTA's slices]: (Hll + lambda I)^-1
+  int32_t* meta_s = reinterpret_cast<int32_t*>(res_smem + of.meta);  // per slice: first entry (relative), steps, shift, first row, row end
 
-  const int bt = rp.bt, ncta = (int)gridDim.x, cta = (int)blockIdx.x;
+  const int bt = rp.bt, ncta = CL ? (int)gridDim.x : 1, cta = CL ? (int)blockIdx.x : 0;
   const int spc = bt >> 5;  // 32-row slices per CTA
   const bool has_pl = g.Hpl.rows > 0;
   // ---- this CTA's share of the matrices -> shared memory
@@ -115,7 +120,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
   const int e0pp = g.Hpp.sbase[sp0], npp = g.Hpp.sbase[sp1] - e0pp;
   const int e0pl = has_pl ? g.Hpl.sbase[sp0] : 0, npl = has_pl ? g.Hpl.sbase[sp1] - e0pl : 0;
   const int ns_l = g.Hlp.nslices;
-  const int sl0 = min(ns_l, cta * spc), sl1 = min(ns_l, (cta + 1) * spc);
+  // a cluster CTA owns as many slices as it has warps; a single CTA owns them all (its warps take them in turns)
+  const int sl0 = CL ? min(ns_l, cta * spc) : 0, sl1 = CL ? min(ns_l, (cta + 1) * spc) : ns_l;
   const int e0lp = ns_l > 0 ? g.Hlp.sbase[sl0] : 0, nlp = ns_l > 0 ? g.Hlp.sbase[sl1] - e0lp : 0;
   stage_copy(cpp, g.Hpp.col + e0pp, npp);
   stage_copy(vpp, g.Hpp.vals + (size_t)e0pp * 9, npp * 9);
@@ -136,7 +142,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
     for (int q = 0; q < 9; ++q) cinv_s[q * bt + lr] = cg4[(size_t)q * g.nP + lp];
   }
   // ---- per-thread constants of the solve
-  const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   const int slice = lp >> 5, lane = lp & 31;
   int wpp = 0, bpp = 0, wpl = 0, bpl = 0;
   if (act) {
@@ -147,43 +152,69 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
       bpl = g.Hpl.sbase[slice] - e0pl + lane;
     }
   }
-  // landmark-major slice of this warp
-  const int wsl = cta * spc + (lr >> 5);
-  const bool has_slice = wsl < ns_l;
-  int lm_e = 0, lm_steps = 0, lm_sh = 0, lm_row = 0;
-  bool lm_writer = false;
-  double w11 = 0.0, w12 = 0.0, w22 = 0.0;
-  if (has_slice) {
-    lm_e = g.Hlp.sbase[wsl] - e0lp + (lr & 31);
-    lm_steps = (g.Hlp.sbase[wsl + 1] - g.Hlp.sbase[wsl]) >> 5;
-    lm_sh = g.Hlp.sshift[wsl];
-    lm_row = g.Hlp.srow[wsl] + ((lr & 31) >> (5 - lm_sh));
-    lm_writer = ((lr & 31) & ((32 >> lm_sh) - 1)) == 0 && lm_row < g.Hlp.srow[wsl + 1];
-    if (lm_writer) {
-      const double* W = g.Hll_inv[g.rank];
-      w11 = W[lm_row];
-      w12 = W[(size_t)g.capL + lm_row];
-      w22 = W[2 * (size_t)g.capL + lm_row];
-    }
+  // descriptors of this CTA's landmark-major slices and the W of their rows -> shared memory
+  const int lrow0 = sl1 > sl0 ? g.Hlp.srow[sl0] : 0, nlrows = sl1 > sl0 ? g.Hlp.srow[sl1] - lrow0 : 0;
+  for (int q = (int)threadIdx.x; q < sl1 - sl0; q += (int)blockDim.x) {
+    const int sl = sl0 + q;
+    meta_s[5 * q] = g.Hlp.sbase[sl] - e0lp;
+    meta_s[5 * q + 1] = (g.Hlp.sbase[sl + 1] - g.Hlp.sbase[sl]) >> 5;
+    meta_s[5 * q + 2] = g.Hlp.sshift[sl];
+    meta_s[5 * q + 3] = g.Hlp.srow[sl];
+    meta_s[5 * q + 4] = g.Hlp.srow[sl + 1];
   }
-  unsigned long long seq = sc->xseq, epoch = 0;
-  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sc);  // non-NULL marker only: never dereferenced on the cluster path
-  double* part = nullptr;
+  for (int q = (int)threadIdx.x; q < nlrows; q += (int)blockDim.x) {
+    const double* W = g.Hll_inv[g.rank];
+    w_s[q] = W[lrow0 + q];
+    w_s[nlrows + q] = W[(size_t)g.capL + lrow0 + q];
+    w_s[2 * nlrows + q] = W[2 * (size_t)g.capL + lrow0 + q];
+  }
+  unsigned long long epoch = 0;
+  unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm);  // non-NULL marker only: never dereferenced on the cluster path
+  // barrier (+ all-reduce of one block-wide sum, already known to every thread of the CTA). Cluster: every CTA WRITES its
+  // partial into the slot it owns in every CTA's shared memory (DSMEM stores are fire-and-forget), one hardware cluster
+  // barrier, then every thread adds the ncta local slots in CTA order -- no remote read (215 cycles) and no block barrier
+  // after the cluster barrier. cl_part = [2][16] doubles, double-buffered by the parity of the reduction count: a slot is
+  // rewritten two reductions later, i.e. after another cluster barrier that every reader has passed.
+  auto sync_sum = [&](double* v, int nv) {
+    if (CL) {
+      cg::cluster_group cl = cg::this_cluster();
+      ++seq;
+      double* mine = cl_part + (seq & 1ull) * 16;
+      if (nv > 0 && (int)threadIdx.x < ncta) cl.map_shared_rank(mine, (int)threadIdx.x)[cta] = v[0];
+      cl.sync();
+      if (nv > 0) {
+        double acc = 0.0;
+        for (int o = 0; o < ncta; ++o) acc += mine[o];
+        v[0] = acc;
+      }
+    } else {
+      __syncthreads();
+    }
+  };
+  (void)bar; (void)epoch; (void)s_last;
+  // store into every CTA's copy of a replicated vector
+  auto put_z = [&](const double* zz) {
+    if (CL) {
+      cg::cluster_group cl = cg::this_cluster();
+      for (int rk = 0; rk < ncta; ++rk) {
+        double* zr = cl.map_shared_rank(z_s, rk) + 3 * lp;
+        zr[0] = zz[0]; zr[1] = zz[1]; zr[2] = zz[2];
+      }
+    } else {
+      z_s[3 * lp] = zz[0]; z_s[3 * lp + 1] = zz[1]; z_s[3 * lp + 2] = zz[2];
+    }
+  };
 
   // ---- x = 0, r = bt, z = M^-1 r, d = s = 0
   double x[3] = {0.0, 0.0, 0.0}, r[3] = {0.0, 0.0, 0.0}, d[3] = {0.0, 0.0, 0.0}, s[3] = {0.0, 0.0, 0.0}, z[3];
   if (act)
     for (int c = 0; c < 3; ++c) r[c] = g.bt[3 * (size_t)lp + c];
-  __syncthreads();  // cinv_s of the chunk-mates is complete
+  __syncthreads();  // the staged arrays and cinv_s of the chunk-mates are complete
   double acc = precond_row_res(cinv_s, bt, lr, act, r, z);
-  cl.sync();  // nobody writes into another CTA's shared memory before that CTA has started
-  if (act)
-    for (int rk = 0; rk < ncta; ++rk) {
-      double* zr = cl.map_shared_rank(z_s, rk) + 3 * lp;
-      zr[0] = z[0]; zr[1] = z[1]; zr[2] = z[2];
-    }
+  if (CL) cg::this_cluster().sync();  // nobody writes into another CTA's shared memory before that CTA has started
+  if (act) put_z(z);
   double gam = block_sum(acc, sm);
-  grid_xreduce(g, bar, (unsigned)ncta, epoch, seq, part, &gam, 1, sm, &s_last, cl_part);  // also: every copy of z is complete
+  sync_sum(&gam, 1);  // also: every copy of z is complete
   const double gam0 = gam, target = prm.tol * prm.tol * gam0;
   double gam_old = 0.0, alpha_old = 0.0;
   int it = 0, flag = 1;
@@ -197,7 +228,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
       const double beta = it == 0 ? 0.0 : gam / gam_old;
       // ---- phase A: t = W Hlp^T z, this warp's slice
       if (ns_l > 0) {
-        if (has_slice) {
+        for (int q = lr >> 5; q < sl1 - sl0; q += spc) {  // one slice per warp in a cluster, all slices in turns in a single CTA
+          const int lm_e = meta_s[5 * q] + (lr & 31), lm_steps = meta_s[5 * q + 1], lm_sh = meta_s[5 * q + 2];
+          const int lm_row = meta_s[5 * q + 3] + ((lr & 31) >> (5 - lm_sh));
+          const bool lm_writer = ((lr & 31) & ((32 >> lm_sh) - 1)) == 0 && lm_row < meta_s[5 * q + 4];
           double u0 = 0.0, u1 = 0.0;
           for (int j = 0; j < lm_steps; ++j) {
             const int e = lm_e + 32 * j;
@@ -212,15 +246,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
           }
           lm_group_sum(lm_sh, u0, u1);
           if (lm_writer) {
+            const double w11 = w_s[lm_row - lrow0], w12 = w_s[nlrows + lm_row - lrow0], w22 = w_s[2 * nlrows + lm_row - lrow0];
             const double t0 = w11 * u0 + w12 * u1, t1 = w12 * u0 + w22 * u1;
-            for (int rk = 0; rk < ncta; ++rk) {
-              double* tr = cl.map_shared_rank(t_s, rk) + 2 * lm_row;
-              tr[0] = t0;
-              tr[1] = t1;
+            if (CL) {
+              cg::cluster_group cl = cg::this_cluster();
+              for (int rk = 0; rk < ncta; ++rk) {
+                double* tr = cl.map_shared_rank(t_s, rk) + 2 * lm_row;
+                tr[0] = t0;
+                tr[1] = t1;
+              }
+            } else {
+              t_s[2 * lm_row] = t0;
+              t_s[2 * lm_row + 1] = t1;
             }
           }
         }
-        grid_xreduce(g, bar, (unsigned)ncta, epoch, seq, part, nullptr, 0, sm, &s_last, cl_part);  // every copy of t is complete
+        sync_sum(nullptr, 0);  // every copy of t is complete
       }
       // ---- phase B: w = (Hpp + lambda) z - Hpl t, delta = z.w, d = z + beta d, s = w + beta s
       acc = 0.0;
@@ -254,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
         acc = vi0 * q0 + vi1 * q1 + vi2 * q2;
       }
       double del = block_sum(acc, sm);
-      grid_xreduce(g, bar, (unsigned)ncta, epoch, seq, part, &del, 1, sm, &s_last, cl_part);
+      sync_sum(&del, 1);
       const double denom = it == 0 ? del : del - beta * gam / alpha_old;
       if (!(denom > 0.0)) { flag = 2; break; }
       const double alpha = gam / denom;
@@ -265,30 +306,73 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
           r[c] -= alpha * s[c];
         }
       acc = precond_row_res(cinv_s, bt, lr, act, r, z);
-      if (act)
-        for (int rk = 0; rk < ncta; ++rk) {
-          double* zr = cl.map_shared_rank(z_s, rk) + 3 * lp;
-          zr[0] = z[0]; zr[1] = z[1]; zr[2] = z[2];
-        }
+      if (act) put_z(z);
       ++it;
       gam_old = gam;
       alpha_old = alpha;
       gam = block_sum(acc, sm);
-      grid_xreduce(g, bar, (unsigned)ncta, epoch, seq, part, &gam, 1, sm, &s_last, cl_part);  // every copy of z is complete
+      sync_sum(&gam, 1);  // every copy of z is complete
     }
   }
   if (act)
     for (int c = 0; c < 3; ++c) g.x_p[g.rank][3 * (size_t)lp + c] = x[c];
-  if (lp == 0) {
-    sc->xseq = seq;
-    sc->rz0 = gam0;
-    sc->rz = gam;
-    sc->pcg_iters = it;
-    sc->pcg_flag = flag;
-    sc->pcg_rel = gam0 > 0.0 ? sqrt(fabs(gam) / gam0) : 0.0;
+  out.gam0 = gam0;
+  out.gam = gam;
+  out.iters = it;
+  out.flag = flag;
+}
+
+// the batched kernel's entry (k_lm_block, sgb_kernels.cuh): one CTA owns the whole graph
+__device__ void pcg_resident_block(const DevGraph& g, const PcgParams& prm, double lambda, const ResPlanFwd& rpf,
+                                   unsigned char* res_smem, double* sm, int* s_last, unsigned long long& seq, PcgOut& out) {
+  ResPlan rp;
+  rp.valid = rpf.valid; rp.bt = rpf.bt; rp.ncta = rpf.ncta; rp.cap_pp = rpf.cap_pp; rp.cap_pl = rpf.cap_pl; rp.cap_lp = rpf.cap_lp;
+  rp.nz = rpf.nz; rp.nt = rpf.nt; rp.bytes = rpf.bytes; rp.cap_sl = rpf.cap_sl; rp.cap_lr = rpf.cap_lr;
+  pcg_resident_solve<false>(g, prm, lambda, rp, res_smem, sm, nullptr, s_last, seq, out);
+}
+
+// One damped system of one graph, launched as ONE cluster of rp.ncta CTAs of rp.bt threads with rp.bytes of dynamic
+// shared memory (single GPU).
+__global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  __shared__ double sm[32];
+  __shared__ double cl_part[32];
+  __shared__ int s_last;
+  unsigned long long seq = 0;  // counts the reductions of this launch (parity of the partial-sum slots)
+  const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
+  PcgOut out;
+  pcg_resident_solve<true>(g, prm, lambda, rp, res_smem, sm, cl_part, &s_last, seq, out);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->rz0 = out.gam0;
+    sc->rz = out.gam;
+    sc->pcg_iters = out.iters;
+    sc->pcg_flag = out.flag;
+    sc->pcg_rel = out.gam0 > 0.0 ? sqrt(fabs(out.gam) / out.gam0) : 0.0;
   }
-  cl.sync();  // no CTA may exit while another one can still write into (or read from) its shared memory
+  cooperative_groups::this_cluster().sync();  // no CTA may exit while another one can still write into (or read from) its shared memory
 }
 #endif
 
+}  // namespace sgb
+
+namespace sgb {
+#if defined(__CUDACC__)
+// The same solve for a graph that fits ONE CTA (rows <= blockDim.x): block barriers only, no cluster.
+__global__ void __launch_bounds__(kThreads, 1) k_pcg_res1(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  __shared__ double sm[32];
+  __shared__ int s_last;
+  unsigned long long seq = 0;
+  const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
+  PcgOut out;
+  pcg_resident_solve<false>(g, prm, lambda, rp, res_smem, sm, nullptr, &s_last, seq, out);
+  if (threadIdx.x == 0) {
+    sc->rz0 = out.gam0;
+    sc->rz = out.gam;
+    sc->pcg_iters = out.iters;
+    sc->pcg_flag = out.flag;
+    sc->pcg_rel = out.gam0 > 0.0 ? sqrt(fabs(out.gam) / out.gam0) : 0.0;
+  }
+}
+#endif
 }  // namespace sgb
