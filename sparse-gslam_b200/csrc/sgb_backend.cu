@@ -99,6 +99,7 @@ struct sgb_handle {
   int pcg_cluster = 0;  // > 0: the PCG grid is one thread-block cluster of this many CTAs (small graph, one GPU)
   ResPlan res;          // valid: the graph fits one cluster's shared memory -> the cluster-resident solve (sgb_resident.cuh)
   ResPlan res_block;    // valid: the graph fits ONE 256-thread CTA -> the resident solve inside the batched kernel
+  ResPlan res4;         // valid: the resident solve with four lanes per pose row (one CTA of up to 1024 threads, or a cluster)
   // LinearSolver-level entry (sgb_linear_set_pattern / sgb_linear_solve): per input block its value offset, kind and
   // the SELL entries it lands in; device copies live in the pooled memory of the current graph
   struct LinearMap {
@@ -310,7 +311,27 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   prm.use_override = use_override;
   SGB_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned long long), h->stream));
   static const bool no_res1 = std::getenv("SGB_NO_RESIDENT1") != nullptr;
-  if (h->res_block.valid && G.world == 1 && !no_res1) {  // the whole graph in ONE CTA: block barriers only
+  if (h->res4.valid && G.world == 1) {  // four lanes per pose row, everything on chip
+    ResPlan rp = h->res4;
+    if (rp.ncta == 1) {
+      k_pcg_res4<<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+      SGB_CUDA(cudaGetLastError());
+    } else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(rp.ncta);
+      cfg.blockDim = dim3(rp.bt);
+      cfg.dynamicSmemBytes = (size_t)rp.bytes;
+      cfg.stream = h->stream;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = rp.ncta;
+      at[0].val.clusterDim.y = 1;
+      at[0].val.clusterDim.z = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4, G, sc, prm, rp));
+    }
+  } else if (h->res_block.valid && G.world == 1 && !no_res1) {  // the whole graph in ONE CTA: block barriers only
     ResPlan rp = h->res_block;
     k_pcg_res1<<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
     SGB_CUDA(cudaGetLastError());
@@ -1000,6 +1021,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
       rp.cap_pp = cap_of(P.Hpp, spc, cb); rp.cap_pl = cap_of(P.Hpl, spc, cb); rp.cap_lp = cap_of(P.Hlp, spc, cb);
       rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
       rp.cap_sl = spc; rp.cap_lr = 32 * spc;  // a slice holds at most 32 landmark rows
+      rp.rows_cta = bt;
       rp.bytes = (int)res_offsets(rp).total;
       if (rp.bytes > 224 * 1024) continue;
       if (cudaFuncSetAttribute(k_pcg_res, cudaFuncAttributeMaxDynamicSharedMemorySize, rp.bytes) != cudaSuccess) { cudaGetLastError(); continue; }
@@ -1022,6 +1044,53 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
       }
       cudaGetLastError();
     }
+    {  // four lanes per pose row: one CTA if the graph fits it, else the smallest cluster
+      h->res4 = ResPlan();
+      static const bool no_res4 = std::getenv("SGB_NO_RES4") != nullptr;
+      static const bool np4_ok = cudaFuncSetAttribute(k_pcg_res4, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      bool done4 = no_res4;
+      for (int pass = 0; pass < 2 && !done4; ++pass)        // pass 0: single CTA, pass 1: clusters
+        for (int bt : (pass == 0 ? std::initializer_list<int>{256, 512, 1024} : std::initializer_list<int>{1024, 512, 256})) {
+          const int rows_cta = bt / 4, spc_p = rows_cta / 32, spc_l = bt / 32;
+          if (spc_p < 1) continue;
+          int need = std::max((P.nP + rows_cta - 1) / rows_cta, pass == 0 ? 1 : (P.Hlp.nslices + spc_l - 1) / spc_l);
+          int cb = 1;
+          while (cb < need) cb <<= 1;
+          if ((pass == 0) != (cb == 1)) continue;
+          if (cb > 16 || (cb > 8 && !np4_ok)) continue;
+          ResPlan rp;
+          rp.valid = 0; rp.bt = bt; rp.ncta = cb; rp.rows_cta = rows_cta;
+          rp.cap_pp = cap_of(P.Hpp, spc_p, cb); rp.cap_pl = cap_of(P.Hpl, spc_p, cb);
+          rp.cap_lp = cb == 1 ? (int)P.Hlp.entries() : cap_of(P.Hlp, spc_l, cb);
+          rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
+          rp.cap_sl = cb == 1 ? std::max(1, P.Hlp.nslices) : spc_l;
+          rp.cap_lr = cb == 1 ? std::max(1, P.nL) : 32 * spc_l;
+          rp.bytes = (int)res_offsets(rp).total;
+          if (rp.bytes > 224 * 1024) continue;
+          if (cudaFuncSetAttribute(k_pcg_res4, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) { cudaGetLastError(); continue; }
+          if (cb > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cb);
+            cfg.blockDim = dim3(bt);
+            cfg.dynamicSmemBytes = (size_t)rp.bytes;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = cb;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (!(cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_res4, &cfg) == cudaSuccess && nclusters >= 1)) { cudaGetLastError(); continue; }
+          }
+          rp.valid = 1;
+          h->res4 = rp;
+          done4 = true;
+          break;
+        }
+      if (prof) std::fprintf(stderr, "[sgb_set_graph] resident solve, four lanes per row: %s (%d CTAs x %d threads, %d bytes)\n",
+                             h->res4.valid ? "yes" : "no", h->res4.ncta, h->res4.bt, h->res4.bytes);
+    }
     {  // the same question for one 256-thread CTA (sgb_optimize_batch: one graph per CTA)
       h->res_block = ResPlan();
       ResPlan rp;
@@ -1030,6 +1099,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
       rp.cap_lp = (int)P.Hlp.entries();  // a single CTA keeps every landmark-major slice
       rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
       rp.cap_sl = std::max(1, P.Hlp.nslices); rp.cap_lr = std::max(1, P.nL);
+      rp.rows_cta = kThreads;
       rp.bytes = (int)res_offsets(rp).total;
       if (P.nP <= kThreads && rp.bytes <= 200 * 1024 &&
           cudaFuncSetAttribute(k_pcg_res1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess) {
@@ -1764,7 +1834,7 @@ static sgb_status optimize_batch_impl(sgb_handle* const* hs, int32_t n, int32_t 
     items[i].g = hs[i]->G;
     items[i].sc = hs[i]->d_sc;
     const ResPlan& r = hs[i]->res_block;
-    items[i].res = ResPlanFwd{r.valid, r.bt, r.ncta, r.cap_pp, r.cap_pl, r.cap_lp, r.nz, r.nt, r.bytes, r.cap_sl, r.cap_lr};
+    items[i].res = ResPlanFwd{r.valid, r.bt, r.ncta, r.cap_pp, r.cap_pl, r.cap_lp, r.nz, r.nt, r.bytes, r.cap_sl, r.cap_lr, r.rows_cta};
     if (r.valid) smem_bytes = std::max(smem_bytes, r.bytes);
   }
   static_assert(sizeof(ResPlanFwd) == sizeof(ResPlan), "ResPlanFwd mirrors ResPlan");

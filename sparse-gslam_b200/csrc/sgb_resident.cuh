@@ -27,11 +27,12 @@ struct ResPlan {   // host-computed, the same for every CTA of the launch
   int nz, nt;      // doubles of the replicated vectors z (3 per pose) and t (2 per landmark), padded to even
   int bytes;       // dynamic shared memory per CTA
   int cap_sl, cap_lr;  // landmark-major slices / landmark rows of the largest per-CTA share
+  int rows_cta;        // pose rows per CTA: bt (one thread per row) or bt / 4 (four lanes per row)
 };
 
 // byte offsets inside the dynamic shared memory (doubles first, then floats, then ints: natural alignment)
 struct ResOffsets {
-  size_t vpp, vpl, vlp, z, t, w, cinv, cpp, cpl, clp, meta, total;
+  size_t vpp, vpl, vlp, z, t, w, rvec, cinv, cpp, cpl, clp, meta, total;
 };
 __host__ __device__ inline ResOffsets res_offsets(const ResPlan& p) {
   ResOffsets o;
@@ -43,7 +44,8 @@ __host__ __device__ inline ResOffsets res_offsets(const ResPlan& p) {
   o.z = take((size_t)p.nz * 8);
   o.t = take((size_t)p.nt * 8);
   o.w = take((size_t)p.cap_lr * 3 * 8);
-  o.cinv = take((size_t)p.bt * 9 * 16);
+  o.rvec = take((size_t)p.rows_cta * 3 * 8);
+  o.cinv = take((size_t)p.rows_cta * 9 * 16);
   o.cpp = take((size_t)p.cap_pp * 4);
   o.cpl = take((size_t)p.cap_pl * 4);
   o.clp = take((size_t)p.cap_lp * 4);
@@ -322,12 +324,246 @@ __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgP
   out.flag = flag;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Four lanes per pose row: lane c < 3 of a row's group owns COMPONENT c of the row (of x, r, d, s, z and of every product),
+// the fourth lane idles in the pose-major phases. One thread per row left the SM empty -- 7 warps for a 200-pose graph,
+// ~670 dependent instructions per warp and iteration at an IPC of 0.1 (ncu, profiles/r2_res1_stream_*) -- and every
+// product serial: here a pose-major row costs 3 instead of 9 multiply-adds per block and lane, the preconditioner 12
+// instead of 36, and a 256-row CTA runs 32 warps. rp.bt threads per CTA own rp.bt / 4 rows and rp.bt / 32 landmark slices.
+template <bool CL>
+__device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const PcgParams& prm, const double lambda, const ResPlan& rp,
+                                                    unsigned char* res_smem, double* sm, double* cl_part, unsigned long long& seq,
+                                                    PcgOut& out) {
+  namespace cg = cooperative_groups;
+  const ResOffsets of = res_offsets(rp);
+  double* vpp = reinterpret_cast<double*>(res_smem + of.vpp);
+  double* vpl = reinterpret_cast<double*>(res_smem + of.vpl);
+  double* vlp = reinterpret_cast<double*>(res_smem + of.vlp);
+  double* z_s = reinterpret_cast<double*>(res_smem + of.z);
+  double* t_s = reinterpret_cast<double*>(res_smem + of.t);
+  float4* cinv_s = reinterpret_cast<float4*>(res_smem + of.cinv);   // [9][rows of the CTA]
+  int32_t* cpp = reinterpret_cast<int32_t*>(res_smem + of.cpp);
+  int32_t* cpl = reinterpret_cast<int32_t*>(res_smem + of.cpl);
+  int32_t* clp = reinterpret_cast<int32_t*>(res_smem + of.clp);
+  double* w_s = reinterpret_cast<double*>(res_smem + of.w);
+  int32_t* meta_s = reinterpret_cast<int32_t*>(res_smem + of.meta);
+  double* r_s = reinterpret_cast<double*>(res_smem + of.rvec);      // [3 * rows of the CTA]: residual, read by the chunk-mates
+
+  const int bt = rp.bt, rows_cta = bt >> 2, ncta = CL ? (int)gridDim.x : 1, cta = CL ? (int)blockIdx.x : 0;
+  const int spc_p = rows_cta >> 5;  // pose slices per CTA
+  const int spc_l = bt >> 5;        // landmark-major slices per CTA = warps
+  const bool has_pl = g.Hpl.rows > 0;
+  const int ns_p = g.Hpp.nslices;
+  const int sp0 = min(ns_p, cta * spc_p), sp1 = min(ns_p, (cta + 1) * spc_p);
+  const int e0pp = g.Hpp.sbase[sp0], npp = g.Hpp.sbase[sp1] - e0pp;
+  const int e0pl = has_pl ? g.Hpl.sbase[sp0] : 0, npl = has_pl ? g.Hpl.sbase[sp1] - e0pl : 0;
+  const int ns_l = g.Hlp.nslices;
+  const int sl0 = CL ? min(ns_l, cta * spc_l) : 0, sl1 = CL ? min(ns_l, (cta + 1) * spc_l) : ns_l;
+  const int e0lp = ns_l > 0 ? g.Hlp.sbase[sl0] : 0, nlp = ns_l > 0 ? g.Hlp.sbase[sl1] - e0lp : 0;
+  stage_copy(cpp, g.Hpp.col + e0pp, npp);
+  stage_copy(vpp, g.Hpp.vals + (size_t)e0pp * 9, npp * 9);
+  if (has_pl) {
+    stage_copy(cpl, g.Hpl.col + e0pl, npl);
+    stage_copy(vpl, g.Hpl.vals + (size_t)e0pl * 6, npl * 6);
+  }
+  if (nlp > 0) {
+    stage_copy(clp, g.Hlp.col + e0lp, nlp);
+    stage_copy(vlp, g.Hlp.vals + (size_t)e0lp * 6, nlp * 6);
+  }
+  const int row0 = cta * rows_cta;
+  const int tid = (int)threadIdx.x;
+  const int lr = tid >> 2, c = tid & 3, lp = row0 + lr;
+  const bool rowact = lp < g.nP, act = rowact && c < 3;
+  {  // preconditioner rows of this CTA's poses: nine float4 per row, copied by the row's four lanes
+    const float4* cg4 = reinterpret_cast<const float4*>(g.Cinv);
+    if (rowact)
+      for (int q = c; q < 9; q += 4) cinv_s[q * rows_cta + lr] = cg4[(size_t)q * g.nP + lp];
+  }
+  const int lrow0 = sl1 > sl0 ? g.Hlp.srow[sl0] : 0, nlrows = sl1 > sl0 ? g.Hlp.srow[sl1] - lrow0 : 0;
+  for (int q = tid; q < sl1 - sl0; q += bt) {
+    const int sl = sl0 + q;
+    meta_s[5 * q] = g.Hlp.sbase[sl] - e0lp;
+    meta_s[5 * q + 1] = (g.Hlp.sbase[sl + 1] - g.Hlp.sbase[sl]) >> 5;
+    meta_s[5 * q + 2] = g.Hlp.sshift[sl];
+    meta_s[5 * q + 3] = g.Hlp.srow[sl];
+    meta_s[5 * q + 4] = g.Hlp.srow[sl + 1];
+  }
+  for (int q = tid; q < nlrows; q += bt) {
+    const double* W = g.Hll_inv[g.rank];
+    w_s[q] = W[lrow0 + q];
+    w_s[nlrows + q] = W[(size_t)g.capL + lrow0 + q];
+    w_s[2 * nlrows + q] = W[2 * (size_t)g.capL + lrow0 + q];
+  }
+  // ---- per-thread constants
+  const int slice = lp >> 5, lane_p = lp & 31;
+  int wpp = 0, bpp = 0, wpl = 0, bpl = 0;
+  if (act) {
+    wpp = sell_width(g.Hpp, slice);
+    bpp = g.Hpp.sbase[slice] - e0pp + lane_p;
+    if (has_pl) {
+      wpl = sell_width(g.Hpl, slice);
+      bpl = g.Hpl.sbase[slice] - e0pl + lane_p;
+    }
+  }
+  const int lane = tid & 31, warp = tid >> 5;
+  auto sync_sum = [&](double* v, int nv) {
+    if (CL) {
+      cg::cluster_group cl = cg::this_cluster();
+      ++seq;
+      double* mine = cl_part + (seq & 1ull) * 16;
+      if (nv > 0 && tid < ncta) cl.map_shared_rank(mine, tid)[cta] = v[0];
+      cl.sync();
+      if (nv > 0) {
+        double acc = 0.0;
+        for (int o = 0; o < ncta; ++o) acc += mine[o];
+        v[0] = acc;
+      }
+    } else {
+      __syncthreads();
+    }
+  };
+  auto put_z = [&](double zc) {  // component c of row lp into every CTA's copy of z
+    if (CL) {
+      cg::cluster_group cl = cg::this_cluster();
+      for (int rk = 0; rk < ncta; ++rk) cl.map_shared_rank(z_s, rk)[3 * lp + c] = zc;
+    } else {
+      z_s[3 * lp + c] = zc;
+    }
+  };
+  // z_c = sum_j Cinv[c][j] r_j over the 12 residual components of the row's chunk (read from r_s), returns r_c z_c
+  auto precond = [&](double rc, double* zc) {
+    if (act) r_s[3 * lr + c] = rc;
+    __syncwarp();
+    double acc = 0.0;
+    if (act) {
+      const double* rr = r_s + 3 * (lr & ~(kChunk - 1));
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        const float4 v = cinv_s[(3 * c + q) * rows_cta + lr];
+        acc += (double)v.x * rr[4 * q] + (double)v.y * rr[4 * q + 1] + (double)v.z * rr[4 * q + 2] + (double)v.w * rr[4 * q + 3];
+      }
+    }
+    __syncwarp();
+    *zc = acc;
+    return rc * acc;
+  };
+
+  // ---- x = 0, r = bt, z = M^-1 r, d = s = 0 (one component per lane)
+  double x = 0.0, r = 0.0, d = 0.0, s = 0.0, z = 0.0;
+  if (act) r = g.bt[3 * (size_t)lp + c];
+  __syncthreads();  // staged arrays complete
+  // the rows of a chunk whose pose does not exist contribute zeros
+  if (!rowact && c < 3 && lr < rows_cta) r_s[3 * lr + c] = 0.0;
+  __syncthreads();
+  double acc = precond(r, &z);
+  if (CL) cg::this_cluster().sync();
+  if (act) put_z(z);
+  double gam = block_sum(acc, sm);
+  sync_sum(&gam, 1);
+  const double gam0 = gam, target = prm.tol * prm.tol * gam0;
+  double gam_old = 0.0, alpha_old = 0.0;
+  int it = 0, flag = 1;
+  if (!(gam0 > 0.0)) {
+    flag = (gam0 == 0.0) ? 0 : 2;
+  } else {
+    while (true) {
+      if (!(gam == gam)) { flag = 2; break; }
+      if (gam <= target) { flag = 0; break; }
+      if (it >= prm.maxit) break;
+      const double beta = it == 0 ? 0.0 : gam / gam_old;
+      // ---- phase A: t = W Hlp^T z; warp w takes the slices w, w + warps, ... of this CTA
+      if (ns_l > 0) {
+        for (int q = warp; q < sl1 - sl0; q += spc_l) {
+          const int lm_e = meta_s[5 * q] + lane, lm_steps = meta_s[5 * q + 1], lm_sh = meta_s[5 * q + 2];
+          const int lm_row = meta_s[5 * q + 3] + (lane >> (5 - lm_sh));
+          const bool lm_writer = (lane & ((32 >> lm_sh) - 1)) == 0 && lm_row < meta_s[5 * q + 4];
+          double u0 = 0.0, u1 = 0.0;
+          for (int j = 0; j < lm_steps; ++j) {
+            const int e = lm_e + 32 * j;
+            const int col = clp[e];
+            if (col >= 0) {
+              const double* pv = z_s + 3 * (col & kLocalMask);
+              const double* pa = vlp + (size_t)(e & ~31) * 6 + (e & 31);
+              const double v0 = pv[0], v1 = pv[1], v2 = pv[2];
+              u0 += pa[0] * v0 + pa[64] * v1 + pa[128] * v2;
+              u1 += pa[32] * v0 + pa[96] * v1 + pa[160] * v2;
+            }
+          }
+          lm_group_sum(lm_sh, u0, u1);
+          if (lm_writer) {
+            const double w11 = w_s[lm_row - lrow0], w12 = w_s[nlrows + lm_row - lrow0], w22 = w_s[2 * nlrows + lm_row - lrow0];
+            const double t0 = w11 * u0 + w12 * u1, t1 = w12 * u0 + w22 * u1;
+            if (CL) {
+              cg::cluster_group cl = cg::this_cluster();
+              for (int rk = 0; rk < ncta; ++rk) {
+                double* tr = cl.map_shared_rank(t_s, rk) + 2 * lm_row;
+                tr[0] = t0;
+                tr[1] = t1;
+              }
+            } else {
+              t_s[2 * lm_row] = t0;
+              t_s[2 * lm_row + 1] = t1;
+            }
+          }
+        }
+        sync_sum(nullptr, 0);
+      }
+      // ---- phase B, component c of row lp: w_c = lambda z_c + sum_k Hpp_k[c][:] z_k - sum_k Hpl_k[c][:] t_k
+      acc = 0.0;
+      if (act) {
+        double q = lambda * z;
+        for (int k = 0; k < wpp; ++k) {
+          const int e = bpp + 32 * k;
+          const int col = cpp[e];
+          if (col < 0) continue;
+          const double* pv = z_s + 3 * (col & kLocalMask);
+          const double* pa = vpp + (size_t)(e & ~31) * 9 + (e & 31) + 96 * c;   // row c of the 3x3 block
+          q += pa[0] * pv[0] + pa[32] * pv[1] + pa[64] * pv[2];
+        }
+        for (int k = 0; k < wpl; ++k) {
+          const int e = bpl + 32 * k;
+          const int col = cpl[e];
+          if (col < 0) continue;
+          const double* pt = t_s + 2 * (col & kLocalMask);
+          const double* pa = vpl + (size_t)(e & ~31) * 6 + (e & 31) + 64 * c;   // row c of the 3x2 block
+          q -= pa[0] * pt[0] + pa[32] * pt[1];
+        }
+        d = z + beta * d;
+        s = q + beta * s;
+        acc = z * q;
+      }
+      double del = block_sum(acc, sm);
+      sync_sum(&del, 1);
+      const double denom = it == 0 ? del : del - beta * gam / alpha_old;
+      if (!(denom > 0.0)) { flag = 2; break; }
+      const double alpha = gam / denom;
+      // ---- phase C
+      if (act) {
+        x += alpha * d;
+        r -= alpha * s;
+      }
+      acc = precond(r, &z);
+      if (act) put_z(z);
+      ++it;
+      gam_old = gam;
+      alpha_old = alpha;
+      gam = block_sum(acc, sm);
+      sync_sum(&gam, 1);
+    }
+  }
+  if (act) g.x_p[g.rank][3 * (size_t)lp + c] = x;
+  out.gam0 = gam0;
+  out.gam = gam;
+  out.iters = it;
+  out.flag = flag;
+}
+
 // the batched kernel's entry (k_lm_block, sgb_kernels.cuh): one CTA owns the whole graph
 __device__ void pcg_resident_block(const DevGraph& g, const PcgParams& prm, double lambda, const ResPlanFwd& rpf,
                                    unsigned char* res_smem, double* sm, int* s_last, unsigned long long& seq, PcgOut& out) {
   ResPlan rp;
   rp.valid = rpf.valid; rp.bt = rpf.bt; rp.ncta = rpf.ncta; rp.cap_pp = rpf.cap_pp; rp.cap_pl = rpf.cap_pl; rp.cap_lp = rpf.cap_lp;
-  rp.nz = rpf.nz; rp.nt = rpf.nt; rp.bytes = rpf.bytes; rp.cap_sl = rpf.cap_sl; rp.cap_lr = rpf.cap_lr;
+  rp.nz = rpf.nz; rp.nt = rpf.nt; rp.bytes = rpf.bytes; rp.cap_sl = rpf.cap_sl; rp.cap_lr = rpf.cap_lr; rp.rows_cta = rpf.rows_cta;
   pcg_resident_solve<false>(g, prm, lambda, rp, res_smem, sm, nullptr, s_last, seq, out);
 }
 
@@ -357,6 +593,25 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
 
 namespace sgb {
 #if defined(__CUDACC__)
+// Four lanes per row (pcg_resident_solve4): up to 1024 threads per CTA, a cluster of such CTAs or a single one.
+__global__ void __launch_bounds__(1024, 1) k_pcg_res4(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  __shared__ double sm[32];
+  __shared__ double cl_part[32];
+  unsigned long long seq = 0;
+  const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
+  PcgOut out;
+  if (gridDim.x > 1) pcg_resident_solve4<true>(g, prm, lambda, rp, res_smem, sm, cl_part, seq, out);
+  else pcg_resident_solve4<false>(g, prm, lambda, rp, res_smem, sm, cl_part, seq, out);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    sc->rz0 = out.gam0;
+    sc->rz = out.gam;
+    sc->pcg_iters = out.iters;
+    sc->pcg_flag = out.flag;
+    sc->pcg_rel = out.gam0 > 0.0 ? sqrt(fabs(out.gam) / out.gam0) : 0.0;
+  }
+  if (gridDim.x > 1) cooperative_groups::this_cluster().sync();
+}
 // The same solve for a graph that fits ONE CTA (rows <= blockDim.x): block barriers only, no cluster.
 __global__ void __launch_bounds__(kThreads, 1) k_pcg_res1(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
   extern __shared__ __align__(16) unsigned char res_smem[];
