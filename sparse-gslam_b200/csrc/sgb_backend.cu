@@ -1050,7 +1050,9 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
       static const bool np4_ok = cudaFuncSetAttribute(k_pcg_res4, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
       bool done4 = no_res4;
       for (int pass = 0; pass < 2 && !done4; ++pass)        // pass 0: single CTA, pass 1: clusters
-        for (int bt : (pass == 0 ? std::initializer_list<int>{256, 512, 1024} : std::initializer_list<int>{1024, 512, 256})) {
+        for (int ib = 0; ib < 3 && !done4; ++ib) {
+          static const int kBt[2][3] = {{256, 512, 1024}, {1024, 512, 256}};  // smallest CTA that holds the rows / fewest CTAs
+          const int bt = kBt[pass][ib];
           const int rows_cta = bt / 4, spc_p = rows_cta / 32, spc_l = bt / 32;
           if (spc_p < 1) continue;
           int need = std::max((P.nP + rows_cta - 1) / rows_cta, pass == 0 ? 1 : (P.Hlp.nslices + spc_l - 1) / spc_l);
@@ -1086,7 +1088,6 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
           rp.valid = 1;
           h->res4 = rp;
           done4 = true;
-          break;
         }
       if (prof) std::fprintf(stderr, "[sgb_set_graph] resident solve, four lanes per row: %s (%d CTAs x %d threads, %d bytes)\n",
                              h->res4.valid ? "yes" : "no", h->res4.ncta, h->res4.bt, h->res4.bytes);
