@@ -162,21 +162,44 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     S.pp_src.reserve(g.n_pp);
     S.pl_src.reserve(g.n_pl);
   }
-  for (int k = 0; k < g.n_pp; ++k) {
-    int i = g.pp_i[k], j = g.pp_j[k];
-    if (i < 0 || i >= P || j < 0 || j >= P || i == j) { err = "pose-pose edge with a bad vertex index"; return SGB_ERR_INVALID; }
-    if (pfixed(i) && pfixed(j)) continue;
-    if (!filtered) S.pp_src.push_back(k);
-    pact[i] = pact[j] = 1;
-    if (g.pp_phi && g.pp_phi[k] > 0.0) S.has_robust = true;
-  }
-  for (int k = 0; k < g.n_pl; ++k) {
-    int p = g.pl_pose[k], l = g.pl_lm[k];
-    if (p < 0 || p >= P || l < 0 || l >= L) { err = "pose-line edge with a bad vertex index"; return SGB_ERR_INVALID; }
-    if (pfixed(p) && lfixed(l)) continue;
-    if (!filtered) S.pl_src.push_back(k);
-    pact[p] = 1;
-    lact[l] = 1;
+  // (filtered build, large graph: the scan only marks vertices -- every writer stores the same 1 -- so it is split over host
+  // threads; every rank of a multi-GPU job runs this part on the WHOLE graph, it is what does not shrink with the rank count)
+  const int nth_scan = (filtered && (size_t)g.n_pp + g.n_pl > 400000) ? 4 : 1;
+  {
+    std::vector<int> bad(nth_scan, 0), robust(nth_scan, 0);
+    auto scan = [&](int t) {
+      const int a0 = (int)((int64_t)g.n_pp * t / nth_scan), a1 = (int)((int64_t)g.n_pp * (t + 1) / nth_scan);
+      const int b0 = (int)((int64_t)g.n_pl * t / nth_scan), b1 = (int)((int64_t)g.n_pl * (t + 1) / nth_scan);
+      for (int k = a0; k < a1; ++k) {
+        int i = g.pp_i[k], j = g.pp_j[k];
+        if (i < 0 || i >= P || j < 0 || j >= P || i == j) { bad[t] = 1; return; }
+        if (pfixed(i) && pfixed(j)) continue;
+        if (!filtered) S.pp_src.push_back(k);
+        pact[i] = pact[j] = 1;
+        if (g.pp_phi && g.pp_phi[k] > 0.0) robust[t] = 1;
+      }
+      for (int k = b0; k < b1; ++k) {
+        int p = g.pl_pose[k], l = g.pl_lm[k];
+        if (p < 0 || p >= P || l < 0 || l >= L) { bad[t] = 2; return; }
+        if (pfixed(p) && lfixed(l)) continue;
+        if (!filtered) S.pl_src.push_back(k);
+        pact[p] = 1;
+        lact[l] = 1;
+      }
+    };
+    if (nth_scan == 1) {
+      scan(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int t = 1; t < nth_scan; ++t) th.emplace_back(scan, t);
+      scan(0);
+      for (auto& t : th) t.join();
+    }
+    for (int t = 0; t < nth_scan; ++t) {
+      if (bad[t] == 1) { err = "pose-pose edge with a bad vertex index"; return SGB_ERR_INVALID; }
+      if (bad[t] == 2) { err = "pose-line edge with a bad vertex index"; return SGB_ERR_INVALID; }
+      if (robust[t]) S.has_robust = true;
+    }
   }
   lap("active scan");
   // global insertion rank of an active edge (ties: pose-pose first, then caller index -- both orders are stable)
@@ -220,27 +243,47 @@ sgb_status build_structure(const sgb_graph_soa& g, Structure& S, std::string& er
     const int chunk = partition_chunk(S.Pf, world);
     auto mine = [&](int h) { return h >= 0 && h / chunk == rank; };
     std::vector<char> keep(L, 0), free_obs(L, 0);
-    for (int k = 0; k < g.n_pl; ++k) {
-      int p = g.pl_pose[k], l = g.pl_lm[k];
-      if (pfixed(p) && lfixed(l)) continue;
-      int hp = S.pose_h[p];
-      if (hp >= 0) {
-        free_obs[l] = 1;
-        if (mine(hp)) keep[l] = 1;
+    const int nth = nth_scan;
+    auto run = [&](auto&& body) {  // body(t) on nth host threads
+      if (nth == 1) { body(0); return; }
+      std::vector<std::thread> th;
+      for (int t = 1; t < nth; ++t) th.emplace_back(body, t);
+      body(0);
+      for (auto& t : th) t.join();
+    };
+    run([&](int t) {  // marks only: every writer stores the same 1
+      const int b0 = (int)((int64_t)g.n_pl * t / nth), b1 = (int)((int64_t)g.n_pl * (t + 1) / nth);
+      for (int k = b0; k < b1; ++k) {
+        int p = g.pl_pose[k], l = g.pl_lm[k];
+        if (pfixed(p) && lfixed(l)) continue;
+        int hp = S.pose_h[p];
+        if (hp >= 0) {
+          free_obs[l] = 1;
+          if (mine(hp)) keep[l] = 1;
+        }
       }
-    }
+    });
     if (rank == 0)
       for (int l = 0; l < L; ++l)
         if (lact[l] && !free_obs[l]) keep[l] = 1;
-    for (int k = 0; k < g.n_pp; ++k) {
-      int i = g.pp_i[k], j = g.pp_j[k];
-      if (pfixed(i) && pfixed(j)) continue;
-      if (mine(S.pose_h[i]) || mine(S.pose_h[j])) S.pp_src.push_back(k);
-    }
-    for (int k = 0; k < g.n_pl; ++k) {
-      int p = g.pl_pose[k], l = g.pl_lm[k];
-      if (pfixed(p) && lfixed(l)) continue;
-      if (mine(S.pose_h[p]) || (S.lm_h[l] >= 0 && keep[l])) S.pl_src.push_back(k);
+    std::vector<std::vector<int32_t>> sel_pp(nth), sel_pl(nth);  // per thread, caller order inside; concatenated in thread order
+    run([&](int t) {
+      const int a0 = (int)((int64_t)g.n_pp * t / nth), a1 = (int)((int64_t)g.n_pp * (t + 1) / nth);
+      const int b0 = (int)((int64_t)g.n_pl * t / nth), b1 = (int)((int64_t)g.n_pl * (t + 1) / nth);
+      for (int k = a0; k < a1; ++k) {
+        int i = g.pp_i[k], j = g.pp_j[k];
+        if (pfixed(i) && pfixed(j)) continue;
+        if (mine(S.pose_h[i]) || mine(S.pose_h[j])) sel_pp[t].push_back(k);
+      }
+      for (int k = b0; k < b1; ++k) {
+        int p = g.pl_pose[k], l = g.pl_lm[k];
+        if (pfixed(p) && lfixed(l)) continue;
+        if (mine(S.pose_h[p]) || (S.lm_h[l] >= 0 && keep[l])) sel_pl[t].push_back(k);
+      }
+    });
+    for (int t = 0; t < nth; ++t) {
+      S.pp_src.insert(S.pp_src.end(), sel_pp[t].begin(), sel_pp[t].end());
+      S.pl_src.insert(S.pl_src.end(), sel_pl[t].begin(), sel_pl[t].end());
     }
     S.lm_present.assign(S.Lf, 0);
     for (int l = 0; l < L; ++l)
