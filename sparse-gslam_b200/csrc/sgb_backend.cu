@@ -949,11 +949,13 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
     const double pen[3] = {1.0, 1.04, 1.15};
     double best = 0.0;
     int best_bt = kThreads, best_blocks = 1;
-    // only where whole rows per thread matter: with more than three rows per thread the phases are bandwidth-bound and the
-    // 256-thread build with its 80 registers wins (C5 on one GPU: 41.9 / 40.6 / 39.6 LM it/s with 256 / 288 / 320 threads)
+    // Measured (C5, LM it/s with 256 / 288 / 320 threads): one GPU, 8.8 rows per thread: 41.9 / 40.6 / 39.6; two GPUs,
+    // 4.4 rows per thread: 77.2 / 76.0 / 72.3 -- going from five to four whole rows per thread buys nothing, the phases are
+    // not quantised in rows at these sizes, and the smaller register budget costs. The larger blocks are therefore only
+    // considered when a rank holds at most ~1.5 rows per thread (the 8-GPU shard of a 1M-pose graph).
     int per_sm256 = 0;
     SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm256, (const void*)k_pcg<256>, 256, 0));
-    const bool quantised = (double)P.nP / ((double)std::max(1, per_sm256) * h->sm_count * 256.0) <= 3.0;
+    const bool quantised = (double)P.nP / ((double)std::max(1, per_sm256) * h->sm_count * 256.0) <= 1.5;
     for (int c = 0; c < 3; ++c) {
       if (forced > 0 && cand[c] != forced) continue;
       if (forced <= 0 && c > 0 && !quantised) continue;
