@@ -949,13 +949,14 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
     const double pen[3] = {1.0, 1.04, 1.15};
     double best = 0.0;
     int best_bt = kThreads, best_blocks = 1;
-    // Measured (C5, LM it/s with 256 / 288 / 320 threads): one GPU, 8.8 rows per thread: 41.9 / 40.6 / 39.6; two GPUs,
-    // 4.4 rows per thread: 77.2 / 76.0 / 72.3 -- going from five to four whole rows per thread buys nothing, the phases are
-    // not quantised in rows at these sizes, and the smaller register budget costs. The larger blocks are therefore only
-    // considered when a rank holds at most ~1.5 rows per thread (the 8-GPU shard of a 1M-pose graph).
+    // Measured (C5, LM it/s with 256 / 288 / 320 threads; rows per thread at 256 threads in brackets): one GPU (8.8)
+    // 41.9 / 40.6 / 39.6; two GPUs (4.4) 77.2 / 76.0 / 72.3; four GPUs (2.2) 122.7 / 129.6 / 124.8; eight GPUs (1.1)
+    // 175.0 / 197.4 / -- . A phase lasts as many whole rows as its busiest thread owns only when that number is small:
+    // three -> two rows (4 GPUs) and two -> one (8 GPUs) pay, five -> four and nine -> eight do not, and the smaller
+    // register budget of the larger blocks always costs a little. The larger blocks are considered up to three rows per thread.
     int per_sm256 = 0;
     SGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm256, (const void*)k_pcg<256>, 256, 0));
-    const bool quantised = (double)P.nP / ((double)std::max(1, per_sm256) * h->sm_count * 256.0) <= 1.5;
+    const bool quantised = (double)P.nP / ((double)std::max(1, per_sm256) * h->sm_count * 256.0) <= 3.0;
     for (int c = 0; c < 3; ++c) {
       if (forced > 0 && cand[c] != forced) continue;
       if (forced <= 0 && c > 0 && !quantised) continue;
