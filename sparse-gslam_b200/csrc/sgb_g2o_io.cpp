@@ -51,12 +51,16 @@ sgb_status sgb_g2o_load(const char* path, sgb_graph_file** out, char* errbuf, in
   }
   auto* f = new sgb_graph_file();
   std::unordered_map<int64_t, int32_t> pose_of, lm_of;
-  struct RawPP { int64_t i, j; };
-  struct RawPL { int64_t p, l; };
+  // every entry that is resolved after the whole file has been read remembers its line: errors found there (an edge or
+  // a FIX naming an unknown vertex, a robust kernel on an unknown edge) are reported with it
+  struct RawPP { int64_t i, j, line; };
+  struct RawPL { int64_t p, l, line; };
+  struct RawFix { int64_t id, line; };
+  struct RawDcs { int64_t k; double d; int64_t line; };
   std::vector<RawPP> rpp;
   std::vector<RawPL> rpl;
-  std::vector<int64_t> fixed_ids;
-  std::vector<std::pair<int64_t, double>> dcs;
+  std::vector<RawFix> fixed_ids;
+  std::vector<RawDcs> dcs;
   std::string line, tag;
   int64_t seq = 0, lineno = 0;
   auto fail = [&](const std::string& what) {
@@ -90,6 +94,7 @@ sgb_status sgb_g2o_load(const char* path, sgb_graph_file** out, char* errbuf, in
       if (!(ls >> e.i >> e.j)) return fail("malformed EDGE_SE2");
       for (double& d : v)
         if (!(ls >> d)) return fail("malformed EDGE_SE2");
+      e.line = lineno;
       rpp.push_back(e);
       f->pp_z.insert(f->pp_z.end(), v, v + 3);
       f->pp_info.insert(f->pp_info.end(), v + 3, v + 9);
@@ -100,24 +105,26 @@ sgb_status sgb_g2o_load(const char* path, sgb_graph_file** out, char* errbuf, in
       if (!(ls >> e.p >> e.l)) return fail("malformed EDGE_SE2_RHOTHETA");
       for (double& d : v)
         if (!(ls >> d)) return fail("malformed EDGE_SE2_RHOTHETA");
+      e.line = lineno;
       rpl.push_back(e);
       f->pl_z.insert(f->pl_z.end(), v, v + 2);
       f->pl_info.insert(f->pl_info.end(), v + 2, v + 5);
       f->pl_seq.push_back(seq++);
     } else if (tag == "FIX") {
       int64_t id;
-      while (ls >> id) fixed_ids.push_back(id);
+      while (ls >> id) fixed_ids.push_back({id, lineno});
     } else if (tag == "ROBUST_KERNEL_DCS") {
       int64_t k;
       double d;
       if (!(ls >> k >> d)) return fail("malformed ROBUST_KERNEL_DCS");
-      dcs.push_back({k, d});
+      dcs.push_back({k, d, lineno});
     }  // anything else: not a type of this path, skipped like g2o skips unknown tags
   }
-  lineno = 0;
   f->pose_fixed.assign(f->pose_id.size(), 0);
   f->lm_fixed.assign(f->lm_id.size(), 0);
-  for (int64_t id : fixed_ids) {
+  for (auto& fx : fixed_ids) {
+    const int64_t id = fx.id;
+    lineno = fx.line;
     auto a = pose_of.find(id);
     if (a != pose_of.end()) { f->pose_fixed[a->second] = 1; continue; }
     auto b = lm_of.find(id);
@@ -125,12 +132,14 @@ sgb_status sgb_g2o_load(const char* path, sgb_graph_file** out, char* errbuf, in
     return fail("FIX of an unknown vertex " + std::to_string(id));
   }
   for (auto& e : rpp) {
+    lineno = e.line;
     auto a = pose_of.find(e.i), b = pose_of.find(e.j);
     if (a == pose_of.end() || b == pose_of.end()) return fail("EDGE_SE2 references an unknown VERTEX_SE2");
     f->pp_i.push_back(a->second);
     f->pp_j.push_back(b->second);
   }
   for (auto& e : rpl) {
+    lineno = e.line;
     auto a = pose_of.find(e.p);
     auto b = lm_of.find(e.l);
     if (a == pose_of.end() || b == lm_of.end()) return fail("EDGE_SE2_RHOTHETA references an unknown vertex");
@@ -139,8 +148,9 @@ sgb_status sgb_g2o_load(const char* path, sgb_graph_file** out, char* errbuf, in
   }
   f->pp_phi.assign(f->pp_i.size(), 0.0);
   for (auto& kd : dcs) {
-    if (kd.first < 0 || kd.first >= (int64_t)f->pp_phi.size()) return fail("ROBUST_KERNEL_DCS on an unknown edge");
-    f->pp_phi[(size_t)kd.first] = kd.second;
+    lineno = kd.line;
+    if (kd.k < 0 || kd.k >= (int64_t)f->pp_phi.size()) return fail("ROBUST_KERNEL_DCS on an unknown edge");
+    f->pp_phi[(size_t)kd.k] = kd.d;
   }
   *out = f;
   return SGB_OK;
@@ -219,7 +229,8 @@ sgb_status sgb_g2o_save(const char* path, const sgb_graph_soa* g) {
     }
   }
   for (auto& kd : dcs) std::fprintf(fp, "ROBUST_KERNEL_DCS %" PRId64 " %.17g\n", kd.first, kd.second);
-  bool ok = std::fclose(fp) == 0;
+  bool ok = std::ferror(fp) == 0;  // a failed write (full disk ...) is an error even when fclose succeeds
+  ok = (std::fclose(fp) == 0) && ok;
   return ok ? SGB_OK : SGB_ERR_INVALID;
 }
 

@@ -678,6 +678,13 @@ __global__ void __launch_bounds__(kThreads) k_update(DevGraph g, DevScalars* sc,
   if (threadIdx.x == 0) part[2 * kMaxBlocks + blockIdx.x] = s;
 }
 
+// Did the linear solve produce a usable step? flag 0 = converged; flag 2 = breakdown (not SPD / non-finite) = g2o's
+// solve() == false. flag 1 = the iteration limit was hit: LinearSolverEigen either solves exactly or fails, so an
+// arbitrarily inexact step must not pass as a success -- it counts only if the preconditioned residual had already
+// dropped by six orders of magnitude (step error ~1e-6 relative), otherwise the trial is rejected (LM) / the iteration
+// fails (GN, sgb_linear_solve).
+__host__ __device__ __forceinline__ bool pcg_usable(int flag, double rel) { return flag == 0 || (flag == 1 && rel <= 1e-6); }
+
 // OptimizationAlgorithmLevenberg::solve, the part after the trial's chi2 is known: gain ratio, lambda /
 // nu update, accept / reject, Terminate conditions, with g2o's constants. c / cr = activeChi2 / activeRobustChi2 of the
 // trial estimates, scale = computeScale sum, solve_ok = the linear solve did not break down. One thread.
@@ -733,7 +740,7 @@ __global__ void __launch_bounds__(kThreads) k_lm_control(DevGraph g, DevScalars*
   xreduce(g, ++seq, &fail, 1, 1, true);
   if (threadIdx.x == 0) {
     sc->xseq = seq;
-    lm_control_update(sc, v[0], v[1], v[2], (sc->pcg_flag != 2) && (fail == 0.0), max_trials);
+    lm_control_update(sc, v[0], v[1], v[2], pcg_usable(sc->pcg_flag, sc->pcg_rel) && (fail == 0.0), max_trials);
   }
 }
 // Gauss-Newton: the solve succeeded iff no rank saw a breakdown
@@ -744,7 +751,7 @@ __global__ void k_gn_control(DevGraph g, DevScalars* sc) {
   xreduce(g, ++seq, &fail, 1, 1, true);
   if (threadIdx.x == 0) {
     sc->xseq = seq;
-    bool ok = (sc->pcg_flag != 2) && (fail == 0.0);
+    bool ok = pcg_usable(sc->pcg_flag, sc->pcg_rel) && (fail == 0.0);
     sc->result = ok ? 1 : -1;
     sc->setup_fail = 0;
   }
@@ -860,7 +867,7 @@ __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, B
         s += v < g.nP ? update_pose_row(g, v, lambda, dst) : update_lm_row(g, v - g.nP, lambda, dst);
       const double scale = block_sum(s, sm);
       __syncthreads();
-      const bool solve_ok = po.flag != 2 && s_ok != 0;
+      const bool solve_ok = pcg_usable(po.flag, po.gam0 > 0.0 ? sqrt(fabs(po.gam) / po.gam0) : 0.0) && s_ok != 0;
       if (prm.algo != 0) {  // Gauss-Newton
         if (tid == 0) {
           sc.pcg_iters = po.iters;

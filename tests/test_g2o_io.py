@@ -68,7 +68,13 @@ def test_save_load_round_trip_is_exact(tmp_path, maker):
 def test_malformed_files_are_rejected_with_a_message(tmp_path):
     bad = tmp_path / "bad.g2o"
     bad.write_text("VERTEX_SE2 0 0 0 0\nEDGE_SE2 0 7 1 0 0 1 0 0 1 0 1\n")
-    with pytest.raises(ValueError, match="unknown VERTEX_SE2"):
+    with pytest.raises(ValueError, match="bad.g2o:2: EDGE_SE2 references an unknown VERTEX_SE2"):
+        gg.load_g2o(str(bad))   # errors found when the references are resolved carry the line of the offending entry
+    bad.write_text("# c\nVERTEX_SE2 0 0 0 0\nVERTEX_SE2 1 1 0 0\nEDGE_SE2 0 1 1 0 0 1 0 0 1 0 1\n\nFIX 9\n")
+    with pytest.raises(ValueError, match="bad.g2o:6: FIX of an unknown vertex 9"):
+        gg.load_g2o(str(bad))
+    bad.write_text("VERTEX_SE2 0 0 0 0\nVERTEX_SE2 1 1 0 0\nEDGE_SE2 0 1 1 0 0 1 0 0 1 0 1\nROBUST_KERNEL_DCS 3 1.0\n")
+    with pytest.raises(ValueError, match="bad.g2o:4: ROBUST_KERNEL_DCS on an unknown edge"):
         gg.load_g2o(str(bad))
     bad.write_text("VERTEX_SE2 0 0 0\n")
     with pytest.raises(ValueError, match="bad.g2o:1: malformed VERTEX_SE2"):
