@@ -55,6 +55,34 @@ __host__ __device__ inline ResOffsets res_offsets(const ResPlan& p) {
 }
 
 #if defined(__CUDACC__)
+// ---- cluster barrier on shared-memory mbarriers. cooperative_groups' cluster.sync() compiles to MEMBAR.ALL.GPU + ERRBAR +
+// UCGABAR_ARV / UCGABAR_WAIT + CCTL.IVALL in EVERY warp; in the resident solve of the key-frame stream (4 CTAs x 16 warps,
+// three barriers per PCG iteration) 55 % of the stall samples sat on those instructions, ~1.2 us per barrier
+// (profiles/r2_res4_stream_*). Here every CTA owns one mbarrier expecting one arrival per CTA of the cluster: after the CTA's
+// own block barrier, thread t < ncta arrives (release, cluster scope) on the mbarrier of CTA t through its shared::cluster
+// address, and every thread waits (acquire, cluster scope) on its own CTA's mbarrier -- one remote arrive (~215 cycles) and
+// a hardware-slept try_wait instead of the grid-style barrier. The distributed-shared-memory stores made before the block
+// barrier are ordered before the arrive by the barrier + release chain, and visible after the acquire.
+__device__ __forceinline__ unsigned res_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void res_mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(res_smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void res_mbar_arrive_remote(unsigned long long* bar, unsigned cta) {
+  unsigned raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(res_smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void res_mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "RES_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@!p bra RES_WAIT_%=;\n"
+      "}\n" ::"r"(res_smem_u32(bar)), "r"(parity) : "memory");
+}
+
 // z_i = sum_j Cinv_ij r_j with the row's nine float4 in shared memory (layout [q][row of the CTA])
 __device__ __forceinline__ double precond_row_res(const float4* cinv_s, int bt, int lr, bool active, const double r[3], double z[3]) {
   const unsigned lane = threadIdx.x & 31u;
@@ -332,8 +360,8 @@ __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgP
 // instead of 36, and a 256-row CTA runs 32 warps. rp.bt threads per CTA own rp.bt / 4 rows and rp.bt / 32 landmark slices.
 template <bool CL>
 __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const PcgParams& prm, const double lambda, const ResPlan& rp,
-                                                    unsigned char* res_smem, double* sm, double* cl_part, unsigned long long& seq,
-                                                    PcgOut& out) {
+                                                    unsigned char* res_smem, double* sm, double* cl_part, unsigned long long* cbar,
+                                                    unsigned long long& seq, PcgOut& out) {
   namespace cg = cooperative_groups;
   const ResOffsets of = res_offsets(rp);
   double* vpp = reinterpret_cast<double*>(res_smem + of.vpp);
@@ -406,13 +434,17 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
     }
   }
   const int lane = tid & 31, warp = tid >> 5;
+  unsigned cpar = 0;  // phase parity of this CTA's mbarrier
   auto sync_sum = [&](double* v, int nv) {
     if (CL) {
       cg::cluster_group cl = cg::this_cluster();
       ++seq;
       double* mine = cl_part + (seq & 1ull) * 16;
       if (nv > 0 && tid < ncta) cl.map_shared_rank(mine, tid)[cta] = v[0];
-      cl.sync();
+      __syncthreads();                                   // this CTA's distributed-shared-memory stores are issued
+      if (tid < ncta) res_mbar_arrive_remote(cbar, tid);  // one arrival on every CTA's mbarrier
+      res_mbar_wait(cbar, cpar);                          // all CTAs have arrived here
+      cpar ^= 1u;
       if (nv > 0) {
         double acc = 0.0;
         for (int o = 0; o < ncta; ++o) acc += mine[o];
@@ -456,7 +488,10 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
   if (!rowact && c < 3 && lr < rows_cta) r_s[3 * lr + c] = 0.0;
   __syncthreads();
   double acc = precond(r, &z);
-  if (CL) cg::this_cluster().sync();
+  if (CL) {
+    if (tid == 0) res_mbar_init(cbar, (unsigned)ncta);
+    cg::this_cluster().sync();  // every CTA has started and initialised its mbarrier before anybody stores into it
+  }
   if (act) put_z(z);
   double gam = block_sum(acc, sm);
   sync_sum(&gam, 1);
@@ -598,11 +633,12 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_res4(DevGraph g, DevScalars* sc
   extern __shared__ __align__(16) unsigned char res_smem[];
   __shared__ double sm[32];
   __shared__ double cl_part[32];
+  __shared__ __align__(8) unsigned long long cbar;
   unsigned long long seq = 0;
   const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   PcgOut out;
-  if (gridDim.x > 1) pcg_resident_solve4<true>(g, prm, lambda, rp, res_smem, sm, cl_part, seq, out);
-  else pcg_resident_solve4<false>(g, prm, lambda, rp, res_smem, sm, cl_part, seq, out);
+  if (gridDim.x > 1) pcg_resident_solve4<true>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, seq, out);
+  else pcg_resident_solve4<false>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, seq, out);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc->rz0 = out.gam0;
     sc->rz = out.gam;
