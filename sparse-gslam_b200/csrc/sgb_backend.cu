@@ -314,7 +314,8 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   if (h->res4.valid && G.world == 1) {  // four lanes per pose row, everything on chip
     ResPlan rp = h->res4;
     if (rp.ncta == 1) {
-      k_pcg_res4<<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+      if (rp.bt <= 512) k_pcg_res4<512, 4><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+      else k_pcg_res4<1024, 2><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
       SGB_CUDA(cudaGetLastError());
     } else {
       cudaLaunchConfig_t cfg = {};
@@ -329,7 +330,8 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4, G, sc, prm, rp));
+      if (rp.bt <= 512) SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4<512, 4>, G, sc, prm, rp));
+      else SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4<1024, 2>, G, sc, prm, rp));
     }
   } else if (h->res_block.valid && G.world == 1 && !no_res1) {  // the whole graph in ONE CTA: block barriers only
     ResPlan rp = h->res_block;
@@ -1050,7 +1052,8 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
     {  // four lanes per pose row: one CTA if the graph fits it, else the smallest cluster
       h->res4 = ResPlan();
       static const bool no_res4 = std::getenv("SGB_NO_RES4") != nullptr;
-      static const bool np4_ok = cudaFuncSetAttribute(k_pcg_res4, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      static const bool np4_ok = cudaFuncSetAttribute(k_pcg_res4<512, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                                 cudaFuncSetAttribute(k_pcg_res4<1024, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
       bool done4 = no_res4;
       for (int pass = 0; pass < 2 && !done4; ++pass)        // pass 0: single CTA, pass 1: clusters
         for (int ib = 0; ib < 3 && !done4; ++ib) {
@@ -1072,7 +1075,8 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
           rp.cap_lr = cb == 1 ? std::max(1, P.nL) : 32 * spc_l;
           rp.bytes = (int)res_offsets(rp).total;
           if (rp.bytes > 224 * 1024) continue;
-          if (cudaFuncSetAttribute(k_pcg_res4, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) { cudaGetLastError(); continue; }
+          const void* fn4 = bt <= 512 ? (const void*)k_pcg_res4<512, 4> : (const void*)k_pcg_res4<1024, 2>;
+          if (cudaFuncSetAttribute(fn4, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) { cudaGetLastError(); continue; }
           if (cb > 1) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(cb);
@@ -1086,7 +1090,9 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
             cfg.attrs = at;
             cfg.numAttrs = 1;
             int nclusters = 0;
-            if (!(cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_res4, &cfg) == cudaSuccess && nclusters >= 1)) { cudaGetLastError(); continue; }
+            cudaError_t eo = bt <= 512 ? cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_res4<512, 4>, &cfg)
+                                       : cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_res4<1024, 2>, &cfg);
+            if (!(eo == cudaSuccess && nclusters >= 1)) { cudaGetLastError(); continue; }
           }
           rp.valid = 1;
           h->res4 = rp;

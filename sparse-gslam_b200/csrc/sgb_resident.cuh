@@ -83,6 +83,15 @@ __device__ __forceinline__ void res_mbar_wait(unsigned long long* bar, unsigned 
       "}\n" ::"r"(res_smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// store into the shared memory of CTA `rk` of the cluster at the address that `local_ptr` has in this CTA (mapa + st.shared::cluster:
+// no generic-address conversion and no read of the CTA-id special register per store, which cooperative_groups'
+// map_shared_rank costs inside a loop -- 7 % of the stall samples of the first build sat on S2R SR_CgaCtaId)
+__device__ __forceinline__ void res_st_dsmem(const double* local_ptr, unsigned rk, double v) {
+  unsigned raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(res_smem_u32(local_ptr)), "r"(rk));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(raddr), "d"(v) : "memory");
+}
+
 // z_i = sum_j Cinv_ij r_j with the row's nine float4 in shared memory (layout [q][row of the CTA])
 __device__ __forceinline__ double precond_row_res(const float4* cinv_s, int bt, int lr, bool active, const double r[3], double z[3]) {
   const unsigned lane = threadIdx.x & 31u;
@@ -358,7 +367,7 @@ __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgP
 // ~670 dependent instructions per warp and iteration at an IPC of 0.1 (ncu, profiles/r2_res1_stream_*) -- and every
 // product serial: here a pose-major row costs 3 instead of 9 multiply-adds per block and lane, the preconditioner 12
 // instead of 36, and a 256-row CTA runs 32 warps. rp.bt threads per CTA own rp.bt / 4 rows and rp.bt / 32 landmark slices.
-template <bool CL>
+template <bool CL, int U>
 __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const PcgParams& prm, const double lambda, const ResPlan& rp,
                                                     unsigned char* res_smem, double* sm, double* cl_part, unsigned long long* cbar,
                                                     unsigned long long& seq, PcgOut& out) {
@@ -437,10 +446,9 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
   unsigned cpar = 0;  // phase parity of this CTA's mbarrier
   auto sync_sum = [&](double* v, int nv) {
     if (CL) {
-      cg::cluster_group cl = cg::this_cluster();
       ++seq;
       double* mine = cl_part + (seq & 1ull) * 16;
-      if (nv > 0 && tid < ncta) cl.map_shared_rank(mine, tid)[cta] = v[0];
+      if (nv > 0 && tid < ncta) res_st_dsmem(mine + cta, (unsigned)tid, v[0]);
       __syncthreads();                                   // this CTA's distributed-shared-memory stores are issued
       if (tid < ncta) res_mbar_arrive_remote(cbar, tid);  // one arrival on every CTA's mbarrier
       res_mbar_wait(cbar, cpar);                          // all CTAs have arrived here
@@ -456,8 +464,7 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
   };
   auto put_z = [&](double zc) {  // component c of row lp into every CTA's copy of z
     if (CL) {
-      cg::cluster_group cl = cg::this_cluster();
-      for (int rk = 0; rk < ncta; ++rk) cl.map_shared_rank(z_s, rk)[3 * lp + c] = zc;
+      for (int rk = 0; rk < ncta; ++rk) res_st_dsmem(z_s + 3 * lp + c, (unsigned)rk, zc);
     } else {
       z_s[3 * lp + c] = zc;
     }
@@ -529,11 +536,9 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
             const double w11 = w_s[lm_row - lrow0], w12 = w_s[nlrows + lm_row - lrow0], w22 = w_s[2 * nlrows + lm_row - lrow0];
             const double t0 = w11 * u0 + w12 * u1, t1 = w12 * u0 + w22 * u1;
             if (CL) {
-              cg::cluster_group cl = cg::this_cluster();
               for (int rk = 0; rk < ncta; ++rk) {
-                double* tr = cl.map_shared_rank(t_s, rk) + 2 * lm_row;
-                tr[0] = t0;
-                tr[1] = t1;
+                res_st_dsmem(t_s + 2 * lm_row, (unsigned)rk, t0);
+                res_st_dsmem(t_s + 2 * lm_row + 1, (unsigned)rk, t1);
               }
             } else {
               t_s[2 * lm_row] = t0;
@@ -547,21 +552,45 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
       acc = 0.0;
       if (act) {
         double q = lambda * z;
-        for (int k = 0; k < wpp; ++k) {
-          const int e = bpp + 32 * k;
-          const int col = cpp[e];
-          if (col < 0) continue;
-          const double* pv = z_s + 3 * (col & kLocalMask);
-          const double* pa = vpp + (size_t)(e & ~31) * 9 + (e & 31) + 96 * c;   // row c of the 3x3 block
-          q += pa[0] * pv[0] + pa[32] * pv[1] + pa[64] * pv[2];
+        // U blocks per step: their column indices, then their gathers and values, are independent shared-memory loads
+        // (a block is three dependent round trips -- index, operands, multiply-add -- and a row has up to a dozen blocks)
+        for (int k0 = 0; k0 < wpp; k0 += U) {
+          int col[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) col[u] = k0 + u < wpp ? cpp[bpp + 32 * (k0 + u)] : -1;
+          double a[U][3], v[U][3];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            a[u][0] = a[u][1] = a[u][2] = v[u][0] = v[u][1] = v[u][2] = 0.0;
+            if (col[u] >= 0) {
+              const int e = bpp + 32 * (k0 + u);
+              const double* pv = z_s + 3 * (col[u] & kLocalMask);
+              const double* pa = vpp + (size_t)(e & ~31) * 9 + (e & 31) + 96 * c;   // row c of the 3x3 block
+              v[u][0] = pv[0]; v[u][1] = pv[1]; v[u][2] = pv[2];
+              a[u][0] = pa[0]; a[u][1] = pa[32]; a[u][2] = pa[64];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) q += a[u][0] * v[u][0] + a[u][1] * v[u][1] + a[u][2] * v[u][2];
         }
-        for (int k = 0; k < wpl; ++k) {
-          const int e = bpl + 32 * k;
-          const int col = cpl[e];
-          if (col < 0) continue;
-          const double* pt = t_s + 2 * (col & kLocalMask);
-          const double* pa = vpl + (size_t)(e & ~31) * 6 + (e & 31) + 64 * c;   // row c of the 3x2 block
-          q -= pa[0] * pt[0] + pa[32] * pt[1];
+        for (int k0 = 0; k0 < wpl; k0 += U) {
+          int col[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) col[u] = k0 + u < wpl ? cpl[bpl + 32 * (k0 + u)] : -1;
+          double a[U][2], tv[U][2];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            a[u][0] = a[u][1] = tv[u][0] = tv[u][1] = 0.0;
+            if (col[u] >= 0) {
+              const int e = bpl + 32 * (k0 + u);
+              const double* pt = t_s + 2 * (col[u] & kLocalMask);
+              const double* pa = vpl + (size_t)(e & ~31) * 6 + (e & 31) + 64 * c;   // row c of the 3x2 block
+              tv[u][0] = pt[0]; tv[u][1] = pt[1];
+              a[u][0] = pa[0]; a[u][1] = pa[32];
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) q -= a[u][0] * tv[u][0] + a[u][1] * tv[u][1];
         }
         d = z + beta * d;
         s = q + beta * s;
@@ -629,7 +658,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
 namespace sgb {
 #if defined(__CUDACC__)
 // Four lanes per row (pcg_resident_solve4): up to 1024 threads per CTA, a cluster of such CTAs or a single one.
-__global__ void __launch_bounds__(1024, 1) k_pcg_res4(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
+template <int MAXT, int U>  // MAXT = largest CTA (sets the register budget: 64 at 1024 threads, 128 at 512), U = blocks per step
+__global__ void __launch_bounds__(MAXT, 1) k_pcg_res4(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
   extern __shared__ __align__(16) unsigned char res_smem[];
   __shared__ double sm[32];
   __shared__ double cl_part[32];
@@ -637,8 +667,8 @@ __global__ void __launch_bounds__(1024, 1) k_pcg_res4(DevGraph g, DevScalars* sc
   unsigned long long seq = 0;
   const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   PcgOut out;
-  if (gridDim.x > 1) pcg_resident_solve4<true>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, seq, out);
-  else pcg_resident_solve4<false>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, seq, out);
+  if (gridDim.x > 1) pcg_resident_solve4<true, U>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, seq, out);
+  else pcg_resident_solve4<false, U>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, seq, out);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc->rz0 = out.gam0;
     sc->rz = out.gam;
