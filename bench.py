@@ -816,6 +816,14 @@ def main():
                 # PCG iterations of every k_pcg launch of one step, in launch order (maps an ncu capture of launch #k
                 # to its algorithmic bytes)
                 "pcg_iterations_per_lm_iteration": [int(x["pcg_iters"]) for x in last_stats]}
+    # the linearise + assemble stage against the same roofline (B_lin per evaluation), rank 0's share
+    b_lin = (80 * g.n_pp + 48 * g.n_pl + 120 * st["n_free_poses"] + 64 * st["n_free_landmarks"] + 72 * st["n_pairs_pp"] +
+             48 * st["n_pairs_pl"]) // world
+    lin_s = agg["linearize_ms"] * 1e-3
+    lin_gbs = b_lin * agg["linearizations"] / lin_s / 1e9 if lin_s > 0 else 0.0
+    roofline_lin = {"bound": "hbm", "kernel": "k_lin_pose + k_lin_lm (+ k_finalize_lin)", "achieved": lin_gbs, "peak": peak,
+                    "unit": "GB/s", "frac": lin_gbs / peak, "algorithmic_bytes_per_linearization": b_lin,
+                    "linearizations": agg["linearizations"], "share_of_step": agg["linearize_ms"] / dev_ms if dev_ms > 0 else None}
     line = {
         "metric": "LM iterations/s", "value": value, "unit": "LM iterations/s", "n_gpus": world, "steps": args.steps,
         "warmup": warmup, "ms_per_step": dev_ms_max / max(1, args.steps), "higher_is_better": True,
@@ -832,7 +840,7 @@ def main():
         "phases_ms": {k: agg[k] for k in ("linearize_ms", "setup_ms", "pcg_ms", "update_ms", "total_ms")},
         "lm_trials": agg["trials"], "set_graph_s": t_setgraph,
         "gpu_launches": int(agg["kernel_launches"]),
-        "clocks": clocks, "roofline": roofline,
+        "clocks": clocks, "roofline": roofline, "roofline_linearize": roofline_lin,
     }
     if e2e is not None:
         line["e2e"] = e2e

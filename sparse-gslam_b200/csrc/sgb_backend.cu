@@ -142,6 +142,8 @@ int grid_for(int n) {
   int b = (n + kThreads - 1) / kThreads;
   return std::max(1, std::min(b, 148 * 8));
 }
+// k_lin_lm: one warp per slice of the landmark-major matrix
+int lin_lm_grid(const DevGraph& G) { return grid_for(32 * G.Hlp.nslices); }
 
 // individually allocated (and individually freed) device memory
 template <class T>
@@ -266,7 +268,7 @@ sgb_status need_graph(sgb_handle* h) {
 // ---- launches (all on the handle's stream) --------------------------------------------------------------
 sgb_status launch_linearize(sgb_handle* h) {
   DevGraph& G = h->G;
-  int gp = grid_for(G.nP), gl = grid_for(G.nL);
+  int gp = grid_for(G.nP), gl = lin_lm_grid(G);
   if (G.nP > 0) k_lin_pose<<<gp, kThreads, 0, h->stream>>>(G, h->d_part_p);
   if (G.nL > 0) k_lin_lm<<<gl, kThreads, 0, h->stream>>>(G, h->d_part_l);
   h->tm.kernel_launches += (G.nP > 0) + (G.nL > 0);
@@ -278,7 +280,7 @@ sgb_status launch_finalize_lin(sgb_handle* h, int init_lambda) {
   DevGraph& G = h->G;
   double tau = h->opt.lm_tau > 0 ? h->opt.lm_tau : 1e-5;
   k_finalize_lin<<<1, kThreads, 0, h->stream>>>(G, h->d_sc, h->d_part_p, G.nP > 0 ? grid_for(G.nP) : 0, h->d_part_l,
-                                                G.nL > 0 ? grid_for(G.nL) : 0, init_lambda, tau, h->opt.lm_user_lambda);
+                                                G.nL > 0 ? lin_lm_grid(G) : 0, init_lambda, tau, h->opt.lm_user_lambda);
   h->tm.kernel_launches++;
   SGB_CUDA(cudaGetLastError());
   return SGB_OK;
@@ -919,6 +921,17 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   UP(pinc_ptr, P.pinc_ptr); UP(pinc, P.pinc); UP(linc_ptr, P.linc_ptr); UP(linc, P.linc);
   UP(hpp_diag, P.hpp_diag);
   if (P.pushed) { UP(send_ptr, P.send_ptr); UP(send_dst, P.send_dst); }
+  // maps of the lane-per-block landmark linearisation: entry -> leading edge, and the observations from fixed poses
+  // (function scope: alive until the stream has been synchronised at the end of this call)
+  std::vector<int32_t> hlp_edge((size_t)P.Hlp.entries(), -1), lfix_ptr((size_t)P.nL + 1, 0), lfix;
+  for (int k = 0; k < P.n_pl; ++k)
+    if (P.pl_e_lp[k] >= 0) hlp_edge[(size_t)P.pl_e_lp[k]] = k;
+  for (int l = 0; l < P.nL; ++l) {
+    for (int q = P.linc_ptr[l]; q < P.linc_ptr[l + 1]; ++q)
+      if (P.pl_hp[P.linc[q]] < 0) lfix.push_back(P.linc[q]);
+    lfix_ptr[(size_t)l + 1] = (int32_t)lfix.size();
+  }
+  UP(hlp_edge, hlp_edge); UP(lfix_ptr, lfix_ptr); UP(lfix, lfix);
   lap("upload maps");
   for (auto& t : workers) t.join();
   workers.clear();

@@ -105,6 +105,10 @@ struct DevGraph {
   Sell Hpl;                  // nP x Lf, 3x2 blocks row-major (NC = 6); columns = encoded landmarks
   Sell Hlp;                  // nL x Pf, the same 3x2 blocks (NC = 6), landmark-major; row r = local landmark r
   const int32_t* hpp_diag;   // [nP] Hpp entry of the diagonal block
+  const int32_t* hlp_edge;   // [Hlp entries] local pose-line edge that leads the vertex pair stored at this entry, -1 = padding
+                             //               (the landmark rows are linearised by one lane per entry, k_lin_lm)
+  const int32_t* lfix_ptr;   // [nL + 1] CSR over the landmark rows: their observations from FIXED poses (no Hessian block;
+  const int32_t* lfix;       //          usually only the first key-frame's), local edge indices in insertion order
   double* Hll;               // [3][nL] (11,12,22), stride nL
   double* b_p;               // [3*nP]
   // ---- vectors other ranks gather from: tbl[rank] is this rank's own array
