@@ -142,8 +142,9 @@ int grid_for(int n) {
   int b = (n + kThreads - 1) / kThreads;
   return std::max(1, std::min(b, 148 * 8));
 }
-// k_lin_lm: one warp per slice of the landmark-major matrix
+// k_lin_lm: one warp per slice of the landmark-major matrix; k_lin_pose: four lanes per pose row
 int lin_lm_grid(const DevGraph& G) { return grid_for(32 * G.Hlp.nslices); }
+int lin_pose_grid(const DevGraph& G) { return grid_for(4 * G.nP); }
 
 // individually allocated (and individually freed) device memory
 template <class T>
@@ -268,7 +269,7 @@ sgb_status need_graph(sgb_handle* h) {
 // ---- launches (all on the handle's stream) --------------------------------------------------------------
 sgb_status launch_linearize(sgb_handle* h) {
   DevGraph& G = h->G;
-  int gp = grid_for(G.nP), gl = lin_lm_grid(G);
+  int gp = lin_pose_grid(G), gl = lin_lm_grid(G);
   if (G.nP > 0) k_lin_pose<<<gp, kThreads, 0, h->stream>>>(G, h->d_part_p);
   if (G.nL > 0) k_lin_lm<<<gl, kThreads, 0, h->stream>>>(G, h->d_part_l);
   h->tm.kernel_launches += (G.nP > 0) + (G.nL > 0);
@@ -279,7 +280,7 @@ sgb_status launch_linearize(sgb_handle* h) {
 sgb_status launch_finalize_lin(sgb_handle* h, int init_lambda) {
   DevGraph& G = h->G;
   double tau = h->opt.lm_tau > 0 ? h->opt.lm_tau : 1e-5;
-  k_finalize_lin<<<1, kThreads, 0, h->stream>>>(G, h->d_sc, h->d_part_p, G.nP > 0 ? grid_for(G.nP) : 0, h->d_part_l,
+  k_finalize_lin<<<1, kThreads, 0, h->stream>>>(G, h->d_sc, h->d_part_p, G.nP > 0 ? lin_pose_grid(G) : 0, h->d_part_l,
                                                 G.nL > 0 ? lin_lm_grid(G) : 0, init_lambda, tau, h->opt.lm_user_lambda);
   h->tm.kernel_launches++;
   SGB_CUDA(cudaGetLastError());
@@ -690,6 +691,14 @@ __global__ void __launch_bounds__(kThreads) k_gather_pl(const int32_t* __restric
   }
 }
 
+// out[map[k]] = k for every k with map[k] >= 0 (out pre-filled with -1): the inverse of an injective scatter map
+__global__ void __launch_bounds__(kThreads) k_invert_map(const int32_t* __restrict__ map, int n, int32_t* __restrict__ out) {
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int e = map[k];
+    if (e >= 0) out[e] = k;
+  }
+}
+
 // ---- LinearSolver-level entry: block values handed over in g2o's SparseBlockMatrix order ----------------------------
 // one thread per input block: copies its values (column-major, like Eigen) into the SELL / Hll slots of the device
 // layout. kind 0 = pose diagonal (Hpp entry e1), 1 = landmark diagonal (Hll index e1), 2 = pose-pose off-diagonal
@@ -923,15 +932,36 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   if (P.pushed) { UP(send_ptr, P.send_ptr); UP(send_dst, P.send_dst); }
   // maps of the lane-per-block landmark linearisation: entry -> leading edge, and the observations from fixed poses
   // (function scope: alive until the stream has been synchronised at the end of this call)
-  std::vector<int32_t> hlp_edge((size_t)P.Hlp.entries(), -1), lfix_ptr((size_t)P.nL + 1, 0), lfix;
-  for (int k = 0; k < P.n_pl; ++k)
-    if (P.pl_e_lp[k] >= 0) hlp_edge[(size_t)P.pl_e_lp[k]] = k;
-  for (int l = 0; l < P.nL; ++l) {
-    for (int q = P.linc_ptr[l]; q < P.linc_ptr[l + 1]; ++q)
-      if (P.pl_hp[P.linc[q]] < 0) lfix.push_back(P.linc[q]);
-    lfix_ptr[(size_t)l + 1] = (int32_t)lfix.size();
+  // The entry -> edge map is the inverse of pl_e_lp, which is on the device already: scattered there (k_invert_map). The
+  // observations from fixed poses are few (the reference fixes the first pose only): one scan of the edges' pose indices
+  // finds them, then they are bucketed by landmark row in insertion order.
+  std::vector<int32_t> lfix_ptr((size_t)P.nL + 1, 0), lfix;
+  {
+    std::vector<std::pair<int32_t, int32_t>> fx;  // (landmark row, local edge)
+    std::vector<int32_t> row_of_edge;
+    for (int k = 0; k < P.n_pl; ++k)
+      if (P.pl_hp[k] < 0 && P.pl_hl[k] >= 0) fx.push_back({-1, k});
+    if (!fx.empty()) {  // their rows: the incidence lists of the landmarks name them (only walked when there is something to find)
+      std::vector<char> want((size_t)P.n_pl, 0);
+      for (auto& f : fx) want[(size_t)f.second] = 1;
+      fx.clear();
+      for (int l = 0; l < P.nL; ++l)
+        for (int q = P.linc_ptr[l]; q < P.linc_ptr[l + 1]; ++q)
+          if (want[(size_t)P.linc[q]]) fx.push_back({l, P.linc[q]});
+    }
+    for (auto& f : fx) lfix_ptr[(size_t)f.first + 1]++;
+    for (int l = 0; l < P.nL; ++l) lfix_ptr[(size_t)l + 1] += lfix_ptr[(size_t)l];
+    for (auto& f : fx) lfix.push_back(f.second);  // fx is ordered by (row, position in the row's insertion-ordered list)
   }
-  UP(hlp_edge, hlp_edge); UP(lfix_ptr, lfix_ptr); UP(lfix, lfix);
+  UP(lfix_ptr, lfix_ptr); UP(lfix, lfix);
+  {
+    int32_t* d_map = nullptr;
+    if ((st = dalloc(h, &d_map, (size_t)P.Hlp.entries())) != SGB_OK) return st;
+    SGB_CUDA(cudaMemsetAsync(d_map, 0xff, std::max<size_t>((size_t)P.Hlp.entries(), 1) * sizeof(int32_t), h->stream));
+    if (P.n_pl > 0) k_invert_map<<<grid_for(P.n_pl), kThreads, 0, h->stream>>>(G.pl_e_lp, P.n_pl, d_map);
+    SGB_CUDA(cudaGetLastError());
+    G.hlp_edge = d_map;
+  }
   lap("upload maps");
   for (auto& t : workers) t.join();
   workers.clear();

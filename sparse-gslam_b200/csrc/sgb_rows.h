@@ -186,13 +186,10 @@ SGB_HD void pp_chain_block(const DevGraph& g, int k, const PPTerm& t, int row_h,
 }
 
 // linearise + assemble, owned pose row lp: diagonal block, gradient, and the off-diagonal blocks of THIS row
-SGB_HD void lin_pose_row(const DevGraph& g, int lp, LinAcc& acc) {
-  const double* pose = cur_pose(g);
-  const double* lm = cur_lm(g);
-  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-  double bv[3] = {0, 0, 0};
-  int beg = g.pinc_ptr[lp], end = g.pinc_ptr[lp + 1];
-  for (int it = beg; it < end; ++it) {
+// one entry of a pose row's incidence list: the edge's contribution to the row's diagonal block H and gradient bv, the
+// off-diagonal block(s) this row owns (written to Hpp / Hpl), the edge's chi2 if it is accounted on this row
+SGB_HD void lin_pose_entry(const DevGraph& g, const double* pose, const double* lm, int it, double H[9], double bv[3], LinAcc& acc) {
+  {
     int packed = SGB_LDG(&g.pinc[it]);
     int k = packed >> 2, role = (packed >> 1) & 1, type = packed & 1;
     if (type == 0) {
@@ -257,11 +254,49 @@ SGB_HD void lin_pose_row(const DevGraph& g, int lp, LinAcc& acc) {
       }
     }
   }
+}
+// linearise + assemble, owned pose row lp: diagonal block, gradient, and the off-diagonal blocks of THIS row
+SGB_HD void lin_pose_row(const DevGraph& g, int lp, LinAcc& acc) {
+  const double* pose = cur_pose(g);
+  const double* lm = cur_lm(g);
+  double H[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double bv[3] = {0, 0, 0};
+  int beg = g.pinc_ptr[lp], end = g.pinc_ptr[lp + 1];
+  for (int it = beg; it < end; ++it) lin_pose_entry(g, pose, lm, it, H, bv, acc);
   int ed = g.hpp_diag[lp];
   for (int c = 0; c < 9; ++c) g.Hpp.vals[sell_vaddr(ed, 9, c)] = H[c];
   for (int r = 0; r < 3; ++r) g.b_p[3 * (size_t)lp + r] = bv[r];
   acc.maxd = fmax(acc.maxd, fmax(fabs(H[0]), fmax(fabs(H[4]), fabs(H[8]))));
 }
+#if defined(__CUDACC__)
+// The same row on FOUR lanes: lane `sub` takes the incidence entries sub, sub + 4, ... (each entry is an independent edge
+// evaluation with its own chain of gathers), the four partial sums of the diagonal block and the gradient are then added
+// in lane order ((p0 + p1) + p2) + p3 -- a fixed order that depends on the row's incidence list only, so the result is
+// the same for every partition of the graph; it differs from the serial row above by rounding. All four lanes of a row's
+// group must call (active == false for the lanes of a group beyond the last row).
+__device__ __forceinline__ void lin_pose_row_lanes(const DevGraph& g, int lp, int sub, bool active, LinAcc& acc) {
+  const double* pose = cur_pose(g);
+  const double* lm = cur_lm(g);
+  double v[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};  // H (9), bv (3)
+  if (active) {
+    const int beg = g.pinc_ptr[lp], end = g.pinc_ptr[lp + 1];
+    for (int it = beg + sub; it < end; it += 4) lin_pose_entry(g, pose, lm, it, v, v + 9, acc);
+  }
+  const unsigned lane = threadIdx.x & 31u, base = lane & ~3u, mask = 0xfu << base;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const double p0 = __shfl_sync(mask, v[q], (int)base), p1 = __shfl_sync(mask, v[q], (int)base + 1);
+    const double p2 = __shfl_sync(mask, v[q], (int)base + 2), p3 = __shfl_sync(mask, v[q], (int)base + 3);
+    v[q] = ((p0 + p1) + p2) + p3;
+  }
+  if (active && sub == 0) {
+    const int ed = g.hpp_diag[lp];
+    for (int c = 0; c < 9; ++c) g.Hpp.vals[sell_vaddr(ed, 9, c)] = v[c];
+    for (int r = 0; r < 3; ++r) g.b_p[3 * (size_t)lp + r] = v[9 + r];
+    acc.maxd = fmax(acc.maxd, fmax(fabs(v[0]), fmax(fabs(v[4]), fabs(v[8]))));
+  }
+}
+#endif
 
 // linearise + assemble, owned landmark row ll: 2x2 diagonal block, gradient, and the landmark-major copy of the
 // pose-line blocks (recomputed here so that every rank writes only rows it owns)
