@@ -142,9 +142,9 @@ int grid_for(int n) {
   int b = (n + kThreads - 1) / kThreads;
   return std::max(1, std::min(b, 148 * 8));
 }
-// k_lin_lm: one warp per slice of the landmark-major matrix; k_lin_pose: four lanes per pose row
+// k_lin_lm: one warp per slice of the landmark-major matrix; k_lin_pose: one thread per pose row
 int lin_lm_grid(const DevGraph& G) { return grid_for(32 * G.Hlp.nslices); }
-int lin_pose_grid(const DevGraph& G) { return grid_for(4 * G.nP); }
+int lin_pose_grid(const DevGraph& G) { return grid_for(G.nP); }
 
 // individually allocated (and individually freed) device memory
 template <class T>
@@ -934,24 +934,21 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
   // (function scope: alive until the stream has been synchronised at the end of this call)
   // The entry -> edge map is the inverse of pl_e_lp, which is on the device already: scattered there (k_invert_map). The
   // observations from fixed poses are few (the reference fixes the first pose only): one scan of the edges' pose indices
-  // finds them, then they are bucketed by landmark row in insertion order.
+  // finds them, then they are bucketed by landmark row, in insertion order inside a row.
   std::vector<int32_t> lfix_ptr((size_t)P.nL + 1, 0), lfix;
   {
-    std::vector<std::pair<int32_t, int32_t>> fx;  // (landmark row, local edge)
-    std::vector<int32_t> row_of_edge;
-    for (int k = 0; k < P.n_pl; ++k)
-      if (P.pl_hp[k] < 0 && P.pl_hl[k] >= 0) fx.push_back({-1, k});
-    if (!fx.empty()) {  // their rows: the incidence lists of the landmarks name them (only walked when there is something to find)
-      std::vector<char> want((size_t)P.n_pl, 0);
-      for (auto& f : fx) want[(size_t)f.second] = 1;
-      fx.clear();
-      for (int l = 0; l < P.nL; ++l)
-        for (int q = P.linc_ptr[l]; q < P.linc_ptr[l + 1]; ++q)
-          if (want[(size_t)P.linc[q]]) fx.push_back({l, P.linc[q]});
+    struct Fx { int32_t row, gedge, k; };  // landmark row on this rank, global (insertion-ordered) edge index, local edge
+    std::vector<Fx> fx;
+    for (int k = 0; k < P.n_pl; ++k) {
+      if (!(P.pl_hp[k] < 0 && P.pl_hl[k] >= 0)) continue;
+      const int32_t enc = P.enc_lm_here.empty() ? P.enc_lm[P.pl_hl[k]] : P.enc_lm_here[P.pl_hl[k]];
+      if (enc < 0 || (enc >> kOwnerShift) != rank) continue;  // a landmark row kept elsewhere
+      fx.push_back({enc & kLocalMask, P.pl_g[k], k});
     }
-    for (auto& f : fx) lfix_ptr[(size_t)f.first + 1]++;
+    std::sort(fx.begin(), fx.end(), [](const Fx& a, const Fx& b) { return a.row != b.row ? a.row < b.row : a.gedge < b.gedge; });
+    for (auto& f : fx) lfix_ptr[(size_t)f.row + 1]++;
     for (int l = 0; l < P.nL; ++l) lfix_ptr[(size_t)l + 1] += lfix_ptr[(size_t)l];
-    for (auto& f : fx) lfix.push_back(f.second);  // fx is ordered by (row, position in the row's insertion-ordered list)
+    for (auto& f : fx) lfix.push_back(f.k);
   }
   UP(lfix_ptr, lfix_ptr); UP(lfix, lfix);
   {

@@ -156,12 +156,13 @@ __global__ void k_xbarrier(DevGraph g, DevScalars* sc) {
 
 // ------------------------------------------------------------------------------------------------ linearise
 // part layout: [0]=chi [1]=chi_r [2]=maxd, each kMaxBlocks wide
-// four lanes per pose row (lin_pose_row_lanes): a row's ~7 incident edges are independent evaluations
+// One thread per pose row. (Four lanes per row -- lin_pose_row_lanes, kept in sgb_rows.h -- were measured on the 1M-pose
+// graph: 662 us instead of 357: with consecutive lanes on the same row the writes of the k-th off-diagonal block of
+// consecutive rows are no longer coalesced, and the 12 x 4 shuffles of the combine step spill at 128 registers.)
 __global__ void __launch_bounds__(kThreads) k_lin_pose(DevGraph g, double* part) {
   __shared__ double sm[32];
   LinAcc acc;
-  const int nthreads = gridDim.x * blockDim.x;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; (t >> 2) < g.nP; t += nthreads) lin_pose_row_lanes(g, t >> 2, t & 3, true, acc);
+  for (int lp = blockIdx.x * blockDim.x + threadIdx.x; lp < g.nP; lp += gridDim.x * blockDim.x) lin_pose_row(g, lp, acc);
   double c = block_sum(acc.chi, sm), cr = block_sum(acc.chi_r, sm), m = block_max(acc.maxd, sm);
   if (threadIdx.x == 0) {
     part[blockIdx.x] = c;
