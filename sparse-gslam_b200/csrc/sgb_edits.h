@@ -204,39 +204,39 @@ SGB_HD F4 ld_cov(const float* p) {
 #endif
 }
 SGB_HD void line_fit(const float* pts, const float* pcov, int n, float rhotheta[2], float cov[4]) {
-  float sx = 0.0f, sy = 0.0f, sxy = 0.0f, sxx = 0.0f, syy = 0.0f;
+  float sx = 0.0f, sy = 0.0f, sum_xy = 0.0f, sum_xx = 0.0f, sum_yy = 0.0f;
   for (int i = 0; i < n; ++i) {
     F2 pt = ld_pt(pts + 2 * (size_t)i);
     float x = pt.x, y = pt.y;
     sx += x;
     sy += y;
-    sxy += x * y;
-    sxx += x * x;
-    syy += y * y;
+    sum_xy += x * y;
+    sum_xx += x * x;
+    sum_yy += y * y;
   }
   const float nf = (float)n;
-  float xbar = sx / nf, ybar = sy / nf;
-  sxx -= nf * (xbar * xbar);
-  syy -= nf * (ybar * ybar);
-  sxy -= nf * (xbar * ybar);
-  float d = syy - sxx;
-  rhotheta[1] = (float)(0.5 * (double)atan2f(-2 * sxy, d));  // float atan2, then the double literal 0.5 promotes
-  float ct = cosf(rhotheta[1]), st = sinf(rhotheta[1]);
-  rhotheta[0] = xbar * ct + ybar * st;
+  float mean_x = sx / nf, mean_y = sy / nf;
+  sum_xx -= nf * (mean_x * mean_x);
+  sum_yy -= nf * (mean_y * mean_y);
+  sum_xy -= nf * (mean_x * mean_y);
+  float d = sum_yy - sum_xx;
+  rhotheta[1] = (float)(0.5 * (double)atan2f(-2 * sum_xy, d));  // float atan2, then the double literal 0.5 promotes
+  float cos_t = cosf(rhotheta[1]), sin_t = sinf(rhotheta[1]);
+  rhotheta[0] = mean_x * cos_t + mean_y * sin_t;
   check_rho_theta_f(rhotheta);
-  ct = cosf(rhotheta[1]);
-  st = sinf(rhotheta[1]);
-  float xbar_st = xbar * st, ybar_ct = ybar * ct;
+  cos_t = cosf(rhotheta[1]);
+  sin_t = sinf(rhotheta[1]);
+  float mean_x_sin = mean_x * sin_t, mean_y_cos = mean_y * cos_t;
   cov[0] = cov[1] = cov[2] = cov[3] = 0.0f;
-  float denum = (float)(1.0 / (double)(d * d + 4 * sxy * sxy));
-  float ct_n = ct / nf, st_n = st / nf;
+  float inv_norm = (float)(1.0 / (double)(d * d + 4 * sum_xy * sum_xy));
+  float cos_over_n = cos_t / nf, sin_over_n = sin_t / nf;
   for (int i = 0; i < n; ++i) {
     F2 pt = ld_pt(pts + 2 * (size_t)i);
-    float dx = xbar - pt.x, dy = ybar - pt.y;
-    float a10 = (dy * d + 2 * sxy * dx) * denum;
-    float a11 = (dx * d - 2 * sxy * dy) * denum;
-    float a00 = ct_n - xbar_st * a10 + ybar_ct * a10;
-    float a01 = st_n - xbar_st * a11 + ybar_ct * a11;
+    float dx = mean_x - pt.x, dy = mean_y - pt.y;
+    float a10 = (dy * d + 2 * sum_xy * dx) * inv_norm;
+    float a11 = (dx * d - 2 * sum_xy * dy) * inv_norm;
+    float a00 = cos_over_n - mean_x_sin * a10 + mean_y_cos * a10;
+    float a01 = sin_over_n - mean_x_sin * a11 + mean_y_cos * a11;
     const F4 C = ld_cov(pcov + 4 * (size_t)i);
     // cov += Ai * C * Ai^T, (Ai * C) first
     float m00 = a00 * C.a + a01 * C.c, m01 = a00 * C.b + a01 * C.d;

@@ -127,13 +127,35 @@ void build_grouped_sell(const FlatRows& rows, int target_steps, HostSell& S) {
 
 // block-steps per lane in the landmark pass: a large matrix is throughput-bound (fewer, longer lane loops issue
 // fewer warp-steps), a small one latency-bound (more lanes per row shorten the dependent chain)
-int lm_target_steps(size_t blocks) {
+int lm_target_steps(const FlatRows& rows) {
   static const int forced = [] {
     const char* e = std::getenv("SGB_LM_STEPS");  // tuning knob
     return e ? std::atoi(e) : 0;
   }();
   if (forced > 0) return forced;
-  return blocks >= ((size_t)1 << 20) ? 10 : 2;
+  const size_t blocks = rows.col.size();
+  if (blocks >= ((size_t)1 << 20)) return 10;
+  // Latency-bound sizes: a warp of the persistent kernel (3 CTAs x 148 SMs x 8 warps) takes the slices w, w + warps, ...
+  // one after the other, each slice costing its number of block-steps. Few steps per slice means many slices: on one of
+  // eight shards of a 1M-pose graph 2 steps give 13 000 slices = FOUR per warp (8 step-units), 5 steps give 3 250 = one
+  // per warp (5 step-units). Pick the target that minimises ceil(slices / warps) x steps; small graphs (fewer slices
+  // than warps whatever the target) keep the shortest chain, 2.
+  const int warps = 148 * 3 * 8;
+  int best = 2;
+  long best_cost = -1;
+  for (int ts : {2, 3, 4, 5, 6, 8, 10}) {
+    long slices = 0, steps_max = 0;
+    for (int r = 0, n = rows.rows(); r < n;) {
+      const int len = rows.size(r);
+      const int G = std::min(32, pow2_ceil((len + ts - 1) / ts));
+      slices++;
+      steps_max = std::max<long>(steps_max, (len + G - 1) / G);
+      r += 32 / G;
+    }
+    const long cost = ((slices + warps - 1) / warps) * std::max<long>(steps_max, 1);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = ts; }
+  }
+  return best;
 }
 
 // world == 1: the local plan IS the global structure -- same rows, same edge order, same pose-major SELL layout;
@@ -180,7 +202,7 @@ sgb_status partition_single(const Structure& S, LocalPlan& P, Structure* consume
       obs.col.insert(obs.col.end(), S.lp_col.begin() + S.lp_ptr[hl], S.lp_col.begin() + S.lp_ptr[hl + 1]);
       obs.close_row();
     }
-    build_grouped_sell(obs, lm_target_steps(obs.col.size()), P.Hlp);
+    build_grouped_sell(obs, lm_target_steps(obs), P.Hlp);
     // needs Hlp: the landmark-major entry of every leading pose-line edge (independent per edge: two threads when large)
     P.pl_e_lp.assign(S.n_pl, -1);
     auto entries = [&](int k0, int k1) {
@@ -412,7 +434,7 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
     }
   };
   auto finish_lm_rows = [&]() {
-    build_grouped_sell(obs, lm_target_steps(obs.col.size()), P.Hlp);  // rows already sorted by descending length
+    build_grouped_sell(obs, lm_target_steps(obs), P.Hlp);  // rows already sorted by descending length
   };
   const bool threaded = (size_t)P.n_pp + P.n_pl > 200000;
   if (threaded) {
