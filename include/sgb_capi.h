@@ -59,6 +59,9 @@ typedef struct sgb_options {
   int32_t lm_max_trials;    /* <=0 -> 10 (g2o maxTrialsAfterFailure) */
   int32_t incremental;      /* != 0: the handle keeps what sgb_update_graph needs (an index mirror of the graph on the host
                              * and the raw edge values on the device); 0 (default): sgb_set_graph keeps nothing of the caller's */
+  int32_t coarse_nodes;     /* two-level preconditioner of the resident solve (small graphs on one GPU; no reference
+                             * counterpart, LinearSolverEigen factorises exactly): > 0 = at most this many coarse nodes
+                             * (<= 40), < 0 = off, 0 = the library default (environment SGB_COARSE / SGB_COARSE_NODES) */
 } sgb_options;
 
 /* Host SoA graph. Edges reference vertices by ARRAY INDEX; ids only define g2o's vertex

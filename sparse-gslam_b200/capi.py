@@ -30,7 +30,8 @@ EXPORTS = [
 class Options(C.Structure):
     _fields_ = [("device", C.c_int32), ("jacobian_mode", C.c_int32), ("pcg_tolerance", C.c_double),
                 ("pcg_max_iters", C.c_int32), ("verbose", C.c_int32), ("lm_tau", C.c_double),
-                ("lm_user_lambda", C.c_double), ("lm_max_trials", C.c_int32), ("incremental", C.c_int32)]
+                ("lm_user_lambda", C.c_double), ("lm_max_trials", C.c_int32), ("incremental", C.c_int32),
+                ("coarse_nodes", C.c_int32)]
 
 
 class GraphSoA(C.Structure):

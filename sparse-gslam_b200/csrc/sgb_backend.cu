@@ -100,6 +100,7 @@ struct sgb_handle {
   ResPlan res;          // valid: the graph fits one cluster's shared memory -> the cluster-resident solve (sgb_resident.cuh)
   ResPlan res_block;    // valid: the graph fits ONE 256-thread CTA -> the resident solve inside the batched kernel
   ResPlan res4;         // valid: the resident solve with four lanes per pose row (one CTA of up to 1024 threads, or a cluster)
+  CoarsePlan cz;        // host gather lists of the two-level preconditioner's coarse matrix (res4.cz_nc > 0; sgb_coarse.h)
   // LinearSolver-level entry (sgb_linear_set_pattern / sgb_linear_solve): per input block its value offset, kind and
   // the SELL entries it lands in; device copies live in the pooled memory of the current graph
   struct LinearMap {
@@ -299,6 +300,11 @@ sgb_status launch_setup(sgb_handle* h, double lambda_override, int use_override)
     k_setup_pose<<<grid_for(G.nP), kThreads, 0, h->stream>>>(G, h->d_sc, lambda_override, use_override);
   }
   h->tm.kernel_launches += 2 * (G.nP > 0) + (G.nL > 0);
+  if (G.cz_h > 0) {  // coarse matrix of the two-level preconditioner -> its inverse (needs k_setup_lm's (Hll + lambda I)^-1)
+    const int nc = 3 * G.cz_nn;
+    k_setup_coarse<<<1, 1024, ((size_t)nc * cz_ld(nc) + nc) * sizeof(double), h->stream>>>(G, h->d_sc, lambda_override, use_override);
+    h->tm.kernel_launches++;
+  }
   SGB_CUDA(cudaGetLastError());
   return SGB_OK;
 }
@@ -316,9 +322,15 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   static const bool no_res1 = std::getenv("SGB_NO_RESIDENT1") != nullptr;
   if (h->res4.valid && G.world == 1) {  // four lanes per pose row, everything on chip
     ResPlan rp = h->res4;
+    const bool cz = rp.cz_nc > 0;
     if (rp.ncta == 1) {
-      if (rp.bt <= 512) k_pcg_res4<512, 4><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
-      else k_pcg_res4<1024, 2><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+      if (rp.bt <= 512) {
+        if (cz) k_pcg_res4<512, 4, true><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+        else k_pcg_res4<512, 4, false><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+      } else {
+        if (cz) k_pcg_res4<1024, 2, true><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+        else k_pcg_res4<1024, 2, false><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
+      }
       SGB_CUDA(cudaGetLastError());
     } else {
       cudaLaunchConfig_t cfg = {};
@@ -333,8 +345,13 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
       at[0].val.clusterDim.z = 1;
       cfg.attrs = at;
       cfg.numAttrs = 1;
-      if (rp.bt <= 512) SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4<512, 4>, G, sc, prm, rp));
-      else SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4<1024, 2>, G, sc, prm, rp));
+      if (rp.bt <= 512) {
+        if (cz) SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4<512, 4, true>, G, sc, prm, rp));
+        else SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4<512, 4, false>, G, sc, prm, rp));
+      } else {
+        if (cz) SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4<1024, 2, true>, G, sc, prm, rp));
+        else SGB_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_res4<1024, 2, false>, G, sc, prm, rp));
+      }
     }
   } else if (h->res_block.valid && G.world == 1 && !no_res1) {  // the whole graph in ONE CTA: block barriers only
     ResPlan rp = h->res_block;
@@ -1061,7 +1078,7 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
       int cb = 1;
       while (cb < need) cb <<= 1;
       if (cb > 16 || (cb > 8 && !np_ok)) continue;
-      ResPlan rp;
+      ResPlan rp = ResPlan();
       rp.valid = 0; rp.bt = bt; rp.ncta = cb;
       rp.cap_pp = cap_of(P.Hpp, spc, cb); rp.cap_pl = cap_of(P.Hpl, spc, cb); rp.cap_lp = cap_of(P.Hlp, spc, cb);
       rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
@@ -1091,59 +1108,101 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
     }
     {  // four lanes per pose row: one CTA if the graph fits it, else the smallest cluster
       h->res4 = ResPlan();
+      h->cz = CoarsePlan();
       static const bool no_res4 = std::getenv("SGB_NO_RES4") != nullptr;
-      static const bool np4_ok = cudaFuncSetAttribute(k_pcg_res4<512, 4>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
-                                 cudaFuncSetAttribute(k_pcg_res4<1024, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
-      bool done4 = no_res4;
-      for (int pass = 0; pass < 2 && !done4; ++pass)        // pass 0: single CTA, pass 1: clusters
-        for (int ib = 0; ib < 3 && !done4; ++ib) {
-          static const int kBt[2][3] = {{256, 512, 1024}, {1024, 512, 256}};  // smallest CTA that holds the rows / fewest CTAs
-          const int bt = kBt[pass][ib];
-          const int rows_cta = bt / 4, spc_p = rows_cta / 32, spc_l = bt / 32;
-          if (spc_p < 1) continue;
-          int need = std::max((P.nP + rows_cta - 1) / rows_cta, pass == 0 ? 1 : (P.Hlp.nslices + spc_l - 1) / spc_l);
-          int cb = 1;
-          while (cb < need) cb <<= 1;
-          if ((pass == 0) != (cb == 1)) continue;
-          if (cb > 16 || (cb > 8 && !np4_ok)) continue;
-          ResPlan rp;
-          rp.valid = 0; rp.bt = bt; rp.ncta = cb; rp.rows_cta = rows_cta;
-          rp.cap_pp = cap_of(P.Hpp, spc_p, cb); rp.cap_pl = cap_of(P.Hpl, spc_p, cb);
-          rp.cap_lp = cb == 1 ? (int)P.Hlp.entries() : cap_of(P.Hlp, spc_l, cb);
-          rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
-          rp.cap_sl = cb == 1 ? std::max(1, P.Hlp.nslices) : spc_l;
-          rp.cap_lr = cb == 1 ? std::max(1, P.nL) : 32 * spc_l;
-          rp.bytes = (int)res_offsets(rp).total;
-          if (rp.bytes > 224 * 1024) continue;
-          const void* fn4 = bt <= 512 ? (const void*)k_pcg_res4<512, 4> : (const void*)k_pcg_res4<1024, 2>;
-          if (cudaFuncSetAttribute(fn4, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024) != cudaSuccess) { cudaGetLastError(); continue; }
-          if (cb > 1) {
-            cudaLaunchConfig_t cfg = {};
-            cfg.gridDim = dim3(cb);
-            cfg.blockDim = dim3(bt);
-            cfg.dynamicSmemBytes = (size_t)rp.bytes;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = cb;
-            at[0].val.clusterDim.y = 1;
-            at[0].val.clusterDim.z = 1;
-            cfg.attrs = at;
-            cfg.numAttrs = 1;
-            int nclusters = 0;
-            cudaError_t eo = bt <= 512 ? cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_res4<512, 4>, &cfg)
-                                       : cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_res4<1024, 2>, &cfg);
-            if (!(eo == cudaSuccess && nclusters >= 1)) { cudaGetLastError(); continue; }
+      static const bool np4_ok = cudaFuncSetAttribute(k_pcg_res4<512, 4, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                                 cudaFuncSetAttribute(k_pcg_res4<1024, 2, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                                 cudaFuncSetAttribute(k_pcg_res4<512, 4, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
+                                 cudaFuncSetAttribute(k_pcg_res4<1024, 2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+      // Two-level preconditioner (sgb_coarse.h): planned first WITH the coarse inverse in every CTA's shared memory, then
+      // without it. sgb_options.coarse_nodes, else SGB_COARSE=1 (+ SGB_COARSE_NODES) in the environment, switch it on.
+      static const int cz_default = [] {
+        const char* on = std::getenv("SGB_COARSE");
+        if (!on || std::atoi(on) == 0) return 0;
+        const char* e = std::getenv("SGB_COARSE_NODES");
+        return e ? std::atoi(e) : kCzMaxNodes;
+      }();
+      const int cz_nodes = std::max(0, std::min(h->opt.coarse_nodes != 0 ? h->opt.coarse_nodes : cz_default, kCzMaxNodes));
+      const int cz_h = cz_nodes > 0 ? coarse_spacing(P.nP, cz_nodes) : 0;
+      auto plan4 = [&](int h_cz) {
+        for (int pass = 0; pass < 2; ++pass)        // pass 0: single CTA, pass 1: clusters
+          for (int ib = 0; ib < 3; ++ib) {
+            static const int kBt[2][3] = {{256, 512, 1024}, {1024, 512, 256}};  // smallest CTA that holds the rows / fewest CTAs
+            const int bt = kBt[pass][ib];
+            const int rows_cta = bt / 4, spc_p = rows_cta / 32, spc_l = bt / 32;
+            if (spc_p < 1) continue;
+            if (h_cz > 0 && rows_cta % h_cz != 0) continue;  // a segment of the coarse space never spans two CTAs
+            int need = std::max((P.nP + rows_cta - 1) / rows_cta, pass == 0 ? 1 : (P.Hlp.nslices + spc_l - 1) / spc_l);
+            int cb = 1;
+            while (cb < need) cb <<= 1;
+            if ((pass == 0) != (cb == 1)) continue;
+            if (cb > 16 || (cb > 8 && !np4_ok)) continue;
+            ResPlan rp = ResPlan();
+            rp.valid = 0; rp.bt = bt; rp.ncta = cb; rp.rows_cta = rows_cta;
+            rp.cap_pp = cap_of(P.Hpp, spc_p, cb); rp.cap_pl = cap_of(P.Hpl, spc_p, cb);
+            rp.cap_lp = cb == 1 ? (int)P.Hlp.entries() : cap_of(P.Hlp, spc_l, cb);
+            rp.nz = (3 * P.nP + 1) & ~1; rp.nt = std::max(2, 2 * P.nL);
+            rp.cap_sl = cb == 1 ? std::max(1, P.Hlp.nslices) : spc_l;
+            rp.cap_lr = cb == 1 ? std::max(1, P.nL) : 32 * spc_l;
+            rp.cz_h = h_cz;
+            rp.cz_nc = h_cz > 0 ? 3 * ((P.nP + h_cz - 1) / h_cz + 1) : 0;
+            rp.bytes = (int)res_offsets(rp).total;
+            if (rp.bytes > (h_cz > 0 ? 218 : 224) * 1024) continue;  // the coarse build keeps 5.4 KB more of static shared memory
+            const void* fn4 = h_cz > 0 ? (bt <= 512 ? (const void*)k_pcg_res4<512, 4, true> : (const void*)k_pcg_res4<1024, 2, true>)
+                                       : (bt <= 512 ? (const void*)k_pcg_res4<512, 4, false> : (const void*)k_pcg_res4<1024, 2, false>);
+            if (cudaFuncSetAttribute(fn4, cudaFuncAttributeMaxDynamicSharedMemorySize, (h_cz > 0 ? 218 : 224) * 1024) != cudaSuccess) { cudaGetLastError(); continue; }
+            if (cb > 1) {
+              cudaLaunchConfig_t cfg = {};
+              cfg.gridDim = dim3(cb);
+              cfg.blockDim = dim3(bt);
+              cfg.dynamicSmemBytes = (size_t)rp.bytes;
+              cudaLaunchAttribute at[1];
+              at[0].id = cudaLaunchAttributeClusterDimension;
+              at[0].val.clusterDim.x = cb;
+              at[0].val.clusterDim.y = 1;
+              at[0].val.clusterDim.z = 1;
+              cfg.attrs = at;
+              cfg.numAttrs = 1;
+              int nclusters = 0;
+              cudaError_t eo = cudaOccupancyMaxActiveClusters(&nclusters, fn4, &cfg);
+              if (!(eo == cudaSuccess && nclusters >= 1)) { cudaGetLastError(); continue; }
+            }
+            rp.valid = 1;
+            h->res4 = rp;
+            return true;
           }
-          rp.valid = 1;
-          h->res4 = rp;
-          done4 = true;
+        return false;
+      };
+      if (!no_res4) {
+        bool with_cz = false;
+        if (cz_h > 0) {
+          const bool cz_attr = cudaFuncSetAttribute(k_setup_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                           (int)(((size_t)kCzMaxDim * cz_ld(kCzMaxDim) + kCzMaxDim) * sizeof(double))) == cudaSuccess;
+          with_cz = cz_attr && plan4(cz_h);
+          cudaGetLastError();
         }
-      if (prof) std::fprintf(stderr, "[sgb_set_graph] resident solve, four lanes per row: %s (%d CTAs x %d threads, %d bytes)\n",
-                             h->res4.valid ? "yes" : "no", h->res4.ncta, h->res4.bt, h->res4.bytes);
+        if (!with_cz) plan4(0);
+        if (h->res4.valid && h->res4.cz_nc > 0) {  // gather lists of the coarse matrix, scratch and the inverse
+          plan_coarse(P, cz_h, h->cz);
+          const CoarsePlan& C = h->cz;
+          sgb_status stc;
+          G.cz_h = C.h; G.cz_nn = C.nn; G.cz_ng = C.ng;
+          if ((stc = upload(h, &G.cz_g_ptr, C.g_ptr)) != SGB_OK || (stc = upload(h, &G.cz_g_e, C.g_e)) != SGB_OK ||
+              (stc = upload(h, &G.cz_g_w, C.g_w)) != SGB_OK || (stc = upload(h, &G.cz_g_lm, C.g_lm)) != SGB_OK ||
+              (stc = upload(h, &G.cz_p_ptr, C.p_ptr)) != SGB_OK || (stc = upload(h, &G.cz_p_e, C.p_e)) != SGB_OK ||
+              (stc = upload(h, &G.cz_p_w, C.p_w)) != SGB_OK || (stc = upload(h, &G.cz_rr, C.rr)) != SGB_OK ||
+              (stc = upload(h, &G.cz_t_ptr, C.t_ptr)) != SGB_OK || (stc = upload(h, &G.cz_t_g, C.t_g)) != SGB_OK ||
+              (stc = dalloc(h, &G.cz_G, 6 * (size_t)C.ng)) != SGB_OK ||
+              (stc = dalloc(h, &G.cz_A, (size_t)9 * C.nn * C.nn)) != SGB_OK || (stc = dalloc(h, &G.cz_fail, 1)) != SGB_OK)
+            return stc;
+        }
+      }
+      if (prof) std::fprintf(stderr, "[sgb_set_graph] resident solve, four lanes per row: %s (%d CTAs x %d threads, %d bytes), coarse space: %d nodes every %d rows\n",
+                             h->res4.valid ? "yes" : "no", h->res4.ncta, h->res4.bt, h->res4.bytes, h->res4.cz_nc / 3, h->res4.cz_h);
     }
     {  // the same question for one 256-thread CTA (sgb_optimize_batch: one graph per CTA)
       h->res_block = ResPlan();
-      ResPlan rp;
+      ResPlan rp = ResPlan();
       rp.valid = 0; rp.bt = kThreads; rp.ncta = 1;
       rp.cap_pp = cap_of(P.Hpp, kThreads / 32, 1); rp.cap_pl = cap_of(P.Hpl, kThreads / 32, 1);
       rp.cap_lp = (int)P.Hlp.entries();  // a single CTA keeps every landmark-major slice
@@ -1642,7 +1701,9 @@ sgb_status sgb_linear_solve(sgb_handle* h, const double* values, const double* b
   if (rel) *rel = h->h_sc->pcg_rel;
   if ((st = gather_owned_vector(h, h->G.x_p[h->LP.rank], h->G.x_l, x)) != SGB_OK) return st;
   if (h->h_sc->result != 1) {
-    h->err = "linear solve failed (matrix not positive definite)";  // LinearSolver::solve() == false
+    // LinearSolver::solve() == false: breakdown, or the iteration cap was hit with a residual above 1e-6 (pcg_usable)
+    h->err = h->h_sc->pcg_flag == 1 ? "linear solve failed (PCG hit its iteration cap without converging)"
+                                    : "linear solve failed (matrix not positive definite)";
     return SGB_ERR_SOLVE_FAILED;
   }
   return SGB_OK;
@@ -1884,7 +1945,7 @@ static sgb_status optimize_batch_impl(sgb_handle* const* hs, int32_t n, int32_t 
     items[i].g = hs[i]->G;
     items[i].sc = hs[i]->d_sc;
     const ResPlan& r = hs[i]->res_block;
-    items[i].res = ResPlanFwd{r.valid, r.bt, r.ncta, r.cap_pp, r.cap_pl, r.cap_lp, r.nz, r.nt, r.bytes, r.cap_sl, r.cap_lr, r.rows_cta};
+    items[i].res = ResPlanFwd{r.valid, r.bt, r.ncta, r.cap_pp, r.cap_pl, r.cap_lp, r.nz, r.nt, r.bytes, r.cap_sl, r.cap_lr, r.rows_cta, 0, 0};
     if (r.valid) smem_bytes = std::max(smem_bytes, r.bytes);
   }
   static_assert(sizeof(ResPlanFwd) == sizeof(ResPlan), "ResPlanFwd mirrors ResPlan");

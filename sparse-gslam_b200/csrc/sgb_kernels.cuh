@@ -844,7 +844,7 @@ __global__ void k_gn_control(DevGraph g, DevScalars* sc) {
 // and lambda control -- with block barriers where the single-graph path has kernel boundaries or grid barriers. The
 // per-row bodies (sgb_rows.h), the PCG (pcg_solve) and the LM control (lm_control_update) are the very same code.
 struct ResPlanFwd {  // = ResPlan of sgb_resident.cuh (declared here so that BatchItem can carry one)
-  int valid, bt, ncta, cap_pp, cap_pl, cap_lp, nz, nt, bytes, cap_sl, cap_lr, rows_cta;
+  int valid, bt, ncta, cap_pp, cap_pl, cap_lp, nz, nt, bytes, cap_sl, cap_lr, rows_cta, cz_nc, cz_h;
 };
 struct BatchItem {
   DevGraph g;

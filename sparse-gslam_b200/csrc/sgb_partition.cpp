@@ -585,6 +585,122 @@ static sgb_status partition_impl(const Structure& S, int world, int rank, LocalP
 }
 
 // where every block of the reference-order list lives: owner rank and, on the owner, the local entry
+int coarse_spacing(int nP, int max_nodes) {
+  if (nP < 24 || max_nodes < 3) return 0;  // a handful of rows: block-Jacobi alone converges in a few iterations
+  for (int h : {8, 16, 32, 64})
+    if ((nP + h - 1) / h + 1 <= max_nodes) return h;
+  return 0;
+}
+
+// Gather lists of the coarse matrix R S R^T (sgb_coarse.h) for hat functions with a node every h pose rows. Everything is
+// emitted in a fixed order (rows ascending, blocks of a row in storage order), so the device sums are reproducible.
+void plan_coarse(const LocalPlan& P, int h, CoarsePlan& C) {
+  C = CoarsePlan();
+  if (h <= 0 || P.world != 1 || P.nP <= 0) return;
+  const int nP = P.nP, nn = (nP + h - 1) / h + 1;
+  C.h = h;
+  C.nn = nn;
+  struct NodeW { int n[2]; double w[2]; int cnt; };
+  auto nodes_of = [&](int i) {
+    NodeW r;
+    const double wr = (double)(i % h) / (double)h;
+    r.n[0] = i / h; r.w[0] = 1.0 - wr; r.cnt = 1;
+    if (wr != 0.0) { r.n[1] = i / h + 1; r.w[1] = wr; r.cnt = 2; }
+    return r;
+  };
+  const int npair = nn * nn;
+  // ---- Hpp items and R R^T per node pair (m <= n): count, then fill
+  C.p_ptr.assign((size_t)npair + 1, 0);
+  C.rr.assign(npair, 0.0);
+  auto each_pp = [&](auto&& f) {
+    for (int i = 0; i < nP; ++i) {
+      const NodeW a = nodes_of(i);
+      const int w = P.Hpp.width(P.Hpp.slice_of(i));
+      for (int k = 0; k < w; ++k) {
+        const int e = P.Hpp.entry(i, k), enc = P.Hpp.col[e];
+        if (enc < 0) continue;
+        const NodeW b = nodes_of(enc & kLocalMask);
+        for (int x = 0; x < a.cnt; ++x)
+          for (int y = 0; y < b.cnt; ++y)
+            if (a.n[x] <= b.n[y]) f(a.n[x] * nn + b.n[y], e, a.w[x] * b.w[y]);
+      }
+    }
+  };
+  each_pp([&](int b, int, double) { C.p_ptr[b + 1]++; });
+  for (int b = 0; b < npair; ++b) C.p_ptr[b + 1] += C.p_ptr[b];
+  C.p_e.resize(C.p_ptr[npair]);
+  C.p_w.resize(C.p_ptr[npair]);
+  {
+    std::vector<int32_t> pos(C.p_ptr.begin(), C.p_ptr.end() - 1);
+    each_pp([&](int b, int e, double w) { C.p_e[pos[b]] = e; C.p_w[pos[b]++] = w; });
+  }
+  for (int i = 0; i < nP; ++i) {
+    const NodeW a = nodes_of(i);
+    for (int x = 0; x < a.cnt; ++x)
+      for (int y = 0; y < a.cnt; ++y)
+        if (a.n[x] <= a.n[y]) C.rr[a.n[x] * nn + a.n[y]] += a.w[x] * a.w[y];
+  }
+  // ---- G = R Hpl: its non-zero (landmark, node) pairs, ordered by landmark then node; the items of a pair in row order
+  const int nL = P.nL;
+  std::vector<int32_t> key_cnt((size_t)nL * nn + 1, 0);
+  auto each_pl = [&](auto&& f) {
+    for (int i = 0; i < nP; ++i) {
+      const NodeW a = nodes_of(i);
+      const int w = P.Hpl.rows > 0 ? P.Hpl.width(P.Hpl.slice_of(i)) : 0;
+      for (int k = 0; k < w; ++k) {
+        const int e = P.Hpl.entry(i, k), enc = P.Hpl.col[e];
+        if (enc < 0) continue;
+        const int l = enc & kLocalMask;
+        for (int x = 0; x < a.cnt; ++x) f(l * nn + a.n[x], e, a.w[x]);
+      }
+    }
+  };
+  each_pl([&](int key, int, double) { key_cnt[key + 1]++; });
+  std::vector<int32_t> g_of_key((size_t)nL * nn, -1);
+  C.g_ptr.assign(1, 0);
+  for (int key = 0; key < nL * nn; ++key)
+    if (key_cnt[key + 1] > 0) {
+      g_of_key[key] = (int)C.g_lm.size();
+      C.g_lm.push_back(key / nn);
+      C.g_ptr.push_back(C.g_ptr.back() + key_cnt[key + 1]);
+    }
+  C.ng = (int)C.g_lm.size();
+  C.g_e.resize(C.g_ptr.back());
+  C.g_w.resize(C.g_ptr.back());
+  {
+    std::vector<int32_t> pos(C.g_ptr.begin(), C.g_ptr.end() - 1);
+    each_pl([&](int key, int e, double w) { const int gi = g_of_key[key]; C.g_e[pos[gi]] = e; C.g_w[pos[gi]++] = w; });
+  }
+  // ---- Schur terms: the pairs of one landmark, (g1, g2) with node(g1) <= node(g2), grouped by node pair
+  C.t_ptr.assign((size_t)npair + 1, 0);
+  auto each_term = [&](auto&& f) {
+    int g0 = 0;
+    while (g0 < C.ng) {
+      int g1 = g0;
+      while (g1 < C.ng && C.g_lm[g1] == C.g_lm[g0]) ++g1;
+      const int l = C.g_lm[g0];
+      // the pairs of landmark l are g0 .. g1-1 in node order; node of pair gi = its key % nn: recover it from the keys
+      for (int a = g0; a < g1; ++a)
+        for (int b = a; b < g1; ++b) f(a, b, l);
+      g0 = g1;
+    }
+  };
+  std::vector<int32_t> g_node(C.ng, 0);
+  for (int key = 0; key < nL * nn; ++key)
+    if (g_of_key[key] >= 0) g_node[g_of_key[key]] = key % nn;
+  each_term([&](int a, int b, int) { C.t_ptr[g_node[a] * nn + g_node[b] + 1]++; });
+  for (int b = 0; b < npair; ++b) C.t_ptr[b + 1] += C.t_ptr[b];
+  C.t_g.resize(2 * (size_t)C.t_ptr[npair]);
+  {
+    std::vector<int32_t> pos(C.t_ptr.begin(), C.t_ptr.end() - 1);
+    each_term([&](int a, int b, int) {
+      const int q = pos[g_node[a] * nn + g_node[b]]++;
+      C.t_g[2 * (size_t)q] = a;
+      C.t_g[2 * (size_t)q + 1] = b;
+    });
+  }
+}
+
 void build_export(Structure& S, LocalPlan& P) {
   if (P.export_built) return;
   build_block_list(S);

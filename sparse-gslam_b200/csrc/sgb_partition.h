@@ -65,6 +65,18 @@ bool partition_ghost_landmarks();
 void partition_use_pushed_halos(bool on);
 bool partition_pushed_halos();
 
+// Coarse space of the two-level preconditioner (sgb_coarse.h): gather lists for R S R^T over the rows of ONE rank
+// (world == 1). nn = 0: not planned.
+struct CoarsePlan {
+  int h = 0, nn = 0, ng = 0;
+  std::vector<int32_t> g_ptr, g_e, g_lm, p_ptr, p_e, t_ptr, t_g;
+  std::vector<double> g_w, p_w, rr;
+};
+// node spacing for a graph of nP pose rows: the smallest of 8 / 16 / 32 / 64 that needs at most max_nodes nodes
+// (<= kCzMaxNodes, sgb_coarse.h); 0 = the graph is too long for a dense coarse solve (or too short to need one)
+int coarse_spacing(int nP, int max_nodes);
+void plan_coarse(const LocalPlan& P, int h, CoarsePlan& C);
+
 inline int enc_pose(int hp, int chunkP) { return ((hp / chunkP) << 26) | (hp % chunkP); }
 
 sgb_status partition(const Structure& S, int world, int rank, LocalPlan& out, std::string& err);

@@ -15,6 +15,7 @@
 // One thread owns one pose row, one warp one slice of the landmark-major matrix (the host sizes the cluster for that).
 // The arithmetic per row is that of sgb_rows.h (same expressions, same order of the blocks).
 #pragma once
+#include "sgb_coarse.h"
 #include "sgb_kernels.cuh"
 
 namespace sgb {
@@ -28,11 +29,12 @@ struct ResPlan {   // host-computed, the same for every CTA of the launch
   int bytes;       // dynamic shared memory per CTA
   int cap_sl, cap_lr;  // landmark-major slices / landmark rows of the largest per-CTA share
   int rows_cta;        // pose rows per CTA: bt (one thread per row) or bt / 4 (four lanes per row)
+  int cz_nc, cz_h;     // two-level preconditioner (sgb_coarse.h, four-lane solve only): coarse dimension (0 = off), node spacing
 };
 
 // byte offsets inside the dynamic shared memory (doubles first, then floats, then ints: natural alignment)
 struct ResOffsets {
-  size_t vpp, vpl, vlp, z, t, w, rvec, cinv, cpp, cpl, clp, meta, total;
+  size_t vpp, vpl, vlp, z, t, w, rvec, cinv, ainv, cpp, cpl, clp, meta, total;
 };
 __host__ __device__ inline ResOffsets res_offsets(const ResPlan& p) {
   ResOffsets o;
@@ -46,6 +48,7 @@ __host__ __device__ inline ResOffsets res_offsets(const ResPlan& p) {
   o.w = take((size_t)p.cap_lr * 3 * 8);
   o.rvec = take((size_t)p.rows_cta * 3 * 8);
   o.cinv = take((size_t)p.rows_cta * 9 * 16);
+  o.ainv = take((size_t)p.cz_nc * (size_t)cz_ld(p.cz_nc) * 8);   // the coarse inverse, odd leading dimension
   o.cpp = take((size_t)p.cap_pp * 4);
   o.cpl = take((size_t)p.cap_pl * 4);
   o.clp = take((size_t)p.cap_lp * 4);
@@ -367,10 +370,18 @@ __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgP
 // ~670 dependent instructions per warp and iteration at an IPC of 0.1 (ncu, profiles/r2_res1_stream_*) -- and every
 // product serial: here a pose-major row costs 3 instead of 9 multiply-adds per block and lane, the preconditioner 12
 // instead of 36, and a 256-row CTA runs 32 warps. rp.bt threads per CTA own rp.bt / 4 rows and rp.bt / 32 landmark slices.
-template <bool CL, int U>
+//
+// CZ = true adds the coarse term of the two-level preconditioner (sgb_coarse.h): z = blockJacobi^-1 r + R^T Ainv (R r).
+// The coarse residual rc = R r is kept, replicated, in every CTA and follows r through its own recurrence
+// rc -= alpha R s: the hat-weighted sums of s over a segment of h rows are formed by the warps that own the rows
+// (shuffles, then a fixed-order sum of the warp partials), stored into every CTA's copy through distributed shared
+// memory and published by the barrier that already carries delta = z.w -- no barrier is added across the cluster; the
+// dense nc x nc product Ainv rc is evaluated redundantly by every CTA from its own shared-memory copy of Ainv.
+// czs = [cqL | cqR | rc | yc] (kCzMaxDim doubles each) + warp partials [32 * 6], static shared memory of the kernel.
+template <bool CL, int U, bool CZ>
 __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const PcgParams& prm, const double lambda, const ResPlan& rp,
                                                     unsigned char* res_smem, double* sm, double* cl_part, unsigned long long* cbar,
-                                                    unsigned long long& seq, PcgOut& out) {
+                                                    double* czs, unsigned long long& seq, PcgOut& out) {
   namespace cg = cooperative_groups;
   const ResOffsets of = res_offsets(rp);
   double* vpp = reinterpret_cast<double*>(res_smem + of.vpp);
@@ -385,6 +396,12 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
   double* w_s = reinterpret_cast<double*>(res_smem + of.w);
   int32_t* meta_s = reinterpret_cast<int32_t*>(res_smem + of.meta);
   double* r_s = reinterpret_cast<double*>(res_smem + of.rvec);      // [3 * rows of the CTA]: residual, read by the chunk-mates
+  double* ainv_s = reinterpret_cast<double*>(res_smem + of.ainv);   // [nc][ld]: (R S R^T)^-1 of this trial
+  double* cqL = czs;                     // [3 * node]: sum of (left weight x s) over the segment to the node's right
+  double* cqR = czs + kCzMaxDim;         // [3 * node]: sum of (right weight x s) over the segment to the node's left
+  double* rc_s = czs + 2 * kCzMaxDim;    // coarse residual R r
+  double* yc_s = czs + 3 * kCzMaxDim;    // Ainv rc
+  double* cw_s = czs + 4 * kCzMaxDim;    // [warp][side][component] partial sums of one restriction
 
   const int bt = rp.bt, rows_cta = bt >> 2, ncta = CL ? (int)gridDim.x : 1, cta = CL ? (int)blockIdx.x : 0;
   const int spc_p = rows_cta >> 5;  // pose slices per CTA
@@ -443,6 +460,14 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
     }
   }
   const int lane = tid & 31, warp = tid >> 5;
+  // ---- coarse space: hat weights of this lane's row, the staged inverse, cleared exchange slots
+  const int cz_nc = CZ ? rp.cz_nc : 0, cz_h = CZ ? rp.cz_h : 8, cz_ldc = cz_ld(cz_nc), cz_nn = cz_nc / 3;
+  const double cz_r = (CZ && rowact) ? cz_wr(lp, cz_h) : 0.0, cz_l = (CZ && rowact) ? 1.0 - cz_r : 0.0;
+  const int cz_n0 = lp / cz_h;
+  if (CZ) {
+    for (int i = tid; i < cz_nc * cz_nc; i += bt) ainv_s[(i / cz_nc) * cz_ldc + (i % cz_nc)] = g.cz_A[i];
+    for (int i = tid; i < 4 * kCzMaxDim; i += bt) czs[i] = 0.0;
+  }
   unsigned cpar = 0;  // phase parity of this CTA's mbarrier
   auto sync_sum = [&](double* v, int nv) {
     if (CL) {
@@ -487,6 +512,57 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
     return rc * acc;
   };
 
+  // component c of row lp of a vector (0 on idle lanes) -> the hat-weighted sums over this CTA's segments, into every
+  // CTA's cqL / cqR. A warp holds 8 consecutive rows, all inside one segment (h and the CTA's first row are multiples of 8).
+  auto cz_restrict = [&](double v) {
+    double a = cz_l * v, b = cz_r * v;
+#pragma unroll
+    for (int off = 4; off < 32; off <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, off);
+      b += __shfl_xor_sync(0xffffffffu, b, off);
+    }
+    if (lane < 3) {
+      cw_s[warp * 6 + lane] = a;
+      cw_s[warp * 6 + 3 + lane] = b;
+    }
+    __syncthreads();
+    const int wps = cz_h >> 3, nseg = rows_cta / cz_h;
+    if (tid < 6 * nseg) {
+      const int sgm = tid / 6, side = (tid % 6) / 3, cc = tid % 3;
+      double acc = 0.0;
+      for (int w = sgm * wps; w < (sgm + 1) * wps; ++w) acc += cw_s[w * 6 + side * 3 + cc];
+      const int gs = cta * nseg + sgm;  // the segment between nodes gs and gs + 1
+      if (gs < cz_nn - 1) {
+        double* dst = (side == 0 ? cqL + 3 * gs : cqR + 3 * (gs + 1)) + cc;
+        if (CL) {
+          for (int rk = 0; rk < ncta; ++rk) res_st_dsmem(dst, (unsigned)rk, acc);
+        } else {
+          *dst = acc;
+        }
+      }
+    }
+  };
+  // rc = R r (init) or rc -= alpha R s, then yc = Ainv rc: every CTA for itself, thread t owns coarse component t
+  auto cz_update = [&](double alpha, bool init) {
+    for (int t = tid; t < cz_nc; t += bt) {
+      const double q = cqR[t] + cqL[t];
+      rc_s[t] = init ? q : rc_s[t] - alpha * q;
+    }
+    __syncthreads();
+    for (int t = tid; t < cz_nc; t += bt) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;  // nc is a multiple of 3
+      for (int j = 0; j < cz_nc; j += 3) {
+        a0 += ainv_s[j * cz_ldc + t] * rc_s[j];
+        a1 += ainv_s[(j + 1) * cz_ldc + t] * rc_s[j + 1];
+        a2 += ainv_s[(j + 2) * cz_ldc + t] * rc_s[j + 2];
+      }
+      yc_s[t] = (a0 + a1) + a2;
+    }
+    __syncthreads();
+  };
+  // the coarse part of z for this lane's component
+  auto cz_prolong = [&]() { return cz_l * yc_s[3 * cz_n0 + c] + cz_r * yc_s[3 * (cz_n0 + 1) + c]; };
+
   // ---- x = 0, r = bt, z = M^-1 r, d = s = 0 (one component per lane)
   double x = 0.0, r = 0.0, d = 0.0, s = 0.0, z = 0.0;
   if (act) r = g.bt[3 * (size_t)lp + c];
@@ -498,6 +574,16 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
   if (CL) {
     if (tid == 0) res_mbar_init(cbar, (unsigned)ncta);
     cg::this_cluster().sync();  // every CTA has started and initialised its mbarrier before anybody stores into it
+  }
+  if (CZ) {
+    cz_restrict(r);
+    sync_sum(nullptr, 0);  // every copy of cqL / cqR is complete
+    cz_update(0.0, true);
+    if (act) {
+      const double zc = cz_prolong();
+      z += zc;
+      acc += r * zc;
+    }
   }
   if (act) put_z(z);
   double gam = block_sum(acc, sm);
@@ -596,17 +682,24 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
         s = q + beta * s;
         acc = z * q;
       }
+      if (CZ) cz_restrict(s);  // R s rides the barrier of delta
       double del = block_sum(acc, sm);
       sync_sum(&del, 1);
       const double denom = it == 0 ? del : del - beta * gam / alpha_old;
       if (!(denom > 0.0)) { flag = 2; break; }
       const double alpha = gam / denom;
+      if (CZ) cz_update(alpha, false);
       // ---- phase C
       if (act) {
         x += alpha * d;
         r -= alpha * s;
       }
       acc = precond(r, &z);
+      if (CZ && act) {
+        const double zc = cz_prolong();
+        z += zc;
+        acc += r * zc;
+      }
       if (act) put_z(z);
       ++it;
       gam_old = gam;
@@ -628,6 +721,7 @@ __device__ void pcg_resident_block(const DevGraph& g, const PcgParams& prm, doub
   ResPlan rp;
   rp.valid = rpf.valid; rp.bt = rpf.bt; rp.ncta = rpf.ncta; rp.cap_pp = rpf.cap_pp; rp.cap_pl = rpf.cap_pl; rp.cap_lp = rpf.cap_lp;
   rp.nz = rpf.nz; rp.nt = rpf.nt; rp.bytes = rpf.bytes; rp.cap_sl = rpf.cap_sl; rp.cap_lr = rpf.cap_lr; rp.rows_cta = rpf.rows_cta;
+  rp.cz_nc = 0; rp.cz_h = 0;  // the batched solve keeps the plain block-Jacobi preconditioner
   pcg_resident_solve<false>(g, prm, lambda, rp, res_smem, sm, nullptr, s_last, seq, out);
 }
 
@@ -658,17 +752,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
 namespace sgb {
 #if defined(__CUDACC__)
 // Four lanes per row (pcg_resident_solve4): up to 1024 threads per CTA, a cluster of such CTAs or a single one.
-template <int MAXT, int U>  // MAXT = largest CTA (sets the register budget: 64 at 1024 threads, 128 at 512), U = blocks per step
+// MAXT = largest CTA (sets the register budget: 64 at 1024 threads, 128 at 512), U = blocks per step, CZ = with the coarse
+// term of the two-level preconditioner (a separate instantiation: the plain solve keeps its code and registers)
+template <int MAXT, int U, bool CZ>
 __global__ void __launch_bounds__(MAXT, 1) k_pcg_res4(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {
   extern __shared__ __align__(16) unsigned char res_smem[];
   __shared__ double sm[32];
   __shared__ double cl_part[32];
   __shared__ __align__(8) unsigned long long cbar;
+  __shared__ double czs[CZ ? 4 * kCzMaxDim + 32 * 6 : 1];
   unsigned long long seq = 0;
   const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   PcgOut out;
-  if (gridDim.x > 1) pcg_resident_solve4<true, U>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, seq, out);
-  else pcg_resident_solve4<false, U>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, seq, out);
+  if (gridDim.x > 1) pcg_resident_solve4<true, U, CZ>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, czs, seq, out);
+  else pcg_resident_solve4<false, U, CZ>(g, prm, lambda, rp, res_smem, sm, cl_part, &cbar, czs, seq, out);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc->rz0 = out.gam0;
     sc->rz = out.gam;
@@ -677,6 +774,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg_res4(DevGraph g, DevScalars* sc
     sc->pcg_rel = out.gam0 > 0.0 ? sqrt(fabs(out.gam) / out.gam0) : 0.0;
   }
   if (gridDim.x > 1) cooperative_groups::this_cluster().sync();
+}
+// Coarse matrix of the two-level preconditioner -> its inverse (sgb_coarse.h), once per LM trial after k_setup_lm: ONE CTA,
+// the matrix in (3 nn) x ld doubles of dynamic shared memory followed by 3 nn reciprocal pivots.
+__global__ void __launch_bounds__(1024, 1) k_setup_coarse(DevGraph g, DevScalars* sc, double lambda_override, int use_override) {
+  extern __shared__ __align__(16) unsigned char cz_smem[];
+  double* A = reinterpret_cast<double*>(cz_smem);
+  const int nc = 3 * g.cz_nn;
+  double* dinv = A + (size_t)nc * cz_ld(nc);
+  const double lambda = use_override ? lambda_override : sc->lambda;
+  coarse_factor(g, lambda, A, dinv, g.cz_A, g.cz_fail, (int)threadIdx.x, (int)blockDim.x, [] { __syncthreads(); });
 }
 // The same solve for a graph that fits ONE CTA (rows <= blockDim.x): block barriers only, no cluster.
 __global__ void __launch_bounds__(kThreads, 1) k_pcg_res1(DevGraph g, DevScalars* sc, PcgParams prm, ResPlan rp) {

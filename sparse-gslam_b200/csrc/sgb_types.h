@@ -129,6 +129,23 @@ struct DevGraph {
   double* r;                 // residual
   double* d;                 // search direction
   double* s;                 // S d
+  // ---- coarse space of the two-level preconditioner (sgb_coarse.h; single GPU, the resident four-lane solve only).
+  // cz_h = 0: off. Node n sits at pose row n * cz_h; gather lists built by the host (plan_coarse, sgb_partition.h):
+  int32_t cz_h, cz_nn;       // node spacing in pose rows (a multiple of 8), number of nodes (coarse dimension 3 * cz_nn)
+  int32_t cz_ng;             // (node, landmark) pairs with a non-zero G = R Hpl block
+  const int32_t* cz_g_ptr;   // [cz_ng + 1] CSR over the pairs: Hpl entries and hat weights that sum to the 3x2 block
+  const int32_t* cz_g_e;
+  const double* cz_g_w;
+  const int32_t* cz_g_lm;    // [cz_ng] local landmark row of the pair
+  const int32_t* cz_p_ptr;   // [cz_nn^2 + 1] CSR over node pairs (m * cz_nn + n, m <= n): Hpp entries and weight products
+  const int32_t* cz_p_e;
+  const double* cz_p_w;
+  const double* cz_rr;       // [cz_nn^2] (R R^T)(m, n): what lambda multiplies
+  const int32_t* cz_t_ptr;   // [cz_nn^2 + 1] CSR over node pairs: Schur terms (g1, g2) = two G pairs of one landmark
+  const int32_t* cz_t_g;     // [2 * terms]
+  double* cz_G;              // [6 * cz_ng] G values of the current linearisation
+  double* cz_A;              // [(3 cz_nn)^2] (R S R^T)^-1 of the current trial, row-major
+  int32_t* cz_fail;          // 1: the last factorisation met a non-positive pivot (coarse term switched off for that solve)
 };
 
 // scalars of the optimiser kept on the device (LM / GN control, reductions); identical on every rank

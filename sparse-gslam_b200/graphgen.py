@@ -73,6 +73,19 @@ class Graph:
     def n_pl(self):
         return int(self.pl_pose.shape[0])
 
+    def chain_prefix(self, n: int) -> "Graph":
+        """The landmark graph of the first n key-frames: poses < n, their odometry edges and line observations (what the
+        reference re-optimises after key-frame n, drone.cpp:146-156; loop closures live in the other graph)."""
+        import dataclasses
+        mpp = (self.pp_j - self.pp_i == 1) & (self.pp_j < n)
+        mpl = self.pl_pose < n
+        return dataclasses.replace(
+            self, name=f"{self.name}[:{n}]", pose_id=self.pose_id[:n], pose_est=self.pose_est[:n].copy(),
+            pose_fixed=self.pose_fixed[:n], pose_gt=self.pose_gt[:n], pp_i=self.pp_i[mpp], pp_j=self.pp_j[mpp],
+            pp_z=self.pp_z[mpp], pp_info=self.pp_info[mpp], pp_phi=self.pp_phi[mpp], pp_seq=self.pp_seq[mpp],
+            pl_pose=self.pl_pose[mpl], pl_lm=self.pl_lm[mpl], pl_z=self.pl_z[mpl], pl_info=self.pl_info[mpl],
+            pl_seq=self.pl_seq[mpl], meta=dict(self.meta))
+
     def pose_only(self, phi: float | None = None) -> "Graph":
         """Pose-graph view (what SubmapLoopCloser optimises with GN + DCS on closures)."""
         g = Graph(

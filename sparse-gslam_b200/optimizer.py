@@ -61,7 +61,7 @@ class SparseOptimizerB200:
     """One optimiser handle = one of the reference's two graphs (LandmarkGraph.opt / PoseGraph.opt, graphs.h:19-40)."""
 
     def __init__(self, algo=capi.ALGO_LM, jacobian_mode=capi.JAC_G2O_NUMERIC, pcg_tolerance=1e-10, pcg_max_iters=0,
-                 device=-1, lm_user_lambda=0.0, incremental=False):
+                 device=-1, lm_user_lambda=0.0, incremental=False, coarse_nodes=0):
         self.L = capi.load()
         if self.L.sgb_device_count() <= 0:
             raise SgbError(capi.ERR_NO_DEVICE, "no CUDA device: the backend has no CPU path")
@@ -73,6 +73,7 @@ class SparseOptimizerB200:
         opt.pcg_max_iters = pcg_max_iters
         opt.lm_user_lambda = lm_user_lambda
         opt.incremental = int(bool(incremental))
+        opt.coarse_nodes = int(coarse_nodes)   # two-level preconditioner of the resident solve: >0 on, <0 off, 0 default
         self.algo = algo
         self.h = C.c_void_p()
         st = self.L.sgb_create(C.byref(opt), C.byref(self.h))

@@ -77,13 +77,14 @@ class GpuBackend:
     """The product path: one sgb handle, estimates resident on the device between the calls of one key-frame.
     `prof` accumulates the wall time of every protocol call and the device-side counters of optimize()."""
 
-    def __init__(self, jacobian_mode=capi.JAC_G2O_NUMERIC, device=-1, incremental=True):
+    def __init__(self, jacobian_mode=capi.JAC_G2O_NUMERIC, device=-1, incremental=True, coarse_nodes=0):
         import os
         from .optimizer import SparseOptimizerB200
         if os.environ.get("SGB_SESSION_FULL") == "1":   # tuning runs: every key-frame re-initialises from host buffers
             incremental = False
         self.incremental = incremental
-        self.opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=jacobian_mode, device=device, incremental=incremental)
+        self.opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=jacobian_mode, device=device, incremental=incremental,
+                                       coarse_nodes=coarse_nodes)
         self.prof = dict(initialize_s=0.0, push_s=0.0, optimize_s=0.0, chi2_s=0.0, pop_discard_s=0.0, estimates_s=0.0,
                          device_ms=0.0, pcg_iters=0, trials=0, kernel_launches=0, calls=0)
 

@@ -21,7 +21,8 @@ def build():
     srcs = [os.path.join(HERE, "hostsim.cpp"), os.path.join(HERE, "hostsim_edits.cpp"),
             os.path.join(csrc, "sgb_structure.cpp"), os.path.join(csrc, "sgb_partition.cpp")]
     deps = srcs + [os.path.join(csrc, f) for f in
-                   ("sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h", "sgb_partition.h", "sgb_edits.h")]
+                   ("sgb_rows.h", "sgb_math.h", "sgb_types.h", "sgb_structure.h", "sgb_partition.h", "sgb_edits.h",
+                    "sgb_coarse.h")]
     def fresh():
         return os.path.exists(SO) and all(os.path.getmtime(d) <= os.path.getmtime(SO) for d in deps)
 
@@ -61,6 +62,8 @@ def lib():
         L.hs_time_symbolic.argtypes = [C.POINTER(capi.GraphSoA), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.hs_time_symbolic.restype = C.c_double
         L.hs_preconditioner.argtypes = [vp, C.c_double, vp]
+        L.hs_use_coarse.argtypes = [C.c_int]
+        L.hs_coarse.argtypes = [vp, vp, vp]
         L.hs_pg_append.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.hs_closure_chi2.argtypes = [vp, vp, vp, vp, vp, C.c_int, vp]
         L.hs_odom_information.argtypes = [vp, vp, C.c_int, C.c_double, C.c_double, C.c_double, vp, vp, vp]
@@ -74,6 +77,11 @@ def lib():
 def use_ghost_landmarks(on: bool):
     """Planner switch (sgb_partition.h): ghost copies of the landmark rows other ranks own. Process-global."""
     lib().hs_use_ghost_landmarks(int(bool(on)))
+
+
+def use_coarse(max_nodes: int):
+    """Two-level preconditioner of the resident solve (sgb_coarse.h): at most `max_nodes` coarse nodes, 0 = off."""
+    lib().hs_use_coarse(int(max_nodes))
 
 
 def use_filtered_structure(on: bool):
@@ -150,6 +158,16 @@ class HostSim:
         self.L.hs_partition_stats(self.h, _p(o))
         keys = ("nP", "nL", "n_pp", "n_pl", "n_pp_owned", "n_pl_owned", "halo_p", "halo_t", "nL_owned", "remote_cols", "nH")
         return [dict(zip(keys, map(int, row))) for row in o]
+
+    def coarse(self):
+        """(node spacing h, nodes, failed, inverse coarse matrix of the last solve or None): sgb_coarse.h"""
+        info = np.zeros(3, np.int32)
+        self.L.hs_coarse(self.h, _p(info), None)
+        if info[0] == 0:
+            return 0, 0, 0, None
+        out = np.zeros((3 * int(info[1]), 3 * int(info[1])))
+        self.L.hs_coarse(self.h, _p(info), _p(out))
+        return int(info[0]), int(info[1]), int(info[2]), out
 
     def preconditioner(self, lam, n_free_poses):
         """Rows of the inverse 12x12 Schur diagonal blocks as the kernels store them: [nP, 3, 12] float32 (rank 0)."""

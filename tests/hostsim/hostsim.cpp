@@ -19,12 +19,16 @@
 
 #include "../../include/sgb_capi.h"
 #include "../../sparse-gslam_b200/csrc/sgb_partition.h"
+#include "../../sparse-gslam_b200/csrc/sgb_coarse.h"
 #include "../../sparse-gslam_b200/csrc/sgb_rows.h"
 #include "../../sparse-gslam_b200/csrc/sgb_structure.h"
 
 using namespace sgb;
 
 struct Rank {
+  CoarsePlan CZ;
+  std::vector<double> cz_work, cz_dinv;  // the factorisation's scratch (shared memory on the device)
+  int cz_fail = 0;
   Structure Sr;  // this rank's own (filtered) structure when the rank-filtered symbolic phase is simulated
   LocalPlan P;
   DevGraph G;
@@ -59,6 +63,9 @@ static void mk_sell(Rank* r, Sell* out, const HostSell& s, int NC) {
 extern "C" {
 
 void hs_use_ghost_landmarks(int on) { partition_use_ghost_landmarks(on != 0); }
+static int g_coarse_nodes = 0;
+// two-level preconditioner (sgb_coarse.h): at most `max_nodes` coarse nodes, 0 = block-Jacobi only (world == 1)
+void hs_use_coarse(int max_nodes) { g_coarse_nodes = max_nodes; }
 static bool g_filtered = false;
 // every virtual rank builds its own rank-filtered structure (build_structure(..., world, rank)), as libsgb does on >1 GPUs
 void hs_use_filtered_structure(int on) { g_filtered = on != 0; }
@@ -133,6 +140,19 @@ hs_handle* hs_create(const sgb_graph_soa* g, int jac_numeric, double tol, int ma
     G.pushed = P.pushed ? 1 : 0;
     if (P.pushed) { G.send_ptr = r->I(P.send_ptr); G.send_dst = r->I(P.send_dst); }
     G.t[rk] = r->D(2 * (size_t)P.capL); G.b_l[rk] = r->D(2 * (size_t)P.capL); G.Hll_inv[rk] = r->D(3 * (size_t)P.capL);
+    if (h->world == 1 && g_coarse_nodes > 0) {
+      plan_coarse(P, coarse_spacing(P.nP, std::min(g_coarse_nodes, kCzMaxNodes)), r->CZ);
+      const CoarsePlan& C = r->CZ;
+      if (C.nn > 0) {
+        G.cz_h = C.h; G.cz_nn = C.nn; G.cz_ng = C.ng;
+        G.cz_g_ptr = C.g_ptr.data(); G.cz_g_e = C.g_e.data(); G.cz_g_w = C.g_w.data(); G.cz_g_lm = C.g_lm.data();
+        G.cz_p_ptr = C.p_ptr.data(); G.cz_p_e = C.p_e.data(); G.cz_p_w = C.p_w.data(); G.cz_rr = C.rr.data();
+        G.cz_t_ptr = C.t_ptr.data(); G.cz_t_g = C.t_g.data();
+        const int nc = 3 * C.nn;
+        G.cz_G = r->D(6 * (size_t)C.ng); G.cz_A = r->D((size_t)nc * nc); G.cz_fail = &r->cz_fail;
+        r->cz_work.assign((size_t)nc * cz_ld(nc), 0.0); r->cz_dinv.assign(nc, 0.0);
+      }
+    }
   }
   // "sgb_comm_connect": cross-link the peer tables
   for (int a = 0; a < h->world; ++a)
@@ -326,14 +346,52 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
   for (auto& r : h->R) for (int ll = 0; ll < r->G.nL; ++ll) ok &= setup_lm_row(r->G, ll, lambda);
   for (auto& r : h->R) for (int lp = 0; lp < r->G.nP; ++lp) ok &= setup_pose_row(r->G, lp, lambda);
   for (auto& r : h->R) for (int ch = 0; ch < (r->G.nP + kChunk - 1) / kChunk; ++ch) ok &= setup_chunk(r->G, ch, lambda);
+  // two-level preconditioner (world == 1): k_setup_coarse, then the coarse residual rc = R r follows r through the
+  // recurrence rc -= alpha R s, and every z gets R^T (R S R^T)^-1 rc on top of the block-Jacobi term
+  DevGraph& G0 = h->R[0]->G;
+  const bool cz = h->world == 1 && G0.cz_h > 0;
+  const int cz_nc = cz ? 3 * G0.cz_nn : 0;
+  std::vector<double> rc(cz_nc, 0.0), yc(cz_nc, 0.0), tmp(cz_nc, 0.0);
+  if (cz) coarse_factor(G0, lambda, h->R[0]->cz_work.data(), h->R[0]->cz_dinv.data(), G0.cz_A, G0.cz_fail, 0, 1, [] {});
+  auto cz_restrict = [&](const double* v, double* out) {
+    std::fill(out, out + cz_nc, 0.0);
+    for (int i = 0; i < G0.nP; ++i) {
+      const double wr = cz_wr(i, G0.cz_h), wl = 1.0 - wr;
+      const int n0 = i / G0.cz_h;
+      for (int c = 0; c < 3; ++c) {
+        out[3 * n0 + c] += wl * v[3 * (size_t)i + c];
+        out[3 * (n0 + 1) + c] += wr * v[3 * (size_t)i + c];
+      }
+    }
+  };
+  auto cz_solve = [&]() {
+    for (int t = 0; t < cz_nc; ++t) {
+      double a = 0.0;
+      for (int j = 0; j < cz_nc; ++j) a += G0.cz_A[(size_t)j * cz_nc + t] * rc[j];
+      yc[t] = a;
+    }
+  };
+  auto cz_add = [&](int i, const double* r3, double z[3]) {  // z += (R^T yc)_i, returns r_i . (R^T yc)_i
+    const double wr = cz_wr(i, G0.cz_h), wl = 1.0 - wr;
+    const int n0 = i / G0.cz_h;
+    double dot = 0.0;
+    for (int c = 0; c < 3; ++c) {
+      const double v = wl * yc[3 * n0 + c] + wr * yc[3 * (n0 + 1) + c];
+      z[c] += v;
+      dot += r3[c] * v;
+    }
+    return dot;
+  };
   double gam = 0;
   for (auto& rk : h->R) {
     DevGraph& G = rk->G;
     double* x = G.x_p[G.rank]; double* zin = G.p[G.rank];
     for (int i = 0; i < 3 * G.nP; ++i) { x[i] = 0; G.r[i] = G.bt[i]; G.d[i] = 0; G.s[i] = 0; }
+    if (cz) { cz_restrict(G.r, rc.data()); cz_solve(); }
     for (int lp = 0; lp < G.nP; ++lp) {  // the device exchanges the chunk's residuals with shuffles; here they are in G.r
       double z[3];
       gam += precond_row_from(G, lp, G.r, z);
+      if (cz) gam += cz_add(lp, G.r + 3 * (size_t)lp, z);
       for (int c = 0; c < 3; ++c) zin[3 * lp + c] = z[c];
       const double x0[3] = {0.0, 0.0, 0.0};
       if (G.pushed) push_halo_row(G, lp, z, x0);
@@ -367,9 +425,15 @@ static int solve(hs_handle* h, double lambda, int* iters, double* rel) {
           x[o] += alpha * G.d[o];
           G.r[o] = G.r[o] - alpha * G.s[o];
         }
+        if (cz) {
+          cz_restrict(G.s, tmp.data());
+          for (int t = 0; t < cz_nc; ++t) rc[t] -= alpha * tmp[t];
+          cz_solve();
+        }
         for (int lp = 0; lp < G.nP; ++lp) {
           double z[3];
           gnew += precond_row_from(G, lp, G.r, z);
+          if (cz) gnew += cz_add(lp, G.r + 3 * (size_t)lp, z);
           for (int c = 0; c < 3; ++c) zin[3 * (size_t)lp + c] = z[c];
           if (G.pushed) push_halo_row(G, lp, z, x + 3 * (size_t)lp);
         }
@@ -477,6 +541,14 @@ int hs_preconditioner(hs_handle* h, double lambda, float* out) {
   for (int lp = 0; lp < G.nP; ++lp)
     for (int idx = 0; idx < 9 * kChunk; ++idx) out[(size_t)lp * 9 * kChunk + idx] = G.Cinv[((size_t)(idx >> 2) * G.nP + lp) * 4 + (idx & 3)];
   return ok ? 0 : 1;
+}
+
+// coarse space of the two-level preconditioner (sgb_coarse.h) of rank 0: info[0] = node spacing h (0 = not planned),
+// info[1] = nodes, info[2] = 1 when the last factorisation failed; out (may be NULL) = (R S R^T)^-1 of the last solve, [3nn][3nn]
+void hs_coarse(hs_handle* h, int32_t* info, double* out) {
+  const Rank& r = *h->R[0];
+  info[0] = r.G.cz_h; info[1] = r.G.cz_nn; info[2] = r.cz_fail;
+  if (out && r.G.cz_h > 0) std::memcpy(out, r.G.cz_A, sizeof(double) * 9 * (size_t)r.G.cz_nn * r.G.cz_nn);
 }
 
 }  // extern "C"

@@ -1,5 +1,6 @@
 """Short runs of the hot path for compute-sanitizer (memcheck / racecheck): a few LM iterations of one workload through
-the C ABI. usage: python tools/sanitize_run.py <small|c1|c5s|stream> [iterations]"""
+the C ABI. usage: python tools/sanitize_run.py <small|c1|c5s|stream|coarse> [iterations]
+(coarse = 150 / 300 key-frames of C1 with the two-level preconditioner on: one CTA, then a cluster)"""
 import os
 import sys
 
@@ -17,6 +18,13 @@ if name == "stream":
     s = LandmarkGraphSession(GpuBackend(jacobian_mode=capi.JAC_ANALYTIC), iters=iters)
     s.run(frames)
     print("stream ok:", len(s.log), "key-frames, last chi2", s.log[-1].chi2)
+elif name == "coarse":
+    for n in (150, 300):
+        g = gg.make("c1").chain_prefix(n)
+        opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC, coarse_nodes=40)
+        assert opt.initialize_optimization(g)
+        k, st = opt.optimize(iters)
+        print("coarse", n, "ok: iterations", k, "chi2", st[-1]["chi2"], "pcg", [s["pcg_iters"] for s in st])
 else:
     g = gg.make_c5(rows=60, cols=60) if name == "c5s" else gg.make(name)
     opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
