@@ -27,3 +27,14 @@ for tool in racecheck memcheck; do
 done
 SGB_COARSE=1 timeout 240 python -m pytest tests -m gpu -x -q > $O/w_all_tests_coarse_on.log 2>&1
 echo "all gpu tests with SGB_COARSE=1 rc=$?" >> $O/w_all_tests_coarse_on.log; tail -4 $O/w_all_tests_coarse_on.log
+SGB_COARSE=1 timeout 100 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"k_setup_coarse|k_pcg_res4|k_setup_chunk" -c 900 --csv \
+  --log-file $O/w_launches_stream_coarse.csv python tools/sanitize_run.py stream 15 > $O/w_ncu_stream.log 2>&1
+echo "ncu rc=$?"; python - <<'PY'
+import csv, collections, io
+rows = [l for l in open("gpurun_out/r2/w_launches_stream_coarse.csv") if l.startswith('"')]
+agg = collections.defaultdict(list)
+for r in csv.DictReader(io.StringIO("".join(rows))):
+    try: agg[r["Kernel Name"][:40]].append(float(r["Metric Value"].replace(",", "")))
+    except Exception: pass
+for k, v in agg.items(): print("   %-40s n=%d mean %.1f us max %.1f us" % (k, len(v), sum(v) / len(v) / 1e3, max(v) / 1e3))
+PY
