@@ -115,7 +115,7 @@ typedef struct sgb_structure_info {
   int32_t scalar_dim;       /* 3*free poses + 2*free landmarks */
   int32_t n_active_pp;
   int32_t n_active_pl;
-  int32_t reserved;
+  int32_t coarse_nodes;     /* nodes of the two-level preconditioner's coarse space planned for this graph (0: block-Jacobi only) */
   int64_t block_values;     /* doubles in the concatenated block value array */
 } sgb_structure_info;
 

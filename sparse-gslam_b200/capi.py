@@ -67,7 +67,7 @@ class IterStat(C.Structure):
 class StructureInfo(C.Structure):
     _fields_ = [("n_free", C.c_int32), ("n_free_poses", C.c_int32), ("n_free_landmarks", C.c_int32),
                 ("n_blocks", C.c_int32), ("scalar_dim", C.c_int32), ("n_active_pp", C.c_int32),
-                ("n_active_pl", C.c_int32), ("reserved", C.c_int32), ("block_values", C.c_int64)]
+                ("n_active_pl", C.c_int32), ("coarse_nodes", C.c_int32), ("block_values", C.c_int64)]
 
 
 class Timings(C.Structure):

@@ -1178,12 +1178,13 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
         if (cz_h > 0) {
           const bool cz_attr = cudaFuncSetAttribute(k_setup_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                            (int)(((size_t)kCzMaxDim * cz_ld(kCzMaxDim) + kCzMaxDim) * sizeof(double))) == cudaSuccess;
-          with_cz = cz_attr && plan4(cz_h);
+          // a coarser space (fewer nodes, a smaller inverse) when the finest one does not fit next to the matrices
+          for (int hc = cz_h; hc <= 64 && cz_attr && !with_cz; hc *= 2) with_cz = plan4(hc);
           cudaGetLastError();
         }
         if (!with_cz) plan4(0);
         if (h->res4.valid && h->res4.cz_nc > 0) {  // gather lists of the coarse matrix, scratch and the inverse
-          plan_coarse(P, cz_h, h->cz);
+          plan_coarse(P, h->res4.cz_h, h->cz);
           const CoarsePlan& C = h->cz;
           sgb_status stc;
           G.cz_h = C.h; G.cz_nn = C.nn; G.cz_ng = C.ng;
@@ -1466,7 +1467,7 @@ sgb_status sgb_get_structure_info(const sgb_handle* h, sgb_structure_info* o) {
   o->scalar_dim = S.dim;
   o->n_active_pp = S.n_pp;
   o->n_active_pl = S.n_pl;
-  o->reserved = 0;
+  o->coarse_nodes = h->G.cz_h > 0 ? h->G.cz_nn : 0;
   o->block_values = S.block_values;
   return SGB_OK;
 }

@@ -200,7 +200,7 @@ class SparseOptimizerB200:
         info = capi.StructureInfo()
         self._check(self.L.sgb_get_structure_info(self.h, C.byref(info)))
         return dict(n_free=info.n_free, n_blocks=info.n_blocks, dim=info.scalar_dim, block_values=info.block_values,
-                    n_free_poses=info.n_free_poses, n_free_landmarks=info.n_free_landmarks)
+                    n_free_poses=info.n_free_poses, n_free_landmarks=info.n_free_landmarks, coarse_nodes=info.coarse_nodes)
 
     def linearize(self, hessian=True):
         """hessian=False skips the block export (a rank-filtered multi-GPU handle only holds its own share of the

@@ -189,7 +189,7 @@ const char* hs_error(hs_handle* h) { return h->err.c_str(); }
 void hs_info(hs_handle* h, sgb_structure_info* o) {
   const Structure& S = h->S;
   o->n_free = S.Pf + S.Lf; o->n_free_poses = S.Pf; o->n_free_landmarks = S.Lf; o->n_blocks = (int)S.blk_row.size();
-  o->scalar_dim = S.dim; o->n_active_pp = S.n_pp; o->n_active_pl = S.n_pl; o->reserved = 0; o->block_values = S.block_values;
+  o->scalar_dim = S.dim; o->n_active_pp = S.n_pp; o->n_active_pl = S.n_pl; o->coarse_nodes = h->R[0]->G.cz_h > 0 ? h->R[0]->G.cz_nn : 0; o->block_values = S.block_values;
 }
 void hs_structure(hs_handle* h, int32_t* kind, int32_t* index, int32_t* offset, int32_t* br, int32_t* bc, int32_t* bnr,
                   int32_t* bnc, int32_t* ph, int32_t* lh) {

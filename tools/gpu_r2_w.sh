@@ -19,7 +19,8 @@ PY
 run stream_coarse40 stream SGB_COARSE=1
 run stream_coarse24 stream SGB_COARSE=1 SGB_COARSE_NODES=24
 run stream_plain stream SGB_COARSE=0
-run c1_coarse c1 SGB_COARSE=1
+run c1_coarse c1 SGB_COARSE=1 SGB_PROFILE=1
+grep -m1 'four lanes' $O/w_c1_coarse.err
 run c1_plain c1 SGB_COARSE=0
 for tool in racecheck memcheck; do
   timeout 150 compute-sanitizer --tool $tool python tools/sanitize_run.py coarse 2 > $O/w_${tool}_coarse.log 2>&1
