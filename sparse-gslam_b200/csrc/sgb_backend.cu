@@ -322,7 +322,7 @@ sgb_status launch_pcg(sgb_handle* h, double lambda_override, int use_override) {
   static const bool no_res1 = std::getenv("SGB_NO_RESIDENT1") != nullptr;
   if (h->res4.valid && G.world == 1) {  // four lanes per pose row, everything on chip
     ResPlan rp = h->res4;
-    const bool cz = rp.cz_nc > 0;
+    const bool cz = rp.cz_nc > 0 && G.cz_h > 0 && G.cz_A != nullptr;
     if (rp.ncta == 1) {
       if (rp.bt <= 512) {
         if (cz) k_pcg_res4<512, 4, true><<<1, rp.bt, (size_t)rp.bytes, h->stream>>>(G, sc, prm, rp);
@@ -1060,7 +1060,12 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
     if (prof) std::fprintf(stderr, "[sgb_set_graph] pcg cluster %d (wanted %d CTAs)\n", h->pcg_cluster, want);
   }
   // a graph whose per-CTA share of the matrices fits the shared memory of a cluster: the cluster-resident solve
+  // (all three plans are reset HERE: a graph without free poses skips the planning below, and a plan left over from the
+  // previous graph of a recycled handle would launch the resident kernel with that graph's geometry)
   h->res = ResPlan();
+  h->res4 = ResPlan();
+  h->res_block = ResPlan();
+  h->cz = CoarsePlan();
   static const bool no_res = std::getenv("SGB_NO_RESIDENT") != nullptr;
   if (world == 1 && !no_res && !no_cluster && P.nP > 0) {
     static const bool np_ok = cudaFuncSetAttribute(k_pcg_res, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
