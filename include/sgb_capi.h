@@ -61,7 +61,8 @@ typedef struct sgb_options {
                              * and the raw edge values on the device); 0 (default): sgb_set_graph keeps nothing of the caller's */
   int32_t coarse_nodes;     /* two-level preconditioner of the resident solve (small graphs on one GPU; no reference
                              * counterpart, LinearSolverEigen factorises exactly): > 0 = at most this many coarse nodes
-                             * (<= 40), < 0 = off, 0 = the library default (environment SGB_COARSE / SGB_COARSE_NODES) */
+                             * (<= 40), < 0 = off, 0 = the library default: on with 40 nodes unless the environment says
+                             * SGB_COARSE=0 (off) or SGB_COARSE_NODES=n */
 } sgb_options;
 
 /* Host SoA graph. Edges reference vertices by ARRAY INDEX; ids only define g2o's vertex

@@ -1120,10 +1120,10 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
                                  cudaFuncSetAttribute(k_pcg_res4<512, 4, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
                                  cudaFuncSetAttribute(k_pcg_res4<1024, 2, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
       // Two-level preconditioner (sgb_coarse.h): planned first WITH the coarse inverse in every CTA's shared memory, then
-      // without it. sgb_options.coarse_nodes, else SGB_COARSE=1 (+ SGB_COARSE_NODES) in the environment, switch it on.
-      static const int cz_default = [] {
+      // without it. sgb_options.coarse_nodes, else the environment (SGB_COARSE=0: off, SGB_COARSE_NODES: cap), decide.
+      static const int cz_default = [] {  // on by default (validated on hardware in round 2); SGB_COARSE=0 switches it off
         const char* on = std::getenv("SGB_COARSE");
-        if (!on || std::atoi(on) == 0) return 0;
+        if (on && std::atoi(on) == 0) return 0;
         const char* e = std::getenv("SGB_COARSE_NODES");
         return e ? std::atoi(e) : kCzMaxNodes;
       }();
