@@ -19,12 +19,12 @@ if name == "stream":
     s.run(frames)
     print("stream ok:", len(s.log), "key-frames, last chi2", s.log[-1].chi2)
 elif name == "coarse":
-    for n in (150, 300):
+    for n in ([int(a) for a in sys.argv[3:]] or [150, 300]):   # 150 / 300: clusters of two CTAs; <= 100: one CTA
         g = gg.make("c1").chain_prefix(n)
         opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC, coarse_nodes=40)
         assert opt.initialize_optimization(g)
         k, st = opt.optimize(iters)
-        print("coarse", n, "ok: iterations", k, "chi2", st[-1]["chi2"], "pcg", [s["pcg_iters"] for s in st])
+        print("coarse", n, "nodes", opt.structure_info()["coarse_nodes"], "ok: iterations", k, "chi2", st[-1]["chi2"], "pcg", [s["pcg_iters"] for s in st])
 else:
     g = gg.make_c5(rows=60, cols=60) if name == "c5s" else gg.make(name)
     opt = SparseOptimizerB200(capi.ALGO_LM, jacobian_mode=capi.JAC_ANALYTIC)
