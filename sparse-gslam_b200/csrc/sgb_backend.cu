@@ -1219,6 +1219,16 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
       if (P.nP <= kThreads && rp.bytes <= 200 * 1024 &&
           cudaFuncSetAttribute(k_pcg_res1, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) == cudaSuccess) {
         rp.valid = 1;
+        // the batched kernel (k_lm_block) applies the two-level preconditioner too when the graph's coarse lists exist (they
+        // were planned with the four-lane solve above), a segment fits a warp and the inverse fits next to the matrices
+        static const bool no_cz_block = std::getenv("SGB_COARSE_BATCH") != nullptr && std::atoi(std::getenv("SGB_COARSE_BATCH")) == 0;
+        if (G.cz_h > 0 && G.cz_h <= 32 && !no_cz_block) {
+          ResPlan rc = rp;
+          rc.cz_h = G.cz_h;
+          rc.cz_nc = 3 * G.cz_nn;
+          rc.bytes = (int)res_offsets(rc).total;
+          if (rc.bytes <= 200 * 1024) rp = rc;
+        }
         h->res_block = rp;
       }
       cudaGetLastError();
@@ -1951,7 +1961,7 @@ static sgb_status optimize_batch_impl(sgb_handle* const* hs, int32_t n, int32_t 
     items[i].g = hs[i]->G;
     items[i].sc = hs[i]->d_sc;
     const ResPlan& r = hs[i]->res_block;
-    items[i].res = ResPlanFwd{r.valid, r.bt, r.ncta, r.cap_pp, r.cap_pl, r.cap_lp, r.nz, r.nt, r.bytes, r.cap_sl, r.cap_lr, r.rows_cta, 0, 0};
+    items[i].res = ResPlanFwd{r.valid, r.bt, r.ncta, r.cap_pp, r.cap_pl, r.cap_lp, r.nz, r.nt, r.bytes, r.cap_sl, r.cap_lr, r.rows_cta, r.cz_nc, r.cz_h};
     if (r.valid) smem_bytes = std::max(smem_bytes, r.bytes);
   }
   static_assert(sizeof(ResPlanFwd) == sizeof(ResPlan), "ResPlanFwd mirrors ResPlan");

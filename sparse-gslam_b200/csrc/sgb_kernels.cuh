@@ -19,6 +19,7 @@
 #include <float.h>
 
 #include "sgb_rows.h"
+#include "sgb_coarse.h"
 
 namespace sgb {
 
@@ -865,7 +866,9 @@ struct BatchResult {
 // free, the latency chain of a row is what counts), 2 otherwise (more resident CTAs per SM)
 // the CTA-resident solve of sgb_resident.cuh (defined there; this header is included first)
 __device__ void pcg_resident_block(const DevGraph& g, const PcgParams& prm, double lambda, const ResPlanFwd& rp,
-                                   unsigned char* res_smem, double* sm, int* s_last, unsigned long long& seq, PcgOut& out);
+                                   unsigned char* res_smem, double* sm, int* s_last, double* czs, unsigned long long& seq, PcgOut& out);
+// where the resident solve keeps the coarse inverse inside its shared memory (the factorisation's work array until then)
+__device__ double* pcg_resident_ainv(const ResPlanFwd& rp, unsigned char* res_smem);
 
 template <int U>
 __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, BatchParams prm, BatchResult* results) {
@@ -876,6 +879,7 @@ __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, B
   __shared__ double sm[32];
   __shared__ int s_last, s_ok;
   __shared__ unsigned long long ph_ns[4], t_ph;
+  __shared__ double czs[5 * kCzMaxDim];  // two-level preconditioner: [cqL | cqR | rc | yc | reciprocal pivots] (sgb_coarse.h)
   {  // this block's graph descriptor -> shared memory (word copy)
     const int* src = reinterpret_cast<const int*>(&items[blockIdx.x].g);
     int* dst = reinterpret_cast<int*>(&g);
@@ -932,7 +936,12 @@ __global__ void __launch_bounds__(kThreads) k_lm_block(const BatchItem* items, B
       PcgOut po;
       if (res.valid) {
         __syncthreads();  // Hll_inv, bt and the preconditioner rows written above are complete
-        pcg_resident_block(g, pcg, lambda, res, lm_block_smem, sm, &s_last, seq, po);
+        if (res.cz_nc > 0) {  // coarse matrix -> its inverse (global g.cz_A), worked on where the solve will stage it
+          coarse_factor(g, lambda, pcg_resident_ainv(res, lm_block_smem), czs + 4 * kCzMaxDim, g.cz_A, g.cz_fail, tid, nth,
+                        [] { __syncthreads(); });
+          __syncthreads();
+        }
+        pcg_resident_block(g, pcg, lambda, res, lm_block_smem, sm, &s_last, czs, seq, po);
         __syncthreads();  // x_p is complete
       } else {
         pcg_solve<U>(g, tid, nth, 1u, nullptr, nullptr, seq, pcg, lambda, sm, &s_last, ph_ns, &t_ph, po);

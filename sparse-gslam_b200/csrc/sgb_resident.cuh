@@ -135,10 +135,13 @@ __device__ __forceinline__ void stage_copy(T* dst, const T* src, int n) {
 // owns the whole graph (the batched kernel k_lm_block_res: one graph per CTA), the cluster barrier becomes a block
 // barrier and "every CTA's copy" is the CTA's own. rp.bt = blockDim.x threads, rp.bytes of dynamic shared memory at
 // `res_smem`. Same recurrences, scalars and exit flags as pcg_solve (sgb_kernels.cuh). x is written to g.x_p.
-template <bool CL>
+// CZ = true (single CTA only, node spacing <= 32 rows): the coarse term of the two-level preconditioner, as in
+// pcg_resident_solve4 below; czs = [cqL | cqR | rc | yc], kCzMaxDim doubles each, shared memory of the caller.
+template <bool CL, bool CZ>
 __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgParams& prm, const double lambda, const ResPlan& rp,
-                                                   unsigned char* res_smem, double* sm, double* cl_part, int* s_last,
+                                                   unsigned char* res_smem, double* sm, double* cl_part, int* s_last, double* czs,
                                                    unsigned long long& seq, PcgOut& out) {
+  static_assert(!(CL && CZ), "the coarse term of the one-lane solve is built for a single CTA");
   namespace cg = cooperative_groups;
   const ResOffsets of = res_offsets(rp);
   double* vpp = reinterpret_cast<double*>(res_smem + of.vpp);
@@ -183,6 +186,62 @@ __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgP
 #pragma unroll
     for (int q = 0; q < 9; ++q) cinv_s[q * bt + lr] = cg4[(size_t)q * g.nP + lp];
   }
+  // ---- coarse space (single CTA: row0 = 0, a segment of h <= 32 rows is h consecutive lanes of one warp)
+  double* ainv_s = reinterpret_cast<double*>(res_smem + of.ainv);
+  double* cqL = czs;
+  double* cqR = czs + kCzMaxDim;
+  double* rc_s = czs + 2 * kCzMaxDim;
+  double* yc_s = czs + 3 * kCzMaxDim;
+  const int cz_nc = CZ ? rp.cz_nc : 0, cz_h = CZ ? rp.cz_h : 8, cz_ldc = cz_ld(cz_nc), cz_nn = cz_nc / 3;
+  const double cz_r = (CZ && act) ? cz_wr(lp, cz_h) : 0.0, cz_l = (CZ && act) ? 1.0 - cz_r : 0.0;
+  const int cz_n0 = lp / cz_h;
+  if (CZ) {
+    for (int i = (int)threadIdx.x; i < cz_nc * cz_nc; i += bt) ainv_s[(i / cz_nc) * cz_ldc + (i % cz_nc)] = g.cz_A[i];
+    for (int i = (int)threadIdx.x; i < 4 * kCzMaxDim; i += bt) czs[i] = 0.0;
+  }
+  // hat-weighted sums of a row vector over the segments: shuffle trees over the h lanes of a segment, its first lane stores
+  auto cz_restrict = [&](const double* v) {
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      double a = cz_l * v[cc], b = cz_r * v[cc];
+      for (int off = 1; off < cz_h; off <<= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, off);
+        b += __shfl_xor_sync(0xffffffffu, b, off);
+      }
+      if ((lr & (cz_h - 1)) == 0 && cz_n0 < cz_nn - 1) {
+        cqL[3 * cz_n0 + cc] = a;
+        cqR[3 * (cz_n0 + 1) + cc] = b;
+      }
+    }
+    __syncthreads();
+  };
+  auto cz_update = [&](double alpha, bool init) {
+    for (int t = (int)threadIdx.x; t < cz_nc; t += bt) {
+      const double q = cqR[t] + cqL[t];
+      rc_s[t] = init ? q : rc_s[t] - alpha * q;
+    }
+    __syncthreads();
+    for (int t = (int)threadIdx.x; t < cz_nc; t += bt) {
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+      for (int j = 0; j < cz_nc; j += 3) {
+        a0 += ainv_s[j * cz_ldc + t] * rc_s[j];
+        a1 += ainv_s[(j + 1) * cz_ldc + t] * rc_s[j + 1];
+        a2 += ainv_s[(j + 2) * cz_ldc + t] * rc_s[j + 2];
+      }
+      yc_s[t] = (a0 + a1) + a2;
+    }
+    __syncthreads();
+  };
+  auto cz_add = [&](const double* rr, double* zz) {  // z += (R^T yc) of this row, returns r . (R^T yc)
+    double dot = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      const double zc = cz_l * yc_s[3 * cz_n0 + cc] + cz_r * yc_s[3 * (cz_n0 + 1) + cc];
+      zz[cc] += zc;
+      dot += rr[cc] * zc;
+    }
+    return dot;
+  };
   // ---- per-thread constants of the solve
   const int slice = lp >> 5, lane = lp & 31;
   int wpp = 0, bpp = 0, wpl = 0, bpl = 0;
@@ -254,6 +313,11 @@ __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgP
   __syncthreads();  // the staged arrays and cinv_s of the chunk-mates are complete
   double acc = precond_row_res(cinv_s, bt, lr, act, r, z);
   if (CL) cg::this_cluster().sync();  // nobody writes into another CTA's shared memory before that CTA has started
+  if (CZ) {
+    cz_restrict(r);
+    cz_update(0.0, true);
+    if (act) acc += cz_add(r, z);
+  }
   if (act) put_z(z);
   double gam = block_sum(acc, sm);
   sync_sum(&gam, 1);  // also: every copy of z is complete
@@ -336,11 +400,13 @@ __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgP
         s[0] = q0 + beta * s[0]; s[1] = q1 + beta * s[1]; s[2] = q2 + beta * s[2];
         acc = vi0 * q0 + vi1 * q1 + vi2 * q2;
       }
+      if (CZ) cz_restrict(s);
       double del = block_sum(acc, sm);
       sync_sum(&del, 1);
       const double denom = it == 0 ? del : del - beta * gam / alpha_old;
       if (!(denom > 0.0)) { flag = 2; break; }
       const double alpha = gam / denom;
+      if (CZ) cz_update(alpha, false);
       // ---- phase C: x += alpha d, r -= alpha s, z = M^-1 r, gamma = r.z; the new z goes into every CTA's copy
       if (act)
         for (int c = 0; c < 3; ++c) {
@@ -348,6 +414,7 @@ __device__ __forceinline__ void pcg_resident_solve(const DevGraph& g, const PcgP
           r[c] -= alpha * s[c];
         }
       acc = precond_row_res(cinv_s, bt, lr, act, r, z);
+      if (CZ && act) acc += cz_add(r, z);
       if (act) put_z(z);
       ++it;
       gam_old = gam;
@@ -715,14 +782,22 @@ __device__ __forceinline__ void pcg_resident_solve4(const DevGraph& g, const Pcg
   out.flag = flag;
 }
 
-// the batched kernel's entry (k_lm_block, sgb_kernels.cuh): one CTA owns the whole graph
-__device__ void pcg_resident_block(const DevGraph& g, const PcgParams& prm, double lambda, const ResPlanFwd& rpf,
-                                   unsigned char* res_smem, double* sm, int* s_last, unsigned long long& seq, PcgOut& out) {
+__device__ double* pcg_resident_ainv(const ResPlanFwd& rpf, unsigned char* res_smem) {
   ResPlan rp;
   rp.valid = rpf.valid; rp.bt = rpf.bt; rp.ncta = rpf.ncta; rp.cap_pp = rpf.cap_pp; rp.cap_pl = rpf.cap_pl; rp.cap_lp = rpf.cap_lp;
   rp.nz = rpf.nz; rp.nt = rpf.nt; rp.bytes = rpf.bytes; rp.cap_sl = rpf.cap_sl; rp.cap_lr = rpf.cap_lr; rp.rows_cta = rpf.rows_cta;
-  rp.cz_nc = 0; rp.cz_h = 0;  // the batched solve keeps the plain block-Jacobi preconditioner
-  pcg_resident_solve<false>(g, prm, lambda, rp, res_smem, sm, nullptr, s_last, seq, out);
+  rp.cz_nc = rpf.cz_nc; rp.cz_h = rpf.cz_h;
+  return reinterpret_cast<double*>(res_smem + res_offsets(rp).ainv);
+}
+// the batched kernel's entry (k_lm_block, sgb_kernels.cuh): one CTA owns the whole graph
+__device__ void pcg_resident_block(const DevGraph& g, const PcgParams& prm, double lambda, const ResPlanFwd& rpf,
+                                   unsigned char* res_smem, double* sm, int* s_last, double* czs, unsigned long long& seq, PcgOut& out) {
+  ResPlan rp;
+  rp.valid = rpf.valid; rp.bt = rpf.bt; rp.ncta = rpf.ncta; rp.cap_pp = rpf.cap_pp; rp.cap_pl = rpf.cap_pl; rp.cap_lp = rpf.cap_lp;
+  rp.nz = rpf.nz; rp.nt = rpf.nt; rp.bytes = rpf.bytes; rp.cap_sl = rpf.cap_sl; rp.cap_lr = rpf.cap_lr; rp.rows_cta = rpf.rows_cta;
+  rp.cz_nc = rpf.cz_nc; rp.cz_h = rpf.cz_h;
+  if (rp.cz_nc > 0) pcg_resident_solve<false, true>(g, prm, lambda, rp, res_smem, sm, nullptr, s_last, czs, seq, out);
+  else pcg_resident_solve<false, false>(g, prm, lambda, rp, res_smem, sm, nullptr, s_last, czs, seq, out);
 }
 
 // One damped system of one graph, launched as ONE cluster of rp.ncta CTAs of rp.bt threads with rp.bytes of dynamic
@@ -735,7 +810,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res(DevGraph g, DevScalars*
   unsigned long long seq = 0;  // counts the reductions of this launch (parity of the partial-sum slots)
   const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   PcgOut out;
-  pcg_resident_solve<true>(g, prm, lambda, rp, res_smem, sm, cl_part, &s_last, seq, out);
+  pcg_resident_solve<true, false>(g, prm, lambda, rp, res_smem, sm, cl_part, &s_last, nullptr, seq, out);
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     sc->rz0 = out.gam0;
     sc->rz = out.gam;
@@ -793,7 +868,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_pcg_res1(DevGraph g, DevScalars
   unsigned long long seq = 0;
   const double lambda = prm.use_override ? prm.lambda_override : sc->lambda;
   PcgOut out;
-  pcg_resident_solve<false>(g, prm, lambda, rp, res_smem, sm, nullptr, &s_last, seq, out);
+  pcg_resident_solve<false, false>(g, prm, lambda, rp, res_smem, sm, nullptr, &s_last, nullptr, seq, out);
   if (threadIdx.x == 0) {
     sc->rz0 = out.gam0;
     sc->rz = out.gam;
