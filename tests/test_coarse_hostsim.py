@@ -123,3 +123,53 @@ def test_spacing_rule_and_switch_off():
     assert hostsim.HostSim(gg.make("c2"), jac_numeric=False).coarse()[0] == 0   # 5488 poses
     hostsim.use_coarse(0)
     assert hostsim.HostSim(chain_prefix(c1, 200), jac_numeric=False).coarse()[0] == 0
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_two_level_solve_on_collision_fuzz(seed):
+    """The coarse space is defined over the ROW ORDER of the reduced system, whatever the graph: on random graphs with
+    shuffled ids (the rows are then no chain at all), duplicate and reversed edges, fixed and inactive vertices and DCS
+    edges the two-level operator is still symmetric positive definite and the solve still returns the oracle's step."""
+    from test_structure_hostsim import _random_graph
+    g = _random_graph(np.random.default_rng(5000 + seed), p_range=(40, 130))
+    o = Oracle(g)
+    if not o.initialize_optimization():
+        return
+    hostsim.use_coarse(40)
+    hs = hostsim.HostSim(g, jac_numeric=False, tol=1e-12)
+    assert hs.status == capi.OK, hs.error
+    lam = 10.0
+    ok, xo = o.solve_once(lam, JAC_ANALYTIC)
+    f, xh, it, rel = hs.solve_once(lam)
+    h, nn, failed, Ainv = hs.coarse()
+    n_free_poses = int((hs.structure()["kind"] == 0).sum())
+    assert (h > 0) == (n_free_poses >= 24) and not failed
+    assert ok and f == 0, (ok, f)
+    assert np.abs(xh - xo).max() <= 1e-8 * max(1e-3, np.abs(xo).max())
+    if h:
+        assert np.linalg.eigvalsh(Ainv).min() > 0
+
+
+def test_two_level_gauss_newton_on_a_pose_graph():
+    """lambda = 0 and no landmarks at all (the reference's pose graph: GN + DCS closures, submap_loop_closer.cpp:286-288):
+    the coarse matrix is R Hpp R^T alone, no G lists, and the loop closures put blocks far off the chain's diagonal."""
+    from oracle.cpu_oracle import ALGO_GN
+    g = gg.make("c1").pose_only(phi=1.0)
+    keep = (g.pp_i < 300) & (g.pp_j < 300)
+    import dataclasses
+    g = dataclasses.replace(g, pose_id=g.pose_id[:300], pose_est=g.pose_est[:300].copy(), pose_fixed=g.pose_fixed[:300],
+                            pose_gt=g.pose_gt[:300], pp_i=g.pp_i[keep], pp_j=g.pp_j[keep], pp_z=g.pp_z[keep],
+                            pp_info=g.pp_info[keep], pp_phi=g.pp_phi[keep], pp_seq=g.pp_seq[keep])
+    o = Oracle(g)
+    assert o.initialize_optimization()
+    assert o.optimize(6, ALGO_GN)[0] == 6
+    its = {}
+    for nodes in (0, 40):
+        hostsim.use_coarse(nodes)
+        hs = hostsim.HostSim(g, tol=1e-12)
+        n, stats = hs.optimize(6, capi.ALGO_GN)
+        assert n == 6
+        np.testing.assert_allclose(hs.estimates()[0], o.estimates()[0], atol=1e-8)
+        its[nodes] = sum(s["pcg_iters"] for s in stats)
+        assert (hs.coarse()[0] > 0) == (nodes > 0)
+    assert its[40] < its[0], its

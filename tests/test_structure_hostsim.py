@@ -277,10 +277,10 @@ def test_preconditioner_blocks_are_the_inverse_schur_diagonal_blocks(lam):
             assert np.all(C[p][:, 3 * (c1 - c0):] == 0)  # no coupling to the poses missing from a partial chunk
 
 
-def _random_graph(rng):
+def _random_graph(rng, p_range=(2, 40)):
     """Small random graph with the collisions the structure builder has to get right: duplicate and reversed edges,
     several fixed poses, fixed landmarks, unobserved (inactive) vertices, shuffled ids, shuffled insertion ranks."""
-    P, L = int(rng.integers(2, 40)), int(rng.integers(0, 9))
+    P, L = int(rng.integers(*p_range)), int(rng.integers(0, 9))
     gt = np.cumsum(rng.normal(size=(P, 3)) * [0.5, 0.2, 0.2], axis=0)
     lines = np.stack([rng.uniform(0.5, 6.0, L), rng.uniform(-np.pi, np.pi, L)], 1) if L else np.zeros((0, 2))
     n_pp = int(rng.integers(1, 3 * P))
