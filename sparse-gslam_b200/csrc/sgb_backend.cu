@@ -1190,6 +1190,14 @@ static sgb_status set_graph_impl(sgb_handle* h, const sgb_graph_soa* g_in, int w
         if (!with_cz) plan4(0);
         if (h->res4.valid && h->res4.cz_nc > 0) {  // gather lists of the coarse matrix, scratch and the inverse
           plan_coarse(P, h->res4.cz_h, h->cz);
+          // a landmark reached from k nodes contributes k (k + 1) / 2 Schur terms: a graph whose every landmark is seen from
+          // every part of the trajectory would need lists out of proportion to its size -- it keeps the plain preconditioner
+          if (h->cz.t_g.size() / 2 > ((size_t)4 << 20)) {
+            h->cz = CoarsePlan();
+            plan4(0);
+          }
+        }
+        if (h->res4.valid && h->res4.cz_nc > 0 && h->cz.nn > 0) {
           const CoarsePlan& C = h->cz;
           sgb_status stc;
           G.cz_h = C.h; G.cz_nn = C.nn; G.cz_ng = C.ng;
