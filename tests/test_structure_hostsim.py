@@ -445,3 +445,27 @@ def test_ghost_landmarks_fuzz(seed, ghost_landmarks):
     assert one.optimize(3, capi.ALGO_LM)[0] == many.optimize(3, capi.ALGO_LM)[0]
     np.testing.assert_allclose(many.estimates(2)[0], one.estimates()[0], atol=1e-8)
     np.testing.assert_allclose(many.estimates(1)[1], one.estimates()[1], atol=1e-8)
+
+
+def test_ctypes_mirrors_have_the_layout_of_the_c_structs(tmp_path):
+    """The Python host side talks to libsgb.so through ctypes mirrors of the structs of include/sgb_capi.h: a C program
+    compiled against the header prints sizeof and the offset of the last member of each, which must be what ctypes lays
+    out (a member added on one side only would shift everything behind it silently)."""
+    import subprocess
+    pairs = [("sgb_options", capi.Options), ("sgb_graph_soa", capi.GraphSoA), ("sgb_graph_delta", capi.GraphDelta),
+             ("sgb_iter_stat", capi.IterStat), ("sgb_structure_info", capi.StructureInfo), ("sgb_timings", capi.Timings),
+             ("sgb_partition_info", capi.PartitionInfo), ("sgb_block_matrix", capi.BlockMatrix),
+             ("sgb_device_values", capi.DeviceValues), ("sgb_pg_info", capi.PgInfo)]
+    lines = []
+    for cname, cls in pairs:   # the mirrors use the header's member names: offsetof of a misnamed member does not compile
+        last = cls._fields_[-1][0]
+        lines.append('printf("%s %%zu %%zu\\n", sizeof(%s), offsetof(%s, %s));' % (cname, cname, cname, last))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "sgb_capi.h"\nint main(void) {\n' + "\n".join(lines) + "\nreturn 0; }\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(os.path.dirname(capi.HERE), "include"), "-o", str(exe), str(src)])
+    out = subprocess.check_output([str(exe)], text=True).split("\n")
+    for (cname, cls), ln in zip(pairs, out):
+        name, size, off = ln.split()
+        last = cls._fields_[-1][0]
+        assert name == cname and int(size) == C.sizeof(cls) and int(off) == getattr(cls, last).offset, (ln, C.sizeof(cls))
